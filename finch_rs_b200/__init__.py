@@ -1,0 +1,520 @@
+"""finch_rs_b200 -- host-side mirror (Python) of the finch-rs sketching surface over the C ABI
+of ``libfinch_b200.so`` (hand-written sm_100a CUDA; see include/finch_b200.h).
+
+The names and argument meanings follow the reference (paths relative to the reference root):
+
+  ``SketchParams.mash / .scaled`` + ``create_sketcher``   lib/src/sketch_schemes/mod.rs:53-113
+  ``MashSketcher`` / ``ScaledSketcher``                    lib/src/sketch_schemes/mash.rs, scaled.rs
+     ``.push(kmer, extra_count)``, ``.process(seq)``, ``.total_bases_and_kmers()``, ``.to_vec()``
+  ``FilterParams`` (+ ``filter_counts``)                   lib/src/filtering.rs:11-87
+  ``sketch_stream`` / ``sketch_files``                     lib/src/lib.rs:29-94
+  ``raw_distance`` / ``distance``                          lib/src/distance.rs:9-126
+
+Every compute call goes to the GPU through the C ABI.  There is no CPU fallback: importing works
+anywhere, but creating a sketcher without the built library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfinch_b200.so")
+
+OK = 0
+EINVAL, ECUDA, EFORMAT, ERECORD, EEMPTY, ETOOFEW, EUNSUPPORTED, EIO, ENOMEM = range(-1, -10, -1)
+KIND_MASH, KIND_SCALED = 0, 1
+FORMAT_UNKNOWN, FORMAT_FASTA, FORMAT_FASTQ = 0, 1, 2
+
+
+class FinchError(RuntimeError):
+    """FinchError::Message (lib/src/errors.rs:5-23) carrying the C-ABI status code."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.message = msg
+
+
+class _Params(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("kmers_to_sketch", C.c_uint64), ("final_size", C.c_uint64),
+                ("no_strict", C.c_int32), ("kmer_length", C.c_uint8), ("hash_seed", C.c_uint64),
+                ("scale", C.c_double), ("device", C.c_int32), ("stream", C.c_void_p)]
+
+
+class _Filter(C.Structure):
+    _fields_ = [("filter_on", C.c_int32), ("has_abun_low", C.c_int32), ("abun_low", C.c_uint32),
+                ("has_abun_high", C.c_int32), ("abun_high", C.c_uint32),
+                ("err_filter", C.c_double), ("strand_filter", C.c_double)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("hashes", C.POINTER(C.c_uint64)), ("counts", C.POINTER(C.c_uint32)),
+                ("extras", C.POINTER(C.c_uint32)), ("kmers", C.POINTER(C.c_uint8)),
+                ("kmer_stride", C.c_uint32), ("seq_length", C.c_uint64),
+                ("num_valid_kmers", C.c_uint64), ("format", C.c_int32), ("filters", _Filter)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("chunks", C.c_uint64), ("prunes", C.c_uint64), ("hash_launches", C.c_uint64),
+                ("hash_kernel_ms", C.c_double), ("parse_kernel_ms", C.c_double),
+                ("hash_symbols", C.c_uint64)]
+
+
+class _PairOut(C.Structure):
+    _fields_ = [("common", C.c_uint32), ("i", C.c_uint32), ("j", C.c_uint32)]
+
+
+EXPORTS = [
+    "fb2_sketcher_create", "fb2_sketcher_destroy", "fb2_sketcher_reset", "fb2_sketcher_process",
+    "fb2_sketcher_push", "fb2_sketcher_feed_fastx", "fb2_sketcher_feed_device", "fb2_sketcher_format",
+    "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_result_free", "fb2_sketcher_stats",
+    "fb2_sketcher_enable_timing", "fb2_filter_counts", "fb2_process_post_filter",
+    "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_dist_batch",
+    "fb2_dist_all_pairs", "fb2_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
+    "fb2_synth_genome", "fb2_synth_fasta", "fb2_synth_fastq",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libfinch_b200.so (built by __graft_entry__.build() / make -C finch_rs_b200/csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FinchError(ECUDA, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                                f"g.build()'` -- finch_rs_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.fb2_sketcher_create.argtypes = [C.POINTER(_Params), C.POINTER(vp)]
+    L.fb2_sketcher_destroy.argtypes = [vp]
+    L.fb2_sketcher_destroy.restype = None
+    L.fb2_sketcher_reset.argtypes = [vp]
+    L.fb2_sketcher_process.argtypes = [vp, vp, sz]
+    L.fb2_sketcher_push.argtypes = [vp, C.c_char_p, sz, C.c_uint8]
+    L.fb2_sketcher_feed_fastx.argtypes = [vp, vp, sz, C.c_int]
+    L.fb2_sketcher_feed_device.argtypes = [vp, vp, sz, C.c_int]
+    L.fb2_sketcher_format.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.fb2_sketcher_totals.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.fb2_sketcher_result.argtypes = [vp, C.POINTER(_Result)]
+    L.fb2_result_free.argtypes = [C.POINTER(_Result)]
+    L.fb2_result_free.restype = None
+    L.fb2_sketcher_stats.argtypes = [vp, C.POINTER(_Stats)]
+    L.fb2_sketcher_enable_timing.argtypes = [vp, C.c_int]
+    L.fb2_filter_counts.argtypes = [C.POINTER(_Result), C.POINTER(_Filter)]
+    L.fb2_process_post_filter.argtypes = [C.POINTER(_Result), C.POINTER(_Params), C.c_char_p]
+    L.fb2_guess_filter_threshold.argtypes = [vp, sz, C.c_double]
+    L.fb2_guess_filter_threshold.restype = C.c_uint32
+    L.fb2_sketch_stream.argtypes = [vp, sz, C.c_char_p, C.POINTER(_Params), C.POINTER(_Filter), C.POINTER(_Result)]
+    L.fb2_sketch_files.argtypes = [C.POINTER(C.c_char_p), sz, C.POINTER(_Params), C.POINTER(_Filter), C.POINTER(_Result)]
+    L.fb2_dist_batch.argtypes = [vp, vp, sz, sz, C.c_double, vp, vp, sz, vp, C.c_int32]
+    L.fb2_dist_all_pairs.argtypes = [vp, vp, sz, sz, C.c_double, sz, sz, vp, C.c_int32]
+    L.fb2_distance_finish.argtypes = [C.POINTER(_PairOut), C.c_uint8, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.fb2_distance_finish.restype = None
+    L.fb2_last_error.restype = C.c_char_p
+    L.fb2_version.restype = C.c_char_p
+    L.fb2_synth_genome.argtypes = [vp, sz, C.c_uint64]
+    L.fb2_synth_genome.restype = sz
+    L.fb2_synth_fasta.argtypes = [vp, sz, sz, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_uint64]
+    L.fb2_synth_fasta.restype = sz
+    L.fb2_synth_fastq.argtypes = [vp, sz, vp, sz, C.c_uint64, C.c_uint32, C.c_double, C.c_uint64, C.c_uint64,
+                                  C.POINTER(C.c_uint64)]
+    L.fb2_synth_fastq.restype = sz
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise FinchError(rc, lib().fb2_last_error().decode("utf-8", "replace"))
+
+
+def _addr(b):
+    """bytes-like / numpy uint8 -> (address, nbytes, keepalive)"""
+    if isinstance(b, np.ndarray):
+        a = np.ascontiguousarray(b).view(np.uint8).reshape(-1)
+        return a.ctypes.data, a.size, a
+    if isinstance(b, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(b, dtype=np.uint8)
+        return (a.ctypes.data if a.size else None), a.size, a
+    raise TypeError(f"unsupported buffer type {type(b)}")
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class KmerCount:
+    """lib/src/sketch_schemes/mod.rs:15-22"""
+    hash: int
+    kmer: bytes
+    count: int
+    extra_count: int
+    label: Optional[bytes] = None
+
+
+@dataclass
+class FilterParams:
+    """lib/src/filtering.rs:11-16.  err_filter is the internal value (CLI percent * k / 100)."""
+    filter_on: Optional[bool] = False
+    abun_filter: Tuple[Optional[int], Optional[int]] = (None, None)
+    err_filter: float = 0.0
+    strand_filter: float = 0.0
+
+    def _c(self):
+        lo, hi = self.abun_filter
+        return _Filter(-1 if self.filter_on is None else int(bool(self.filter_on)),
+                       lo is not None, lo or 0, hi is not None, hi or 0, self.err_filter, self.strand_filter)
+
+    @staticmethod
+    def _from_c(f):
+        return FilterParams(None if f.filter_on < 0 else bool(f.filter_on),
+                            (f.abun_low if f.has_abun_low else None, f.abun_high if f.has_abun_high else None),
+                            f.err_filter, f.strand_filter)
+
+
+@dataclass
+class SketchParams:
+    """enum SketchParams (mod.rs:53-71) restricted to the GPU path's variants."""
+    kind: int = KIND_MASH
+    kmers_to_sketch: int = 1000
+    final_size: int = 1000
+    no_strict: bool = False
+    kmer_length: int = 21
+    hash_seed: int = 0
+    scale: float = 0.0
+    device: int = -1
+
+    @staticmethod
+    def mash(kmers_to_sketch=1000, final_size=1000, no_strict=False, kmer_length=21, hash_seed=0, device=-1):
+        return SketchParams(KIND_MASH, kmers_to_sketch, final_size, no_strict, kmer_length, hash_seed, 0.0, device)
+
+    @staticmethod
+    def scaled(kmers_to_sketch=1000, kmer_length=21, scale=0.001, hash_seed=0, device=-1):
+        return SketchParams(KIND_SCALED, kmers_to_sketch, 0, False, kmer_length, hash_seed, scale, device)
+
+    @staticmethod
+    def from_cli(sketch_type="mash", n_hashes=1000, kmer_length=21, seed=0, oversketch=200, scale=0.001,
+                 no_strict=False, filters_enabled: Optional[bool] = None, device=-1):
+        """parse_sketch_options (cli/src/cli.rs:277-340): Mash over-sketches n*200 unless --no-filter."""
+        if sketch_type == "mash":
+            size = n_hashes * oversketch if filters_enabled in (True, None) else n_hashes
+            return SketchParams.mash(size, n_hashes, no_strict, kmer_length, seed, device)
+        if sketch_type == "scaled":
+            return SketchParams.scaled(n_hashes, kmer_length, scale, seed, device)
+        raise FinchError(EINVAL, "A unknown sketch type was selected")
+
+    def k(self):
+        return self.kmer_length
+
+    def expected_size(self):  # mod.rs:148-156
+        return self.final_size if self.kind == KIND_MASH else self.kmers_to_sketch
+
+    def _c(self, stream=None):
+        return _Params(self.kind, self.kmers_to_sketch, self.final_size, int(self.no_strict), self.kmer_length,
+                       self.hash_seed, self.scale, self.device, stream)
+
+    def create_sketcher(self, stream=None):
+        """mod.rs:86-113"""
+        return _Sketcher(self, stream)
+
+
+def _result_to_py(r, k):
+    n, st = int(r.n), int(r.kmer_stride)
+    if n:
+        h = np.ctypeslib.as_array(r.hashes, (n,)).copy()
+        c = np.ctypeslib.as_array(r.counts, (n,)).copy()
+        x = np.ctypeslib.as_array(r.extras, (n,)).copy()
+        km = np.ctypeslib.as_array(r.kmers, (n * st,)).copy().reshape(n, st)
+    else:
+        h, c, x = np.zeros(0, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+        km = np.zeros((0, max(st, 1)), np.uint8)
+    return h, c, x, km
+
+
+@dataclass
+class Sketch:
+    """lib/src/serialization/mod.rs:45-55 (SoA arrays + a KmerCount view)."""
+    name: str
+    seq_length: int
+    num_valid_kmers: int
+    comment: str
+    hashes_u64: np.ndarray
+    counts: np.ndarray
+    extra_counts: np.ndarray
+    kmers: np.ndarray            # [n, stride] uint8
+    filter_params: FilterParams
+    sketch_params: SketchParams
+    format: int = FORMAT_UNKNOWN
+
+    def __len__(self):
+        return len(self.hashes_u64)
+
+    def kmer_bytes(self, i, k=None):
+        return self.kmers[i, :(k or self.sketch_params.kmer_length)].tobytes()
+
+    @property
+    def hashes(self) -> List[KmerCount]:
+        k = self.sketch_params.kmer_length
+        return [KmerCount(int(self.hashes_u64[i]), self.kmers[i, :k].tobytes(), int(self.counts[i]),
+                          int(self.extra_counts[i])) for i in range(len(self))]
+
+
+class _Sketcher:
+    """A GPU-resident MashSketcher / ScaledSketcher (trait SketchScheme, mod.rs:24-51)."""
+
+    def __init__(self, params: SketchParams, stream=None):
+        self.params = params
+        self._h = C.c_void_p()
+        cp = params._c(stream)
+        _check(lib().fb2_sketcher_create(C.byref(cp), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().fb2_sketcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def reset(self):
+        _check(lib().fb2_sketcher_reset(self._h))
+
+    # -- SketchScheme ---------------------------------------------------------------------
+    def process(self, seq):
+        """process(&mut self, seq: &dyn Sequence): one record's raw sequence bytes."""
+        addr, n, keep = _addr(seq)
+        _check(lib().fb2_sketcher_process(self._h, addr, n))
+
+    def push(self, kmer: bytes, extra_count: int):
+        """MashSketcher::push / ScaledSketcher::push (mash.rs:34, scaled.rs:37)."""
+        _check(lib().fb2_sketcher_push(self._h, bytes(kmer), len(kmer), extra_count))
+
+    def total_bases_and_kmers(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(lib().fb2_sketcher_totals(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def parameters(self):
+        return self.params
+
+    def to_arrays(self):
+        """(hashes u64[n], counts u32[n], extras u32[n], kmers u8[n, stride], seq_length, n_kmers, format)"""
+        r = _Result()
+        _check(lib().fb2_sketcher_result(self._h, C.byref(r)))
+        try:
+            h, c, x, km = _result_to_py(r, self.params.kmer_length)
+            return h, c, x, km, int(r.seq_length), int(r.num_valid_kmers), int(r.format)
+        finally:
+            lib().fb2_result_free(C.byref(r))
+
+    def to_vec(self, kmer_len=None) -> List[KmerCount]:
+        h, c, x, km, *_ = self.to_arrays()
+        k = kmer_len if kmer_len is not None else self.params.kmer_length
+        return [KmerCount(int(h[i]), km[i, :k].tobytes(), int(c[i]), int(x[i])) for i in range(len(h))]
+
+    def to_sketch(self) -> Sketch:
+        """mod.rs:33-50: name "", default filters."""
+        h, c, x, km, sl, nk, fmt = self.to_arrays()
+        return Sketch("", sl, nk, "", h, c, x, km, FilterParams(), self.params, fmt)
+
+    # -- bulk feeds (replace the record loop lib.rs:60-68) ---------------------------------------
+    def feed_fastx(self, data, final=True):
+        addr, n, keep = _addr(data)
+        _check(lib().fb2_sketcher_feed_fastx(self._h, addr, n, int(final)))
+
+    def feed_fastx_ptr(self, host_ptr: int, nbytes: int, final=True):
+        _check(lib().fb2_sketcher_feed_fastx(self._h, host_ptr, nbytes, int(final)))
+
+    def feed_device(self, dev_ptr: int, nbytes: int, final=True):
+        _check(lib().fb2_sketcher_feed_device(self._h, dev_ptr, nbytes, int(final)))
+
+    def format(self):
+        f = C.c_int32()
+        _check(lib().fb2_sketcher_format(self._h, C.byref(f)))
+        return f.value
+
+    def enable_timing(self, on=True):
+        _check(lib().fb2_sketcher_enable_timing(self._h, int(on)))
+
+    def stats(self):
+        s = _Stats()
+        _check(lib().fb2_sketcher_stats(self._h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in _Stats._fields_}
+
+
+def MashSketcher(size, kmer_length, seed, device=-1):
+    """MashSketcher::new(size, kmer_length, seed)  (mash.rs:21)"""
+    return SketchParams.mash(size, size, False, kmer_length, seed, device).create_sketcher()
+
+
+def ScaledSketcher(size, scale, kmer_length, seed, device=-1):
+    """ScaledSketcher::new(size, scale, kmer_length, seed)  (scaled.rs:22)"""
+    return SketchParams.scaled(size, kmer_length, scale, seed, device).create_sketcher()
+
+
+# ---------------------------------------------------------------------------------------------
+def _finish(r, name, sp):
+    try:
+        h, c, x, km = _result_to_py(r, sp.kmer_length)
+        return Sketch(name, int(r.seq_length), int(r.num_valid_kmers), "", h, c, x, km,
+                      FilterParams._from_c(r.filters), sp, int(r.format))
+    finally:
+        lib().fb2_result_free(C.byref(r))
+
+
+def sketch_stream(data, name: str, sketch_params: SketchParams, filters: FilterParams) -> Sketch:
+    """lib/src/lib.rs:51-94 over an in-memory byte stream."""
+    addr, n, keep = _addr(data)
+    r = _Result()
+    cp, cf = sketch_params._c(), filters._c()
+    _check(lib().fb2_sketch_stream(addr, n, name.encode(), C.byref(cp), C.byref(cf), C.byref(r)))
+    return _finish(r, name, sketch_params)
+
+
+def sketch_files(filenames, sketch_params: SketchParams, filters: FilterParams) -> List[Sketch]:
+    """lib/src/lib.rs:29-49; results in input order."""
+    n = len(filenames)
+    arr = (C.c_char_p * n)(*[f.encode() for f in filenames])
+    outs = (_Result * n)()
+    cp, cf = sketch_params._c(), filters._c()
+    _check(lib().fb2_sketch_files(arr, n, C.byref(cp), C.byref(cf), outs))
+    return [_finish(outs[i], filenames[i], sketch_params) for i in range(n)]
+
+
+def filter_counts(filters: FilterParams, hashes, counts, extras, fmt=FORMAT_FASTQ):
+    """FilterParams::filter_counts on plain arrays -> (kept hashes, counts, extras, updated FilterParams)."""
+    h = np.ascontiguousarray(hashes, np.uint64).copy()
+    c = np.ascontiguousarray(counts, np.uint32).copy()
+    x = np.ascontiguousarray(extras, np.uint32).copy()
+    km = np.zeros(max(1, len(h)), np.uint8)
+    r = _Result(len(h), h.ctypes.data_as(C.POINTER(C.c_uint64)), c.ctypes.data_as(C.POINTER(C.c_uint32)),
+                x.ctypes.data_as(C.POINTER(C.c_uint32)), km.ctypes.data_as(C.POINTER(C.c_uint8)), 1, 0, 0, fmt,
+                _Filter())
+    cf = filters._c()
+    _check(lib().fb2_filter_counts(C.byref(r), C.byref(cf)))
+    n = int(r.n)
+    return h[:n], c[:n], x[:n], FilterParams._from_c(cf)
+
+
+def guess_filter_threshold(counts, level):
+    c = np.ascontiguousarray(counts, np.uint32)
+    return int(lib().fb2_guess_filter_threshold(c.ctypes.data, c.size, level))
+
+
+# ---- distance ---------------------------------------------------------------------------------
+@dataclass
+class SketchDistance:
+    """lib/src/serialization/mod.rs:31-43"""
+    containment: float
+    jaccard: float
+    mash_distance: float
+    common_hashes: int
+    total_hashes: int
+    query: str = ""
+    reference: str = ""
+
+
+def _pack(sketch_hashes):
+    lens = np.array([len(s) for s in sketch_hashes], np.uint32)
+    stride = max(1, int(lens.max()) if len(lens) else 1)
+    mat = np.zeros((len(sketch_hashes), stride), np.uint64)
+    for i, s in enumerate(sketch_hashes):
+        mat[i, :len(s)] = np.asarray(s, np.uint64)
+    return mat, lens, stride
+
+
+def dist_batch(sketch_hashes, q_idx, r_idx, scale=0.0, device=-1):
+    """Integer part of raw_distance for many pairs: -> array[(common, i, j)] (uint32 x 3)."""
+    mat, lens, stride = _pack(sketch_hashes)
+    q, r = np.ascontiguousarray(q_idx, np.uint32), np.ascontiguousarray(r_idx, np.uint32)
+    out = np.zeros((len(q), 3), np.uint32)
+    _check(lib().fb2_dist_batch(mat.ctypes.data, lens.ctypes.data, len(lens), stride, scale, q.ctypes.data,
+                                r.ctypes.data, len(q), out.ctypes.data, device))
+    return out
+
+
+def dist_all_pairs(mat, lens, scale=0.0, q0=0, q1=None, device=-1):
+    mat = np.ascontiguousarray(mat, np.uint64)
+    lens = np.ascontiguousarray(lens, np.uint32)
+    n, stride = mat.shape
+    q1 = n if q1 is None else q1
+    out = np.zeros(((q1 - q0) * n, 3), np.uint32)
+    _check(lib().fb2_dist_all_pairs(mat.ctypes.data, lens.ctypes.data, n, stride, scale, q0, q1,
+                                    out.ctypes.data, device))
+    return out.reshape(q1 - q0, n, 3)
+
+
+def _finish_pair(row, k):
+    p = _PairOut(int(row[0]), int(row[1]), int(row[2]))
+    cont, jac, md = C.c_double(), C.c_double(), C.c_double()
+    com, tot = C.c_uint64(), C.c_uint64()
+    lib().fb2_distance_finish(C.byref(p), k, C.byref(cont), C.byref(jac), C.byref(md), C.byref(com), C.byref(tot))
+    return cont.value, jac.value, md.value, com.value, tot.value
+
+
+def raw_distance(query_hashes, ref_hashes, scale=0.0):
+    """distance.rs:66-126 -> (containment, jaccard, common, total)"""
+    out = dist_batch([query_hashes, ref_hashes], [0], [1], scale)
+    cont, jac, _, com, tot = _finish_pair(out[0], 1)
+    return cont, jac, com, tot
+
+
+def distance(query: Sketch, ref: Sketch, old_mode=False) -> SketchDistance:
+    """distance.rs:9-47 (old_mode is the legacy path and is out of scope)."""
+    if old_mode:
+        raise FinchError(EUNSUPPORTED, "old_distance is out of scope")
+    s1 = query.sketch_params.scale if query.sketch_params.kind == KIND_SCALED else None
+    s2 = ref.sketch_params.scale if ref.sketch_params.kind == KIND_SCALED else None
+    min_scale = min(s1, s2) if (s1 is not None and s2 is not None) else 0.0
+    out = dist_batch([query.hashes_u64, ref.hashes_u64], [0], [1], min_scale)
+    cont, jac, md, com, tot = _finish_pair(out[0], query.sketch_params.kmer_length)
+    return SketchDistance(cont, jac, md, com, tot, query.name, ref.name)
+
+
+# ---- synthetic inputs ---------------------------------------------------------------
+def synth_genome(n_bases, seed):
+    out = np.empty(n_bases, np.uint8)
+    lib().fb2_synth_genome(out.ctypes.data, n_bases, seed)
+    return out
+
+
+def synth_fasta(n_bases, n_records=1, line_width=80, lower_frac=0.0, n_frac=0.0, seed=1):
+    need = lib().fb2_synth_fasta(None, 0, n_bases, n_records, line_width, lower_frac, n_frac, seed)
+    out = np.empty(need, np.uint8)
+    lib().fb2_synth_fasta(out.ctypes.data, need, n_bases, n_records, line_width, lower_frac, n_frac, seed)
+    return out
+
+
+def fastq_nbytes(n_reads, read_len, first_read_id=0):
+    """Exact size of synth_fastq's output: '@r<id>\\n' + seq + '\\n+\\n' + qual + '\\n' per read."""
+    total, lo, digits = 0, first_read_id, None
+    hi = first_read_id + n_reads
+    while lo < hi:
+        digits = len(str(lo))
+        nxt = min(hi, 10 ** digits)
+        total += (nxt - lo) * (2 + digits + 1 + read_len + 1 + 2 + read_len + 1)
+        lo = nxt
+    return total
+
+
+def synth_fastq(genome, n_reads, read_len=150, err_rate=0.005, seed=3, first_read_id=0, out=None):
+    genome = np.ascontiguousarray(genome, np.uint8)
+    need = fastq_nbytes(n_reads, read_len, first_read_id)
+    if out is None:
+        out = np.empty(need, np.uint8)
+    addr = out.ctypes.data if isinstance(out, np.ndarray) else int(out)
+    nb = C.c_uint64()
+    got = lib().fb2_synth_fastq(addr, need, genome.ctypes.data, genome.size, n_reads, read_len, err_rate, seed,
+                                first_read_id, C.byref(nb))
+    assert got == need, (got, need)
+    return out, int(nb.value)

@@ -1,0 +1,80 @@
+// device_types.cuh -- structures shared between the kernels and the host engine.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fb2 {
+
+constexpr int TILE_THREADS = 256;   // parse: threads per tile
+constexpr int TILE_BYTES = 4096;    // parse: raw bytes per tile (16 per thread)
+constexpr int SYM_FRONT = 64;       // symbols carried in front of each chunk's symbol buffer
+constexpr int HASH_THREADS = 256;
+constexpr int HASH_W = 32;          // k-mer end positions per thread
+constexpr uint32_t HASH_TILE = HASH_THREADS * HASH_W;  // symbols per block
+
+enum ParseMode : int { MODE_LINES = 0, MODE_FASTA = 1, MODE_FASTQ = 2 };
+
+// Per-tile transducer summary: for every possible state at the tile's first byte, the state
+// after its last byte and the number of symbols the tile emits.
+//   FASTQ: state = phase (0 header, 1 sequence, 2 '+', 3 quality) of the current line (4 states)
+//   FASTA: state = 0 sequence line / 1 header line (2 states);  LINES: 1 state
+struct TileSummary {
+    uint32_t next;     // 2 bits per start state
+    uint32_t cnt[4];   // symbols emitted per start state
+};
+struct TilePrefix {
+    uint32_t state_in;
+    uint32_t sym_off;  // chunk-relative symbol offset of the tile's first symbol
+};
+
+// Parser + stream state that persists across chunks (device resident; mirrored to the host
+// after every chunk).  All positions are global (stream) offsets.
+struct ParseCarry {
+    uint32_t state;          // state of the line containing the next byte
+    uint32_t prev1, prev2;   // last / second-to-last raw byte of the stream so far
+    uint32_t error;          // sticky device-side error bits
+    uint64_t raw_total;      // raw bytes consumed
+    uint64_t ordinal;        // symbols (+ pushed k-mers) emitted so far == next position id
+    uint64_t total_bases;    // Sum of record sequence().len() (wrapping arithmetic)
+    uint64_t n_records;
+    uint64_t first_bad_pos;  // FASTQ: min raw pos of a line start failing the '@' / '+' check
+    uint64_t last_sig;       // FASTQ: max ((raw pos + 1) << 2 | phase) over bytes that are not CR/LF
+    uint64_t chunk_raw_base; // raw_total before the current chunk
+    uint64_t chunk_ord_base; // ordinal before the current chunk
+    uint32_t chunk_syms;     // symbols produced by the current chunk
+    uint32_t cprev1, cprev2; // prev1 / prev2 as they were at the start of the current chunk
+    uint32_t pad;
+};
+
+// Sketch state (device resident; mirrored to the host when the host needs to decide).
+struct SketchState {
+    unsigned long long threshold;     // admit hash <= threshold (only ever decreases)
+    unsigned long long total_kmers;   // committed
+    unsigned long long launch_kmers;  // valid k-mers seen by the current hash launch
+    unsigned int log_count;           // entries appended by the current hash launch (may exceed cap)
+    unsigned int occupied;            // table slots in use (excl. the u64::MAX side slot)
+    unsigned int has_max_key;         // side slot for hash == u64::MAX in use
+    unsigned int gather_count;
+    unsigned int keep_count;          // result of select_keep
+    unsigned int pad;
+    unsigned long long new_threshold;
+};
+
+struct LogView {
+    unsigned long long *hash;   // murmur h1
+    unsigned long long *kmer;   // LSB-first 2-bit codes, or arena index for pushed k-mers
+    unsigned long long *posx;   // position id << 9 | is_arena << 8 | extra_count (u8)
+    unsigned int cap;
+};
+struct TableView {
+    unsigned long long *key;    // EMPTY_KEY when free; slot `cap` is the side slot for u64::MAX
+    unsigned long long *cnt;
+    unsigned long long *ext;
+    unsigned long long *posx;   // min posx over occurrences (first occurrence wins the kmer)
+    unsigned long long *kmer;
+    unsigned int cap;           // power of two
+    unsigned int shift;         // 64 - log2(cap)
+};
+constexpr unsigned long long EMPTY_KEY = ~0ULL;
+
+}  // namespace fb2

@@ -1,0 +1,811 @@
+// engine.cu -- the sketcher object behind the C ABI (include/finch_b200.h).
+//
+// Host-side orchestration only: all arithmetic on sequence data runs in the kernels of
+// parse.cu / hash.cu / table.cu.  There is no CPU fallback.
+//
+// Mirrors, per handle, the state of MashSketcher / ScaledSketcher (mash.rs:10-18, scaled.rs:10-19):
+//   heap + counts map  ->  device hash table (TableView) + admission threshold
+//   total_kmers        ->  host counter fed by the hash kernel's per-launch count
+//   total_bases        ->  ParseCarry::total_bases (FASTX) + host sum (process())
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace fb2;
+
+// ---- error plumbing --------------------------------------------------------------------------
+static thread_local std::string g_err;
+int fb2_fail(int code, const std::string &msg) { g_err = msg; return code; }
+extern "C" const char *fb2_last_error(void) { return g_err.c_str(); }
+
+#define CU(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess)                                                                  \
+            return fb2_fail(FB2_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+#define TRY(x) do { int r_ = (x); if (r_ != FB2_OK) return r_; } while (0)
+
+static size_t env_size(const char *name, size_t dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (size_t)strtoull(v, nullptr, 10);
+}
+static uint32_t next_pow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t)p;
+}
+static inline uint32_t cdivu(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {  // contents are NOT preserved
+        if (bytes <= cap) return FB2_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+        return FB2_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Table {
+    DevBuf key, cnt, ext, posx, kmer;
+    uint32_t cap = 0;
+    int alloc(uint32_t c) {
+        const size_t n = (size_t)c + 1;  // + side slot for hash == u64::MAX
+        TRY(key.ensure(n * 8)); TRY(cnt.ensure(n * 8)); TRY(ext.ensure(n * 8));
+        TRY(posx.ensure(n * 8)); TRY(kmer.ensure(n * 8));
+        cap = c;
+        return FB2_OK;
+    }
+    TableView view() const {
+        TableView v;
+        v.key = key.as<unsigned long long>(); v.cnt = cnt.as<unsigned long long>();
+        v.ext = ext.as<unsigned long long>(); v.posx = posx.as<unsigned long long>();
+        v.kmer = kmer.as<unsigned long long>();
+        v.cap = cap;
+        uint32_t lg = 0; while ((1u << lg) < cap) ++lg;
+        v.shift = 64u - lg;
+        return v;
+    }
+    void release() { key.release(); cnt.release(); ext.release(); posx.release(); kmer.release(); cap = 0; }
+};
+
+struct fb2_sketcher {
+    fb2_params prm{};
+    int device = 0;
+    bool scaled = false;
+    uint64_t size = 0, max_hash = 0;
+    int k = 0;
+    cudaStream_t st = nullptr, copy_st = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev_h2d[2]{}, ev_rawfree[2]{}, ev_t0 = nullptr, ev_t1 = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
+    bool rawfree_pending[2] = {false, false};
+
+    size_t chunk_bytes = 0;
+    DevBuf d_raw[2], d_sym, d_sums, d_pre, d_carry, d_state;
+    DevBuf log_hash, log_kmer, log_posx;
+    uint32_t log_cap = 0;
+    Table tab[2];
+    int cur = 0;
+    DevBuf sort_keys, sort_slots, sort_tkeys, sort_tslots, sort_hist;
+    DevBuf out_hash, out_cnt, out_ext, out_kmer, out_posx;
+    DevBuf d_push_bytes, d_push_offs, d_push_extra;
+
+    ParseCarry *h_carry = nullptr;  // pinned mirrors
+    SketchState *h_state = nullptr;
+
+    uint8_t *h_stage = nullptr;     // pinned staging for process() and small feed pieces
+    size_t stage_cap = 0, stage_fill = 0;
+    int stage_mode = -1;
+
+    std::vector<uint8_t> push_bytes, push_extra;
+    std::vector<uint32_t> push_offs;
+    std::vector<std::string> arena;  // bytes of pushed k-mers (unit-test surface)
+    size_t arena_flushed = 0;
+
+    int format = FB2_FORMAT_UNKNOWN;
+    bool stream_open = false;        // a FASTX stream has begun and not yet seen `final`
+    uint8_t sniff[2] = {0, 0};
+    uint64_t lines_bases = 0, total_kmers = 0;
+    uint32_t next_launch = 0;
+    fb2_stats stats{};
+    bool timing = false;
+};
+
+// ---- small helpers ---------------------------------------------------------------------------
+static LogView log_view(fb2_sketcher *s) {
+    LogView l;
+    l.hash = s->log_hash.as<unsigned long long>(); l.kmer = s->log_kmer.as<unsigned long long>();
+    l.posx = s->log_posx.as<unsigned long long>(); l.cap = s->log_cap;
+    return l;
+}
+static int pull_state(fb2_sketcher *s) {  // device -> pinned mirrors, then wait
+    CU(cudaMemcpyAsync(s->h_state, s->d_state.p, sizeof(SketchState), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->h_carry, s->d_carry.p, sizeof(ParseCarry), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->stats.d2h_bytes += sizeof(SketchState) + sizeof(ParseCarry);
+    return FB2_OK;
+}
+static int push_carry(fb2_sketcher *s) {
+    CU(cudaMemcpyAsync(s->d_carry.p, s->h_carry, sizeof(ParseCarry), cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return FB2_OK;
+}
+static int push_state(fb2_sketcher *s) {
+    CU(cudaMemcpyAsync(s->d_state.p, s->h_state, sizeof(SketchState), cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return FB2_OK;
+}
+
+static int ensure_table(fb2_sketcher *s, int which, uint32_t cap) {
+    TRY(s->tab[which].alloc(cap));
+    return FB2_OK;
+}
+static int ensure_sort(fb2_sketcher *s, uint32_t n) {
+    const size_t m = (size_t)n + 64;
+    TRY(s->sort_keys.ensure(m * 8)); TRY(s->sort_tkeys.ensure(m * 8));
+    TRY(s->sort_slots.ensure(m * 4)); TRY(s->sort_tslots.ensure(m * 4));
+    TRY(s->sort_hist.ensure((size_t)radix_hist_words(n) * 4));
+    return FB2_OK;
+}
+
+static int reset_sketch_state(fb2_sketcher *s) {
+    memset(s->h_state, 0, sizeof(SketchState));
+    s->h_state->threshold = (s->scaled && s->size == 0) ? s->max_hash : ~0ULL;
+    TRY(push_state(s));
+    memset(s->h_carry, 0, sizeof(ParseCarry));
+    s->h_carry->prev1 = s->h_carry->prev2 = '\n';
+    s->h_carry->first_bad_pos = ~0ULL;
+    TRY(push_carry(s));
+    launch_table_clear(s->tab[s->cur].view(), s->st);
+    launch_fill_bytes(s->d_sym.as<uint8_t>(), SYM_FRONT, SYM_BREAK, s->st);
+    s->stats.kernel_launches += 2;
+    CU(cudaStreamSynchronize(s->st));
+    s->format = FB2_FORMAT_UNKNOWN; s->stream_open = false;
+    s->lines_bases = 0; s->total_kmers = 0; s->stage_fill = 0; s->stage_mode = -1;
+    s->next_launch = 32u * HASH_TILE;
+    s->push_bytes.clear(); s->push_extra.clear(); s->push_offs.assign(1, 0u);
+    s->arena.clear(); s->arena_flushed = 0;
+    return FB2_OK;
+}
+
+// ---- create / destroy --------------------------------------------------------------------------
+extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
+    if (!p || !out) return fb2_fail(FB2_EINVAL, "null argument");
+    *out = nullptr;
+    if (p->kind != FB2_KIND_MASH && p->kind != FB2_KIND_SCALED) return fb2_fail(FB2_EINVAL, "unknown sketch kind");
+    if (p->kmer_length < 1 || p->kmer_length > 32)
+        return fb2_fail(FB2_EUNSUPPORTED, "kmer_length must be in 1..=32 on this build");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
+    int dev = p->device;
+    if (dev < 0) { CU(cudaGetDevice(&dev)); }
+    if (dev >= ndev) return fb2_fail(FB2_EINVAL, "device ordinal out of range");
+    CU(cudaSetDevice(dev));
+
+    fb2_sketcher *s = new fb2_sketcher();
+    s->prm = *p; s->device = dev; s->k = p->kmer_length;
+    s->scaled = p->kind == FB2_KIND_SCALED;
+    s->size = p->kmers_to_sketch;
+    if (s->scaled) {
+        // scaled.rs:23,31: iscale = (1./scale) as u64 (saturating); max_hash = u64::MAX / iscale
+        const double inv = 1.0 / p->scale;
+        uint64_t iscale;
+        if (!(inv == inv) || inv <= 0.0) iscale = 0;
+        else if (inv >= 18446744073709551616.0) iscale = UINT64_MAX;
+        else iscale = (uint64_t)inv;
+        if (iscale == 0) { delete s; return fb2_fail(FB2_EINVAL, "scale must be in (0, 1]"); }
+        s->max_hash = UINT64_MAX / iscale;
+    }
+    if (p->stream) { s->st = (cudaStream_t)p->stream; s->own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking)); s->own_stream = true; }
+    CU(cudaStreamCreateWithFlags(&s->copy_st, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_rawfree[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreate(&s->ev_t0)); CU(cudaEventCreate(&s->ev_t1));
+    CU(cudaEventCreate(&s->ev_p0)); CU(cudaEventCreate(&s->ev_p1));
+
+    s->chunk_bytes = env_size("FB2_CHUNK_MB", 128) << 20;
+    if (s->chunk_bytes < (1u << 20)) s->chunk_bytes = 1u << 20;
+    if (s->chunk_bytes > (1ull << 30)) s->chunk_bytes = 1ull << 30;
+    s->log_cap = (uint32_t)(env_size("FB2_LOG_M", 8) << 20);
+    if (s->log_cap < 32u * HASH_TILE) s->log_cap = 32u * HASH_TILE;
+
+    int rc = FB2_OK;
+    do {
+        if ((rc = s->d_carry.ensure(sizeof(ParseCarry))) != FB2_OK) break;
+        if ((rc = s->d_state.ensure(sizeof(SketchState))) != FB2_OK) break;
+        if ((rc = s->d_sym.ensure(SYM_FRONT + 4096)) != FB2_OK) break;
+        if (cudaHostAlloc((void **)&s->h_carry, sizeof(ParseCarry), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void **)&s->h_state, sizeof(SketchState), cudaHostAllocDefault) != cudaSuccess) {
+            rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed"); break;
+        }
+        if ((rc = s->log_hash.ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
+        if ((rc = s->log_kmer.ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
+        if ((rc = s->log_posx.ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
+        uint64_t want = s->size ? 4 * s->size : 1;
+        if (want < (1u << 16)) want = 1u << 16;
+        if (want > (1u << 22)) want = 1u << 22;  // grows on demand
+        if ((rc = ensure_table(s, 0, next_pow2(want))) != FB2_OK) break;
+        s->cur = 0;
+        if ((rc = reset_sketch_state(s)) != FB2_OK) break;
+    } while (0);
+    if (rc != FB2_OK) { fb2_sketcher_destroy(s); return rc; }
+    *out = s;
+    return FB2_OK;
+}
+
+extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->st) cudaStreamSynchronize(s->st);
+    if (s->copy_st) cudaStreamSynchronize(s->copy_st);
+    for (int i = 0; i < 2; ++i) {
+        s->d_raw[i].release(); s->tab[i].release();
+        if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
+        if (s->ev_rawfree[i]) cudaEventDestroy(s->ev_rawfree[i]);
+    }
+    if (s->ev_t0) cudaEventDestroy(s->ev_t0);
+    if (s->ev_t1) cudaEventDestroy(s->ev_t1);
+    if (s->ev_p0) cudaEventDestroy(s->ev_p0);
+    if (s->ev_p1) cudaEventDestroy(s->ev_p1);
+    s->d_sym.release(); s->d_sums.release(); s->d_pre.release(); s->d_carry.release(); s->d_state.release();
+    s->log_hash.release(); s->log_kmer.release(); s->log_posx.release();
+    s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release();
+    s->out_hash.release(); s->out_cnt.release(); s->out_ext.release(); s->out_kmer.release(); s->out_posx.release();
+    s->d_push_bytes.release(); s->d_push_offs.release(); s->d_push_extra.release();
+    if (s->h_carry) cudaFreeHost(s->h_carry);
+    if (s->h_state) cudaFreeHost(s->h_state);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    if (s->own_stream && s->st) cudaStreamDestroy(s->st);
+    if (s->copy_st) cudaStreamDestroy(s->copy_st);
+    delete s;
+}
+
+extern "C" int fb2_sketcher_reset(fb2_sketcher *s) {
+    if (!s) return fb2_fail(FB2_EINVAL, "null handle");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st));
+    return reset_sketch_state(s);
+}
+
+// ---- pruning: bottom-s selection + table rebuild -------------------------------------------------
+// Sort the occupied keys, decide how many the sketch keeps (select_keep_kernel), rebuild the other
+// table from those and lower the threshold.  Grows the table when what must be kept needs it.
+static int sort_table(fb2_sketcher *s, uint32_t *n_out) {
+    TRY(pull_state(s));
+    const uint32_t n = s->h_state->occupied + (s->h_state->has_max_key ? 1u : 0u);
+    TRY(ensure_sort(s, std::max(n, 1u)));
+    launch_gather(s->tab[s->cur].view(), (SketchState *)s->d_state.p, s->sort_keys.as<unsigned long long>(),
+                  s->sort_slots.as<uint32_t>(), s->st);
+    launch_radix_sort(s->sort_keys.as<unsigned long long>(), s->sort_slots.as<uint32_t>(),
+                      s->sort_tkeys.as<unsigned long long>(), s->sort_tslots.as<uint32_t>(), n,
+                      s->sort_hist.as<uint32_t>(), s->st);
+    launch_select_keep(s->sort_keys.as<unsigned long long>(), n, s->scaled ? 1 : 0, s->size, s->max_hash,
+                       (SketchState *)s->d_state.p, s->st);
+    s->stats.kernel_launches += 2 + (n >= 2 ? 24 : 0) + 1;
+    TRY(pull_state(s));
+    *n_out = n;
+    return FB2_OK;
+}
+static int prune(fb2_sketcher *s, uint32_t need_room) {
+    uint32_t n = 0;
+    TRY(sort_table(s, &n));
+    const uint32_t keep = s->h_state->keep_count;
+    // new capacity: keep + the room the caller needs must stay under 3/4 load
+    uint32_t cap = s->tab[s->cur].cap;
+    while ((uint64_t)keep + need_room > (uint64_t)cap / 4 * 3 || (uint64_t)keep * 2 > cap) {
+        if (cap >= (1u << 30)) return fb2_fail(FB2_ENOMEM, "sketch table would exceed 2^30 slots");
+        cap <<= 1;
+    }
+    const int other = s->cur ^ 1;
+    TRY(ensure_table(s, other, cap));
+    launch_rebuild(s->sort_keys.as<unsigned long long>(), s->sort_slots.as<uint32_t>(), keep,
+                   s->tab[s->cur].view(), s->tab[other].view(), (SketchState *)s->d_state.p, s->st);
+    launch_commit_threshold((SketchState *)s->d_state.p, s->st);
+    s->stats.kernel_launches += 4;
+    s->cur = other;
+    s->stats.prunes++;
+    TRY(pull_state(s));
+    return FB2_OK;
+}
+
+// Absorb log[0, cnt) into the table, pruning / growing so the table never passes 3/4 load.
+static int absorb_log(fb2_sketcher *s, uint32_t cnt) {
+    uint32_t i = 0;
+    while (i < cnt) {
+        const uint32_t cap = s->tab[s->cur].cap;
+        const uint32_t limit = cap / 4 * 3;
+        const uint32_t occ = s->h_state->occupied;
+        uint32_t room = occ < limit ? limit - occ : 0;
+        const uint32_t left = cnt - i;
+        if (room < std::min(left, cap / 4)) {
+            TRY(prune(s, std::min(left, cap / 4)));
+            continue;
+        }
+        const uint32_t m = std::min(left, room);
+        launch_absorb(log_view(s), i, i + m, s->tab[s->cur].view(), (SketchState *)s->d_state.p, s->st);
+        s->stats.kernel_launches += 2;
+        i += m;
+        TRY(pull_state(s));
+    }
+    // keep the threshold moving: first finite threshold as soon as `size` keys exist, then at half load
+    const uint32_t occ = s->h_state->occupied;
+    const bool infinite = s->h_state->threshold == ~0ULL;
+    const bool can_lower = s->size > 0 && occ >= s->size;
+    if ((infinite && can_lower) || occ > s->tab[s->cur].cap / 2) TRY(prune(s, 0));
+    return FB2_OK;
+}
+
+// ---- one chunk of raw bytes resident in HBM ---------------------------------------------------------
+static int hash_range(fb2_sketcher *s, uint32_t upper) {
+    uint8_t *sym0 = s->d_sym.as<uint8_t>() + SYM_FRONT;
+    SketchState *dst = (SketchState *)s->d_state.p;
+    uint32_t pos = 0;
+    bool known = false;
+    uint32_t n_sym = upper;
+    while (pos < n_sym) {
+        uint32_t n = std::max(s->next_launch, HASH_TILE);
+        n = (n + HASH_TILE - 1) / HASH_TILE * HASH_TILE;
+        if (n > n_sym - pos) n = (n_sym - pos + HASH_TILE - 1) / HASH_TILE * HASH_TILE;
+        // zero the per-launch counters (log_count, launch_kmers)
+        s->h_state->log_count = 0; s->h_state->launch_kmers = 0;
+        CU(cudaMemsetAsync(&dst->log_count, 0, sizeof(unsigned int), s->st));
+        CU(cudaMemsetAsync(&dst->launch_kmers, 0, sizeof(unsigned long long), s->st));
+        if (s->timing) CU(cudaEventRecord(s->ev_t0, s->st));
+        launch_hash(s->k, sym0, pos, pos + n, (const ParseCarry *)s->d_carry.p, dst, log_view(s), s->prm.hash_seed, s->st);
+        if (s->timing) CU(cudaEventRecord(s->ev_t1, s->st));
+        s->stats.kernel_launches++; s->stats.hash_launches++;
+        TRY(pull_state(s));
+        if (s->timing) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
+            s->stats.hash_kernel_ms += ms;
+        }
+        if (!known) { n_sym = s->h_carry->chunk_syms; known = true; }
+        const uint32_t cnt = s->h_state->log_count;
+        if (cnt > s->log_cap) {  // log overflowed: nothing committed, redo this range in smaller launches
+            s->next_launch = std::max<uint32_t>(HASH_TILE, std::min(n / 4, s->log_cap / HASH_TILE * HASH_TILE));
+            continue;
+        }
+        const uint32_t done = pos >= n_sym ? 0 : std::min(n, n_sym - pos);
+        s->total_kmers += s->h_state->launch_kmers;
+        s->stats.hash_symbols += done;
+        TRY(absorb_log(s, cnt));
+        pos += n;
+        // next launch: aim the candidate count at a quarter of the log
+        const double frac = done ? std::max((double)cnt, 1.0) / (double)done : 1.0;
+        double next = (double)(s->log_cap / 4) / frac;
+        if (next > 2147483648.0) next = 2147483648.0;
+        s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (uint32_t)next);
+    }
+    return FB2_OK;
+}
+
+static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mode, int rawbuf /* -1: not ours */) {
+    if (!len) return FB2_OK;
+    const uint32_t n_tiles = cdivu(len, TILE_BYTES);
+    TRY(s->d_sums.ensure((size_t)n_tiles * sizeof(TileSummary)));
+    TRY(s->d_pre.ensure((size_t)n_tiles * sizeof(TilePrefix)));
+    const size_t sym_need = (size_t)SYM_FRONT + len + 2 * HASH_TILE;
+    if (sym_need > s->d_sym.cap) {  // preserve the carried front symbols
+        DevBuf nb;
+        TRY(nb.ensure(sym_need));
+        CU(cudaMemcpyAsync(nb.p, s->d_sym.p, SYM_FRONT, cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        s->d_sym.release();
+        s->d_sym = nb;
+    }
+    ParseCarry *dc = (ParseCarry *)s->d_carry.p;
+    if (s->timing) CU(cudaEventRecord(s->ev_p0, s->st));
+    launch_tile_summary(mode, d_raw, len, dc, s->d_sums.as<TileSummary>(), n_tiles, s->st);
+    launch_tile_scan(s->d_sums.as<TileSummary>(), n_tiles, dc, s->d_pre.as<TilePrefix>(), d_raw, len, s->st);
+    launch_pack(mode, d_raw, len, dc, s->d_pre.as<TilePrefix>(), s->d_sym.as<uint8_t>() + SYM_FRONT, n_tiles, s->st);
+    if (s->timing) CU(cudaEventRecord(s->ev_p1, s->st));
+    if (rawbuf >= 0) { CU(cudaEventRecord(s->ev_rawfree[rawbuf], s->st)); s->rawfree_pending[rawbuf] = true; }
+    s->stats.kernel_launches += 3; s->stats.chunks++;
+    TRY(hash_range(s, len));
+    if (s->timing) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev_p0, s->ev_p1));
+        s->stats.parse_kernel_ms += ms;
+    }
+    launch_carry_front(s->d_sym.as<uint8_t>(), dc, s->st);
+    s->stats.kernel_launches++;
+    return FB2_OK;
+}
+
+// Host bytes -> chunks, H2D double-buffered on the copy stream against the compute stream.
+static int feed_host_chunks(fb2_sketcher *s, const uint8_t *bytes, size_t len, int mode) {
+    if (!len) return FB2_OK;
+    const size_t chunk = s->chunk_bytes;
+    const size_t nch = (len + chunk - 1) / chunk;
+    const size_t bufsz = std::min(chunk, (len + 4095) / 4096 * 4096) + 64;
+    auto issue = [&](size_t c) -> int {
+        const int b = (int)(c & 1);
+        const size_t off = c * chunk, n = std::min(chunk, len - off);
+        TRY(s->d_raw[b].ensure(bufsz));
+        if (s->rawfree_pending[b]) { CU(cudaStreamWaitEvent(s->copy_st, s->ev_rawfree[b], 0)); s->rawfree_pending[b] = false; }
+        CU(cudaMemcpyAsync(s->d_raw[b].p, bytes + off, n, cudaMemcpyHostToDevice, s->copy_st));
+        CU(cudaEventRecord(s->ev_h2d[b], s->copy_st));
+        s->stats.h2d_bytes += n;
+        return FB2_OK;
+    };
+    // make sure earlier work that used the raw buffers is ordered before we overwrite them
+    for (int b = 0; b < 2; ++b) if (s->rawfree_pending[b]) { CU(cudaStreamWaitEvent(s->copy_st, s->ev_rawfree[b], 0)); s->rawfree_pending[b] = false; }
+    TRY(issue(0));
+    for (size_t c = 0; c < nch; ++c) {
+        if (c + 1 < nch) TRY(issue(c + 1));
+        const int b = (int)(c & 1);
+        const size_t off = c * chunk, n = std::min(chunk, len - off);
+        CU(cudaStreamWaitEvent(s->st, s->ev_h2d[b], 0));
+        TRY(run_chunk(s, s->d_raw[b].as<uint8_t>(), (uint32_t)n, mode, b));
+    }
+    return FB2_OK;
+}
+
+static int flush_stage(fb2_sketcher *s) {
+    if (!s->stage_fill) return FB2_OK;
+    const size_t n = s->stage_fill;
+    const int mode = s->stage_mode;
+    s->stage_fill = 0;
+    TRY(feed_host_chunks(s, s->h_stage, n, mode));
+    // the staging buffer is reused right away: wait for its H2D copies
+    CU(cudaStreamSynchronize(s->copy_st));
+    return FB2_OK;
+}
+static int ensure_stage(fb2_sketcher *s) {
+    if (s->h_stage) return FB2_OK;
+    s->stage_cap = std::min<size_t>(s->chunk_bytes, 64u << 20);
+    CU(cudaHostAlloc((void **)&s->h_stage, s->stage_cap, cudaHostAllocDefault));
+    return FB2_OK;
+}
+
+static int flush_push(fb2_sketcher *s) {
+    const uint32_t n = (uint32_t)s->push_extra.size();
+    if (!n) return FB2_OK;
+    TRY(s->d_push_bytes.ensure(s->push_bytes.size() + 16));
+    TRY(s->d_push_offs.ensure((size_t)(n + 1) * 4));
+    TRY(s->d_push_extra.ensure(n));
+    CU(cudaMemcpyAsync(s->d_push_bytes.p, s->push_bytes.data(), s->push_bytes.size(), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_push_offs.p, s->push_offs.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_push_extra.p, s->push_extra.data(), n, cudaMemcpyHostToDevice, s->st));
+    s->stats.h2d_bytes += s->push_bytes.size() + (size_t)(n + 1) * 4 + n;
+    SketchState *dst = (SketchState *)s->d_state.p;
+    CU(cudaMemsetAsync(&dst->log_count, 0, sizeof(unsigned int), s->st));
+    CU(cudaMemsetAsync(&dst->launch_kmers, 0, sizeof(unsigned long long), s->st));
+    launch_push_hash(s->d_push_bytes.as<uint8_t>(), s->d_push_offs.as<uint32_t>(), s->d_push_extra.as<uint8_t>(), n,
+                     s->arena_flushed, (ParseCarry *)s->d_carry.p, dst, log_view(s), s->prm.hash_seed, s->st);
+    s->stats.kernel_launches += 2;
+    TRY(pull_state(s));
+    s->total_kmers += s->h_state->launch_kmers;
+    s->arena_flushed += n;
+    s->push_bytes.clear(); s->push_extra.clear(); s->push_offs.assign(1, 0u);
+    TRY(absorb_log(s, s->h_state->log_count));
+    return FB2_OK;
+}
+static int flush_all(fb2_sketcher *s) {
+    TRY(flush_stage(s));
+    TRY(flush_push(s));
+    return FB2_OK;
+}
+
+// ---- SketchScheme::process ------------------------------------------------------------------------
+extern "C" int fb2_sketcher_process(fb2_sketcher *s, const uint8_t *seq, size_t len) {
+    if (!s || (!seq && len)) return fb2_fail(FB2_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    if (s->stream_open) return fb2_fail(FB2_EINVAL, "process() while a FASTX stream is open");
+    TRY(flush_push(s));
+    TRY(ensure_stage(s));
+    if (s->stage_mode != MODE_LINES) { TRY(flush_stage(s)); s->stage_mode = MODE_LINES; }
+    s->lines_bases += len;  // mash.rs:72: total_bases += seq.sequence().len()
+    size_t done = 0;
+    // the record goes into staging with interior '\n' rewritten to ' ' (both are dropped by
+    // normalize) and one '\n' appended as the record separator; long records span flushes.
+    while (done < len) {
+        if (s->stage_fill == s->stage_cap) { TRY(flush_stage(s)); s->stage_mode = MODE_LINES; }
+        const size_t n = std::min(len - done, s->stage_cap - s->stage_fill);
+        uint8_t *dst = s->h_stage + s->stage_fill;
+        for (size_t i = 0; i < n; ++i) { const uint8_t c = seq[done + i]; dst[i] = c == '\n' ? ' ' : c; }
+        s->stage_fill += n; done += n;
+    }
+    if (s->stage_fill == s->stage_cap) { TRY(flush_stage(s)); s->stage_mode = MODE_LINES; }
+    s->h_stage[s->stage_fill++] = '\n';
+    return FB2_OK;
+}
+
+// ---- push -----------------------------------------------------------------------------------------
+extern "C" int fb2_sketcher_push(fb2_sketcher *s, const uint8_t *kmer, size_t k, uint8_t extra_count) {
+    if (!s || (!kmer && k)) return fb2_fail(FB2_EINVAL, "null argument");
+    if (k > 255) return fb2_fail(FB2_EINVAL, "k-mer longer than 255 bytes");
+    CU(cudaSetDevice(s->device));
+    TRY(flush_stage(s));
+    s->push_bytes.insert(s->push_bytes.end(), kmer, kmer + k);
+    s->push_offs.push_back((uint32_t)s->push_bytes.size());
+    s->push_extra.push_back(extra_count);
+    s->arena.emplace_back((const char *)kmer, k);
+    if (s->push_extra.size() >= (size_t)s->log_cap / 2) TRY(flush_push(s));
+    return FB2_OK;
+}
+
+// ---- FASTX streams -------------------------------------------------------------------------------
+static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
+    const uint8_t c = first[0];
+    if (c == '>') s->format = FB2_FORMAT_FASTA;
+    else if (c == '@') s->format = FB2_FORMAT_FASTQ;
+    else if ((c == 0x1f && n > 1 && first[1] == 0x8b) || (c == 'B' && n > 1 && first[1] == 'Z') ||
+             (c == 0xFD && n > 1 && first[1] == '7'))
+        return fb2_fail(FB2_EUNSUPPORTED, "compressed input is not supported; decompress first");
+    else return fb2_fail(FB2_EFORMAT, "could not detect FASTA/FASTQ: first byte is neither '>' nor '@'");
+    TRY(flush_all(s));
+    TRY(pull_state(s));
+    ParseCarry *c_ = s->h_carry;
+    c_->state = s->format == FB2_FORMAT_FASTA ? 1u : 0u;  // FASTA: pretend a header line precedes byte 0
+    c_->prev1 = c_->prev2 = '\n';
+    c_->raw_total = 0; c_->n_records = 0; c_->first_bad_pos = ~0ULL; c_->last_sig = 0; c_->error = 0;
+    TRY(push_carry(s));
+    s->stream_open = true;
+    return FB2_OK;
+}
+static int end_stream(fb2_sketcher *s) {
+    TRY(flush_stage(s));
+    TRY(pull_state(s));
+    ParseCarry *c = s->h_carry;
+    int rc = FB2_OK;
+    if (s->format == FB2_FORMAT_FASTA) {
+        // last record: raw sequence loses its final '\n' (+ CR before it) or a dangling CR
+        if (c->state == 0u) {
+            if (c->prev1 == '\n') { c->total_bases -= 1; if (c->prev2 == '\r') c->total_bases -= 1; }
+            else if (c->prev1 == '\r') c->total_bases -= 1;
+        }
+    } else if (s->format == FB2_FORMAT_FASTQ) {
+        if (c->last_sig == 0) rc = fb2_fail(FB2_EEMPTY, "no records in FASTQ stream");
+        else if ((c->last_sig & 3ULL) != 3ULL) rc = fb2_fail(FB2_ERECORD, "truncated FASTQ record at end of input");
+        else if (c->first_bad_pos != ~0ULL && c->first_bad_pos < (c->last_sig >> 2))
+            rc = fb2_fail(FB2_ERECORD, "invalid FASTQ record: line at byte " + std::to_string(c->first_bad_pos) +
+                                           " does not start with the expected '@' / '+'");
+    }
+    // a later stream or record must not join this one: break the carried symbols
+    c->state = 0; c->prev1 = c->prev2 = '\n';
+    TRY(push_carry(s));
+    launch_fill_bytes(s->d_sym.as<uint8_t>(), SYM_FRONT, SYM_BREAK, s->st);
+    s->stats.kernel_launches++;
+    s->stream_open = false;
+    return rc;
+}
+
+extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, size_t len, int final) {
+    if (!s || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    if (len) {
+        if (!s->stream_open) TRY(begin_stream(s, bytes, len));
+        const int mode = s->format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ;
+        if (len < (1u << 20)) {  // small piece: gather in pinned staging
+            TRY(ensure_stage(s));
+            if (s->stage_mode != mode) { TRY(flush_stage(s)); s->stage_mode = mode; }
+            size_t done = 0;
+            while (done < len) {
+                if (s->stage_fill == s->stage_cap) { TRY(flush_stage(s)); s->stage_mode = mode; }
+                const size_t n = std::min(len - done, s->stage_cap - s->stage_fill);
+                memcpy(s->h_stage + s->stage_fill, bytes + done, n);
+                s->stage_fill += n; done += n;
+            }
+        } else {
+            TRY(flush_stage(s));
+            TRY(feed_host_chunks(s, bytes, len, mode));
+            CU(cudaStreamSynchronize(s->copy_st));  // caller may reuse `bytes` after we return
+        }
+    }
+    if (final) {
+        if (!s->stream_open) return fb2_fail(FB2_EEMPTY, "empty input: no records");
+        TRY(end_stream(s));
+    }
+    return FB2_OK;
+}
+
+extern "C" int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev, size_t len, int final) {
+    if (!s || (!dev && len)) return fb2_fail(FB2_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    if (len) {
+        if (!s->stream_open) {
+            uint8_t first[2] = {0, 0};
+            CU(cudaMemcpy(first, dev, std::min<size_t>(2, len), cudaMemcpyDeviceToHost));
+            TRY(begin_stream(s, first, std::min<size_t>(2, len)));
+        }
+        TRY(flush_stage(s));
+        const int mode = s->format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ;
+        const size_t chunk = s->chunk_bytes;
+        const bool aligned = ((uintptr_t)dev & 15u) == 0;
+        for (size_t off = 0; off < len; off += chunk) {
+            const size_t n = std::min(chunk, len - off);
+            if (aligned) {
+                TRY(run_chunk(s, dev + off, (uint32_t)n, mode, -1));
+            } else {
+                TRY(s->d_raw[0].ensure(n + 64));
+                CU(cudaMemcpyAsync(s->d_raw[0].p, dev + off, n, cudaMemcpyDeviceToDevice, s->st));
+                TRY(run_chunk(s, s->d_raw[0].as<uint8_t>(), (uint32_t)n, mode, -1));
+            }
+        }
+    }
+    if (final) {
+        if (!s->stream_open) return fb2_fail(FB2_EEMPTY, "empty input: no records");
+        TRY(end_stream(s));
+    }
+    return FB2_OK;
+}
+
+extern "C" int fb2_sketcher_format(fb2_sketcher *s, int32_t *format) {
+    if (!s || !format) return fb2_fail(FB2_EINVAL, "null argument");
+    *format = s->format;
+    return FB2_OK;
+}
+
+// ---- totals / result -------------------------------------------------------------------------------
+extern "C" int fb2_sketcher_totals(fb2_sketcher *s, uint64_t *total_bases, uint64_t *total_kmers) {
+    if (!s) return fb2_fail(FB2_EINVAL, "null handle");
+    CU(cudaSetDevice(s->device));
+    TRY(flush_all(s));
+    TRY(pull_state(s));
+    if (total_bases) *total_bases = s->h_carry->total_bases + s->lines_bases;
+    if (total_kmers) *total_kmers = s->total_kmers;
+    return FB2_OK;
+}
+
+extern "C" void fb2_result_free(fb2_result *r) {
+    if (!r) return;
+    free(r->hashes); free(r->counts); free(r->extras); free(r->kmers);
+    r->hashes = nullptr; r->counts = nullptr; r->extras = nullptr; r->kmers = nullptr; r->n = 0;
+}
+
+extern "C" int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out) {
+    if (!s || !out) return fb2_fail(FB2_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    memset(out, 0, sizeof(*out));
+    TRY(flush_all(s));
+    uint32_t n = 0;
+    TRY(sort_table(s, &n));
+    const uint32_t keep = s->h_state->keep_count;
+    std::vector<unsigned long long> h_kmer(keep), h_posx(keep);
+    out->n = keep;
+    out->hashes = (uint64_t *)malloc(std::max<size_t>(1, (size_t)keep * 8));
+    out->counts = (uint32_t *)malloc(std::max<size_t>(1, (size_t)keep * 4));
+    out->extras = (uint32_t *)malloc(std::max<size_t>(1, (size_t)keep * 4));
+    if (!out->hashes || !out->counts || !out->extras) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
+    if (keep) {
+        TRY(s->out_hash.ensure((size_t)keep * 8)); TRY(s->out_kmer.ensure((size_t)keep * 8));
+        TRY(s->out_posx.ensure((size_t)keep * 8));
+        TRY(s->out_cnt.ensure((size_t)keep * 4)); TRY(s->out_ext.ensure((size_t)keep * 4));
+        launch_export(s->sort_keys.as<unsigned long long>(), s->sort_slots.as<uint32_t>(), keep, s->tab[s->cur].view(),
+                      s->out_hash.as<unsigned long long>(), s->out_cnt.as<uint32_t>(), s->out_ext.as<uint32_t>(),
+                      s->out_kmer.as<unsigned long long>(), s->out_posx.as<unsigned long long>(), s->st);
+        s->stats.kernel_launches++;
+        CU(cudaMemcpyAsync(out->hashes, s->out_hash.p, (size_t)keep * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(out->counts, s->out_cnt.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(out->extras, s->out_ext.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(h_kmer.data(), s->out_kmer.p, (size_t)keep * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(h_posx.data(), s->out_posx.p, (size_t)keep * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        s->stats.d2h_bytes += (size_t)keep * 32;
+    }
+    // k-mer bytes: 2-bit codes -> ASCII, or the bytes handed to push()
+    size_t stride = (size_t)s->k;
+    for (uint32_t i = 0; i < keep; ++i)
+        if (h_posx[i] & (1ULL << 8)) stride = std::max(stride, s->arena[(size_t)h_kmer[i]].size());
+    out->kmer_stride = (uint32_t)stride;
+    out->kmers = (uint8_t *)calloc(std::max<size_t>(1, (size_t)keep * stride), 1);
+    if (!out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
+    for (uint32_t i = 0; i < keep; ++i) {
+        uint8_t *dst = out->kmers + (size_t)i * stride;
+        if (h_posx[i] & (1ULL << 8)) { const std::string &a = s->arena[(size_t)h_kmer[i]]; memcpy(dst, a.data(), a.size()); }
+        else codes_to_ascii(h_kmer[i], s->k, dst);
+    }
+    out->seq_length = s->h_carry->total_bases + s->lines_bases;
+    out->num_valid_kmers = s->total_kmers;
+    out->format = s->format;
+    out->filters.filter_on = 0;
+    return FB2_OK;
+}
+
+extern "C" int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out) {
+    if (!s || !out) return fb2_fail(FB2_EINVAL, "null argument");
+    *out = s->stats;
+    return FB2_OK;
+}
+extern "C" int fb2_sketcher_enable_timing(fb2_sketcher *s, int on) {
+    if (!s) return fb2_fail(FB2_EINVAL, "null handle");
+    s->timing = on != 0;
+    return FB2_OK;
+}
+
+// ---- dist --------------------------------------------------------------------------------------------
+static unsigned long long dist_max_hash(double scale) {
+    // distance.rs:100: u64::MAX / scale.recip() as u64
+    const double rec = 1.0 / scale;
+    const uint64_t d = rec >= 18446744073709551616.0 ? UINT64_MAX : (uint64_t)rec;
+    return d ? UINT64_MAX / d : UINT64_MAX;
+}
+static int dist_common(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride, int32_t device,
+                       DevBuf &d_h, DevBuf &d_l) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
+    if (device >= 0) CU(cudaSetDevice(device));
+    TRY(d_h.ensure(std::max<size_t>(8, n_sk * stride * 8)));
+    TRY(d_l.ensure(std::max<size_t>(4, n_sk * 4)));
+    CU(cudaMemcpy(d_h.p, hashes, n_sk * stride * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_l.p, lens, n_sk * 4, cudaMemcpyHostToDevice));
+    return FB2_OK;
+}
+extern "C" int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride, double scale,
+                              const uint32_t *q_idx, const uint32_t *r_idx, size_t n_pairs, fb2_pair_out *out,
+                              int32_t device) {
+    if ((!hashes && n_sk * stride) || !lens || (n_pairs && (!q_idx || !r_idx || !out)))
+        return fb2_fail(FB2_EINVAL, "null argument");
+    for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
+    for (size_t i = 0; i < n_pairs; ++i)
+        if (q_idx[i] >= n_sk || r_idx[i] >= n_sk) return fb2_fail(FB2_EINVAL, "pair index out of range");
+    DevBuf d_h, d_l, d_q, d_r, d_o;
+    int rc = dist_common(hashes, lens, n_sk, stride, device, d_h, d_l);
+    if (rc == FB2_OK && n_pairs) {
+        do {
+            if ((rc = d_q.ensure(n_pairs * 4)) != FB2_OK) break;
+            if ((rc = d_r.ensure(n_pairs * 4)) != FB2_OK) break;
+            if ((rc = d_o.ensure(n_pairs * sizeof(fb2_pair_out))) != FB2_OK) break;
+            cudaMemcpy(d_q.p, q_idx, n_pairs * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(d_r.p, r_idx, n_pairs * 4, cudaMemcpyHostToDevice);
+            launch_dist_pairs(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, d_q.as<uint32_t>(),
+                              d_r.as<uint32_t>(), n_pairs, scale > 0.0, scale > 0.0 ? dist_max_hash(scale) : 0,
+                              d_o.as<fb2_pair_out>(), 0);
+            cudaError_t e = cudaMemcpy(out, d_o.p, n_pairs * sizeof(fb2_pair_out), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+        } while (0);
+    }
+    d_h.release(); d_l.release(); d_q.release(); d_r.release(); d_o.release();
+    return rc;
+}
+extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
+                                  double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device) {
+    if ((!hashes && n_sk * stride) || !lens || q0 > q1 || q1 > n_sk) return fb2_fail(FB2_EINVAL, "bad argument");
+    for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
+    const uint64_t n_pairs = (uint64_t)(q1 - q0) * n_sk;
+    if (n_pairs && !out) return fb2_fail(FB2_EINVAL, "null output");
+    DevBuf d_h, d_l, d_o;
+    int rc = dist_common(hashes, lens, n_sk, stride, device, d_h, d_l);
+    if (rc == FB2_OK && n_pairs) {
+        // bounded slabs of whole query rows so the output buffer stays small
+        const uint64_t rows = std::max<uint64_t>(1, (1ull << 24) / std::max<size_t>(1, n_sk));
+        rc = d_o.ensure(std::min<uint64_t>(n_pairs, rows * n_sk) * sizeof(fb2_pair_out));
+        for (uint64_t q = q0; rc == FB2_OK && q < q1; q += rows) {
+            const uint64_t m = std::min<uint64_t>(rows, q1 - q) * n_sk;
+            launch_dist_all(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, (uint32_t)n_sk,
+                            (uint32_t)q, m, scale > 0.0, scale > 0.0 ? dist_max_hash(scale) : 0,
+                            d_o.as<fb2_pair_out>(), 0);
+            cudaError_t e = cudaMemcpy(out + (q - q0) * n_sk, d_o.p, m * sizeof(fb2_pair_out), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+        }
+    }
+    d_h.release(); d_l.release(); d_o.release();
+    return rc;
+}
+
+extern "C" int fb2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" const char *fb2_version(void) { return "finch_b200 0.1.0 (sm_100a)"; }

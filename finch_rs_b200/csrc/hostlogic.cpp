@@ -1,0 +1,282 @@
+// hostlogic.cpp -- the O(sketch size) host steps around the GPU path, and the callers of it.
+//
+//   fb2_filter_counts        <- FilterParams::filter_counts      (lib/src/filtering.rs:60-87)
+//     strand filter          <- filter_strands                   (filtering.rs:413-432)
+//     error cutoff           <- guess_filter_threshold + hist    (filtering.rs:154-195, statistics.rs:30-47)
+//     abundance filter       <- filter_abundance                 (filtering.rs:329-343)
+//   fb2_process_post_filter  <- SketchParams::process_post_filter (sketch_schemes/mod.rs:115-128)
+//   fb2_sketch_stream/files  <- sketch_stream / sketch_files     (lib/src/lib.rs:29-94)
+//   fb2_distance_finish      <- raw_distance tail + distance     (distance.rs:117-125, :35-41)
+// These stay on the host exactly as SURVEY 8a (row S14, D2) scopes them: a few f64 compares over
+// <= kmers_to_sketch entries.  Written independently of oracle/ (which is test infrastructure).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/finch_b200.h"
+
+int fb2_fail(int code, const std::string &msg);  // engine.cu
+
+// ---- filters ---------------------------------------------------------------------------------
+static void compact(fb2_result *r, const std::vector<uint8_t> &keep) {
+    uint64_t m = 0;
+    const size_t st = r->kmer_stride;
+    for (uint64_t i = 0; i < r->n; ++i) {
+        if (!keep[i]) continue;
+        if (m != i) {
+            r->hashes[m] = r->hashes[i]; r->counts[m] = r->counts[i]; r->extras[m] = r->extras[i];
+            memmove(r->kmers + m * st, r->kmers + i * st, st);
+        }
+        ++m;
+    }
+    r->n = m;
+}
+
+extern "C" uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n, double filter_level) {
+    // histogram of counts: hist[c-1] = number of k-mers seen c times (statistics.rs:30-47)
+    uint32_t max_count = 0;
+    for (size_t i = 0; i < n; ++i) max_count = std::max(max_count, counts[i]);
+    std::vector<uint64_t> hist(max_count, 0);
+    for (size_t i = 0; i < n; ++i) if (counts[i]) hist[counts[i] - 1]++;
+    uint64_t total = 0;
+    for (size_t c = 0; c < hist.size(); ++c) total += (uint64_t)(c + 1) * hist[c];
+    const double cutoff_amt = filter_level * (double)total;
+    // coverage index below which `filter_level` of the weighted data lies
+    size_t wgt_cutoff = 0;
+    uint64_t cum = 0;
+    for (size_t c = 0; c < hist.size(); ++c) {
+        cum += (uint64_t)wgt_cutoff * hist[c];
+        if ((double)cum > cutoff_amt) break;
+        ++wgt_cutoff;
+    }
+    if (wgt_cutoff == 0) return 1;
+    // left-most... actually right-most minimum of the sliding window sum left of the cutoff
+    const size_t win = std::max<size_t>(1, wgt_cutoff / 20);
+    uint64_t sum = 0;
+    for (size_t c = 0; c < win; ++c) sum += hist[c];
+    uint64_t lowest = sum;
+    size_t lowest_idx = win - 1;
+    for (size_t lo = 0, hi = win; hi < wgt_cutoff; ++lo, ++hi) {
+        if (sum <= lowest) { lowest = sum; lowest_idx = hi; }
+        sum -= hist[lo];
+        sum += hist[hi];
+    }
+    return (uint32_t)lowest_idx + 1;
+}
+
+extern "C" int fb2_filter_counts(fb2_result *r, fb2_filter *f) {
+    if (!r || !f) return fb2_fail(FB2_EINVAL, "null argument");
+    if (f->filter_on < 0) {  // lib.rs:71-76
+        if (r->format == FB2_FORMAT_FASTA) f->filter_on = 0;
+        else if (r->format == FB2_FORMAT_FASTQ) f->filter_on = 1;
+        else return fb2_fail(FB2_EEMPTY, "Should have got a type");
+    }
+    const bool on = f->filter_on == 1;
+    if (on && f->strand_filter > 0.0) {
+        std::vector<uint8_t> keep(r->n, 1);
+        for (uint64_t i = 0; i < r->n; ++i) {
+            const uint32_t c = r->counts[i];
+            if (c < 16) continue;  // too few observations to call an adapter
+            const uint32_t lowest = std::min(r->extras[i], c - r->extras[i]);
+            keep[i] = ((double)lowest / (double)c) >= f->strand_filter;
+        }
+        compact(r, keep);
+    }
+    if (on && f->err_filter > 0.0) {
+        const uint32_t cutoff = fb2_guess_filter_threshold(r->counts, (size_t)r->n, f->err_filter);
+        if (f->has_abun_low) { if (cutoff > f->abun_low) f->abun_low = cutoff; }
+        else { f->has_abun_low = 1; f->abun_low = cutoff; }
+    }
+    if (on && (f->has_abun_low || f->has_abun_high)) {
+        const uint32_t lo = f->has_abun_low ? f->abun_low : 0u;
+        const uint32_t hi = f->has_abun_high ? f->abun_high : UINT32_MAX;
+        std::vector<uint8_t> keep(r->n);
+        for (uint64_t i = 0; i < r->n; ++i) keep[i] = lo <= r->counts[i] && r->counts[i] <= hi;
+        compact(r, keep);
+    }
+    r->filters = *f;
+    return FB2_OK;
+}
+
+extern "C" int fb2_process_post_filter(fb2_result *r, const fb2_params *p, const char *name) {
+    if (!r || !p) return fb2_fail(FB2_EINVAL, "null argument");
+    if (p->kind == FB2_KIND_MASH) {
+        if (r->n > p->final_size) r->n = p->final_size;
+        if (!p->no_strict && r->n < p->final_size)
+            return fb2_fail(FB2_ETOOFEW, std::string(name ? name : "") + " had too few kmers (" +
+                                             std::to_string(r->n) + ") to sketch");
+    }
+    return FB2_OK;
+}
+
+// ---- sketch_stream / sketch_files ----------------------------------------------------------------
+static int finish_sketch(fb2_sketcher *s, const char *name, const fb2_params *p, const fb2_filter *f,
+                         fb2_result *out) {
+    int rc = fb2_sketcher_result(s, out);
+    if (rc != FB2_OK) return rc;
+    fb2_filter ff = *f;
+    rc = fb2_filter_counts(out, &ff);
+    if (rc == FB2_OK) rc = fb2_process_post_filter(out, p, name);
+    if (rc != FB2_OK) fb2_result_free(out);
+    return rc;
+}
+
+extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
+                                 const fb2_filter *f, fb2_result *out) {
+    if (!p || !f || !out || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
+    memset(out, 0, sizeof(*out));
+    fb2_sketcher *s = nullptr;
+    int rc = fb2_sketcher_create(p, &s);
+    if (rc != FB2_OK) return rc;
+    rc = fb2_sketcher_feed_fastx(s, bytes, len, 1);
+    if (rc == FB2_OK) rc = finish_sketch(s, name, p, f, out);
+    fb2_sketcher_destroy(s);
+    return rc;
+}
+
+extern "C" int fb2_sketch_files(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
+                                fb2_result *outs) {
+    if (!p || !f || (n && (!paths || !outs))) return fb2_fail(FB2_EINVAL, "null argument");
+    for (size_t i = 0; i < n; ++i) memset(&outs[i], 0, sizeof(fb2_result));
+    if (!n) return FB2_OK;
+    fb2_sketcher *s = nullptr;
+    int rc = fb2_sketcher_create(p, &s);
+    if (rc != FB2_OK) return rc;
+    const size_t piece = 64u << 20;
+    std::vector<uint8_t> buf(piece);
+    for (size_t i = 0; i < n && rc == FB2_OK; ++i) {
+        const bool is_stdin = strcmp(paths[i], "-") == 0;  // lib.rs:38-40
+        FILE *fp = is_stdin ? stdin : fopen(paths[i], "rb");
+        if (!fp) { rc = fb2_fail(FB2_EIO, std::string(paths[i]) + ": No such file or directory"); break; }
+        if (i) rc = fb2_sketcher_reset(s);
+        bool any = false;
+        while (rc == FB2_OK) {
+            const size_t got = fread(buf.data(), 1, piece, fp);
+            if (got) { any = true; rc = fb2_sketcher_feed_fastx(s, buf.data(), got, 0); }
+            if (got < piece) break;
+        }
+        if (!is_stdin) fclose(fp);
+        if (rc == FB2_OK && !any) rc = fb2_fail(FB2_EEMPTY, std::string(paths[i]) + ": empty input");
+        if (rc == FB2_OK) rc = fb2_sketcher_feed_fastx(s, nullptr, 0, 1);
+        if (rc == FB2_OK) rc = finish_sketch(s, paths[i], p, f, &outs[i]);
+    }
+    fb2_sketcher_destroy(s);
+    if (rc != FB2_OK) for (size_t i = 0; i < n; ++i) fb2_result_free(&outs[i]);
+    return rc;
+}
+
+// ---- distance epilogue ---------------------------------------------------------------------------
+extern "C" void fb2_distance_finish(const fb2_pair_out *p, uint8_t kmer_length, double *containment,
+                                    double *jaccard, double *mash_distance, uint64_t *common_hashes,
+                                    uint64_t *total_hashes) {
+    const uint64_t common = p->common, i = p->i, j = p->j;
+    const double cont = j == 0 ? 0.0 : (double)common / (double)j;
+    const uint64_t total = i - common + j;
+    const double jac = total == 0 ? 1.0 : (double)common / (double)total;
+    double md = -1.0 * std::log((2.0 * jac) / (1.0 + jac)) / (double)kmer_length;
+    md = (md != md) ? 0.0 : (md > 0.0 ? md : 0.0);  // f64::max(0, md)
+    md = md < 1.0 ? md : 1.0;                       // f64::min(1, md)
+    if (containment) *containment = cont;
+    if (jaccard) *jaccard = jac;
+    if (mash_distance) *mash_distance = md;
+    if (common_hashes) *common_hashes = common;
+    if (total_hashes) *total_hashes = total;
+}
+
+// ---- synthetic inputs ------------------------------------------------------------------
+static inline uint64_t splitmix64(uint64_t &x) {
+    uint64_t z = (x += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+struct Rng {
+    uint64_t s;
+    explicit Rng(uint64_t seed) : s(seed) {}
+    uint64_t next() { return splitmix64(s); }
+    double unif() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+extern "C" size_t fb2_synth_genome(uint8_t *out, size_t n_bases, uint64_t seed) {
+    if (!out) return n_bases;
+    Rng r(seed);
+    size_t i = 0;
+    while (i < n_bases) {
+        uint64_t w = r.next();
+        for (int b = 0; b < 32 && i < n_bases; ++b, w >>= 2) out[i++] = (uint8_t)"ACGT"[w & 3];
+    }
+    return n_bases;
+}
+
+extern "C" size_t fb2_synth_fasta(uint8_t *out, size_t cap, size_t n_bases, uint32_t n_records,
+                                  uint32_t line_width, double lower_frac, double n_frac, uint64_t seed) {
+    if (n_records == 0) n_records = 1;
+    if (line_width == 0) line_width = 80;
+    Rng r(seed);
+    size_t o = 0;
+    auto put = [&](uint8_t c) { if (out && o < cap) out[o] = c; ++o; };
+    const size_t per = n_bases / n_records;
+    for (uint32_t rec = 0; rec < n_records; ++rec) {
+        const size_t len = rec + 1 == n_records ? n_bases - per * (n_records - 1) : per;
+        char hdr[64];
+        const int hl = snprintf(hdr, sizeof hdr, ">contig%u len=%zu\n", rec + 1, len);
+        for (int i = 0; i < hl; ++i) put((uint8_t)hdr[i]);
+        size_t i = 0, col = 0;
+        int run_kind = 0;        // 0 plain, 1 lowercase run, 2 N run
+        size_t run_left = 0;
+        uint64_t w = 0; int wb = 0;
+        while (i < len) {
+            if (run_left == 0) {
+                const double u = r.unif();
+                // runs of ~200 bases; fractions are of bases
+                if (u < n_frac) run_kind = 2; else if (u < n_frac + lower_frac) run_kind = 1; else run_kind = 0;
+                run_left = 100 + (size_t)(r.next() % 200);
+            }
+            if (wb == 0) { w = r.next(); wb = 32; }
+            uint8_t c = (uint8_t)"ACGT"[w & 3]; w >>= 2; --wb;
+            if (run_kind == 1) c = (uint8_t)(c | 0x20);
+            else if (run_kind == 2) c = 'N';
+            put(c); ++i; --run_left;
+            if (++col == line_width) { put('\n'); col = 0; }
+        }
+        if (col) put('\n');
+    }
+    return o;
+}
+
+extern "C" size_t fb2_synth_fastq(uint8_t *out, size_t cap, const uint8_t *genome, size_t genome_len,
+                                  uint64_t n_reads, uint32_t read_len, double err_rate, uint64_t seed,
+                                  uint64_t first_read_id, uint64_t *n_bases_out) {
+    if (!genome || genome_len < read_len) return 0;
+    size_t o = 0;
+    auto put = [&](uint8_t c) { if (out && o < cap) out[o] = c; ++o; };
+    const uint32_t err_thr = (uint32_t)(err_rate * 4294967296.0);
+    for (uint64_t i = 0; i < n_reads; ++i) {
+        Rng r(seed ^ ((first_read_id + i) * 0xD1342543DE82EF95ULL + 0x2545F4914F6CDD1DULL));  // per-read stream
+        const uint64_t id = first_read_id + i;
+        char hdr[32];
+        const int hl = snprintf(hdr, sizeof hdr, "@r%llu\n", (unsigned long long)id);
+        for (int j = 0; j < hl; ++j) put((uint8_t)hdr[j]);
+        const size_t start = (size_t)(r.next() % (genome_len - read_len + 1));
+        const bool rev = r.next() & 1;
+        for (uint32_t j = 0; j < read_len; ++j) {
+            uint8_t c = rev ? genome[start + read_len - 1 - j] : genome[start + j];
+            if (rev) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A';
+            const uint64_t w = r.next();
+            if ((uint32_t)w < err_thr) {  // substitution by one of the three other bases
+                const uint8_t alt = (uint8_t)"ACGT"[(w >> 32) & 3];
+                c = alt != c ? alt : (uint8_t)"ACGT"[((w >> 32) + 1) & 3];
+            }
+            put(c);
+        }
+        put('\n'); put('+'); put('\n');
+        for (uint32_t j = 0; j < read_len; ++j) put('I');
+        put('\n');
+    }
+    if (n_bases_out) *n_bases_out = n_reads * read_len;
+    return o;
+}

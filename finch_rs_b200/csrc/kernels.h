@@ -1,0 +1,49 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (parse.cu, hash.cu, table.cu, dist.cu).
+#pragma once
+#include "device_types.cuh"
+#include "../../include/finch_b200.h"
+
+namespace fb2 {
+
+// parse.cu
+void launch_tile_summary(int mode, const uint8_t *raw, uint32_t len, const ParseCarry *carry,
+                         TileSummary *out, uint32_t n_tiles, cudaStream_t st);
+void launch_tile_scan(const TileSummary *sums, uint32_t n_tiles, ParseCarry *carry, TilePrefix *pre,
+                      const uint8_t *raw, uint32_t len, cudaStream_t st);
+void launch_pack(int mode, const uint8_t *raw, uint32_t len, ParseCarry *carry, const TilePrefix *pre,
+                 uint8_t *sym, uint32_t n_tiles, cudaStream_t st);
+void launch_carry_front(uint8_t *symbuf, const ParseCarry *carry, cudaStream_t st);
+void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t st);
+
+// hash.cu
+void launch_hash(int k, const uint8_t *sym, uint32_t s0, uint32_t s1, const ParseCarry *carry,
+                 SketchState *st, LogView log, uint64_t seed, cudaStream_t stream);
+void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
+                      uint64_t arena_base, ParseCarry *carry, SketchState *st, LogView log,
+                      uint64_t seed, cudaStream_t stream);
+
+// table.cu
+void launch_absorb(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st, cudaStream_t s);
+void launch_table_clear(TableView t, cudaStream_t s);
+void launch_gather(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots, cudaStream_t s);
+void launch_radix_sort(unsigned long long *keys, uint32_t *vals, unsigned long long *tkeys, uint32_t *tvals,
+                       uint32_t n, uint32_t *hist, cudaStream_t s);
+uint32_t radix_hist_words(uint32_t n);
+void launch_select_keep(const unsigned long long *keys, uint32_t n, int scaled, unsigned long long size,
+                        unsigned long long max_hash, SketchState *st, cudaStream_t s);
+void launch_commit_threshold(SketchState *st, cudaStream_t s);
+void launch_rebuild(const unsigned long long *keys, const uint32_t *slots, uint32_t keep, TableView from,
+                    TableView to, SketchState *st, cudaStream_t s);
+void launch_export(const unsigned long long *keys, const uint32_t *slots, uint32_t keep, TableView t,
+                   unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext, unsigned long long *o_kmer,
+                   unsigned long long *o_posx, cudaStream_t s);
+
+// dist.cu
+void launch_dist_pairs(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, const uint32_t *q_idx,
+                       const uint32_t *r_idx, uint64_t n_pairs, int scaled, unsigned long long max_hash,
+                       fb2_pair_out *out, cudaStream_t s);
+void launch_dist_all(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk,
+                     uint32_t q0, uint64_t n_pairs, int scaled, unsigned long long max_hash, fb2_pair_out *out,
+                     cudaStream_t s);
+
+}  // namespace fb2

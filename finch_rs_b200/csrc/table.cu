@@ -1,0 +1,278 @@
+// table.cu -- K4/K5: candidate log -> distinct-hash table with count / extra_count / first k-mer,
+// pruning to the bottom-s, and the final ascending export.
+//
+// Replaces the state behind MashSketcher::push / ScaledSketcher::push
+//   BinaryHeap<HashedItem<Vec<u8>>> + HashMap<ItemHash,(u32,u32)>   (mash.rs:10-18,43-61; scaled.rs:41-60)
+// and to_vec (mash.rs:86-102 / scaled.rs:84-100) by their closed forms:
+//   Mash(s):          the s smallest distinct hashes of the whole input with their full totals
+//   Scaled(s, m):     the max(|{h <= m}|, s) smallest (just {h <= m} when s == 0)
+// The admission threshold only ever decreases, so a key that survives to the result was never
+// rejected or purged and its totals are complete.
+#include "common.cuh"
+#include "device_types.cuh"
+
+namespace fb2 {
+
+__device__ __forceinline__ uint32_t home_slot(unsigned long long key, uint32_t shift) {
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> shift);
+}
+
+// Find-or-insert `key`; returns its slot.  The table always has free slots (host guarantees
+// occupied + batch <= 3/4 cap), so the probe terminates.
+__device__ __forceinline__ uint32_t table_upsert(const TableView &t, unsigned long long key, SketchState *st) {
+    if (key == EMPTY_KEY) {                       // u64::MAX cannot be stored in a slot: side slot
+        if (atomicExch(&st->has_max_key, 1u) == 0u) { /* first use */ }
+        return t.cap;
+    }
+    uint32_t slot = home_slot(key, t.shift);
+    const uint32_t maskc = t.cap - 1u;
+    while (true) {
+        unsigned long long cur = t.key[slot];
+        if (cur == key) return slot;
+        if (cur == EMPTY_KEY) {
+            const unsigned long long prev = atomicCAS(&t.key[slot], EMPTY_KEY, key);
+            if (prev == EMPTY_KEY) { atomicAdd(&st->occupied, 1u); return slot; }
+            if (prev == key) return slot;
+        }
+        slot = (slot + 1u) & maskc;
+    }
+}
+__device__ __forceinline__ uint32_t table_find(const TableView &t, unsigned long long key) {
+    if (key == EMPTY_KEY) return t.cap;
+    uint32_t slot = home_slot(key, t.shift);
+    const uint32_t maskc = t.cap - 1u;
+    while (true) {
+        const unsigned long long cur = t.key[slot];
+        if (cur == key) return slot;
+        if (cur == EMPTY_KEY) return 0xFFFFFFFFu;
+        slot = (slot + 1u) & maskc;
+    }
+}
+
+// Pass 1: counts, strand counts and the minimum position per key.  Entries above the current
+// threshold (logged under an older, larger threshold) are dropped.
+__global__ void absorb_count_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st) {
+    const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    const unsigned long long key = log.hash[i];
+    if (key > st->threshold) return;
+    const unsigned long long px = log.posx[i];
+    const uint32_t slot = table_upsert(t, key, st);
+    atomicAdd(&t.cnt[slot], 1ULL);
+    const unsigned long long extra = px & 0xFFULL;
+    if (extra) atomicAdd(&t.ext[slot], extra);
+    atomicMin(&t.posx[slot], px);
+}
+// Pass 2: the occurrence that owns the minimum position donates the k-mer (mash.rs:52-55 keeps
+// the k-mer of the first push of a hash).
+__global__ void absorb_kmer_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, const SketchState *st) {
+    const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    const unsigned long long key = log.hash[i];
+    if (key > st->threshold) return;
+    const uint32_t slot = table_find(t, key);
+    if (slot == 0xFFFFFFFFu) return;
+    const unsigned long long px = log.posx[i];
+    if (t.posx[slot] == px) t.kmer[slot] = log.kmer[i];
+}
+
+__global__ void table_clear_kernel(TableView t) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= t.cap) {  // includes the side slot
+        t.key[i] = EMPTY_KEY; t.cnt[i] = 0; t.ext[i] = 0; t.posx[i] = ~0ULL; t.kmer[i] = 0;
+    }
+}
+
+// Occupied slots -> (key, slot) pairs, arbitrary order.
+__global__ void gather_kernel(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > t.cap) return;
+    bool occ;
+    if (i == t.cap) occ = st->has_max_key != 0u;
+    else occ = t.key[i] != EMPTY_KEY;
+    const uint32_t m = __ballot_sync(__activemask(), occ);
+    if (!occ) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t act = __activemask();
+    (void)act;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&st->gather_count, (unsigned int)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const uint32_t idx = base + __popc(m & ((1u << lane) - 1u));
+    keys[idx] = (i == t.cap) ? EMPTY_KEY : t.key[i];
+    slots[idx] = i;
+}
+
+// ---- LSD radix sort, 8 bits per pass, (u64 key, u32 value), stable --------------------------
+// Work unit = one warp over a contiguous segment of SORT_SEG keys.
+constexpr int SORT_WARPS = 8;
+constexpr uint32_t SORT_SEG = 2048;
+
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+radix_hist_kernel(const unsigned long long *__restrict__ keys, uint32_t n, int shift, uint32_t n_segs,
+                  uint32_t *__restrict__ hist /* [256][n_segs] */) {
+    __shared__ uint32_t h[SORT_WARPS][256];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    for (int i = lane; i < 256; i += 32) h[w][i] = 0;
+    __syncwarp();
+    const uint32_t seg = blockIdx.x * SORT_WARPS + w;
+    if (seg < n_segs) {
+        const uint32_t a = seg * SORT_SEG, b = min(a + SORT_SEG, n);
+        for (uint32_t i = a + lane; i < b; i += 32) atomicAdd(&h[w][(uint32_t)(keys[i] >> shift) & 255u], 1u);
+        __syncwarp();
+        for (int d = lane; d < 256; d += 32) hist[(uint32_t)d * n_segs + seg] = h[w][d];
+    }
+}
+// Exclusive scan of hist in (digit-major, segment-minor) order.  Single block of 1024 threads.
+__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *hist, uint32_t total) {
+    __shared__ uint32_t part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t G = (total + 1023u) / 1024u;
+    const uint32_t a = min(tid * G, total), b = min(a + G, total);
+    uint32_t s = 0;
+    for (uint32_t i = a; i < b; ++i) s += hist[i];
+    part[tid] = s;
+    __syncthreads();
+    // inclusive Hillis-Steele over 1024 partials
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        const uint32_t v = tid >= d ? part[tid - d] : 0u;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[tid] - s;
+    for (uint32_t i = a; i < b; ++i) { const uint32_t v = hist[i]; hist[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+radix_scatter_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n,
+                     int shift, uint32_t n_segs, const uint32_t *__restrict__ hist,
+                     unsigned long long *__restrict__ okeys, uint32_t *__restrict__ ovals) {
+    __shared__ uint32_t off[SORT_WARPS][256];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t seg = blockIdx.x * SORT_WARPS + w;
+    if (seg >= n_segs) return;
+    for (int d = lane; d < 256; d += 32) off[w][d] = hist[(uint32_t)d * n_segs + seg];
+    __syncwarp();
+    const uint32_t a = seg * SORT_SEG, b = min(a + SORT_SEG, n);
+    for (uint32_t base = a; base < b; base += 32) {
+        const uint32_t i = base + lane;
+        const bool in = i < b;
+        unsigned long long key = 0; uint32_t val = 0, d = 0;
+        if (in) { key = keys[i]; val = vals[i]; d = (uint32_t)(key >> shift) & 255u; }
+        const uint32_t act = __ballot_sync(0xffffffffu, in);
+        const uint32_t peers = __match_any_sync(0xffffffffu, in ? d : (256u + lane)) & act;
+        uint32_t dst = 0;
+        if (in) {
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            dst = off[w][d] + rank;
+        }
+        __syncwarp();
+        if (in && (int)lane == (31 - __clz(peers))) off[w][d] += __popc(peers);  // one writer per digit
+        __syncwarp();
+        if (in) { okeys[dst] = key; ovals[dst] = val; }
+    }
+}
+
+// After the sort: how many entries the sketch keeps, and the threshold that follows.
+//   Mash:   keep = min(n, s)                      new_threshold = key[s-1] when n >= s
+//   Scaled: keep = max(#{key <= max_hash}, min(n, s)); threshold = max(max_hash, key[s-1]) when n >= s
+__global__ void select_keep_kernel(const unsigned long long *keys, uint32_t n, int scaled,
+                                   unsigned long long size, unsigned long long max_hash, SketchState *st) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t keep = (unsigned long long)n < size ? n : (uint32_t)size;
+    unsigned long long thr = st->threshold;
+    if (!scaled) {
+        if ((unsigned long long)n >= size && size > 0) thr = min(thr, keys[size - 1]);
+    } else {
+        uint32_t lo = 0, hi = n;  // first index with key > max_hash
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] <= max_hash) lo = mid + 1; else hi = mid; }
+        if (lo > keep) keep = lo;
+        if (size == 0) { keep = lo; thr = min(thr, max_hash); }
+        else if ((unsigned long long)n >= size) thr = min(thr, max(max_hash, keys[size - 1]));
+    }
+    st->keep_count = keep;
+    st->new_threshold = thr;
+}
+__global__ void commit_threshold_kernel(SketchState *st) { st->threshold = st->new_threshold; }
+
+// Re-insert the first `keep` sorted entries of the old table into a (cleared) new table.
+__global__ void rebuild_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ slots,
+                               uint32_t keep, TableView from, TableView to, SketchState *st) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= keep) return;
+    const unsigned long long key = keys[i];
+    const uint32_t src = slots[i];
+    const uint32_t dst = table_upsert(to, key, st);
+    to.cnt[dst] = from.cnt[src]; to.ext[dst] = from.ext[src];
+    to.posx[dst] = from.posx[src]; to.kmer[dst] = from.kmer[src];
+}
+__global__ void reset_occupancy_kernel(SketchState *st) { st->occupied = 0; st->has_max_key = 0; }
+__global__ void reset_gather_kernel(SketchState *st) { st->gather_count = 0; }
+
+// to_vec export: first `keep` sorted entries -> SoA with saturating u32 counts (mash.rs:48-49).
+__global__ void export_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ slots,
+                              uint32_t keep, TableView t, unsigned long long *o_hash, uint32_t *o_cnt,
+                              uint32_t *o_ext, unsigned long long *o_kmer, unsigned long long *o_posx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= keep) return;
+    const uint32_t s = slots[i];
+    const unsigned long long c = t.cnt[s], e = t.ext[s];
+    o_hash[i] = keys[i];
+    o_cnt[i] = c > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)c;
+    o_ext[i] = e > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)e;
+    o_kmer[i] = t.kmer[s];
+    o_posx[i] = t.posx[s];
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+void launch_absorb(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st, cudaStream_t s) {
+    if (i1 <= i0) return;
+    absorb_count_kernel<<<cdiv(i1 - i0, 256), 256, 0, s>>>(log, i0, i1, t, st);
+    absorb_kmer_kernel<<<cdiv(i1 - i0, 256), 256, 0, s>>>(log, i0, i1, t, st);
+}
+void launch_table_clear(TableView t, cudaStream_t s) {
+    table_clear_kernel<<<cdiv(t.cap + 1, 256), 256, 0, s>>>(t);
+}
+void launch_gather(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots, cudaStream_t s) {
+    reset_gather_kernel<<<1, 1, 0, s>>>(st);
+    gather_kernel<<<cdiv(t.cap + 1, 256), 256, 0, s>>>(t, st, keys, slots);
+}
+// Sorts (keys, vals) of length n; result ends in (keys, vals) (8 passes ping-pong back).
+void launch_radix_sort(unsigned long long *keys, uint32_t *vals, unsigned long long *tkeys, uint32_t *tvals,
+                       uint32_t n, uint32_t *hist, cudaStream_t s) {
+    if (n < 2) return;
+    const uint32_t n_segs = cdiv(n, SORT_SEG);
+    const uint32_t blocks = cdiv(n_segs, SORT_WARPS);
+    unsigned long long *ka = keys, *kb = tkeys;
+    uint32_t *va = vals, *vb = tvals;
+    for (int pass = 0; pass < 8; ++pass) {
+        radix_hist_kernel<<<blocks, SORT_WARPS * 32, 0, s>>>(ka, n, pass * 8, n_segs, hist);
+        radix_scan_kernel<<<1, 1024, 0, s>>>(hist, 256u * n_segs);
+        radix_scatter_kernel<<<blocks, SORT_WARPS * 32, 0, s>>>(ka, va, n, pass * 8, n_segs, hist, kb, vb);
+        unsigned long long *tk = ka; ka = kb; kb = tk;
+        uint32_t *tv = va; va = vb; vb = tv;
+    }
+}
+uint32_t radix_hist_words(uint32_t n) { return 256u * cdiv(n ? n : 1, SORT_SEG); }
+
+void launch_select_keep(const unsigned long long *keys, uint32_t n, int scaled, unsigned long long size,
+                        unsigned long long max_hash, SketchState *st, cudaStream_t s) {
+    select_keep_kernel<<<1, 1, 0, s>>>(keys, n, scaled, size, max_hash, st);
+}
+void launch_commit_threshold(SketchState *st, cudaStream_t s) { commit_threshold_kernel<<<1, 1, 0, s>>>(st); }
+void launch_rebuild(const unsigned long long *keys, const uint32_t *slots, uint32_t keep, TableView from,
+                    TableView to, SketchState *st, cudaStream_t s) {
+    launch_table_clear(to, s);
+    reset_occupancy_kernel<<<1, 1, 0, s>>>(st);
+    if (keep) rebuild_kernel<<<cdiv(keep, 256), 256, 0, s>>>(keys, slots, keep, from, to, st);
+}
+void launch_export(const unsigned long long *keys, const uint32_t *slots, uint32_t keep, TableView t,
+                   unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext, unsigned long long *o_kmer,
+                   unsigned long long *o_posx, cudaStream_t s) {
+    if (keep) export_kernel<<<cdiv(keep, 256), 256, 0, s>>>(keys, slots, keep, t, o_hash, o_cnt, o_ext, o_kmer, o_posx);
+}
+
+}  // namespace fb2

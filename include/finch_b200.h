@@ -1,0 +1,185 @@
+/*
+ * finch_b200.h -- C ABI of the B200-native MinHash sketching engine (libfinch_b200.so).
+ *
+ * Drop-in boundary for ONE path of onecodex/finch-rs (reference @ bb481c0):
+ *   FASTA/FASTQ bytes -> canonical k-mers -> murmurhash3_x64_128(kmer, seed).0
+ *   -> bottom-s distinct hashes with count / extra_count (MashSketcher / ScaledSketcher),
+ *   the host filter that follows it, and `dist`'s sorted-hash intersection.
+ *
+ * The reference has no FFI; its operator boundary is the Rust trait `SketchScheme`
+ * (lib/src/sketch_schemes/mod.rs:24-51), the factory `SketchParams::create_sketcher`
+ * (mod.rs:86-113), `sketch_files` / `sketch_stream` (lib/src/lib.rs:29-94) and
+ * `distance` / `raw_distance` (lib/src/distance.rs:9-126).  Each entry point below names the
+ * reference item it replaces; INTEGRATION.md shows the Rust `extern "C"` binding and the
+ * `impl SketchScheme` shim a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns FB2_OK (0) or a negative
+ * FB2_E* code and never aborts/unwinds across the ABI; fb2_last_error() returns a thread-local
+ * message.  All compute runs in hand-written sm_100a CUDA kernels; there is NO CPU fallback:
+ * without a CUDA device every compute entry point returns FB2_ECUDA.
+ * Thread-safety: distinct handles may be used from distinct threads (as rayon does with one
+ * sketcher per file, lib.rs:36-46); a single handle is not re-entrant (`&mut self`).
+ */
+#ifndef FINCH_B200_H
+#define FINCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB2_OK 0
+#define FB2_EINVAL (-1)       /* bad argument */
+#define FB2_ECUDA (-2)        /* CUDA runtime failure / no device */
+#define FB2_EFORMAT (-3)      /* first byte neither '>' nor '@'      (lib.rs:60 panics) */
+#define FB2_ERECORD (-4)      /* invalid / truncated FASTQ record    (lib.rs:63 panics) */
+#define FB2_EEMPTY (-5)       /* no records in the stream            (lib.rs:72 panics) */
+#define FB2_ETOOFEW (-6)      /* "<name> had too few kmers (<n>) to sketch" (mod.rs:115-128) */
+#define FB2_EUNSUPPORTED (-7) /* kmer_length outside 1..=32, compressed input */
+#define FB2_EIO (-8)          /* file could not be opened / read     (lib.rs:43) */
+#define FB2_ENOMEM (-9)
+
+#define FB2_KIND_MASH 0   /* SketchParams::Mash   (mod.rs:55-61) */
+#define FB2_KIND_SCALED 1 /* SketchParams::Scaled (mod.rs:62-67) */
+
+#define FB2_FORMAT_UNKNOWN 0
+#define FB2_FORMAT_FASTA 1 /* needletail::parser::Format::Fasta */
+#define FB2_FORMAT_FASTQ 2 /* needletail::parser::Format::Fastq */
+
+/* SketchParams (mod.rs:53-71) + placement. */
+typedef struct fb2_params {
+    int32_t kind;             /* FB2_KIND_* */
+    uint64_t kmers_to_sketch; /* Mash: heap size; Scaled: fill-up size (0 = pure scaled) */
+    uint64_t final_size;      /* Mash only: process_post_filter truncation */
+    int32_t no_strict;        /* Mash only */
+    uint8_t kmer_length;      /* 1..=32 on this build */
+    uint64_t hash_seed;
+    double scale;             /* Scaled only */
+    int32_t device;           /* CUDA ordinal; -1 = current device */
+    void *stream;             /* cudaStream_t to launch on; NULL = library-owned stream */
+} fb2_params;
+
+/* FilterParams (lib/src/filtering.rs:11-16). */
+typedef struct fb2_filter {
+    int32_t filter_on;     /* -1 = None (auto by format, lib.rs:71-76), 0 = Some(false), 1 = Some(true) */
+    int32_t has_abun_low;  uint32_t abun_low;   /* abun_filter.0 */
+    int32_t has_abun_high; uint32_t abun_high;  /* abun_filter.1 */
+    double err_filter;     /* already multiplied by k/100 as cli.rs:264-265 does */
+    double strand_filter;
+} fb2_filter;
+
+/* Vec<KmerCount> (mod.rs:15-22) as library-owned SoA, ascending by hash; plus the Sketch
+ * metadata sketch_stream fills (lib.rs:84-93).  Free with fb2_result_free. */
+typedef struct fb2_result {
+    uint64_t n;
+    uint64_t *hashes;      /* n */
+    uint32_t *counts;      /* n, saturating u32 (mash.rs:48) */
+    uint32_t *extras;      /* n, saturating u32 (mash.rs:49) */
+    uint8_t *kmers;        /* n * kmer_stride bytes: canonical k-mer of the first occurrence */
+    uint32_t kmer_stride;
+    uint64_t seq_length;       /* total_bases  (mash.rs:72,82-84) */
+    uint64_t num_valid_kmers;  /* total_kmers  (mash.rs:35) */
+    int32_t format;            /* FB2_FORMAT_* seen by the parser */
+    fb2_filter filters;        /* FilterParams as updated by filter_counts (sketch_* calls only) */
+} fb2_result;
+
+typedef struct fb2_sketcher fb2_sketcher;
+
+/* ---- SketchParams::create_sketcher / MashSketcher::new / ScaledSketcher::new ------------- */
+/* (mod.rs:86-113, mash.rs:21, scaled.rs:22) */
+int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out);
+/* Drop */
+void fb2_sketcher_destroy(fb2_sketcher *s);
+/* Forget all state but keep device buffers (one handle re-used across files). */
+int fb2_sketcher_reset(fb2_sketcher *s);
+
+/* ---- SketchScheme::process (mod.rs:25-28; mash.rs:67-80, scaled.rs:65-78) ---------------- */
+/* One record's RAW, un-normalised sequence bytes.  Batches internally; the GPU work happens
+ * when a staging chunk fills or on totals/result. */
+int fb2_sketcher_process(fb2_sketcher *s, const uint8_t *seq, size_t len);
+
+/* ---- MashSketcher::push / ScaledSketcher::push (mash.rs:34, scaled.rs:37) ---------------- */
+/* Unit-test surface: hashes the given bytes as they are (any bytes, any length <= 255). */
+int fb2_sketcher_push(fb2_sketcher *s, const uint8_t *kmer, size_t k, uint8_t extra_count);
+
+/* ---- bulk replacement of the record loop lib.rs:60-68 ------------------------------------ */
+/* Raw FASTA/FASTQ file bytes in arbitrary pieces (seams anywhere); `final` != 0 on the last
+ * piece.  `bytes` may be pageable or pinned host memory. */
+int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, size_t len, int final);
+/* Same, bytes already resident in device memory (HBM) of the sketcher's device. */
+int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev_bytes, size_t len, int final);
+/* needletail SequenceRecord::format() of the stream fed so far (lib.rs:64-66). */
+int fb2_sketcher_format(fb2_sketcher *s, int32_t *format);
+
+/* ---- SketchScheme::total_bases_and_kmers (mash.rs:82-84) --------------------------------- */
+int fb2_sketcher_totals(fb2_sketcher *s, uint64_t *total_bases, uint64_t *total_kmers);
+/* ---- SketchScheme::to_vec (mash.rs:86-102, scaled.rs:84-100) ----------------------------- */
+/* Non-destructive (the trait takes &self): more input may follow. */
+int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out);
+void fb2_result_free(fb2_result *r);
+
+/* Counters for benchmarking: kernels launched and bytes moved by this handle so far. */
+typedef struct fb2_stats {
+    uint64_t kernel_launches, h2d_bytes, d2h_bytes, chunks, prunes, hash_launches;
+    double hash_kernel_ms;   /* CUDA-event time of the k-mer hash kernel (only if timing enabled) */
+    double parse_kernel_ms;  /* CUDA-event time of the parse/pack kernels */
+    uint64_t hash_symbols;   /* symbols (bases + record breaks) the hash kernel walked */
+} fb2_stats;
+int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out);
+int fb2_sketcher_enable_timing(fb2_sketcher *s, int on);
+
+/* ---- FilterParams::filter_counts + SketchParams::process_post_filter ---------------------- */
+/* (filtering.rs:60-87, mod.rs:115-128).  In place on `r`; `f` is updated like the reference
+ * (filter_on resolved from `format` when -1; abun_low raised to the guessed cutoff). */
+int fb2_filter_counts(fb2_result *r, fb2_filter *f);
+int fb2_process_post_filter(fb2_result *r, const fb2_params *p, const char *name);
+/* statistics.rs:30-47 / filtering.rs:154-195 (exposed for parity tests) */
+uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n, double filter_level);
+
+/* ---- sketch_stream (lib.rs:51-94) over a host buffer -------------------------------------- */
+int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
+                      const fb2_filter *f, fb2_result *out);
+/* ---- sketch_files (lib.rs:29-49): outs[i] <- paths[i], input order; "-" is stdin ---------- */
+int fb2_sketch_files(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
+                     fb2_result *outs);
+
+/* ---- raw_distance (distance.rs:66-126), integer part, batched ----------------------------- */
+typedef struct fb2_pair_out {
+    uint32_t common; /* |A n B| up to the stopping point */
+    uint32_t i;      /* query hashes consumed */
+    uint32_t j;      /* reference hashes consumed */
+} fb2_pair_out;
+/* hashes: n_sk sketches, sketch s occupies hashes[s*stride .. s*stride+lens[s]) ascending.
+ * For pair p: query q_idx[p], reference r_idx[p].  scale as raw_distance's (0 = none).
+ * The f64 epilogue (containment, jaccard, mash distance) stays on the host: fb2_distance_finish. */
+int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
+                   double scale, const uint32_t *q_idx, const uint32_t *r_idx, size_t n_pairs,
+                   fb2_pair_out *out, int32_t device);
+/* All ordered pairs (q, r), q in [q0,q1), r in [0,n_sk): out[(q-q0)*n_sk + r]. */
+int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
+                       double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device);
+/* distance.rs:117-125 and :35-41 from the integers of one pair. */
+void fb2_distance_finish(const fb2_pair_out *p, uint8_t kmer_length, double *containment,
+                         double *jaccard, double *mash_distance, uint64_t *common_hashes,
+                         uint64_t *total_hashes);
+
+/* ---- misc --------------------------------------------------------------------------------- */
+const char *fb2_last_error(void);
+int fb2_device_count(void);
+const char *fb2_version(void);
+
+/* Deterministic synthetic inputs, written into caller memory.  Return bytes
+ * written, or the required size when out == NULL. */
+size_t fb2_synth_genome(uint8_t *out, size_t n_bases, uint64_t seed); /* ACGT, no framing */
+size_t fb2_synth_fasta(uint8_t *out, size_t cap, size_t n_bases, uint32_t n_records,
+                       uint32_t line_width, double lower_frac, double n_frac, uint64_t seed);
+size_t fb2_synth_fastq(uint8_t *out, size_t cap, const uint8_t *genome, size_t genome_len,
+                       uint64_t n_reads, uint32_t read_len, double err_rate, uint64_t seed,
+                       uint64_t first_read_id, uint64_t *n_bases_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FINCH_B200_H */

@@ -1,0 +1,312 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle.
+Integer / byte work => bit-exact: identical hash lists, counts, extra_counts, k-mers, totals."""
+import os
+
+import numpy as np
+import pytest
+
+import gen
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def assert_same(fbres, ora, k):
+    h, c, x, km, seq_len, n_kmers, fmt = fbres
+    assert len(h) == len(ora["hashes"]), (len(h), len(ora["hashes"]))
+    assert np.array_equal(h, ora["hashes"])
+    assert np.array_equal(c, ora["counts"])
+    assert np.array_equal(x, ora["extras"])
+    assert [km[i, :k].tobytes() for i in range(len(h))] == ora["kmers"]
+
+
+def oracle_sketch(oracle, data, kind, size, k, seed, scale=0.001):
+    """records through fo_process; returns to_vec + totals."""
+    s = oracle.Sketcher.mash(size, k, seed) if kind == "mash" else oracle.Sketcher.scaled(size, scale, k, seed)
+    rc, fmt, recs = oracle.parse_fastx(data)
+    assert rc == oracle.OK
+    for r in recs:
+        s.process(r)
+    return s.to_vec(), s.total_bases_and_kmers(), fmt
+
+
+def gpu_sketch(fb, data, kind, size, k, seed, scale=0.001, pieces=None):
+    sp = fb.SketchParams.mash(size, size, False, k, seed) if kind == "mash" else fb.SketchParams.scaled(size, k, scale, seed)
+    with sp.create_sketcher() as s:
+        if pieces is None:
+            s.feed_fastx(data, final=True)
+        else:
+            pos = 0
+            for p in pieces:
+                s.feed_fastx(data[pos:pos + p], final=False)
+                pos += p
+            s.feed_fastx(data[pos:], final=True)
+        return s.to_arrays(), s.total_bases_and_kmers(), s.format()
+
+
+# ---- the reference's own unit tests, through the mirrored API ----------------------------------
+def _push4(q):
+    q.push(b"ca", 0); q.push(b"cc", 1); q.push(b"ac", 0); q.push(b"ac", 1)
+    return q.to_vec(2)
+
+
+@pytest.mark.parametrize("mk", ["mash", "scaled1", "scaled1000"])
+def test_minhashkmers(fb, mk):  # mash.rs:115-134, scaled.rs:118-161
+    q = {"mash": lambda: fb.MashSketcher(3, 2, 42), "scaled1": lambda: fb.ScaledSketcher(3, 1.0, 2, 42),
+         "scaled1000": lambda: fb.ScaledSketcher(3, 0.001, 2, 42)}[mk]()
+    a = _push4(q)
+    assert [e.kmer for e in a] == [b"cc", b"ca", b"ac"]
+    assert [(e.count, e.extra_count) for e in a] == [(1, 1), (1, 0), (2, 1)]
+    assert a[0].hash < a[1].hash < a[2].hash
+    assert q.total_bases_and_kmers() == (0, 4)
+
+
+def test_minhashkmers_eviction(fb):  # scaled.rs:163-176
+    q = fb.ScaledSketcher(1, 0.01, 4, 42)
+    q.push(b"AAAA", 0); q.push(b"AGTA", 0); q.push(b"CCCC", 1); q.push(b"ATAA", 0)
+    a = q.to_vec(4)
+    assert len(a) == 3 and all(e.kmer != b"AAAA" for e in a)
+
+
+def test_minhashkmers_pure_scaled_empty(fb):  # scaled.rs:178-200
+    assert _push4(fb.ScaledSketcher(0, 0.001, 2, 42)) == []
+
+
+def test_pure_scaled_property(fb):  # scaled.rs:202-213
+    rng = np.random.default_rng(11)
+    seq = gen.rand_seq(rng, 700)
+    q = fb.ScaledSketcher(0, 1.0 / 100.0, 2, 42)
+    for i in range(len(seq) - 3):
+        q.push(seq[i:i + 4], 0)
+    assert all(e.hash <= (2**64 - 1) // 100 for e in q.to_vec(4))
+
+
+def test_longer_sequence_seed42(fb):  # mash.rs:136-154
+    q = fb.MashSketcher(100, 21, 42)
+    q.process(b"ACACGGAAATCCTCACGTCGCGGCGCCGGGC")
+    assert [e.hash for e in q.to_vec()] == [
+        3186265289206375993, 3197567229193635484, 5157287830980272133, 7515070071080094037,
+        9123665698461883699, 9650810550987401968, 10462414310441547028, 12872951831549606632,
+        13584836512372089324, 14093285637546356047, 16069721578136260683]
+    assert q.total_bases_and_kmers() == (31, 11)
+
+
+KC_KMERS = [b"ATGCTAGCTACGTAACGTCGC", b"CAGTCGATCGATCGTAGCTGA", b"CTCAGATGCTGAGCCGGTCTA",
+            b"GCTAGCTAGCATCGCTAGCTA", b"GACTAGCTAGCTAGCTAGCGA", b"CGCTAGCTACGATCGATCGAC",
+            b"TAATTTATACGGGCCTATTAA", b"GCATCAGCTAGCATCGCTGTA", b"AGCCGGTCTACTACTACACAT",
+            b"AAGGCCTAACTTAATAGGCCC"]
+
+
+@pytest.mark.parametrize("kind", ["mash", "scaled"])
+def test_cli_golden_query_fa(fb, kind):  # cli/tests/test_cli.rs:80-149
+    data = open(os.path.join(GOLD, "query.fa"), "rb").read()
+    sp = fb.SketchParams.from_cli(kind, n_hashes=10, scale=0.001)
+    fp = fb.FilterParams(None, (None, None), 1.0 * 21 / 100, 0.1)
+    sk = fb.sketch_stream(data, "tests/data/query.fa", sp, fp)
+    assert [sk.kmer_bytes(i) for i in range(len(sk))] == KC_KMERS
+    assert sk.num_valid_kmers == 339 and sk.seq_length == 405
+    assert sk.format == fb.FORMAT_FASTA and sk.filter_params.filter_on is False
+
+
+# ---- randomized parity against the oracle ------------------------------------------------------
+CASES = []
+for i, (kind, size, k) in enumerate([("mash", 50, 21), ("mash", 1000, 21), ("mash", 7, 5), ("mash", 300, 31),
+                                     ("mash", 100, 32), ("mash", 100, 16), ("mash", 64, 1), ("scaled", 20, 21),
+                                     ("scaled", 0, 11), ("scaled", 500, 31), ("mash", 100000, 13)]):
+    CASES.append((i, kind, size, k))
+
+
+@pytest.mark.parametrize("case,kind,size,k", CASES)
+@pytest.mark.parametrize("fmt", ["fasta", "fasta_crlf_ragged", "fastq", "fastq_crlf"])
+def test_random_small(fb, oracle, case, kind, size, k, fmt):
+    rng = np.random.default_rng(100 * case + len(fmt))
+    if fmt == "fasta":
+        data = gen.fasta(rng, n_records=5, max_len=3000, width=70, messy=0.01)
+    elif fmt == "fasta_crlf_ragged":
+        data = gen.fasta(rng, n_records=7, max_len=800, width=25, messy=0.03, crlf=True, blank_lines=True,
+                         ragged=True, final_newline=bool(case % 2))
+    elif fmt == "fastq":
+        data = gen.fastq(rng, n_records=60, max_len=250, messy=0.01, final_newline=bool(case % 2))
+    else:
+        data = gen.fastq(rng, n_records=40, max_len=120, messy=0.05, crlf=True)
+    scale = 0.05
+    ovec, ototals, ofmt = oracle_sketch(oracle, data, kind, size, k, 7, scale)
+    gres, gtotals, gfmt = gpu_sketch(fb, data, kind, size, k, 7, scale)
+    assert gfmt == ofmt
+    assert gtotals == ototals
+    assert_same(gres, ovec, k)
+
+
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+def test_chunk_seams_anywhere(fb, oracle, fmt):
+    rng = np.random.default_rng(77)
+    data = (gen.fasta(rng, n_records=4, max_len=1500, width=40, messy=0.02, crlf=True, ragged=True)
+            if fmt == "fasta" else gen.fastq(rng, n_records=30, max_len=150, crlf=False))
+    ovec, ototals, _ = oracle_sketch(oracle, data, "mash", 200, 21, 0)
+    for trial in range(4):
+        cuts = sorted(rng.integers(1, 40, size=int(rng.integers(1, 60))).tolist())
+        pieces = [c for c in cuts if c > 0]
+        if sum(pieces) >= len(data):
+            pieces = [1, 2, 3]
+        gres, gtotals, _ = gpu_sketch(fb, data, "mash", 200, 21, 0, pieces=pieces)
+        assert gtotals == ototals
+        assert_same(gres, ovec, 21)
+
+
+def test_process_records_api(fb, oracle):
+    """SketchScheme::process per record (mash.rs:67-80), records with newlines / lowercase / N."""
+    rng = np.random.default_rng(5)
+    recs = [gen.rand_seq(rng, int(rng.integers(0, 400)), 0.03) for _ in range(50)]
+    recs[3] = recs[3][:50] + b"\n" + recs[3][50:] + b"\r\n"
+    recs[7] = b""
+    o = oracle.Sketcher.mash(150, 21, 3)
+    g = fb.MashSketcher(150, 21, 3)
+    for r in recs:
+        o.process(r); g.process(r)
+    assert g.total_bases_and_kmers() == o.total_bases_and_kmers()
+    ov = o.to_vec()
+    assert_same(g.to_arrays(), ov, 21)
+    # to_vec is non-destructive: keep going
+    more = gen.rand_seq(rng, 5000)
+    o.process(more); g.process(more)
+    assert_same(g.to_arrays(), o.to_vec(), 21)
+    assert g.total_bases_and_kmers() == o.total_bases_and_kmers()
+
+
+@pytest.mark.parametrize("kind,size,k,scale", [("mash", 1000, 21, 0), ("mash", 200000, 21, 0),
+                                               ("scaled", 1000, 31, 0.001), ("scaled", 0, 21, 0.01)])
+def test_medium_fasta(fb, oracle, kind, size, k, scale):
+    """~3 Mbp multi-record FASTA with lowercase and N runs (C1/C4-shaped, reduced)."""
+    data = fb.synth_fasta(3_000_000, n_records=3, line_width=80, lower_frac=0.02, n_frac=0.01, seed=4).tobytes()
+    ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, k, 0, scale or 0.001)
+    gres, gtotals, _ = gpu_sketch(fb, data, kind, size, k, 0, scale or 0.001)
+    assert gtotals == ototals
+    assert_same(gres, ovec, k)
+
+
+def test_medium_fastq_with_coverage(fb, oracle):
+    """C2-shaped, reduced: 40k x 150 bp reads from a 20 kbp genome (300x), 0.5% errors, heap 200000."""
+    genome = fb.synth_genome(20_000, 2)
+    data, nb = fb.synth_fastq(genome, 40_000, 150, 0.005, 3)
+    data = data.tobytes()
+    ovec, ototals, _ = oracle_sketch(oracle, data, "mash", 200000, 21, 0)
+    gres, gtotals, _ = gpu_sketch(fb, data, "mash", 200000, 21, 0)
+    assert ototals[0] == nb and gtotals == ototals
+    assert_same(gres, ovec, 21)
+    # ...and through sketch_stream with the CLI's filter defaults (-f): identical filtered sketch
+    sp_o = oracle.mash_params(200000, 1000, False, 21, 0)
+    rc, osk = oracle.sketch_stream(data, sp_o, oracle.make_filter(True, (None, None), 0.21, 0.1))
+    assert rc == oracle.OK
+    sk = fb.sketch_stream(data, "reads.fq", fb.SketchParams.mash(200000, 1000, False, 21, 0),
+                          fb.FilterParams(True, (None, None), 0.21, 0.1))
+    assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+    assert np.array_equal(sk.extra_counts, osk["extras"])
+    assert sk.filter_params.abun_filter[0] == osk["min_copies"]
+    assert len(sk) == 1000
+
+
+def test_multi_chunk_stream(fb, oracle, monkeypatch):
+    """Chunks of 1 MiB so one stream crosses many chunk seams inside the engine."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    genome = fb.synth_genome(300_000, 9)
+    data, _ = fb.synth_fastq(genome, 25_000, 100, 0.01, 5)
+    data = data.tobytes()
+    assert len(data) > 5 * (1 << 20)
+    ovec, ototals, _ = oracle_sketch(oracle, data, "mash", 5000, 21, 0)
+    gres, gtotals, _ = gpu_sketch(fb, data, "mash", 5000, 21, 0)
+    assert gtotals == ototals
+    assert_same(gres, ovec, 21)
+    # device-resident feed of the same bytes
+    import torch
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    with fb.SketchParams.mash(5000, 5000, False, 21, 0).create_sketcher() as s:
+        s.feed_device(t.data_ptr(), t.numel(), final=True)
+        assert s.total_bases_and_kmers() == ototals
+        assert_same(s.to_arrays(), ovec, 21)
+
+
+def test_errors(fb):
+    sp = fb.SketchParams.mash(10, 10, False, 21, 0)
+    with pytest.raises(fb.FinchError) as e:
+        fb.sketch_stream(b"ACGT\n", "x", sp, fb.FilterParams())
+    assert e.value.code == fb.EFORMAT
+    with pytest.raises(fb.FinchError) as e:
+        fb.sketch_stream(b"", "x", sp, fb.FilterParams())
+    assert e.value.code == fb.EEMPTY
+    with pytest.raises(fb.FinchError) as e:
+        fb.sketch_stream(b"@r1\nACGT\n+\n", "x", sp, fb.FilterParams())       # truncated record
+    assert e.value.code == fb.ERECORD
+    with pytest.raises(fb.FinchError) as e:
+        fb.sketch_stream(b"@r1\nACGT\n-\nIIII\n", "x", sp, fb.FilterParams())  # bad separator
+    assert e.value.code == fb.ERECORD
+    with pytest.raises(fb.FinchError) as e:                                      # strict: too few k-mers
+        fb.sketch_stream(b">a\nACGTACGTACGTACGTACGTACGTAAAC\n", "few", sp, fb.FilterParams())
+    assert e.value.code == fb.ETOOFEW and "few had too few kmers (" in e.value.message
+    with pytest.raises(fb.FinchError) as e:
+        fb.SketchParams.mash(10, 10, False, 33, 0).create_sketcher()
+    assert e.value.code == fb.EUNSUPPORTED
+    with pytest.raises(fb.FinchError) as e:
+        fb.sketch_files(["/nonexistent/file.fa"], sp, fb.FilterParams())
+    assert e.value.code == fb.EIO and "No such file or directory" in e.value.message  # test_cli.rs:9-18
+
+
+def test_sketch_files(fb, oracle, tmp_path):
+    rng = np.random.default_rng(21)
+    paths, datas = [], []
+    for i in range(5):
+        d = gen.fasta(rng, n_records=2, max_len=4000, width=80) if i % 2 == 0 else gen.fastq(rng, n_records=50)
+        p = tmp_path / f"in{i}.{'fa' if i % 2 == 0 else 'fq'}"
+        p.write_bytes(d)
+        paths.append(str(p)); datas.append(d)
+    sp = fb.SketchParams.mash(400, 20, True, 21, 0)
+    fp = fb.FilterParams(None, (None, None), 0.21, 0.1)
+    sks = fb.sketch_files(paths, sp, fp)
+    for p, d, sk in zip(paths, datas, sks):
+        rc, osk = oracle.sketch_stream(d, oracle.mash_params(400, 20, True, 21, 0),
+                                       oracle.make_filter(None, (None, None), 0.21, 0.1))
+        assert rc == oracle.OK and sk.name == p
+        assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+        assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+        assert sk.filter_params.filter_on == osk["filter_on"]
+
+
+# ---- dist -----------------------------------------------------------------------------------------
+def test_raw_distance_kats(fb):  # distance.rs:188-242
+    rd = fb.raw_distance
+    assert rd([0, 1, 2], [1, 2]) == (2. / 2., 2. / 3., 2, 3)
+    assert rd([0, 2], [1, 2]) == (1. / 2., 1. / 3., 1, 3)
+    assert rd([0, 1], [2, 3]) == (0., 0., 0, 2)
+    assert rd([], []) == (0., 1., 0, 0)
+    assert rd([], [5]) == (0., 1., 0, 0)
+    assert rd([10, 15, 20], [15, 20], 1e-18) == (1., 2. / 3., 2, 3)
+    assert rd([5, 10, 15], [5, 10], 1e-18) == (1., 2. / 3., 2, 3)
+    assert rd([5, 10, 15, 20], [5, 10], 1e-18) == (1., 2. / 3., 2, 3)
+    assert rd([5, 10], [5, 10, 15, 20], 1e-18) == (2. / 3., 2. / 3., 2, 3)
+
+
+def test_dist_batch_random(fb, oracle):
+    rng = np.random.default_rng(8)
+    pool = np.unique(rng.integers(0, 2**63, size=4000, dtype=np.uint64))
+    sk = [np.sort(rng.choice(pool, size=int(rng.integers(0, 1000)), replace=False)) for _ in range(24)]
+    sk.append(np.array([2**64 - 1], np.uint64)); sk.append(np.zeros(0, np.uint64))
+    n = len(sk)
+    q, r = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    for scale in (0.0, 0.3):
+        out = fb.dist_batch(sk, q.ravel(), r.ravel(), scale)
+        mat, lens, stride = fb._pack(sk)
+        allp = fb.dist_all_pairs(mat, lens, scale)
+        for p, (a, b) in enumerate(zip(q.ravel(), r.ravel())):
+            cont, jac, com, tot = oracle.raw_distance(sk[a], sk[b], scale)
+            c, i, j = (int(v) for v in out[p])
+            assert (c, i - c + j) == (com, tot), (a, b, scale)
+            assert fb._finish_pair(out[p], 21)[:2] == (cont, jac)
+            assert tuple(allp[a, b]) == (c, i, j)
+
+
+def test_distance_scaled_end_to_end(fb):  # distance.rs:312-337
+    def mk():
+        q = fb.ScaledSketcher(3, 0.001, 2, 42)
+        q.push(b"ca", 0); q.push(b"cc", 1); q.push(b"ac", 0); q.push(b"ac", 1)
+        return q.to_sketch()
+    d = fb.distance(mk(), mk(), False)
+    assert (d.jaccard, d.containment, d.common_hashes) == (1.0, 1.0, 3)
