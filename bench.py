@@ -337,6 +337,9 @@ def main():
                      "parse_kernels_ms_per_step": parse_ms / 2,
                      "note": "integer-issue-bound, not HBM-bound (~190 SASS instr per k-mer); see DESIGN.md"},
         "bit_exact": None,
+        "aux": {"prunes_per_step": stats_res["prunes"] / args.steps, "chunks_per_step": stats_res["chunks"] / args.steps,
+                "hash_launches_per_step": stats_res["hash_launches"] / args.steps,
+                "kernel_launches_per_step": stats_res["kernel_launches"] / args.steps},
     }
 
     # ---- CPU baseline (oracle port, 1 core, bounded sample) + bit-exactness on that sample ------

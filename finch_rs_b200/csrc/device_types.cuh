@@ -14,17 +14,16 @@ constexpr uint32_t HASH_TILE = HASH_THREADS * HASH_W;  // symbols per block
 
 enum ParseMode : int { MODE_LINES = 0, MODE_FASTA = 1, MODE_FASTQ = 2 };
 
-// Per-tile transducer summary: for every possible state at the tile's first byte, the state
-// after its last byte and the number of symbols the tile emits.
-//   FASTQ: state = phase (0 header, 1 sequence, 2 '+', 3 quality) of the current line (4 states)
-//   FASTA: state = 0 sequence line / 1 header line (2 states);  LINES: 1 state
-struct TileSummary {
-    uint32_t next;     // 2 bits per start state
-    uint32_t cnt[4];   // symbols emitted per start state
-};
-struct TilePrefix {
-    uint32_t state_in;
-    uint32_t sym_off;  // chunk-relative symbol offset of the tile's first symbol
+// Geometry of one chunk: tiles of 4 KiB grouped into supertiles; every supertile owns a symbol
+// region of st_bytes (+ SYM_FRONT pad in front of it) in the symbol buffer.
+struct ChunkGeom {
+    uint32_t len;            // raw bytes in the chunk
+    uint32_t n_tiles;        // ceil(len / TILE_BYTES)
+    uint32_t st_tiles;       // tiles per supertile
+    uint32_t n_st;           // supertiles
+    uint32_t st_bytes;       // st_tiles * TILE_BYTES == region capacity in symbols
+    uint32_t region_stride;  // st_bytes + SYM_FRONT
+    uint32_t hash_tiles;     // hash blocks per region = ceil(st_bytes / HASH_TILE)
 };
 
 // Parser + stream state that persists across chunks (device resident; mirrored to the host
@@ -34,14 +33,12 @@ struct ParseCarry {
     uint32_t prev1, prev2;   // last / second-to-last raw byte of the stream so far
     uint32_t error;          // sticky device-side error bits
     uint64_t raw_total;      // raw bytes consumed
-    uint64_t ordinal;        // symbols (+ pushed k-mers) emitted so far == next position id
     uint64_t total_bases;    // Sum of record sequence().len() (wrapping arithmetic)
     uint64_t n_records;
     uint64_t first_bad_pos;  // FASTQ: min raw pos of a line start failing the '@' / '+' check
     uint64_t last_sig;       // FASTQ: max ((raw pos + 1) << 2 | phase) over bytes that are not CR/LF
     uint64_t chunk_raw_base; // raw_total before the current chunk
-    uint64_t chunk_ord_base; // ordinal before the current chunk
-    uint32_t chunk_syms;     // symbols produced by the current chunk
+    uint32_t chunk_syms;     // symbols produced by the current chunk (all regions)
     uint32_t cprev1, cprev2; // prev1 / prev2 as they were at the start of the current chunk
     uint32_t pad;
 };

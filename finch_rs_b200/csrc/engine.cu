@@ -94,12 +94,14 @@ struct fb2_sketcher {
     bool rawfree_pending[2] = {false, false};
 
     size_t chunk_bytes = 0;
-    DevBuf d_raw[2], d_sym, d_sums, d_pre, d_carry, d_state;
+    DevBuf d_raw[2], d_sym, d_stmap, d_ststate, d_rcount, d_tail, d_carry, d_state;
+    int tail_sel = 0;               // which half of d_tail holds the symbols carried into the next chunk
+    uint64_t ordinal = 0;           // next position id (symbols of all regions so far + pushed k-mers)
     DevBuf log_hash, log_kmer, log_posx;
     uint32_t log_cap = 0;
     Table tab[2];
     int cur = 0;
-    DevBuf sort_keys, sort_slots, sort_tkeys, sort_tslots, sort_hist;
+    DevBuf sort_keys, sort_slots, sort_tkeys, sort_tslots, sort_hist, d_bins;
     DevBuf out_hash, out_cnt, out_ext, out_kmer, out_posx;
     DevBuf d_push_bytes, d_push_offs, d_push_extra;
 
@@ -170,9 +172,10 @@ static int reset_sketch_state(fb2_sketcher *s) {
     s->h_carry->first_bad_pos = ~0ULL;
     TRY(push_carry(s));
     launch_table_clear(s->tab[s->cur].view(), s->st);
-    launch_fill_bytes(s->d_sym.as<uint8_t>(), SYM_FRONT, SYM_BREAK, s->st);
+    launch_fill_bytes(s->d_tail.as<uint8_t>(), 64, SYM_BREAK, s->st);
     s->stats.kernel_launches += 2;
     CU(cudaStreamSynchronize(s->st));
+    s->tail_sel = 0; s->ordinal = 0;
     s->format = FB2_FORMAT_UNKNOWN; s->stream_open = false;
     s->lines_bases = 0; s->total_kmers = 0; s->stage_fill = 0; s->stage_mode = -1;
     s->next_launch = 32u * HASH_TILE;
@@ -231,6 +234,7 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
         if ((rc = s->d_carry.ensure(sizeof(ParseCarry))) != FB2_OK) break;
         if ((rc = s->d_state.ensure(sizeof(SketchState))) != FB2_OK) break;
         if ((rc = s->d_sym.ensure(SYM_FRONT + 4096)) != FB2_OK) break;
+        if ((rc = s->d_tail.ensure(64)) != FB2_OK) break;
         if (cudaHostAlloc((void **)&s->h_carry, sizeof(ParseCarry), cudaHostAllocDefault) != cudaSuccess ||
             cudaHostAlloc((void **)&s->h_state, sizeof(SketchState), cudaHostAllocDefault) != cudaSuccess) {
             rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed"); break;
@@ -264,9 +268,10 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     if (s->ev_t1) cudaEventDestroy(s->ev_t1);
     if (s->ev_p0) cudaEventDestroy(s->ev_p0);
     if (s->ev_p1) cudaEventDestroy(s->ev_p1);
-    s->d_sym.release(); s->d_sums.release(); s->d_pre.release(); s->d_carry.release(); s->d_state.release();
+    s->d_sym.release(); s->d_stmap.release(); s->d_ststate.release(); s->d_rcount.release(); s->d_tail.release();
+    s->d_carry.release(); s->d_state.release();
     s->log_hash.release(); s->log_kmer.release(); s->log_posx.release();
-    s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release();
+    s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release(); s->d_bins.release();
     s->out_hash.release(); s->out_cnt.release(); s->out_ext.release(); s->out_kmer.release(); s->out_posx.release();
     s->d_push_bytes.release(); s->d_push_offs.release(); s->d_push_extra.release();
     if (s->h_carry) cudaFreeHost(s->h_carry);
@@ -304,10 +309,23 @@ static int sort_table(fb2_sketcher *s, uint32_t *n_out) {
     return FB2_OK;
 }
 static int prune(fb2_sketcher *s, uint32_t need_room) {
-    uint32_t n = 0;
-    TRY(sort_table(s, &n));
-    const uint32_t keep = s->h_state->keep_count;
-    // new capacity: keep + the room the caller needs must stay under 3/4 load
+    // Histogram-select a bin-boundary threshold that keeps >= size keys, gather the survivors,
+    // rebuild them into the other table (grown when needed) and commit the lower threshold.
+    const uint32_t occ_ub = s->tab[s->cur].cap + 1;
+    TRY(ensure_sort(s, occ_ub));
+    TRY(s->d_bins.ensure(4096 * sizeof(uint32_t)));
+    SketchState *dst = (SketchState *)s->d_state.p;
+    const unsigned long long thr = s->h_state->threshold;  // mirror may be stale-high: still a valid bound
+    uint32_t bits = 0;
+    while (bits < 64 && (thr >> bits) != 0ULL) ++bits;
+    const uint32_t shift = bits > 12 ? bits - 12 : 0;
+    launch_prune_select(s->tab[s->cur].view(), dst, shift, s->d_bins.as<uint32_t>(), s->scaled ? 1 : 0,
+                        (!s->scaled && s->size == 0) ? 0ULL : s->size, s->max_hash,
+                        s->sort_keys.as<unsigned long long>(), s->sort_slots.as<uint32_t>(), s->st);
+    s->stats.kernel_launches += 4;
+    TRY(pull_state(s));
+    uint32_t keep = s->h_state->gather_count;
+    if (!s->scaled && s->size == 0) keep = 0;  // MashSketcher::new(0, ..) keeps nothing
     uint32_t cap = s->tab[s->cur].cap;
     while ((uint64_t)keep + need_room > (uint64_t)cap / 4 * 3 || (uint64_t)keep * 2 > cap) {
         if (cap >= (1u << 30)) return fb2_fail(FB2_ENOMEM, "sketch table would exceed 2^30 slots");
@@ -316,8 +334,8 @@ static int prune(fb2_sketcher *s, uint32_t need_room) {
     const int other = s->cur ^ 1;
     TRY(ensure_table(s, other, cap));
     launch_rebuild(s->sort_keys.as<unsigned long long>(), s->sort_slots.as<uint32_t>(), keep,
-                   s->tab[s->cur].view(), s->tab[other].view(), (SketchState *)s->d_state.p, s->st);
-    launch_commit_threshold((SketchState *)s->d_state.p, s->st);
+                   s->tab[s->cur].view(), s->tab[other].view(), dst, s->st);
+    launch_commit_threshold(dst, s->st);
     s->stats.kernel_launches += 4;
     s->cur = other;
     s->stats.prunes++;
@@ -326,15 +344,19 @@ static int prune(fb2_sketcher *s, uint32_t need_room) {
 }
 
 // Absorb log[0, cnt) into the table, pruning / growing so the table never passes 3/4 load.
+// Between pulls the host only knows an upper bound of the occupancy (every absorbed entry may be
+// a new key); it fetches the exact value before deciding to prune.
 static int absorb_log(fb2_sketcher *s, uint32_t cnt) {
     uint32_t i = 0;
+    bool exact = true;  // h_state->occupied is exact right after a pull
     while (i < cnt) {
         const uint32_t cap = s->tab[s->cur].cap;
         const uint32_t limit = cap / 4 * 3;
         const uint32_t occ = s->h_state->occupied;
-        uint32_t room = occ < limit ? limit - occ : 0;
+        const uint32_t room = occ < limit ? limit - occ : 0;
         const uint32_t left = cnt - i;
         if (room < std::min(left, cap / 4)) {
+            if (!exact) { TRY(pull_state(s)); exact = true; continue; }
             TRY(prune(s, std::min(left, cap / 4)));
             continue;
         }
@@ -342,33 +364,55 @@ static int absorb_log(fb2_sketcher *s, uint32_t cnt) {
         launch_absorb(log_view(s), i, i + m, s->tab[s->cur].view(), (SketchState *)s->d_state.p, s->st);
         s->stats.kernel_launches += 2;
         i += m;
-        TRY(pull_state(s));
+        s->h_state->occupied = occ + m;  // upper bound until the next pull
+        exact = false;
     }
     // keep the threshold moving: first finite threshold as soon as `size` keys exist, then at half load
-    const uint32_t occ = s->h_state->occupied;
-    const bool infinite = s->h_state->threshold == ~0ULL;
-    const bool can_lower = s->size > 0 && occ >= s->size;
-    if ((infinite && can_lower) || occ > s->tab[s->cur].cap / 2) TRY(prune(s, 0));
+    auto wants_prune = [&]() {
+        const uint32_t occ = s->h_state->occupied;
+        const bool infinite = s->h_state->threshold == ~0ULL;
+        const bool can_lower = s->size > 0 && occ >= s->size;
+        return (infinite && can_lower) || occ > s->tab[s->cur].cap / 2;
+    };
+    if (wants_prune()) {
+        if (!exact) TRY(pull_state(s));
+        if (wants_prune()) TRY(prune(s, 0));
+    }
     return FB2_OK;
 }
 
 // ---- one chunk of raw bytes resident in HBM ---------------------------------------------------------
-static int hash_range(fb2_sketcher *s, uint32_t upper) {
-    uint8_t *sym0 = s->d_sym.as<uint8_t>() + SYM_FRONT;
+static ChunkGeom make_geom(uint32_t len) {
+    ChunkGeom g;
+    g.len = len;
+    g.n_tiles = cdivu(len, TILE_BYTES);
+    uint32_t stt = g.n_tiles / 592u;   // aim at >= 4 blocks per SM before growing supertiles
+    if (stt < 1) stt = 1;
+    if (stt > 32) stt = 32;
+    g.st_tiles = stt;
+    g.n_st = cdivu(g.n_tiles, stt);
+    g.st_bytes = stt * TILE_BYTES;
+    g.region_stride = g.st_bytes + SYM_FRONT;
+    g.hash_tiles = cdivu(g.st_bytes, HASH_TILE);
+    return g;
+}
+
+// Hash the regions of the current chunk in launches sized so the candidate log cannot overflow
+// unnoticed, absorbing the log after each launch.
+static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base) {
     SketchState *dst = (SketchState *)s->d_state.p;
-    uint32_t pos = 0;
+    const uint32_t total_blocks = g.n_st * g.hash_tiles;
+    uint32_t b = 0;
     bool known = false;
-    uint32_t n_sym = upper;
-    while (pos < n_sym) {
-        uint32_t n = std::max(s->next_launch, HASH_TILE);
-        n = (n + HASH_TILE - 1) / HASH_TILE * HASH_TILE;
-        if (n > n_sym - pos) n = (n_sym - pos + HASH_TILE - 1) / HASH_TILE * HASH_TILE;
-        // zero the per-launch counters (log_count, launch_kmers)
-        s->h_state->log_count = 0; s->h_state->launch_kmers = 0;
+    double fill = 1.0;  // symbols per launched position
+    while (b < total_blocks) {
+        uint32_t nb = std::max<uint32_t>(s->next_launch / HASH_TILE, 1u);
+        nb = std::min(nb, total_blocks - b);
         CU(cudaMemsetAsync(&dst->log_count, 0, sizeof(unsigned int), s->st));
         CU(cudaMemsetAsync(&dst->launch_kmers, 0, sizeof(unsigned long long), s->st));
         if (s->timing) CU(cudaEventRecord(s->ev_t0, s->st));
-        launch_hash(s->k, sym0, pos, pos + n, (const ParseCarry *)s->d_carry.p, dst, log_view(s), s->prm.hash_seed, s->st);
+        launch_hash(s->k, s->d_sym.as<uint8_t>(), g, b, b + nb, s->d_rcount.as<uint32_t>(), ord_base, dst, log_view(s),
+                    s->prm.hash_seed, s->st);
         if (s->timing) CU(cudaEventRecord(s->ev_t1, s->st));
         s->stats.kernel_launches++; s->stats.hash_launches++;
         TRY(pull_state(s));
@@ -377,20 +421,24 @@ static int hash_range(fb2_sketcher *s, uint32_t upper) {
             CU(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
             s->stats.hash_kernel_ms += ms;
         }
-        if (!known) { n_sym = s->h_carry->chunk_syms; known = true; }
+        if (!known) {
+            known = true;
+            s->stats.hash_symbols += s->h_carry->chunk_syms;
+            fill = std::max(1e-6, (double)s->h_carry->chunk_syms / ((double)total_blocks * HASH_TILE));
+            if (s->h_carry->chunk_syms == 0) break;  // nothing to hash in this chunk
+        }
         const uint32_t cnt = s->h_state->log_count;
         if (cnt > s->log_cap) {  // log overflowed: nothing committed, redo this range in smaller launches
-            s->next_launch = std::max<uint32_t>(HASH_TILE, std::min(n / 4, s->log_cap / HASH_TILE * HASH_TILE));
+            s->next_launch = std::max<uint32_t>(HASH_TILE, std::min((nb * HASH_TILE) / 4, s->log_cap / HASH_TILE * HASH_TILE));
             continue;
         }
-        const uint32_t done = pos >= n_sym ? 0 : std::min(n, n_sym - pos);
         s->total_kmers += s->h_state->launch_kmers;
-        s->stats.hash_symbols += done;
         TRY(absorb_log(s, cnt));
-        pos += n;
+        b += nb;
         // next launch: aim the candidate count at a quarter of the log
-        const double frac = done ? std::max((double)cnt, 1.0) / (double)done : 1.0;
-        double next = (double)(s->log_cap / 4) / frac;
+        const double walked = std::max(1.0, (double)nb * HASH_TILE * fill);
+        const double frac = std::max((double)cnt, 1.0) / walked;           // candidates per symbol
+        double next = (double)(s->log_cap / 4) / frac / fill;               // launched positions
         if (next > 2147483648.0) next = 2147483648.0;
         s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (uint32_t)next);
     }
@@ -399,34 +447,28 @@ static int hash_range(fb2_sketcher *s, uint32_t upper) {
 
 static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mode, int rawbuf /* -1: not ours */) {
     if (!len) return FB2_OK;
-    const uint32_t n_tiles = cdivu(len, TILE_BYTES);
-    TRY(s->d_sums.ensure((size_t)n_tiles * sizeof(TileSummary)));
-    TRY(s->d_pre.ensure((size_t)n_tiles * sizeof(TilePrefix)));
-    const size_t sym_need = (size_t)SYM_FRONT + len + 2 * HASH_TILE;
-    if (sym_need > s->d_sym.cap) {  // preserve the carried front symbols
-        DevBuf nb;
-        TRY(nb.ensure(sym_need));
-        CU(cudaMemcpyAsync(nb.p, s->d_sym.p, SYM_FRONT, cudaMemcpyDeviceToDevice, s->st));
-        CU(cudaStreamSynchronize(s->st));
-        s->d_sym.release();
-        s->d_sym = nb;
-    }
+    const ChunkGeom g = make_geom(len);
+    TRY(s->d_stmap.ensure((size_t)g.n_st * 4)); TRY(s->d_ststate.ensure((size_t)g.n_st * 4));
+    TRY(s->d_rcount.ensure((size_t)g.n_st * 4));
+    TRY(s->d_sym.ensure((size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + 2 * HASH_TILE));
     ParseCarry *dc = (ParseCarry *)s->d_carry.p;
+    uint8_t *tail_in = s->d_tail.as<uint8_t>() + 32 * s->tail_sel, *tail_out = s->d_tail.as<uint8_t>() + 32 * (s->tail_sel ^ 1);
     if (s->timing) CU(cudaEventRecord(s->ev_p0, s->st));
-    launch_tile_summary(mode, d_raw, len, dc, s->d_sums.as<TileSummary>(), n_tiles, s->st);
-    launch_tile_scan(s->d_sums.as<TileSummary>(), n_tiles, dc, s->d_pre.as<TilePrefix>(), d_raw, len, s->st);
-    launch_pack(mode, d_raw, len, dc, s->d_pre.as<TilePrefix>(), s->d_sym.as<uint8_t>() + SYM_FRONT, n_tiles, s->st);
+    launch_phase(mode, d_raw, g, dc, s->d_stmap.as<uint32_t>(), s->d_ststate.as<uint32_t>(), s->st);
+    launch_pack(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym.as<uint8_t>(), s->d_rcount.as<uint32_t>(),
+                tail_in, tail_out, s->st);
     if (s->timing) CU(cudaEventRecord(s->ev_p1, s->st));
     if (rawbuf >= 0) { CU(cudaEventRecord(s->ev_rawfree[rawbuf], s->st)); s->rawfree_pending[rawbuf] = true; }
-    s->stats.kernel_launches += 3; s->stats.chunks++;
-    TRY(hash_range(s, len));
+    s->tail_sel ^= 1;
+    s->stats.kernel_launches += (mode == MODE_LINES ? 3 : 4); s->stats.chunks++;
+    const uint64_t ord_base = s->ordinal;
+    s->ordinal += (uint64_t)g.n_st * g.st_bytes;
+    TRY(hash_range(s, g, ord_base));
     if (s->timing) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, s->ev_p0, s->ev_p1));
         s->stats.parse_kernel_ms += ms;
     }
-    launch_carry_front(s->d_sym.as<uint8_t>(), dc, s->st);
-    s->stats.kernel_launches++;
     return FB2_OK;
 }
 
@@ -490,7 +532,8 @@ static int flush_push(fb2_sketcher *s) {
     CU(cudaMemsetAsync(&dst->log_count, 0, sizeof(unsigned int), s->st));
     CU(cudaMemsetAsync(&dst->launch_kmers, 0, sizeof(unsigned long long), s->st));
     launch_push_hash(s->d_push_bytes.as<uint8_t>(), s->d_push_offs.as<uint32_t>(), s->d_push_extra.as<uint8_t>(), n,
-                     s->arena_flushed, (ParseCarry *)s->d_carry.p, dst, log_view(s), s->prm.hash_seed, s->st);
+                     s->arena_flushed, s->ordinal, dst, log_view(s), s->prm.hash_seed, s->st);
+    s->ordinal += n;
     s->stats.kernel_launches += 2;
     TRY(pull_state(s));
     s->total_kmers += s->h_state->launch_kmers;
@@ -583,7 +626,7 @@ static int end_stream(fb2_sketcher *s) {
     // a later stream or record must not join this one: break the carried symbols
     c->state = 0; c->prev1 = c->prev2 = '\n';
     TRY(push_carry(s));
-    launch_fill_bytes(s->d_sym.as<uint8_t>(), SYM_FRONT, SYM_BREAK, s->st);
+    launch_fill_bytes(s->d_tail.as<uint8_t>(), 64, SYM_BREAK, s->st);
     s->stats.kernel_launches++;
     s->stream_open = false;
     return rc;

@@ -22,17 +22,20 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 
 template <int K>
 __global__ void __launch_bounds__(HASH_THREADS)
-hash_kernel(const uint8_t *__restrict__ sym,  // symbol 0 of the chunk; SYM_FRONT carried symbols precede it
-            uint32_t s0, uint32_t s1,         // symbol range of this launch (multiples of HASH_TILE)
-            const ParseCarry *__restrict__ carry, SketchState *st, LogView log, int k_rt, uint64_t seed) {
+hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r starts at SYM_FRONT + r * region_stride
+            ChunkGeom g, uint32_t b0,             // first hash block (region-major) of this launch
+            const uint32_t *__restrict__ region_count, uint64_t ord_base, SketchState *st, LogView log,
+            int k_rt, uint64_t seed) {
     const int k = K > 0 ? K : k_rt;
     const uint64_t mask = kmer_mask(k);
-    const uint32_t n_sym = carry->chunk_syms;
-    const uint32_t end = min(s1, n_sym);
-    const uint64_t ord_base = carry->chunk_ord_base;
+    const uint32_t blk = b0 + blockIdx.x;
+    const uint32_t region = blk / g.hash_tiles, lt = blk - region * g.hash_tiles;
+    const uint32_t end = region_count[region];
+    const uint8_t *sym = symbuf + (size_t)SYM_FRONT + (size_t)region * g.region_stride;
+    const uint64_t ord_region = ord_base + (uint64_t)region * g.st_bytes;
     const unsigned long long T = st->threshold;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t p0 = s0 + (blockIdx.x * (uint32_t)HASH_THREADS + threadIdx.x) * (uint32_t)HASH_W;
+    const uint32_t p0 = lt * HASH_TILE + threadIdx.x * (uint32_t)HASH_W;
     // Warp-uniform early exit: a warp's positions are contiguous and ascending.
     if (__all_sync(0xffffffffu, p0 >= end)) return;
 
@@ -76,7 +79,7 @@ hash_kernel(const uint8_t *__restrict__ sym,  // symbol 0 of the chunk; SYM_FRON
                     if (idx < log.cap) {
                         log.hash[idx] = h;
                         log.kmer[idx] = codes;
-                        log.posx[idx] = ((ord_base + p) << 9) | (is_rc ? 1ull : 0ull);
+                        log.posx[idx] = ((ord_region + p) << 9) | (is_rc ? 1ull : 0ull);
                     }
                 }
             }
@@ -90,7 +93,7 @@ hash_kernel(const uint8_t *__restrict__ sym,  // symbol 0 of the chunk; SYM_FRON
 // `push` unit-test surface (mash.rs:34 / scaled.rs:37): hash arbitrary byte strings.
 __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32_t *__restrict__ offs,
                                  const uint8_t *__restrict__ extra, uint32_t n, uint64_t arena_base,
-                                 ParseCarry *carry, SketchState *st, LogView log, uint64_t seed) {
+                                 uint64_t ord_base, SketchState *st, LogView log, uint64_t seed) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t a = offs[i], b = offs[i + 1];
@@ -101,30 +104,26 @@ __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32
         if (idx < log.cap) {
             log.hash[idx] = h;
             log.kmer[idx] = arena_base + i;
-            log.posx[idx] = ((carry->ordinal + i) << 9) | (1ull << 8) | (unsigned long long)extra[i];
+            log.posx[idx] = ((ord_base + i) << 9) | (1ull << 8) | (unsigned long long)extra[i];
         }
     }
 }
-__global__ void push_commit_kernel(ParseCarry *carry, SketchState *st, uint32_t n) {
-    carry->ordinal += n;
-    st->launch_kmers += n;
-}
+__global__ void push_commit_kernel(SketchState *st, uint32_t n) { st->launch_kmers += n; }
 
-void launch_hash(int k, const uint8_t *sym, uint32_t s0, uint32_t s1, const ParseCarry *carry,
-                 SketchState *st, LogView log, uint64_t seed, cudaStream_t stream) {
-    const uint32_t n = s1 - s0;
-    const uint32_t blocks = (n + HASH_TILE - 1) / HASH_TILE;
-    if (!blocks) return;
-    if (k == 21) hash_kernel<21><<<blocks, HASH_THREADS, 0, stream>>>(sym, s0, s1, carry, st, log, k, seed);
-    else if (k == 31) hash_kernel<31><<<blocks, HASH_THREADS, 0, stream>>>(sym, s0, s1, carry, st, log, k, seed);
-    else hash_kernel<0><<<blocks, HASH_THREADS, 0, stream>>>(sym, s0, s1, carry, st, log, k, seed);
+void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t b0, uint32_t b1, const uint32_t *region_count,
+                 uint64_t ord_base, SketchState *st, LogView log, uint64_t seed, cudaStream_t stream) {
+    if (b1 <= b0) return;
+    const uint32_t blocks = b1 - b0;
+    if (k == 21) hash_kernel<21><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, log, k, seed);
+    else if (k == 31) hash_kernel<31><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, log, k, seed);
+    else hash_kernel<0><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, log, k, seed);
 }
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
-                      uint64_t arena_base, ParseCarry *carry, SketchState *st, LogView log,
+                      uint64_t arena_base, uint64_t ord_base, SketchState *st, LogView log,
                       uint64_t seed, cudaStream_t stream) {
     if (!n) return;
-    push_hash_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bytes, offs, extra, n, arena_base, carry, st, log, seed);
-    push_commit_kernel<<<1, 1, 0, stream>>>(carry, st, n);
+    push_hash_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bytes, offs, extra, n, arena_base, ord_base, st, log, seed);
+    push_commit_kernel<<<1, 1, 0, stream>>>(st, n);
 }
 
 }  // namespace fb2

@@ -6,20 +6,17 @@
 namespace fb2 {
 
 // parse.cu
-void launch_tile_summary(int mode, const uint8_t *raw, uint32_t len, const ParseCarry *carry,
-                         TileSummary *out, uint32_t n_tiles, cudaStream_t st);
-void launch_tile_scan(const TileSummary *sums, uint32_t n_tiles, ParseCarry *carry, TilePrefix *pre,
-                      const uint8_t *raw, uint32_t len, cudaStream_t st);
-void launch_pack(int mode, const uint8_t *raw, uint32_t len, ParseCarry *carry, const TilePrefix *pre,
-                 uint8_t *sym, uint32_t n_tiles, cudaStream_t st);
-void launch_carry_front(uint8_t *symbuf, const ParseCarry *carry, cudaStream_t st);
+void launch_phase(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_map, uint32_t *st_state,
+                  cudaStream_t s);
+void launch_pack(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, const uint32_t *st_state, uint8_t *sym,
+                 uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, cudaStream_t s);
 void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t st);
 
 // hash.cu
-void launch_hash(int k, const uint8_t *sym, uint32_t s0, uint32_t s1, const ParseCarry *carry,
-                 SketchState *st, LogView log, uint64_t seed, cudaStream_t stream);
+void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t b0, uint32_t b1, const uint32_t *region_count,
+                 uint64_t ord_base, SketchState *st, LogView log, uint64_t seed, cudaStream_t stream);
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
-                      uint64_t arena_base, ParseCarry *carry, SketchState *st, LogView log,
+                      uint64_t arena_base, uint64_t ord_base, SketchState *st, LogView log,
                       uint64_t seed, cudaStream_t stream);
 
 // table.cu
@@ -29,6 +26,9 @@ void launch_gather(TableView t, SketchState *st, unsigned long long *keys, uint3
 void launch_radix_sort(unsigned long long *keys, uint32_t *vals, unsigned long long *tkeys, uint32_t *tvals,
                        uint32_t n, uint32_t *hist, cudaStream_t s);
 uint32_t radix_hist_words(uint32_t n);
+void launch_prune_select(TableView t, SketchState *st, uint32_t shift, uint32_t *bins, int scaled,
+                         unsigned long long size, unsigned long long max_hash, unsigned long long *keys,
+                         uint32_t *slots, cudaStream_t s);
 void launch_select_keep(const unsigned long long *keys, uint32_t n, int scaled, unsigned long long size,
                         unsigned long long max_hash, SketchState *st, cudaStream_t s);
 void launch_commit_threshold(SketchState *st, cudaStream_t s);

@@ -1,4 +1,4 @@
-// parse.cu -- K1/K2: raw FASTA/FASTQ bytes in HBM -> dense symbol stream in HBM.
+// parse.cu -- K1/K2: raw FASTA/FASTQ bytes in HBM -> symbol regions in HBM.
 //
 // Replaces, in bulk, needletail's record loop (lib/src/lib.rs:60-68) and the per-record
 // `seq.normalize(false)` of SketchScheme::process (lib/src/sketch_schemes/mash.rs:72-73):
@@ -6,58 +6,102 @@
 // position (N, IUPAC, gaps) and every record boundary becomes SYM_BREAK (4); whitespace and
 // non-sequence lines vanish.  k-mers of the symbol stream == canonical_kmers of the records.
 //
-// Three kernels per chunk:
-//   tile_summary_kernel : per 4 KiB tile, a transducer summary (next state + symbols emitted for
-//                         every possible start state)
-//   tile_scan_kernel    : exclusive scan of the summaries -> per-tile start state and output offset
-//   pack_kernel         : re-reads the tile, writes symbols at their final offsets, accumulates
-//                         total_bases / record count / FASTQ validity.
+// A chunk is cut into supertiles of st_tiles x 4 KiB.  Per chunk:
+//   phase_kernel      : per supertile, how the line state changes across it (FASTQ: newline
+//                       count mod 4; FASTA: is the last line a header) -- newline masks only
+//   phase_scan_kernel : scan of those state maps -> start state of every supertile
+//   pack_kernel       : one block per supertile walks its tiles with the known state and writes
+//                       the symbols into the supertile's own region (count in region_count[]);
+//                       no global compaction is needed because the hash kernel walks regions
+//   front_fix_kernel  : copies the last 32 symbols before each region into its front pad (and
+//                       the chunk's tail into the carry buffer) so k-mers span region / chunk seams
+// Byte classification is SIMD-in-register on the common case (ACGTacgt + '\n'), with an exact
+// per-byte LUT fallback whenever a thread meets anything else among its sequence bytes.
 #include "common.cuh"
 #include "device_types.cuh"
 
 namespace fb2 {
 
-struct Masks16 {
-    uint32_t valid, nl, cr, ws, gt, at, plus;
-    uint64_t codes;  // 4 bits per byte: min(class, 4)
-};
+// 0x80 in every byte of x that is zero (exact, no cross-byte borrows)
+__device__ __forceinline__ uint32_t zero_bytes80(uint32_t x) {
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+// flags at bits 7,15,23,31 -> 4 contiguous bits
+__device__ __forceinline__ uint32_t gather4(uint32_t f80) { return ((f80 >> 7) * 0x01020408u) >> 24; }
+// 4 bits -> 0xFF in each flagged byte
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
-__device__ __forceinline__ void load_classify(const uint8_t *__restrict__ raw, uint32_t off, uint32_t len,
-                                              const uint8_t *lut, Masks16 &m) {
-    uint32_t w[4] = {0, 0, 0, 0};
+struct Raw16 {
+    uint32_t w[4];
+    uint32_t valid;   // bytes that exist (off + i < len)
+    uint32_t nl;      // '\n'
+};
+__device__ __forceinline__ uint32_t raw_byte(const Raw16 &r, int i) {
+    const uint64_t lo = (uint64_t)r.w[0] | ((uint64_t)r.w[1] << 32), hi = (uint64_t)r.w[2] | ((uint64_t)r.w[3] << 32);
+    return (uint32_t)((i < 8 ? (lo >> (8 * i)) : (hi >> (8 * (i - 8)))) & 0xFFu);
+}
+__device__ __forceinline__ void load_raw(const uint8_t *__restrict__ raw, uint32_t off, uint32_t len, Raw16 &r) {
+    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0;
     int nvalid;
     if (off + 16u <= len) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + off));
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
         nvalid = 16;
     } else {
         nvalid = off < len ? (int)(len - off) : 0;
-        for (int i = 0; i < nvalid; ++i) w[i >> 2] |= (uint32_t)raw[off + i] << (8 * (i & 3));
+        for (int i = 0; i < nvalid; ++i) r.w[i >> 2] |= (uint32_t)raw[off + i] << (8 * (i & 3));
     }
-    m.valid = nvalid >= 16 ? 0xFFFFu : ((1u << nvalid) - 1u);
-    m.nl = m.cr = m.ws = m.gt = m.at = m.plus = 0;
-    m.codes = 0;
+    r.valid = nvalid >= 16 ? 0xFFFFu : ((1u << nvalid) - 1u);
+    uint32_t nl = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-        const uint32_t c = lut[b];
-        m.nl |= (c == CLS_NL ? 1u : 0u) << i;
-        m.cr |= (c == CLS_CR ? 1u : 0u) << i;
-        m.ws |= (c == CLS_WS ? 1u : 0u) << i;
-        m.gt |= (c == CLS_GT ? 1u : 0u) << i;
-        m.at |= (c == CLS_AT ? 1u : 0u) << i;
-        m.plus |= (c == CLS_PLUS ? 1u : 0u) << i;
-        m.codes |= (uint64_t)(c < 4u ? c : 4u) << (4 * i);
-    }
-    m.nl &= m.valid; m.cr &= m.valid; m.ws &= m.valid; m.gt &= m.valid; m.at &= m.valid; m.plus &= m.valid;
+    for (int j = 0; j < 4; ++j) nl |= gather4(zero_bytes80(r.w[j] ^ 0x0A0A0A0Au)) << (4 * j);
+    r.nl = nl & r.valid;
 }
 
-// byte at chunk offset off-d (d = 1, 2); before the chunk: the carried stream bytes.
-__device__ __forceinline__ uint32_t byte_before(const uint8_t *__restrict__ raw, uint32_t off, uint32_t d,
-                                                uint32_t prev1, uint32_t prev2) {
-    if (off >= d) return raw[off - d];
-    const uint32_t back = d - off;  // 1 or 2 bytes before the chunk start
-    return back == 1 ? prev1 : prev2;
+// Classification of the sequence bytes `sm` of a thread (bytes outside sm are ignored).
+struct SeqCls {
+    uint32_t wsm;    // ' ', '\t', '\r' among sm          (removed by normalize)
+    uint32_t cr;     // '\r' among the 16 bytes            (0 on the fast path: none among sm)
+    uint32_t bad;    // kept but not a base, among sm      (N, IUPAC, '>', digits, ...)
+    uint32_t cw[4];  // per byte: 2-bit base code in the low bits
+};
+__device__ __forceinline__ void classify_seq(const Raw16 &r, uint32_t sm, const uint8_t *lut, SeqCls &c) {
+    // fast path: code from bits 1,2 of the upper-cased letter; re-expand and compare, which is
+    // equal exactly for ACGTacgt.  Any mismatch inside sm sends the thread to the exact LUT.
+    uint32_t diff = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t u = r.w[j] & 0xDFDFDFDFu;
+        const uint32_t c2 = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+        c.cw[j] = c2;
+        uint32_t z = (c2 | (c2 >> 4)) & 0x00FF00FFu;
+        z = (z | (z >> 8)) & 0xFFFFu;
+        const uint32_t e = __byte_perm(0x54474341u, 0u, z);
+        diff |= (e ^ u) & spread4((sm >> (4 * j)) & 0xFu);
+    }
+    c.wsm = 0; c.cr = 0; c.bad = 0;
+    if (diff != 0u) {  // exact per-byte classes (needletail normalize(false))
+        uint32_t wsm = 0, cr = 0, bad = 0;
+        c.cw[0] = c.cw[1] = c.cw[2] = c.cw[3] = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t b = (r.w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            const uint32_t k = lut[b];
+            cr |= (k == CLS_CR ? 1u : 0u) << i;
+            wsm |= ((k == CLS_WS || k == CLS_CR) ? 1u : 0u) << i;
+            bad |= ((k >= 4u && k != CLS_WS && k != CLS_CR && k != CLS_NL) ? 1u : 0u) << i;
+            c.cw[i >> 2] |= (k & 3u) << (8 * (i & 3));
+        }
+        c.wsm = wsm & sm; c.cr = cr & r.valid; c.bad = bad & sm;
+    }
+}
+// Final symbol code words: base code, or SYM_BREAK (4) where `four` is set.
+__device__ __forceinline__ void code_words(const SeqCls &c, uint32_t four, uint32_t out[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t m1 = (((four >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u;
+        out[j] = (c.cw[j] & ~(m1 * 3u)) | (m1 << 2);
+    }
 }
 
 // ---- block-wide helpers (256 threads) ---------------------------------------------------------
@@ -105,38 +149,28 @@ __device__ __forceinline__ uint32_t block_exscan_max(uint32_t v, uint32_t *sh8, 
     total = tot;
     return max(base, ex);
 }
-__device__ __forceinline__ unsigned long long block_reduce_add64(unsigned long long v, unsigned long long *sh8) {
+struct OpAdd { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; } };
+struct OpMin { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a < b ? a : b; } };
+struct OpMax { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a > b ? a : b; } };
+template <class Op>
+__device__ __forceinline__ unsigned long long block_reduce64(unsigned long long v, unsigned long long *sh8, Op op,
+                                                             unsigned long long ident) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_down_sync(0xffffffffu, v, d));
     __syncthreads();
     if ((threadIdx.x & 31) == 0) sh8[threadIdx.x >> 5] = v;
     __syncthreads();
-    unsigned long long t = 0;
+    unsigned long long t = ident;
 #pragma unroll
-    for (int i = 0; i < TILE_THREADS / 32; ++i) t += sh8[i];
+    for (int i = 0; i < TILE_THREADS / 32; ++i) t = op(t, sh8[i]);
     return t;
 }
-__device__ __forceinline__ unsigned long long block_reduce_min64(unsigned long long v, unsigned long long *sh8) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, d));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh8[threadIdx.x >> 5] = v;
-    __syncthreads();
-    unsigned long long t = ~0ULL;
-#pragma unroll
-    for (int i = 0; i < TILE_THREADS / 32; ++i) t = min(t, sh8[i]);
-    return t;
-}
-__device__ __forceinline__ unsigned long long block_reduce_max64(unsigned long long v, unsigned long long *sh8) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_down_sync(0xffffffffu, v, d));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh8[threadIdx.x >> 5] = v;
-    __syncthreads();
-    unsigned long long t = 0;
-#pragma unroll
-    for (int i = 0; i < TILE_THREADS / 32; ++i) t = max(t, sh8[i]);
-    return t;
+
+// previous raw byte of each thread's first byte: neighbour lane's last byte, or memory for lane 0
+__device__ __forceinline__ uint32_t prev_byte(const Raw16 &r, const uint8_t *__restrict__ raw, uint32_t off, uint32_t carried) {
+    uint32_t p = __shfl_up_sync(0xffffffffu, r.w[3] >> 24, 1);
+    if ((threadIdx.x & 31) == 0) p = off ? raw[off - 1] : carried;
+    return p;
 }
 
 // FASTQ: mask of this thread's bytes that lie in sequence lines (their '\n' included), given
@@ -155,268 +189,292 @@ __device__ __forceinline__ uint32_t fastq_seq_mask(uint32_t nl, uint32_t phase0)
     }
     return qm;
 }
-
-// FASTA: header-byte mask (header lines including their '\n') for this thread's 16 bytes.
-//   hs      : header starts ('>' at a line start) among the bytes
-//   seed0   : byte 0 continues a header line begun earlier
-// Carry-propagation flood: a seed at the bottom of a run of non-newline bytes floods the run and
-// the newline that ends it.
+// FASTA: which line starts begin with '>' (line starts are few per thread: point look-ups)
+__device__ __forceinline__ uint32_t header_starts(const Raw16 &r, uint32_t ls) {
+    uint32_t hs = 0, l = ls;
+    while (l) {
+        const int i = __ffs(l) - 1;
+        l &= l - 1u;
+        if (raw_byte(r, i) == '>') hs |= 1u << i;
+    }
+    return hs;
+}
+// FASTA: header-byte mask (header lines including their '\n').  Carry-propagation flood: a seed at
+// the bottom of a run of non-newline bytes floods the run and the newline that ends it.
 __device__ __forceinline__ uint32_t fasta_header_mask(uint32_t hs, uint32_t nl, bool seed0) {
     const uint32_t g = hs | (seed0 ? 1u : 0u);
     const uint32_t p = ~nl & 0xFFFFu;
-    return ((g + p) ^ p) & 0x1FFFFu;  // bit 16 = still in a header after byte 15
+    return ((g + p) ^ p) & 0x1FFFFu;
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per supertile: state map as 2 bits per start state.  FASTQ: phase += newlines.  FASTA: state of
+// the line containing the supertile's last byte (0 sequence, 1 header), or unchanged if the
+// supertile holds no line start.
 template <int MODE>
 __global__ void __launch_bounds__(TILE_THREADS)
-tile_summary_kernel(const uint8_t *__restrict__ raw, uint32_t len, const ParseCarry *__restrict__ carry,
-                    TileSummary *__restrict__ out) {
-    __shared__ uint8_t lut[256];
-    __shared__ uint32_t sh8[8];
+phase_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, const ParseCarry *__restrict__ carry,
+             uint32_t *__restrict__ st_map) {
     __shared__ unsigned long long sh8l[8];
     const int tid = threadIdx.x;
-    lut[tid] = classify_byte((uint8_t)tid);
-    __syncthreads();
-    const uint32_t off = blockIdx.x * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u;
-    Masks16 m;
-    load_classify(raw, off, len, lut, m);
-    const uint32_t wsm = m.ws | m.cr;
-    TileSummary s;
-    s.next = 0; s.cnt[0] = s.cnt[1] = s.cnt[2] = s.cnt[3] = 0;
-
-    if (MODE == MODE_LINES) {
-        const unsigned long long t = block_reduce_add64(__popc(m.valid & ~wsm), sh8l);
-        s.next = 0; s.cnt[0] = (uint32_t)t;
-    } else if (MODE == MODE_FASTQ) {
-        uint32_t total_nl;
-        const uint32_t rel = block_exscan_add(__popc(m.nl), sh8, total_nl);
-        // symbols per relative line class, 16 bits each
-        unsigned long long acc = 0;
-        uint32_t mm = m.nl, lo = 0, r = rel & 3u;
-        while (true) {
-            const int nb = mm ? (__ffs(mm) - 1) : 16;
-            const uint32_t upto = nb >= 15 ? 0xFFFFu : ((2u << nb) - 1u);
-            const uint32_t seg = upto & ~((1u << lo) - 1u);
-            acc += (unsigned long long)__popc(seg & m.valid & ~wsm) << (16 * r);
-            if (nb >= 15) break;
-            mm &= mm - 1u;
-            lo = (uint32_t)nb + 1u;
-            r = (r + 1u) & 3u;
-        }
-        acc = block_reduce_add64(acc, sh8l);
-        for (uint32_t h = 0; h < 4; ++h) {
-            s.next |= ((h + total_nl) & 3u) << (2 * h);
-            s.cnt[h] = (uint32_t)((acc >> (16 * ((1u - h) & 3u))) & 0xFFFFu);
-        }
-    } else {  // MODE_FASTA
-        const uint32_t p1 = byte_before(raw, off, 1, carry->prev1, carry->prev2);
-        const uint32_t ls = ((m.nl << 1) | (p1 == '\n' ? 1u : 0u)) & m.valid;
-        const uint32_t hs = ls & m.gt;
-        // "last line start so far" scan: value = (tid+1) << 1 | is_header
-        uint32_t mine = 0;
-        if (ls) {
-            const int hi = 31 - __clz(ls);
-            mine = ((uint32_t)(tid + 1) << 1) | ((m.gt >> hi) & 1u);
-        }
-        uint32_t last;
-        const uint32_t prev = block_exscan_max(mine, sh8, last);
-        const bool defined_in = prev != 0;
-        const bool in_hdr = defined_in && (prev & 1u);
-        const uint32_t hm = fasta_header_mask(hs, m.nl, in_hdr && !(ls & 1u));
-        const uint32_t pre = (ls ? ((ls & (0u - ls)) - 1u) : 0xFFFFu) & m.valid;  // before first line start
-        const uint32_t seqsym = ~hm & ~wsm & ~m.nl & m.valid;
-        uint32_t post_cnt, pre_cnt;
-        if (defined_in) { post_cnt = __popc(seqsym) + __popc(hs); pre_cnt = 0; }
-        else { post_cnt = __popc(seqsym & ~pre) + __popc(hs); pre_cnt = __popc(seqsym & pre); }
-        const unsigned long long t =
-            block_reduce_add64(((unsigned long long)pre_cnt << 32) | post_cnt, sh8l);
-        const uint32_t post = (uint32_t)t, pres = (uint32_t)(t >> 32);
-        const bool has = last != 0;
-        const uint32_t outst = last & 1u;
-        // states: 0 = sequence line, 1 = header line
-        s.next = (has ? outst : 0u) | ((has ? outst : 1u) << 2);
-        s.cnt[0] = post + pres;
-        s.cnt[1] = post;
-    }
-    if (tid == 0) out[blockIdx.x] = s;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Single block.  Thread t composes tiles [t*G, (t+1)*G), thread 0 chains the 1024 group summaries,
-// then every thread replays its tiles with a known start state.
-__global__ void __launch_bounds__(1024)
-tile_scan_kernel(const TileSummary *__restrict__ sums, uint32_t n_tiles, ParseCarry *carry,
-                 TilePrefix *__restrict__ pre, const uint8_t *__restrict__ raw, uint32_t len) {
-    __shared__ uint32_t g_next[1024];
-    __shared__ uint32_t g_cnt[4][1024];
-    __shared__ uint32_t g_state[1024];
-    __shared__ uint32_t g_off[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t G = (n_tiles + 1023u) / 1024u;
-    const uint32_t t0 = min(tid * G, n_tiles), t1 = min(t0 + G, n_tiles);
-    uint32_t nx[4] = {0, 1, 2, 3}, ct[4] = {0, 0, 0, 0};
+    const uint32_t st = blockIdx.x;
+    const uint32_t t0 = st * g.st_tiles, t1 = min(t0 + g.st_tiles, g.n_tiles);
+    unsigned long long acc = 0;  // FASTQ: newline count; FASTA: max over line starts of (pos+1) << 1 | is_header
     for (uint32_t t = t0; t < t1; ++t) {
-        const TileSummary s = sums[t];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const uint32_t mid = nx[h];
-            ct[h] += s.cnt[mid];
-            nx[h] = (s.next >> (2 * mid)) & 3u;
-        }
-    }
-    g_next[tid] = nx[0] | (nx[1] << 2) | (nx[2] << 4) | (nx[3] << 6);
-#pragma unroll
-    for (int h = 0; h < 4; ++h) g_cnt[h][tid] = ct[h];
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t st = carry->state & 3u, off = 0;
-        for (uint32_t g = 0; g < 1024; ++g) {
-            g_state[g] = st; g_off[g] = off;
-            off += g_cnt[st][g];
-            st = (g_next[g] >> (2 * st)) & 3u;
-        }
-        carry->cprev1 = carry->prev1; carry->cprev2 = carry->prev2;
-        if (len >= 2) { carry->prev2 = raw[len - 2]; carry->prev1 = raw[len - 1]; }
-        else if (len == 1) { carry->prev2 = carry->prev1; carry->prev1 = raw[0]; }
-        carry->state = st;
-        carry->chunk_syms = off;
-        carry->chunk_raw_base = carry->raw_total;
-        carry->raw_total += len;
-        carry->chunk_ord_base = carry->ordinal;
-        carry->ordinal += off;
-    }
-    __syncthreads();
-    uint32_t st = g_state[tid], off = g_off[tid];
-    for (uint32_t t = t0; t < t1; ++t) {
-        const TileSummary s = sums[t];
-        TilePrefix p; p.state_in = st; p.sym_off = off;
-        pre[t] = p;
-        off += s.cnt[st];
-        st = (s.next >> (2 * st)) & 3u;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(TILE_THREADS)
-pack_kernel(const uint8_t *__restrict__ raw, uint32_t len, ParseCarry *carry,
-            const TilePrefix *__restrict__ pre, uint8_t *__restrict__ sym) {
-    __shared__ uint8_t lut[256];
-    __shared__ uint32_t sh8[8];
-    __shared__ unsigned long long sh8l[8];
-    const int tid = threadIdx.x;
-    lut[tid] = classify_byte((uint8_t)tid);
-    __syncthreads();
-    const uint32_t off = blockIdx.x * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u;
-    Masks16 m;
-    load_classify(raw, off, len, lut, m);
-    const uint32_t wsm = m.ws | m.cr;
-    const TilePrefix tp = pre[blockIdx.x];
-    const uint64_t raw_base = carry->chunk_raw_base;
-
-    uint32_t em = 0;               // bytes that emit a symbol
-    long long bases_delta = 0;     // contribution to total_bases
-    uint32_t recs = 0;
-
-    if (MODE == MODE_LINES) {
-        em = m.valid & ~wsm;       // '\n' (class NL -> code 4) separates records
-    } else if (MODE == MODE_FASTQ) {
-        uint32_t total_nl;
-        const uint32_t rel = block_exscan_add(__popc(m.nl), sh8, total_nl);
-        const uint32_t ph0 = (tp.state_in + rel) & 3u;
-        const uint32_t qm = fastq_seq_mask(m.nl, ph0) & m.valid;
-        em = qm & ~wsm;
-        const uint32_t p1 = byte_before(raw, off, 1, carry->cprev1, carry->cprev2);
-        const uint32_t crprev = ((m.cr << 1) | (p1 == '\r' ? 1u : 0u)) & 0xFFFFu;
-        // sequence().len(): the line without its '\n' and without one CR right before it
-        bases_delta = (long long)__popc(qm & ~m.nl) - (long long)__popc(qm & m.nl & crprev);
-        // line-start checks: phase 0 must start with '@', phase 2 with '+'
-        uint32_t ls = ((m.nl << 1) | (p1 == '\n' ? 1u : 0u)) & m.valid;
-        unsigned long long bad = ~0ULL;
-        while (ls) {
-            const int i = __ffs(ls) - 1;
-            ls &= ls - 1u;
-            const uint32_t ph = (ph0 + __popc(m.nl & ((1u << i) - 1u))) & 3u;
-            if (ph == 0u) recs++;
-            const bool ok = ph == 0u ? ((m.at >> i) & 1u) : (ph == 2u ? ((m.plus >> i) & 1u) : 1u);
-            if (!ok) bad = min(bad, (unsigned long long)(raw_base + off + (uint32_t)i));
-        }
-        bad = block_reduce_min64(bad, sh8l);
-        unsigned long long sig = 0;
-        const uint32_t sg = m.valid & ~(m.nl | m.cr);
-        if (sg) {
-            const int i = 31 - __clz(sg);
-            const uint32_t ph = (ph0 + __popc(m.nl & ((1u << i) - 1u))) & 3u;
-            sig = ((unsigned long long)(raw_base + off + (uint32_t)i + 1u) << 2) | ph;
-        }
-        sig = block_reduce_max64(sig, sh8l);
-        if (tid == 0) {
-            if (bad != ~0ULL) atomicMin((unsigned long long *)&carry->first_bad_pos, bad);
-            if (sig) atomicMax((unsigned long long *)&carry->last_sig, sig);
-        }
-    } else {  // MODE_FASTA
-        const uint32_t p1 = byte_before(raw, off, 1, carry->cprev1, carry->cprev2);
-        const uint32_t p2 = byte_before(raw, off, 2, carry->cprev1, carry->cprev2);
-        const uint32_t ls = ((m.nl << 1) | (p1 == '\n' ? 1u : 0u)) & m.valid;
-        const uint32_t hs = ls & m.gt;
-        uint32_t mine = 0;
-        if (ls) {
-            const int hi = 31 - __clz(ls);
-            mine = ((uint32_t)(tid + 1) << 1) | ((m.gt >> hi) & 1u);
-        }
-        uint32_t last;
-        const uint32_t prev = block_exscan_max(mine, sh8, last);
-        // state of the line containing the byte before this thread's first byte
-        const uint32_t st_in = prev ? (prev & 1u) : (tp.state_in & 1u);
-        const uint32_t hm = fasta_header_mask(hs, m.nl, st_in && !(ls & 1u));
-        em = ((~hm & ~wsm & ~m.nl) | hs) & m.valid;
-        recs = __popc(hs);
-        bases_delta = __popc(~hm & m.valid);
-        // a new header ends the previous record: its raw sequence loses the final '\n'
-        // (and one CR before it) when that newline closed a sequence line
-        uint32_t h = hs;
-        const uint32_t crm = m.cr;
-        while (h) {
-            const int i = __ffs(h) - 1;
-            h &= h - 1u;
-            const bool prev_in_hdr = i >= 1 ? ((hm >> (i - 1)) & 1u) : (st_in != 0u);
-            if (!prev_in_hdr) {
-                bases_delta -= 1;
-                const bool cr2 = i >= 2 ? ((crm >> (i - 2)) & 1u) : ((i == 1 ? p1 : p2) == '\r');
-                if (cr2) bases_delta -= 1;
+        const uint32_t off = t * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u;
+        Raw16 r;
+        load_raw(raw, off, g.len, r);
+        if (MODE == MODE_FASTQ) {
+            acc += __popc(r.nl);
+        } else {
+            const uint32_t p1 = prev_byte(r, raw, off, carry->prev1);
+            const uint32_t ls = ((r.nl << 1) | (p1 == '\n' ? 1u : 0u)) & r.valid;
+            if (ls) {
+                const int hi = 31 - __clz(ls);
+                acc = ((unsigned long long)(off + hi + 1u) << 1) | (raw_byte(r, hi) == '>' ? 1ull : 0ull);
             }
         }
     }
-
-    // ---- emit -----------------------------------------------------------------------------
-    uint32_t tile_total;
-    const uint32_t local = block_exscan_add(__popc(em), sh8, tile_total);
-    uint8_t *o = sym + tp.sym_off + local;
-    uint32_t e = em;
-    while (e) {
-        const int i = __ffs(e) - 1;
-        e &= e - 1u;
-        *o++ = (uint8_t)((m.codes >> (4 * i)) & 0xFu);
+    uint32_t map;
+    if (MODE == MODE_FASTQ) {
+        const uint32_t n = (uint32_t)block_reduce64(acc, sh8l, OpAdd(), 0ull);
+        map = 0;
+        for (uint32_t h = 0; h < 4; ++h) map |= ((h + n) & 3u) << (2 * h);
+    } else {
+        const unsigned long long last = block_reduce64(acc, sh8l, OpMax(), 0ull);
+        const uint32_t o = (uint32_t)(last & 1ull);
+        map = last ? (o | (o << 2) | (o << 4) | (o << 6)) : 0xE4u;
     }
+    if (tid == 0) st_map[st] = map;
+}
+
+__device__ __forceinline__ uint32_t fcompose(uint32_t first, uint32_t then) {  // 2 bits per state
+    uint32_t r = 0;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        const uint32_t mid = (first >> (2 * h)) & 3u;
+        r |= ((then >> (2 * mid)) & 3u) << (2 * h);
+    }
+    return r;
+}
+// One block of 1024 threads: exclusive scan (function composition) of the supertile state maps.
+__global__ void __launch_bounds__(1024)
+phase_scan_kernel(const uint32_t *__restrict__ st_map, ChunkGeom g, ParseCarry *carry, uint32_t *__restrict__ st_state,
+                  const uint8_t *__restrict__ raw, int has_maps) {
+    __shared__ uint32_t w_fun[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t IDENT = 0xE4u;
+    const uint32_t G = (g.n_st + 1023u) / 1024u;
+    const uint32_t a = min(tid * G, g.n_st), b = min(a + G, g.n_st);
+    uint32_t mine = IDENT;
+    if (has_maps) for (uint32_t i = a; i < b; ++i) mine = fcompose(mine, st_map[i]);
+    uint32_t f = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t h = __shfl_up_sync(0xffffffffu, f, d);
+        if (lane >= (uint32_t)d) f = fcompose(h, f);
+    }
+    if (lane == 31u) w_fun[wid] = f;
+    uint32_t f_ex = __shfl_up_sync(0xffffffffu, f, 1);
+    if (lane == 0u) f_ex = IDENT;
+    __syncthreads();
+    if (wid == 0u) {
+        uint32_t q = w_fun[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t h = __shfl_up_sync(0xffffffffu, q, d);
+            if (lane >= (uint32_t)d) q = fcompose(h, q);
+        }
+        uint32_t q_ex = __shfl_up_sync(0xffffffffu, q, 1);
+        if (lane == 0u) q_ex = IDENT;
+        w_fun[lane] = q_ex;
+    }
+    __syncthreads();
+    uint32_t before = fcompose(w_fun[wid], f_ex);
+    const uint32_t st0 = carry->state & 3u;
+    for (uint32_t i = a; i < b; ++i) {
+        st_state[i] = (before >> (2 * st0)) & 3u;
+        if (has_maps) before = fcompose(before, st_map[i]);
+    }
+    __syncthreads();  // every thread has read carry->state
+    if (tid == 1023u) {
+        carry->state = (before >> (2 * st0)) & 3u;
+        carry->cprev1 = carry->prev1; carry->cprev2 = carry->prev2;
+        if (g.len >= 2) { carry->prev2 = raw[g.len - 2]; carry->prev1 = raw[g.len - 1]; }
+        else if (g.len == 1) { carry->prev2 = carry->prev1; carry->prev1 = raw[0]; }
+        carry->chunk_syms = 0;
+        carry->chunk_raw_base = carry->raw_total;
+        carry->raw_total += g.len;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(TILE_THREADS)
+pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, const uint32_t *__restrict__ st_state,
+            uint8_t *__restrict__ sym, uint32_t *__restrict__ region_count) {
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t sh8[8];
+    __shared__ unsigned long long sh8l[8];
+    const int tid = threadIdx.x;
+    lut[tid] = classify_byte((uint8_t)tid);
+    __syncthreads();
+    const uint32_t st = blockIdx.x;
+    const uint32_t t0 = st * g.st_tiles, t1 = min(t0 + g.st_tiles, g.n_tiles);
+    const uint64_t raw_base = carry->chunk_raw_base;
+    const uint32_t cprev1 = carry->cprev1, cprev2 = carry->cprev2;
+    uint8_t *region = sym + (size_t)SYM_FRONT + (size_t)st * g.region_stride;
+
+    uint32_t state = MODE == MODE_LINES ? 0u : st_state[st];  // state of the line holding the previous byte
+    uint32_t out_off = 0;                                     // symbols written so far in this region
+    long long bases_delta = 0;
+    uint32_t recs = 0;
+    unsigned long long bad_pos = ~0ULL, sig = 0;
+
+    for (uint32_t t = t0; t < t1; ++t) {
+        const uint32_t off = t * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u;
+        Raw16 r;
+        load_raw(raw, off, g.len, r);
+        uint32_t em = 0, four = 0;
+        SeqCls c;
+
+        if (MODE == MODE_LINES) {
+            const uint32_t sm = r.valid & ~r.nl;
+            classify_seq(r, sm, lut, c);
+            em = (sm & ~c.wsm) | r.nl;     // '\n' separates records
+            four = c.bad | r.nl;
+        } else if (MODE == MODE_FASTQ) {
+            uint32_t total_nl;
+            const uint32_t rel = block_exscan_add(__popc(r.nl), sh8, total_nl);
+            const uint32_t ph0 = (state + rel) & 3u;
+            const uint32_t qm = fastq_seq_mask(r.nl, ph0) & r.valid;
+            const uint32_t sm = qm & ~r.nl;
+            if (qm) classify_seq(r, sm, lut, c);
+            else { c.wsm = c.cr = c.bad = 0; c.cw[0] = c.cw[1] = c.cw[2] = c.cw[3] = 0; }
+            em = (sm & ~c.wsm) | (qm & r.nl);
+            four = c.bad | (qm & r.nl);
+            const uint32_t p1 = prev_byte(r, raw, off, cprev1);
+            // sequence().len(): the line without its '\n' and without one CR right before it
+            const uint32_t crprev = ((c.cr << 1) | (p1 == '\r' ? 1u : 0u)) & 0xFFFFu;
+            bases_delta += (long long)__popc(sm) - (long long)__popc(qm & r.nl & crprev);
+            // line-start checks: phase 0 must start with '@', phase 2 with '+'
+            uint32_t ls = ((r.nl << 1) | (p1 == '\n' ? 1u : 0u)) & r.valid;
+            while (ls) {
+                const int i = __ffs(ls) - 1;
+                ls &= ls - 1u;
+                const uint32_t ph = (ph0 + __popc(r.nl & ((1u << i) - 1u))) & 3u;
+                if (ph == 0u) recs++;
+                const bool ok = ph == 0u ? (raw_byte(r, i) == '@') : (ph == 2u ? (raw_byte(r, i) == '+') : true);
+                if (!ok) bad_pos = min(bad_pos, (unsigned long long)(raw_base + off + (uint32_t)i));
+            }
+            // last byte that is neither CR nor LF, with its phase (truncation check at end of stream)
+            uint32_t sg = r.valid & ~r.nl;
+            while (sg) {
+                const int i = 31 - __clz(sg);
+                if (raw_byte(r, i) != '\r') {
+                    const uint32_t ph = (ph0 + __popc(r.nl & ((1u << i) - 1u))) & 3u;
+                    sig = ((unsigned long long)(raw_base + off + (uint32_t)i + 1u) << 2) | ph;
+                    break;
+                }
+                sg &= ~(1u << i);
+            }
+            state = (state + total_nl) & 3u;
+        } else {  // MODE_FASTA
+            const uint32_t p1 = prev_byte(r, raw, off, cprev1);
+            const uint32_t ls = ((r.nl << 1) | (p1 == '\n' ? 1u : 0u)) & r.valid;
+            const uint32_t hs = header_starts(r, ls);
+            uint32_t mine = 0;
+            if (ls) {
+                const int hi = 31 - __clz(ls);
+                mine = ((uint32_t)(tid + 1) << 1) | ((hs >> hi) & 1u);
+            }
+            uint32_t last;
+            const uint32_t prev = block_exscan_max(mine, sh8, last);
+            const uint32_t st_in = prev ? (prev & 1u) : (state & 1u);
+            const uint32_t hm = fasta_header_mask(hs, r.nl, st_in && !(ls & 1u));
+            const uint32_t sm = ~hm & ~r.nl & r.valid;
+            if (sm) classify_seq(r, sm, lut, c);
+            else { c.wsm = c.cr = c.bad = 0; c.cw[0] = c.cw[1] = c.cw[2] = c.cw[3] = 0; }
+            em = (sm & ~c.wsm) | hs;
+            four = c.bad | hs;
+            recs += __popc(hs);
+            bases_delta += __popc(~hm & r.valid);
+            // a new header ends the previous record: its raw sequence loses the final '\n'
+            // (and one CR before it) when that newline closed a sequence line
+            uint32_t h = hs;
+            while (h) {
+                const int i = __ffs(h) - 1;
+                h &= h - 1u;
+                const bool prev_in_hdr = i >= 1 ? ((hm >> (i - 1)) & 1u) : (st_in != 0u);
+                if (!prev_in_hdr) {
+                    bases_delta -= 1;
+                    uint32_t b2;
+                    if (i >= 2) b2 = raw_byte(r, i - 2);
+                    else if (i == 1) b2 = p1;
+                    else b2 = off >= 2 ? raw[off - 2] : (off == 1 ? cprev1 : cprev2);
+                    if (b2 == '\r') bases_delta -= 1;
+                }
+            }
+            if (last) state = last & 1u;
+        }
+
+        // ---- emit ---------------------------------------------------------------------------
+        uint32_t tile_total;
+        const uint32_t local = block_exscan_add(__popc(em), sh8, tile_total);
+        if (em) {
+            four &= em;
+            uint32_t cw[4];
+            if (four) code_words(c, four, cw);
+            else { cw[0] = c.cw[0]; cw[1] = c.cw[1]; cw[2] = c.cw[2]; cw[3] = c.cw[3]; }
+            uint8_t *o = region + out_off + local;
+            if (em == 0xFFFFu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = (uint8_t)((cw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if ((em >> i) & 1u) *o++ = (uint8_t)((cw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+            }
+        }
+        out_off += tile_total;
+    }
+
+    if (tid == 0) { region_count[st] = out_off; atomicAdd(&carry->chunk_syms, out_off); }
     if (MODE != MODE_LINES) {
-        const unsigned long long packed =
-            block_reduce_add64((unsigned long long)bases_delta, sh8l);  // wrapping add is fine
-        const unsigned long long r = block_reduce_add64(recs, sh8l);
+        const unsigned long long bsum = block_reduce64((unsigned long long)bases_delta, sh8l, OpAdd(), 0ull);
+        const unsigned long long rsum = block_reduce64(recs, sh8l, OpAdd(), 0ull);
         if (tid == 0) {
-            if (packed) atomicAdd((unsigned long long *)&carry->total_bases, packed);
-            if (r) atomicAdd((unsigned long long *)&carry->n_records, r);
+            if (bsum) atomicAdd((unsigned long long *)&carry->total_bases, bsum);
+            if (rsum) atomicAdd((unsigned long long *)&carry->n_records, rsum);
+        }
+        if (MODE == MODE_FASTQ) {
+            const unsigned long long bmin = block_reduce64(bad_pos, sh8l, OpMin(), ~0ULL);
+            const unsigned long long smax = block_reduce64(sig, sh8l, OpMax(), 0ull);
+            if (tid == 0) {
+                if (bmin != ~0ULL) atomicMin((unsigned long long *)&carry->first_bad_pos, bmin);
+                if (smax) atomicMax((unsigned long long *)&carry->last_sig, smax);
+            }
         }
     }
 }
 
-// After the hash kernel has consumed a chunk: move the last SYM_FRONT symbols of
-// (front pad + chunk) to the front pad for the next chunk.  One block of SYM_FRONT threads.
-__global__ void carry_front_kernel(uint8_t *symbuf /* start of the front pad */, const ParseCarry *carry) {
-    const uint32_t n = carry->chunk_syms;
-    const uint8_t v = symbuf[n + threadIdx.x];
-    __syncthreads();
-    symbuf[threadIdx.x] = v;
+// Front pads: thread r fills the 32 bytes before region r (r < n_st) or the outgoing chunk tail
+// (r == n_st) with the last 32 symbols that precede it in stream order, walking back over short
+// or empty regions and finally into the incoming chunk tail.
+__global__ void front_fix_kernel(uint8_t *__restrict__ sym, ChunkGeom g, const uint32_t *__restrict__ region_count,
+                                 const uint8_t *__restrict__ tail_in, uint8_t *__restrict__ tail_out) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > g.n_st) return;
+    uint8_t *dst = r < g.n_st ? (sym + (size_t)SYM_FRONT + (size_t)r * g.region_stride - 32) : tail_out;
+    int need = 32;
+    for (int j = (int)r - 1; need > 0 && j >= 0; --j) {
+        const uint32_t n = region_count[j];
+        const int take = n < (uint32_t)need ? (int)n : need;
+        const uint8_t *src = sym + (size_t)SYM_FRONT + (size_t)j * g.region_stride + (n - take);
+        for (int t = 0; t < take; ++t) dst[need - take + t] = src[t];
+        need -= take;
+    }
+    for (int t = 0; t < need; ++t) dst[t] = tail_in[32 - need + t];
 }
 
 __global__ void fill_bytes_kernel(uint8_t *p, uint32_t n, uint8_t v) {
@@ -425,27 +483,21 @@ __global__ void fill_bytes_kernel(uint8_t *p, uint32_t n, uint8_t v) {
 }
 
 // ---- launchers ---------------------------------------------------------------------------------
-void launch_tile_summary(int mode, const uint8_t *raw, uint32_t len, const ParseCarry *carry,
-                         TileSummary *out, uint32_t n_tiles, cudaStream_t st) {
-    if (mode == MODE_LINES) tile_summary_kernel<MODE_LINES><<<n_tiles, TILE_THREADS, 0, st>>>(raw, len, carry, out);
-    else if (mode == MODE_FASTA) tile_summary_kernel<MODE_FASTA><<<n_tiles, TILE_THREADS, 0, st>>>(raw, len, carry, out);
-    else tile_summary_kernel<MODE_FASTQ><<<n_tiles, TILE_THREADS, 0, st>>>(raw, len, carry, out);
+void launch_phase(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_map, uint32_t *st_state,
+                  cudaStream_t s) {
+    if (mode == MODE_FASTQ) phase_kernel<MODE_FASTQ><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_map);
+    else if (mode == MODE_FASTA) phase_kernel<MODE_FASTA><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_map);
+    phase_scan_kernel<<<1, 1024, 0, s>>>(st_map, g, carry, st_state, raw, mode == MODE_LINES ? 0 : 1);
 }
-void launch_tile_scan(const TileSummary *sums, uint32_t n_tiles, ParseCarry *carry, TilePrefix *pre,
-                      const uint8_t *raw, uint32_t len, cudaStream_t st) {
-    tile_scan_kernel<<<1, 1024, 0, st>>>(sums, n_tiles, carry, pre, raw, len);
+void launch_pack(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, const uint32_t *st_state, uint8_t *sym,
+                 uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, cudaStream_t s) {
+    if (mode == MODE_LINES) pack_kernel<MODE_LINES><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
+    else if (mode == MODE_FASTA) pack_kernel<MODE_FASTA><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
+    else pack_kernel<MODE_FASTQ><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
+    front_fix_kernel<<<(g.n_st + 1 + 127) / 128, 128, 0, s>>>(sym, g, region_count, tail_in, tail_out);
 }
-void launch_pack(int mode, const uint8_t *raw, uint32_t len, ParseCarry *carry, const TilePrefix *pre,
-                 uint8_t *sym, uint32_t n_tiles, cudaStream_t st) {
-    if (mode == MODE_LINES) pack_kernel<MODE_LINES><<<n_tiles, TILE_THREADS, 0, st>>>(raw, len, carry, pre, sym);
-    else if (mode == MODE_FASTA) pack_kernel<MODE_FASTA><<<n_tiles, TILE_THREADS, 0, st>>>(raw, len, carry, pre, sym);
-    else pack_kernel<MODE_FASTQ><<<n_tiles, TILE_THREADS, 0, st>>>(raw, len, carry, pre, sym);
-}
-void launch_carry_front(uint8_t *symbuf, const ParseCarry *carry, cudaStream_t st) {
-    carry_front_kernel<<<1, SYM_FRONT, 0, st>>>(symbuf, carry);
-}
-void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t st) {
-    if (n) fill_bytes_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, n, v);
+void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t s) {
+    if (n) fill_bytes_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
 }
 
 }  // namespace fb2

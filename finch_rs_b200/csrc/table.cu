@@ -104,6 +104,90 @@ __global__ void gather_kernel(TableView t, SketchState *st, unsigned long long *
     slots[idx] = i;
 }
 
+__global__ void reset_gather_kernel(SketchState *st);
+
+// ---- pruning without a sort: 4096-bin histogram of the occupied keys -> threshold ----------------
+// Any threshold T' with #{keys <= T'} >= size is valid (a key of the final
+// bottom-s is never above an intermediate threshold), so the cut is placed on a bin boundary.
+constexpr int PRUNE_BINS = 4096;
+__global__ void __launch_bounds__(256)
+table_hist_kernel(TableView t, const SketchState *st, uint32_t shift, uint32_t *__restrict__ bins) {
+    __shared__ uint32_t h[PRUNE_BINS];
+    for (int i = threadIdx.x; i < PRUNE_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= t.cap; i += stride) {
+        unsigned long long key;
+        bool occ;
+        if (i == t.cap) { occ = st->has_max_key != 0u; key = EMPTY_KEY; }
+        else { key = t.key[i]; occ = key != EMPTY_KEY; }
+        if (occ) atomicAdd(&h[min((unsigned long long)(PRUNE_BINS - 1), key >> shift)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PRUNE_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&bins[i], h[i]);
+}
+// One block of 1024 threads, 4 bins each: smallest bin boundary with cumulative count >= size.
+__global__ void __launch_bounds__(1024)
+table_select_kernel(const uint32_t *__restrict__ bins, uint32_t shift, int scaled, unsigned long long size,
+                    unsigned long long max_hash, SketchState *st) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t b0 = bins[4 * tid], b1 = bins[4 * tid + 1], b2 = bins[4 * tid + 2], b3 = bins[4 * tid + 3];
+    const uint32_t c = b0 + b1 + b2 + b3;
+    uint32_t x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += n; }
+    if (lane == 31u) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0u) {
+        uint32_t v = wsum[lane], y = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, y, d); if (lane >= (uint32_t)d) y += n; }
+        wsum[lane] = y - v;
+    }
+    __syncthreads();
+    const unsigned long long before = (unsigned long long)wsum[wid] + x - c;  // keys in bins < 4*tid
+    if (tid == 0u) st->new_threshold = st->threshold;                          // default: no change
+    __syncthreads();
+    if (size > 0 && before < size && before + c >= size) {                     // the crossing is in my 4 bins
+        unsigned long long cum = before;
+        uint32_t b = 4 * tid;
+        const uint32_t bb[4] = {b0, b1, b2, b3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cum += bb[j]; if (cum >= size) { b = 4 * tid + j; break; } }
+        unsigned long long thr = ~0ULL;
+        if (b + 1u < (uint32_t)PRUNE_BINS && shift < 64u) {
+            const unsigned long long top = ((unsigned long long)(b + 1u)) << shift;
+            // (b+1) << shift may exceed 64 bits only for the last bin, excluded above
+            thr = top - 1ULL;
+        }
+        if (scaled && thr < max_hash) thr = max_hash;
+        if (thr < st->threshold) st->new_threshold = thr;
+    }
+}
+// Occupied slots with key <= new_threshold -> (key, slot), arbitrary order; count in gather_count.
+__global__ void gather_le_kernel(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > t.cap) return;
+    const unsigned long long thr = st->new_threshold;
+    unsigned long long key = EMPTY_KEY;
+    bool occ;
+    if (i == t.cap) occ = st->has_max_key != 0u;
+    else { key = t.key[i]; occ = key != EMPTY_KEY; }
+    occ = occ && key <= thr;
+    const uint32_t m = __ballot_sync(__activemask(), occ);
+    if (!occ) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&st->gather_count, (unsigned int)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const uint32_t idx = base + __popc(m & ((1u << lane) - 1u));
+    keys[idx] = key;
+    slots[idx] = i;
+}
+
 // ---- LSD radix sort, 8 bits per pass, (u64 key, u32 value), stable --------------------------
 // Work unit = one warp over a contiguous segment of SORT_SEG keys.
 constexpr int SORT_WARPS = 8;
@@ -255,6 +339,17 @@ void launch_radix_sort(unsigned long long *keys, uint32_t *vals, unsigned long l
         unsigned long long *tk = ka; ka = kb; kb = tk;
         uint32_t *tv = va; va = vb; vb = tv;
     }
+}
+// hist -> select -> filtered gather; the host then reads gather_count (= keys kept).
+void launch_prune_select(TableView t, SketchState *st, uint32_t shift, uint32_t *bins, int scaled,
+                         unsigned long long size, unsigned long long max_hash, unsigned long long *keys,
+                         uint32_t *slots, cudaStream_t s) {
+    cudaMemsetAsync(bins, 0, PRUNE_BINS * sizeof(uint32_t), s);
+    const uint32_t blocks = min(cdiv(t.cap + 1, 256), 592u);
+    table_hist_kernel<<<blocks, 256, 0, s>>>(t, st, shift, bins);
+    table_select_kernel<<<1, 1024, 0, s>>>(bins, shift, scaled, size, max_hash, st);
+    reset_gather_kernel<<<1, 1, 0, s>>>(st);
+    gather_le_kernel<<<cdiv(t.cap + 1, 256), 256, 0, s>>>(t, st, keys, slots);
 }
 uint32_t radix_hist_words(uint32_t n) { return 256u * cdiv(n ? n : 1, SORT_SEG); }
 
