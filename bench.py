@@ -247,8 +247,8 @@ def main():
             sk.feed_device(devbuf.data_ptr(), nbytes, final=True)
         else:
             sk.feed_fastx_ptr(host.data_ptr(), nbytes, final=True)
-        h, c, x, km, seq_len, n_kmers, fmt = sk.to_arrays()
-        hh, cc, xx = finish(h, c, x)
+        res = sk.sketch("bench.fq", fp)   # to_vec + filter_counts + process_post_filter (lib.rs:78-82)
+        hh, cc, xx, seq_len, n_kmers = res.hashes_u64, res.counts, res.extra_counts, res.seq_length, res.num_valid_kmers
         if dist is not None:  # one NCCL gather of the finished sketch (hash, count, extra) to rank 0
             t = torch.from_numpy(np.stack([hh.view(np.int64), cc.astype(np.int64), xx.astype(np.int64)])).to(dev)
             outl = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None

@@ -71,7 +71,7 @@ class _PairOut(C.Structure):
 EXPORTS = [
     "fb2_sketcher_create", "fb2_sketcher_destroy", "fb2_sketcher_reset", "fb2_sketcher_process",
     "fb2_sketcher_push", "fb2_sketcher_feed_fastx", "fb2_sketcher_feed_device", "fb2_sketcher_format",
-    "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_result_free", "fb2_sketcher_stats",
+    "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats",
     "fb2_sketcher_enable_timing", "fb2_filter_counts", "fb2_process_post_filter",
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_dist_batch",
     "fb2_dist_all_pairs", "fb2_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
@@ -102,6 +102,7 @@ def lib():
     L.fb2_sketcher_format.argtypes = [vp, C.POINTER(C.c_int32)]
     L.fb2_sketcher_totals.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.fb2_sketcher_result.argtypes = [vp, C.POINTER(_Result)]
+    L.fb2_sketcher_sketch.argtypes = [vp, C.c_char_p, C.POINTER(_Params), C.POINTER(_Filter), C.POINTER(_Result)]
     L.fb2_result_free.argtypes = [C.POINTER(_Result)]
     L.fb2_result_free.restype = None
     L.fb2_sketcher_stats.argtypes = [vp, C.POINTER(_Stats)]
@@ -326,6 +327,13 @@ class _Sketcher:
         """mod.rs:33-50: name "", default filters."""
         h, c, x, km, sl, nk, fmt = self.to_arrays()
         return Sketch("", sl, nk, "", h, c, x, km, FilterParams(), self.params, fmt)
+
+    def sketch(self, name: str, filters: "FilterParams") -> "Sketch":
+        """The tail of sketch_stream (lib.rs:78-93): to_vec + filter_counts + process_post_filter."""
+        r = _Result()
+        cp, cf = self.params._c(), filters._c()
+        _check(lib().fb2_sketcher_sketch(self._h, name.encode(), C.byref(cp), C.byref(cf), C.byref(r)))
+        return _finish(r, name, self.params)
 
     # -- bulk feeds (replace the record loop lib.rs:60-68) ---------------------------------------
     def feed_fastx(self, data, final=True):

@@ -43,12 +43,21 @@ struct ParseCarry {
     uint32_t pad;
 };
 
+// Counters of one hash launch (two slots: chunk c+1 may be hashed while chunk c is verified).
+struct LaunchSlot {
+    unsigned long long launch_kmers;  // valid k-mers seen by the launch
+    unsigned int log_count;           // entries appended to the slot's log (may exceed its capacity)
+    unsigned int decision;            // absorb_decide_kernel: 0 none, 1 absorbed, 2 log overflowed, 3 table too full
+    unsigned int chunk_syms;          // symbols of the chunk (copied from ParseCarry for the host)
+    unsigned int pad;
+};
+constexpr unsigned int DECIDE_GO = 1, DECIDE_OVERFLOW = 2, DECIDE_FULL = 3;
+
 // Sketch state (device resident; mirrored to the host when the host needs to decide).
 struct SketchState {
     unsigned long long threshold;     // admit hash <= threshold (only ever decreases)
-    unsigned long long total_kmers;   // committed
-    unsigned long long launch_kmers;  // valid k-mers seen by the current hash launch
-    unsigned int log_count;           // entries appended by the current hash launch (may exceed cap)
+    unsigned long long total_kmers;   // unused on device (the host commits per-launch counts)
+    LaunchSlot slot[2];               // per-launch counters, one per in-flight chunk
     unsigned int occupied;            // table slots in use (excl. the u64::MAX side slot)
     unsigned int has_max_key;         // side slot for hash == u64::MAX in use
     unsigned int gather_count;

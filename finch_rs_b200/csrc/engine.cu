@@ -94,15 +94,23 @@ struct fb2_sketcher {
     bool rawfree_pending[2] = {false, false};
 
     size_t chunk_bytes = 0;
-    DevBuf d_raw[2], d_sym, d_stmap, d_ststate, d_rcount, d_tail, d_carry, d_state;
+    DevBuf d_raw[2], d_sym[2], d_stmap, d_ststate, d_rcount[2], d_tail, d_carry, d_state;
     int tail_sel = 0;               // which half of d_tail holds the symbols carried into the next chunk
     uint64_t ordinal = 0;           // next position id (symbols of all regions so far + pushed k-mers)
-    DevBuf log_hash, log_kmer, log_posx;
+    DevBuf log_hash[2], log_kmer[2], log_posx[2];   // one candidate log per in-flight chunk
     uint32_t log_cap = 0;
+    int par = 0;                     // parity (slot / log / symbol buffer) of the next chunk
+    struct Pending { bool valid = false; ChunkGeom g{}; uint64_t ord_base = 0; } pend[2];
+    cudaEvent_t ev_chunk[2]{};
+    SketchState *h_snap[2] = {nullptr, nullptr};   // pinned snapshots written after each async chunk
+    bool steady = false;             // a whole chunk's candidates fit the log: chunks run asynchronously
     Table tab[2];
     int cur = 0;
     DevBuf sort_keys, sort_slots, sort_tkeys, sort_tslots, sort_hist, d_bins;
     DevBuf out_hash, out_cnt, out_ext, out_kmer, out_posx;
+    DevBuf sel_hash, sel_cnt, sel_ext, sel_kmer, sel_posx, sel_bytes, sel_idx;
+    uint8_t *h_res = nullptr;        // pinned read-back staging
+    size_t h_res_cap = 0;
     DevBuf d_push_bytes, d_push_offs, d_push_extra;
 
     ParseCarry *h_carry = nullptr;  // pinned mirrors
@@ -127,12 +135,13 @@ struct fb2_sketcher {
 };
 
 // ---- small helpers ---------------------------------------------------------------------------
-static LogView log_view(fb2_sketcher *s) {
+static LogView log_view(fb2_sketcher *s, int par) {
     LogView l;
-    l.hash = s->log_hash.as<unsigned long long>(); l.kmer = s->log_kmer.as<unsigned long long>();
-    l.posx = s->log_posx.as<unsigned long long>(); l.cap = s->log_cap;
+    l.hash = s->log_hash[par].as<unsigned long long>(); l.kmer = s->log_kmer[par].as<unsigned long long>();
+    l.posx = s->log_posx[par].as<unsigned long long>(); l.cap = s->log_cap;
     return l;
 }
+static inline LaunchSlot *dev_slot(fb2_sketcher *s, int par) { return &((SketchState *)s->d_state.p)->slot[par]; }
 static int pull_state(fb2_sketcher *s) {  // device -> pinned mirrors, then wait
     CU(cudaMemcpyAsync(s->h_state, s->d_state.p, sizeof(SketchState), cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(s->h_carry, s->d_carry.p, sizeof(ParseCarry), cudaMemcpyDeviceToHost, s->st));
@@ -175,7 +184,8 @@ static int reset_sketch_state(fb2_sketcher *s) {
     launch_fill_bytes(s->d_tail.as<uint8_t>(), 64, SYM_BREAK, s->st);
     s->stats.kernel_launches += 2;
     CU(cudaStreamSynchronize(s->st));
-    s->tail_sel = 0; s->ordinal = 0;
+    s->tail_sel = 0; s->ordinal = 0; s->par = 0; s->steady = false;
+    s->pend[0].valid = s->pend[1].valid = false;
     s->format = FB2_FORMAT_UNKNOWN; s->stream_open = false;
     s->lines_bases = 0; s->total_kmers = 0; s->stage_fill = 0; s->stage_mode = -1;
     s->next_launch = 32u * HASH_TILE;
@@ -233,15 +243,21 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
     do {
         if ((rc = s->d_carry.ensure(sizeof(ParseCarry))) != FB2_OK) break;
         if ((rc = s->d_state.ensure(sizeof(SketchState))) != FB2_OK) break;
-        if ((rc = s->d_sym.ensure(SYM_FRONT + 4096)) != FB2_OK) break;
         if ((rc = s->d_tail.ensure(64)) != FB2_OK) break;
         if (cudaHostAlloc((void **)&s->h_carry, sizeof(ParseCarry), cudaHostAllocDefault) != cudaSuccess ||
             cudaHostAlloc((void **)&s->h_state, sizeof(SketchState), cudaHostAllocDefault) != cudaSuccess) {
             rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed"); break;
         }
-        if ((rc = s->log_hash.ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
-        if ((rc = s->log_kmer.ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
-        if ((rc = s->log_posx.ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
+        for (int i = 0; i < 2 && rc == FB2_OK; ++i) {
+            if ((rc = s->log_hash[i].ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
+            if ((rc = s->log_kmer[i].ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
+            if ((rc = s->log_posx[i].ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
+            if (cudaHostAlloc((void **)&s->h_snap[i], sizeof(SketchState), cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) {
+                rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc/cudaEventCreate failed");
+            }
+        }
+        if (rc != FB2_OK) break;
         uint64_t want = s->size ? 4 * s->size : 1;
         if (want < (1u << 16)) want = 1u << 16;
         if (want > (1u << 22)) want = 1u << 22;  // grows on demand
@@ -268,11 +284,18 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     if (s->ev_t1) cudaEventDestroy(s->ev_t1);
     if (s->ev_p0) cudaEventDestroy(s->ev_p0);
     if (s->ev_p1) cudaEventDestroy(s->ev_p1);
-    s->d_sym.release(); s->d_stmap.release(); s->d_ststate.release(); s->d_rcount.release(); s->d_tail.release();
+    for (int i = 0; i < 2; ++i) {
+        s->d_sym[i].release(); s->d_rcount[i].release(); s->log_hash[i].release(); s->log_kmer[i].release(); s->log_posx[i].release();
+        if (s->h_snap[i]) cudaFreeHost(s->h_snap[i]);
+        if (s->ev_chunk[i]) cudaEventDestroy(s->ev_chunk[i]);
+    }
+    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release();
     s->d_carry.release(); s->d_state.release();
-    s->log_hash.release(); s->log_kmer.release(); s->log_posx.release();
     s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release(); s->d_bins.release();
     s->out_hash.release(); s->out_cnt.release(); s->out_ext.release(); s->out_kmer.release(); s->out_posx.release();
+    s->sel_hash.release(); s->sel_cnt.release(); s->sel_ext.release(); s->sel_kmer.release(); s->sel_posx.release();
+    s->sel_bytes.release(); s->sel_idx.release();
+    if (s->h_res) cudaFreeHost(s->h_res);
     s->d_push_bytes.release(); s->d_push_offs.release(); s->d_push_extra.release();
     if (s->h_carry) cudaFreeHost(s->h_carry);
     if (s->h_state) cudaFreeHost(s->h_state);
@@ -286,6 +309,7 @@ extern "C" int fb2_sketcher_reset(fb2_sketcher *s) {
     if (!s) return fb2_fail(FB2_EINVAL, "null handle");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->st));
+    CU(cudaStreamSynchronize(s->copy_st));
     return reset_sketch_state(s);
 }
 
@@ -346,7 +370,7 @@ static int prune(fb2_sketcher *s, uint32_t need_room) {
 // Absorb log[0, cnt) into the table, pruning / growing so the table never passes 3/4 load.
 // Between pulls the host only knows an upper bound of the occupancy (every absorbed entry may be
 // a new key); it fetches the exact value before deciding to prune.
-static int absorb_log(fb2_sketcher *s, uint32_t cnt) {
+static int absorb_log(fb2_sketcher *s, int par, uint32_t cnt) {
     uint32_t i = 0;
     bool exact = true;  // h_state->occupied is exact right after a pull
     while (i < cnt) {
@@ -361,7 +385,7 @@ static int absorb_log(fb2_sketcher *s, uint32_t cnt) {
             continue;
         }
         const uint32_t m = std::min(left, room);
-        launch_absorb(log_view(s), i, i + m, s->tab[s->cur].view(), (SketchState *)s->d_state.p, s->st);
+        launch_absorb(log_view(s, par), i, i + m, s->tab[s->cur].view(), (SketchState *)s->d_state.p, s->st);
         s->stats.kernel_launches += 2;
         i += m;
         s->h_state->occupied = occ + m;  // upper bound until the next pull
@@ -397,10 +421,13 @@ static ChunkGeom make_geom(uint32_t len) {
     return g;
 }
 
-// Hash the regions of the current chunk in launches sized so the candidate log cannot overflow
-// unnoticed, absorbing the log after each launch.
-static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base) {
+// Synchronous hashing of a chunk's regions: launches sized so the candidate log cannot overflow
+// unnoticed, the host reads the counters after each launch and absorbs the log (pruning as needed).
+// Used while the threshold is still falling (early in a stream), for redo after a log overflow,
+// and when kernel timing is on.
+static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, int par) {
     SketchState *dst = (SketchState *)s->d_state.p;
+    LaunchSlot *slot = dev_slot(s, par);
     const uint32_t total_blocks = g.n_st * g.hash_tiles;
     uint32_t b = 0;
     bool known = false;
@@ -408,11 +435,10 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base) {
     while (b < total_blocks) {
         uint32_t nb = std::max<uint32_t>(s->next_launch / HASH_TILE, 1u);
         nb = std::min(nb, total_blocks - b);
-        CU(cudaMemsetAsync(&dst->log_count, 0, sizeof(unsigned int), s->st));
-        CU(cudaMemsetAsync(&dst->launch_kmers, 0, sizeof(unsigned long long), s->st));
+        CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
         if (s->timing) CU(cudaEventRecord(s->ev_t0, s->st));
-        launch_hash(s->k, s->d_sym.as<uint8_t>(), g, b, b + nb, s->d_rcount.as<uint32_t>(), ord_base, dst, log_view(s),
-                    s->prm.hash_seed, s->st);
+        launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, b, b + nb, s->d_rcount[par].as<uint32_t>(), ord_base, dst, slot,
+                    log_view(s, par), s->prm.hash_seed, s->st);
         if (s->timing) CU(cudaEventRecord(s->ev_t1, s->st));
         s->stats.kernel_launches++; s->stats.hash_launches++;
         TRY(pull_state(s));
@@ -427,13 +453,14 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base) {
             fill = std::max(1e-6, (double)s->h_carry->chunk_syms / ((double)total_blocks * HASH_TILE));
             if (s->h_carry->chunk_syms == 0) break;  // nothing to hash in this chunk
         }
-        const uint32_t cnt = s->h_state->log_count;
+        const uint32_t cnt = s->h_state->slot[par].log_count;
         if (cnt > s->log_cap) {  // log overflowed: nothing committed, redo this range in smaller launches
             s->next_launch = std::max<uint32_t>(HASH_TILE, std::min((nb * HASH_TILE) / 4, s->log_cap / HASH_TILE * HASH_TILE));
+            s->steady = false;
             continue;
         }
-        s->total_kmers += s->h_state->launch_kmers;
-        TRY(absorb_log(s, cnt));
+        s->total_kmers += s->h_state->slot[par].launch_kmers;
+        TRY(absorb_log(s, par, cnt));
         b += nb;
         // next launch: aim the candidate count at a quarter of the log
         const double walked = std::max(1.0, (double)nb * HASH_TILE * fill);
@@ -445,17 +472,63 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base) {
     return FB2_OK;
 }
 
+// Verify an asynchronously hashed chunk one chunk later: commit its counters, or redo / prune in the
+// rare cases the device-side guard declined to absorb its log.
+static int settle(fb2_sketcher *s, int q) {
+    if (!s->pend[q].valid) return FB2_OK;
+    s->pend[q].valid = false;
+    CU(cudaEventSynchronize(s->ev_chunk[q]));
+    const SketchState snap = *s->h_snap[q];
+    const LaunchSlot sl = snap.slot[q];
+    const ChunkGeom g = s->pend[q].g;
+    s->stats.hash_symbols += sl.chunk_syms;
+    if (sl.decision == DECIDE_OVERFLOW) {
+        // nothing of this chunk was absorbed: hash it again in bounded launches
+        const double pos = (double)g.n_st * g.hash_tiles * HASH_TILE;
+        s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (uint32_t)std::min(pos / 4.0, (double)(s->log_cap / 2)));
+        s->steady = false;
+        TRY(pull_state(s));
+        return hash_range(s, g, s->pend[q].ord_base, q);
+    }
+    s->total_kmers += sl.launch_kmers;
+    if (sl.decision == DECIDE_FULL) {
+        TRY(pull_state(s));
+        TRY(absorb_log(s, q, sl.log_count));
+    } else {
+        *s->h_state = snap;   // exact as of the end of this chunk's absorb
+    }
+    // adapt the launch size to the observed candidate rate
+    const double pos = std::max(1.0, (double)g.n_st * g.hash_tiles * HASH_TILE);
+    const double per_pos = std::max((double)sl.log_count, 1.0) / pos;
+    double next = (double)(s->log_cap / 4) / per_pos;
+    if (next > 2147483648.0) next = 2147483648.0;
+    s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (uint32_t)next);
+    if (s->h_state->occupied > s->tab[s->cur].cap / 2) {
+        TRY(pull_state(s));   // drains the stream: later chunks may already have absorbed more
+        if (s->h_state->occupied > s->tab[s->cur].cap / 2) TRY(prune(s, 0));
+    }
+    return FB2_OK;
+}
+static int settle_all(fb2_sketcher *s) {
+    TRY(settle(s, s->par));       // older chunk first
+    TRY(settle(s, s->par ^ 1));
+    return FB2_OK;
+}
+
 static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mode, int rawbuf /* -1: not ours */) {
     if (!len) return FB2_OK;
+    const int par = s->par;
+    TRY(settle(s, par));           // its buffers are about to be reused (normally already settled)
     const ChunkGeom g = make_geom(len);
     TRY(s->d_stmap.ensure((size_t)g.n_st * 4)); TRY(s->d_ststate.ensure((size_t)g.n_st * 4));
-    TRY(s->d_rcount.ensure((size_t)g.n_st * 4));
-    TRY(s->d_sym.ensure((size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + 2 * HASH_TILE));
+    TRY(s->d_rcount[par].ensure((size_t)g.n_st * 4));
+    TRY(s->d_sym[par].ensure((size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + 2 * HASH_TILE));
     ParseCarry *dc = (ParseCarry *)s->d_carry.p;
+    SketchState *dst = (SketchState *)s->d_state.p;
     uint8_t *tail_in = s->d_tail.as<uint8_t>() + 32 * s->tail_sel, *tail_out = s->d_tail.as<uint8_t>() + 32 * (s->tail_sel ^ 1);
     if (s->timing) CU(cudaEventRecord(s->ev_p0, s->st));
     launch_phase(mode, d_raw, g, dc, s->d_stmap.as<uint32_t>(), s->d_ststate.as<uint32_t>(), s->st);
-    launch_pack(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym.as<uint8_t>(), s->d_rcount.as<uint32_t>(),
+    launch_pack(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym[par].as<uint8_t>(), s->d_rcount[par].as<uint32_t>(),
                 tail_in, tail_out, s->st);
     if (s->timing) CU(cudaEventRecord(s->ev_p1, s->st));
     if (rawbuf >= 0) { CU(cudaEventRecord(s->ev_rawfree[rawbuf], s->st)); s->rawfree_pending[rawbuf] = true; }
@@ -463,7 +536,30 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     s->stats.kernel_launches += (mode == MODE_LINES ? 3 : 4); s->stats.chunks++;
     const uint64_t ord_base = s->ordinal;
     s->ordinal += (uint64_t)g.n_st * g.st_bytes;
-    TRY(hash_range(s, g, ord_base));
+    s->par ^= 1;
+
+    const uint32_t total_blocks = g.n_st * g.hash_tiles;
+    const double positions = (double)total_blocks * HASH_TILE;
+    if (!s->timing && positions <= (double)s->next_launch) s->steady = true;
+    if (s->steady && !s->timing && positions <= (double)s->next_launch) {
+        // asynchronous: hash the whole chunk, let the device decide about absorbing, snapshot the
+        // state; the host looks at the outcome while the next chunk is already running
+        LaunchSlot *slot = dev_slot(s, par);
+        CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
+        launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, total_blocks, s->d_rcount[par].as<uint32_t>(), ord_base, dst,
+                    slot, log_view(s, par), s->prm.hash_seed, s->st);
+        launch_absorb_guarded(log_view(s, par), slot, s->tab[s->cur].view(), dst, dc, s->log_cap / 4, s->st);
+        CU(cudaMemcpyAsync(s->h_snap[par], dst, sizeof(SketchState), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaEventRecord(s->ev_chunk[par], s->st));
+        s->stats.kernel_launches += 4; s->stats.hash_launches++;
+        s->stats.d2h_bytes += sizeof(SketchState);
+        s->pend[par].valid = true; s->pend[par].g = g; s->pend[par].ord_base = ord_base;
+        TRY(settle(s, par ^ 1));   // the previous chunk, while this one runs
+    } else {
+        TRY(settle(s, par ^ 1));
+        TRY(pull_state(s));
+        TRY(hash_range(s, g, ord_base, par));
+    }
     if (s->timing) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, s->ev_p0, s->ev_p1));
@@ -521,6 +617,8 @@ static int ensure_stage(fb2_sketcher *s) {
 static int flush_push(fb2_sketcher *s) {
     const uint32_t n = (uint32_t)s->push_extra.size();
     if (!n) return FB2_OK;
+    TRY(settle_all(s));
+    const int par = s->par;
     TRY(s->d_push_bytes.ensure(s->push_bytes.size() + 16));
     TRY(s->d_push_offs.ensure((size_t)(n + 1) * 4));
     TRY(s->d_push_extra.ensure(n));
@@ -529,22 +627,23 @@ static int flush_push(fb2_sketcher *s) {
     CU(cudaMemcpyAsync(s->d_push_extra.p, s->push_extra.data(), n, cudaMemcpyHostToDevice, s->st));
     s->stats.h2d_bytes += s->push_bytes.size() + (size_t)(n + 1) * 4 + n;
     SketchState *dst = (SketchState *)s->d_state.p;
-    CU(cudaMemsetAsync(&dst->log_count, 0, sizeof(unsigned int), s->st));
-    CU(cudaMemsetAsync(&dst->launch_kmers, 0, sizeof(unsigned long long), s->st));
+    LaunchSlot *slot = dev_slot(s, par);
+    CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
     launch_push_hash(s->d_push_bytes.as<uint8_t>(), s->d_push_offs.as<uint32_t>(), s->d_push_extra.as<uint8_t>(), n,
-                     s->arena_flushed, s->ordinal, dst, log_view(s), s->prm.hash_seed, s->st);
+                     s->arena_flushed, s->ordinal, dst, slot, log_view(s, par), s->prm.hash_seed, s->st);
     s->ordinal += n;
     s->stats.kernel_launches += 2;
     TRY(pull_state(s));
-    s->total_kmers += s->h_state->launch_kmers;
+    s->total_kmers += s->h_state->slot[par].launch_kmers;
     s->arena_flushed += n;
     s->push_bytes.clear(); s->push_extra.clear(); s->push_offs.assign(1, 0u);
-    TRY(absorb_log(s, s->h_state->log_count));
+    TRY(absorb_log(s, par, s->h_state->slot[par].log_count));
     return FB2_OK;
 }
 static int flush_all(fb2_sketcher *s) {
     TRY(flush_stage(s));
     TRY(flush_push(s));
+    TRY(settle_all(s));
     return FB2_OK;
 }
 
@@ -607,6 +706,7 @@ static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
 }
 static int end_stream(fb2_sketcher *s) {
     TRY(flush_stage(s));
+    TRY(settle_all(s));
     TRY(pull_state(s));
     ParseCarry *c = s->h_carry;
     int rc = FB2_OK;
@@ -682,7 +782,12 @@ extern "C" int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev, siz
                 TRY(s->d_raw[0].ensure(n + 64));
                 CU(cudaMemcpyAsync(s->d_raw[0].p, dev + off, n, cudaMemcpyDeviceToDevice, s->st));
                 TRY(run_chunk(s, s->d_raw[0].as<uint8_t>(), (uint32_t)n, mode, -1));
+                CU(cudaStreamSynchronize(s->st));   // d_raw[0] is reused by the next piece
             }
+        }
+        if (aligned) {  // the caller may release `dev` after we return: the parse kernels must be done
+            CU(cudaEventRecord(s->ev_rawfree[0], s->st));
+            CU(cudaEventSynchronize(s->ev_rawfree[0]));
         }
     }
     if (final) {
@@ -715,20 +820,26 @@ extern "C" void fb2_result_free(fb2_result *r) {
     r->hashes = nullptr; r->counts = nullptr; r->extras = nullptr; r->kmers = nullptr; r->n = 0;
 }
 
-extern "C" int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out) {
-    if (!s || !out) return fb2_fail(FB2_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
-    memset(out, 0, sizeof(*out));
-    TRY(flush_all(s));
+// hostlogic.cpp
+int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, fb2_filter *f, int format,
+                      std::vector<uint32_t> &keep);
+
+// Pinned host staging for result read-back (grown on demand).
+static int ensure_hres(fb2_sketcher *s, size_t bytes) {
+    if (bytes <= s->h_res_cap) return FB2_OK;
+    if (s->h_res) cudaFreeHost(s->h_res);
+    s->h_res = nullptr; s->h_res_cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    CU(cudaHostAlloc((void **)&s->h_res, want, cudaHostAllocDefault));
+    s->h_res_cap = want;
+    return FB2_OK;
+}
+
+// Sort the table and export the kept entries as device SoA (out_hash/out_cnt/out_ext/out_kmer/out_posx).
+static int export_sorted(fb2_sketcher *s, uint32_t *keep_out) {
     uint32_t n = 0;
     TRY(sort_table(s, &n));
     const uint32_t keep = s->h_state->keep_count;
-    std::vector<unsigned long long> h_kmer(keep), h_posx(keep);
-    out->n = keep;
-    out->hashes = (uint64_t *)malloc(std::max<size_t>(1, (size_t)keep * 8));
-    out->counts = (uint32_t *)malloc(std::max<size_t>(1, (size_t)keep * 4));
-    out->extras = (uint32_t *)malloc(std::max<size_t>(1, (size_t)keep * 4));
-    if (!out->hashes || !out->counts || !out->extras) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
     if (keep) {
         TRY(s->out_hash.ensure((size_t)keep * 8)); TRY(s->out_kmer.ensure((size_t)keep * 8));
         TRY(s->out_posx.ensure((size_t)keep * 8));
@@ -737,31 +848,124 @@ extern "C" int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out) {
                       s->out_hash.as<unsigned long long>(), s->out_cnt.as<uint32_t>(), s->out_ext.as<uint32_t>(),
                       s->out_kmer.as<unsigned long long>(), s->out_posx.as<unsigned long long>(), s->st);
         s->stats.kernel_launches++;
-        CU(cudaMemcpyAsync(out->hashes, s->out_hash.p, (size_t)keep * 8, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaMemcpyAsync(out->counts, s->out_cnt.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaMemcpyAsync(out->extras, s->out_ext.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaMemcpyAsync(h_kmer.data(), s->out_kmer.p, (size_t)keep * 8, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaMemcpyAsync(h_posx.data(), s->out_posx.p, (size_t)keep * 8, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaStreamSynchronize(s->st));
-        s->stats.d2h_bytes += (size_t)keep * 32;
     }
-    // k-mer bytes: 2-bit codes -> ASCII, or the bytes handed to push()
-    size_t stride = (size_t)s->k;
-    for (uint32_t i = 0; i < keep; ++i)
-        if (h_posx[i] & (1ULL << 8)) stride = std::max(stride, s->arena[(size_t)h_kmer[i]].size());
-    out->kmer_stride = (uint32_t)stride;
-    out->kmers = (uint8_t *)calloc(std::max<size_t>(1, (size_t)keep * stride), 1);
+    *keep_out = keep;
+    return FB2_OK;
+}
+
+// Bring m exported rows to the host as an fb2_result: rows idx[0..m) (device indices) or the first m.
+static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_result *out) {
+    const size_t stride = (size_t)s->k;   // pushed k-mers may be longer: fixed up below
+    out->n = m;
+    out->hashes = (uint64_t *)malloc(std::max<size_t>(1, (size_t)m * 8));
+    out->counts = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
+    out->extras = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
+    if (!out->hashes || !out->counts || !out->extras) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
+    std::vector<unsigned long long> h_kmer(m), h_posx(m);
+    std::vector<uint8_t> bytes((size_t)m * stride);
+    if (m) {
+        TRY(s->sel_hash.ensure((size_t)m * 8)); TRY(s->sel_kmer.ensure((size_t)m * 8)); TRY(s->sel_posx.ensure((size_t)m * 8));
+        TRY(s->sel_cnt.ensure((size_t)m * 4)); TRY(s->sel_ext.ensure((size_t)m * 4)); TRY(s->sel_bytes.ensure((size_t)m * stride));
+        const uint32_t *d_idx = nullptr;
+        if (h_idx) {
+            TRY(s->sel_idx.ensure((size_t)m * 4));
+            CU(cudaMemcpyAsync(s->sel_idx.p, h_idx, (size_t)m * 4, cudaMemcpyHostToDevice, s->st));
+            s->stats.h2d_bytes += (size_t)m * 4;
+            d_idx = s->sel_idx.as<uint32_t>();
+        }
+        launch_select_rows(d_idx, m, s->k, (uint32_t)stride, s->out_hash.as<unsigned long long>(), s->out_cnt.as<uint32_t>(),
+                           s->out_ext.as<uint32_t>(), s->out_kmer.as<unsigned long long>(), s->out_posx.as<unsigned long long>(),
+                           s->sel_hash.as<unsigned long long>(), s->sel_cnt.as<uint32_t>(), s->sel_ext.as<uint32_t>(),
+                           s->sel_kmer.as<unsigned long long>(), s->sel_posx.as<unsigned long long>(),
+                           s->sel_bytes.as<uint8_t>(), s->st);
+        s->stats.kernel_launches++;
+        // one pinned staging block: hash | kmer | posx | cnt | ext | bytes
+        const size_t o_hash = 0, o_kmer = (size_t)m * 8, o_posx = (size_t)m * 16, o_cnt = (size_t)m * 24,
+                     o_ext = (size_t)m * 28, o_bytes = (size_t)m * 32, total = o_bytes + (size_t)m * stride;
+        TRY(ensure_hres(s, total));
+        CU(cudaMemcpyAsync(s->h_res + o_hash, s->sel_hash.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(s->h_res + o_kmer, s->sel_kmer.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(s->h_res + o_posx, s->sel_posx.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(s->h_res + o_cnt, s->sel_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(s->h_res + o_ext, s->sel_ext.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(s->h_res + o_bytes, s->sel_bytes.p, (size_t)m * stride, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        s->stats.d2h_bytes += total;
+        memcpy(out->hashes, s->h_res + o_hash, (size_t)m * 8);
+        memcpy(h_kmer.data(), s->h_res + o_kmer, (size_t)m * 8);
+        memcpy(h_posx.data(), s->h_res + o_posx, (size_t)m * 8);
+        memcpy(out->counts, s->h_res + o_cnt, (size_t)m * 4);
+        memcpy(out->extras, s->h_res + o_ext, (size_t)m * 4);
+        memcpy(bytes.data(), s->h_res + o_bytes, (size_t)m * stride);
+    }
+    // k-mer bytes: expanded on the device; entries that came through push() carry the caller's bytes
+    size_t ostride = stride;
+    for (uint32_t i = 0; i < m; ++i)
+        if (h_posx[i] & (1ULL << 8)) ostride = std::max(ostride, s->arena[(size_t)h_kmer[i]].size());
+    out->kmer_stride = (uint32_t)ostride;
+    out->kmers = (uint8_t *)calloc(std::max<size_t>(1, (size_t)m * ostride), 1);
     if (!out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
-    for (uint32_t i = 0; i < keep; ++i) {
-        uint8_t *dst = out->kmers + (size_t)i * stride;
+    for (uint32_t i = 0; i < m; ++i) {
+        uint8_t *dst = out->kmers + (size_t)i * ostride;
         if (h_posx[i] & (1ULL << 8)) { const std::string &a = s->arena[(size_t)h_kmer[i]]; memcpy(dst, a.data(), a.size()); }
-        else codes_to_ascii(h_kmer[i], s->k, dst);
+        else memcpy(dst, bytes.data() + (size_t)i * stride, stride);
     }
     out->seq_length = s->h_carry->total_bases + s->lines_bases;
     out->num_valid_kmers = s->total_kmers;
     out->format = s->format;
     out->filters.filter_on = 0;
     return FB2_OK;
+}
+
+extern "C" int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out) {
+    if (!s || !out) return fb2_fail(FB2_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    memset(out, 0, sizeof(*out));
+    TRY(flush_all(s));
+    uint32_t keep = 0;
+    TRY(export_sorted(s, &keep));
+    return collect_rows(s, nullptr, keep, out);
+}
+
+// to_vec -> filter_counts -> process_post_filter (lib.rs:78-82), moving only what is needed:
+// counts/extras of every entry for the filter decisions, then the surviving rows.
+extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_params *p, const fb2_filter *f,
+                                   fb2_result *out) {
+    if (!s || !p || !f || !out) return fb2_fail(FB2_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    memset(out, 0, sizeof(*out));
+    TRY(flush_all(s));
+    uint32_t keep = 0;
+    TRY(export_sorted(s, &keep));
+    fb2_filter ff = *f;
+    if (ff.filter_on < 0) {  // lib.rs:71-76
+        if (s->format == FB2_FORMAT_FASTA) ff.filter_on = 0;
+        else if (s->format == FB2_FORMAT_FASTQ) ff.filter_on = 1;
+        else return fb2_fail(FB2_EEMPTY, "Should have got a type");
+    }
+    std::vector<uint32_t> sel;
+    const uint32_t *idx = nullptr;
+    uint32_t m = keep;
+    if (ff.filter_on == 1 && keep) {
+        TRY(ensure_hres(s, (size_t)keep * 8));
+        uint32_t *hc = (uint32_t *)s->h_res, *hx = hc + keep;
+        CU(cudaMemcpyAsync(hc, s->out_cnt.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(hx, s->out_ext.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        s->stats.d2h_bytes += (size_t)keep * 8;
+        TRY(fb2_filter_select(hc, hx, keep, &ff, s->format, sel));
+        m = (uint32_t)sel.size();
+        idx = sel.data();
+    }
+    if (p->kind == FB2_KIND_MASH) {  // process_post_filter (mod.rs:115-128)
+        if (m > p->final_size) m = (uint32_t)p->final_size;
+        if (!p->no_strict && m < p->final_size)
+            return fb2_fail(FB2_ETOOFEW, std::string(name ? name : "") + " had too few kmers (" + std::to_string(m) +
+                                             ") to sketch");
+    }
+    const int rc = collect_rows(s, idx, m, out);
+    if (rc == FB2_OK) out->filters = ff;
+    return rc;
 }
 
 extern "C" int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out) {

@@ -24,8 +24,8 @@ template <int K>
 __global__ void __launch_bounds__(HASH_THREADS)
 hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r starts at SYM_FRONT + r * region_stride
             ChunkGeom g, uint32_t b0,             // first hash block (region-major) of this launch
-            const uint32_t *__restrict__ region_count, uint64_t ord_base, SketchState *st, LogView log,
-            int k_rt, uint64_t seed) {
+            const uint32_t *__restrict__ region_count, uint64_t ord_base, const SketchState *st,
+            LaunchSlot *slot, LogView log, int k_rt, uint64_t seed) {
     const int k = K > 0 ? K : k_rt;
     const uint64_t mask = kmer_mask(k);
     const uint32_t blk = b0 + blockIdx.x;
@@ -72,7 +72,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
             if (em) {  // warp-aggregated append
                 const int leader = __ffs(em) - 1;
                 uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(&st->log_count, (unsigned int)__popc(em));
+                if ((int)lane == leader) base = atomicAdd(&slot->log_count, (unsigned int)__popc(em));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (emit) {
                     const uint32_t idx = base + __popc(em & lanemask_lt());
@@ -87,20 +87,20 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
     }
     // valid-window count of this launch (committed to total_kmers by the host on success)
     nvalid = __reduce_add_sync(0xffffffffu, nvalid);
-    if (lane == 0 && nvalid) atomicAdd(&st->launch_kmers, (unsigned long long)nvalid);
+    if (lane == 0 && nvalid) atomicAdd(&slot->launch_kmers, (unsigned long long)nvalid);
 }
 
 // `push` unit-test surface (mash.rs:34 / scaled.rs:37): hash arbitrary byte strings.
 __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32_t *__restrict__ offs,
                                  const uint8_t *__restrict__ extra, uint32_t n, uint64_t arena_base,
-                                 uint64_t ord_base, SketchState *st, LogView log, uint64_t seed) {
+                                 uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, uint64_t seed) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t a = offs[i], b = offs[i + 1];
     const uint64_t h = murmur_bytes_h1(bytes + a, b - a, seed);
     const unsigned long long T = st->threshold;
     if (h <= T) {
-        const uint32_t idx = atomicAdd(&st->log_count, 1u);
+        const uint32_t idx = atomicAdd(&slot->log_count, 1u);
         if (idx < log.cap) {
             log.hash[idx] = h;
             log.kmer[idx] = arena_base + i;
@@ -108,22 +108,23 @@ __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32
         }
     }
 }
-__global__ void push_commit_kernel(SketchState *st, uint32_t n) { st->launch_kmers += n; }
+__global__ void push_commit_kernel(LaunchSlot *slot, uint32_t n) { slot->launch_kmers += n; }
 
 void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t b0, uint32_t b1, const uint32_t *region_count,
-                 uint64_t ord_base, SketchState *st, LogView log, uint64_t seed, cudaStream_t stream) {
+                 uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, uint64_t seed,
+                 cudaStream_t stream) {
     if (b1 <= b0) return;
     const uint32_t blocks = b1 - b0;
-    if (k == 21) hash_kernel<21><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, log, k, seed);
-    else if (k == 31) hash_kernel<31><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, log, k, seed);
-    else hash_kernel<0><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, log, k, seed);
+    if (k == 21) hash_kernel<21><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, slot, log, k, seed);
+    else if (k == 31) hash_kernel<31><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, slot, log, k, seed);
+    else hash_kernel<0><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, slot, log, k, seed);
 }
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
-                      uint64_t arena_base, uint64_t ord_base, SketchState *st, LogView log,
+                      uint64_t arena_base, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
                       uint64_t seed, cudaStream_t stream) {
     if (!n) return;
-    push_hash_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bytes, offs, extra, n, arena_base, ord_base, st, log, seed);
-    push_commit_kernel<<<1, 1, 0, stream>>>(st, n);
+    push_hash_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bytes, offs, extra, n, arena_base, ord_base, st, slot, log, seed);
+    push_commit_kernel<<<1, 1, 0, stream>>>(slot, n);
 }
 
 }  // namespace fb2

@@ -54,7 +54,7 @@ extern "C" uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n,
         ++wgt_cutoff;
     }
     if (wgt_cutoff == 0) return 1;
-    // left-most... actually right-most minimum of the sliding window sum left of the cutoff
+    // minimum of the sliding window sum left of the cutoff (ties: the right-most window)
     const size_t win = std::max<size_t>(1, wgt_cutoff / 20);
     uint64_t sum = 0;
     for (size_t c = 0; c < win; ++c) sum += hist[c];
@@ -68,36 +68,59 @@ extern "C" uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n,
     return (uint32_t)lowest_idx + 1;
 }
 
-extern "C" int fb2_filter_counts(fb2_result *r, fb2_filter *f) {
-    if (!r || !f) return fb2_fail(FB2_EINVAL, "null argument");
+// Core of FilterParams::filter_counts on bare (count, extra) columns: writes the indices that
+// survive, ascending, and updates `f` like the reference (filter_on resolved, abun_low raised).
+int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, fb2_filter *f, int format,
+                      std::vector<uint32_t> &keep) {
     if (f->filter_on < 0) {  // lib.rs:71-76
-        if (r->format == FB2_FORMAT_FASTA) f->filter_on = 0;
-        else if (r->format == FB2_FORMAT_FASTQ) f->filter_on = 1;
+        if (format == FB2_FORMAT_FASTA) f->filter_on = 0;
+        else if (format == FB2_FORMAT_FASTQ) f->filter_on = 1;
         else return fb2_fail(FB2_EEMPTY, "Should have got a type");
     }
+    keep.resize(n);
+    for (size_t i = 0; i < n; ++i) keep[i] = (uint32_t)i;
     const bool on = f->filter_on == 1;
-    if (on && f->strand_filter > 0.0) {
-        std::vector<uint8_t> keep(r->n, 1);
-        for (uint64_t i = 0; i < r->n; ++i) {
-            const uint32_t c = r->counts[i];
-            if (c < 16) continue;  // too few observations to call an adapter
-            const uint32_t lowest = std::min(r->extras[i], c - r->extras[i]);
-            keep[i] = ((double)lowest / (double)c) >= f->strand_filter;
+    if (on && f->strand_filter > 0.0) {  // filter_strands (filtering.rs:413-432)
+        size_t m = 0;
+        for (size_t j = 0; j < keep.size(); ++j) {
+            const uint32_t i = keep[j], c = counts[i];
+            bool ok = true;
+            if (c >= 16) {  // fewer observations are too noisy to call an adapter
+                const uint32_t lowest = std::min(extras[i], c - extras[i]);
+                ok = ((double)lowest / (double)c) >= f->strand_filter;
+            }
+            if (ok) keep[m++] = i;
         }
-        compact(r, keep);
+        keep.resize(m);
     }
-    if (on && f->err_filter > 0.0) {
-        const uint32_t cutoff = fb2_guess_filter_threshold(r->counts, (size_t)r->n, f->err_filter);
+    if (on && f->err_filter > 0.0) {     // guess_filter_threshold on what is left (filtering.rs:68-79)
+        std::vector<uint32_t> c(keep.size());
+        for (size_t j = 0; j < keep.size(); ++j) c[j] = counts[keep[j]];
+        const uint32_t cutoff = fb2_guess_filter_threshold(c.data(), c.size(), f->err_filter);
         if (f->has_abun_low) { if (cutoff > f->abun_low) f->abun_low = cutoff; }
         else { f->has_abun_low = 1; f->abun_low = cutoff; }
     }
-    if (on && (f->has_abun_low || f->has_abun_high)) {
+    if (on && (f->has_abun_low || f->has_abun_high)) {  // filter_abundance (filtering.rs:329-343)
         const uint32_t lo = f->has_abun_low ? f->abun_low : 0u;
         const uint32_t hi = f->has_abun_high ? f->abun_high : UINT32_MAX;
-        std::vector<uint8_t> keep(r->n);
-        for (uint64_t i = 0; i < r->n; ++i) keep[i] = lo <= r->counts[i] && r->counts[i] <= hi;
-        compact(r, keep);
+        size_t m = 0;
+        for (size_t j = 0; j < keep.size(); ++j) {
+            const uint32_t c = counts[keep[j]];
+            if (lo <= c && c <= hi) keep[m++] = keep[j];
+        }
+        keep.resize(m);
     }
+    return FB2_OK;
+}
+
+extern "C" int fb2_filter_counts(fb2_result *r, fb2_filter *f) {
+    if (!r || !f) return fb2_fail(FB2_EINVAL, "null argument");
+    std::vector<uint32_t> keep;
+    const int rc = fb2_filter_select(r->counts, r->extras, (size_t)r->n, f, r->format, keep);
+    if (rc != FB2_OK) return rc;
+    std::vector<uint8_t> flag((size_t)r->n, 0);
+    for (uint32_t i : keep) flag[i] = 1;
+    compact(r, flag);
     r->filters = *f;
     return FB2_OK;
 }
@@ -116,13 +139,7 @@ extern "C" int fb2_process_post_filter(fb2_result *r, const fb2_params *p, const
 // ---- sketch_stream / sketch_files ----------------------------------------------------------------
 static int finish_sketch(fb2_sketcher *s, const char *name, const fb2_params *p, const fb2_filter *f,
                          fb2_result *out) {
-    int rc = fb2_sketcher_result(s, out);
-    if (rc != FB2_OK) return rc;
-    fb2_filter ff = *f;
-    rc = fb2_filter_counts(out, &ff);
-    if (rc == FB2_OK) rc = fb2_process_post_filter(out, p, name);
-    if (rc != FB2_OK) fb2_result_free(out);
-    return rc;
+    return fb2_sketcher_sketch(s, name, p, f, out);
 }
 
 extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,

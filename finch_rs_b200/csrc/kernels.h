@@ -14,13 +14,16 @@ void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t st);
 
 // hash.cu
 void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t b0, uint32_t b1, const uint32_t *region_count,
-                 uint64_t ord_base, SketchState *st, LogView log, uint64_t seed, cudaStream_t stream);
+                 uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, uint64_t seed,
+                 cudaStream_t stream);
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
-                      uint64_t arena_base, uint64_t ord_base, SketchState *st, LogView log,
+                      uint64_t arena_base, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
                       uint64_t seed, cudaStream_t stream);
 
 // table.cu
 void launch_absorb(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st, cudaStream_t s);
+void launch_absorb_guarded(LogView log, LaunchSlot *slot, TableView t, SketchState *st, const ParseCarry *carry,
+                           uint32_t expect, cudaStream_t s);
 void launch_table_clear(TableView t, cudaStream_t s);
 void launch_gather(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots, cudaStream_t s);
 void launch_radix_sort(unsigned long long *keys, uint32_t *vals, unsigned long long *tkeys, uint32_t *tvals,
@@ -29,6 +32,10 @@ uint32_t radix_hist_words(uint32_t n);
 void launch_prune_select(TableView t, SketchState *st, uint32_t shift, uint32_t *bins, int scaled,
                          unsigned long long size, unsigned long long max_hash, unsigned long long *keys,
                          uint32_t *slots, cudaStream_t s);
+void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride, const unsigned long long *i_hash,
+                        const uint32_t *i_cnt, const uint32_t *i_ext, const unsigned long long *i_kmer,
+                        const unsigned long long *i_posx, unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext,
+                        unsigned long long *o_kmer, unsigned long long *o_posx, uint8_t *o_bytes, cudaStream_t s);
 void launch_select_keep(const unsigned long long *keys, uint32_t n, int scaled, unsigned long long size,
                         unsigned long long max_hash, SketchState *st, cudaStream_t s);
 void launch_commit_threshold(SketchState *st, cudaStream_t s);

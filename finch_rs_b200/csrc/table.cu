@@ -76,6 +76,48 @@ __global__ void absorb_kmer_kernel(LogView log, uint32_t i0, uint32_t i1, TableV
     if (t.posx[slot] == px) t.kmer[slot] = log.kmer[i];
 }
 
+// ---- device-decided absorb (asynchronous chunks) ---------------------------------------------------
+// One thread decides whether the slot's log may be absorbed: the log must not have overflowed and
+// the table must stay under 3/4 load even if every entry is a new key.  The host reads the decision
+// one chunk later and redoes / prunes in the (rare) other cases.
+__global__ void absorb_decide_kernel(LaunchSlot *slot, const SketchState *st, const ParseCarry *carry,
+                                     uint32_t table_cap, uint32_t log_cap) {
+    const uint32_t cnt = slot->log_count;
+    unsigned int d = DECIDE_GO;
+    if (cnt > log_cap) d = DECIDE_OVERFLOW;
+    else if ((unsigned long long)st->occupied + cnt > (unsigned long long)(table_cap / 4) * 3) d = DECIDE_FULL;
+    slot->decision = d;
+    slot->chunk_syms = carry->chunk_syms;
+}
+__global__ void absorb_count_guarded_kernel(LogView log, const LaunchSlot *slot, TableView t, SketchState *st) {
+    if (slot->decision != DECIDE_GO) return;
+    const uint32_t n = slot->log_count, stride = gridDim.x * blockDim.x;
+    const unsigned long long thr = st->threshold;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = log.hash[i];
+        if (key > thr) continue;
+        const unsigned long long px = log.posx[i];
+        const uint32_t s = table_upsert(t, key, st);
+        atomicAdd(&t.cnt[s], 1ULL);
+        const unsigned long long extra = px & 0xFFULL;
+        if (extra) atomicAdd(&t.ext[s], extra);
+        atomicMin(&t.posx[s], px);
+    }
+}
+__global__ void absorb_kmer_guarded_kernel(LogView log, const LaunchSlot *slot, TableView t, const SketchState *st) {
+    if (slot->decision != DECIDE_GO) return;
+    const uint32_t n = slot->log_count, stride = gridDim.x * blockDim.x;
+    const unsigned long long thr = st->threshold;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = log.hash[i];
+        if (key > thr) continue;
+        const uint32_t s = table_find(t, key);
+        if (s == 0xFFFFFFFFu) continue;
+        const unsigned long long px = log.posx[i];
+        if (t.posx[s] == px) t.kmer[s] = log.kmer[i];
+    }
+}
+
 __global__ void table_clear_kernel(TableView t) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= t.cap) {  // includes the side slot
@@ -309,6 +351,27 @@ __global__ void export_kernel(const unsigned long long *__restrict__ keys, const
     o_posx[i] = t.posx[s];
 }
 
+// Select rows of the exported SoA by index (idx == nullptr: the first m rows) and expand the 2-bit
+// k-mer codes to the ASCII bytes KmerCount::kmer holds.  Pushed k-mers (arena flag) keep their index.
+__global__ void select_rows_kernel(const uint32_t *__restrict__ idx, uint32_t m, int k, uint32_t stride,
+                                   const unsigned long long *__restrict__ i_hash, const uint32_t *__restrict__ i_cnt,
+                                   const uint32_t *__restrict__ i_ext, const unsigned long long *__restrict__ i_kmer,
+                                   const unsigned long long *__restrict__ i_posx, unsigned long long *o_hash,
+                                   uint32_t *o_cnt, uint32_t *o_ext, unsigned long long *o_kmer,
+                                   unsigned long long *o_posx, uint8_t *o_bytes) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t i = idx ? idx[j] : j;
+    const unsigned long long codes = i_kmer[i], px = i_posx[i];
+    o_hash[j] = i_hash[i]; o_cnt[j] = i_cnt[i]; o_ext[j] = i_ext[i]; o_kmer[j] = codes; o_posx[j] = px;
+    uint8_t *dst = o_bytes + (size_t)j * stride;
+    if (px & (1ULL << 8)) { for (uint32_t t = 0; t < stride; ++t) dst[t] = 0; }
+    else {
+        for (int t = 0; t < k; ++t) dst[t] = (uint8_t)"ACGT"[(codes >> (2 * t)) & 3ULL];
+        for (uint32_t t = (uint32_t)k; t < stride; ++t) dst[t] = 0;
+    }
+}
+
 // ---- launchers ---------------------------------------------------------------------------------
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
@@ -316,6 +379,13 @@ void launch_absorb(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchSta
     if (i1 <= i0) return;
     absorb_count_kernel<<<cdiv(i1 - i0, 256), 256, 0, s>>>(log, i0, i1, t, st);
     absorb_kmer_kernel<<<cdiv(i1 - i0, 256), 256, 0, s>>>(log, i0, i1, t, st);
+}
+void launch_absorb_guarded(LogView log, LaunchSlot *slot, TableView t, SketchState *st, const ParseCarry *carry,
+                           uint32_t expect, cudaStream_t s) {
+    absorb_decide_kernel<<<1, 1, 0, s>>>(slot, st, carry, t.cap, log.cap);
+    const uint32_t blocks = max(64u, min(cdiv(expect, 256), 2048u));
+    absorb_count_guarded_kernel<<<blocks, 256, 0, s>>>(log, slot, t, st);
+    absorb_kmer_guarded_kernel<<<blocks, 256, 0, s>>>(log, slot, t, st);
 }
 void launch_table_clear(TableView t, cudaStream_t s) {
     table_clear_kernel<<<cdiv(t.cap + 1, 256), 256, 0, s>>>(t);
@@ -353,6 +423,13 @@ void launch_prune_select(TableView t, SketchState *st, uint32_t shift, uint32_t 
 }
 uint32_t radix_hist_words(uint32_t n) { return 256u * cdiv(n ? n : 1, SORT_SEG); }
 
+void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride, const unsigned long long *i_hash,
+                        const uint32_t *i_cnt, const uint32_t *i_ext, const unsigned long long *i_kmer,
+                        const unsigned long long *i_posx, unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext,
+                        unsigned long long *o_kmer, unsigned long long *o_posx, uint8_t *o_bytes, cudaStream_t s) {
+    if (m) select_rows_kernel<<<cdiv(m, 128), 128, 0, s>>>(idx, m, k, stride, i_hash, i_cnt, i_ext, i_kmer, i_posx, o_hash,
+                                                          o_cnt, o_ext, o_kmer, o_posx, o_bytes);
+}
 void launch_select_keep(const unsigned long long *keys, uint32_t n, int scaled, unsigned long long size,
                         unsigned long long max_hash, SketchState *st, cudaStream_t s) {
     select_keep_kernel<<<1, 1, 0, s>>>(keys, n, scaled, size, max_hash, st);

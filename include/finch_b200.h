@@ -119,6 +119,12 @@ int fb2_sketcher_totals(fb2_sketcher *s, uint64_t *total_bases, uint64_t *total_
 /* Non-destructive (the trait takes &self): more input may follow. */
 int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out);
 void fb2_result_free(fb2_result *r);
+/* ---- the tail of sketch_stream (lib.rs:78-93) in one call ----------------------------------- */
+/* to_vec + FilterParams::filter_counts + SketchParams::process_post_filter with identical results,
+ * but only the surviving entries cross PCIe (counts/extras of all entries do, for the filter).
+ * `p` supplies final_size / no_strict; `name` is used in the "too few kmers" message. */
+int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_params *p, const fb2_filter *f,
+                        fb2_result *out);
 
 /* Counters for benchmarking: kernels launched and bytes moved by this handle so far. */
 typedef struct fb2_stats {
