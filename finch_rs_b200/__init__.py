@@ -72,7 +72,7 @@ EXPORTS = [
     "fb2_sketcher_create", "fb2_sketcher_destroy", "fb2_sketcher_reset", "fb2_sketcher_process",
     "fb2_sketcher_push", "fb2_sketcher_feed_fastx", "fb2_sketcher_feed_device", "fb2_sketcher_format",
     "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats",
-    "fb2_sketcher_enable_timing", "fb2_filter_counts", "fb2_process_post_filter",
+    "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_filter_counts", "fb2_process_post_filter",
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_dist_batch",
     "fb2_dist_all_pairs", "fb2_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
     "fb2_synth_genome", "fb2_synth_fasta", "fb2_synth_fastq",
@@ -107,6 +107,7 @@ def lib():
     L.fb2_result_free.restype = None
     L.fb2_sketcher_stats.argtypes = [vp, C.POINTER(_Stats)]
     L.fb2_sketcher_enable_timing.argtypes = [vp, C.c_int]
+    L.fb2_sketcher_debug_symbols.argtypes = [vp, vp, vp, sz, vp, sz]
     L.fb2_filter_counts.argtypes = [C.POINTER(_Result), C.POINTER(_Filter)]
     L.fb2_process_post_filter.argtypes = [C.POINTER(_Result), C.POINTER(_Params), C.c_char_p]
     L.fb2_guess_filter_threshold.argtypes = [vp, sz, C.c_double]
@@ -350,6 +351,19 @@ class _Sketcher:
         f = C.c_int32()
         _check(lib().fb2_sketcher_format(self._h, C.byref(f)))
         return f.value
+
+    def debug_symbols(self):
+        """(geom dict, counts[n_st], list of per-region symbol arrays, raw buffer) of the last chunk."""
+        g = np.zeros(7, np.uint32)
+        _check(lib().fb2_sketcher_debug_symbols(self._h, g.ctypes.data, None, 0, None, 0))
+        names = ("len", "n_tiles", "st_tiles", "n_st", "st_bytes", "region_stride", "hash_tiles")
+        geom = dict(zip(names, (int(x) for x in g)))
+        counts = np.zeros(geom["n_st"], np.uint32)
+        buf = np.zeros(64 + geom["n_st"] * geom["region_stride"] + 64, np.uint8)
+        _check(lib().fb2_sketcher_debug_symbols(self._h, g.ctypes.data, counts.ctypes.data, counts.size,
+                                                buf.ctypes.data, buf.size))
+        regs = [buf[64 + r * geom["region_stride"]: 64 + r * geom["region_stride"] + int(counts[r])] for r in range(geom["n_st"])]
+        return geom, counts, regs, buf
 
     def enable_timing(self, on=True):
         _check(lib().fb2_sketcher_enable_timing(self._h, int(on)))

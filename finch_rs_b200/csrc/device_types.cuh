@@ -9,7 +9,7 @@ constexpr int TILE_THREADS = 256;   // parse: threads per tile
 constexpr int TILE_BYTES = 4096;    // parse: raw bytes per tile (16 per thread)
 constexpr int SYM_FRONT = 64;       // symbols carried in front of each chunk's symbol buffer
 constexpr int HASH_THREADS = 256;
-constexpr int HASH_W = 32;          // k-mer end positions per thread
+constexpr int HASH_W = 64;          // k-mer end positions per thread
 constexpr uint32_t HASH_TILE = HASH_THREADS * HASH_W;  // symbols per block
 
 enum ParseMode : int { MODE_LINES = 0, MODE_FASTA = 1, MODE_FASTQ = 2 };

@@ -104,6 +104,7 @@ struct fb2_sketcher {
     cudaEvent_t ev_chunk[2]{};
     SketchState *h_snap[2] = {nullptr, nullptr};   // pinned snapshots written after each async chunk
     bool steady = false;             // a whole chunk's candidates fit the log: chunks run asynchronously
+    ChunkGeom last_geom{};
     Table tab[2];
     int cur = 0;
     DevBuf sort_keys, sort_slots, sort_tkeys, sort_tslots, sort_hist, d_bins;
@@ -520,6 +521,7 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     const int par = s->par;
     TRY(settle(s, par));           // its buffers are about to be reused (normally already settled)
     const ChunkGeom g = make_geom(len);
+    s->last_geom = g;
     TRY(s->d_stmap.ensure((size_t)g.n_st * 4)); TRY(s->d_ststate.ensure((size_t)g.n_st * 4));
     TRY(s->d_rcount[par].ensure((size_t)g.n_st * 4));
     TRY(s->d_sym[par].ensure((size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + 2 * HASH_TILE));
@@ -966,6 +968,22 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
     const int rc = collect_rows(s, idx, m, out);
     if (rc == FB2_OK) out->filters = ff;
     return rc;
+}
+
+// Debug/inspection: symbol regions of the most recent chunk (for tests of the parse kernels).
+extern "C" int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint32_t *counts, size_t counts_cap,
+                                          uint8_t *sym, size_t sym_cap) {
+    if (!s || !geom7) return fb2_fail(FB2_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st));
+    const int par = s->par ^ 1;   // the chunk that ran last
+    const ChunkGeom g = s->last_geom;
+    const uint32_t gv[7] = {g.len, g.n_tiles, g.st_tiles, g.n_st, g.st_bytes, g.region_stride, g.hash_tiles};
+    memcpy(geom7, gv, sizeof gv);
+    if (counts && counts_cap >= g.n_st) CU(cudaMemcpy(counts, s->d_rcount[par].p, (size_t)g.n_st * 4, cudaMemcpyDeviceToHost));
+    const size_t need = (size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + HASH_W;
+    if (sym && sym_cap >= need) CU(cudaMemcpy(sym, s->d_sym[par].p, need, cudaMemcpyDeviceToHost));
+    return FB2_OK;
 }
 
 extern "C" int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out) {

@@ -20,12 +20,89 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+// ---- murmur3 with the first multiply taken from shared-memory tables ---------------------------
+// Every 8-base word w of the k-mer enters murmur3 as  w * c  (c = c1 for k1-type words, c2 for
+// k2-type words), w being the 8 ASCII bytes of the bases.  Multiplication distributes over the
+// byte groups:  w * c = A4(lo) * c + (A4(hi) * c << 32)  with A4(b) the 4 ASCII bytes of the 4
+// bases b.  lut_c[b] = A4(b) * c (64 bit) turns "expand 2-bit codes to ASCII, then multiply" into
+// two shared-memory loads and one add, which moves ~20 instructions per k-mer off the ALU pipe.
+struct MulLut { const uint2 *c1; const uint2 *c2; };
+
+template <int NBYTES, bool IS_C1>
+__device__ __forceinline__ uint64_t mul_word(uint32_t g16, const MulLut &L) {
+    // g16: 8 bases (2 bits each, base 0 lowest); NBYTES of them exist, the rest are zero bytes.
+    const uint2 *T = IS_C1 ? L.c1 : L.c2;
+    const uint64_t C = IS_C1 ? MM_C1 : MM_C2;
+    if (NBYTES >= 8) {
+        const uint2 a = T[g16 & 0xFFu], b = T[g16 >> 8];
+        return ((uint64_t)(a.y + b.x) << 32) | a.x;
+    } else if (NBYTES > 4) {
+        const uint2 a = T[g16 & 0xFFu];
+        const uint32_t hi4 = expand4(g16 >> 8) & (uint32_t)low_bytes_mask(NBYTES - 4);
+        return ((uint64_t)(a.y + hi4 * (uint32_t)C) << 32) | a.x;
+    } else if (NBYTES == 4) {
+        const uint2 a = T[g16 & 0xFFu];
+        return ((uint64_t)a.y << 32) | a.x;
+    } else {
+        const uint32_t lo4 = expand4(g16 & 0xFFu) & (uint32_t)low_bytes_mask(NBYTES);
+        return (uint64_t)lo4 * C;
+    }
+}
+
+template <int K>
+__device__ __forceinline__ uint64_t murmur_kmer_h1_lut(uint64_t codes, uint64_t seed, const MulLut &L) {
+    static_assert(K >= 1 && K <= 32, "k out of range");
+    uint64_t h1 = seed, h2 = seed;
+    constexpr int NB = K / 16, T = K & 15;
+    if (NB >= 1) {
+        uint64_t k1 = mul_word<8, true>((uint32_t)(codes & 0xFFFFu), L);
+        uint64_t k2 = mul_word<8, false>((uint32_t)((codes >> 16) & 0xFFFFu), L);
+        k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+        k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+    }
+    if (NB >= 2) {
+        uint64_t k1 = mul_word<8, true>((uint32_t)((codes >> 32) & 0xFFFFu), L);
+        uint64_t k2 = mul_word<8, false>((uint32_t)((codes >> 48) & 0xFFFFu), L);
+        k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+        k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+    }
+    constexpr int TW = 2 * NB;  // first tail word
+    if (T > 8) {
+        uint64_t k2 = mul_word<(T > 8 ? T - 8 : 1), false>((uint32_t)((codes >> (16 * ((TW + 1) & 3))) & 0xFFFFu), L);
+        k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
+    }
+    if (T > 0) {
+        uint64_t k1 = mul_word<(T > 8 ? 8 : (T > 0 ? T : 1)), true>((uint32_t)((codes >> (16 * (TW & 3))) & 0xFFFFu), L);
+        k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
+    }
+    h1 ^= (uint64_t)K; h2 ^= (uint64_t)K;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2;
+    return h1;
+}
+
 template <int K>
 __global__ void __launch_bounds__(HASH_THREADS)
 hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r starts at SYM_FRONT + r * region_stride
             ChunkGeom g, uint32_t b0,             // first hash block (region-major) of this launch
             const uint32_t *__restrict__ region_count, uint64_t ord_base, const SketchState *st,
             LaunchSlot *slot, LogView log, int k_rt, uint64_t seed) {
+    __shared__ uint2 lut_c1[256], lut_c2[256];
+    if (K > 0) {
+        const uint32_t a4 = expand4(threadIdx.x & 0xFFu);
+        const uint64_t p1 = (uint64_t)a4 * MM_C1, p2 = (uint64_t)a4 * MM_C2;
+        if (threadIdx.x < 256) {
+            lut_c1[threadIdx.x] = make_uint2((uint32_t)p1, (uint32_t)(p1 >> 32));
+            lut_c2[threadIdx.x] = make_uint2((uint32_t)p2, (uint32_t)(p2 >> 32));
+        }
+        __syncthreads();
+    }
+    MulLut L; L.c1 = lut_c1; L.c2 = lut_c2;
     const int k = K > 0 ? K : k_rt;
     const uint64_t mask = kmer_mask(k);
     const uint32_t blk = b0 + blockIdx.x;
@@ -36,7 +113,8 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
     const unsigned long long T = st->threshold;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t p0 = lt * HASH_TILE + threadIdx.x * (uint32_t)HASH_W;
-    // Warp-uniform early exit: a warp's positions are contiguous and ascending.
+    // Warp-uniform early exit: a warp's positions are contiguous and ascending.  Positions in
+    // [end, end + HASH_W) hold SYM_BREAK (written by pack_kernel), so no per-position bound test.
     if (__all_sync(0xffffffffu, p0 >= end)) return;
 
     Roll r; r.fwd = 0; r.rc = 0; r.run = 0;
@@ -52,20 +130,26 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
             roll_push(r, (w[i >> 2] >> (8 * (i & 3))) & 0xFFu, k, mask);
         }
     }
+    // lanes past the end of the region (in a warp that is not entirely past it) never load: they
+    // walk SYM_BREAK words.  Live lanes stay inside [p0, p0 + HASH_W) which the padding covers.
+    const bool live = p0 < end;
+    if (!live) r.run = 0;
     uint32_t nvalid = 0;
-    uint32_t word = __ldg(wp);
+    uint32_t word = live ? __ldg(wp) : 0x04040404u;
 #pragma unroll 1
     for (int j = 0; j < HASH_W / 4; ++j) {
         const uint32_t cur = word;
-        if (j + 1 < HASH_W / 4) word = __ldg(wp + j + 1);  // prefetch next 4 symbols
+        if (j + 1 < HASH_W / 4) word = live ? __ldg(wp + j + 1) : 0x04040404u;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const uint32_t p = p0 + 4u * (uint32_t)j + (uint32_t)b;
             roll_push(r, (cur >> (8 * b)) & 0xFFu, k, mask);
-            const bool ok = (r.run >= (uint32_t)k) && (p < end);
+            const bool ok = r.run >= (uint32_t)k;
             bool is_rc;
             const uint64_t codes = roll_canonical_lsb(r, mask, is_rc);
-            const uint64_t h = murmur_kmer_h1<K>(codes, k, seed);
+            uint64_t h;
+            if (K > 0) h = murmur_kmer_h1_lut<(K > 0 ? K : 1)>(codes, seed, L);
+            else h = murmur_kmer_h1<0>(codes, k, seed);
             nvalid += ok ? 1u : 0u;
             const bool emit = ok && (h <= T);
             const uint32_t em = __ballot_sync(0xffffffffu, emit);

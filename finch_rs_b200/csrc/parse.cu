@@ -439,6 +439,8 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
         out_off += tile_total;
     }
 
+    // the hash kernel walks up to HASH_W positions past the region's end: make them breaks
+    if (tid < HASH_W) region[out_off + tid] = SYM_BREAK;
     if (tid == 0) { region_count[st] = out_off; atomicAdd(&carry->chunk_syms, out_off); }
     if (MODE != MODE_LINES) {
         const unsigned long long bsum = block_reduce64((unsigned long long)bases_delta, sh8l, OpAdd(), 0ull);

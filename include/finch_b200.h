@@ -134,6 +134,10 @@ typedef struct fb2_stats {
     uint64_t hash_symbols;   /* symbols (bases + record breaks) the hash kernel walked */
 } fb2_stats;
 int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out);
+/* Inspection hook for tests: geometry (7 x u32), per-region symbol counts and the raw symbol buffer of the
+ * most recent chunk (see finch_rs_b200/csrc/parse.cu for the layout). */
+int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint32_t *counts, size_t counts_cap,
+                               uint8_t *sym, size_t sym_cap);
 int fb2_sketcher_enable_timing(fb2_sketcher *s, int on);
 
 /* ---- FilterParams::filter_counts + SketchParams::process_post_filter ---------------------- */

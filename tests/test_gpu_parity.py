@@ -310,3 +310,25 @@ def test_distance_scaled_end_to_end(fb):  # distance.rs:312-337
         return q.to_sketch()
     d = fb.distance(mk(), mk(), False)
     assert (d.jaccard, d.containment, d.common_hashes) == (1.0, 1.0, 3)
+
+
+def test_symbol_regions_match_normalize(fb, oracle):
+    """pack_kernel output == per-record BREAK + normalize(false) (mash.rs:73), region by region."""
+    rng = np.random.default_rng(99)
+    lut = np.full(256, 4, np.uint8)
+    for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3)):
+        lut[ch[0]] = v
+    for fmt in ("fasta", "fastq"):
+        data = (gen.fasta(rng, n_records=9, max_len=9000, width=61, messy=0.02, crlf=True)
+                if fmt == "fasta" else gen.fastq(rng, n_records=200, max_len=300, messy=0.02))
+        rc, f, recs = oracle.parse_fastx(data)
+        exp = []
+        for r in recs:
+            norm = lut[np.frombuffer(oracle.normalize(r), np.uint8)]
+            exp += ([np.array([4], np.uint8), norm] if fmt == "fasta" else [norm, np.array([4], np.uint8)])
+        exp = np.concatenate(exp)
+        with fb.SketchParams.mash(10, 10, False, 3, 0).create_sketcher() as s:
+            s.feed_fastx(data, final=True)
+            geom, counts, regs, buf = s.debug_symbols()
+        assert geom["n_st"] > 1
+        assert np.array_equal(np.concatenate(regs), exp)
