@@ -86,6 +86,34 @@ __device__ __forceinline__ uint64_t murmur_kmer_h1_lut(uint64_t codes, uint64_t 
     return h1;
 }
 
+constexpr uint32_t LOG_RESERVE = 8;   // extra log slots a warp reserves per atomic (<= 31)
+
+// ---- TMA (1-D bulk copy) staging of the block's symbol tile ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy by the TMA unit; completion is signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 template <int K>
 __global__ void __launch_bounds__(HASH_THREADS)
 hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r starts at SYM_FRONT + r * region_stride
@@ -103,26 +131,46 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
         __syncthreads();
     }
     MulLut L; L.c1 = lut_c1; L.c2 = lut_c2;
+    __shared__ __align__(128) uint8_t tile[32 + HASH_TILE];   // 32 symbols of halo, then the block's positions
+    __shared__ __align__(8) uint64_t tile_bar;
     const int k = K > 0 ? K : k_rt;
     const uint64_t mask = kmer_mask(k);
     const uint32_t blk = b0 + blockIdx.x;
     const uint32_t region = blk / g.hash_tiles, lt = blk - region * g.hash_tiles;
     const uint32_t end = region_count[region];
+    const uint32_t pb = lt * HASH_TILE;          // first position of this block in its region
+    if (pb >= end) return;                        // block-uniform: nothing to do
     const uint8_t *sym = symbuf + (size_t)SYM_FRONT + (size_t)region * g.region_stride;
     const uint64_t ord_region = ord_base + (uint64_t)region * g.st_bytes;
     const unsigned long long T = st->threshold;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t p0 = lt * HASH_TILE + threadIdx.x * (uint32_t)HASH_W;
-    // Warp-uniform early exit: a warp's positions are contiguous and ascending.  Positions in
-    // [end, end + HASH_W) hold SYM_BREAK (written by pack_kernel), so no per-position bound test.
+    // ---- stage [pb - 32, min(end + HASH_W, pb + HASH_TILE)) with one TMA bulk copy --------------
+    // (positions in [end, end + HASH_W) hold SYM_BREAK, written by pack_kernel)
+    {
+        const uint32_t npos = min(end + (uint32_t)HASH_W - pb, (uint32_t)HASH_TILE);
+        const uint32_t bytes = (32u + npos + 15u) & ~15u;
+        if (threadIdx.x == 0) { mbar_init(&tile_bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&tile_bar, bytes);
+            tma_load_1d(tile, sym + pb - 32, bytes, &tile_bar);
+        }
+        mbar_wait(&tile_bar, 0);
+    }
+    const uint32_t t0 = threadIdx.x * (uint32_t)HASH_W;   // this thread's first position within the tile
+    const uint32_t p0 = pb + t0;
+    // Warp-uniform early exit: a warp's positions are contiguous and ascending.
     if (__all_sync(0xffffffffu, p0 >= end)) return;
+    // lanes past the end of the region (in a warp that is not entirely past it) never read: they
+    // walk SYM_BREAK words.  Live lanes stay inside [p0 - 32, p0 + HASH_W), which was staged.
+    const bool live = p0 < end;
 
     Roll r; r.fwd = 0; r.rc = 0; r.run = 0;
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(sym + p0);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + 32 + t0);
     // ---- warm-up on the 32 symbols before p0 (only the last k-1 matter) -------------------
-    {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(sym + p0) - 2);
-        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(sym + p0) - 1);
+    if (live) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(tile + t0);
+        const uint4 b = *reinterpret_cast<const uint4 *>(tile + t0 + 16);
         const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -130,16 +178,13 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
             roll_push(r, (w[i >> 2] >> (8 * (i & 3))) & 0xFFu, k, mask);
         }
     }
-    // lanes past the end of the region (in a warp that is not entirely past it) never load: they
-    // walk SYM_BREAK words.  Live lanes stay inside [p0, p0 + HASH_W) which the padding covers.
-    const bool live = p0 < end;
-    if (!live) r.run = 0;
     uint32_t nvalid = 0;
-    uint32_t word = live ? __ldg(wp) : 0x04040404u;
+    uint32_t res_base = 0, res_left = 0;   // warp-uniform: this warp's reserved slice of the log
+    uint32_t word = live ? wp[0] : 0x04040404u;
 #pragma unroll 1
     for (int j = 0; j < HASH_W / 4; ++j) {
         const uint32_t cur = word;
-        if (j + 1 < HASH_W / 4) word = live ? __ldg(wp + j + 1) : 0x04040404u;
+        if (j + 1 < HASH_W / 4) word = live ? wp[j + 1] : 0x04040404u;  // next 4 symbols
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const uint32_t p = p0 + 4u * (uint32_t)j + (uint32_t)b;
@@ -153,22 +198,31 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
             nvalid += ok ? 1u : 0u;
             const bool emit = ok && (h <= T);
             const uint32_t em = __ballot_sync(0xffffffffu, emit);
-            if (em) {  // warp-aggregated append
-                const int leader = __ffs(em) - 1;
-                uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(&slot->log_count, (unsigned int)__popc(em));
-                base = __shfl_sync(0xffffffffu, base, leader);
+            if (em) {
+                // Warp-private bump reservation in the log: the global atomic (and the wait for its
+                // result) happens once per LOG_RESERVE candidates, not once per candidate.
+                const uint32_t n = __popc(em);
+                if (n > res_left) {                                   // warp-uniform
+                    if (lane < res_left && res_base + lane < log.cap) log.posx[res_base + lane] = ~0ULL;  // unused slots
+                    const uint32_t want = n + LOG_RESERVE;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&slot->log_count, want);
+                    res_base = __shfl_sync(0xffffffffu, base, 0);
+                    res_left = want;
+                }
                 if (emit) {
-                    const uint32_t idx = base + __popc(em & lanemask_lt());
+                    const uint32_t idx = res_base + __popc(em & lanemask_lt());
                     if (idx < log.cap) {
                         log.hash[idx] = h;
                         log.kmer[idx] = codes;
                         log.posx[idx] = ((ord_region + p) << 9) | (is_rc ? 1ull : 0ull);
                     }
                 }
+                res_base += n; res_left -= n;
             }
         }
     }
+    if (lane < res_left && res_base + lane < log.cap) log.posx[res_base + lane] = ~0ULL;  // unused tail of the reservation
     // valid-window count of this launch (committed to total_kmers by the host on success)
     nvalid = __reduce_add_sync(0xffffffffu, nvalid);
     if (lane == 0 && nvalid) atomicAdd(&slot->launch_kmers, (unsigned long long)nvalid);

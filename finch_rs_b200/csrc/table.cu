@@ -54,9 +54,10 @@ __device__ __forceinline__ uint32_t table_find(const TableView &t, unsigned long
 __global__ void absorb_count_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st) {
     const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= i1) return;
+    const unsigned long long px = log.posx[i];
+    if (px == ~0ULL) return;                      // unused slot of a warp's reservation
     const unsigned long long key = log.hash[i];
     if (key > st->threshold) return;
-    const unsigned long long px = log.posx[i];
     const uint32_t slot = table_upsert(t, key, st);
     atomicAdd(&t.cnt[slot], 1ULL);
     const unsigned long long extra = px & 0xFFULL;
@@ -68,11 +69,12 @@ __global__ void absorb_count_kernel(LogView log, uint32_t i0, uint32_t i1, Table
 __global__ void absorb_kmer_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, const SketchState *st) {
     const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= i1) return;
+    const unsigned long long px = log.posx[i];
+    if (px == ~0ULL) return;
     const unsigned long long key = log.hash[i];
     if (key > st->threshold) return;
     const uint32_t slot = table_find(t, key);
     if (slot == 0xFFFFFFFFu) return;
-    const unsigned long long px = log.posx[i];
     if (t.posx[slot] == px) t.kmer[slot] = log.kmer[i];
 }
 
@@ -94,9 +96,10 @@ __global__ void absorb_count_guarded_kernel(LogView log, const LaunchSlot *slot,
     const uint32_t n = slot->log_count, stride = gridDim.x * blockDim.x;
     const unsigned long long thr = st->threshold;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long px = log.posx[i];
+        if (px == ~0ULL) continue;                // unused slot of a warp's reservation
         const unsigned long long key = log.hash[i];
         if (key > thr) continue;
-        const unsigned long long px = log.posx[i];
         const uint32_t s = table_upsert(t, key, st);
         atomicAdd(&t.cnt[s], 1ULL);
         const unsigned long long extra = px & 0xFFULL;
@@ -109,11 +112,12 @@ __global__ void absorb_kmer_guarded_kernel(LogView log, const LaunchSlot *slot, 
     const uint32_t n = slot->log_count, stride = gridDim.x * blockDim.x;
     const unsigned long long thr = st->threshold;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long px = log.posx[i];
+        if (px == ~0ULL) continue;
         const unsigned long long key = log.hash[i];
         if (key > thr) continue;
         const uint32_t s = table_find(t, key);
         if (s == 0xFFFFFFFFu) continue;
-        const unsigned long long px = log.posx[i];
         if (t.posx[s] == px) t.kmer[s] = log.kmer[i];
     }
 }
