@@ -105,6 +105,7 @@ struct fb2_sketcher {
     SketchState *h_snap[2] = {nullptr, nullptr};   // pinned snapshots written after each async chunk
     bool steady = false;             // a whole chunk's candidates fit the log: chunks run asynchronously
     ChunkGeom last_geom{};
+    std::vector<uint8_t> tail_host;   // last <= 4096 raw bytes of the open stream (end-of-stream checks)
     Table tab[2];
     int cur = 0;
     DevBuf sort_keys, sort_slots, sort_tkeys, sort_tslots, sort_hist, d_bins;
@@ -688,6 +689,14 @@ extern "C" int fb2_sketcher_push(fb2_sketcher *s, const uint8_t *kmer, size_t k,
 }
 
 // ---- FASTX streams -------------------------------------------------------------------------------
+// remember the last bytes of the stream (host copy) for the end-of-stream checks
+static void note_tail(fb2_sketcher *s, const uint8_t *bytes, size_t len) {
+    const size_t keep = 4096;
+    if (len >= keep) { s->tail_host.assign(bytes + (len - keep), bytes + len); return; }
+    s->tail_host.insert(s->tail_host.end(), bytes, bytes + len);
+    if (s->tail_host.size() > keep) s->tail_host.erase(s->tail_host.begin(), s->tail_host.end() - keep);
+}
+
 static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
     const uint8_t c = first[0];
     if (c == '>') s->format = FB2_FORMAT_FASTA;
@@ -704,6 +713,7 @@ static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
     c_->raw_total = 0; c_->n_records = 0; c_->first_bad_pos = ~0ULL; c_->last_sig = 0; c_->error = 0;
     TRY(push_carry(s));
     s->stream_open = true;
+    s->tail_host.clear();
     return FB2_OK;
 }
 static int end_stream(fb2_sketcher *s) {
@@ -719,11 +729,27 @@ static int end_stream(fb2_sketcher *s) {
             else if (c->prev1 == '\r') c->total_bases -= 1;
         }
     } else if (s->format == FB2_FORMAT_FASTQ) {
-        if (c->last_sig == 0) rc = fb2_fail(FB2_EEMPTY, "no records in FASTQ stream");
-        else if ((c->last_sig & 3ULL) != 3ULL) rc = fb2_fail(FB2_ERECORD, "truncated FASTQ record at end of input");
-        else if (c->first_bad_pos != ~0ULL && c->first_bad_pos < (c->last_sig >> 2))
-            rc = fb2_fail(FB2_ERECORD, "invalid FASTQ record: line at byte " + std::to_string(c->first_bad_pos) +
-                                           " does not start with the expected '@' / '+'");
+        // Trailing blank lines are tolerated; the last byte that is neither CR nor LF must lie in a
+        // quality line (phase 3), and every line before it must have passed the '@' / '+' checks.
+        // c->state is the phase of the line the next byte would belong to.
+        const std::vector<uint8_t> &t = s->tail_host;
+        size_t n_trail = 0, nl_trail = 0;
+        while (n_trail < t.size() && (t[t.size() - 1 - n_trail] == '\n' || t[t.size() - 1 - n_trail] == '\r')) {
+            nl_trail += t[t.size() - 1 - n_trail] == '\n';
+            ++n_trail;
+        }
+        const uint64_t L = c->raw_total;
+        if (n_trail == L) rc = fb2_fail(FB2_EEMPTY, "no records in FASTQ stream");
+        else if (n_trail == t.size()) rc = fb2_fail(FB2_ERECORD, "too many trailing line terminators after the last FASTQ record");
+        else {
+            const uint32_t phase_last = (c->state + 4u - (uint32_t)(nl_trail % 4)) & 3u;
+            const uint64_t last_sig_pos = L - n_trail - 1;
+            if (phase_last != 3u)
+                rc = fb2_fail(FB2_ERECORD, "truncated FASTQ record at end of input");
+            else if (c->first_bad_pos != ~0ULL && c->first_bad_pos <= last_sig_pos)
+                rc = fb2_fail(FB2_ERECORD, "invalid FASTQ record: line at byte " + std::to_string(c->first_bad_pos) +
+                                               " does not start with the expected '@' / '+'");
+        }
     }
     // a later stream or record must not join this one: break the carried symbols
     c->state = 0; c->prev1 = c->prev2 = '\n';
@@ -740,6 +766,7 @@ extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, si
     if (len) {
         if (!s->stream_open) TRY(begin_stream(s, bytes, len));
         const int mode = s->format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ;
+        note_tail(s, bytes, len);
         if (len < (1u << 20)) {  // small piece: gather in pinned staging
             TRY(ensure_stage(s));
             if (s->stage_mode != mode) { TRY(flush_stage(s)); s->stage_mode = mode; }
@@ -774,6 +801,12 @@ extern "C" int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev, siz
         }
         TRY(flush_stage(s));
         const int mode = s->format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ;
+        {
+            const size_t tl = std::min<size_t>(len, 4096);
+            std::vector<uint8_t> tmp(tl);
+            CU(cudaMemcpy(tmp.data(), dev + (len - tl), tl, cudaMemcpyDeviceToHost));
+            note_tail(s, tmp.data(), tl);
+        }
         const size_t chunk = s->chunk_bytes;
         const bool aligned = ((uintptr_t)dev & 15u) == 0;
         for (size_t off = 0; off < len; off += chunk) {

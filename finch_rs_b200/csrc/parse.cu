@@ -49,7 +49,9 @@ __device__ __forceinline__ void load_raw(const uint8_t *__restrict__ raw, uint32
         nvalid = 16;
     } else {
         nvalid = off < len ? (int)(len - off) : 0;
-        for (int i = 0; i < nvalid; ++i) r.w[i >> 2] |= (uint32_t)raw[off + i] << (8 * (i & 3));
+#pragma unroll
+        for (int i = 0; i < 16; ++i)   // static indices keep w[] in registers
+            if (i < nvalid) r.w[i >> 2] |= (uint32_t)raw[off + i] << (8 * (i & 3));
     }
     r.valid = nvalid >= 16 ? 0xFFFFu : ((1u << nvalid) - 1u);
     uint32_t nl = 0;
@@ -329,7 +331,7 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
     uint32_t out_off = 0;                                     // symbols written so far in this region
     long long bases_delta = 0;
     uint32_t recs = 0;
-    unsigned long long bad_pos = ~0ULL, sig = 0;
+    unsigned long long bad_pos = ~0ULL;
 
     for (uint32_t t = t0; t < t1; ++t) {
         const uint32_t off = t * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u;
@@ -364,19 +366,9 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
                 ls &= ls - 1u;
                 const uint32_t ph = (ph0 + __popc(r.nl & ((1u << i) - 1u))) & 3u;
                 if (ph == 0u) recs++;
-                const bool ok = ph == 0u ? (raw_byte(r, i) == '@') : (ph == 2u ? (raw_byte(r, i) == '+') : true);
+                bool ok = true;
+                if (ph == 0u || ph == 2u) ok = raw[off + (uint32_t)i] == (ph == 0u ? '@' : '+');
                 if (!ok) bad_pos = min(bad_pos, (unsigned long long)(raw_base + off + (uint32_t)i));
-            }
-            // last byte that is neither CR nor LF, with its phase (truncation check at end of stream)
-            uint32_t sg = r.valid & ~r.nl;
-            while (sg) {
-                const int i = 31 - __clz(sg);
-                if (raw_byte(r, i) != '\r') {
-                    const uint32_t ph = (ph0 + __popc(r.nl & ((1u << i) - 1u))) & 3u;
-                    sig = ((unsigned long long)(raw_base + off + (uint32_t)i + 1u) << 2) | ph;
-                    break;
-                }
-                sg &= ~(1u << i);
             }
             state = (state + total_nl) & 3u;
         } else {  // MODE_FASTA
@@ -426,10 +418,16 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
             uint32_t cw[4];
             if (four) code_words(c, four, cw);
             else { cw[0] = c.cw[0]; cw[1] = c.cw[1]; cw[2] = c.cw[2]; cw[3] = c.cw[3]; }
+            // a contiguous run of flags (whole piece, prefix or suffix: nearly always) is written with
+            // statically indexed predicated stores
             uint8_t *o = region + out_off + local;
-            if (em == 0xFFFFu) {
+            const int a0 = __ffs(em) - 1;
+            const uint32_t run = em >> a0;
+            if ((run & (run + 1u)) == 0u) {
+                uint8_t *ob = o - a0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = (uint8_t)((cw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                for (int i = 0; i < 16; ++i)
+                    if ((em >> i) & 1u) ob[i] = (uint8_t)((cw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
@@ -451,11 +449,7 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
         }
         if (MODE == MODE_FASTQ) {
             const unsigned long long bmin = block_reduce64(bad_pos, sh8l, OpMin(), ~0ULL);
-            const unsigned long long smax = block_reduce64(sig, sh8l, OpMax(), 0ull);
-            if (tid == 0) {
-                if (bmin != ~0ULL) atomicMin((unsigned long long *)&carry->first_bad_pos, bmin);
-                if (smax) atomicMax((unsigned long long *)&carry->last_sig, smax);
-            }
+            if (tid == 0 && bmin != ~0ULL) atomicMin((unsigned long long *)&carry->first_bad_pos, bmin);
         }
     }
 }
