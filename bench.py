@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--cpu-reads", type=int, default=150_000, help="cpu_baseline sample (reads, 1 core)")
-    ap.add_argument("--ref-reads", type=int, default=2_000_000, help="--impl reference sample per step (all cores)")
+    ap.add_argument("--ref-reads", type=int, default=6_000_000, help="--impl reference sample per step (all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
