@@ -332,3 +332,27 @@ def test_symbol_regions_match_normalize(fb, oracle):
             geom, counts, regs, buf = s.debug_symbols()
         assert geom["n_st"] > 1
         assert np.array_equal(np.concatenate(regs), exp)
+
+
+@pytest.mark.parametrize("kind,size,k,scale", [("scaled", 1000, 21, 0.05), ("scaled", 0, 31, 0.2),
+                                               ("mash", 5_000_000, 21, 0)])
+def test_table_growth(fb, oracle, kind, size, k, scale):
+    """Sketches far larger than the initial table (Scaled keeps ~scale * distinct k-mers; a Mash heap larger
+    than the input keeps everything): the table must grow and stay exact."""
+    data = fb.synth_fasta(2_000_000, n_records=2, line_width=70, lower_frac=0.05, n_frac=0.002, seed=11).tobytes()
+    ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, k, 0, scale or 0.001)
+    gres, gtotals, _ = gpu_sketch(fb, data, kind, size, k, 0, scale or 0.001)
+    assert gtotals == ototals
+    assert len(ovec["hashes"]) > 90_000
+    assert_same(gres, ovec, k)
+
+
+def test_repetitive_input(fb, oracle):
+    """Low-complexity input (few distinct k-mers, huge counts): the threshold never becomes finite."""
+    unit = b"ACGTTGCAAGGCTTAACCGGATATCGCGTA"
+    data = b">rep\n" + unit * 40000 + b"\n>polyA\n" + b"A" * 300000 + b"\n"
+    ovec, ototals, _ = oracle_sketch(oracle, data, "mash", 1000, 21, 0)
+    gres, gtotals, _ = gpu_sketch(fb, data, "mash", 1000, 21, 0)
+    assert gtotals == ototals
+    assert_same(gres, ovec, 21)
+    assert int(ovec["counts"].max()) >= 40000 - 1
