@@ -329,13 +329,16 @@ def main():
         "gpu_launches": int(stats_res["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "frac": achieved / peak if peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch (61.0 M symbols of a
+                     # 128 MiB chunk), ncu --set full: profiles/r01_ncu_full_v10_hash_fullsize.txt  => 1.08 B/symbol
+                     "traffic": 66.04e6, "traffic_unit": "bytes per launch (61.0e6 algorithmic bytes)",
                      "kernel": "fb2::hash_kernel<21>", "peak_source": peak_src,
                      "algorithmic_bytes_per_unit": "1 B per base (symbol) walked by the hash kernel",
                      "avg_launch_ms": hash_ms / max(1, hash_launches), "launches_per_step": hash_launches / 2,
                      "hash_kernel_share_of_step": (hash_ms / 2) / (ms_res / args.steps),
                      "parse_kernels_ms_per_step": parse_ms / 2,
-                     "note": "integer-issue-bound, not HBM-bound (~190 SASS instr per k-mer); see DESIGN.md"},
+                     "note": "ALU-pipe-bound, not HBM-bound (~150 SASS instr per k-mer, ALU pipe 81% busy in ncu); see DESIGN.md"},
         "bit_exact": None,
         "aux": {"prunes_per_step": stats_res["prunes"] / args.steps, "chunks_per_step": stats_res["chunks"] / args.steps,
                 "hash_launches_per_step": stats_res["hash_launches"] / args.steps,

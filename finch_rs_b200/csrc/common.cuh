@@ -157,14 +157,14 @@ FB2_HD uint64_t murmur_bytes_h1(const uint8_t *data, uint32_t len, uint64_t seed
 // Identity used below:  LSB-first(rc) == ~fwd & mask  and  LSB-first(fwd) == ~rc & mask.
 struct Roll {
     uint64_t fwd, rc;
-    uint32_t run;  // number of consecutive bases ending here (saturates at 64)
+    uint32_t run;  // number of consecutive bases ending here (callers walk far fewer than 2^32 symbols)
 };
 FB2_HD uint64_t kmer_mask(int k) { return k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1ULL); }
 FB2_HD void roll_push(Roll &r, uint32_t sym, int k, uint64_t mask) {
     const uint64_t c = sym & 3u;
     r.fwd = ((r.fwd << 2) | c) & mask;
     r.rc = (r.rc >> 2) | ((c ^ 3ULL) << (2 * (k - 1)));
-    r.run = sym < 4u ? (r.run < 64u ? r.run + 1u : 64u) : 0u;
+    r.run = sym < 4u ? r.run + 1u : 0u;
 }
 // Canonical choice of needletail's canonical_kmers: fwd < rc ? (fwd,false) : (rc,true);
 // a palindrome therefore reports is_rc = true.  Returns LSB-first codes of the chosen k-mer.

@@ -334,9 +334,12 @@ static int sort_table(fb2_sketcher *s, uint32_t *n_out) {
     *n_out = n;
     return FB2_OK;
 }
-static int prune(fb2_sketcher *s, uint32_t need_room) {
-    // Histogram-select a bin-boundary threshold that keeps >= size keys, gather the survivors,
-    // rebuild them into the other table (grown when needed) and commit the lower threshold.
+// Histogram-select a bin-boundary threshold that keeps >= size keys, gather the survivors,
+// rebuild them into the other table (grown when needed) and commit the lower threshold.
+// With `limit`: only commit when the selected threshold is <= *limit (i.e. the table already holds
+// >= size keys at or below it); otherwise leave everything untouched and report *ok = false.
+static int prune(fb2_sketcher *s, uint32_t need_room, const unsigned long long *limit = nullptr, bool *ok = nullptr) {
+    if (ok) *ok = true;
     const uint32_t occ_ub = s->tab[s->cur].cap + 1;
     TRY(ensure_sort(s, occ_ub));
     TRY(s->d_bins.ensure(4096 * sizeof(uint32_t)));
@@ -350,6 +353,7 @@ static int prune(fb2_sketcher *s, uint32_t need_room) {
                         s->sort_keys.as<unsigned long long>(), s->sort_slots.as<uint32_t>(), s->st);
     s->stats.kernel_launches += 4;
     TRY(pull_state(s));
+    if (limit && s->h_state->new_threshold > *limit) { if (ok) *ok = false; return FB2_OK; }
     uint32_t keep = s->h_state->gather_count;
     if (!s->scaled && s->size == 0) keep = 0;  // MashSketcher::new(0, ..) keeps nothing
     uint32_t cap = s->tab[s->cur].cap;
@@ -372,7 +376,69 @@ static int prune(fb2_sketcher *s, uint32_t need_room) {
 // Absorb log[0, cnt) into the table, pruning / growing so the table never passes 3/4 load.
 // Between pulls the host only knows an upper bound of the occupancy (every absorbed entry may be
 // a new key); it fetches the exact value before deciding to prune.
+// Large logs (threshold still falling): most entries would be pruned right after being inserted.
+// Histogram the log's hashes, absorb only the lowest band that should already contain `size` distinct
+// keys, and let the table histogram confirm it (the selected threshold must not exceed the band);
+// widen the band only when it does not.  Entries above the final band never touch the table.
+static int absorb_log_banded(fb2_sketcher *s, int par, uint32_t cnt, bool *done) {
+    *done = false;
+    SketchState *dst = (SketchState *)s->d_state.p;
+    TRY(pull_state(s));
+    const unsigned long long thr = s->h_state->threshold;
+    uint32_t bits = 0;
+    while (bits < 64 && (thr >> bits) != 0ULL) ++bits;
+    const uint32_t shift = bits > 12 ? bits - 12 : 0;
+    TRY(s->d_bins.ensure(4096 * sizeof(uint32_t)));
+    launch_log_hist(log_view(s, par), cnt, dst, shift, s->d_bins.as<uint32_t>(), s->st);
+    s->stats.kernel_launches++;
+    std::vector<uint32_t> bins(4096);
+    CU(cudaMemcpyAsync(bins.data(), s->d_bins.p, 4096 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->stats.d2h_bytes += 4096 * sizeof(uint32_t);
+    std::vector<uint64_t> cum(4096);
+    uint64_t run = 0;
+    for (int b = 0; b < 4096; ++b) { run += bins[b]; cum[b] = run; }
+    uint64_t target = s->size + s->size / 4 + 1024;
+    unsigned long long lo = 0; int use_lo = 0; uint64_t lo_cum = 0;
+    while (true) {
+        int b = 0;
+        while (b < 4095 && cum[b] < target) ++b;
+        unsigned long long hi = thr;
+        if (b < 4095 && shift < 64) {
+            const unsigned long long top = (((unsigned long long)b + 1ULL) << shift) - 1ULL;
+            if (top < thr) hi = top;
+        }
+        if (s->scaled && hi < s->max_hash) {      // everything <= max_hash is kept: the band must reach it
+            hi = std::min<unsigned long long>(thr, s->max_hash);
+            b = (int)std::min<unsigned long long>(4095ULL, hi >> shift);
+        }
+        const uint64_t n_band = cum[b] - lo_cum;  // upper bound of the entries inside (lo, hi]
+        // room for n_band new keys (prune / grow first when the table is too full)
+        {
+            const uint32_t cap = s->tab[s->cur].cap, limit = cap / 4 * 3;
+            if ((uint64_t)s->h_state->occupied + n_band > limit) TRY(prune(s, (uint32_t)std::min<uint64_t>(n_band, 1u << 30)));
+        }
+        launch_absorb_band(log_view(s, par), cnt, s->tab[s->cur].view(), dst, lo, use_lo, hi, s->st);
+        s->stats.kernel_launches += 2;
+        if (hi >= thr) break;                     // the whole log has been absorbed
+        bool ok = false;
+        TRY(prune(s, 0, &hi, &ok));               // pulls the state; commits only if >= size keys are <= hi
+        if (ok) { *done = true; return FB2_OK; }
+        lo = hi; use_lo = 1; lo_cum = cum[b];
+        target = cum[b] * 4 + 1024;
+    }
+    TRY(pull_state(s));
+    return FB2_OK;
+}
+
 static int absorb_log(fb2_sketcher *s, int par, uint32_t cnt) {
+    if (s->size > 0 && cnt > 65536u && (uint64_t)cnt > 2 * s->size) {
+        bool done = false;
+        TRY(absorb_log_banded(s, par, cnt, &done));
+        if (done) return FB2_OK;
+        // the whole log was absorbed band by band: fall through to the usual post-absorb pruning
+        cnt = 0;
+    }
     uint32_t i = 0;
     bool exact = true;  // h_state->occupied is exact right after a pull
     while (i < cnt) {

@@ -26,22 +26,41 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 // byte groups:  w * c = A4(lo) * c + (A4(hi) * c << 32)  with A4(b) the 4 ASCII bytes of the 4
 // bases b.  lut_c[b] = A4(b) * c (64 bit) turns "expand 2-bit codes to ASCII, then multiply" into
 // two shared-memory loads and one add, which moves ~20 instructions per k-mer off the ALU pipe.
-struct MulLut { const uint2 *c1; const uint2 *c2; };
+struct MulLut { uint32_t c1; uint32_t c2; };   // shared-window byte addresses of the two tables
+
+// The kernel is bound by the ALU pipe (LOP3/SHF/IADD3/ISETP); IMAD runs on the FMA pipe.  These
+// helpers keep 64-bit additions and table address arithmetic on the FMA pipe.
+__device__ __forceinline__ uint64_t add64_fma(uint64_t a, uint64_t b) {
+    uint64_t t;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(t) : "r"((uint32_t)a), "l"(b));       // b + a.lo (64-bit)
+    uint32_t hi;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(hi) : "r"((uint32_t)(a >> 32)), "r"((uint32_t)(t >> 32)));
+    return ((uint64_t)hi << 32) | (uint32_t)t;
+}
+__device__ __forceinline__ uint2 lut_load(uint32_t table, uint32_t idx) {
+    uint32_t addr;
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(idx), "r"(table));
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 
 template <int NBYTES, bool IS_C1>
 __device__ __forceinline__ uint64_t mul_word(uint32_t g16, const MulLut &L) {
     // g16: 8 bases (2 bits each, base 0 lowest); NBYTES of them exist, the rest are zero bytes.
-    const uint2 *T = IS_C1 ? L.c1 : L.c2;
+    const uint32_t T = IS_C1 ? L.c1 : L.c2;
     const uint64_t C = IS_C1 ? MM_C1 : MM_C2;
     if (NBYTES >= 8) {
-        const uint2 a = T[g16 & 0xFFu], b = T[g16 >> 8];
-        return ((uint64_t)(a.y + b.x) << 32) | a.x;
+        const uint2 a = lut_load(T, g16 & 0xFFu), b = lut_load(T, g16 >> 8);
+        uint32_t hi;
+        asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(hi) : "r"(b.x), "r"(a.y));
+        return ((uint64_t)hi << 32) | a.x;
     } else if (NBYTES > 4) {
-        const uint2 a = T[g16 & 0xFFu];
+        const uint2 a = lut_load(T, g16 & 0xFFu);
         const uint32_t hi4 = expand4(g16 >> 8) & (uint32_t)low_bytes_mask(NBYTES - 4);
         return ((uint64_t)(a.y + hi4 * (uint32_t)C) << 32) | a.x;
     } else if (NBYTES == 4) {
-        const uint2 a = T[g16 & 0xFFu];
+        const uint2 a = lut_load(T, g16 & 0xFFu);
         return ((uint64_t)a.y << 32) | a.x;
     } else {
         const uint32_t lo4 = expand4(g16 & 0xFFu) & (uint32_t)low_bytes_mask(NBYTES);
@@ -58,17 +77,17 @@ __device__ __forceinline__ uint64_t murmur_kmer_h1_lut(uint64_t codes, uint64_t 
         uint64_t k1 = mul_word<8, true>((uint32_t)(codes & 0xFFFFu), L);
         uint64_t k2 = mul_word<8, false>((uint32_t)((codes >> 16) & 0xFFFFu), L);
         k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
-        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+        h1 = rotl64(h1, 27); h1 = add64_fma(h1, h2); h1 = h1 * 5 + 0x52dce729ULL;
         k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
-        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+        h2 = rotl64(h2, 31); h2 = add64_fma(h2, h1); h2 = h2 * 5 + 0x38495ab5ULL;
     }
     if (NB >= 2) {
         uint64_t k1 = mul_word<8, true>((uint32_t)((codes >> 32) & 0xFFFFu), L);
         uint64_t k2 = mul_word<8, false>((uint32_t)((codes >> 48) & 0xFFFFu), L);
         k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
-        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+        h1 = rotl64(h1, 27); h1 = add64_fma(h1, h2); h1 = h1 * 5 + 0x52dce729ULL;
         k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
-        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+        h2 = rotl64(h2, 31); h2 = add64_fma(h2, h1); h2 = h2 * 5 + 0x38495ab5ULL;
     }
     constexpr int TW = 2 * NB;  // first tail word
     if (T > 8) {
@@ -86,7 +105,7 @@ __device__ __forceinline__ uint64_t murmur_kmer_h1_lut(uint64_t codes, uint64_t 
     return h1;
 }
 
-constexpr uint32_t LOG_RESERVE = 8;   // extra log slots a warp reserves per atomic (<= 31)
+constexpr uint32_t LOG_RESERVE = 3;   // extra log slots a warp reserves per atomic (<= 31)
 
 // ---- TMA (1-D bulk copy) staging of the block's symbol tile ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,7 +149,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
         }
         __syncthreads();
     }
-    MulLut L; L.c1 = lut_c1; L.c2 = lut_c2;
+    MulLut L; L.c1 = smem_u32(lut_c1); L.c2 = smem_u32(lut_c2);
     __shared__ __align__(128) uint8_t tile[32 + HASH_TILE];   // 32 symbols of halo, then the block's positions
     __shared__ __align__(8) uint64_t tile_bar;
     const int k = K > 0 ? K : k_rt;
@@ -143,6 +162,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
     const uint8_t *sym = symbuf + (size_t)SYM_FRONT + (size_t)region * g.region_stride;
     const uint64_t ord_region = ord_base + (uint64_t)region * g.st_bytes;
     const unsigned long long T = st->threshold;
+    const uint32_t T_hi = (uint32_t)(T >> 32);
     const uint32_t lane = threadIdx.x & 31u;
     // ---- stage [pb - 32, min(end + HASH_W, pb + HASH_TILE)) with one TMA bulk copy --------------
     // (positions in [end, end + HASH_W) hold SYM_BREAK, written by pack_kernel)
@@ -196,9 +216,12 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
             if (K > 0) h = murmur_kmer_h1_lut<(K > 0 ? K : 1)>(codes, seed, L);
             else h = murmur_kmer_h1<0>(codes, k, seed);
             nvalid += ok ? 1u : 0u;
-            const bool emit = ok && (h <= T);
-            const uint32_t em = __ballot_sync(0xffffffffu, emit);
-            if (em) {
+            // hot path: compare only the high words (conservative); the exact test is in the branch
+            const bool maybe = ok && ((uint32_t)(h >> 32) <= T_hi);
+            if (__any_sync(0xffffffffu, maybe)) {
+              const bool emit = maybe && (h <= T);
+              const uint32_t em = __ballot_sync(0xffffffffu, emit);
+              if (em) {
                 // Warp-private bump reservation in the log: the global atomic (and the wait for its
                 // result) happens once per LOG_RESERVE candidates, not once per candidate.
                 const uint32_t n = __popc(em);
@@ -219,6 +242,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
                     }
                 }
                 res_base += n; res_left -= n;
+              }
             }
         }
     }

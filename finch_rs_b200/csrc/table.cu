@@ -51,28 +51,33 @@ __device__ __forceinline__ uint32_t table_find(const TableView &t, unsigned long
 
 // Pass 1: counts, strand counts and the minimum position per key.  Entries above the current
 // threshold (logged under an older, larger threshold) are dropped.
-__global__ void absorb_count_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st) {
+// Optional hash band (lo, hi]: only entries inside it are absorbed (banded absorb of large logs).
+struct Band { unsigned long long lo, hi; int use_lo; };
+__device__ __forceinline__ bool in_band(const Band &b, unsigned long long key) {
+    return key <= b.hi && (!b.use_lo || key > b.lo);
+}
+__global__ void absorb_count_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st, Band band) {
     const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= i1) return;
     const unsigned long long px = log.posx[i];
     if (px == ~0ULL) return;                      // unused slot of a warp's reservation
     const unsigned long long key = log.hash[i];
-    if (key > st->threshold) return;
+    if (key > st->threshold || !in_band(band, key)) return;
     const uint32_t slot = table_upsert(t, key, st);
     atomicAdd(&t.cnt[slot], 1ULL);
     const unsigned long long extra = px & 0xFFULL;
     if (extra) atomicAdd(&t.ext[slot], extra);
-    atomicMin(&t.posx[slot], px);
+    if (px < __ldcg(&t.posx[slot])) atomicMin(&t.posx[slot], px);   // stored value only decreases: a stale read is safe
 }
 // Pass 2: the occurrence that owns the minimum position donates the k-mer (mash.rs:52-55 keeps
 // the k-mer of the first push of a hash).
-__global__ void absorb_kmer_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, const SketchState *st) {
+__global__ void absorb_kmer_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, const SketchState *st, Band band) {
     const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= i1) return;
     const unsigned long long px = log.posx[i];
     if (px == ~0ULL) return;
     const unsigned long long key = log.hash[i];
-    if (key > st->threshold) return;
+    if (key > st->threshold || !in_band(band, key)) return;
     const uint32_t slot = table_find(t, key);
     if (slot == 0xFFFFFFFFu) return;
     if (t.posx[slot] == px) t.kmer[slot] = log.kmer[i];
@@ -104,7 +109,7 @@ __global__ void absorb_count_guarded_kernel(LogView log, const LaunchSlot *slot,
         atomicAdd(&t.cnt[s], 1ULL);
         const unsigned long long extra = px & 0xFFULL;
         if (extra) atomicAdd(&t.ext[s], extra);
-        atomicMin(&t.posx[s], px);
+        if (px < __ldcg(&t.posx[s])) atomicMin(&t.posx[s], px);
     }
 }
 __global__ void absorb_kmer_guarded_kernel(LogView log, const LaunchSlot *slot, TableView t, const SketchState *st) {
@@ -173,6 +178,24 @@ table_hist_kernel(TableView t, const SketchState *st, uint32_t shift, uint32_t *
     for (int i = threadIdx.x; i < PRUNE_BINS; i += blockDim.x)
         if (h[i]) atomicAdd(&bins[i], h[i]);
 }
+// Histogram of the hashes of a candidate log (valid entries at or below the threshold).
+__global__ void __launch_bounds__(256)
+log_hist_kernel(LogView log, uint32_t n, const SketchState *st, uint32_t shift, uint32_t *__restrict__ bins) {
+    __shared__ uint32_t h[PRUNE_BINS];
+    for (int i = threadIdx.x; i < PRUNE_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const unsigned long long thr = st->threshold;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (log.posx[i] == ~0ULL) continue;
+        const unsigned long long key = log.hash[i];
+        if (key > thr) continue;
+        atomicAdd(&h[min((unsigned long long)(PRUNE_BINS - 1), key >> shift)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PRUNE_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&bins[i], h[i]);
+}
 // One block of 1024 threads, 4 bins each: smallest bin boundary with cumulative count >= size.
 __global__ void __launch_bounds__(1024)
 table_select_kernel(const uint32_t *__restrict__ bins, uint32_t shift, int scaled, unsigned long long size,
@@ -213,25 +236,32 @@ table_select_kernel(const uint32_t *__restrict__ bins, uint32_t shift, int scale
     }
 }
 // Occupied slots with key <= new_threshold -> (key, slot), arbitrary order; count in gather_count.
-__global__ void gather_le_kernel(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots) {
+// One global atomic per block (warp ballots -> shared counter -> block base).
+__global__ void __launch_bounds__(256)
+gather_le_kernel(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots) {
+    __shared__ uint32_t blk_count, blk_base;
+    if (threadIdx.x == 0) blk_count = 0;
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > t.cap) return;
     const unsigned long long thr = st->new_threshold;
     unsigned long long key = EMPTY_KEY;
-    bool occ;
-    if (i == t.cap) occ = st->has_max_key != 0u;
-    else { key = t.key[i]; occ = key != EMPTY_KEY; }
+    bool occ = false;
+    if (i < t.cap) { key = t.key[i]; occ = key != EMPTY_KEY; }
+    else if (i == t.cap) occ = st->has_max_key != 0u;
     occ = occ && key <= thr;
-    const uint32_t m = __ballot_sync(__activemask(), occ);
-    if (!occ) return;
+    const uint32_t m = __ballot_sync(0xffffffffu, occ);
     const uint32_t lane = threadIdx.x & 31u;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(&st->gather_count, (unsigned int)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    const uint32_t idx = base + __popc(m & ((1u << lane) - 1u));
-    keys[idx] = key;
-    slots[idx] = i;
+    uint32_t wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&blk_count, (unsigned int)__popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk_count) blk_base = atomicAdd(&st->gather_count, blk_count);
+    __syncthreads();
+    if (occ) {
+        const uint32_t idx = blk_base + wbase + __popc(m & ((1u << lane) - 1u));
+        keys[idx] = key;
+        slots[idx] = i;
+    }
 }
 
 // ---- LSD radix sort, 8 bits per pass, (u64 key, u32 value), stable --------------------------
@@ -381,8 +411,20 @@ static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 void launch_absorb(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st, cudaStream_t s) {
     if (i1 <= i0) return;
-    absorb_count_kernel<<<cdiv(i1 - i0, 256), 256, 0, s>>>(log, i0, i1, t, st);
-    absorb_kmer_kernel<<<cdiv(i1 - i0, 256), 256, 0, s>>>(log, i0, i1, t, st);
+    Band all; all.lo = 0; all.hi = ~0ULL; all.use_lo = 0;
+    absorb_count_kernel<<<cdiv(i1 - i0, 256), 256, 0, s>>>(log, i0, i1, t, st, all);
+    absorb_kmer_kernel<<<cdiv(i1 - i0, 256), 256, 0, s>>>(log, i0, i1, t, st, all);
+}
+void launch_absorb_band(LogView log, uint32_t n, TableView t, SketchState *st, unsigned long long lo, int use_lo,
+                        unsigned long long hi, cudaStream_t s) {
+    if (!n) return;
+    Band b; b.lo = lo; b.hi = hi; b.use_lo = use_lo;
+    absorb_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(log, 0, n, t, st, b);
+    absorb_kmer_kernel<<<cdiv(n, 256), 256, 0, s>>>(log, 0, n, t, st, b);
+}
+void launch_log_hist(LogView log, uint32_t n, const SketchState *st, uint32_t shift, uint32_t *bins, cudaStream_t s) {
+    cudaMemsetAsync(bins, 0, PRUNE_BINS * sizeof(uint32_t), s);
+    if (n) log_hist_kernel<<<min(cdiv(n, 256), 1184u), 256, 0, s>>>(log, n, st, shift, bins);
 }
 void launch_absorb_guarded(LogView log, LaunchSlot *slot, TableView t, SketchState *st, const ParseCarry *carry,
                            uint32_t expect, cudaStream_t s) {
