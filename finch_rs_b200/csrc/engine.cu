@@ -478,7 +478,7 @@ static ChunkGeom make_geom(uint32_t len) {
     ChunkGeom g;
     g.len = len;
     g.n_tiles = cdivu(len, TILE_BYTES);
-    uint32_t stt = g.n_tiles / 592u;   // aim at >= 4 blocks per SM before growing supertiles
+    uint32_t stt = g.n_tiles / 4096u;  // ~4096 supertiles per full chunk: several waves of blocks, small tails
     if (stt < 1) stt = 1;
     if (stt > 32) stt = 32;
     g.st_tiles = stt;

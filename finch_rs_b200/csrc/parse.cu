@@ -40,11 +40,17 @@ __device__ __forceinline__ uint32_t raw_byte(const Raw16 &r, int i) {
     const uint64_t lo = (uint64_t)r.w[0] | ((uint64_t)r.w[1] << 32), hi = (uint64_t)r.w[2] | ((uint64_t)r.w[3] << 32);
     return (uint32_t)((i < 8 ? (lo >> (8 * i)) : (hi >> (8 * (i - 8)))) & 0xFFu);
 }
-__device__ __forceinline__ void load_raw(const uint8_t *__restrict__ raw, uint32_t off, uint32_t len, Raw16 &r) {
+// issue the 16-byte load of a full piece early (software pipelining of the tile loop)
+__device__ __forceinline__ uint4 fetch_raw(const uint8_t *__restrict__ raw, uint32_t off, uint32_t len) {
+    if (off + 16u <= len) return __ldg(reinterpret_cast<const uint4 *>(raw + off));
+    return make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void load_raw(const uint8_t *__restrict__ raw, uint32_t off, uint32_t len, Raw16 &r,
+                                         const uint4 *pre = nullptr) {
     r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0;
     int nvalid;
     if (off + 16u <= len) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + off));
+        const uint4 v = pre ? *pre : __ldg(reinterpret_cast<const uint4 *>(raw + off));
         r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
         nvalid = 16;
     } else {
@@ -222,10 +228,13 @@ phase_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, const ParseCarry *__r
     const uint32_t st = blockIdx.x;
     const uint32_t t0 = st * g.st_tiles, t1 = min(t0 + g.st_tiles, g.n_tiles);
     unsigned long long acc = 0;  // FASTQ: newline count; FASTA: max over line starts of (pos+1) << 1 | is_header
+    uint4 nextv = fetch_raw(raw, t0 * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u, g.len);
     for (uint32_t t = t0; t < t1; ++t) {
         const uint32_t off = t * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u;
         Raw16 r;
-        load_raw(raw, off, g.len, r);
+        const uint4 curv = nextv;
+        if (t + 1 < t1) nextv = fetch_raw(raw, off + (uint32_t)TILE_BYTES, g.len);
+        load_raw(raw, off, g.len, r, &curv);
         if (MODE == MODE_FASTQ) {
             acc += __popc(r.nl);
         } else {
@@ -333,10 +342,13 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
     uint32_t recs = 0;
     unsigned long long bad_pos = ~0ULL;
 
+    uint4 nextv = fetch_raw(raw, t0 * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u, g.len);
     for (uint32_t t = t0; t < t1; ++t) {
         const uint32_t off = t * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u;
         Raw16 r;
-        load_raw(raw, off, g.len, r);
+        const uint4 curv = nextv;
+        if (t + 1 < t1) nextv = fetch_raw(raw, off + (uint32_t)TILE_BYTES, g.len);   // next tile's bytes in flight
+        load_raw(raw, off, g.len, r, &curv);
         uint32_t em = 0, four = 0;
         SeqCls c;
 
