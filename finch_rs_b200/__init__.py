@@ -385,13 +385,38 @@ def ScaledSketcher(size, scale, kmer_length, seed, device=-1):
 
 
 # ---------------------------------------------------------------------------------------------
+class _ResultOwner:
+    """Keeps a library-owned fb2_result alive while numpy views of its arrays are in use."""
+
+    def __init__(self, r):
+        self.r = r
+
+    def __del__(self):
+        try:
+            lib().fb2_result_free(C.byref(self.r))
+        except Exception:
+            pass
+
+
 def _finish(r, name, sp):
-    try:
-        h, c, x, km = _result_to_py(r, sp.kmer_length)
-        return Sketch(name, int(r.seq_length), int(r.num_valid_kmers), "", h, c, x, km,
-                      FilterParams._from_c(r.filters), sp, int(r.format))
-    finally:
-        lib().fb2_result_free(C.byref(r))
+    n, st = int(r.n), int(r.kmer_stride)
+    if n < 65536:   # small: plain copies
+        try:
+            h, c, x, km = _result_to_py(r, sp.kmer_length)
+            return Sketch(name, int(r.seq_length), int(r.num_valid_kmers), "", h, c, x, km,
+                          FilterParams._from_c(r.filters), sp, int(r.format))
+        finally:
+            lib().fb2_result_free(C.byref(r))
+    # large (e.g. Scaled sketches of whole genomes): zero-copy views, freed with the Sketch
+    owner = _ResultOwner(r)
+    h = np.ctypeslib.as_array(r.hashes, (n,))
+    c = np.ctypeslib.as_array(r.counts, (n,))
+    x = np.ctypeslib.as_array(r.extras, (n,))
+    km = np.ctypeslib.as_array(r.kmers, (n * st,)).reshape(n, st)
+    sk = Sketch(name, int(r.seq_length), int(r.num_valid_kmers), "", h, c, x, km,
+                FilterParams._from_c(r.filters), sp, int(r.format))
+    sk._owner = owner
+    return sk
 
 
 def sketch_stream(data, name: str, sketch_params: SketchParams, filters: FilterParams) -> Sketch:

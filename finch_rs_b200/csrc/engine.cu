@@ -322,14 +322,45 @@ static int sort_table(fb2_sketcher *s, uint32_t *n_out) {
     TRY(pull_state(s));
     const uint32_t n = s->h_state->occupied + (s->h_state->has_max_key ? 1u : 0u);
     TRY(ensure_sort(s, std::max(n, 1u)));
-    launch_gather(s->tab[s->cur].view(), (SketchState *)s->d_state.p, s->sort_keys.as<unsigned long long>(),
-                  s->sort_slots.as<uint32_t>(), s->st);
-    launch_radix_sort(s->sort_keys.as<unsigned long long>(), s->sort_slots.as<uint32_t>(),
-                      s->sort_tkeys.as<unsigned long long>(), s->sort_tslots.as<uint32_t>(), n,
-                      s->sort_hist.as<uint32_t>(), s->st);
-    launch_select_keep(s->sort_keys.as<unsigned long long>(), n, s->scaled ? 1 : 0, s->size, s->max_hash,
-                       (SketchState *)s->d_state.p, s->st);
-    s->stats.kernel_launches += 2 + (n >= 2 ? 24 : 0) + 1;
+    TRY(s->d_bins.ensure(3 * 4096 * sizeof(uint32_t)));
+    SketchState *dst = (SketchState *)s->d_state.p;
+    unsigned long long *keys = s->sort_keys.as<unsigned long long>(), *tkeys = s->sort_tkeys.as<unsigned long long>();
+    uint32_t *slots = s->sort_slots.as<uint32_t>(), *tslots = s->sort_tslots.as<uint32_t>();
+    launch_gather(s->tab[s->cur].view(), dst, tkeys, tslots, s->st);          // unsorted -> (tkeys, tslots)
+    s->stats.kernel_launches += 2;
+    // bucket + rank sort on the top 12 bits below the threshold; keys above the threshold cannot
+    // exist in the table except the u64::MAX side slot (threshold == MAX then)
+    const unsigned long long thr = s->h_state->threshold;
+    uint32_t bits = 0;
+    while (bits < 64 && (thr >> bits) != 0ULL) ++bits;
+    const uint32_t shift = bits > 12 ? bits - 12 : 0;
+    bool sorted = false;
+    if (n >= 2) {
+        uint32_t *bins = s->d_bins.as<uint32_t>();
+        // scatter target: (keys, slots) as scratch is not possible (rank needs a third buffer): use
+        // out_hash/out_cnt-sized scratch from the sort pool: tkeys -> keys (scatter) -> tkeys (rank)
+        launch_bucket_sort(tkeys, tslots, keys, slots, tkeys, tslots, n, shift, bins, bins + 4096, bins + 8192, dst, s->st);
+        s->stats.kernel_launches += 4;
+        TRY(pull_state(s));
+        if (s->h_state->gather_count <= bucket_cap()) {
+            // result is in (tkeys, tslots): copy to (keys, slots) where the consumers expect it
+            CU(cudaMemcpyAsync(keys, tkeys, (size_t)n * 8, cudaMemcpyDeviceToDevice, s->st));
+            CU(cudaMemcpyAsync(slots, tslots, (size_t)n * 4, cudaMemcpyDeviceToDevice, s->st));
+            sorted = true;
+        } else {
+            // non-uniform keys: (keys, slots) hold the bucket-scattered (complete) set: radix sort them
+            launch_radix_sort(keys, slots, tkeys, tslots, n, s->sort_hist.as<uint32_t>(), s->st);
+            s->stats.kernel_launches += 24;
+            sorted = true;
+        }
+    } else if (n == 1) {
+        CU(cudaMemcpyAsync(keys, tkeys, 8, cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaMemcpyAsync(slots, tslots, 4, cudaMemcpyDeviceToDevice, s->st));
+        sorted = true;
+    }
+    (void)sorted;
+    launch_select_keep(keys, n, s->scaled ? 1 : 0, s->size, s->max_hash, dst, s->st);
+    s->stats.kernel_launches += 1;
     TRY(pull_state(s));
     *n_out = n;
     return FB2_OK;

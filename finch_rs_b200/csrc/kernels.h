@@ -32,6 +32,10 @@ void launch_gather(TableView t, SketchState *st, unsigned long long *keys, uint3
 void launch_radix_sort(unsigned long long *keys, uint32_t *vals, unsigned long long *tkeys, uint32_t *tvals,
                        uint32_t n, uint32_t *hist, cudaStream_t s);
 uint32_t radix_hist_words(uint32_t n);
+void launch_bucket_sort(const unsigned long long *keys, const uint32_t *vals, unsigned long long *tkeys, uint32_t *tvals,
+                        unsigned long long *okeys, uint32_t *ovals, uint32_t n, uint32_t shift, uint32_t *bins,
+                        uint32_t *offs, uint32_t *cursor, SketchState *st, cudaStream_t s);
+uint32_t bucket_cap();
 void launch_prune_select(TableView t, SketchState *st, uint32_t shift, uint32_t *bins, int scaled,
                          unsigned long long size, unsigned long long max_hash, unsigned long long *keys,
                          uint32_t *slots, cudaStream_t s);

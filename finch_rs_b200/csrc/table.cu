@@ -334,6 +334,85 @@ radix_scatter_kernel(const unsigned long long *__restrict__ keys, const uint32_t
     }
 }
 
+// ---- bucket + rank sort for (nearly) uniform keys ------------------------------------------------
+// Sketch keys are murmur hashes below a known threshold, i.e. uniform: 4096 buckets on the top bits
+// hold ~n/4096 keys each, and a block ranks one bucket in shared memory by counting.  4 launches
+// instead of the radix sort's 24.  The host falls back to the radix sort when a bucket exceeds
+// BUCKET_CAP (non-uniform keys).
+constexpr uint32_t BUCKET_CAP = 2048;
+__global__ void __launch_bounds__(256)
+bucket_hist_kernel(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t shift, uint32_t *__restrict__ bins) {
+    __shared__ uint32_t h[PRUNE_BINS];
+    for (int i = threadIdx.x; i < PRUNE_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&h[min((unsigned long long)(PRUNE_BINS - 1), keys[i] >> shift)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < PRUNE_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&bins[i], h[i]);
+}
+// bins[4096] -> exclusive offsets in offs[4096] (+ cursors), largest bucket in st->gather_count
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__restrict__ bins, uint32_t *__restrict__ offs,
+                                                           uint32_t *__restrict__ cursor, SketchState *st) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t wmax[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t b0 = bins[4 * tid], b1 = bins[4 * tid + 1], b2 = bins[4 * tid + 2], b3 = bins[4 * tid + 3];
+    const uint32_t c = b0 + b1 + b2 + b3;
+    uint32_t mx = max(max(b0, b1), max(b2, b3));
+    uint32_t x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += v; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (lane == 31u) wsum[wid] = x;
+    if (lane == 0u) wmax[wid] = mx;
+    __syncthreads();
+    if (wid == 0u) {
+        uint32_t v = wsum[lane], y = v, m2 = wmax[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, y, d); if (lane >= (uint32_t)d) y += u; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m2 = max(m2, __shfl_xor_sync(0xffffffffu, m2, d));
+        wsum[lane] = y - v;
+        if (lane == 0u) st->gather_count = m2;   // reused as "largest bucket"
+    }
+    __syncthreads();
+    uint32_t o = wsum[wid] + x - c;
+    offs[4 * tid] = o; cursor[4 * tid] = o; o += b0;
+    offs[4 * tid + 1] = o; cursor[4 * tid + 1] = o; o += b1;
+    offs[4 * tid + 2] = o; cursor[4 * tid + 2] = o; o += b2;
+    offs[4 * tid + 3] = o; cursor[4 * tid + 3] = o;
+}
+__global__ void bucket_scatter_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                      uint32_t n, uint32_t shift, uint32_t *__restrict__ cursor,
+                                      unsigned long long *__restrict__ okeys, uint32_t *__restrict__ ovals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    const uint32_t b = (uint32_t)min((unsigned long long)(PRUNE_BINS - 1), k >> shift);
+    const uint32_t pos = atomicAdd(&cursor[b], 1u);
+    okeys[pos] = k; ovals[pos] = vals[i];
+}
+// one block per bucket: rank every key among the bucket's keys (all distinct) and write it in order
+__global__ void __launch_bounds__(128)
+bucket_rank_kernel(const unsigned long long *__restrict__ ikeys, const uint32_t *__restrict__ ivals,
+                   const uint32_t *__restrict__ offs, const uint32_t *__restrict__ bins,
+                   unsigned long long *__restrict__ okeys, uint32_t *__restrict__ ovals) {
+    __shared__ unsigned long long sk[BUCKET_CAP];
+    const uint32_t b = blockIdx.x, o = offs[b], m = bins[b];
+    if (m == 0 || m > BUCKET_CAP) return;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) sk[i] = ikeys[o + i];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const unsigned long long k = sk[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < m; ++j) rank += sk[j] < k ? 1u : 0u;
+        okeys[o + rank] = k; ovals[o + rank] = ivals[o + i];
+    }
+}
+
 // After the sort: how many entries the sketch keeps, and the threshold that follows.
 //   Mash:   keep = min(n, s)                      new_threshold = key[s-1] when n >= s
 //   Scaled: keep = max(#{key <= max_hash}, min(n, s)); threshold = max(max_hash, key[s-1]) when n >= s
@@ -467,6 +546,19 @@ void launch_prune_select(TableView t, SketchState *st, uint32_t shift, uint32_t 
     reset_gather_kernel<<<1, 1, 0, s>>>(st);
     gather_le_kernel<<<cdiv(t.cap + 1, 256), 256, 0, s>>>(t, st, keys, slots);
 }
+// Bucket sort (keys <= 2^bits - 1 assumed roughly uniform).  Result lands in (tkeys, tvals); the
+// largest bucket is left in st->gather_count for the host to check against bucket_cap().
+void launch_bucket_sort(const unsigned long long *keys, const uint32_t *vals, unsigned long long *tkeys, uint32_t *tvals,
+                        unsigned long long *okeys, uint32_t *ovals, uint32_t n, uint32_t shift, uint32_t *bins,
+                        uint32_t *offs, uint32_t *cursor, SketchState *st, cudaStream_t s) {
+    cudaMemsetAsync(bins, 0, PRUNE_BINS * sizeof(uint32_t), s);
+    if (!n) return;
+    bucket_hist_kernel<<<min(cdiv(n, 256), 1184u), 256, 0, s>>>(keys, n, shift, bins);
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(bins, offs, cursor, st);
+    bucket_scatter_kernel<<<cdiv(n, 256), 256, 0, s>>>(keys, vals, n, shift, cursor, tkeys, tvals);
+    bucket_rank_kernel<<<PRUNE_BINS, 128, 0, s>>>(tkeys, tvals, offs, bins, okeys, ovals);
+}
+uint32_t bucket_cap() { return BUCKET_CAP; }
 uint32_t radix_hist_words(uint32_t n) { return 256u * cdiv(n ? n : 1, SORT_SEG); }
 
 void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride, const unsigned long long *i_hash,
