@@ -320,28 +320,16 @@ phase_scan_kernel(const uint32_t *__restrict__ st_map, ChunkGeom g, ParseCarry *
 }
 
 // ------------------------------------------------------------------------------------------------
+// Exact tile walk of one supertile: 16 raw bytes per thread, every byte classified, line state by
+// block scans, symbols written byte by byte.  Handles anything (blanks / CRs inside sequence lines,
+// thousands of lines per tile); pack_kernel below falls back to it when its fast path declines.
 template <int MODE>
-__global__ void __launch_bounds__(TILE_THREADS)
-pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, const uint32_t *__restrict__ st_state,
-            uint8_t *__restrict__ sym, uint32_t *__restrict__ region_count) {
-    __shared__ uint8_t lut[256];
-    __shared__ uint32_t sh8[8];
-    __shared__ unsigned long long sh8l[8];
+__device__ __forceinline__ void pack_exact(const uint8_t *__restrict__ raw, const ChunkGeom &g, uint32_t t0, uint32_t t1,
+                                           uint64_t raw_base, uint32_t cprev1, uint32_t cprev2, uint32_t state,
+                                           uint8_t *__restrict__ region, const uint8_t *lut, uint32_t *sh8,
+                                           uint32_t &out_off, long long &bases_delta, uint32_t &recs,
+                                           unsigned long long &bad_pos) {
     const int tid = threadIdx.x;
-    lut[tid] = classify_byte((uint8_t)tid);
-    __syncthreads();
-    const uint32_t st = blockIdx.x;
-    const uint32_t t0 = st * g.st_tiles, t1 = min(t0 + g.st_tiles, g.n_tiles);
-    const uint64_t raw_base = carry->chunk_raw_base;
-    const uint32_t cprev1 = carry->cprev1, cprev2 = carry->cprev2;
-    uint8_t *region = sym + (size_t)SYM_FRONT + (size_t)st * g.region_stride;
-
-    uint32_t state = MODE == MODE_LINES ? 0u : st_state[st];  // state of the line holding the previous byte
-    uint32_t out_off = 0;                                     // symbols written so far in this region
-    long long bases_delta = 0;
-    uint32_t recs = 0;
-    unsigned long long bad_pos = ~0ULL;
-
     uint4 nextv = fetch_raw(raw, t0 * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u, g.len);
     for (uint32_t t = t0; t < t1; ++t) {
         const uint32_t off = t * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u;
@@ -447,6 +435,254 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
             }
         }
         out_off += tile_total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack_kernel: one block per supertile.  Fast path, per batch of 8 KiB staged in shared memory:
+//   1. 2 x 16 bytes per thread -> shared memory; newline masks from registers
+//   2. block scan of newline counts -> sorted newline positions s_nl[]: the batch is now a list of
+//      line pieces (N newlines -> N + 1 pieces; piece 0 / piece N may be cut by the batch edges)
+//   3. one thread per piece: line state of the piece (FASTQ: phase = state + index; FASTA: header
+//      iff the line starts with '>'), the record / base counters and FASTQ '@' / '+' checks of the
+//      reference parser, and the piece's output entry (source offset, kept length, trailing BREAK);
+//      block scan of the output lengths; every 16-byte output word learns its first entry
+//   4. one thread per ALIGNED 16-byte output word: unaligned 16-byte read from shared memory
+//      (5 LDS + 4 PRMT), SIMD-in-register base codes, one 16-byte store
+// Only sequence bytes are classified and every store is a full aligned word.  The fast path
+// assumes what normalize(false) would remove inside a sequence line is at most one CR at its end;
+// a blank or CR anywhere else, or more than PB_NLCAP newlines in a batch, makes the block redo its
+// supertile with pack_exact.
+constexpr int PB_BYTES = 2 * TILE_BYTES;
+constexpr int PB_NLCAP = 1535;
+
+__device__ __forceinline__ void ones128(uint32_t nbytes, uint64_t &lo, uint64_t &hi) {   // nbytes in 0..16
+    lo = nbytes >= 8u ? ~0ULL : ((1ULL << (8u * nbytes)) - 1ULL);
+    hi = nbytes <= 8u ? 0ULL : (nbytes >= 16u ? ~0ULL : ((1ULL << (8u * (nbytes - 8u))) - 1ULL));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE_THREADS)
+pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, const uint32_t *__restrict__ st_state,
+            uint8_t *__restrict__ sym, uint32_t *__restrict__ region_count) {
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t sh8[8];
+    __shared__ unsigned long long sh8l[8];
+    __shared__ __align__(16) uint8_t s_rawbuf[16 + PB_BYTES + 32];   // [16 front pad | batch | back pad]
+    __shared__ uint16_t s_nl[PB_NLCAP + 1];
+    __shared__ uint16_t e_src[PB_NLCAP + 1], e_len[PB_NLCAP + 1], e_out[PB_NLCAP + 1];
+    __shared__ uint16_t s_first[PB_BYTES / 16 + 2];
+    __shared__ uint32_t s_flag[2];   // [0] fast path declined, [1] FASTA: state after the batch
+    const int tid = threadIdx.x;
+    lut[tid] = classify_byte((uint8_t)tid);
+    if (tid < 2) s_flag[tid] = 0;
+    __syncthreads();
+    const uint32_t st = blockIdx.x;
+    const uint32_t t0 = st * g.st_tiles, t1 = min(t0 + g.st_tiles, g.n_tiles);
+    const uint32_t B0 = t0 * (uint32_t)TILE_BYTES, B1 = min(t1 * (uint32_t)TILE_BYTES, g.len);
+    const uint64_t raw_base = carry->chunk_raw_base;
+    const uint32_t cprev1 = carry->cprev1, cprev2 = carry->cprev2;
+    uint8_t *region = sym + (size_t)SYM_FRONT + (size_t)st * g.region_stride;
+    const uint32_t state0 = MODE == MODE_LINES ? 0u : st_state[st];  // state of the line holding the previous byte
+    constexpr uint32_t STEP = MODE == MODE_FASTQ ? 4u : 1u;          // FASTQ: only every 4th piece emits
+
+    uint32_t state = state0;
+    uint32_t out_off = 0;                                     // symbols written so far in this region
+    long long bases_delta = 0;
+    uint32_t recs = 0;
+    unsigned long long bad_pos = ~0ULL;
+    uint8_t *rawb = s_rawbuf + 16;
+    const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(s_rawbuf);
+    bool declined = false;
+
+    uint4 nextv[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) nextv[p] = fetch_raw(raw, B0 + (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u, B1);
+    for (uint32_t b = B0; b < B1; b += PB_BYTES) {
+        const uint32_t blen = min((uint32_t)PB_BYTES, B1 - b);
+        // ---- 1. stage the batch, newline masks --------------------------------------------------
+        uint32_t nlm[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t po = (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u;
+            const uint4 curv = nextv[p];
+            if (b + PB_BYTES < B1) nextv[p] = fetch_raw(raw, b + PB_BYTES + po, B1);   // next batch in flight
+            Raw16 r;
+            if (po < blen) load_raw(raw, b + po, B1, r, &curv);
+            else { r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0; r.nl = 0; }
+            *reinterpret_cast<uint4 *>(rawb + po) = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
+            nlm[p] = r.nl;
+        }
+        if (tid == 0) {   // the two bytes in front of the batch
+            rawb[-1] = (uint8_t)(b >= 1u ? raw[b - 1] : cprev1);
+            rawb[-2] = (uint8_t)(b >= 2u ? raw[b - 2] : (b == 1u ? cprev1 : cprev2));
+        }
+        // ---- 2. newline positions ---------------------------------------------------------------
+        uint32_t tot;
+        const uint32_t ex = block_exscan_add((uint32_t)__popc(nlm[0]) | ((uint32_t)__popc(nlm[1]) << 16), sh8, tot);
+        const uint32_t tot0 = tot & 0xFFFFu, N = tot0 + (tot >> 16);
+        if (N > (uint32_t)PB_NLCAP) { declined = true; break; }   // uniform
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            uint32_t m = nlm[p], at = p ? tot0 + (ex >> 16) : (ex & 0xFFFFu);
+            const uint32_t po = (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u;
+            while (m) {
+                s_nl[at++] = (uint16_t)(po + (uint32_t)(__ffs(m) - 1));
+                m &= m - 1u;
+            }
+        }
+        __syncthreads();
+        // ---- 3. pieces -> entries ---------------------------------------------------------------
+        const uint32_t NP = N + 1u;
+        const uint32_t G = (NP + TILE_THREADS - 1u) / TILE_THREADS;
+        const uint32_t i_lo = min((uint32_t)tid * G, NP), i_hi = min(i_lo + G, NP);
+        const bool ls0 = rawb[-1] == '\n';
+        // FASTA: the piece holding the batch's last byte (the trailing piece unless it is empty)
+        const uint32_t fa_tgt = ((N ? (uint32_t)s_nl[N - 1u] + 1u : 0u) < blen) ? N : N - 1u;
+        uint32_t sum = 0;
+        for (uint32_t i = i_lo; i < i_hi; ++i) {
+            const uint32_t start = i ? (uint32_t)s_nl[i - 1] + 1u : 0u;
+            const bool has_nl = i < N;
+            const uint32_t end = has_nl ? (uint32_t)s_nl[i] : blen;
+            const uint32_t len = end - start;
+            const bool line_start = i > 0u || ls0;
+            const uint32_t pb = rawb[(int)end - 1];            // byte in front of the piece's end
+            uint32_t klen = len - ((len > 0u && pb == '\r') ? 1u : 0u);   // one trailing CR goes
+            uint32_t L = 0;
+            if (MODE == MODE_LINES) {
+                L = klen | (has_nl ? 0x8000u : 0u);
+            } else if (MODE == MODE_FASTQ) {
+                const uint32_t ph = (state + i) & 3u;
+                if (line_start && start < blen) {
+                    if (ph == 0u) recs++;
+                    if ((ph == 0u || ph == 2u) && rawb[start] != (ph == 0u ? '@' : '+'))
+                        bad_pos = min(bad_pos, (unsigned long long)(raw_base + b + start));
+                }
+                if (ph == 1u) {
+                    // sequence().len(): the line without its '\n' and without one CR right before it
+                    bases_delta += (long long)len - ((has_nl && pb == '\r') ? 1 : 0);
+                    L = klen | (has_nl ? 0x8000u : 0u);
+                }
+            } else {  // MODE_FASTA
+                const bool hdr = line_start ? (start < blen && rawb[start] == '>') : ((state & 1u) != 0u);
+                if (line_start && hdr) {
+                    recs++;
+                    L = 0x8000u;                               // the header start is a record break
+                    bool prev_in_hdr;
+                    if (i == 0u) prev_in_hdr = state != 0u;
+                    else {
+                        const uint32_t ps = i > 1u ? (uint32_t)s_nl[i - 2] + 1u : 0u;
+                        prev_in_hdr = (i > 1u || ls0) ? rawb[ps] == '>' : ((state & 1u) != 0u);
+                    }
+                    // a new header ends the previous record: its raw sequence loses the final '\n'
+                    // (and one CR before it) when that newline closed a sequence line
+                    if (!prev_in_hdr) {
+                        bases_delta -= 1;
+                        if (rawb[(int)start - 2] == '\r') bases_delta -= 1;
+                    }
+                } else if (!hdr) {
+                    bases_delta += (long long)len + (has_nl ? 1 : 0);
+                    L = klen;
+                }
+                // state for the next batch: the line holding this batch's last byte
+                if (i == fa_tgt) s_flag[1] = hdr ? 1u : 0u;
+            }
+            e_src[i] = (uint16_t)start;
+            e_len[i] = (uint16_t)L;
+            e_out[i] = (uint16_t)sum;
+            sum += (L & 0x7FFFu) + (L >> 15);
+        }
+        uint32_t T;
+        const uint32_t exo = block_exscan_add(sum, sh8, T);
+        const uint32_t a = out_off & 15u;
+        for (uint32_t i = i_lo; i < i_hi; ++i) {
+            const uint32_t eo = (uint32_t)e_out[i] + exo, L = e_len[i];
+            const uint32_t outlen = (L & 0x7FFFu) + (L >> 15);
+            e_out[i] = (uint16_t)eo;
+            if (outlen) {   // words whose first byte this entry provides
+                if (eo == 0u) s_first[0] = (uint16_t)i;
+                const uint32_t w_hi = (eo + outlen - 1u + a) >> 4;
+                for (uint32_t w = (eo + a + 15u) >> 4; w <= w_hi; ++w) s_first[w] = (uint16_t)i;
+            }
+        }
+        __syncthreads();
+        // ---- 4. aligned output words ------------------------------------------------------------
+        const uint32_t W = (a + T + 15u) >> 4;
+        uint8_t *obase = region + (out_off - a);
+        for (uint32_t w = tid; w < W; w += TILE_THREADS) {
+            const uint32_t f0 = w == 0u ? a : 0u;
+            uint32_t filled = f0;
+            uint32_t pos = 16u * w + filled - a;               // output position within the batch
+            uint32_t i = s_first[w];
+            uint32_t d = pos - (uint32_t)e_out[i];
+            uint64_t alo = 0, ahi = 0;
+            while (filled < 16u && pos < T) {
+                const uint32_t L = e_len[i], len = L & 0x7FFFu, brk = L >> 15;
+                if (d < len) {
+                    const uint32_t n = min(16u - filled, len - d);
+                    const uint32_t A = 16u + (uint32_t)e_src[i] + d - filled;   // s_rawbuf offset of output byte 0
+                    const uint32_t wi = A >> 2, sel = 0x3210u + 0x1111u * (A & 3u);
+                    uint32_t x[5], v[4];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) x[j] = raw32[wi + j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = __byte_perm(x[j], x[j + 1], sel);
+                    uint64_t l0, h0, l1, h1;
+                    ones128(filled, l0, h0);
+                    ones128(filled + n, l1, h1);
+                    const uint64_t mlo = l1 & ~l0, mhi = h1 & ~h0;
+                    const uint32_t m[4] = {(uint32_t)mlo, (uint32_t)(mlo >> 32), (uint32_t)mhi, (uint32_t)(mhi >> 32)};
+                    uint32_t cw[4], diff = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t u = v[j] & 0xDFDFDFDFu;
+                        const uint32_t c2 = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+                        cw[j] = c2;
+                        uint32_t z = (c2 | (c2 >> 4)) & 0x00FF00FFu;
+                        z = (z | (z >> 8)) & 0xFFFFu;
+                        diff |= (__byte_perm(0x54474341u, 0u, z) ^ u) & m[j];
+                    }
+                    if (diff) {   // exact per-byte classes (needletail normalize(false))
+                        bool blank = false;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const uint32_t k = lut[(v[q >> 2] >> (8 * (q & 3))) & 0xFFu];
+                            const bool in = (uint32_t)q >= filled && (uint32_t)q < filled + n;
+                            blank |= in && (k == CLS_WS || k == CLS_CR);
+                            cw[q >> 2] = (cw[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | ((k < 4u ? k : (uint32_t)SYM_BREAK) << (8 * (q & 3)));
+                        }
+                        if (blank) s_flag[0] = 1u;
+                    }
+                    alo |= ((uint64_t)cw[0] | ((uint64_t)cw[1] << 32)) & mlo;
+                    ahi |= ((uint64_t)cw[2] | ((uint64_t)cw[3] << 32)) & mhi;
+                    filled += n; pos += n; d += n;
+                }
+                if (filled < 16u && d == len && brk) {
+                    if (filled < 8u) alo |= (uint64_t)SYM_BREAK << (8u * filled);
+                    else ahi |= (uint64_t)SYM_BREAK << (8u * (filled - 8u));
+                    filled++; pos++; d++;
+                }
+                if (d >= len + brk) { i += STEP; d = 0; }
+            }
+            uint8_t *o = obase + 16u * w;
+            if (f0 == 0u && filled == 16u) {
+                *reinterpret_cast<uint4 *>(o) = make_uint4((uint32_t)alo, (uint32_t)(alo >> 32), (uint32_t)ahi, (uint32_t)(ahi >> 32));
+            } else {   // first / last word of the batch
+                for (uint32_t q = f0; q < filled; ++q)
+                    o[q] = (uint8_t)((q < 8u ? (alo >> (8u * q)) : (ahi >> (8u * (q - 8u)))) & 0xFFu);
+            }
+        }
+        out_off += T;
+        if (MODE == MODE_FASTQ) state = (state + N) & 3u;
+        __syncthreads();
+        if (MODE == MODE_FASTA) state = s_flag[1];
+        if (s_flag[0]) { declined = true; break; }   // uniform: read after the barrier
+    }
+
+    if (declined) {
+        __syncthreads();
+        out_off = 0; bases_delta = 0; recs = 0; bad_pos = ~0ULL;
+        pack_exact<MODE>(raw, g, t0, t1, raw_base, cprev1, cprev2, state0, region, lut, sh8, out_off, bases_delta, recs, bad_pos);
     }
 
     // the hash kernel walks up to HASH_W positions past the region's end: make them breaks
