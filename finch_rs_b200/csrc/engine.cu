@@ -1185,8 +1185,18 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
         // bounded slabs of whole query rows so the output buffer stays small
         const uint64_t rows = std::max<uint64_t>(1, (1ull << 24) / std::max<size_t>(1, n_sk));
         rc = d_o.ensure(std::min<uint64_t>(n_pairs, rows * n_sk) * sizeof(fb2_pair_out));
+        // short query sketches (the usual n <= 1000): shared-memory tiled kernel; otherwise warp-per-pair
+        uint32_t max_qlen = 0;
+        for (size_t q = q0; q < q1; ++q) max_qlen = std::max(max_qlen, lens[q]);
+        const bool tiled = max_qlen <= dist_tile_max_len() && !getenv("FB2_DIST_NO_TILE");
         for (uint64_t q = q0; rc == FB2_OK && q < q1; q += rows) {
             const uint64_t m = std::min<uint64_t>(rows, q1 - q) * n_sk;
+            if (tiled) {
+                if (launch_dist_tile(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, (uint32_t)n_sk,
+                                     (uint32_t)q, (uint32_t)(q + m / n_sk), scale > 0.0,
+                                     scale > 0.0 ? dist_max_hash(scale) : 0, d_o.as<fb2_pair_out>(), 0) != 0)
+                    rc = fb2_fail(FB2_ECUDA, "dist_tile_kernel: could not reserve shared memory");
+            } else
             launch_dist_all(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, (uint32_t)n_sk,
                             (uint32_t)q, m, scale > 0.0, scale > 0.0 ? dist_max_hash(scale) : 0,
                             d_o.as<fb2_pair_out>(), 0);

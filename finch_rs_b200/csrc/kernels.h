@@ -56,6 +56,9 @@ void launch_export(const unsigned long long *keys, const uint32_t *slots, uint32
 void launch_dist_pairs(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, const uint32_t *q_idx,
                        const uint32_t *r_idx, uint64_t n_pairs, int scaled, unsigned long long max_hash,
                        fb2_pair_out *out, cudaStream_t s);
+uint32_t dist_tile_max_len();
+int launch_dist_tile(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
+                     uint32_t q1, int scaled, unsigned long long max_hash, fb2_pair_out *out, cudaStream_t s);
 void launch_dist_all(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk,
                      uint32_t q0, uint64_t n_pairs, int scaled, unsigned long long max_hash, fb2_pair_out *out,
                      cudaStream_t s);
