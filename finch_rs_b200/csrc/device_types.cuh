@@ -49,7 +49,7 @@ struct LaunchSlot {
     unsigned int log_count;           // entries appended to the slot's log (may exceed its capacity)
     unsigned int decision;            // absorb_decide_kernel: 0 none, 1 absorbed, 2 log overflowed, 3 table too full
     unsigned int chunk_syms;          // symbols of the chunk (copied from ParseCarry for the host)
-    unsigned int pad;
+    unsigned int next_item;           // hash_kernel: work-item counter of the launch (warps claim items dynamically)
 };
 constexpr unsigned int DECIDE_GO = 1, DECIDE_OVERFLOW = 2, DECIDE_FULL = 3;
 

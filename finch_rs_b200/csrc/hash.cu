@@ -9,6 +9,7 @@
 // canonical strand by integer compare, expands it to the ASCII bytes the reference hashes,
 // computes h1 and appends (hash, k-mer codes, position|strand) to the log when h1 <= threshold.
 // Order-independence of the sketch makes the unordered log exact.
+#include <algorithm>
 #include "common.cuh"
 #include "device_types.cuh"
 
@@ -88,46 +89,68 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t x, int n) { return __byte_p
 // Every 8-base word w of the k-mer enters murmur3 as  w * c  (c = c1 for k1-type words, c2 for
 // k2-type words), w being the 8 ASCII bytes of the bases.  Multiplication distributes over the
 // byte groups:  w * c = A4(lo) * c + (A4(hi) * c << 32)  with A4(b) the 4 ASCII bytes of the 4
-// bases b.  lut_c[b] = A4(b) * c (64 bit) turns "expand 2-bit codes to ASCII, then multiply" into
-// two shared-memory loads and one add.  For k = 21 the 5-byte tail (10 bits of codes) has its own
-// 1024-entry table, so the whole tail word is one load.
-struct MulLut { uint32_t c1, c2, t5; uint32_t stride; };   // shared-window byte addresses; stride == 8 (in a register)
+// bases b.  A 256-entry table of A4(b) * c turns "expand 2-bit codes to ASCII, then multiply" into
+// two shared-memory loads and one add.
+//
+// Random table indices from 32 lanes conflict on the 32 shared-memory banks (measured: 6.2
+// wavefronts per load with one copy of each table, which made the LSU data pipe the limiter).
+// The tables are therefore REPLICATED: entry i of copy c sits at (i * R + c), and lane l reads
+// copy l % R, so with R = 16 the 16 lanes of a 64-bit half-warp wavefront always hit 16 different
+// bank pairs (no conflicts), and the 32-bit "high group" tables see at most 32/R lanes per copy.
+constexpr int HP_R64 = 16;              // copies of the 64-bit tables (A4 * c, both words)
+constexpr int HP_R32 = 8;               // copies of the 32-bit tables (low word of A4 * c)
+struct HashConsts {                     // kernel parameters: values ptxas must not fold away
+    uint32_t stride64, stride32, stride1;   // HP_R64 * 8, HP_R32 * 4, 8 (bytes between consecutive entries)
+    uint32_t one;                           // 1: multiplier that keeps 64-bit adds on the FMA pipe
+    unsigned long long add1, add2;          // 0x52dce729, 0x38495ab5 (the +c of h * 5 + c, as IMAD.WIDE addends)
+};
+struct MulLut {                         // per-lane shared-window byte addresses (copy l % R already applied)
+    uint32_t c1_64, c2_64, c1_32, c2_32, t1;
+    uint32_t stride64, stride32, stride1, one;
+    U2 add1, add2;
+};
 
-__device__ __forceinline__ uint2 lut_load(uint32_t table, uint32_t idx, uint32_t stride) {
-    const uint32_t addr = mad_lo(idx, stride, table);
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint32_t lut_load_lo(uint32_t table, uint32_t idx, uint32_t stride) {
-    const uint32_t addr = mad_lo(idx, stride, table);
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-
-// (8 bases given as two table indices) * c
-__device__ __forceinline__ U2 mul_word8(uint32_t table, uint32_t i0, uint32_t i1, uint32_t stride) {
-    const uint2 a = lut_load(table, i0, stride);
-    const uint32_t b = lut_load_lo(table, i1, stride);
-    U2 r; r.lo = a.x; r.hi = mad_lo(b, 1u, a.y);
-    return r;
+__device__ __forceinline__ U2 add_one(U2 a, U2 b, uint32_t /*one*/) {   // a + b (ptxas: IADD3 + IMAD.X; it splits IMAD.WIDE adds anyway)
+    const uint64_t s = (((uint64_t)a.hi << 32) | a.lo) + (((uint64_t)b.hi << 32) | b.lo);
+    U2 t; t.lo = (uint32_t)s; t.hi = (uint32_t)(s >> 32);
+    return t;
 }
-// NBYTES (1..7) bases in g16 (base 0 lowest, the rest zero bytes) times C
-template <int NBYTES, bool IS_C1>
-__device__ __forceinline__ U2 mul_word_part(uint32_t g16, const MulLut &L) {
-    const uint32_t T = IS_C1 ? L.c1 : L.c2;
+__device__ __forceinline__ U2 mul5add_r(U2 x, U2 c) {                     // x * 5 + c
+    const uint64_t s = (((uint64_t)x.hi << 32) | x.lo) * 5ULL + (((uint64_t)c.hi << 32) | c.lo);
+    U2 t; t.lo = (uint32_t)s; t.hi = (uint32_t)(s >> 32);
+    return t;
+}
+
+// (NB bases, 1..8, of the 32-bit codes word cw starting at byte BYTE0) * c.  Bits of cw above the
+// k-mer are zero (the rolling state is masked).
+template <bool IS_C1, int BYTE0, int NB>
+__device__ __forceinline__ U2 word_mul(uint32_t cw, const MulLut &L) {
+    static_assert(NB >= 1 && NB <= 8 && (BYTE0 == 0 || BYTE0 == 2), "bad word");
+    const uint32_t T64 = IS_C1 ? L.c1_64 : L.c2_64, T32 = IS_C1 ? L.c1_32 : L.c2_32;
     const uint64_t C = IS_C1 ? MM_C1 : MM_C2;
     U2 r;
-    if (NBYTES > 4) {
-        const uint2 a = lut_load(T, g16 & 0xFFu, L.stride);
-        const uint32_t hi4 = expand4(g16 >> 8) & (uint32_t)low_bytes_mask(NBYTES - 4);
-        r.lo = a.x; r.hi = mad_lo(hi4, (uint32_t)C, a.y);
-    } else if (NBYTES == 4) {
-        const uint2 a = lut_load(T, g16 & 0xFFu, L.stride);
+    if (NB >= 4) {
+        const uint2 a = lds64(mad_lo(byte_of(cw, BYTE0), L.stride64, T64));
         r.lo = a.x; r.hi = a.y;
+        if (NB == 8) {
+            r.hi = mad_lo(lds32(mad_lo(byte_of(cw, BYTE0 + 1), L.stride32, T32)), L.one, r.hi);
+        } else if (NB > 4) {
+            // the remaining 1..3 bases are the top of the (masked) word: a plain shift isolates them
+            const uint32_t rem = BYTE0 == 0 ? byte_of(cw, 1) : (cw >> 24);
+            r.hi = mad_lo(expand4(rem) & (uint32_t)low_bytes_mask(NB - 4), (uint32_t)C, r.hi);
+        }
     } else {
-        const uint32_t lo4 = expand4(g16 & 0xFFu) & (uint32_t)low_bytes_mask(NBYTES);
+        const uint32_t lo4 = expand4(byte_of(cw, BYTE0)) & (uint32_t)low_bytes_mask(NB);
         r = mul_wide(lo4, (uint32_t)C);
         r.hi = mad_lo(lo4, (uint32_t)(C >> 32), r.hi);
     }
@@ -140,44 +163,41 @@ __device__ __forceinline__ U2 murmur_kmer_h1_lut(U2 codes, U2 seed, const MulLut
     constexpr int NB = K / 16, T = K & 15;
     U2 h1 = seed, h2 = seed;
     if (NB >= 1) {
-        U2 k1 = mul_word8(L.c1, byte_of(codes.lo, 0), byte_of(codes.lo, 1), L.stride);
-        U2 k2 = mul_word8(L.c2, byte_of(codes.lo, 2), byte_of(codes.lo, 3), L.stride);
+        U2 k1 = word_mul<true, 0, 8>(codes.lo, L);
+        U2 k2 = word_mul<false, 2, 8>(codes.lo, L);
         k1 = rotl_u2<31>(k1); k1 = mul_u2<MM_C2>(k1);
         if (SEED0) { h1 = k1; } else { h1.lo ^= k1.lo; h1.hi ^= k1.hi; }
-        h1 = rotl_u2<27>(h1); if (!SEED0) h1 = add_u2(h1, h2); h1 = mul5add_u2<0x52dce729u>(h1);
+        h1 = rotl_u2<27>(h1); if (!SEED0) h1 = add_one(h1, h2, L.one); h1 = mul5add_r(h1, L.add1);
         k2 = rotl_u2<33>(k2); k2 = mul_u2<MM_C1>(k2);
         if (SEED0) { h2 = k2; } else { h2.lo ^= k2.lo; h2.hi ^= k2.hi; }
-        h2 = rotl_u2<31>(h2); h2 = add_u2(h2, h1); h2 = mul5add_u2<0x38495ab5u>(h2);
+        h2 = rotl_u2<31>(h2); h2 = add_one(h2, h1, L.one); h2 = mul5add_r(h2, L.add2);
     }
     if (NB >= 2) {
-        U2 k1 = mul_word8(L.c1, byte_of(codes.hi, 0), byte_of(codes.hi, 1), L.stride);
-        U2 k2 = mul_word8(L.c2, byte_of(codes.hi, 2), byte_of(codes.hi, 3), L.stride);
+        U2 k1 = word_mul<true, 0, 8>(codes.hi, L);
+        U2 k2 = word_mul<false, 2, 8>(codes.hi, L);
         k1 = rotl_u2<31>(k1); k1 = mul_u2<MM_C2>(k1); h1.lo ^= k1.lo; h1.hi ^= k1.hi;
-        h1 = rotl_u2<27>(h1); h1 = add_u2(h1, h2); h1 = mul5add_u2<0x52dce729u>(h1);
+        h1 = rotl_u2<27>(h1); h1 = add_one(h1, h2, L.one); h1 = mul5add_r(h1, L.add1);
         k2 = rotl_u2<33>(k2); k2 = mul_u2<MM_C1>(k2); h2.lo ^= k2.lo; h2.hi ^= k2.hi;
-        h2 = rotl_u2<31>(h2); h2 = add_u2(h2, h1); h2 = mul5add_u2<0x38495ab5u>(h2);
+        h2 = rotl_u2<31>(h2); h2 = add_one(h2, h1, L.one); h2 = mul5add_r(h2, L.add2);
     }
-    // tail words: 16-bit groups TW (k1-type) and TW + 1 (k2-type) of the codes
-    const uint32_t tword = (NB == 0) ? codes.lo : codes.hi;     // NB == 2 has no tail
+    // tail: 16-bit groups (k1-type first, then k2-type) of the next codes word; NB == 2 has none
+    const uint32_t tword = (NB == 0) ? codes.lo : codes.hi;
     if (T > 8) {
-        U2 k2;
-        if (T == 16) k2 = mul_word8(L.c2, byte_of(tword, 2), byte_of(tword, 3), L.stride);
-        else k2 = mul_word_part<(T > 8 ? T - 8 : 1), false>(tword >> 16, L);
+        U2 k2 = word_mul<false, 2, (T > 8 ? T - 8 : 1)>(tword, L);
         k2 = rotl_u2<33>(k2); k2 = mul_u2<MM_C1>(k2); h2.lo ^= k2.lo; h2.hi ^= k2.hi;
     }
     if (T > 0) {
         U2 k1;
-        if (T >= 8) k1 = mul_word8(L.c1, byte_of(tword, 0), byte_of(tword, 1), L.stride);
-        else if (K == 21) {                    // 5 bases = the whole (masked) high word of the codes
-            const uint2 a = lut_load(L.t5, tword, L.stride);
+        if (K == 21) {                       // 5 bases = the whole (masked) high word of the codes: one load
+            const uint2 a = lds64(mad_lo(tword, L.stride1, L.t1));
             k1.lo = a.x; k1.hi = a.y;
-        } else k1 = mul_word_part<(T > 0 && T < 8 ? T : 1), true>(tword & 0xFFFFu, L);
+        } else k1 = word_mul<true, 0, (T >= 8 ? 8 : (T > 0 ? T : 1))>(tword, L);
         k1 = rotl_u2<31>(k1); k1 = mul_u2<MM_C2>(k1); h1.lo ^= k1.lo; h1.hi ^= k1.hi;
     }
     h1.lo ^= (uint32_t)K; h2.lo ^= (uint32_t)K;
-    h1 = add_u2(h1, h2); h2 = add_u2(h2, h1);
+    h1 = add_one(h1, h2, L.one); h2 = add_one(h2, h1, L.one);
     h1 = fmix_u2(h1); h2 = fmix_u2(h2);
-    return add_u2(h1, h2);
+    return add_one(h1, h2, L.one);
 }
 
 constexpr uint32_t LOG_RESERVE = 3;   // extra log slots a warp reserves per atomic (<= 31)
@@ -245,141 +265,210 @@ struct Roll2 {
     }
 };
 
+// ---- the persistent kernel ---------------------------------------------------------------------------
+// One CTA of HP_WARPS warps per SM builds the replicated tables once, then every warp streams
+// through work items on its own: an item is HP_SLICE = 32 lanes x HASH_W consecutive positions of
+// one symbol region, staged (with a 32-symbol halo in front) into the warp's own shared-memory
+// buffer by one 1-D TMA bulk copy signalled on the warp's own mbarrier.  With two buffers per warp
+// the copy of the next item is in flight while the current one is hashed; there is no block-wide
+// synchronisation after the table build.
+constexpr int HP_WARPS = 32;
+constexpr int HP_NBUF = 2;
+constexpr uint32_t HP_SLICE = 32u * HASH_W;                  // positions per item
+constexpr uint32_t HP_BUF = 32u + HP_SLICE;                  // bytes per warp buffer (multiple of 16)
+constexpr uint32_t HP_ITEMS_PER_TILE = HASH_TILE / HP_SLICE; // launch ranges are given in HASH_TILE blocks
+constexpr uint32_t HP_OFF_C1_64 = 0;
+constexpr uint32_t HP_OFF_C2_64 = HP_OFF_C1_64 + 256u * HP_R64 * 8u;
+constexpr uint32_t HP_OFF_C1_32 = HP_OFF_C2_64 + 256u * HP_R64 * 8u;
+constexpr uint32_t HP_OFF_C2_32 = HP_OFF_C1_32 + 256u * HP_R32 * 4u;
+constexpr uint32_t HP_OFF_T1 = HP_OFF_C2_32 + 256u * HP_R32 * 4u;
+constexpr uint32_t HP_OFF_BAR = HP_OFF_T1 + 1024u * 8u;   // T1: (5 ASCII bytes) * c1 for k = 21, one copy
+constexpr uint32_t HP_OFF_BUF = (HP_OFF_BAR + HP_WARPS * HP_NBUF * 8u + 127u) & ~127u;
+constexpr uint32_t HP_SMEM = HP_OFF_BUF + HP_WARPS * HP_NBUF * HP_BUF;
+static_assert(HP_SMEM <= 232448u, "hash kernel shared memory exceeds 227 KB");
+static_assert(HP_BUF % 16u == 0, "TMA size granularity");
+
 template <int K, bool SEED0>
-__global__ void __launch_bounds__(HASH_THREADS)
+__global__ void __launch_bounds__(HP_WARPS * 32, 1)
 hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r starts at SYM_FRONT + r * region_stride
-            ChunkGeom g, uint32_t b0,             // first hash block (region-major) of this launch
+            ChunkGeom g, uint32_t w0, uint32_t w1, // item range [w0, w1) of this launch (region-major)
             const uint32_t *__restrict__ region_count, uint64_t ord_base, const SketchState *st,
-            LaunchSlot *slot, LogView log, int k_rt, uint64_t seed, uint32_t lut_stride /* == 8 */) {
-    __shared__ uint2 lut_c1[256], lut_c2[256];
-    __shared__ uint2 lut_t5[K == 21 ? 1024 : 1];
+            LaunchSlot *slot, LogView log, int k_rt, uint64_t seed, HashConsts hc) {
+    extern __shared__ __align__(128) uint8_t hp_smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // ---- tables (once per CTA) and the warps' mbarriers ----
     if (K > 0) {
-        if (threadIdx.x < 256) {
-            const uint32_t a4 = expand4(threadIdx.x & 0xFFu);
+        uint2 *c1_64 = reinterpret_cast<uint2 *>(hp_smem + HP_OFF_C1_64), *c2_64 = reinterpret_cast<uint2 *>(hp_smem + HP_OFF_C2_64);
+        uint32_t *c1_32 = reinterpret_cast<uint32_t *>(hp_smem + HP_OFF_C1_32), *c2_32 = reinterpret_cast<uint32_t *>(hp_smem + HP_OFF_C2_32);
+        uint2 *t1 = reinterpret_cast<uint2 *>(hp_smem + HP_OFF_T1);
+        for (uint32_t i = tid; i < 256u * HP_R64; i += blockDim.x) {
+            const uint32_t a4 = expand4(i / HP_R64);
             const uint64_t p1 = (uint64_t)a4 * MM_C1, p2 = (uint64_t)a4 * MM_C2;
-            lut_c1[threadIdx.x] = make_uint2((uint32_t)p1, (uint32_t)(p1 >> 32));
-            lut_c2[threadIdx.x] = make_uint2((uint32_t)p2, (uint32_t)(p2 >> 32));
+            c1_64[i] = make_uint2((uint32_t)p1, (uint32_t)(p1 >> 32));
+            c2_64[i] = make_uint2((uint32_t)p2, (uint32_t)(p2 >> 32));
         }
-        if (K == 21) {
-            for (uint32_t i = threadIdx.x; i < 1024u; i += HASH_THREADS) {
-                const uint64_t w = (uint64_t)expand4(i & 0xFFu) | ((uint64_t)(expand4(i >> 8) & 0xFFu) << 32);
-                const uint64_t p = w * MM_C1;
-                lut_t5[i] = make_uint2((uint32_t)p, (uint32_t)(p >> 32));
-            }
+        for (uint32_t i = tid; i < 256u * HP_R32; i += blockDim.x) {
+            const uint32_t a4 = expand4(i / HP_R32);
+            c1_32[i] = a4 * (uint32_t)MM_C1;
+            c2_32[i] = a4 * (uint32_t)MM_C2;
         }
-        __syncthreads();
+        if (K == 21 && tid < 1024u) {        // 5-base tail word of k = 21
+            const uint64_t w = (uint64_t)expand4(tid & 0xFFu) | ((uint64_t)(expand4(tid >> 8) & 0xFFu) << 32);
+            const uint64_t p = w * MM_C1;
+            t1[tid] = make_uint2((uint32_t)p, (uint32_t)(p >> 32));
+        }
     }
-    MulLut L; L.c1 = smem_u32(lut_c1); L.c2 = smem_u32(lut_c2); L.t5 = smem_u32(lut_t5); L.stride = lut_stride;
-    __shared__ __align__(128) uint8_t tile[32 + HASH_TILE];   // 32 symbols of halo, then the block's positions
-    __shared__ __align__(8) uint64_t tile_bar;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(hp_smem + HP_OFF_BAR) + warp * HP_NBUF;
+    uint8_t *bufs = hp_smem + HP_OFF_BUF + warp * (HP_NBUF * HP_BUF);
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < HP_NBUF; ++n) mbar_init(&bars[n], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    MulLut L;
+    L.c1_64 = smem_u32(hp_smem + HP_OFF_C1_64) + (lane % HP_R64) * 8u;
+    L.c2_64 = smem_u32(hp_smem + HP_OFF_C2_64) + (lane % HP_R64) * 8u;
+    L.c1_32 = smem_u32(hp_smem + HP_OFF_C1_32) + (lane % HP_R32) * 4u;
+    L.c2_32 = smem_u32(hp_smem + HP_OFF_C2_32) + (lane % HP_R32) * 4u;
+    L.t1 = smem_u32(hp_smem + HP_OFF_T1);
+    L.stride64 = hc.stride64; L.stride32 = hc.stride32; L.stride1 = hc.stride1; L.one = hc.one;
+    L.add1.lo = 0x52dce729u; L.add1.hi = 0u; L.add2.lo = 0x38495ab5u; L.add2.hi = 0u;
+
     const int k = K > 0 ? K : k_rt;
     const uint64_t mask = kmer_mask(k);
-    const uint32_t blk = b0 + blockIdx.x;
-    const uint32_t region = blk / g.hash_tiles, lt = blk - region * g.hash_tiles;
-    const uint32_t end = region_count[region];
-    const uint32_t pb = lt * HASH_TILE;          // first position of this block in its region
-    if (pb >= end) return;                        // block-uniform: nothing to do
-    const uint8_t *sym = symbuf + (size_t)SYM_FRONT + (size_t)region * g.region_stride;
-    const uint64_t ord_region = ord_base + (uint64_t)region * g.st_bytes;
     const unsigned long long T = st->threshold;
     const uint32_t T_hi = (uint32_t)(T >> 32);
-    const uint32_t lane = threadIdx.x & 31u;
     U2 seed2; seed2.lo = (uint32_t)seed; seed2.hi = (uint32_t)(seed >> 32);
-    // ---- stage [pb - 32, min(end + HASH_W, pb + HASH_TILE)) with one TMA bulk copy --------------
-    // (positions in [end, end + HASH_W) hold SYM_BREAK, written by pack_kernel)
-    {
-        const uint32_t npos = min(end + (uint32_t)HASH_W - pb, (uint32_t)HASH_TILE);
-        const uint32_t bytes = (32u + npos + 15u) & ~15u;
-        if (threadIdx.x == 0) { mbar_init(&tile_bar, 1); fence_mbar_init(); }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(&tile_bar, bytes);
-            tma_load_1d(tile, sym + pb - 32, bytes, &tile_bar);
-        }
-        mbar_wait(&tile_bar, 0);
-    }
-    const uint32_t t0 = threadIdx.x * (uint32_t)HASH_W;   // this thread's first position within the tile
-    const uint32_t p0 = pb + t0;
-    // Warp-uniform early exit: a warp's positions are contiguous and ascending.
-    if (__all_sync(0xffffffffu, p0 >= end)) return;
-    // lanes past the end of the region (in a warp that is not entirely past it) never read: they
-    // walk SYM_BREAK words.  Live lanes stay inside [p0 - 32, p0 + HASH_W), which was staged.
-    const bool live = p0 < end;
 
-    Roll2<K> r; r.A.lo = r.A.hi = r.B.lo = r.B.hi = 0;
-    // brk = position (relative to the current group of 4) of the last non-base symbol; the window
-    // ending at relative position b is valid  <=>  brk <= b - k.
-    int brk = -k;
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + 32 + t0);
-    // ---- warm-up on the 32 symbols before p0 (only the last k-1 matter) -------------------
-    if (live) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(tile + t0);
-        const uint4 b = *reinterpret_cast<const uint4 *>(tile + t0 + 16);
-        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (K > 0 && i < 32 - (K - 1)) continue;  // compile-time skip
-            const uint32_t s = w[i >> 2] >> (8 * (i & 3));
-            if (K == 0 && i < 32 - (k - 1)) continue;
-            r.push(s, k, mask);
-            if ((s & 0xFFu) >= 4u) brk = i - 32;
+    // item -> (region, first position, symbols in the region); skips items past the end of their region
+    uint32_t it_region = 0, it_pb = 0, it_end = 0;
+    // Items are claimed from a per-launch counter: regions are rarely full (FASTQ: ~48 % symbols), so a
+    // static round-robin would hand some warps only the empty tail items of every region.
+    auto next_live = [&]() -> uint32_t {
+        while (true) {
+            uint32_t it = 0;
+            if (lane == 0) it = w0 + atomicAdd(&slot->next_item, 1u);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= w1) return w1;
+            const uint32_t blk = it / HP_ITEMS_PER_TILE, slice = it - blk * HP_ITEMS_PER_TILE;
+            const uint32_t region = blk / g.hash_tiles, lt = blk - region * g.hash_tiles;
+            const uint32_t pb = lt * HASH_TILE + slice * HP_SLICE, end = region_count[region];
+            if (pb < end) { it_region = region; it_pb = pb; it_end = end; return it; }
         }
-    } else {
-        brk = -1;
-    }
+    };
+    // stage [pb - 32, min(end + HASH_W, pb + HP_SLICE)) of the region into buffer n
+    // (positions in [end, end + HASH_W) hold SYM_BREAK, written by pack_kernel)
+    auto issue = [&](int n) {
+        if (lane == 0) {
+            const uint32_t npos = min(it_end + (uint32_t)HASH_W - it_pb, HP_SLICE);
+            const uint32_t bytes = (32u + npos + 15u) & ~15u;
+            const uint8_t *src = symbuf + (size_t)SYM_FRONT + (size_t)it_region * g.region_stride + it_pb - 32;
+            mbar_arrive_expect_tx(&bars[n], bytes);
+            tma_load_1d(bufs + n * HP_BUF, src, bytes, &bars[n]);
+        }
+    };
+
     uint32_t nvalid = 0;
     uint32_t res_base = 0, res_left = 0;   // warp-uniform: this warp's reserved slice of the log
-    uint32_t word = live ? wp[0] : 0x04040404u;
-#pragma unroll 1
-    for (int j = 0; j < HASH_W / 4; ++j) {
-        const uint32_t cur = word;
-        if (j + 1 < HASH_W / 4) word = live ? wp[j + 1] : 0x04040404u;  // next 4 symbols
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            r.push(cur >> (8 * b), k, mask);
-            if (cur & (0xFCu << (8 * b))) brk = b;
-            const bool ok = brk <= b - k;
-            const bool is_rc = (((uint64_t)r.A.hi << 32) | r.A.lo) >= (((uint64_t)r.B.hi << 32) | r.B.lo);
-            U2 codes; codes.lo = is_rc ? r.B.lo : r.A.lo; codes.hi = is_rc ? r.B.hi : r.A.hi;
-            U2 h;
-            if (K > 0) h = murmur_kmer_h1_lut<(K > 0 ? K : 1), SEED0>(codes, seed2, L);
-            else {
-                const uint64_t hv = murmur_kmer_h1<0>(((uint64_t)codes.hi << 32) | codes.lo, k, seed);
-                h.lo = (uint32_t)hv; h.hi = (uint32_t)(hv >> 32);
-            }
-            nvalid += ok ? 1u : 0u;
-            // hot path: compare only the high words (conservative); the exact test is in the branch
-            const bool maybe = ok && (h.hi <= T_hi);
-            if (__any_sync(0xffffffffu, maybe)) {
-              const unsigned long long hv = ((unsigned long long)h.hi << 32) | h.lo;
-              const bool emit = maybe && (hv <= T);
-              const uint32_t em = __ballot_sync(0xffffffffu, emit);
-              if (em) {
-                // Warp-private bump reservation in the log: the global atomic (and the wait for its
-                // result) happens once per LOG_RESERVE candidates, not once per candidate.
-                const uint32_t n = __popc(em);
-                if (n > res_left) {                                   // warp-uniform
-                    if (lane < res_left && res_base + lane < log.cap) log.posx[res_base + lane] = ~0ULL;  // unused slots
-                    const uint32_t want = n + LOG_RESERVE;
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&slot->log_count, want);
-                    res_base = __shfl_sync(0xffffffffu, base, 0);
-                    res_left = want;
-                }
-                if (emit) {
-                    const uint32_t idx = res_base + __popc(em & lanemask_lt());
-                    if (idx < log.cap) {
-                        const uint32_t p = p0 + 4u * (uint32_t)j + (uint32_t)b;
-                        log.hash[idx] = hv;
-                        log.kmer[idx] = ((unsigned long long)codes.hi << 32) | codes.lo;
-                        log.posx[idx] = ((ord_region + p) << 9) | (is_rc ? 1ull : 0ull);
-                    }
-                }
-                res_base += n; res_left -= n;
-              }
-            }
+    uint32_t phases = 0;                   // bit n: parity to wait for on buffer n
+    int cb = 0;
+    uint32_t cur = next_live();
+    if (cur < w1) issue(0);
+    while (cur < w1) {
+        const uint32_t region = it_region, pb = it_pb, end = it_end;
+        uint32_t nxt = w1;
+        if (HP_NBUF > 1) {                 // prefetch the next live item into the other buffer
+            nxt = next_live();
+            if (nxt < w1) issue(cb ^ 1);
         }
-        brk -= 4;
+        mbar_wait(&bars[cb], (phases >> cb) & 1u);
+        phases ^= 1u << cb;
+        const uint8_t *tile = bufs + cb * HP_BUF;
+        const uint64_t ord_region = ord_base + (uint64_t)region * g.st_bytes;
+        const uint32_t t0 = lane * (uint32_t)HASH_W;          // this thread's first position within the item
+        const uint32_t p0 = pb + t0;
+        // lanes past the end of the region never read: they walk SYM_BREAK words.  Live lanes stay
+        // inside [p0 - 32, p0 + HASH_W), which was staged.
+        const bool live = p0 < end;
+
+        Roll2<K> r; r.A.lo = r.A.hi = r.B.lo = r.B.hi = 0;
+        // brk = position (relative to the current group of 4) of the last non-base symbol; the window
+        // ending at relative position b is valid  <=>  brk <= b - k.
+        int brk = -k;
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + 32 + t0);
+        // ---- warm-up on the 32 symbols before p0 (only the last k-1 matter) -------------------
+        if (live) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(tile + t0);
+            const uint4 b = *reinterpret_cast<const uint4 *>(tile + t0 + 16);
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (K > 0 && i < 32 - (K - 1)) continue;  // compile-time skip
+                const uint32_t s = w[i >> 2] >> (8 * (i & 3));
+                if (K == 0 && i < 32 - (k - 1)) continue;
+                r.push(s, k, mask);
+                if ((s & 0xFFu) >= 4u) brk = i - 32;
+            }
+        } else {
+            brk = -1;
+        }
+        uint32_t word = live ? wp[0] : 0x04040404u;
+#pragma unroll 1
+        for (int j = 0; j < HASH_W / 4; ++j) {
+            const uint32_t cw = word;
+            if (j + 1 < HASH_W / 4) word = live ? wp[j + 1] : 0x04040404u;  // next 4 symbols
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                r.push(cw >> (8 * b), k, mask);
+                if (cw & (0xFCu << (8 * b))) brk = b;
+                const bool ok = brk <= b - k;
+                const bool is_rc = (((uint64_t)r.A.hi << 32) | r.A.lo) >= (((uint64_t)r.B.hi << 32) | r.B.lo);
+                U2 codes; codes.lo = is_rc ? r.B.lo : r.A.lo; codes.hi = is_rc ? r.B.hi : r.A.hi;
+                U2 h;
+                if (K > 0) h = murmur_kmer_h1_lut<(K > 0 ? K : 1), SEED0>(codes, seed2, L);
+                else {
+                    const uint64_t hv = murmur_kmer_h1<0>(((uint64_t)codes.hi << 32) | codes.lo, k, seed);
+                    h.lo = (uint32_t)hv; h.hi = (uint32_t)(hv >> 32);
+                }
+                nvalid += ok ? 1u : 0u;
+                // hot path: compare only the high words (conservative); the exact test is in the branch
+                const bool maybe = ok && (h.hi <= T_hi);
+                if (__any_sync(0xffffffffu, maybe)) {
+                  const unsigned long long hv = ((unsigned long long)h.hi << 32) | h.lo;
+                  const bool emit = maybe && (hv <= T);
+                  const uint32_t em = __ballot_sync(0xffffffffu, emit);
+                  if (em) {
+                    // Warp-private bump reservation in the log: the global atomic (and the wait for its
+                    // result) happens once per LOG_RESERVE candidates, not once per candidate.
+                    const uint32_t n = __popc(em);
+                    if (n > res_left) {                                   // warp-uniform
+                        if (lane < res_left && res_base + lane < log.cap) log.posx[res_base + lane] = ~0ULL;  // unused slots
+                        const uint32_t want = n + LOG_RESERVE;
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&slot->log_count, want);
+                        res_base = __shfl_sync(0xffffffffu, base, 0);
+                        res_left = want;
+                    }
+                    if (emit) {
+                        const uint32_t idx = res_base + __popc(em & lanemask_lt());
+                        if (idx < log.cap) {
+                            const uint32_t p = p0 + 4u * (uint32_t)j + (uint32_t)b;
+                            log.hash[idx] = hv;
+                            log.kmer[idx] = ((unsigned long long)codes.hi << 32) | codes.lo;
+                            log.posx[idx] = ((ord_region + p) << 9) | (is_rc ? 1ull : 0ull);
+                        }
+                    }
+                    res_base += n; res_left -= n;
+                  }
+                }
+            }
+            brk -= 4;
+        }
+        __syncwarp();                      // every lane is done with this buffer before it is refilled
+        if (HP_NBUF > 1) { cur = nxt; cb ^= 1; }
+        else { cur = next_live(); if (cur < w1) issue(0); }
     }
     if (lane < res_left && res_base + lane < log.cap) log.posx[res_base + lane] = ~0ULL;  // unused tail of the reservation
     // valid-window count of this launch (committed to total_kmers by the host on success)
@@ -407,23 +496,44 @@ __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32
 }
 __global__ void push_commit_kernel(LaunchSlot *slot, uint32_t n) { slot->launch_kmers += n; }
 
+template <int K, bool SEED0>
+static void launch_hash_ks(uint32_t w0, uint32_t w1, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
+                           uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, int k, uint64_t seed,
+                           cudaStream_t stream) {
+    static int sms[64] = {};   // per device: SM count, set once the shared-memory attribute is in place
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) {
+        cudaFuncSetAttribute(hash_kernel<K, SEED0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HP_SMEM);
+        int n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    HashConsts hc;
+    hc.stride64 = HP_R64 * 8u; hc.stride32 = HP_R32 * 4u; hc.stride1 = 8u; hc.one = 1u;
+    hc.add1 = 0x52dce729ULL; hc.add2 = 0x38495ab5ULL;
+    const uint32_t items = w1 - w0;
+    const uint32_t ctas = std::min<uint32_t>((uint32_t)sms[dev], (items + HP_WARPS - 1) / HP_WARPS);
+    hash_kernel<K, SEED0><<<ctas, HP_WARPS * 32, HP_SMEM, stream>>>(symbuf, g, w0, w1, region_count, ord_base, st, slot, log,
+                                                                   k, seed, hc);
+}
 template <int K>
-static void launch_hash_k(uint32_t blocks, const uint8_t *symbuf, ChunkGeom g, uint32_t b0, const uint32_t *region_count,
+static void launch_hash_k(uint32_t w0, uint32_t w1, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
                           uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, int k, uint64_t seed,
                           cudaStream_t stream) {
-    if (seed == 0 && K > 0)
-        hash_kernel<K, true><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, slot, log, k, seed, 8u);
-    else
-        hash_kernel<K, false><<<blocks, HASH_THREADS, 0, stream>>>(symbuf, g, b0, region_count, ord_base, st, slot, log, k, seed, 8u);
+    if (seed == 0 && K > 0) launch_hash_ks<K, true>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
+    else launch_hash_ks<K, false>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
 }
+// Hash the HASH_TILE-sized blocks [b0, b1) (region-major) of a chunk's symbol regions.
 void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t b0, uint32_t b1, const uint32_t *region_count,
                  uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, uint64_t seed,
                  cudaStream_t stream) {
     if (b1 <= b0) return;
-    const uint32_t blocks = b1 - b0;
-    if (k == 21) launch_hash_k<21>(blocks, symbuf, g, b0, region_count, ord_base, st, slot, log, k, seed, stream);
-    else if (k == 31) launch_hash_k<31>(blocks, symbuf, g, b0, region_count, ord_base, st, slot, log, k, seed, stream);
-    else launch_hash_k<0>(blocks, symbuf, g, b0, region_count, ord_base, st, slot, log, k, seed, stream);
+    const uint32_t w0 = b0 * HP_ITEMS_PER_TILE, w1 = b1 * HP_ITEMS_PER_TILE;
+    if (k == 21) launch_hash_k<21>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
+    else if (k == 31) launch_hash_k<31>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
+    else launch_hash_k<0>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
 }
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
                       uint64_t arena_base, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
