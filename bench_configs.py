@@ -103,6 +103,35 @@ def main():
     print(json.dumps(rows[-1]), flush=True)
     sk_h.close()
 
+    # ---- C3 through sketch_files (lib.rs:29-49): files on tmpfs, worker handles overlap on the GPU ----
+    import shutil
+    import tempfile
+    tdir = tempfile.mkdtemp(prefix="fb2c3_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        nrep = 1 if args.quick else 4                  # 128 files = one GPU's share of the 1024-file batch
+        paths = []
+        for rep in range(nrep):
+            for i, f in enumerate(files):
+                pth = os.path.join(tdir, f"g{rep}_{i}.fa")
+                f.tofile(pth)
+                paths.append(pth)
+        for workers in (1, 8, 16):
+            os.environ["FB2_FILE_WORKERS"] = str(workers)
+            fb.sketch_files(paths[:nfiles], sp, fp)    # warm-up (handles, page cache)
+            t0 = time.perf_counter()
+            sks_f = fb.sketch_files(paths, sp, fp)
+            dtf = time.perf_counter() - t0
+            okf = all(np.array_equal(sks_f[j].hashes_u64, sks[j % nfiles].hashes_u64) and
+                      np.array_equal(sks_f[j].counts, sks[j % nfiles].counts) for j in range(len(paths)))
+            rows.append({"config": f"C3 sketch_files({len(paths)} x ~5 Mbp FASTA on tmpfs), {workers} worker handle(s), 1 GPU",
+                         "gpu_e2e_ms": dtf * 1e3, "ms_per_file": dtf * 1e3 / len(paths),
+                         "gbases_per_s_e2e": total_bases * nrep / dtf / 1e9, "bit_exact": bool(okf),
+                         "bit_exact_on": "every file vs the single-handle result (itself checked against the oracle)"})
+            print(json.dumps(rows[-1]), flush=True)
+        os.environ.pop("FB2_FILE_WORKERS", None)
+    finally:
+        shutil.rmtree(tdir, ignore_errors=True)
+
     # ---- C4: 3 Gbp FASTA (24 records, 60-col, 2% lowercase, 1% N), k=31, scaled 0.001, n=1000 ----------
     nb = 300_000_000 if args.quick else 3_000_000_000
     big = fb.synth_fasta(nb, n_records=24, line_width=60, lower_frac=0.02, n_frac=0.01, seed=4)
@@ -151,12 +180,13 @@ def main():
         mat[i] = np.sort(np.concatenate([rng.choice(b, size=share, replace=False), own]))[:1000]
     lens = np.full(n_sk, 1000, np.uint32)
     q1 = n_sk
-    t0 = time.perf_counter()
-    out = fb.dist_all_pairs(mat, lens, 0.0, 0, q1)
-    dt = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    out = fb.dist_all_pairs(mat, lens, 0.0, 0, q1)
-    dt = min(dt, time.perf_counter() - t0)
+    obuf = np.zeros((q1 * n_sk, 3), np.uint32)     # result array allocated (and its pages touched) once
+    dt, kms = 1e30, 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = fb.dist_all_pairs(mat, lens, 0.0, 0, q1, out=obuf)
+        dt = min(dt, time.perf_counter() - t0)
+        kms = min(kms, fb.lib().fb2_dist_last_kernel_ms())
     npairs = q1 * n_sk
     # CPU port on a bounded sample of pairs
     nq = 4
@@ -170,7 +200,8 @@ def main():
     odt = time.perf_counter() - t0
     cpu_pairs = nq * (n_sk // 4)
     rows.append({"config": f"C5 dist all-vs-all {n_sk} x {n_sk} sketches of 1000 hashes (API call incl. H2D/D2H)",
-                 "pairs": npairs, "gpu_s": dt, "pairs_per_s": npairs / dt, "cpu_port_pairs_per_s": cpu_pairs / odt,
+                 "pairs": npairs, "gpu_s": dt, "pairs_per_s": npairs / dt, "kernel_span_ms": kms,
+                 "kernel_pairs_per_s": npairs / (kms * 1e-3), "cpu_port_pairs_per_s": cpu_pairs / odt,
                  "cpu_threads": 1, "bit_exact": ok, "bit_exact_on": f"{cpu_pairs} sampled pairs"})
     print(json.dumps(rows[-1]), flush=True)
     if args.out:

@@ -73,8 +73,8 @@ EXPORTS = [
     "fb2_sketcher_push", "fb2_sketcher_feed_fastx", "fb2_sketcher_feed_device", "fb2_sketcher_format",
     "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats",
     "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_filter_counts", "fb2_process_post_filter",
-    "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_dist_batch",
-    "fb2_dist_all_pairs", "fb2_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
+    "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_release_pool", "fb2_dist_batch",
+    "fb2_dist_all_pairs", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
     "fb2_synth_genome", "fb2_synth_fasta", "fb2_synth_fastq",
 ]
 
@@ -119,6 +119,8 @@ def lib():
     L.fb2_distance_finish.argtypes = [C.POINTER(_PairOut), C.c_uint8, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.fb2_distance_finish.restype = None
+    L.fb2_dist_last_kernel_ms.argtypes = []
+    L.fb2_dist_last_kernel_ms.restype = C.c_double
     L.fb2_last_error.restype = C.c_char_p
     L.fb2_version.restype = C.c_char_p
     L.fb2_synth_genome.argtypes = [vp, sz, C.c_uint64]
@@ -280,7 +282,11 @@ class _Sketcher:
             lib().fb2_sketcher_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def __enter__(self):
         return self
@@ -490,12 +496,17 @@ def dist_batch(sketch_hashes, q_idx, r_idx, scale=0.0, device=-1):
     return out
 
 
-def dist_all_pairs(mat, lens, scale=0.0, q0=0, q1=None, device=-1):
+def dist_all_pairs(mat, lens, scale=0.0, q0=0, q1=None, device=-1, out=None):
+    """All ordered pairs (q, r), q in [q0, q1): -> uint32 array [q1-q0, n, 3] of (common, i, j).
+    `out`: optional preallocated C-contiguous uint32 array of that size (reused across calls)."""
     mat = np.ascontiguousarray(mat, np.uint64)
     lens = np.ascontiguousarray(lens, np.uint32)
     n, stride = mat.shape
     q1 = n if q1 is None else q1
-    out = np.zeros(((q1 - q0) * n, 3), np.uint32)
+    if out is None:
+        out = np.zeros(((q1 - q0) * n, 3), np.uint32)
+    elif out.dtype != np.uint32 or out.size != (q1 - q0) * n * 3 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint32 array with (q1 - q0) * n * 3 elements")
     _check(lib().fb2_dist_all_pairs(mat.ctypes.data, lens.ctypes.data, n, stride, scale, q0, q1,
                                     out.ctypes.data, device))
     return out.reshape(q1 - q0, n, 3)

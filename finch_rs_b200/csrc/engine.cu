@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -190,7 +191,10 @@ static int reset_sketch_state(fb2_sketcher *s) {
     s->pend[0].valid = s->pend[1].valid = false;
     s->format = FB2_FORMAT_UNKNOWN; s->stream_open = false;
     s->lines_bases = 0; s->total_kmers = 0; s->stage_fill = 0; s->stage_mode = -1;
-    s->next_launch = 32u * HASH_TILE;
+    // First launch of a stream: the threshold is still infinite, every k-mer is a candidate.  Take as
+    // many positions as the log holds (a warp reserves 35 slots per 32 candidates) so that a small
+    // file is hashed in ONE launch and the banded absorb picks the bottom band from the whole log.
+    s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (s->log_cap / 8u * 7u) / HASH_TILE * HASH_TILE);
     s->push_bytes.clear(); s->push_extra.clear(); s->push_offs.assign(1, 0u);
     s->arena.clear(); s->arena_flushed = 0;
     return FB2_OK;
@@ -528,11 +532,12 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
     SketchState *dst = (SketchState *)s->d_state.p;
     LaunchSlot *slot = dev_slot(s, par);
     const uint32_t total_blocks = g.n_st * g.hash_tiles;
+    const uint32_t per_blk = std::min<uint32_t>(HASH_TILE, g.st_bytes);   // positions a block can hold (small chunks: small regions)
     uint32_t b = 0;
     bool known = false;
     double fill = 1.0;  // symbols per launched position
     while (b < total_blocks) {
-        uint32_t nb = std::max<uint32_t>(s->next_launch / HASH_TILE, 1u);
+        uint32_t nb = std::max<uint32_t>(s->next_launch / per_blk, 1u);
         nb = std::min(nb, total_blocks - b);
         CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
         if (s->timing) CU(cudaEventRecord(s->ev_t0, s->st));
@@ -549,12 +554,12 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
         if (!known) {
             known = true;
             s->stats.hash_symbols += s->h_carry->chunk_syms;
-            fill = std::max(1e-6, (double)s->h_carry->chunk_syms / ((double)total_blocks * HASH_TILE));
+            fill = std::max(1e-6, (double)s->h_carry->chunk_syms / ((double)total_blocks * per_blk));
             if (s->h_carry->chunk_syms == 0) break;  // nothing to hash in this chunk
         }
         const uint32_t cnt = s->h_state->slot[par].log_count;
         if (cnt > s->log_cap) {  // log overflowed: nothing committed, redo this range in smaller launches
-            s->next_launch = std::max<uint32_t>(HASH_TILE, std::min((nb * HASH_TILE) / 4, s->log_cap / HASH_TILE * HASH_TILE));
+            s->next_launch = std::max<uint32_t>(per_blk, std::min((nb * per_blk) / 4, s->log_cap / HASH_TILE * HASH_TILE));
             s->steady = false;
             continue;
         }
@@ -562,7 +567,7 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
         TRY(absorb_log(s, par, cnt));
         b += nb;
         // next launch: aim the candidate count at a quarter of the log
-        const double walked = std::max(1.0, (double)nb * HASH_TILE * fill);
+        const double walked = std::max(1.0, (double)nb * per_blk * fill);
         const double frac = std::max((double)cnt, 1.0) / walked;           // candidates per symbol
         double next = (double)(s->log_cap / 4) / frac / fill;               // launched positions
         if (next > 2147483648.0) next = 2147483648.0;
@@ -583,7 +588,7 @@ static int settle(fb2_sketcher *s, int q) {
     s->stats.hash_symbols += sl.chunk_syms;
     if (sl.decision == DECIDE_OVERFLOW) {
         // nothing of this chunk was absorbed: hash it again in bounded launches
-        const double pos = (double)g.n_st * g.hash_tiles * HASH_TILE;
+        const double pos = (double)g.n_st * g.hash_tiles * std::min<uint32_t>(HASH_TILE, g.st_bytes);
         s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (uint32_t)std::min(pos / 4.0, (double)(s->log_cap / 2)));
         s->steady = false;
         TRY(pull_state(s));
@@ -597,7 +602,7 @@ static int settle(fb2_sketcher *s, int q) {
         *s->h_state = snap;   // exact as of the end of this chunk's absorb
     }
     // adapt the launch size to the observed candidate rate
-    const double pos = std::max(1.0, (double)g.n_st * g.hash_tiles * HASH_TILE);
+    const double pos = std::max(1.0, (double)g.n_st * g.hash_tiles * std::min<uint32_t>(HASH_TILE, g.st_bytes));
     const double per_pos = std::max((double)sl.log_count, 1.0) / pos;
     double next = (double)(s->log_cap / 4) / per_pos;
     if (next > 2147483648.0) next = 2147483648.0;
@@ -639,7 +644,7 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     s->par ^= 1;
 
     const uint32_t total_blocks = g.n_st * g.hash_tiles;
-    const double positions = (double)total_blocks * HASH_TILE;
+    const double positions = (double)total_blocks * std::min<uint32_t>(HASH_TILE, g.st_bytes);
     if (!s->timing && positions <= (double)s->next_launch) s->steady = true;
     if (s->steady && !s->timing && positions <= (double)s->next_launch) {
         // asynchronous: hash the whole chunk, let the device decide about absorbing, snapshot the
@@ -1173,38 +1178,106 @@ extern "C" int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size
     d_h.release(); d_l.release(); d_q.release(); d_r.release(); d_o.release();
     return rc;
 }
+static thread_local double g_dist_kernel_ms = 0.0;
+extern "C" double fb2_dist_last_kernel_ms(void) { return g_dist_kernel_ms; }
+
+// Copy `n` bytes with a few host threads (the result slabs are large; one memcpy thread cannot keep
+// up with the kernel + D2H pipeline).
+static void parallel_memcpy(void *dst, const void *src, size_t n) {
+    const size_t min_part = 8u << 20;
+    unsigned parts = (unsigned)std::min<size_t>(4, n / min_part);
+    if (parts < 2) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n / parts + 63) & ~(size_t)63;
+    for (unsigned i = 1; i < parts; ++i) {
+        const size_t off = per * i, len = i + 1 == parts ? n - off : per;
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    memcpy(dst, src, per);
+    for (auto &t : th) t.join();
+}
+
 extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
                                   double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device) {
     if ((!hashes && n_sk * stride) || !lens || q0 > q1 || q1 > n_sk) return fb2_fail(FB2_EINVAL, "bad argument");
     for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
     const uint64_t n_pairs = (uint64_t)(q1 - q0) * n_sk;
     if (n_pairs && !out) return fb2_fail(FB2_EINVAL, "null output");
-    DevBuf d_h, d_l, d_o;
+    DevBuf d_h, d_l, d_o[2];
+    fb2_pair_out *h_pin[2] = {nullptr, nullptr};
+    cudaStream_t st_k = nullptr, st_c = nullptr;
+    cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
     int rc = dist_common(hashes, lens, n_sk, stride, device, d_h, d_l);
     if (rc == FB2_OK && n_pairs) {
-        // bounded slabs of whole query rows so the output buffer stays small
-        const uint64_t rows = std::max<uint64_t>(1, (1ull << 24) / std::max<size_t>(1, n_sk));
-        rc = d_o.ensure(std::min<uint64_t>(n_pairs, rows * n_sk) * sizeof(fb2_pair_out));
+        // Slabs of whole query rows through a 3-stage pipeline: kernel (slab k) | D2H into pinned staging
+        // (slab k-1) | host copy into the caller's (pageable) array (slab k-2).
+        const uint64_t rows = std::max<uint64_t>(1, (1ull << 22) / std::max<size_t>(1, n_sk));
+        const uint64_t slab_pairs = std::min<uint64_t>(n_pairs, rows * n_sk);
         // short query sketches (the usual n <= 1000): shared-memory tiled kernel; otherwise warp-per-pair
         uint32_t max_qlen = 0;
         for (size_t q = q0; q < q1; ++q) max_qlen = std::max(max_qlen, lens[q]);
         const bool tiled = max_qlen <= dist_tile_max_len() && !getenv("FB2_DIST_NO_TILE");
-        for (uint64_t q = q0; rc == FB2_OK && q < q1; q += rows) {
-            const uint64_t m = std::min<uint64_t>(rows, q1 - q) * n_sk;
+        const int scaled = scale > 0.0;
+        const unsigned long long max_hash = scaled ? dist_max_hash(scale) : 0;
+        auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == FB2_OK) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e)); };
+        cu(cudaStreamCreateWithFlags(&st_k, cudaStreamNonBlocking));
+        cu(cudaStreamCreateWithFlags(&st_c, cudaStreamNonBlocking));
+        for (int i = 0; i < 2 && rc == FB2_OK; ++i) {
+            rc = d_o[i].ensure(slab_pairs * sizeof(fb2_pair_out));
+            if (rc == FB2_OK) cu(cudaHostAlloc((void **)&h_pin[i], slab_pairs * sizeof(fb2_pair_out), cudaHostAllocDefault));
+            cu(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+            cu(cudaEventCreateWithFlags(&ev_c[i], cudaEventDisableTiming));
+        }
+        cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+        cu(cudaEventCreate(&ev_t0)); cu(cudaEventCreate(&ev_t1));
+        cu(cudaEventRecord(ev_t0, st_k));
+        struct Slab { uint64_t q, m; };
+        std::vector<Slab> slabs;
+        for (uint64_t q = q0; q < q1; q += rows) slabs.push_back({q, std::min<uint64_t>(rows, q1 - q) * n_sk});
+        auto drain = [&](size_t k) {   // slab k: wait for its D2H, copy to the caller
+            cu(cudaEventSynchronize(ev_c[k & 1]));
+            if (rc == FB2_OK) parallel_memcpy(out + (slabs[k].q - q0) * n_sk, h_pin[k & 1], slabs[k].m * sizeof(fb2_pair_out));
+        };
+        for (size_t k = 0; k < slabs.size() && rc == FB2_OK; ++k) {
+            const int b = (int)(k & 1);
+            if (k >= 2) drain(k - 2);                                   // frees h_pin[b]; its D2H freed d_o[b]
+            const uint64_t q = slabs[k].q, m = slabs[k].m;
             if (tiled) {
                 if (launch_dist_tile(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, (uint32_t)n_sk,
-                                     (uint32_t)q, (uint32_t)(q + m / n_sk), scale > 0.0,
-                                     scale > 0.0 ? dist_max_hash(scale) : 0, d_o.as<fb2_pair_out>(), 0) != 0)
+                                     (uint32_t)q, (uint32_t)(q + m / n_sk), scaled, max_hash, d_o[b].as<fb2_pair_out>(), st_k) != 0)
                     rc = fb2_fail(FB2_ECUDA, "dist_tile_kernel: could not reserve shared memory");
-            } else
-            launch_dist_all(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, (uint32_t)n_sk,
-                            (uint32_t)q, m, scale > 0.0, scale > 0.0 ? dist_max_hash(scale) : 0,
-                            d_o.as<fb2_pair_out>(), 0);
-            cudaError_t e = cudaMemcpy(out + (q - q0) * n_sk, d_o.p, m * sizeof(fb2_pair_out), cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+            } else {
+                launch_dist_all(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, (uint32_t)n_sk,
+                                (uint32_t)q, m, scaled, max_hash, d_o[b].as<fb2_pair_out>(), st_k);
+            }
+            cu(cudaEventRecord(ev_k[b], st_k));
+            cu(cudaStreamWaitEvent(st_c, ev_k[b], 0));
+            cu(cudaMemcpyAsync(h_pin[b], d_o[b].p, m * sizeof(fb2_pair_out), cudaMemcpyDeviceToHost, st_c));
+            cu(cudaEventRecord(ev_c[b], st_c));
+            cu(cudaStreamWaitEvent(st_k, ev_c[b], 0));                  // the kernel of slab k+2 reuses d_o[b]
         }
+        if (ev_t1) cu(cudaEventRecord(ev_t1, st_k));
+        if (rc == FB2_OK && slabs.size() >= 2) drain(slabs.size() - 2);
+        if (rc == FB2_OK && slabs.size() >= 1) drain(slabs.size() - 1);
+        if (st_k) cudaStreamSynchronize(st_k);
+        if (st_c) cudaStreamSynchronize(st_c);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && rc == FB2_OK) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+        // device time from the first kernel's start to the last kernel's end (includes waits for free slabs)
+        float ms = 0.f;
+        if (rc == FB2_OK && ev_t0 && ev_t1 && cudaEventElapsedTime(&ms, ev_t0, ev_t1) == cudaSuccess) g_dist_kernel_ms = ms;
+        if (ev_t0) cudaEventDestroy(ev_t0);
+        if (ev_t1) cudaEventDestroy(ev_t1);
     }
-    d_h.release(); d_l.release(); d_o.release();
+    for (int i = 0; i < 2; ++i) {
+        if (h_pin[i]) cudaFreeHost(h_pin[i]);
+        if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+        if (ev_c[i]) cudaEventDestroy(ev_c[i]);
+        d_o[i].release();
+    }
+    if (st_k) cudaStreamDestroy(st_k);
+    if (st_c) cudaStreamDestroy(st_c);
+    d_h.release(); d_l.release();
     return rc;
 }
 

@@ -10,12 +10,17 @@
 // These stay on the host exactly as SURVEY 8a (row S14, D2) scopes them: a few f64 compares over
 // <= kmers_to_sketch entries.  Written independently of oracle/ (which is test infrastructure).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <cuda_runtime.h>
 
 #include "../../include/finch_b200.h"
 
@@ -155,35 +160,117 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
     return rc;
 }
 
+// One file through handle `s` (lib.rs:51-94 per file): read in pieces into the worker's pinned buffer,
+// feed the raw bytes, finish the sketch.
+static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_t *buf, size_t piece,
+                           const fb2_params *p, const fb2_filter *f, fb2_result *out) {
+    const bool is_stdin = strcmp(path, "-") == 0;  // lib.rs:38-40
+    FILE *fp = is_stdin ? stdin : fopen(path, "rb");
+    if (!fp) return fb2_fail(FB2_EIO, std::string(path) + ": No such file or directory");
+    int rc = reuse ? fb2_sketcher_reset(s) : FB2_OK;
+    bool any = false;
+    while (rc == FB2_OK) {
+        const size_t got = fread(buf, 1, piece, fp);
+        if (got) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, got, 0); }
+        if (got < piece) break;
+    }
+    if (!is_stdin) fclose(fp);
+    if (rc == FB2_OK && !any) rc = fb2_fail(FB2_EEMPTY, std::string(path) + ": empty input");
+    if (rc == FB2_OK) rc = fb2_sketcher_feed_fastx(s, nullptr, 0, 1);
+    if (rc == FB2_OK) rc = finish_sketch(s, path, p, f, out);
+    return rc;
+}
+
+// Idle worker handles (sketcher + pinned read buffer) kept between sketch_files calls: creating a
+// handle allocates its logs and tables (tens of ms, serialised by the driver), which would otherwise
+// dominate batches of small files.  At most FB2_POOL_MAX entries; fb2_sketch_files_release_pool()
+// frees them.
+struct PoolEntry { fb2_params p; fb2_sketcher *s; uint8_t *buf; };
+static std::mutex g_pool_mu;
+static std::vector<PoolEntry> g_pool;
+static const size_t FB2_POOL_MAX = 32;
+static bool same_sketcher_params(const fb2_params &a, const fb2_params &b) {
+    return a.kind == b.kind && a.kmers_to_sketch == b.kmers_to_sketch && a.kmer_length == b.kmer_length &&
+           a.hash_seed == b.hash_seed && a.scale == b.scale && a.device == b.device && a.stream == nullptr &&
+           b.stream == nullptr;
+}
+static bool pool_acquire(const fb2_params *p, fb2_sketcher **s, uint8_t **buf) {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); ++i)
+        if (same_sketcher_params(g_pool[i].p, *p)) {
+            *s = g_pool[i].s; *buf = g_pool[i].buf;
+            g_pool.erase(g_pool.begin() + (long)i);
+            return true;
+        }
+    return false;
+}
+static bool pool_release(const fb2_params *p, fb2_sketcher *s, uint8_t *buf) {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (g_pool.size() >= FB2_POOL_MAX || p->stream) return false;
+    g_pool.push_back(PoolEntry{*p, s, buf});
+    return true;
+}
+extern "C" void fb2_sketch_files_release_pool(void) {
+    std::vector<PoolEntry> old;
+    { std::lock_guard<std::mutex> g(g_pool_mu); old.swap(g_pool); }
+    for (auto &e : old) { cudaFreeHost(e.buf); fb2_sketcher_destroy(e.s); }
+}
+
+// sketch_files (lib.rs:29-49): the reference fans the files out over a rayon pool, one sketcher per task.
+// Here a few host threads each own one sketcher handle (its own CUDA streams and buffers) and pull
+// file indices from a shared counter, so the small kernels and host<->device round trips of different
+// files overlap on the GPU; results land in input order.  FB2_FILE_WORKERS overrides the thread count.
 extern "C" int fb2_sketch_files(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
                                 fb2_result *outs) {
     if (!p || !f || (n && (!paths || !outs))) return fb2_fail(FB2_EINVAL, "null argument");
     for (size_t i = 0; i < n; ++i) memset(&outs[i], 0, sizeof(fb2_result));
     if (!n) return FB2_OK;
-    fb2_sketcher *s = nullptr;
-    int rc = fb2_sketcher_create(p, &s);
-    if (rc != FB2_OK) return rc;
-    const size_t piece = 64u << 20;
-    std::vector<uint8_t> buf(piece);
-    for (size_t i = 0; i < n && rc == FB2_OK; ++i) {
-        const bool is_stdin = strcmp(paths[i], "-") == 0;  // lib.rs:38-40
-        FILE *fp = is_stdin ? stdin : fopen(paths[i], "rb");
-        if (!fp) { rc = fb2_fail(FB2_EIO, std::string(paths[i]) + ": No such file or directory"); break; }
-        if (i) rc = fb2_sketcher_reset(s);
-        bool any = false;
-        while (rc == FB2_OK) {
-            const size_t got = fread(buf.data(), 1, piece, fp);
-            if (got) { any = true; rc = fb2_sketcher_feed_fastx(s, buf.data(), got, 0); }
-            if (got < piece) break;
+    size_t workers = 8;
+    if (const char *e = getenv("FB2_FILE_WORKERS")) { const long v = atol(e); if (v >= 1 && v <= 64) workers = (size_t)v; }
+    workers = std::min(workers, n);
+    for (size_t i = 0; i < n; ++i) if (strcmp(paths[i], "-") == 0) workers = 1;   // stdin is consumed in order
+    const size_t piece = 32u << 20;
+    std::atomic<size_t> next{0};
+    std::atomic<int> first_rc{FB2_OK};
+    std::mutex mu;
+    std::string first_msg;
+    auto fail = [&](int rc) {
+        std::lock_guard<std::mutex> g(mu);
+        if (first_rc.load() == FB2_OK) { first_rc.store(rc); first_msg = fb2_last_error(); }
+    };
+    auto work = [&]() {
+        fb2_sketcher *s = nullptr;
+        uint8_t *buf = nullptr;
+        bool reuse = pool_acquire(p, &s, &buf);     // an idle handle of an earlier call, same parameters
+        int rc = FB2_OK;
+        if (!reuse) {
+            rc = fb2_sketcher_create(p, &s);        // selects the device for this thread
+            if (rc == FB2_OK && cudaHostAlloc((void **)&buf, piece, cudaHostAllocDefault) != cudaSuccess)
+                rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed (file read buffer)");
         }
-        if (!is_stdin) fclose(fp);
-        if (rc == FB2_OK && !any) rc = fb2_fail(FB2_EEMPTY, std::string(paths[i]) + ": empty input");
-        if (rc == FB2_OK) rc = fb2_sketcher_feed_fastx(s, nullptr, 0, 1);
-        if (rc == FB2_OK) rc = finish_sketch(s, paths[i], p, f, &outs[i]);
+        while (rc == FB2_OK && first_rc.load() == FB2_OK) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            rc = sketch_one_file(s, reuse, paths[i], buf, piece, p, f, &outs[i]);
+            reuse = true;
+        }
+        if (rc != FB2_OK) fail(rc);
+        if (rc == FB2_OK && s && buf && pool_release(p, s, buf)) return;   // kept for the next call
+        if (buf) cudaFreeHost(buf);
+        if (s) fb2_sketcher_destroy(s);
+    };
+    if (workers <= 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (size_t w = 0; w < workers; ++w) th.emplace_back(work);
+        for (auto &t : th) t.join();
     }
-    fb2_sketcher_destroy(s);
-    if (rc != FB2_OK) for (size_t i = 0; i < n; ++i) fb2_result_free(&outs[i]);
-    return rc;
+    const int rc = first_rc.load();
+    if (rc != FB2_OK) {
+        for (size_t i = 0; i < n; ++i) fb2_result_free(&outs[i]);
+        return fb2_fail(rc, first_msg);
+    }
+    return FB2_OK;
 }
 
 // ---- distance epilogue ---------------------------------------------------------------------------

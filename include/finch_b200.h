@@ -155,6 +155,10 @@ int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *name, const 
 int fb2_sketch_files(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
                      fb2_result *outs);
 
+/* fb2_sketch_files keeps its idle worker handles (device buffers, pinned read buffers) for the next
+ * call with the same parameters; this frees them. */
+void fb2_sketch_files_release_pool(void);
+
 /* ---- raw_distance (distance.rs:66-126), integer part, batched ----------------------------- */
 typedef struct fb2_pair_out {
     uint32_t common; /* |A n B| up to the stopping point */
@@ -170,6 +174,8 @@ int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, si
 /* All ordered pairs (q, r), q in [q0,q1), r in [0,n_sk): out[(q-q0)*n_sk + r]. */
 int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
                        double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device);
+/* Measurement aid: device time (ms) spanned by the kernels of this thread's last fb2_dist_all_pairs. */
+double fb2_dist_last_kernel_ms(void);
 /* distance.rs:117-125 and :35-41 from the integers of one pair. */
 void fb2_distance_finish(const fb2_pair_out *p, uint8_t kmer_length, double *containment,
                          double *jaccard, double *mash_distance, uint64_t *common_hashes,

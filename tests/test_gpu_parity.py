@@ -303,6 +303,88 @@ def test_dist_batch_random(fb, oracle):
             assert tuple(allp[a, b]) == (c, i, j)
 
 
+def _closed_form_pairs(sk, scale=0.0):
+    """(common, i, j) per ordered pair from the closed form of the merge loop, numpy."""
+    n = len(sk)
+    out = np.zeros((n, n, 3), np.uint32)
+    mh = None
+    if scale > 0.0:
+        mh = (2**64 - 1) // int(1.0 / scale)
+    for a in range(n):
+        A = sk[a]
+        for b in range(n):
+            B = sk[b]
+            c = i = j = 0
+            if len(A) and len(B):
+                c = len(np.intersect1d(A, B, assume_unique=True))
+                t = min(int(A[-1]), int(B[-1]))
+                i = int(np.searchsorted(A, np.uint64(t), side="right"))
+                j = int(np.searchsorted(B, np.uint64(t), side="right"))
+            if mh is not None:
+                i = max(i, int(np.searchsorted(A, np.uint64(mh), side="left")))
+                j = max(j, int(np.searchsorted(B, np.uint64(mh), side="left")))
+            out[a, b] = (c, i, j)
+    return out
+
+
+def test_dist_all_pairs_tiled_edge_cases(fb, oracle):
+    """Tiled shared-memory kernel: colliding table slots, lengths up to its limit (1023), longer
+    reference rows, query sub-ranges, more queries than one tile, and the warp-per-pair fallback."""
+    rng = np.random.default_rng(21)
+    pool = np.unique(rng.integers(0, 2**63, size=6000, dtype=np.uint64))
+    sk = []
+    for n in (1023, 1000, 1, 0, 517, 1023, 999, 1000, 64, 1000, 1000, 333):     # 12 queries -> 2 tiles
+        sk.append(np.sort(rng.choice(pool, size=n, replace=False)))
+    # identical low 13 bits (every key lands in the same table slot) and identical fingerprints
+    sk.append(np.sort((rng.choice(1 << 20, size=300, replace=False).astype(np.uint64) << np.uint64(19)) | np.uint64(0x155)))
+    sk.append(sk[-1][::2].copy())
+    sk.append(np.arange(1, 1001, dtype=np.uint64))                                # consecutive small integers
+    sk.append(np.array([0, 2**64 - 1], np.uint64))
+    n = len(sk)
+    mat, lens, stride = fb._pack(sk)
+    for scale in (0.0, 0.3):
+        want = _closed_form_pairs(sk, scale)
+        got = fb.dist_all_pairs(mat, lens, scale)
+        assert np.array_equal(got, want), np.argwhere((got != want).any(axis=2))[:5]
+        sub = fb.dist_all_pairs(mat, lens, scale, 3, 14)
+        assert np.array_equal(sub, want[3:14])
+    # spot-check the closed form itself against the oracle's literal merge loop
+    for a, b in ((0, 1), (12, 13), (13, 12), (14, 2), (15, 0), (3, 5)):
+        cont, jac, com, tot = oracle.raw_distance(sk[a], sk[b], 0.0)
+        c, i, j = (int(v) for v in _closed_form_pairs([sk[a], sk[b]])[0, 1])
+        assert (c, i - c + j) == (com, tot)
+    # a query longer than the tiled kernel's limit: whole call falls back to the warp-per-pair kernel
+    sk2 = sk[:6] + [np.sort(rng.choice(pool, size=1500, replace=False)), np.sort(rng.choice(pool, size=1024, replace=False))]
+    mat2, lens2, _ = fb._pack(sk2)
+    want2 = _closed_form_pairs(sk2)
+    assert np.array_equal(fb.dist_all_pairs(mat2, lens2, 0.0), want2)
+    # long rows as references only (queries 0..5 are short): tiled kernel with nb > 1023
+    assert np.array_equal(fb.dist_all_pairs(mat2, lens2, 0.0, 0, 6), want2[:6])
+
+
+def test_dist_all_pairs_multi_slab(fb):
+    """More pairs than one output slab (2^22): the kernel / D2H / host-copy pipeline keeps row order."""
+    rng = np.random.default_rng(22)
+    n, m = 2304, 64
+    base = np.sort(rng.choice(1 << 40, size=(n // 16, m), replace=False).astype(np.uint64), axis=1)
+    mat = np.repeat(base, 16, axis=0)                       # 16 identical sketches per cluster
+    noise = rng.integers(0, 1 << 40, size=(n, 8), dtype=np.uint64)
+    mat[:, -8:] = noise + np.uint64(1 << 41)                # 8 private hashes above the shared ones
+    mat.sort(axis=1)
+    lens = np.full(n, m, np.uint32)
+    got = fb.dist_all_pairs(mat, lens, 0.0)
+    assert got.shape == (n, n, 3)
+    idx = rng.integers(0, n, size=(400, 2))
+    for a, b in idx:
+        A, B = mat[a], mat[b]
+        c = len(np.intersect1d(A, B))
+        t = min(int(A[-1]), int(B[-1]))
+        assert tuple(got[a, b]) == (c, int(np.searchsorted(A, np.uint64(t), side="right")),
+                                    int(np.searchsorted(B, np.uint64(t), side="right"))), (a, b)
+    # diagonal: a sketch against itself
+    assert np.array_equal(got[np.arange(n), np.arange(n)], np.tile(np.array([m, m, m], np.uint32), (n, 1)))
+
+
 def test_distance_scaled_end_to_end(fb):  # distance.rs:312-337
     def mk():
         q = fb.ScaledSketcher(3, 0.001, 2, 42)
