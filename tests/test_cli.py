@@ -1,0 +1,217 @@
+"""`finch` command line (finch_rs_b200/cli/finch_cli.cpp) and the `.sk` JSON wire format.
+
+CPU part: flag rules, JSON reader/writer, `hist` / `info` on sketch files, number formatting.
+GPU part (`-m gpu`): the reference's own CLI tests (cli/tests/test_cli.rs) run against this binary:
+same arguments, same assertions, including the golden k-mer lists for tests/data/query.fa.
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FINCH = os.path.join(ROOT, "finch_rs_b200", "finch")
+QUERY = os.path.join(ROOT, "tests", "golden", "query.fa")
+
+GOLDEN_KMERS = [  # cli/tests/test_cli.rs:97-106 and :134-143 (identical for mash and scaled)
+    "ATGCTAGCTACGTAACGTCGC", "CAGTCGATCGATCGTAGCTGA", "CTCAGATGCTGAGCCGGTCTA", "GCTAGCTAGCATCGCTAGCTA",
+    "GACTAGCTAGCTAGCTAGCGA", "CGCTAGCTACGATCGATCGAC", "TAATTTATACGGGCCTATTAA", "GCATCAGCTAGCATCGCTGTA",
+    "AGCCGGTCTACTACTACACAT", "AAGGCCTAACTTAATAGGCCC"]
+
+
+@pytest.fixture(scope="session")
+def finch():
+    if not os.path.exists(FINCH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "finch_rs_b200", "csrc"), "-j8"])
+
+    def run(*args, cwd=None, check=True):
+        p = subprocess.run([FINCH, *args], capture_output=True, text=True, cwd=cwd)
+        if check:
+            assert p.returncode == 0, p.stderr
+        return p
+    return run
+
+
+SK = {"kmer": 21, "alphabet": "ACGT", "preserveCase": False, "canonical": True, "sketchSize": 3,
+      "hashType": "MurmurHash3_x64_128", "hashBits": 64, "hashSeed": 0, "scale": None,
+      "sketches": [{"name": "a \"q\"\n.fa", "seqLength": 405, "numValidKmers": 339, "comment": "",
+                    "filters": {"strandFilter": "0.1", "errFilter": "0.21", "minCopies": "2"},
+                    "hashes": ["933085113509804", "8582128962097342", "18446744073709551615"],
+                    "kmers": ["ATGCTAGCTACGTAACGTCGC", "CAGTCGATCGATCGTAGCTGA", "CTCAGATGCTGAGCCGGTCTA"],
+                    "counts": [1, 3, 3]}]}
+
+
+def test_number_formatting_matches_serde_and_rust_display(finch):
+    vals = ["1", "0.5", "0.001", "1e-5", "1e-6", "1e16", "1e15", "123456.789", "1.5e-7", "0.30000000000000004",
+            "0.21", "1e21", "-2.5", "0", "33.333332"]
+    want = ["1.0 1 1", "0.5 0.5 0.5", "0.001 0.001 0.001", "0.00001 0.00001 0.00001", "1e-6 0.000001 0.000001",
+            "1e16 10000000000000000 10000000000000000", "1000000000000000.0 1000000000000000 1000000000000000",
+            "123456.789 123456.789 123456.79", "1.5e-7 0.00000015 0.00000015",
+            "0.30000000000000004 0.30000000000000004 0.3", "0.21 0.21 0.21",
+            "1e21 1000000000000000000000 1000000000000000000000", "-2.5 -2.5 -2.5", "0.0 0 0",
+            "33.333332 33.333332 33.333332"]
+    assert finch("fmt-f64", *vals).stdout.split("\n")[:-1] == want
+
+
+def test_sk_json_round_trip_is_byte_identical(finch, tmp_path):
+    """json.rs:64-89,141-158: field order, quoted-decimal hashes, escaped names, `scale: null`."""
+    f = tmp_path / "a.sk"
+    text = json.dumps(SK, separators=(",", ":"))
+    f.write_text(text)
+    out = finch("sketch", "-O", str(f)).stdout
+    assert json.loads(out) == SK
+    # byte-identical except for the key order inside `filters` (a HashMap in the reference)
+    a, b = json.loads(out), json.loads(text)
+    a["sketches"][0]["filters"] = b["sketches"][0]["filters"] = {}
+    assert json.dumps(a, separators=(",", ":")) == json.dumps(b, separators=(",", ":"))
+    assert out.startswith('{"kmer":21,"alphabet":"ACGT","preserveCase":false,"canonical":true,"sketchSize":3,'
+                          '"hashType":"MurmurHash3_x64_128","hashBits":64,"hashSeed":0,"scale":null,"sketches":[{"name":')
+    # -o adds the extension when missing (main.rs:29-37)
+    finch("sketch", "-o", str(tmp_path / "out"), str(f))
+    assert json.loads((tmp_path / "out.sk").read_text()) == SK
+
+
+def test_scaled_sk_and_optional_fields(finch, tmp_path):
+    sk = dict(SK, scale=0.001, sketchSize=1000)
+    sk["sketches"] = [{"name": "x", "seqLength": None, "numValidKmers": None, "comment": None, "filters": None,
+                       "hashes": ["5", "7"]}]                      # kmers / counts absent (json.rs:105-121)
+    f = tmp_path / "s.json"
+    f.write_text(json.dumps(sk))
+    out = json.loads(finch("sketch", "-s", "scaled", "-O", str(f)).stdout)
+    assert out["scale"] == 0.001 and out["sketchSize"] == 1000
+    s = out["sketches"][0]
+    assert (s["seqLength"], s["numValidKmers"], s["comment"], s["filters"]) == (0, 0, "", {})
+    assert s["hashes"] == ["5", "7"] and s["counts"] == [1, 1] and s["kmers"] == ["", ""]
+    # sketch type of the file and of the command line must agree (main.rs:345-349)
+    p = finch("sketch", "-O", str(f), check=False)
+    assert p.returncode == 1 and "Sketch types are not the same" in p.stderr
+
+
+def test_hist_and_info_on_sketch_files(finch, tmp_path):
+    f = tmp_path / "a.sk"
+    f.write_text(json.dumps(SK))
+    assert json.loads(finch("hist", str(f)).stdout) == {SK["sketches"][0]["name"]: [1, 0, 2]}   # statistics.rs:30-47
+    info = finch("info", str(f)).stdout.split("\n")
+    assert info[0] == 'a "q"' and info[1] == ".fa (from 405bp)"
+    # cardinality in f32 against usize::MAX (statistics.rs:19-22): hash == u64::MAX -> (3-1)/1.0
+    assert info[2] == "  Estimated # of Unique Kmers: 2"
+    assert info[3] == "  Estimated Average Depth: 2.3333333x"      # (1 + 3 + 3) / 3 in f32
+    gc = sum(k.count("G") + k.count("C") for k in SK["sketches"][0]["kmers"][0:1]) * 1 + \
+        sum(k.count("G") + k.count("C") for k in SK["sketches"][0]["kmers"][1:]) * 3
+    assert info[4].startswith("  Estimated % GC: ") and abs(float(info[4].split(": ")[1][:-1]) - 100.0 * gc / (7 * 21)) < 1e-3
+
+
+def test_flag_rules(finch, tmp_path):
+    f = tmp_path / "a.sk"
+    f.write_text(json.dumps(SK))
+    cases = [
+        (["sketch", "--scale", "0.1", "-O", str(f)], "`scale` can not be specified for `mash` sketch types"),     # cli.rs:293
+        (["sketch", "-s", "scaled", "--oversketch", "3", "-O", str(f)], "`oversketch` can not be specified"),   # cli.rs:314
+        (["sketch", "-s", "scaled", "-N", "-O", str(f)], "`no_strict` can not be specified"),                    # cli.rs:317
+        (["sketch", "--err-filter", "5", "-O", str(f)], "err-filter must be between 0 and 4.761904761904762"),   # cli.rs:264
+        (["sketch", "-n", "x", "-O", str(f)], "n-hashes must be a positive integer"),
+        (["sketch", "-k", "20", "-O", str(f)], "Specified kmer length 20 does not match 21 from sketch"),        # main.rs:367
+        (["sketch", "--seed", "4", "-O", str(f)], "Specified hash seed 4 does not match 0 from sketch"),
+        (["sketch", "-f", "--no-filter", "-O", str(f)], "cannot be used with"),
+        (["sketch", "-o", "x", "-O", str(f)], "cannot be used with"),
+        (["dist", str(f), "-p", "-q", "a"], "cannot be used with"),
+        (["sketch", "-b", "-O", str(f)], "not supported by the B200 build"),
+        (["dist", "--old-dist", str(f)], "not supported by the B200 build"),
+        (["sketch", str(f)], "is not a sequence file?"),                                                          # main.rs:213-219
+        (["sketch", "-O", str(tmp_path / "missing.sk")], "Error opening"),
+        (["frobnicate", "x"], "wasn't expected"),
+    ]
+    for args, msg in cases:
+        p = finch(*args, check=False)
+        assert p.returncode == 1 and msg in p.stderr, (args, p.stderr)
+    bad = tmp_path / "bad.sk"
+    bad.write_text('{"kmer": 21, "sketches": [')
+    p = finch("hist", str(bad), check=False)
+    assert p.returncode == 1 and "Error parsing" in p.stderr
+    # a loaded sketch with -f only gets its filter METADATA updated (filtering.rs:20-52)
+    out = json.loads(finch("sketch", "-f", "--min-abun-filter", "3", "-O", str(f)).stdout)
+    s = out["sketches"][0]
+    assert s["hashes"] == SK["sketches"][0]["hashes"] and s["counts"] == [1, 3, 3]
+    assert s["filters"] == {"strandFilter": "0.1", "errFilter": "0.21", "minCopies": "3"}
+
+
+# ---- the reference's CLI tests (cli/tests/test_cli.rs), against this binary -----------------------------
+@pytest.mark.gpu
+def test_file_doesnt_exist(finch):                       # test_cli.rs:9-18
+    p = finch("sketch", "test/file/doesnt/exist", check=False)
+    assert p.returncode != 0 and "No such file or directory" in p.stderr
+
+
+@pytest.mark.gpu
+def test_finch_sketch(finch):                            # test_cli.rs:20-37
+    sk = json.loads(finch("sketch", "--n-hashes", "10", "-O", QUERY).stdout)
+    assert (sk["kmer"], sk["alphabet"], sk["sketchSize"], sk["hashSeed"]) == (21, "ACGT", 10, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [["--sketch-type", "scaled", "--scale", ".001"], ["--sketch-type", "mash"]])
+def test_finch_sketch_scaled_and_mash(finch, oracle, extra):   # test_cli.rs:80-149
+    sk = json.loads(finch("sketch", "--n-hashes", "10", *extra, QUERY, "-O").stdout)
+    assert (sk["kmer"], sk["alphabet"], sk["sketchSize"], sk["hashSeed"]) == (21, "ACGT", 10, 0)
+    s = sk["sketches"][0]
+    assert s["kmers"] == GOLDEN_KMERS
+    assert sk["scale"] == (0.001 if "scaled" in extra else None)
+    # the rest of the document against the oracle (derived, not pinned upstream: SURVEY 8c)
+    data = open(QUERY, "rb").read()
+    if "scaled" in extra:
+        rc, osk = oracle.sketch_stream(data, oracle.scaled_params(10, 21, 0.001, 0), oracle.make_filter(None, (None, None), 0.21, 0.1))
+    else:
+        rc, osk = oracle.sketch_stream(data, oracle.mash_params(2000, 10, False, 21, 0), oracle.make_filter(None, (None, None), 0.21, 0.1))
+    assert rc == oracle.OK
+    assert [int(h) for h in s["hashes"]] == [int(h) for h in osk["hashes"]]
+    assert s["counts"] == [int(c) for c in osk["counts"]]
+    assert (s["name"], s["seqLength"], s["numValidKmers"], s["comment"], s["filters"]) == \
+        (QUERY, osk["seq_length"], osk["num_valid_kmers"], "", {})
+
+
+@pytest.mark.gpu
+def test_sketch_in_place_then_dist(finch, tmp_path):
+    """generate_sketch_files (main.rs:201-235) + dist over a sketch file and a sequence file
+    (parse_mash_files main.rs:237-313, calc_sketch_distances :315-334, distance.rs:9-47)."""
+    rng = np.random.default_rng(7)
+    genome = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=30000)
+    mut = genome.copy()
+    pos = rng.choice(len(mut), size=300, replace=False)
+    mut[pos] = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=300)
+
+    def fasta(path, seq, name):
+        with open(path, "wb") as fh:
+            fh.write(b">" + name + b"\n")
+            for i in range(0, len(seq), 70):
+                fh.write(seq[i:i + 70].tobytes() + b"\n")
+    a, b = tmp_path / "a.fa", tmp_path / "b.fa"
+    fasta(a, genome, b"a")
+    fasta(b, mut, b"b")
+    finch("sketch", "-n", "500", str(a))
+    ska = json.loads((tmp_path / "a.fa.sk").read_text())
+    assert ska["sketchSize"] == 500 and len(ska["sketches"][0]["hashes"]) == 500
+    assert ska["sketches"][0]["name"] == str(a)
+    # first sketch is the query by default; the pair (a, a) is skipped; a sequence file joins the sketch file.
+    # n-hashes comes from the sketch file (update_sketch_params), so b.fa is sketched with n = 500 too.
+    d = json.loads(finch("dist", str(tmp_path / "a.fa.sk"), str(b)).stdout)
+    assert len(d) == 1 and list(d[0].keys()) == ["containment", "jaccard", "mashDistance", "commonHashes", "totalHashes",
+                                                  "query", "reference"]
+    assert (d[0]["query"], d[0]["reference"]) == (str(a), str(b))
+    ha = np.array([int(h) for h in ska["sketches"][0]["hashes"]], np.uint64)
+    skb = json.loads(finch("sketch", "-n", "500", "-O", str(b)).stdout)
+    hb = np.array([int(h) for h in skb["sketches"][0]["hashes"]], np.uint64)
+    import oracle as o
+    cont, jac, com, tot = o.raw_distance(ha, hb, 0.0)
+    assert (d[0]["commonHashes"], d[0]["totalHashes"]) == (com, tot)
+    assert d[0]["containment"] == cont and d[0]["jaccard"] == jac
+    md = min(1.0, max(0.0, -np.log(2 * jac / (1 + jac)) / 21))
+    assert abs(d[0]["mashDistance"] - md) < 1e-15
+    # pairwise: both ordered pairs, reference-major (main.rs:321-331); max-dist filters
+    dp = json.loads(finch("dist", "-p", str(tmp_path / "a.fa.sk"), str(b)).stdout)
+    assert [(x["query"], x["reference"]) for x in dp] == [(str(b), str(a)), (str(a), str(b))]
+    assert json.loads(finch("dist", "-p", "-d", "0.0", str(tmp_path / "a.fa.sk"), str(b)).stdout) == []
+    # queries by name
+    dq = json.loads(finch("dist", "-q", str(b), "--", str(tmp_path / "a.fa.sk"), str(b)).stdout)
+    assert [(x["query"], x["reference"]) for x in dq] == [(str(b), str(a))]
