@@ -62,8 +62,9 @@ struct SketchState {
     unsigned int has_max_key;         // side slot for hash == u64::MAX in use
     unsigned int gather_count;
     unsigned int keep_count;          // result of select_keep
-    unsigned int pad;
+    unsigned int hist_shift;          // live_bins[key >> hist_shift] counts the keys inserted into the current table
     unsigned long long new_threshold;
+    unsigned int *live_bins;          // 4096 bins (device), maintained by table_upsert; nullptr = off
 };
 
 struct LogView {

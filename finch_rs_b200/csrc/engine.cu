@@ -110,6 +110,8 @@ struct fb2_sketcher {
     Table tab[2];
     int cur = 0;
     DevBuf sort_keys, sort_slots, sort_tkeys, sort_tslots, sort_hist, d_bins;
+    DevBuf d_live_bins;          // live histogram of the current table's keys (table_upsert), 4096 bins
+    uint32_t live_shift = 52;    // its shift (host copy of SketchState::hist_shift)
     DevBuf out_hash, out_cnt, out_ext, out_kmer, out_posx;
     DevBuf sel_hash, sel_cnt, sel_ext, sel_kmer, sel_posx, sel_bytes, sel_idx;
     uint8_t *h_res = nullptr;        // pinned read-back staging
@@ -175,9 +177,29 @@ static int ensure_sort(fb2_sketcher *s, uint32_t n) {
     return FB2_OK;
 }
 
+static uint32_t shift_for_threshold(unsigned long long thr) {   // top 12 bits below the threshold
+    uint32_t bits = 0;
+    while (bits < 64 && (thr >> bits) != 0ULL) ++bits;
+    return bits > 12 ? bits - 12 : 0;
+}
+// (Re)build the live histogram for the current table; called after every rebuild and at reset.
+static int refresh_live_hist(fb2_sketcher *s) {
+    s->live_shift = shift_for_threshold(s->h_state->threshold);
+    s->h_state->hist_shift = s->live_shift;   // keep the host mirror in step (push_state copies it back)
+    launch_live_hist_refresh(s->tab[s->cur].view(), (SketchState *)s->d_state.p, s->live_shift,
+                             s->d_live_bins.as<uint32_t>(), s->st);
+    s->stats.kernel_launches += 2;
+    return FB2_OK;
+}
+
 static int reset_sketch_state(fb2_sketcher *s) {
     memset(s->h_state, 0, sizeof(SketchState));
     s->h_state->threshold = (s->scaled && s->size == 0) ? s->max_hash : ~0ULL;
+    TRY(s->d_live_bins.ensure(4096 * sizeof(uint32_t)));
+    s->h_state->live_bins = s->d_live_bins.as<unsigned int>();
+    s->live_shift = shift_for_threshold(s->h_state->threshold);
+    s->h_state->hist_shift = s->live_shift;
+    CU(cudaMemsetAsync(s->d_live_bins.p, 0, 4096 * sizeof(uint32_t), s->st));
     TRY(push_state(s));
     memset(s->h_carry, 0, sizeof(ParseCarry));
     s->h_carry->prev1 = s->h_carry->prev2 = '\n';
@@ -297,7 +319,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     }
     s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release();
     s->d_carry.release(); s->d_state.release();
-    s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release(); s->d_bins.release();
+    s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release(); s->d_bins.release(); s->d_live_bins.release();
     s->out_hash.release(); s->out_cnt.release(); s->out_ext.release(); s->out_kmer.release(); s->out_posx.release();
     s->sel_hash.release(); s->sel_cnt.release(); s->sel_ext.release(); s->sel_kmer.release(); s->sel_posx.release();
     s->sel_bytes.release(); s->sel_idx.release();
@@ -324,14 +346,16 @@ extern "C" int fb2_sketcher_reset(fb2_sketcher *s) {
 // table from those and lower the threshold.  Grows the table when what must be kept needs it.
 static int sort_table(fb2_sketcher *s, uint32_t *n_out) {
     TRY(pull_state(s));
-    const uint32_t n = s->h_state->occupied + (s->h_state->has_max_key ? 1u : 0u);
-    TRY(ensure_sort(s, std::max(n, 1u)));
+    const uint32_t n_all = s->h_state->occupied + (s->h_state->has_max_key ? 1u : 0u);
+    TRY(ensure_sort(s, std::max(n_all, 1u)));
     TRY(s->d_bins.ensure(3 * 4096 * sizeof(uint32_t)));
     SketchState *dst = (SketchState *)s->d_state.p;
     unsigned long long *keys = s->sort_keys.as<unsigned long long>(), *tkeys = s->sort_tkeys.as<unsigned long long>();
     uint32_t *slots = s->sort_slots.as<uint32_t>(), *tslots = s->sort_tslots.as<uint32_t>();
-    launch_gather(s->tab[s->cur].view(), dst, tkeys, tslots, s->st);          // unsorted -> (tkeys, tslots)
+    launch_gather(s->tab[s->cur].view(), dst, tkeys, tslots, s->st);          // unsorted live keys -> (tkeys, tslots)
     s->stats.kernel_launches += 2;
+    TRY(pull_state(s));
+    const uint32_t n = s->h_state->gather_count;                               // keys at or below the threshold
     // bucket + rank sort on the top 12 bits below the threshold; keys above the threshold cannot
     // exist in the table except the u64::MAX side slot (threshold == MAX then)
     const unsigned long long thr = s->h_state->threshold;
@@ -405,6 +429,7 @@ static int prune(fb2_sketcher *s, uint32_t need_room, const unsigned long long *
     s->cur = other;
     s->stats.prunes++;
     TRY(pull_state(s));
+    TRY(refresh_live_hist(s));
     return FB2_OK;
 }
 
@@ -536,6 +561,11 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
     uint32_t b = 0;
     bool known = false;
     double fill = 1.0;  // symbols per launched position
+    // Infinite threshold (start of a stream): every k-mer is a candidate.  If the whole chunk fits into
+    // one launch of the log take it (small files: one launch, one banded absorb); otherwise start small,
+    // so the threshold is finite before most of the chunk is hashed.
+    if (s->h_state->threshold == ~0ULL && (uint64_t)total_blocks * per_blk > s->next_launch)
+        s->next_launch = 32u * HASH_TILE;
     while (b < total_blocks) {
         uint32_t nb = std::max<uint32_t>(s->next_launch / per_blk, 1u);
         nb = std::min(nb, total_blocks - b);
@@ -654,6 +684,10 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
         launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, total_blocks, s->d_rcount[par].as<uint32_t>(), ord_base, dst,
                     slot, log_view(s, par), s->prm.hash_seed, s->st);
         launch_absorb_guarded(log_view(s, par), slot, s->tab[s->cur].view(), dst, dc, s->log_cap / 4, s->st);
+        if (s->size > 0 && !getenv("FB2_NO_SOFT_THRESHOLD")) {   // keep the admission threshold tight between rebuilds
+            launch_soft_threshold(s->d_live_bins.as<uint32_t>(), s->live_shift, s->scaled ? 1 : 0, s->size, s->max_hash, dst, s->st);
+            s->stats.kernel_launches += 2;
+        }
         CU(cudaMemcpyAsync(s->h_snap[par], dst, sizeof(SketchState), cudaMemcpyDeviceToHost, s->st));
         CU(cudaEventRecord(s->ev_chunk[par], s->st));
         s->stats.kernel_launches += 4; s->stats.hash_launches++;
@@ -962,6 +996,22 @@ int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, 
                       std::vector<uint32_t> &keep);
 
 // Pinned host staging for result read-back (grown on demand).
+// Copy `n` bytes with a few host threads (the result slabs are large; one memcpy thread cannot keep
+// up with the kernel + D2H pipeline).
+static void parallel_memcpy(void *dst, const void *src, size_t n) {
+    const size_t min_part = 8u << 20;
+    unsigned parts = (unsigned)std::min<size_t>(4, n / min_part);
+    if (parts < 2) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n / parts + 63) & ~(size_t)63;
+    for (unsigned i = 1; i < parts; ++i) {
+        const size_t off = per * i, len = i + 1 == parts ? n - off : per;
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    memcpy(dst, src, per);
+    for (auto &t : th) t.join();
+}
+
 static int ensure_hres(fb2_sketcher *s, size_t bytes) {
     if (bytes <= s->h_res_cap) return FB2_OK;
     if (s->h_res) cudaFreeHost(s->h_res);
@@ -998,8 +1048,11 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
     out->counts = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
     out->extras = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
     if (!out->hashes || !out->counts || !out->extras) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
-    std::vector<unsigned long long> h_kmer(m), h_posx(m);
-    std::vector<uint8_t> bytes((size_t)m * stride);
+    // Entries that came through push() carry the caller's bytes (arena) and need their codes / position
+    // words on the host; everything else is expanded to ASCII on the device and copied as one block.
+    const bool has_arena = !s->arena.empty();
+    std::vector<unsigned long long> h_kmer(has_arena ? m : 0), h_posx(has_arena ? m : 0);
+    const uint8_t *h_bytes = nullptr;
     if (m) {
         TRY(s->sel_hash.ensure((size_t)m * 8)); TRY(s->sel_kmer.ensure((size_t)m * 8)); TRY(s->sel_posx.ensure((size_t)m * 8));
         TRY(s->sel_cnt.ensure((size_t)m * 4)); TRY(s->sel_ext.ensure((size_t)m * 4)); TRY(s->sel_bytes.ensure((size_t)m * stride));
@@ -1016,36 +1069,47 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
                            s->sel_kmer.as<unsigned long long>(), s->sel_posx.as<unsigned long long>(),
                            s->sel_bytes.as<uint8_t>(), s->st);
         s->stats.kernel_launches++;
-        // one pinned staging block: hash | kmer | posx | cnt | ext | bytes
-        const size_t o_hash = 0, o_kmer = (size_t)m * 8, o_posx = (size_t)m * 16, o_cnt = (size_t)m * 24,
-                     o_ext = (size_t)m * 28, o_bytes = (size_t)m * 32, total = o_bytes + (size_t)m * stride;
+        // one pinned staging block: hash | cnt | ext | bytes [| kmer | posx]
+        const size_t o_hash = 0, o_cnt = (size_t)m * 8, o_ext = (size_t)m * 12, o_bytes = (size_t)m * 16;
+        const size_t o_kmer = (o_bytes + (size_t)m * stride + 7) & ~(size_t)7, o_posx = o_kmer + (size_t)m * 8;
+        const size_t total = has_arena ? o_posx + (size_t)m * 8 : o_bytes + (size_t)m * stride;
         TRY(ensure_hres(s, total));
         CU(cudaMemcpyAsync(s->h_res + o_hash, s->sel_hash.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaMemcpyAsync(s->h_res + o_kmer, s->sel_kmer.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaMemcpyAsync(s->h_res + o_posx, s->sel_posx.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(s->h_res + o_cnt, s->sel_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(s->h_res + o_ext, s->sel_ext.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(s->h_res + o_bytes, s->sel_bytes.p, (size_t)m * stride, cudaMemcpyDeviceToHost, s->st));
+        if (has_arena) {
+            CU(cudaMemcpyAsync(s->h_res + o_kmer, s->sel_kmer.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
+            CU(cudaMemcpyAsync(s->h_res + o_posx, s->sel_posx.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
+        }
         CU(cudaStreamSynchronize(s->st));
         s->stats.d2h_bytes += total;
-        memcpy(out->hashes, s->h_res + o_hash, (size_t)m * 8);
-        memcpy(h_kmer.data(), s->h_res + o_kmer, (size_t)m * 8);
-        memcpy(h_posx.data(), s->h_res + o_posx, (size_t)m * 8);
-        memcpy(out->counts, s->h_res + o_cnt, (size_t)m * 4);
-        memcpy(out->extras, s->h_res + o_ext, (size_t)m * 4);
-        memcpy(bytes.data(), s->h_res + o_bytes, (size_t)m * stride);
+        parallel_memcpy(out->hashes, s->h_res + o_hash, (size_t)m * 8);
+        parallel_memcpy(out->counts, s->h_res + o_cnt, (size_t)m * 4);
+        parallel_memcpy(out->extras, s->h_res + o_ext, (size_t)m * 4);
+        h_bytes = s->h_res + o_bytes;
+        if (has_arena) {
+            memcpy(h_kmer.data(), s->h_res + o_kmer, (size_t)m * 8);
+            memcpy(h_posx.data(), s->h_res + o_posx, (size_t)m * 8);
+        }
     }
-    // k-mer bytes: expanded on the device; entries that came through push() carry the caller's bytes
     size_t ostride = stride;
-    for (uint32_t i = 0; i < m; ++i)
-        if (h_posx[i] & (1ULL << 8)) ostride = std::max(ostride, s->arena[(size_t)h_kmer[i]].size());
+    if (has_arena)
+        for (uint32_t i = 0; i < m; ++i)
+            if (h_posx[i] & (1ULL << 8)) ostride = std::max(ostride, s->arena[(size_t)h_kmer[i]].size());
     out->kmer_stride = (uint32_t)ostride;
-    out->kmers = (uint8_t *)calloc(std::max<size_t>(1, (size_t)m * ostride), 1);
-    if (!out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
-    for (uint32_t i = 0; i < m; ++i) {
-        uint8_t *dst = out->kmers + (size_t)i * ostride;
-        if (h_posx[i] & (1ULL << 8)) { const std::string &a = s->arena[(size_t)h_kmer[i]]; memcpy(dst, a.data(), a.size()); }
-        else memcpy(dst, bytes.data() + (size_t)i * stride, stride);
+    if (!has_arena) {
+        out->kmers = (uint8_t *)malloc(std::max<size_t>(1, (size_t)m * ostride));
+        if (!out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
+        if (m) parallel_memcpy(out->kmers, h_bytes, (size_t)m * stride);
+    } else {
+        out->kmers = (uint8_t *)calloc(std::max<size_t>(1, (size_t)m * ostride), 1);
+        if (!out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
+        for (uint32_t i = 0; i < m; ++i) {
+            uint8_t *dst = out->kmers + (size_t)i * ostride;
+            if (h_posx[i] & (1ULL << 8)) { const std::string &a = s->arena[(size_t)h_kmer[i]]; memcpy(dst, a.data(), a.size()); }
+            else memcpy(dst, h_bytes + (size_t)i * stride, stride);
+        }
     }
     out->seq_length = s->h_carry->total_bases + s->lines_bases;
     out->num_valid_kmers = s->total_kmers;
@@ -1180,22 +1244,6 @@ extern "C" int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size
 }
 static thread_local double g_dist_kernel_ms = 0.0;
 extern "C" double fb2_dist_last_kernel_ms(void) { return g_dist_kernel_ms; }
-
-// Copy `n` bytes with a few host threads (the result slabs are large; one memcpy thread cannot keep
-// up with the kernel + D2H pipeline).
-static void parallel_memcpy(void *dst, const void *src, size_t n) {
-    const size_t min_part = 8u << 20;
-    unsigned parts = (unsigned)std::min<size_t>(4, n / min_part);
-    if (parts < 2) { memcpy(dst, src, n); return; }
-    std::vector<std::thread> th;
-    const size_t per = (n / parts + 63) & ~(size_t)63;
-    for (unsigned i = 1; i < parts; ++i) {
-        const size_t off = per * i, len = i + 1 == parts ? n - off : per;
-        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
-    }
-    memcpy(dst, src, per);
-    for (auto &t : th) t.join();
-}
 
 extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
                                   double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device) {

@@ -46,6 +46,9 @@ void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride,
 void launch_select_keep(const unsigned long long *keys, uint32_t n, int scaled, unsigned long long size,
                         unsigned long long max_hash, SketchState *st, cudaStream_t s);
 void launch_commit_threshold(SketchState *st, cudaStream_t s);
+void launch_live_hist_refresh(TableView t, SketchState *st, uint32_t shift, uint32_t *live_bins, cudaStream_t s);
+void launch_soft_threshold(const uint32_t *live_bins, uint32_t shift, int scaled, unsigned long long size,
+                           unsigned long long max_hash, SketchState *st, cudaStream_t s);
 void launch_rebuild(const unsigned long long *keys, const uint32_t *slots, uint32_t keep, TableView from,
                     TableView to, SketchState *st, cudaStream_t s);
 void launch_export(const unsigned long long *keys, const uint32_t *slots, uint32_t keep, TableView t,

@@ -31,7 +31,13 @@ __device__ __forceinline__ uint32_t table_upsert(const TableView &t, unsigned lo
         if (cur == key) return slot;
         if (cur == EMPTY_KEY) {
             const unsigned long long prev = atomicCAS(&t.key[slot], EMPTY_KEY, key);
-            if (prev == EMPTY_KEY) { atomicAdd(&st->occupied, 1u); return slot; }
+            if (prev == EMPTY_KEY) {
+                atomicAdd(&st->occupied, 1u);
+                // live histogram of the table's keys (soft threshold updates between rebuilds)
+                unsigned int *lb = st->live_bins;
+                if (lb) atomicAdd(&lb[min(4095ULL, key >> st->hist_shift)], 1u);
+                return slot;
+            }
             if (prev == key) return slot;
         }
         slot = (slot + 1u) & maskc;
@@ -139,8 +145,8 @@ __global__ void gather_kernel(TableView t, SketchState *st, unsigned long long *
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > t.cap) return;
     bool occ;
-    if (i == t.cap) occ = st->has_max_key != 0u;
-    else occ = t.key[i] != EMPTY_KEY;
+    if (i == t.cap) occ = st->has_max_key != 0u && st->threshold == EMPTY_KEY;
+    else { const unsigned long long key = t.key[i]; occ = key != EMPTY_KEY && key <= st->threshold; }   // dead keys (above a soft threshold) stay behind
     const uint32_t m = __ballot_sync(__activemask(), occ);
     if (!occ) return;
     const uint32_t lane = threadIdx.x & 31u;
@@ -573,6 +579,21 @@ void launch_select_keep(const unsigned long long *keys, uint32_t n, int scaled, 
     select_keep_kernel<<<1, 1, 0, s>>>(keys, n, scaled, size, max_hash, st);
 }
 void launch_commit_threshold(SketchState *st, cudaStream_t s) { commit_threshold_kernel<<<1, 1, 0, s>>>(st); }
+// Rebuild the live histogram of table `t` with a new shift (after a rebuild / reset).
+__global__ void set_hist_shift_kernel(SketchState *st, uint32_t shift) { st->hist_shift = shift; }
+void launch_live_hist_refresh(TableView t, SketchState *st, uint32_t shift, uint32_t *live_bins, cudaStream_t s) {
+    cudaMemsetAsync(live_bins, 0, PRUNE_BINS * sizeof(uint32_t), s);
+    set_hist_shift_kernel<<<1, 1, 0, s>>>(st, shift);
+    const uint32_t blocks = min(cdiv(t.cap + 1, 256), 592u);
+    table_hist_kernel<<<blocks, 256, 0, s>>>(t, st, shift, live_bins);
+}
+// Soft threshold update: lower the admission threshold to the smallest bin boundary that keeps >= size
+// keys, from the live histogram alone (no rebuild; entries above it simply stop being updated).
+void launch_soft_threshold(const uint32_t *live_bins, uint32_t shift, int scaled, unsigned long long size,
+                           unsigned long long max_hash, SketchState *st, cudaStream_t s) {
+    table_select_kernel<<<1, 1024, 0, s>>>(live_bins, shift, scaled, size, max_hash, st);
+    commit_threshold_kernel<<<1, 1, 0, s>>>(st);
+}
 void launch_rebuild(const unsigned long long *keys, const uint32_t *slots, uint32_t keep, TableView from,
                     TableView to, SketchState *st, cudaStream_t s) {
     launch_table_clear(to, s);
