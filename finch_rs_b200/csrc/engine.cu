@@ -90,6 +90,9 @@ struct fb2_sketcher {
     uint64_t size = 0, max_hash = 0;
     int k = 0;
     cudaStream_t st = nullptr, copy_st = nullptr;
+    cudaStream_t st2 = nullptr;      // absorb stream: log -> table of chunk c overlaps the parse kernels of chunk c+1
+    cudaEvent_t ev_hash[2]{}, ev_st2 = nullptr;
+    bool st2_dirty = false;          // work was queued on st2 since the last join
     bool own_stream = false;
     cudaEvent_t ev_h2d[2]{}, ev_rawfree[2]{}, ev_t0 = nullptr, ev_t1 = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
     bool rawfree_pending[2] = {false, false};
@@ -147,7 +150,16 @@ static LogView log_view(fb2_sketcher *s, int par) {
     return l;
 }
 static inline LaunchSlot *dev_slot(fb2_sketcher *s, int par) { return &((SketchState *)s->d_state.p)->slot[par]; }
+// Everything queued on the absorb stream so far is ordered before whatever follows on the main stream.
+static int join_absorb_stream(fb2_sketcher *s) {
+    if (!s->st2_dirty) return FB2_OK;
+    CU(cudaEventRecord(s->ev_st2, s->st2));
+    CU(cudaStreamWaitEvent(s->st, s->ev_st2, 0));
+    s->st2_dirty = false;
+    return FB2_OK;
+}
 static int pull_state(fb2_sketcher *s) {  // device -> pinned mirrors, then wait
+    TRY(join_absorb_stream(s));           // every host decision starts here: the table must be quiescent
     CU(cudaMemcpyAsync(s->h_state, s->d_state.p, sizeof(SketchState), cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(s->h_carry, s->d_carry.p, sizeof(ParseCarry), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
@@ -254,6 +266,9 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
     if (p->stream) { s->st = (cudaStream_t)p->stream; s->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking)); s->own_stream = true; }
     CU(cudaStreamCreateWithFlags(&s->copy_st, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s->ev_st2, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&s->ev_hash[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s->ev_rawfree[i], cudaEventDisableTiming));
@@ -303,6 +318,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     cudaSetDevice(s->device);
     if (s->st) cudaStreamSynchronize(s->st);
     if (s->copy_st) cudaStreamSynchronize(s->copy_st);
+    if (s->st2) cudaStreamSynchronize(s->st2);
     for (int i = 0; i < 2; ++i) {
         s->d_raw[i].release(); s->tab[i].release();
         if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
@@ -330,6 +346,9 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->own_stream && s->st) cudaStreamDestroy(s->st);
     if (s->copy_st) cudaStreamDestroy(s->copy_st);
+    if (s->st2) cudaStreamDestroy(s->st2);
+    if (s->ev_st2) cudaEventDestroy(s->ev_st2);
+    for (int i = 0; i < 2; ++i) if (s->ev_hash[i]) cudaEventDestroy(s->ev_hash[i]);
     delete s;
 }
 
@@ -338,6 +357,8 @@ extern "C" int fb2_sketcher_reset(fb2_sketcher *s) {
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->st));
     CU(cudaStreamSynchronize(s->copy_st));
+    CU(cudaStreamSynchronize(s->st2));
+    s->st2_dirty = false;
     return reset_sketch_state(s);
 }
 
@@ -679,18 +700,28 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     if (s->steady && !s->timing && positions <= (double)s->next_launch) {
         // asynchronous: hash the whole chunk, let the device decide about absorbing, snapshot the
         // state; the host looks at the outcome while the next chunk is already running
+        // main stream: parse (above) and hash; absorb stream: log -> table, soft threshold, snapshot.
+        // The absorb of this chunk then runs under the parse kernels of the next one (the persistent
+        // hash kernel fills every SM, the latency-bound absorb kernels fit beside phase / pack).
         LaunchSlot *slot = dev_slot(s, par);
+        cudaStream_t ab = getenv("FB2_NO_ABSORB_STREAM") ? s->st : s->st2;
         CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
+        launch_note_chunk_syms(slot, dc, s->st);
         launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, total_blocks, s->d_rcount[par].as<uint32_t>(), ord_base, dst,
                     slot, log_view(s, par), s->prm.hash_seed, s->st);
-        launch_absorb_guarded(log_view(s, par), slot, s->tab[s->cur].view(), dst, dc, s->log_cap / 4, s->st);
+        if (ab != s->st) {
+            CU(cudaEventRecord(s->ev_hash[par], s->st));
+            CU(cudaStreamWaitEvent(ab, s->ev_hash[par], 0));
+            s->st2_dirty = true;
+        }
+        launch_absorb_guarded(log_view(s, par), slot, s->tab[s->cur].view(), dst, dc, s->log_cap / 4, ab);
         if (s->size > 0 && !getenv("FB2_NO_SOFT_THRESHOLD")) {   // keep the admission threshold tight between rebuilds
-            launch_soft_threshold(s->d_live_bins.as<uint32_t>(), s->live_shift, s->scaled ? 1 : 0, s->size, s->max_hash, dst, s->st);
+            launch_soft_threshold(s->d_live_bins.as<uint32_t>(), s->live_shift, s->scaled ? 1 : 0, s->size, s->max_hash, dst, ab);
             s->stats.kernel_launches += 2;
         }
-        CU(cudaMemcpyAsync(s->h_snap[par], dst, sizeof(SketchState), cudaMemcpyDeviceToHost, s->st));
-        CU(cudaEventRecord(s->ev_chunk[par], s->st));
-        s->stats.kernel_launches += 4; s->stats.hash_launches++;
+        CU(cudaMemcpyAsync(s->h_snap[par], dst, sizeof(SketchState), cudaMemcpyDeviceToHost, ab));
+        CU(cudaEventRecord(s->ev_chunk[par], ab));
+        s->stats.kernel_launches += 5; s->stats.hash_launches++;
         s->stats.d2h_bytes += sizeof(SketchState);
         s->pend[par].valid = true; s->pend[par].g = g; s->pend[par].ord_base = ord_base;
         TRY(settle(s, par ^ 1));   // the previous chunk, while this one runs

@@ -25,6 +25,7 @@ void launch_absorb(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchSta
 void launch_absorb_band(LogView log, uint32_t n, TableView t, SketchState *st, unsigned long long lo, int use_lo,
                         unsigned long long hi, cudaStream_t s);
 void launch_log_hist(LogView log, uint32_t n, const SketchState *st, uint32_t shift, uint32_t *bins, cudaStream_t s);
+void launch_note_chunk_syms(LaunchSlot *slot, const ParseCarry *carry, cudaStream_t s);
 void launch_absorb_guarded(LogView log, LaunchSlot *slot, TableView t, SketchState *st, const ParseCarry *carry,
                            uint32_t expect, cudaStream_t s);
 void launch_table_clear(TableView t, cudaStream_t s);

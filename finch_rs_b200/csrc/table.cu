@@ -100,8 +100,9 @@ __global__ void absorb_decide_kernel(LaunchSlot *slot, const SketchState *st, co
     if (cnt > log_cap) d = DECIDE_OVERFLOW;
     else if ((unsigned long long)st->occupied + cnt > (unsigned long long)(table_cap / 4) * 3) d = DECIDE_FULL;
     slot->decision = d;
-    slot->chunk_syms = carry->chunk_syms;
+    (void)carry;   // chunk_syms is recorded by note_chunk_syms_kernel on the parse stream (the carry may already belong to the next chunk)
 }
+__global__ void note_chunk_syms_kernel(LaunchSlot *slot, const ParseCarry *carry) { slot->chunk_syms = carry->chunk_syms; }
 __global__ void absorb_count_guarded_kernel(LogView log, const LaunchSlot *slot, TableView t, SketchState *st) {
     if (slot->decision != DECIDE_GO) return;
     const uint32_t n = slot->log_count, stride = gridDim.x * blockDim.x;
@@ -511,6 +512,7 @@ void launch_log_hist(LogView log, uint32_t n, const SketchState *st, uint32_t sh
     cudaMemsetAsync(bins, 0, PRUNE_BINS * sizeof(uint32_t), s);
     if (n) log_hist_kernel<<<min(cdiv(n, 256), 1184u), 256, 0, s>>>(log, n, st, shift, bins);
 }
+void launch_note_chunk_syms(LaunchSlot *slot, const ParseCarry *carry, cudaStream_t s) { note_chunk_syms_kernel<<<1, 1, 0, s>>>(slot, carry); }
 void launch_absorb_guarded(LogView log, LaunchSlot *slot, TableView t, SketchState *st, const ParseCarry *carry,
                            uint32_t expect, cudaStream_t s) {
     absorb_decide_kernel<<<1, 1, 0, s>>>(slot, st, carry, t.cap, log.cap);
