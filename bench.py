@@ -338,7 +338,7 @@ def main():
                      "avg_launch_ms": hash_ms / max(1, hash_launches), "launches_per_step": hash_launches / 2,
                      "hash_kernel_share_of_step": (hash_ms / 2) / (ms_res / args.steps),
                      "parse_kernels_ms_per_step": parse_ms / 2,
-                     "note": "ALU-pipe-bound, not HBM-bound (~150 SASS instr per k-mer, ALU pipe 81% busy in ncu); see DESIGN.md"},
+                     "note": "integer-issue-bound, not HBM-bound: ~100 SASS instr per k-mer split over the two half-rate integer pipes (ALU ~60%, IMAD ~60% busy, issue ~70% in ncu); see DESIGN.md"},
         "bit_exact": None,
         "aux": {"prunes_per_step": stats_res["prunes"] / args.steps, "chunks_per_step": stats_res["chunks"] / args.steps,
                 "hash_launches_per_step": stats_res["hash_launches"] / args.steps,

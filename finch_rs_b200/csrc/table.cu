@@ -19,7 +19,10 @@ __device__ __forceinline__ uint32_t home_slot(unsigned long long key, uint32_t s
 
 // Find-or-insert `key`; returns its slot.  The table always has free slots (host guarantees
 // occupied + batch <= 3/4 cap), so the probe terminates.
-__device__ __forceinline__ uint32_t table_upsert(const TableView &t, unsigned long long key, SketchState *st) {
+// `inserted` is set when the key is new: the caller adds the warp's new keys to st->occupied with ONE
+// atomic (commit_inserted) -- a per-key atomic on that single address serialises large absorbs.
+__device__ __forceinline__ uint32_t table_upsert(const TableView &t, unsigned long long key, SketchState *st, bool &inserted) {
+    inserted = false;
     if (key == EMPTY_KEY) {                       // u64::MAX cannot be stored in a slot: side slot
         if (atomicExch(&st->has_max_key, 1u) == 0u) { /* first use */ }
         return t.cap;
@@ -32,7 +35,7 @@ __device__ __forceinline__ uint32_t table_upsert(const TableView &t, unsigned lo
         if (cur == EMPTY_KEY) {
             const unsigned long long prev = atomicCAS(&t.key[slot], EMPTY_KEY, key);
             if (prev == EMPTY_KEY) {
-                atomicAdd(&st->occupied, 1u);
+                inserted = true;
                 // live histogram of the table's keys (soft threshold updates between rebuilds)
                 unsigned int *lb = st->live_bins;
                 if (lb) atomicAdd(&lb[min(4095ULL, key >> st->hist_shift)], 1u);
@@ -42,6 +45,11 @@ __device__ __forceinline__ uint32_t table_upsert(const TableView &t, unsigned lo
         }
         slot = (slot + 1u) & maskc;
     }
+}
+// Called by every lane of a (converged) warp: one atomic for all the warp's new keys.
+__device__ __forceinline__ void commit_inserted(SketchState *st, bool inserted) {
+    const uint32_t m = __ballot_sync(0xffffffffu, inserted);
+    if (m && (threadIdx.x & 31u) == (uint32_t)(__ffs(m) - 1)) atomicAdd(&st->occupied, (unsigned int)__popc(m));
 }
 __device__ __forceinline__ uint32_t table_find(const TableView &t, unsigned long long key) {
     if (key == EMPTY_KEY) return t.cap;
@@ -63,13 +71,16 @@ __device__ __forceinline__ bool in_band(const Band &b, unsigned long long key) {
     return key <= b.hi && (!b.use_lo || key > b.lo);
 }
 __global__ void absorb_count_kernel(LogView log, uint32_t i0, uint32_t i1, TableView t, SketchState *st, Band band) {
-    const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= i1) return;
-    const unsigned long long px = log.posx[i];
-    if (px == ~0ULL) return;                      // unused slot of a warp's reservation
-    const unsigned long long key = log.hash[i];
-    if (key > st->threshold || !in_band(band, key)) return;
-    const uint32_t slot = table_upsert(t, key, st);
+    const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;   // no early return: the warp votes below
+    unsigned long long px = ~0ULL, key = 0;
+    bool valid = i < i1;
+    if (valid) { px = log.posx[i]; valid = px != ~0ULL; }            // ~0: unused slot of a warp's reservation
+    if (valid) { key = log.hash[i]; valid = key <= st->threshold && in_band(band, key); }
+    bool ins = false;
+    uint32_t slot = 0;
+    if (valid) slot = table_upsert(t, key, st, ins);
+    commit_inserted(st, ins);
+    if (!valid) return;
     atomicAdd(&t.cnt[slot], 1ULL);
     const unsigned long long extra = px & 0xFFULL;
     if (extra) atomicAdd(&t.ext[slot], extra);
@@ -107,12 +118,19 @@ __global__ void absorb_count_guarded_kernel(LogView log, const LaunchSlot *slot,
     if (slot->decision != DECIDE_GO) return;
     const uint32_t n = slot->log_count, stride = gridDim.x * blockDim.x;
     const unsigned long long thr = st->threshold;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned long long px = log.posx[i];
-        if (px == ~0ULL) continue;                // unused slot of a warp's reservation
-        const unsigned long long key = log.hash[i];
-        if (key > thr) continue;
-        const uint32_t s = table_upsert(t, key, st);
+    const uint32_t lane = threadIdx.x & 31u;
+    // warp-uniform trip count: every lane reaches the vote in commit_inserted
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += stride) {
+        const uint32_t i = base + lane;
+        unsigned long long px = ~0ULL, key = 0;
+        bool valid = i < n;
+        if (valid) { px = log.posx[i]; valid = px != ~0ULL; }        // ~0: unused slot of a warp's reservation
+        if (valid) { key = log.hash[i]; valid = key <= thr; }
+        bool ins = false;
+        uint32_t s = 0;
+        if (valid) s = table_upsert(t, key, st, ins);
+        commit_inserted(st, ins);
+        if (!valid) continue;
         atomicAdd(&t.cnt[s], 1ULL);
         const unsigned long long extra = px & 0xFFULL;
         if (extra) atomicAdd(&t.ext[s], extra);
@@ -446,10 +464,12 @@ __global__ void commit_threshold_kernel(SketchState *st) { st->threshold = st->n
 __global__ void rebuild_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ slots,
                                uint32_t keep, TableView from, TableView to, SketchState *st) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ins = false;
+    uint32_t dst = 0;
+    if (i < keep) dst = table_upsert(to, keys[i], st, ins);
+    commit_inserted(st, ins);
     if (i >= keep) return;
-    const unsigned long long key = keys[i];
     const uint32_t src = slots[i];
-    const uint32_t dst = table_upsert(to, key, st);
     to.cnt[dst] = from.cnt[src]; to.ext[dst] = from.ext[src];
     to.posx[dst] = from.posx[src]; to.kmer[dst] = from.kmer[src];
 }
