@@ -13,6 +13,16 @@
 #include "common.cuh"
 #include "device_types.cuh"
 
+#ifndef FMIX_HI_A
+#define FMIX_HI_A 1
+#endif
+#ifndef FMIX_HI_B
+#define FMIX_HI_B 1
+#endif
+#ifndef MUL5_LEA
+#define MUL5_LEA 1
+#endif
+
 namespace fb2 {
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -77,10 +87,15 @@ __device__ __forceinline__ U2 rotl_u2(U2 x) {                             // 2 S
     else { d.hi = __funnelshift_l(x.hi, x.lo, R - 32); d.lo = __funnelshift_l(x.lo, x.hi, R - 32); }
     return d;
 }
+// k ^= k >> 33 touches the low word only.  HI_FIRST picks which of the three ">> 1" go through IMAD.HI
+// (FMA pipe, 4 issue cycles) instead of SHF (ALU pipe, 2): measured pipe rates on B200
+// (tools/pipe_rates.cu): LOP3/SHF/PRMT/IADD3/IMAD 0.5 per clock per sub-partition, IMAD.WIDE and
+// IMAD.HI 0.25.  The mix below keeps the two pipes level.
+template <int NHI>
 __device__ __forceinline__ U2 fmix_u2(U2 k) {
-    k.lo ^= shr1_fma(k.hi);  k = mul_u2<0xff51afd7ed558ccdULL>(k);       // k ^= k >> 33 touches the low word only
-    k.lo ^= shr1_fma(k.hi);  k = mul_u2<0xc4ceb9fe1a85ec53ULL>(k);
-    k.lo ^= shr1_fma(k.hi);
+    k.lo ^= (NHI >= 1 ? shr1_fma(k.hi) : (k.hi >> 1));  k = mul_u2<0xff51afd7ed558ccdULL>(k);
+    k.lo ^= (NHI >= 2 ? shr1_fma(k.hi) : (k.hi >> 1));  k = mul_u2<0xc4ceb9fe1a85ec53ULL>(k);
+    k.lo ^= (NHI >= 3 ? shr1_fma(k.hi) : (k.hi >> 1));
     return k;
 }
 __device__ __forceinline__ uint32_t byte_of(uint32_t x, int n) { return __byte_perm(x, 0u, 0x4440u + (uint32_t)n); }
@@ -126,7 +141,12 @@ __device__ __forceinline__ U2 add_one(U2 a, U2 b, uint32_t /*one*/) {   // a + b
     return t;
 }
 __device__ __forceinline__ U2 mul5add_r(U2 x, U2 c) {                     // x * 5 + c
-    const uint64_t s = (((uint64_t)x.hi << 32) | x.lo) * 5ULL + (((uint64_t)c.hi << 32) | c.lo);
+    const uint64_t v = ((uint64_t)x.hi << 32) | x.lo;
+#if MUL5_LEA
+    const uint64_t s = (v << 2) + v + (((uint64_t)c.hi << 32) | c.lo);       // LEA + LEA.HI.X (ALU) instead of IMAD.WIDE (4 FMA cycles)
+#else
+    const uint64_t s = v * 5ULL + (((uint64_t)c.hi << 32) | c.lo);
+#endif
     U2 t; t.lo = (uint32_t)s; t.hi = (uint32_t)(s >> 32);
     return t;
 }
@@ -196,7 +216,7 @@ __device__ __forceinline__ U2 murmur_kmer_h1_lut(U2 codes, U2 seed, const MulLut
     }
     h1.lo ^= (uint32_t)K; h2.lo ^= (uint32_t)K;
     h1 = add_one(h1, h2, L.one); h2 = add_one(h2, h1, L.one);
-    h1 = fmix_u2(h1); h2 = fmix_u2(h2);
+    h1 = fmix_u2<FMIX_HI_A>(h1); h2 = fmix_u2<FMIX_HI_B>(h2);
     return add_one(h1, h2, L.one);
 }
 
