@@ -134,6 +134,29 @@ __device__ __forceinline__ uint32_t block_exscan_add(uint32_t v, uint32_t *sh8, 
     total = tot;
     return base + x - v;
 }
+// Same for four 16-bit counters packed into 64 bits (fields must not overflow: <= 4096 each here).
+__device__ __forceinline__ unsigned long long block_exscan_add64(unsigned long long v, unsigned long long *sh8l,
+                                                                 unsigned long long &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long n = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += n;
+    }
+    __syncthreads();  // protect sh8l from a previous use
+    if (lane == 31) sh8l[wid] = x;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < TILE_THREADS / 32; ++i) {
+        const unsigned long long s = sh8l[i];
+        if (i < wid) base += s;
+        tot += s;
+    }
+    total = tot;
+    return base + x - v;
+}
 __device__ __forceinline__ uint32_t block_exscan_max(uint32_t v, uint32_t *sh8, uint32_t &total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t x = v;
@@ -453,8 +476,11 @@ __device__ __forceinline__ void pack_exact(const uint8_t *__restrict__ raw, cons
 // assumes what normalize(false) would remove inside a sequence line is at most one CR at its end;
 // a blank or CR anywhere else, or more than PB_NLCAP newlines in a batch, makes the block redo its
 // supertile with pack_exact.
-constexpr int PB_BYTES = 2 * TILE_BYTES;
+constexpr int PB_TILES = 4;                        // tiles per batch (16 bytes per thread each)
+constexpr int PB_BYTES = PB_TILES * TILE_BYTES;    // <= 16 KiB: piece lengths must fit 15 bits below the break flag
 constexpr int PB_NLCAP = 1535;
+static_assert(PB_TILES == 2 || PB_TILES == 4, "newline counts are scanned as 16-bit fields of one 64-bit word");
+static_assert(PB_BYTES < 0x8000, "e_len keeps a flag in bit 15");
 
 __device__ __forceinline__ void ones128(uint32_t nbytes, uint64_t &lo, uint64_t &hi) {   // nbytes in 0..16
     lo = nbytes >= 8u ? ~0ULL : ((1ULL << (8u * nbytes)) - 1ULL);
@@ -495,15 +521,15 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
     const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(s_rawbuf);
     bool declined = false;
 
-    uint4 nextv[2];
+    uint4 nextv[PB_TILES];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) nextv[p] = fetch_raw(raw, B0 + (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u, B1);
+    for (int p = 0; p < PB_TILES; ++p) nextv[p] = fetch_raw(raw, B0 + (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u, B1);
     for (uint32_t b = B0; b < B1; b += PB_BYTES) {
         const uint32_t blen = min((uint32_t)PB_BYTES, B1 - b);
         // ---- 1. stage the batch, newline masks --------------------------------------------------
-        uint32_t nlm[2];
+        uint32_t nlm[PB_TILES];
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < PB_TILES; ++p) {
             const uint32_t po = (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u;
             const uint4 curv = nextv[p];
             if (b + PB_BYTES < B1) nextv[p] = fetch_raw(raw, b + PB_BYTES + po, B1);   // next batch in flight
@@ -518,13 +544,19 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
             rawb[-2] = (uint8_t)(b >= 2u ? raw[b - 2] : (b == 1u ? cprev1 : cprev2));
         }
         // ---- 2. newline positions ---------------------------------------------------------------
-        uint32_t tot;
-        const uint32_t ex = block_exscan_add((uint32_t)__popc(nlm[0]) | ((uint32_t)__popc(nlm[1]) << 16), sh8, tot);
-        const uint32_t tot0 = tot & 0xFFFFu, N = tot0 + (tot >> 16);
-        if (N > (uint32_t)PB_NLCAP) { declined = true; break; }   // uniform
+        unsigned long long cnt4 = 0, tot4;
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            uint32_t m = nlm[p], at = p ? tot0 + (ex >> 16) : (ex & 0xFFFFu);
+        for (int p = 0; p < PB_TILES; ++p) cnt4 |= (unsigned long long)__popc(nlm[p]) << (16 * p);
+        const unsigned long long ex4 = block_exscan_add64(cnt4, sh8l, tot4);
+        uint32_t N = 0;
+#pragma unroll
+        for (int p = 0; p < PB_TILES; ++p) N += (uint32_t)(tot4 >> (16 * p)) & 0xFFFFu;
+        if (N > (uint32_t)PB_NLCAP) { declined = true; break; }   // uniform
+        uint32_t before = 0;                                      // newlines of the pieces in front
+#pragma unroll
+        for (int p = 0; p < PB_TILES; ++p) {
+            uint32_t m = nlm[p], at = before + ((uint32_t)(ex4 >> (16 * p)) & 0xFFFFu);
+            before += (uint32_t)(tot4 >> (16 * p)) & 0xFFFFu;
             const uint32_t po = (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u;
             while (m) {
                 s_nl[at++] = (uint16_t)(po + (uint32_t)(__ffs(m) - 1));
