@@ -225,6 +225,66 @@ def test_multi_chunk_stream(fb, oracle, monkeypatch):
         assert_same(s.to_arrays(), ovec, 21)
 
 
+@pytest.mark.parametrize("kind,size,scale", [("mash", 20000, 0.0), ("scaled", 1000, 0.01), ("scaled", 0, 0.02)])
+def test_many_chunks_steady_state(fb, oracle, monkeypatch, kind, size, scale):
+    """~40 chunks of 1 MiB: most of the stream runs through the asynchronous steady-state path (absorb on
+    its own stream under the next chunk's parse kernels, soft threshold updates from the live table
+    histogram after every chunk, occasional rebuilds).  High coverage so counts, strand counts and
+    first-occurrence k-mers of hot keys accumulate across many chunks."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    genome = fb.synth_genome(150_000, 21)
+    data, nb = fb.synth_fastq(genome, 130_000, 150, 0.01, 23)
+    data = data.tobytes()
+    assert len(data) > 38 * (1 << 20)
+    ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, 21, 0, scale or 0.001)
+    gres, gtotals, _ = gpu_sketch(fb, data, kind, size, 21, 0, scale or 0.001)
+    assert ototals[0] == nb and gtotals == ototals
+    assert_same(gres, ovec, 21)
+    assert int(ovec["counts"].max()) > 50
+    # the A/B switches used for the measurements give the same sketch
+    for var in ("FB2_NO_SOFT_THRESHOLD", "FB2_NO_ABSORB_STREAM"):
+        monkeypatch.setenv(var, "1")
+        gres2, gtotals2, _ = gpu_sketch(fb, data, kind, size, 21, 0, scale or 0.001)
+        monkeypatch.delenv(var)
+        assert gtotals2 == ototals
+        assert_same(gres2, ovec, 21)
+
+
+def test_sketch_files_many_workers(fb, oracle, tmp_path, monkeypatch):
+    """fb2_sketch_files with more files than worker handles, mixed formats and sizes, twice (the second
+    call re-uses the pooled handles): results in input order, identical to one-by-one sketching."""
+    rng = np.random.default_rng(77)
+    paths, datas = [], []
+    for i in range(21):
+        if i % 3 == 2:
+            d = gen.fastq(rng, n_records=int(rng.integers(20, 400)), max_len=200)
+        else:
+            d = gen.fasta(rng, n_records=int(rng.integers(1, 4)), max_len=int(rng.integers(2000, 60000)), width=int(rng.integers(40, 90)))
+        p = tmp_path / f"w{i}.{'fq' if i % 3 == 2 else 'fa'}"
+        p.write_bytes(d)
+        paths.append(str(p)); datas.append(d)
+    sp = fb.SketchParams.mash(2000, 100, True, 21, 0)
+    fp = fb.FilterParams(None, (None, None), 0.21, 0.1)
+    want = []
+    for d in datas:
+        rc, osk = oracle.sketch_stream(d, oracle.mash_params(2000, 100, True, 21, 0), oracle.make_filter(None, (None, None), 0.21, 0.1))
+        assert rc == oracle.OK
+        want.append(osk)
+    for workers in ("4", "4", "1", "16"):
+        monkeypatch.setenv("FB2_FILE_WORKERS", workers)
+        sks = fb.sketch_files(paths, sp, fp)
+        for pth, osk, sk in zip(paths, want, sks):
+            assert sk.name == pth
+            assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+            assert np.array_equal(sk.extra_counts, osk["extras"])
+            assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+    # one bad file fails the whole call with its message (lib.rs:29-49 returns the first error)
+    with pytest.raises(fb.FinchError) as ei:
+        fb.sketch_files(paths[:5] + [str(tmp_path / "missing.fa")] + paths[5:], sp, fp)
+    assert "No such file or directory" in str(ei.value)
+    fb.lib().fb2_sketch_files_release_pool()
+
+
 def test_errors(fb):
     sp = fb.SketchParams.mash(10, 10, False, 21, 0)
     with pytest.raises(fb.FinchError) as e:
