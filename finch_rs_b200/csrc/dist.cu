@@ -66,26 +66,34 @@ dist_all_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *_
 
 
 // ---- tiled all-pairs kernel -------------------------------------------------------------------------
-// A block keeps DT_TQ query sketches in shared memory, each as (a) its sorted hash list and (b) an
-// open-addressing table of 16-bit entries (6-bit fingerprint | 10-bit index into the sorted list,
-// load factor <= 1/8), and streams reference sketches past them: a warp takes one reference, every
-// lane probes its 1/32 of the reference's hashes against all DT_TQ tables.  A reference row is read
-// once per DT_TQ pairs; a membership test is ~1 shared-memory load instead of a 10-step binary
-// search.  Murmur outputs are uniform in their low bits (a bottom-s sketch constrains the top bits
-// only), so slot and fingerprint come straight from bits [0,13) and [13,19) of the hash.
+// A block keeps DT_TQ query sketches in shared memory, each as (a) its sorted hash list and (b) a
+// CUCKOO table of 32-bit entries (22-bit fingerprint | 10-bit index into the sorted list; two hash
+// functions, one slot each, load <= 1/4), and streams reference sketches past them: a warp takes one
+// reference, every lane probes its 1/32 of the reference's hashes against all DT_TQ tables.  A
+// membership test is exactly two independent shared-memory loads (no probe chains, so the lanes of a
+// warp never wait for the longest chain among them); the key itself is only read when a fingerprint
+// matches.  A reference row is read once per DT_TQ pairs.
+// Murmur outputs are uniform in every bit slice (a bottom-s sketch constrains the top bits only):
+// slot 1 = bits [0,12), slot 2 = bits [12,24), fingerprint = bits [24,46).  A query whose keys cannot be
+// placed (adversarial, non-random hashes) is flagged and answered by binary search instead.
 // i and j follow from the closed form of the merge loop as in pair_warp.
 constexpr int DT_TQ = 9;                 // query sketches per block
-constexpr int DT_SLOTS = 8192;           // table slots per query (uint16_t each)
+constexpr int DT_SLOTS = 4096;           // cuckoo slots per query (uint32_t each)
 constexpr int DT_MAXLEN = 1023;          // longest query sketch the tiled kernel takes
 constexpr int DT_WARPS = 16;
-constexpr uint32_t DT_EMPTY = 0xFFFFu;
+constexpr int DT_MAXKICK = 96;
+constexpr uint32_t DT_EMPTY = 0xFFFFFFFFu;   // fingerprint all ones, index 1023 (never a valid index)
 struct DistTileSmem {
-    unsigned long long keys[DT_TQ][DT_MAXLEN + 1];   // sorted hashes; [1023] is never a valid index
-    uint16_t tab[DT_TQ][DT_SLOTS];
+    unsigned long long keys[DT_TQ][DT_MAXLEN + 1];   // sorted hashes; [1023] = 0: what an EMPTY entry points at
+    uint32_t tab[DT_TQ][DT_SLOTS];
     unsigned long long maxa[DT_TQ];
     uint32_t na[DT_TQ];
     uint32_t lb[DT_TQ];                               // scaled: #{a < max_hash}
+    uint32_t slow_mask;                               // queries whose cuckoo build failed
 };
+__device__ __forceinline__ uint32_t dt_h1(unsigned long long k) { return (uint32_t)k & (DT_SLOTS - 1); }
+__device__ __forceinline__ uint32_t dt_h2(unsigned long long k) { return (uint32_t)(k >> 12) & (DT_SLOTS - 1); }
+__device__ __forceinline__ uint32_t dt_fp(unsigned long long k) { return (uint32_t)(k >> 24) & 0x3FFFFFu; }
 
 __device__ __forceinline__ uint32_t lower_bound_sm(const unsigned long long *a, uint32_t n, unsigned long long v) {
     uint32_t lo = 0, hi = n;
@@ -105,8 +113,9 @@ dist_tile_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *
     const uint32_t r_begin = blockIdx.y * r_chunk, r_end = min(n_sk, r_begin + r_chunk);
     // ---- build the query tables ----
     {
-        uint32_t *t32 = reinterpret_cast<uint32_t *>(&S.tab[0][0]);
-        for (uint32_t i = tid; i < DT_TQ * DT_SLOTS / 2; i += blockDim.x) t32[i] = 0xFFFFFFFFu;
+        uint32_t *t32 = &S.tab[0][0];
+        for (uint32_t i = tid; i < DT_TQ * DT_SLOTS; i += blockDim.x) t32[i] = DT_EMPTY;
+        if (tid == 0) S.slow_mask = 0;
         for (uint32_t q = 0; q < DT_TQ; ++q) {
             const uint32_t len = q < nq ? lens[qb + q] : 0u;
             const unsigned long long *A = hashes + (uint64_t)(qb + (q < nq ? q : 0u)) * stride;
@@ -121,15 +130,23 @@ dist_tile_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *
         for (uint32_t q = 0; q < nq; ++q) {
             const uint32_t len = S.na[q];
             for (uint32_t x = tid; x < len; x += blockDim.x) {
-                const unsigned long long h = S.keys[q][x];
-                uint32_t s = (uint32_t)h & (DT_SLOTS - 1);
-                const unsigned short val = (unsigned short)(((((uint32_t)h >> 13) & 63u) << 10) | x);
-                while (atomicCAS(&S.tab[q][s], (unsigned short)DT_EMPTY, val) != (unsigned short)DT_EMPTY)
-                    s = (s + 1) & (DT_SLOTS - 1);
+                // cuckoo insertion: swap into the slot, carry the evicted entry to its other slot
+                unsigned long long k = S.keys[q][x];
+                uint32_t cur = (dt_fp(k) << 10) | x, slot = dt_h1(k);
+                int kick = 0;
+                for (; kick < DT_MAXKICK; ++kick) {
+                    const uint32_t old = atomicExch(&S.tab[q][slot], cur);
+                    if (old == DT_EMPTY) break;
+                    cur = old;
+                    k = S.keys[q][old & 1023u];
+                    slot = (slot == dt_h1(k)) ? dt_h2(k) : dt_h1(k);
+                }
+                if (kick == DT_MAXKICK) atomicOr(&S.slow_mask, 1u << q);   // an entry was dropped: table unusable
             }
         }
         __syncthreads();
     }
+    const uint32_t slow_mask = S.slow_mask;
     // ---- stream the references ----
     for (uint32_t r = r_begin + warp; r < r_end; r += DT_WARPS) {
         const uint32_t nb = lens[r];
@@ -139,16 +156,25 @@ dist_tile_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *
         for (int q = 0; q < DT_TQ; ++q) cnt[q] = 0;
         for (uint32_t x = lane; x < nb; x += 32) {
             const unsigned long long b = B[x];
-            const uint32_t s0 = (uint32_t)b & (DT_SLOTS - 1), fp = ((uint32_t)b >> 13) & 63u;
+            const uint32_t s1 = dt_h1(b), s2 = dt_h2(b), fp = dt_fp(b);
+            uint32_t e1[DT_TQ], e2[DT_TQ];
+#pragma unroll
+            for (int q = 0; q < DT_TQ; ++q) { e1[q] = S.tab[q][s1]; e2[q] = S.tab[q][s2]; }   // 2 * DT_TQ loads in flight
 #pragma unroll
             for (int q = 0; q < DT_TQ; ++q) {
-                uint32_t s = s0;
-                while (true) {
-                    const uint32_t e = S.tab[q][s];
-                    if (e == DT_EMPTY) break;
-                    if ((e >> 10) == fp && S.keys[q][e & 1023u] == b) { ++cnt[q]; break; }
-                    s = (s + 1) & (DT_SLOTS - 1);
+                const bool m1 = (e1[q] >> 10) == fp, m2 = (e2[q] >> 10) == fp;
+                if ((m1 || m2) && !((slow_mask >> q) & 1u)) {   // rare unless b is a member: verify against the key itself
+                    const bool hit = (m1 && S.keys[q][e1[q] & 1023u] == b) || (m2 && S.keys[q][e2[q] & 1023u] == b);
+                    cnt[q] += hit ? 1u : 0u;
                 }
+            }
+            if (slow_mask) {      // block-uniform; adversarial hash sets only
+#pragma unroll
+                for (int q = 0; q < DT_TQ; ++q)
+                    if ((slow_mask >> q) & 1u) {
+                        const uint32_t na = S.na[q], p = lower_bound_sm(S.keys[q], na, b);
+                        cnt[q] = cnt[q] + ((p < na && S.keys[q][p] == b) ? 1u : 0u);
+                    }
             }
         }
         uint32_t mine = 0;

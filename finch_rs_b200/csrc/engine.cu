@@ -1031,7 +1031,7 @@ int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, 
 // up with the kernel + D2H pipeline).
 static void parallel_memcpy(void *dst, const void *src, size_t n) {
     const size_t min_part = 8u << 20;
-    unsigned parts = (unsigned)std::min<size_t>(4, n / min_part);
+    unsigned parts = (unsigned)std::min<size_t>(8, n / min_part);
     if (parts < 2) { memcpy(dst, src, n); return; }
     std::vector<std::thread> th;
     const size_t per = (n / parts + 63) & ~(size_t)63;
@@ -1317,10 +1317,12 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
             cu(cudaEventSynchronize(ev_c[k & 1]));
             if (rc == FB2_OK) parallel_memcpy(out + (slabs[k].q - q0) * n_sk, h_pin[k & 1], slabs[k].m * sizeof(fb2_pair_out));
         };
+        std::vector<cudaEvent_t> ev_s0(slabs.size(), nullptr), ev_s1(slabs.size(), nullptr);   // per-slab kernel time
         for (size_t k = 0; k < slabs.size() && rc == FB2_OK; ++k) {
             const int b = (int)(k & 1);
-            if (k >= 2) drain(k - 2);                                   // frees h_pin[b]; its D2H freed d_o[b]
             const uint64_t q = slabs[k].q, m = slabs[k].m;
+            cu(cudaEventCreate(&ev_s0[k])); cu(cudaEventCreate(&ev_s1[k]));
+            cu(cudaEventRecord(ev_s0[k], st_k));
             if (tiled) {
                 if (launch_dist_tile(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, (uint32_t)n_sk,
                                      (uint32_t)q, (uint32_t)(q + m / n_sk), scaled, max_hash, d_o[b].as<fb2_pair_out>(), st_k) != 0)
@@ -1329,7 +1331,9 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
                 launch_dist_all(d_h.as<unsigned long long>(), d_l.as<uint32_t>(), (uint32_t)stride, (uint32_t)n_sk,
                                 (uint32_t)q, m, scaled, max_hash, d_o[b].as<fb2_pair_out>(), st_k);
             }
+            cu(cudaEventRecord(ev_s1[k], st_k));
             cu(cudaEventRecord(ev_k[b], st_k));
+            if (k >= 2) drain(k - 2);               // host copy of slab k-2 while the kernel of slab k runs; frees h_pin[b]
             cu(cudaStreamWaitEvent(st_c, ev_k[b], 0));
             cu(cudaMemcpyAsync(h_pin[b], d_o[b].p, m * sizeof(fb2_pair_out), cudaMemcpyDeviceToHost, st_c));
             cu(cudaEventRecord(ev_c[b], st_c));
@@ -1344,7 +1348,13 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
         if (e != cudaSuccess && rc == FB2_OK) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
         // device time from the first kernel's start to the last kernel's end (includes waits for free slabs)
         float ms = 0.f;
-        if (rc == FB2_OK && ev_t0 && ev_t1 && cudaEventElapsedTime(&ms, ev_t0, ev_t1) == cudaSuccess) g_dist_kernel_ms = ms;
+        double sum = 0.0;
+        for (size_t k = 0; k < slabs.size(); ++k) {
+            if (rc == FB2_OK && ev_s0[k] && ev_s1[k] && cudaEventElapsedTime(&ms, ev_s0[k], ev_s1[k]) == cudaSuccess) sum += ms;
+            if (ev_s0[k]) cudaEventDestroy(ev_s0[k]);
+            if (ev_s1[k]) cudaEventDestroy(ev_s1[k]);
+        }
+        if (rc == FB2_OK) g_dist_kernel_ms = sum;   // kernel time only (the span also holds waits for free slabs)
         if (ev_t0) cudaEventDestroy(ev_t0);
         if (ev_t1) cudaEventDestroy(ev_t1);
     }

@@ -174,7 +174,7 @@ int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, si
 /* All ordered pairs (q, r), q in [q0,q1), r in [0,n_sk): out[(q-q0)*n_sk + r]. */
 int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
                        double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device);
-/* Measurement aid: device time (ms) spanned by the kernels of this thread's last fb2_dist_all_pairs. */
+/* Measurement aid: summed device time (ms) of the kernels of this thread's last fb2_dist_all_pairs. */
 double fb2_dist_last_kernel_ms(void);
 /* distance.rs:117-125 and :35-41 from the integers of one pair. */
 void fb2_distance_finish(const fb2_pair_out *p, uint8_t kmer_length, double *containment,
