@@ -93,6 +93,7 @@ struct fb2_sketcher {
     cudaStream_t st2 = nullptr;      // absorb stream: log -> table of chunk c overlaps the parse kernels of chunk c+1
     cudaEvent_t ev_hash[2]{}, ev_st2 = nullptr;
     bool st2_dirty = false;          // work was queued on st2 since the last join
+    bool skip_provisional = false;   // hash_range: the provisional threshold failed for this chunk, use the exact ramp
     bool own_stream = false;
     cudaEvent_t ev_h2d[2]{}, ev_rawfree[2]{}, ev_t0 = nullptr, ev_t1 = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
     bool rawfree_pending[2] = {false, false};
@@ -585,8 +586,30 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
     // Infinite threshold (start of a stream): every k-mer is a candidate.  If the whole chunk fits into
     // one launch of the log take it (small files: one launch, one banded absorb); otherwise start small,
     // so the threshold is finite before most of the chunk is hashed.
-    if (s->h_state->threshold == ~0ULL && (uint64_t)total_blocks * per_blk > s->next_launch)
-        s->next_launch = 32u * HASH_TILE;
+    // A chunk too large for that gets a PROVISIONAL finite threshold instead of the slow ramp: the
+    // chunk holds N symbols, so T0 = 16 * size * 2^64 / N lets ~16 * size candidate occurrences through
+    // (bounded, whatever the duplication) and the whole chunk is hashed in one launch.  T0 is a valid
+    // admission threshold iff at least `size` DISTINCT keys turn out to lie at or below it, which is
+    // checked after the absorb; if not (very repetitive input) the table is cleared and the chunk is
+    // redone with the exact ramp.  Either way the result is that of an infinite initial threshold.
+    bool provisional = false;
+    unsigned long long prov_kmers = 0;
+    if (s->h_state->threshold == ~0ULL && (uint64_t)total_blocks * per_blk > s->next_launch) {
+        const uint64_t N = s->h_carry->chunk_syms, want = 16ull * s->size;
+        if (!s->skip_provisional && !s->timing && s->size > 0 && want + want / 8 <= s->log_cap / 2 && N > 4 * want &&
+            !getenv("FB2_NO_PROVISIONAL")) {
+            unsigned long long T0 = (~0ULL / N) * want;
+            if (s->scaled && T0 < s->max_hash) T0 = s->max_hash;
+            s->h_state->threshold = T0;
+            TRY(push_state(s));
+            TRY(refresh_live_hist(s));
+            provisional = true;
+            s->next_launch = 0x7FFFFFFFu / HASH_TILE * HASH_TILE;   // the whole chunk
+        } else {
+            s->next_launch = 32u * HASH_TILE;
+        }
+    }
+    s->skip_provisional = false;
     while (b < total_blocks) {
         uint32_t nb = std::max<uint32_t>(s->next_launch / per_blk, 1u);
         nb = std::min(nb, total_blocks - b);
@@ -615,6 +638,7 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
             continue;
         }
         s->total_kmers += s->h_state->slot[par].launch_kmers;
+        if (provisional) prov_kmers += s->h_state->slot[par].launch_kmers;
         TRY(absorb_log(s, par, cnt));
         b += nb;
         // next launch: aim the candidate count at a quarter of the log
@@ -623,6 +647,22 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
         double next = (double)(s->log_cap / 4) / frac / fill;               // launched positions
         if (next > 2147483648.0) next = 2147483648.0;
         s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (uint32_t)next);
+    }
+    if (provisional) {
+        TRY(pull_state(s));
+        const uint64_t have = (uint64_t)s->h_state->occupied + (s->h_state->has_max_key ? 1u : 0u);
+        if (have < s->size) {
+            // the provisional threshold was too low for this input: forget the chunk and redo it exactly
+            s->total_kmers -= prov_kmers;
+            launch_table_clear(s->tab[s->cur].view(), s->st);
+            s->stats.kernel_launches++;
+            s->h_state->threshold = ~0ULL; s->h_state->occupied = 0; s->h_state->has_max_key = 0;
+            TRY(push_state(s));
+            TRY(refresh_live_hist(s));
+            s->skip_provisional = true;
+            s->stats.provisional_redos++;
+            return hash_range(s, g, ord_base, par);
+        }
     }
     return FB2_OK;
 }

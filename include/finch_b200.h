@@ -132,6 +132,7 @@ typedef struct fb2_stats {
     double hash_kernel_ms;   /* CUDA-event time of the k-mer hash kernel (only if timing enabled) */
     double parse_kernel_ms;  /* CUDA-event time of the parse/pack kernels */
     uint64_t hash_symbols;   /* symbols (bases + record breaks) the hash kernel walked */
+    uint64_t provisional_redos; /* chunks redone because the provisional first threshold was too low */
 } fb2_stats;
 int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out);
 /* Inspection hook for tests: geometry (7 x u32), per-region symbol counts and the raw symbol buffer of the

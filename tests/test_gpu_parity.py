@@ -250,6 +250,40 @@ def test_many_chunks_steady_state(fb, oracle, monkeypatch, kind, size, scale):
         assert_same(gres2, ovec, 21)
 
 
+def test_provisional_first_threshold(fb, oracle, monkeypatch):
+    """A first chunk too large for one infinite-threshold launch starts from a provisional finite threshold
+    (16 * size expected candidates) and is hashed in one launch; if fewer than `size` distinct keys lie
+    below it the chunk is redone with the exact ramp.  Smallest log so that small inputs take this path."""
+    monkeypatch.setenv("FB2_LOG_M", "0")
+    genome = fb.synth_genome(400_000, 31)
+    data, nb = fb.synth_fastq(genome, 14_000, 150, 0.01, 33)
+    data = data.tobytes()
+    for kind, size, scale in (("mash", 2000, 0.0), ("scaled", 500, 0.002)):
+        ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, 21, 0, scale or 0.001)
+        sp = fb.SketchParams.mash(size, size, False, 21, 0) if kind == "mash" else fb.SketchParams.scaled(size, 21, scale, 0)
+        with sp.create_sketcher() as s:
+            s.feed_fastx(data, final=True)
+            assert s.total_bases_and_kmers() == ototals
+            assert_same(s.to_arrays(), ovec, 21)
+            st = s.stats()
+            assert st["provisional_redos"] == 0 and st["hash_launches"] <= 2, st
+        monkeypatch.setenv("FB2_NO_PROVISIONAL", "1")
+        with sp.create_sketcher() as s:
+            s.feed_fastx(data, final=True)
+            assert_same(s.to_arrays(), ovec, 21)
+            assert s.stats()["hash_launches"] > 2
+        monkeypatch.delenv("FB2_NO_PROVISIONAL")
+    # very repetitive input: 30 + 1 distinct k-mers in 1.5 M positions -> the provisional threshold cannot hold
+    unit = b"ACGTTGCAAGGCTTAACCGGATATCGCGTA"
+    rep = b">rep\n" + unit * 40000 + b"\n>polyA\n" + b"A" * 300000 + b"\n"
+    ovec, ototals, _ = oracle_sketch(oracle, rep, "mash", 1000, 21, 0)
+    with fb.SketchParams.mash(1000, 1000, True, 21, 0).create_sketcher() as s:
+        s.feed_fastx(rep, final=True)
+        assert s.total_bases_and_kmers() == ototals
+        assert_same(s.to_arrays(), ovec, 21)
+        assert s.stats()["provisional_redos"] == 1
+
+
 def test_sketch_files_many_workers(fb, oracle, tmp_path, monkeypatch):
     """fb2_sketch_files with more files than worker handles, mixed formats and sizes, twice (the second
     call re-uses the pooled handles): results in input order, identical to one-by-one sketching."""
