@@ -507,7 +507,11 @@ static int absorb_log_banded(fb2_sketcher *s, int par, uint32_t cnt, bool *done)
         TRY(prune(s, 0, &hi, &ok));               // pulls the state; commits only if >= size keys are <= hi
         if (ok) { *done = true; return FB2_OK; }
         lo = hi; use_lo = 1; lo_cum = cum[b];
-        target = cum[b] * 4 + 1024;
+        // widen: extrapolate from the multiplicity seen so far (entries absorbed per distinct key in the
+        // table), at least doubling -- high-coverage reads repeat every key several times per chunk
+        const double mult = (double)cum[b] / std::max<double>(1.0, (double)s->h_state->occupied);
+        const double est = ((double)s->size * 1.15 + 1024.0) * std::max(1.0, mult);
+        target = std::max<uint64_t>(cum[b] * 2 + 1024, (uint64_t)std::min(est, 4.0e9));
     }
     TRY(pull_state(s));
     return FB2_OK;
