@@ -619,8 +619,9 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
         nb = std::min(nb, total_blocks - b);
         CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
         if (s->timing) CU(cudaEventRecord(s->ev_t0, s->st));
+        // candidate-dense launches (infinite / provisional threshold, early ramp) reserve log slots in big batches
         launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, b, b + nb, s->d_rcount[par].as<uint32_t>(), ord_base, dst, slot,
-                    log_view(s, par), s->prm.hash_seed, s->st);
+                    log_view(s, par), s->prm.hash_seed, 31u, s->st);
         if (s->timing) CU(cudaEventRecord(s->ev_t1, s->st));
         s->stats.kernel_launches++; s->stats.hash_launches++;
         TRY(pull_state(s));
@@ -752,7 +753,7 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
         CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
         launch_note_chunk_syms(slot, dc, s->st);
         launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, total_blocks, s->d_rcount[par].as<uint32_t>(), ord_base, dst,
-                    slot, log_view(s, par), s->prm.hash_seed, s->st);
+                    slot, log_view(s, par), s->prm.hash_seed, 3u, s->st);
         if (ab != s->st) {
             CU(cudaEventRecord(s->ev_hash[par], s->st));
             CU(cudaStreamWaitEvent(ab, s->ev_hash[par], 0));

@@ -117,6 +117,7 @@ constexpr int HP_R32 = 8;               // copies of the 32-bit tables (low word
 struct HashConsts {                     // kernel parameters: values ptxas must not fold away
     uint32_t stride64, stride32, stride1;   // HP_R64 * 8, HP_R32 * 4, 8 (bytes between consecutive entries)
     uint32_t one;                           // 1: multiplier that keeps 64-bit adds on the FMA pipe
+    uint32_t log_reserve;                   // extra log slots a warp reserves per atomic, <= 31 (candidate-dense launches: 31)
     unsigned long long add1, add2;          // 0x52dce729, 0x38495ab5 (the +c of h * 5 + c, as IMAD.WIDE addends)
 };
 struct MulLut {                         // per-lane shared-window byte addresses (copy l % R already applied)
@@ -220,7 +221,8 @@ __device__ __forceinline__ U2 murmur_kmer_h1_lut(U2 codes, U2 seed, const MulLut
     return add_one(h1, h2, L.one);
 }
 
-constexpr uint32_t LOG_RESERVE = 3;   // extra log slots a warp reserves per atomic (<= 31)
+// A warp reserves n + log_reserve log slots per atomic on the launch's counter (same-address L2 atomics
+// serialise at ~1 per ns: a candidate-dense launch must not issue one per position).
 
 // ---- TMA (1-D bulk copy) staging of the block's symbol tile ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -461,11 +463,11 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
                   const uint32_t em = __ballot_sync(0xffffffffu, emit);
                   if (em) {
                     // Warp-private bump reservation in the log: the global atomic (and the wait for its
-                    // result) happens once per LOG_RESERVE candidates, not once per candidate.
+                    // result) happens once per reservation, not once per candidate.
                     const uint32_t n = __popc(em);
                     if (n > res_left) {                                   // warp-uniform
-                        if (lane < res_left && res_base + lane < log.cap) log.posx[res_base + lane] = ~0ULL;  // unused slots
-                        const uint32_t want = n + LOG_RESERVE;
+                        if (lane < res_left && res_base + lane < log.cap) log.posx[res_base + lane] = ~0ULL;  // unused slots (res_left <= 31)
+                        const uint32_t want = n + hc.log_reserve;
                         uint32_t base = 0;
                         if (lane == 0) base = atomicAdd(&slot->log_count, want);
                         res_base = __shfl_sync(0xffffffffu, base, 0);
@@ -519,7 +521,7 @@ __global__ void push_commit_kernel(LaunchSlot *slot, uint32_t n) { slot->launch_
 template <int K, bool SEED0>
 static void launch_hash_ks(uint32_t w0, uint32_t w1, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
                            uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, int k, uint64_t seed,
-                           cudaStream_t stream) {
+                           uint32_t log_reserve, cudaStream_t stream) {
     static int sms[64] = {};   // per device: SM count, set once the shared-memory attribute is in place
     int dev = 0;
     cudaGetDevice(&dev);
@@ -533,6 +535,7 @@ static void launch_hash_ks(uint32_t w0, uint32_t w1, const uint8_t *symbuf, Chun
     HashConsts hc;
     hc.stride64 = HP_R64 * 8u; hc.stride32 = HP_R32 * 4u; hc.stride1 = 8u; hc.one = 1u;
     hc.add1 = 0x52dce729ULL; hc.add2 = 0x38495ab5ULL;
+    hc.log_reserve = log_reserve;
     const uint32_t items = w1 - w0;
     const uint32_t ctas = std::min<uint32_t>((uint32_t)sms[dev], (items + HP_WARPS - 1) / HP_WARPS);
     hash_kernel<K, SEED0><<<ctas, HP_WARPS * 32, HP_SMEM, stream>>>(symbuf, g, w0, w1, region_count, ord_base, st, slot, log,
@@ -541,19 +544,19 @@ static void launch_hash_ks(uint32_t w0, uint32_t w1, const uint8_t *symbuf, Chun
 template <int K>
 static void launch_hash_k(uint32_t w0, uint32_t w1, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
                           uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, int k, uint64_t seed,
-                          cudaStream_t stream) {
-    if (seed == 0 && K > 0) launch_hash_ks<K, true>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
-    else launch_hash_ks<K, false>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
+                          uint32_t log_reserve, cudaStream_t stream) {
+    if (seed == 0 && K > 0) launch_hash_ks<K, true>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    else launch_hash_ks<K, false>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
 }
 // Hash the HASH_TILE-sized blocks [b0, b1) (region-major) of a chunk's symbol regions.
 void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t b0, uint32_t b1, const uint32_t *region_count,
                  uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, uint64_t seed,
-                 cudaStream_t stream) {
+                 uint32_t log_reserve, cudaStream_t stream) {
     if (b1 <= b0) return;
     const uint32_t w0 = b0 * HP_ITEMS_PER_TILE, w1 = b1 * HP_ITEMS_PER_TILE;
-    if (k == 21) launch_hash_k<21>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
-    else if (k == 31) launch_hash_k<31>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
-    else launch_hash_k<0>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, stream);
+    if (k == 21) launch_hash_k<21>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    else if (k == 31) launch_hash_k<31>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    else launch_hash_k<0>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
 }
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
                       uint64_t arena_base, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
