@@ -32,11 +32,13 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // ---- 32-bit-half arithmetic, placed on the pipes by hand ----------------------------------------
-// The kernel is bound by the ALU pipe (LOP3/SHF/IADD3/ISETP/SEL/PRMT, 16 lanes per SM sub-partition);
-// IMAD runs on the FMA pipe, which has room.  Everything that can be phrased as a multiply-add is:
-// 64-bit adds (IMAD.WIDE + IMAD), *5+c, shared-memory addressing (idx * stride + base with the stride
-// in a register so ptxas cannot turn it back into LEA), ">> 1" of a high word (IMAD.HI by 2^31).
-// 64-bit rotates are two funnel shifts.
+// Measured issue rates on the B200 (tools/pipe_rates.cu), warp instructions per clock per SM
+// sub-partition: LOP3 / SHF / PRMT / IADD3 (ALU pipe) 0.5, IMAD 0.5, IMAD.WIDE and IMAD.HI 0.25, and
+// ALU + IMAD interleave to 0.83.  The kernel is bound by integer issue, so the murmur arithmetic is
+// written in 32-bit halves with the instruction chosen per operation: 64-bit rotates are two funnel
+// shifts; x * C is one IMAD.WIDE + two IMAD; x * 5 + c is LEA + LEA.HI.X + add; shared-memory table
+// addresses are idx * stride + base with the stride in a register (so ptxas keeps an IMAD instead of
+// a shift + add); one of the three ">> 1" of each fmix goes through IMAD.HI to level the two pipes.
 struct U2 { uint32_t lo, hi; };
 
 __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
@@ -116,14 +118,13 @@ constexpr int HP_R64 = 16;              // copies of the 64-bit tables (A4 * c, 
 constexpr int HP_R32 = 8;               // copies of the 32-bit tables (low word of A4 * c)
 struct HashConsts {                     // kernel parameters: values ptxas must not fold away
     uint32_t stride64, stride32, stride1;   // HP_R64 * 8, HP_R32 * 4, 8 (bytes between consecutive entries)
-    uint32_t one;                           // 1: multiplier that keeps 64-bit adds on the FMA pipe
+    uint32_t one;                           // 1: multiplier that keeps the table-word adds on the FMA pipe
     uint32_t log_reserve;                   // extra log slots a warp reserves per atomic, <= 31 (candidate-dense launches: 31)
-    unsigned long long add1, add2;          // 0x52dce729, 0x38495ab5 (the +c of h * 5 + c, as IMAD.WIDE addends)
 };
 struct MulLut {                         // per-lane shared-window byte addresses (copy l % R already applied)
     uint32_t c1_64, c2_64, c1_32, c2_32, t1;
     uint32_t stride64, stride32, stride1, one;
-    U2 add1, add2;
+    U2 add1, add2;                      // the +c of h * 5 + c
 };
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -534,7 +535,6 @@ static void launch_hash_ks(uint32_t w0, uint32_t w1, const uint8_t *symbuf, Chun
     }
     HashConsts hc;
     hc.stride64 = HP_R64 * 8u; hc.stride32 = HP_R32 * 4u; hc.stride1 = 8u; hc.one = 1u;
-    hc.add1 = 0x52dce729ULL; hc.add2 = 0x38495ab5ULL;
     hc.log_reserve = log_reserve;
     const uint32_t items = w1 - w0;
     const uint32_t ctas = std::min<uint32_t>((uint32_t)sms[dev], (items + HP_WARPS - 1) / HP_WARPS);
