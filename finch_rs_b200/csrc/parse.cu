@@ -734,23 +734,24 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
     }
 }
 
-// Front pads: thread r fills the 32 bytes before region r (r < n_st) or the outgoing chunk tail
-// (r == n_st) with the last 32 symbols that precede it in stream order, walking back over short
-// or empty regions and finally into the incoming chunk tail.
+// Front pads: warp r fills the 32 bytes before region r (r < n_st) or the outgoing chunk tail
+// (r == n_st) with the last 32 symbols that precede it in stream order -- lane t fetches the symbol
+// 32 - t places back, walking back over short or empty regions and finally into the incoming chunk tail.
 __global__ void front_fix_kernel(uint8_t *__restrict__ sym, ChunkGeom g, const uint32_t *__restrict__ region_count,
                                  const uint8_t *__restrict__ tail_in, uint8_t *__restrict__ tail_out) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (r > g.n_st) return;
     uint8_t *dst = r < g.n_st ? (sym + (size_t)SYM_FRONT + (size_t)r * g.region_stride - 32) : tail_out;
-    int need = 32;
-    for (int j = (int)r - 1; need > 0 && j >= 0; --j) {
+    uint32_t back = 31u - lane;                      // symbols between the wanted one and the end of the stream so far
+    uint8_t v = 0;
+    bool found = false;
+    for (int j = (int)r - 1; j >= 0; --j) {
         const uint32_t n = region_count[j];
-        const int take = n < (uint32_t)need ? (int)n : need;
-        const uint8_t *src = sym + (size_t)SYM_FRONT + (size_t)j * g.region_stride + (n - take);
-        for (int t = 0; t < take; ++t) dst[need - take + t] = src[t];
-        need -= take;
+        if (back < n) { v = sym[(size_t)SYM_FRONT + (size_t)j * g.region_stride + (n - 1u - back)]; found = true; break; }
+        back -= n;
     }
-    for (int t = 0; t < need; ++t) dst[t] = tail_in[32 - need + t];
+    if (!found) v = tail_in[31u - back];             // back < 32 here: the incoming tail holds the 32 symbols before the chunk
+    dst[lane] = v;
 }
 
 __global__ void fill_bytes_kernel(uint8_t *p, uint32_t n, uint8_t v) {
@@ -770,7 +771,7 @@ void launch_pack(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, c
     if (mode == MODE_LINES) pack_kernel<MODE_LINES><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
     else if (mode == MODE_FASTA) pack_kernel<MODE_FASTA><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
     else pack_kernel<MODE_FASTQ><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
-    front_fix_kernel<<<(g.n_st + 1 + 127) / 128, 128, 0, s>>>(sym, g, region_count, tail_in, tail_out);
+    front_fix_kernel<<<(g.n_st + 1 + 7) / 8, 256, 0, s>>>(sym, g, region_count, tail_in, tail_out);
 }
 void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t s) {
     if (n) fill_bytes_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
