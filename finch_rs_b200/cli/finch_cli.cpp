@@ -9,7 +9,7 @@
 //   update_sketch_params      cli/src/main.rs:336-441
 // The sequence work (sketch_files) and the sorted-hash intersections (raw_distance) run on the GPU
 // through libfinch_b200.so; there is no CPU fallback.  Not supported by this build (clear errors):
-// `.bsk` / `.msh` Cap'n Proto files (-b / -B), `--sketch-type none`, `--old-dist`, compressed input.
+// `.bsk` / `.msh` Cap'n Proto files (-b / -B), `--sketch-type none`, `--old-dist`, bz2 / xz input (gzip works).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

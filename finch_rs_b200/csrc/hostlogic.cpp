@@ -21,6 +21,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <zlib.h>
 
 #include "../../include/finch_b200.h"
 
@@ -161,7 +162,9 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
 }
 
 // One file through handle `s` (lib.rs:51-94 per file): read in pieces into the worker's pinned buffer,
-// feed the raw bytes, finish the sketch.
+// feed the raw bytes, finish the sketch.  gzip input (needletail sniffs the 1f 8b magic, lib.rs:60 via
+// parse_fastx_reader) is inflated on the host by this worker thread, concatenated members included;
+// bz2 / xz stay unsupported (no headers for them in this image) and are reported by the engine.
 static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_t *buf, size_t piece,
                            const fb2_params *p, const fb2_filter *f, fb2_result *out) {
     const bool is_stdin = strcmp(path, "-") == 0;  // lib.rs:38-40
@@ -169,10 +172,51 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
     if (!fp) return fb2_fail(FB2_EIO, std::string(path) + ": No such file or directory");
     int rc = reuse ? fb2_sketcher_reset(s) : FB2_OK;
     bool any = false;
-    while (rc == FB2_OK) {
-        const size_t got = fread(buf, 1, piece, fp);
-        if (got) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, got, 0); }
-        if (got < piece) break;
+    // sniff the first two bytes
+    unsigned char magic[2] = {0, 0};
+    const size_t nmagic = rc == FB2_OK ? fread(magic, 1, 2, fp) : 0;
+    if (rc == FB2_OK && nmagic == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        std::vector<unsigned char> in(1u << 20);
+        memcpy(in.data(), magic, 2);
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, 15 + 32) != Z_OK) rc = fb2_fail(FB2_EIO, std::string(path) + ": zlib initialisation failed");
+        bool zopen = rc == FB2_OK;
+        zs.next_in = in.data(); zs.avail_in = 2;
+        size_t fill = 0;
+        bool eof = false, member_done = false;
+        while (rc == FB2_OK) {
+            if (zs.avail_in == 0 && !eof) {
+                const size_t got = fread(in.data(), 1, in.size(), fp);
+                if (got == 0) eof = true;
+                zs.next_in = in.data(); zs.avail_in = (uInt)got;
+            }
+            if (zs.avail_in == 0 && eof) {
+                if (!member_done) rc = fb2_fail(FB2_EIO, std::string(path) + ": truncated gzip stream");
+                break;
+            }
+            if (member_done) {                      // another gzip member follows (MultiGzDecoder semantics)
+                if (inflateReset(&zs) != Z_OK) { rc = fb2_fail(FB2_EIO, std::string(path) + ": zlib reset failed"); break; }
+                member_done = false;
+            }
+            zs.next_out = buf + fill; zs.avail_out = (uInt)std::min<size_t>(piece - fill, 1u << 30);
+            const int zr = inflate(&zs, Z_NO_FLUSH);
+            fill = (size_t)(zs.next_out - buf);
+            if (zr == Z_STREAM_END) member_done = true;
+            else if (zr != Z_OK && zr != Z_BUF_ERROR) { rc = fb2_fail(FB2_EIO, std::string(path) + ": corrupt gzip stream"); break; }
+            if (fill == piece) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, fill, 0); fill = 0; }
+        }
+        if (rc == FB2_OK && fill) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, fill, 0); }
+        if (zopen) inflateEnd(&zs);
+    } else {
+        size_t fill = nmagic;
+        if (nmagic) memcpy(buf, magic, nmagic);
+        while (rc == FB2_OK) {
+            const size_t got = fread(buf + fill, 1, piece - fill, fp) + fill;
+            fill = 0;
+            if (got) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, got, 0); }
+            if (got < piece) break;
+        }
     }
     if (!is_stdin) fclose(fp);
     if (rc == FB2_OK && !any) rc = fb2_fail(FB2_EEMPTY, std::string(path) + ": empty input");

@@ -250,6 +250,32 @@ def test_many_chunks_steady_state(fb, oracle, monkeypatch, kind, size, scale):
         assert_same(gres2, ovec, 21)
 
 
+def test_sketch_files_gzip(fb, oracle, tmp_path):
+    """gzip input (needletail sniffs 1f 8b): single member, concatenated members, and a truncated stream."""
+    import gzip
+    rng = np.random.default_rng(91)
+    fa = gen.fasta(rng, n_records=3, max_len=50000, width=70)
+    fq = gen.fastq(rng, n_records=800, max_len=250)
+    p1, p2, p3, p4 = (tmp_path / n for n in ("a.fa.gz", "b.fq.gz", "c.fa", "bad.fq.gz"))
+    p1.write_bytes(gzip.compress(fa))
+    half = len(fq) // 2
+    p2.write_bytes(gzip.compress(fq[:half]) + gzip.compress(fq[half:]))       # two members, cut mid-record
+    p3.write_bytes(fa)
+    p4.write_bytes(gzip.compress(fq)[:-200])
+    sp = fb.SketchParams.mash(3000, 200, True, 21, 0)
+    fp = fb.FilterParams(False, (None, None), 0.21, 0.1)
+    sks = fb.sketch_files([str(p1), str(p2), str(p3)], sp, fp)
+    for sk, data in zip(sks, (fa, fq, fa)):
+        rc, osk = oracle.sketch_stream(data, oracle.mash_params(3000, 200, True, 21, 0), oracle.make_filter(False, (None, None), 0.21, 0.1))
+        assert rc == oracle.OK
+        assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+        assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+    assert np.array_equal(sks[0].hashes_u64, sks[2].hashes_u64)
+    with pytest.raises(fb.FinchError) as ei:
+        fb.sketch_files([str(p4)], sp, fp)
+    assert "gzip" in str(ei.value)
+
+
 def test_provisional_first_threshold(fb, oracle, monkeypatch):
     """A first chunk too large for one infinite-threshold launch starts from a provisional finite threshold
     (16 * size expected candidates) and is hashed in one launch; if fewer than `size` distinct keys lie
