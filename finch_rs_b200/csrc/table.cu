@@ -160,24 +160,31 @@ __global__ void table_clear_kernel(TableView t) {
 }
 
 // Occupied slots -> (key, slot) pairs, arbitrary order.
-__global__ void gather_kernel(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots) {
+// One global atomic per block (warp ballots -> shared counter -> block base), as gather_le_kernel below.
+__global__ void __launch_bounds__(256)
+gather_kernel(TableView t, SketchState *st, unsigned long long *keys, uint32_t *slots) {
+    __shared__ uint32_t blk_count, blk_base;
+    if (threadIdx.x == 0) blk_count = 0;
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > t.cap) return;
-    bool occ;
-    if (i == t.cap) occ = st->has_max_key != 0u && st->threshold == EMPTY_KEY;
-    else { const unsigned long long key = t.key[i]; occ = key != EMPTY_KEY && key <= st->threshold; }   // dead keys (above a soft threshold) stay behind
-    const uint32_t m = __ballot_sync(__activemask(), occ);
-    if (!occ) return;
+    const unsigned long long thr = st->threshold;
+    unsigned long long key = EMPTY_KEY;
+    bool occ = false;
+    if (i < t.cap) { key = t.key[i]; occ = key != EMPTY_KEY && key <= thr; }   // dead keys (above a soft threshold) stay behind
+    else if (i == t.cap) occ = st->has_max_key != 0u && thr == EMPTY_KEY;
+    const uint32_t m = __ballot_sync(0xffffffffu, occ);
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t act = __activemask();
-    (void)act;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(&st->gather_count, (unsigned int)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    const uint32_t idx = base + __popc(m & ((1u << lane) - 1u));
-    keys[idx] = (i == t.cap) ? EMPTY_KEY : t.key[i];
-    slots[idx] = i;
+    uint32_t wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&blk_count, (unsigned int)__popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk_count) blk_base = atomicAdd(&st->gather_count, blk_count);
+    __syncthreads();
+    if (occ) {
+        const uint32_t idx = blk_base + wbase + __popc(m & ((1u << lane) - 1u));
+        keys[idx] = key;
+        slots[idx] = i;
+    }
 }
 
 __global__ void reset_gather_kernel(SketchState *st);
