@@ -186,6 +186,33 @@ def workload_name(args):
             f"k={K}, n={N_HASHES}, --filter on (heap {N_HASHES * OVERSKETCH}), per GPU")
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Multi-rank runs: keep this rank's threads (and so its pinned host buffers, first-touch) on the NUMA
+    node its GPU hangs off, like `numactl --cpunodebind --membind`.  Best effort: None when unknown."""
+    try:
+        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bdf is None:
+            import ctypes as C
+            buf = C.create_string_buffer(32)
+            if C.CDLL("libcudart.so.12").cudaDeviceGetPCIBusId(buf, 32, local) != 0:
+                return None
+            bdf = buf.value.decode()
+        node = int(open(f"/sys/bus/pci/devices/{bdf.lower()}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, z = part.partition("-")
+            cpus.update(range(int(a), int(z or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -212,6 +239,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: finch_rs_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -322,6 +350,7 @@ def main():
         "config": {"workload": workload_name(args), "fastq_bytes_per_gpu": nbytes, "bases_per_gpu": nbases,
                    "l2": "inputs (3.1 GB per step) are far larger than the 126 MB L2; no explicit flush",
                    "parallelism": f"files x {world} (one file per GPU, NCCL gather of finished sketches)" if world > 1 else "1 GPU",
+                   "numa_node_rank0": numa,
                    "chunk_mb": int(os.environ.get("FB2_CHUNK_MB", "128"))},
         "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(stats_e2e["h2d_bytes"] // e2e_steps),
                 "d2h_bytes_per_step": int(stats_e2e["d2h_bytes"] // e2e_steps), "ms_per_step": ms_e2e / e2e_steps,
