@@ -188,6 +188,14 @@ def main():
         dt = min(dt, time.perf_counter() - t0)
         kms = min(kms, fb.lib().fb2_dist_last_kernel_ms())
     npairs = q1 * n_sk
+    pinned_out = torch.empty((q1 * n_sk, 3), dtype=torch.int32, pin_memory=True)   # same bits as uint32
+    pbuf = pinned_out.numpy().view(np.uint32)
+    dtp = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        outp = fb.dist_all_pairs(mat, lens, 0.0, 0, q1, out=pbuf)
+        dtp = min(dtp, time.perf_counter() - t0)
+    same_pinned = bool(np.array_equal(outp, out))
     # CPU port on a bounded sample of pairs
     nq = 4
     t0 = time.perf_counter()
@@ -201,7 +209,8 @@ def main():
     cpu_pairs = nq * (n_sk // 4)
     rows.append({"config": f"C5 dist all-vs-all {n_sk} x {n_sk} sketches of 1000 hashes (API call incl. H2D/D2H)",
                  "pairs": npairs, "gpu_s": dt, "pairs_per_s": npairs / dt, "kernel_ms": kms,
-                 "kernel_pairs_per_s": npairs / (kms * 1e-3), "cpu_port_pairs_per_s": cpu_pairs / odt,
+                 "kernel_pairs_per_s": npairs / (kms * 1e-3), "pinned_out_s": dtp, "pinned_out_pairs_per_s": npairs / dtp,
+                 "pinned_out_identical": same_pinned, "cpu_port_pairs_per_s": cpu_pairs / odt,
                  "cpu_threads": 1, "bit_exact": ok, "bit_exact_on": f"{cpu_pairs} sampled pairs"})
     print(json.dumps(rows[-1]), flush=True)
     if args.out:

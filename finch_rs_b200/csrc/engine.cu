@@ -1346,9 +1346,16 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
         auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == FB2_OK) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e)); };
         cu(cudaStreamCreateWithFlags(&st_k, cudaStreamNonBlocking));
         cu(cudaStreamCreateWithFlags(&st_c, cudaStreamNonBlocking));
+        // a caller-provided PINNED result array (cudaHostAlloc / cudaHostRegister) takes the D2H copies directly
+        bool out_pinned = false;
+        {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost) out_pinned = true;
+            else cudaGetLastError();   // clear the error an unregistered pointer may leave on older runtimes
+        }
         for (int i = 0; i < 2 && rc == FB2_OK; ++i) {
             rc = d_o[i].ensure(slab_pairs * sizeof(fb2_pair_out));
-            if (rc == FB2_OK) cu(cudaHostAlloc((void **)&h_pin[i], slab_pairs * sizeof(fb2_pair_out), cudaHostAllocDefault));
+            if (rc == FB2_OK && !out_pinned) cu(cudaHostAlloc((void **)&h_pin[i], slab_pairs * sizeof(fb2_pair_out), cudaHostAllocDefault));
             cu(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
             cu(cudaEventCreateWithFlags(&ev_c[i], cudaEventDisableTiming));
         }
@@ -1360,7 +1367,7 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
         for (uint64_t q = q0; q < q1; q += rows) slabs.push_back({q, std::min<uint64_t>(rows, q1 - q) * n_sk});
         auto drain = [&](size_t k) {   // slab k: wait for its D2H, copy to the caller
             cu(cudaEventSynchronize(ev_c[k & 1]));
-            if (rc == FB2_OK) parallel_memcpy(out + (slabs[k].q - q0) * n_sk, h_pin[k & 1], slabs[k].m * sizeof(fb2_pair_out));
+            if (rc == FB2_OK && !out_pinned) parallel_memcpy(out + (slabs[k].q - q0) * n_sk, h_pin[k & 1], slabs[k].m * sizeof(fb2_pair_out));
         };
         std::vector<cudaEvent_t> ev_s0(slabs.size(), nullptr), ev_s1(slabs.size(), nullptr);   // per-slab kernel time
         for (size_t k = 0; k < slabs.size() && rc == FB2_OK; ++k) {
@@ -1380,7 +1387,8 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
             cu(cudaEventRecord(ev_k[b], st_k));
             if (k >= 2) drain(k - 2);               // host copy of slab k-2 while the kernel of slab k runs; frees h_pin[b]
             cu(cudaStreamWaitEvent(st_c, ev_k[b], 0));
-            cu(cudaMemcpyAsync(h_pin[b], d_o[b].p, m * sizeof(fb2_pair_out), cudaMemcpyDeviceToHost, st_c));
+            cu(cudaMemcpyAsync(out_pinned ? (void *)(out + (q - q0) * n_sk) : (void *)h_pin[b], d_o[b].p, m * sizeof(fb2_pair_out),
+                               cudaMemcpyDeviceToHost, st_c));
             cu(cudaEventRecord(ev_c[b], st_c));
             cu(cudaStreamWaitEvent(st_k, ev_c[b], 0));                  // the kernel of slab k+2 reuses d_o[b]
         }

@@ -172,7 +172,8 @@ typedef struct fb2_pair_out {
 int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
                    double scale, const uint32_t *q_idx, const uint32_t *r_idx, size_t n_pairs,
                    fb2_pair_out *out, int32_t device);
-/* All ordered pairs (q, r), q in [q0,q1), r in [0,n_sk): out[(q-q0)*n_sk + r]. */
+/* All ordered pairs (q, r), q in [q0,q1), r in [0,n_sk): out[(q-q0)*n_sk + r].  `out` is host memory; a pinned
+ * array (cudaHostAlloc / cudaHostRegister) receives the device copies directly, pageable memory goes through staging. */
 int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
                        double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device);
 /* Measurement aid: summed device time (ms) of the kernels of this thread's last fb2_dist_all_pairs. */

@@ -501,6 +501,11 @@ def test_dist_all_pairs_multi_slab(fb):
         t = min(int(A[-1]), int(B[-1]))
         assert tuple(got[a, b]) == (c, int(np.searchsorted(A, np.uint64(t), side="right")),
                                     int(np.searchsorted(B, np.uint64(t), side="right"))), (a, b)
+    # a pinned result array takes the device copies directly: same bits
+    import torch
+    pin = torch.empty((n * n, 3), dtype=torch.int32, pin_memory=True)
+    got_p = fb.dist_all_pairs(mat, lens, 0.0, out=pin.numpy().view(np.uint32))
+    assert np.array_equal(got_p, got)
     # diagonal: a sketch against itself
     assert np.array_equal(got[np.arange(n), np.arange(n)], np.tile(np.array([m, m, m], np.uint32), (n, 1)))
 
