@@ -40,7 +40,7 @@ struct ParseCarry {
     uint64_t chunk_raw_base; // raw_total before the current chunk
     uint32_t chunk_syms;     // symbols produced by the current chunk (all regions)
     uint32_t cprev1, cprev2; // prev1 / prev2 as they were at the start of the current chunk
-    uint32_t pad;
+    uint32_t max_region_syms;// largest region of the current chunk (symbols): bounds the hash kernel's item space
 };
 
 // Counters of one hash launch (two slots: chunk c+1 may be hashed while chunk c is verified).

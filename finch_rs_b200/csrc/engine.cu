@@ -582,8 +582,8 @@ static ChunkGeom make_geom(uint32_t len) {
 static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, int par) {
     SketchState *dst = (SketchState *)s->d_state.p;
     LaunchSlot *slot = dev_slot(s, par);
-    const uint32_t total_blocks = g.n_st * g.hash_tiles;
-    const uint32_t per_blk = std::min<uint32_t>(HASH_TILE, g.st_bytes);   // positions a block can hold (small chunks: small regions)
+    const uint32_t total_blocks = g.n_st;      // launches cover whole symbol regions
+    const uint32_t per_blk = g.st_bytes;       // positions a region can hold
     uint32_t b = 0;
     bool known = false;
     double fill = 1.0;  // symbols per launched position
@@ -620,8 +620,8 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
         CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
         if (s->timing) CU(cudaEventRecord(s->ev_t0, s->st));
         // candidate-dense launches (infinite / provisional threshold, early ramp) reserve log slots in big batches
-        launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, b, b + nb, s->d_rcount[par].as<uint32_t>(), ord_base, dst, slot,
-                    log_view(s, par), s->prm.hash_seed, 31u, s->st);
+        launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, b, b + nb, s->d_rcount[par].as<uint32_t>(),
+                    (const ParseCarry *)s->d_carry.p, ord_base, dst, slot, log_view(s, par), s->prm.hash_seed, 31u, s->st);
         if (s->timing) CU(cudaEventRecord(s->ev_t1, s->st));
         s->stats.kernel_launches++; s->stats.hash_launches++;
         TRY(pull_state(s));
@@ -684,7 +684,7 @@ static int settle(fb2_sketcher *s, int q) {
     s->stats.hash_symbols += sl.chunk_syms;
     if (sl.decision == DECIDE_OVERFLOW) {
         // nothing of this chunk was absorbed: hash it again in bounded launches
-        const double pos = (double)g.n_st * g.hash_tiles * std::min<uint32_t>(HASH_TILE, g.st_bytes);
+        const double pos = (double)g.n_st * g.st_bytes;
         s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (uint32_t)std::min(pos / 4.0, (double)(s->log_cap / 2)));
         s->steady = false;
         TRY(pull_state(s));
@@ -698,7 +698,7 @@ static int settle(fb2_sketcher *s, int q) {
         *s->h_state = snap;   // exact as of the end of this chunk's absorb
     }
     // adapt the launch size to the observed candidate rate
-    const double pos = std::max(1.0, (double)g.n_st * g.hash_tiles * std::min<uint32_t>(HASH_TILE, g.st_bytes));
+    const double pos = std::max(1.0, (double)g.n_st * g.st_bytes);
     const double per_pos = std::max((double)sl.log_count, 1.0) / pos;
     double next = (double)(s->log_cap / 4) / per_pos;
     if (next > 2147483648.0) next = 2147483648.0;
@@ -739,8 +739,8 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     s->ordinal += (uint64_t)g.n_st * g.st_bytes;
     s->par ^= 1;
 
-    const uint32_t total_blocks = g.n_st * g.hash_tiles;
-    const double positions = (double)total_blocks * std::min<uint32_t>(HASH_TILE, g.st_bytes);
+    const uint32_t total_blocks = g.n_st;      // regions
+    const double positions = (double)g.n_st * g.st_bytes;
     if (!s->timing && positions <= (double)s->next_launch) s->steady = true;
     if (s->steady && !s->timing && positions <= (double)s->next_launch) {
         // asynchronous: hash the whole chunk, let the device decide about absorbing, snapshot the
@@ -752,7 +752,7 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
         cudaStream_t ab = getenv("FB2_NO_ABSORB_STREAM") ? s->st : s->st2;
         CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
         launch_note_chunk_syms(slot, dc, s->st);
-        launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, total_blocks, s->d_rcount[par].as<uint32_t>(), ord_base, dst,
+        launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, total_blocks, s->d_rcount[par].as<uint32_t>(), dc, ord_base, dst,
                     slot, log_view(s, par), s->prm.hash_seed, 3u, s->st);
         if (ab != s->st) {
             CU(cudaEventRecord(s->ev_hash[par], s->st));

@@ -314,8 +314,9 @@ static_assert(HP_BUF % 16u == 0, "TMA size granularity");
 template <int K, bool SEED0>
 __global__ void __launch_bounds__(HP_WARPS * 32, 1)
 hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r starts at SYM_FRONT + r * region_stride
-            ChunkGeom g, uint32_t w0, uint32_t w1, // item range [w0, w1) of this launch (region-major)
-            const uint32_t *__restrict__ region_count, uint64_t ord_base, const SketchState *st,
+            ChunkGeom g, uint32_t r0, uint32_t n_regions, // regions [r0, r0 + n_regions) of this launch
+            const uint32_t *__restrict__ region_count, const ParseCarry *__restrict__ carry, uint64_t ord_base,
+            const SketchState *st,
             LaunchSlot *slot, LogView log, int k_rt, uint64_t seed, HashConsts hc) {
     extern __shared__ __align__(128) uint8_t hp_smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -365,19 +366,22 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
     const uint32_t T_hi = (uint32_t)(T >> 32);
     U2 seed2; seed2.lo = (uint32_t)seed; seed2.hi = (uint32_t)(seed >> 32);
 
-    // item -> (region, first position, symbols in the region); skips items past the end of their region
+    // Work items in SLICE-major order: item it = slice (it / n_regions) of region r0 + it % n_regions.  Regions are
+    // rarely full (FASTQ: ~48 % of the raw bytes are symbols), so the item space is cut at the largest
+    // region of the chunk (pack_kernel keeps the maximum): slices past it are never claimed, and the items
+    // a warp does claim are live except in the last slice of shorter regions.  Items are claimed from a
+    // per-launch counter (dynamic balance; a static round-robin would resonate with the region layout).
+    const uint32_t slices = min((carry->max_region_syms + HP_SLICE - 1u) / HP_SLICE, (g.st_bytes + HP_SLICE - 1u) / HP_SLICE);
+    const uint32_t w1 = slices * n_regions;      // one past the last item
     uint32_t it_region = 0, it_pb = 0, it_end = 0;
-    // Items are claimed from a per-launch counter: regions are rarely full (FASTQ: ~48 % symbols), so a
-    // static round-robin would hand some warps only the empty tail items of every region.
     auto next_live = [&]() -> uint32_t {
         while (true) {
             uint32_t it = 0;
-            if (lane == 0) it = w0 + atomicAdd(&slot->next_item, 1u);
+            if (lane == 0) it = atomicAdd(&slot->next_item, 1u);
             it = __shfl_sync(0xffffffffu, it, 0);
             if (it >= w1) return w1;
-            const uint32_t blk = it / HP_ITEMS_PER_TILE, slice = it - blk * HP_ITEMS_PER_TILE;
-            const uint32_t region = blk / g.hash_tiles, lt = blk - region * g.hash_tiles;
-            const uint32_t pb = lt * HASH_TILE + slice * HP_SLICE, end = region_count[region];
+            const uint32_t slice = it / n_regions, region = r0 + (it - slice * n_regions);
+            const uint32_t pb = slice * HP_SLICE, end = region_count[region];
             if (pb < end) { it_region = region; it_pb = pb; it_end = end; return it; }
         }
     };
@@ -520,9 +524,9 @@ __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32
 __global__ void push_commit_kernel(LaunchSlot *slot, uint32_t n) { slot->launch_kmers += n; }
 
 template <int K, bool SEED0>
-static void launch_hash_ks(uint32_t w0, uint32_t w1, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
-                           uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, int k, uint64_t seed,
-                           uint32_t log_reserve, cudaStream_t stream) {
+static void launch_hash_ks(uint32_t r0, uint32_t n_regions, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
+                           const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
+                           int k, uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
     static int sms[64] = {};   // per device: SM count, set once the shared-memory attribute is in place
     int dev = 0;
     cudaGetDevice(&dev);
@@ -536,27 +540,26 @@ static void launch_hash_ks(uint32_t w0, uint32_t w1, const uint8_t *symbuf, Chun
     HashConsts hc;
     hc.stride64 = HP_R64 * 8u; hc.stride32 = HP_R32 * 4u; hc.stride1 = 8u; hc.one = 1u;
     hc.log_reserve = log_reserve;
-    const uint32_t items = w1 - w0;
-    const uint32_t ctas = std::min<uint32_t>((uint32_t)sms[dev], (items + HP_WARPS - 1) / HP_WARPS);
-    hash_kernel<K, SEED0><<<ctas, HP_WARPS * 32, HP_SMEM, stream>>>(symbuf, g, w0, w1, region_count, ord_base, st, slot, log,
-                                                                   k, seed, hc);
+    const uint64_t items_ub = (uint64_t)n_regions * ((g.st_bytes + HP_SLICE - 1u) / HP_SLICE);   // the device cuts it at the largest region
+    const uint32_t ctas = (uint32_t)std::min<uint64_t>((uint64_t)sms[dev], (items_ub + HP_WARPS - 1) / HP_WARPS);
+    hash_kernel<K, SEED0><<<ctas, HP_WARPS * 32, HP_SMEM, stream>>>(symbuf, g, r0, n_regions, region_count, carry, ord_base, st,
+                                                                   slot, log, k, seed, hc);
 }
 template <int K>
-static void launch_hash_k(uint32_t w0, uint32_t w1, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
-                          uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, int k, uint64_t seed,
-                          uint32_t log_reserve, cudaStream_t stream) {
-    if (seed == 0 && K > 0) launch_hash_ks<K, true>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
-    else launch_hash_ks<K, false>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
+static void launch_hash_k(uint32_t r0, uint32_t n_regions, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
+                          const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
+                          int k, uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
+    if (seed == 0 && K > 0) launch_hash_ks<K, true>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    else launch_hash_ks<K, false>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
 }
-// Hash the HASH_TILE-sized blocks [b0, b1) (region-major) of a chunk's symbol regions.
-void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t b0, uint32_t b1, const uint32_t *region_count,
-                 uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, uint64_t seed,
-                 uint32_t log_reserve, cudaStream_t stream) {
-    if (b1 <= b0) return;
-    const uint32_t w0 = b0 * HP_ITEMS_PER_TILE, w1 = b1 * HP_ITEMS_PER_TILE;
-    if (k == 21) launch_hash_k<21>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
-    else if (k == 31) launch_hash_k<31>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
-    else launch_hash_k<0>(w0, w1, symbuf, g, region_count, ord_base, st, slot, log, k, seed, log_reserve, stream);
+// Hash the symbol regions [r0, r1) of a chunk.
+void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t r0, uint32_t r1, const uint32_t *region_count,
+                 const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
+                 uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
+    if (r1 <= r0) return;
+    if (k == 21) launch_hash_k<21>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    else if (k == 31) launch_hash_k<31>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    else launch_hash_k<0>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
 }
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
                       uint64_t arena_base, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,

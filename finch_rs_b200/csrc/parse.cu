@@ -337,6 +337,7 @@ phase_scan_kernel(const uint32_t *__restrict__ st_map, ChunkGeom g, ParseCarry *
         if (g.len >= 2) { carry->prev2 = raw[g.len - 2]; carry->prev1 = raw[g.len - 1]; }
         else if (g.len == 1) { carry->prev2 = carry->prev1; carry->prev1 = raw[0]; }
         carry->chunk_syms = 0;
+        carry->max_region_syms = 0;
         carry->chunk_raw_base = carry->raw_total;
         carry->raw_total += g.len;
     }
@@ -719,7 +720,7 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
 
     // the hash kernel walks up to HASH_W positions past the region's end: make them breaks
     if (tid < HASH_W) region[out_off + tid] = SYM_BREAK;
-    if (tid == 0) { region_count[st] = out_off; atomicAdd(&carry->chunk_syms, out_off); }
+    if (tid == 0) { region_count[st] = out_off; atomicAdd(&carry->chunk_syms, out_off); atomicMax(&carry->max_region_syms, out_off); }
     if (MODE != MODE_LINES) {
         const unsigned long long bsum = block_reduce64((unsigned long long)bases_delta, sh8l, OpAdd(), 0ull);
         const unsigned long long rsum = block_reduce64(recs, sh8l, OpAdd(), 0ull);
