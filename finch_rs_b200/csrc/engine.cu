@@ -598,9 +598,13 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
     // redone with the exact ramp.  Either way the result is that of an infinite initial threshold.
     bool provisional = false;
     unsigned long long prov_kmers = 0;
-    if (s->h_state->threshold == ~0ULL && (uint64_t)total_blocks * per_blk > s->next_launch) {
+    if (s->h_state->threshold == ~0ULL) {
+        const bool big = (uint64_t)total_blocks * per_blk > s->next_launch;
         const uint64_t N = s->h_carry->chunk_syms, want = 16ull * s->size;
-        if (!s->skip_provisional && !s->timing && s->size > 0 && want + want / 8 <= s->log_cap / 2 && N > 4 * want &&
+        // (also when the chunk would fit one infinite-threshold launch: ~16 * size candidates instead of N)
+        // only on an EMPTY table: the fallback below clears it, which must not lose keys of earlier chunks
+        const bool empty = s->h_state->occupied == 0 && s->h_state->has_max_key == 0;
+        if (empty && !s->skip_provisional && !s->timing && s->size > 0 && want + want / 8 <= s->log_cap / 2 && N > 4 * want &&
             !getenv("FB2_NO_PROVISIONAL")) {
             unsigned long long T0 = (~0ULL / N) * want;
             if (s->scaled && T0 < s->max_hash) T0 = s->max_hash;
@@ -609,7 +613,7 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
             TRY(refresh_live_hist(s));
             provisional = true;
             s->next_launch = 0x7FFFFFFFu / HASH_TILE * HASH_TILE;   // the whole chunk
-        } else {
+        } else if (big) {
             s->next_launch = 32u * HASH_TILE;
         }
     }

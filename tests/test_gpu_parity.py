@@ -310,6 +310,21 @@ def test_provisional_first_threshold(fb, oracle, monkeypatch):
         assert s.stats()["provisional_redos"] == 1
 
 
+def test_provisional_threshold_needs_empty_table(fb, oracle, monkeypatch):
+    """Second chunk arrives while the threshold is still infinite and the table already holds keys of the
+    first chunk: the provisional threshold (whose fallback clears the table) must not be used then."""
+    monkeypatch.setenv("FB2_LOG_M", "0")
+    unit = b"ACGTTGCAAGGCTTAACCGGATATCGCGTA"
+    piece1 = b">polyA\n" + b"A" * 1_300_000 + b"\n"                   # >= 1 MiB: fed as its own chunk, 1 distinct k-mer
+    piece2 = b">rep\n" + unit * 60000 + b"\n>polyC\n" + b"C" * 200000 + b"\n"
+    data = piece1 + piece2
+    ovec, ototals, _ = oracle_sketch(oracle, data, "mash", 1000, 21, 0)
+    gres, gtotals, _ = gpu_sketch(fb, data, "mash", 1000, 21, 0, pieces=[len(piece1)])
+    assert gtotals == ototals
+    assert_same(gres, ovec, 21)
+    assert len(ovec["hashes"]) >= 31
+
+
 def test_sketch_files_many_workers(fb, oracle, tmp_path, monkeypatch):
     """fb2_sketch_files with more files than worker handles, mixed formats and sizes, twice (the second
     call re-uses the pooled handles): results in input order, identical to one-by-one sketching."""
