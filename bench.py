@@ -77,47 +77,68 @@ def gen_fastq(fb, genome, n_reads, seed, first_id=0, out_ptr=None, threads=None)
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms.  The sampler is started BEFORE the warm-up
+    (nvidia-smi needs a few hundred ms to deliver its first sample, the timed region is ~150 ms) and the
+    samples are cut to the timed region by their timestamps; if none falls inside, the samples of the
+    warm-up (same workload, same load) are used and `window` says so."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx, self.proc, self.path = gpu_index, None, None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(self.idx)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def region_start(self):
+        self.t0 = time.time()
+
+    def region_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
             return out
+        time.sleep(0.05)   # let the last samples of the region reach the file
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), f[6:10]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        os.unlink(self.path)
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.01 <= r[0] <= (self.t1 or 1e30) + 0.01]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed region (no sample fell inside the timed region)"
+        reasons = set()
+        for _, _, _, flags in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted(reasons), samples=len(inside), window=window)
         return out
 
 
@@ -286,14 +307,17 @@ def main():
         return hh, cc, xx, seq_len, n_kmers
 
     def timed(resident, steps, warmup, sample_clocks=False):
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.5)      # nvidia-smi start-up; the warm-up below keeps the GPU under the same load
         for _ in range(warmup):
             step(resident)
-        sampler = ClockSampler(local) if sample_clocks else None
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         if sampler:
-            sampler.start()
+            sampler.region_start()
         st0 = sk.stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -304,6 +328,8 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+        if sampler:
+            sampler.region_end()
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
         if dist is not None:
