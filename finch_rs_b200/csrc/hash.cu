@@ -430,13 +430,35 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
             const uint4 a = *reinterpret_cast<const uint4 *>(tile + t0);
             const uint4 b = *reinterpret_cast<const uint4 *>(tile + t0 + 16);
             const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            if (K == 21) {
+                // The 20 symbols in front are the words w[3..7]: build both rolling words at once instead of
+                // 20 pushes.  pack4: the 2-bit codes of 4 symbol bytes -> one byte (multiply gathers them).
+                uint32_t y[5];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (K > 0 && i < 32 - (K - 1)) continue;  // compile-time skip
-                const uint32_t s = w[i >> 2] >> (8 * (i & 3));
-                if (K == 0 && i < 32 - (k - 1)) continue;
-                r.push(s, k, mask);
-                if ((s & 0xFFu) >= 4u) brk = i - 32;
+                for (int q = 0; q < 5; ++q) y[q] = ((w[3 + q] & 0x03030303u) * 0x01041040u) >> 24;
+                const uint32_t plo = y[0] | (y[1] << 8) | (y[2] << 16) | (y[3] << 24), phi = y[4];   // code j at bits [2j, 2j+1]
+                // A = sum c_j << (2 + 2j): the 20 symbols sit one place above the slot the next push fills
+                r.A.lo = plo << 2; r.A.hi = __funnelshift_l(plo, phi, 2);
+                // B = sum (3 - c_j) << 2(19 - j): reverse the pair order (bit reverse + swap inside pairs), complement
+                uint32_t rhi = __brev(plo), rlo = __brev(phi);
+                rhi = ((rhi >> 1) & 0x55555555u) | ((rhi & 0x55555555u) << 1);
+                rlo = ((rlo >> 1) & 0x55555555u) | ((rlo & 0x55555555u) << 1);
+                r.B.lo = ~__funnelshift_r(rlo, rhi, 24);
+                r.B.hi = ~(rhi >> 24) & 0xFFu;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {              // last non-base symbol (symbols are 0..4: bit 2 marks a break)
+                    const uint32_t t = w[3 + q] & 0x04040404u;
+                    if (t) brk = 4 * (3 + q) + ((31 - __clz(t)) >> 3) - 32;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (K > 0 && i < 32 - (K - 1)) continue;  // compile-time skip
+                    const uint32_t s = w[i >> 2] >> (8 * (i & 3));
+                    if (K == 0 && i < 32 - (k - 1)) continue;
+                    r.push(s, k, mask);
+                    if ((s & 0xFFu) >= 4u) brk = i - 32;
+                }
             }
         } else {
             brk = -1;
