@@ -74,7 +74,7 @@ EXPORTS = [
     "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats",
     "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_filter_counts", "fb2_process_post_filter",
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_release_pool", "fb2_dist_batch",
-    "fb2_dist_all_pairs", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
+    "fb2_dist_all_pairs", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_old_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
     "fb2_synth_genome", "fb2_synth_fasta", "fb2_synth_fastq",
 ]
 
@@ -119,6 +119,8 @@ def lib():
     L.fb2_distance_finish.argtypes = [C.POINTER(_PairOut), C.c_uint8, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.fb2_distance_finish.restype = None
+    L.fb2_old_distance_finish.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint8, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.fb2_dist_last_kernel_ms.argtypes = []
     L.fb2_dist_last_kernel_ms.restype = C.c_double
     L.fb2_last_error.restype = C.c_char_p
@@ -528,9 +530,15 @@ def raw_distance(query_hashes, ref_hashes, scale=0.0):
 
 
 def distance(query: Sketch, ref: Sketch, old_mode=False) -> SketchDistance:
-    """distance.rs:9-47 (old_mode is the legacy path and is out of scope)."""
-    if old_mode:
-        raise FinchError(EUNSUPPORTED, "old_distance is out of scope")
+    """distance.rs:9-47, both modes."""
+    if old_mode:   # old_distance (distance.rs:136-157): |Q n R| over all of R
+        out = dist_batch([query.hashes_u64, ref.hashes_u64], [0], [1], 0.0)
+        cont, jac, md = C.c_double(), C.c_double(), C.c_double()
+        com, tot = C.c_uint64(), C.c_uint64()
+        _check(lib().fb2_old_distance_finish(int(out[0][0]), len(query.hashes_u64), len(ref.hashes_u64),
+                                             query.sketch_params.kmer_length, C.byref(cont), C.byref(jac), C.byref(md),
+                                             C.byref(com), C.byref(tot)))
+        return SketchDistance(cont.value, jac.value, md.value, com.value, tot.value, query.name, ref.name)
     s1 = query.sketch_params.scale if query.sketch_params.kind == KIND_SCALED else None
     s2 = ref.sketch_params.scale if ref.sketch_params.kind == KIND_SCALED else None
     min_scale = min(s1, s2) if (s1 is not None and s2 is not None) else 0.0

@@ -9,7 +9,7 @@
 //   update_sketch_params      cli/src/main.rs:336-441
 // The sequence work (sketch_files) and the sorted-hash intersections (raw_distance) run on the GPU
 // through libfinch_b200.so; there is no CPU fallback.  Not supported by this build (clear errors):
-// `.bsk` / `.msh` Cap'n Proto files (-b / -B), `--sketch-type none`, `--old-dist`, bz2 / xz input (gzip works).
+// `.bsk` / `.msh` Cap'n Proto files (-b / -B), `--sketch-type none`, bz2 / xz input (gzip works).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -371,7 +371,7 @@ void output_to(const std::string &payload, const char *output, const std::string
 
 // distance() for every (query, reference) pair that calc_sketch_distances keeps (main.rs:315-334,
 // distance.rs:9-47): the integer part of raw_distance runs as ONE batched GPU call per distinct scale.
-std::vector<SketchDistance> calc_sketch_distances(const std::vector<const Sketch *> &queries, const std::vector<Sketch> &refs, double max_dist) {
+std::vector<SketchDistance> calc_sketch_distances(const std::vector<const Sketch *> &queries, const std::vector<Sketch> &refs, bool old_mode, double max_dist) {
     struct Pair { uint32_t q, r; double scale; };
     std::vector<Pair> pairs;
     // one row per distinct sketch object: references first, then queries that are not references
@@ -385,8 +385,8 @@ std::vector<SketchDistance> calc_sketch_distances(const std::vector<const Sketch
     for (size_t r = 0; r < refs.size(); ++r)
         for (const Sketch *q : queries) {
             if (*q == refs[r]) continue;                                  // main.rs:324: equal BY VALUE (Q12)
-            double min_scale = 0.0;                                       // distance.rs:23-28
-            if (q->sketch_params.has_scale() && refs[r].sketch_params.has_scale()) min_scale = std::min(q->sketch_params.scale, refs[r].sketch_params.scale);
+            double min_scale = 0.0;                                       // distance.rs:23-28 (old mode: no scale)
+            if (!old_mode && q->sketch_params.has_scale() && refs[r].sketch_params.has_scale()) min_scale = std::min(q->sketch_params.scale, refs[r].sketch_params.scale);
             pairs.push_back({row_of(q), (uint32_t)r, min_scale});
         }
     std::vector<SketchDistance> out;
@@ -413,6 +413,11 @@ std::vector<SketchDistance> calc_sketch_distances(const std::vector<const Sketch
     for (size_t i = 0; i < pairs.size(); ++i) {
         const Sketch *q = rows[pairs[i].q];
         SketchDistance d;
+        if (old_mode) {                                                   // old_distance (distance.rs:136-157)
+            if (fb2_old_distance_finish(po[i].common, q->hashes.size(), refs[pairs[i].r].hashes.size(), q->sketch_params.kmer_length,
+                                        &d.containment, &d.jaccard, &d.mash_distance, &d.common_hashes, &d.total_hashes) != FB2_OK)
+                bail(fb2_last_error());
+        } else
         fb2_distance_finish(&po[i], q->sketch_params.kmer_length, &d.containment, &d.jaccard, &d.mash_distance, &d.common_hashes, &d.total_hashes);
         d.query = q->name; d.reference = refs[pairs[i].r].name;
         if (d.mash_distance <= max_dist) out.push_back(std::move(d));
@@ -442,7 +447,7 @@ int run(int argc, char **argv) {
             }
         }
     } else if (m.sub == "dist") {
-        if (m.is_present("old_dist_mode")) bail("--old-dist (old_distance, distance.rs:136-157) is not supported by the B200 build");
+        const bool old_mode = m.is_present("old_dist_mode");
         const double max_dist = get_float_arg(m, "max_distance", 1.0);
         const std::vector<Sketch> all = parse_mash_files(m);
         std::vector<const Sketch *> queries;
@@ -456,7 +461,7 @@ int run(int argc, char **argv) {
             if (all.empty()) bail("No sketches present!");
             queries.push_back(&all[0]);
         }
-        output_to(write_distances_json(calc_sketch_distances(queries, all, max_dist)),
+        output_to(write_distances_json(calc_sketch_distances(queries, all, old_mode, max_dist)),
                   m.is_present("output_file") ? m.value_of("output_file") : nullptr, ".json");
     } else if (m.sub == "hist") {
         const std::vector<Sketch> all = parse_mash_files(m);

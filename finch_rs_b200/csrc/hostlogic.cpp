@@ -335,6 +335,27 @@ extern "C" void fb2_distance_finish(const fb2_pair_out *p, uint8_t kmer_length, 
     if (total_hashes) *total_hashes = total;
 }
 
+// old_distance (distance.rs:136-157) from the integers the GPU returns: for sorted distinct lists its pointer
+// walk counts exactly |Q n R| (the `common` of fb2_dist_batch with scale 0) over all |R| reference hashes.
+// An empty query with a non-empty reference panics in the reference (index out of bounds): FB2_EINVAL here.
+extern "C" int fb2_old_distance_finish(uint64_t common, uint64_t query_len, uint64_t ref_len, uint8_t kmer_length,
+                                       double *containment, double *jaccard, double *mash_distance,
+                                       uint64_t *common_hashes, uint64_t *total_hashes) {
+    if (query_len == 0 && ref_len != 0) return fb2_fail(FB2_EINVAL, "old_distance: index out of bounds: the query sketch is empty");
+    const uint64_t total = ref_len;
+    const double cont = (double)common / (double)total;
+    const double jac = (double)common / (double)(common + 2 * (total - common));
+    double md = -1.0 * std::log((2.0 * jac) / (1.0 + jac)) / (double)kmer_length;
+    md = (md != md) ? 0.0 : (md > 0.0 ? md : 0.0);  // f64::max(0, md)
+    md = md < 1.0 ? md : 1.0;                       // f64::min(1, md)
+    if (containment) *containment = cont;
+    if (jaccard) *jaccard = jac;
+    if (mash_distance) *mash_distance = md;
+    if (common_hashes) *common_hashes = common;
+    if (total_hashes) *total_hashes = total;
+    return FB2_OK;
+}
+
 // ---- synthetic inputs ------------------------------------------------------------------
 static inline uint64_t splitmix64(uint64_t &x) {
     uint64_t z = (x += 0x9E3779B97F4A7C15ULL);

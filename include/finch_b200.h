@@ -183,6 +183,12 @@ void fb2_distance_finish(const fb2_pair_out *p, uint8_t kmer_length, double *con
                          double *jaccard, double *mash_distance, uint64_t *common_hashes,
                          uint64_t *total_hashes);
 
+/* old_distance (distance.rs:136-157, `--old-dist`) from `common` of a scale-0 fb2_dist_batch pair and the two
+ * sketch lengths; FB2_EINVAL where the reference panics (empty query, non-empty reference). */
+int fb2_old_distance_finish(uint64_t common, uint64_t query_len, uint64_t ref_len, uint8_t kmer_length,
+                            double *containment, double *jaccard, double *mash_distance,
+                            uint64_t *common_hashes, uint64_t *total_hashes);
+
 /* ---- misc --------------------------------------------------------------------------------- */
 const char *fb2_last_error(void);
 int fb2_device_count(void);

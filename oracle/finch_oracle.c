@@ -566,6 +566,22 @@ void fo_raw_distance(const uint64_t *q, size_t nq, const uint64_t *r, size_t nr,
     *jaccard = (total == 0) ? 1.0 : (double)common / (double)total;
     *common_out = common; *total_out = total;
 }
+/* distance.rs:136-157 old_distance, literally (the pointer walk with its `i < len - 1` guard).
+ * Returns -1 where the reference panics (empty query: index out of bounds). */
+int fo_old_distance(const uint64_t *q, size_t nq, const uint64_t *r, size_t nr,
+                    double *containment, double *jaccard, uint64_t *common_out, uint64_t *total_out) {
+    size_t i = 0; uint64_t common = 0, total = 0;
+    for (size_t x = 0; x < nr; ++x) {
+        if (nq == 0) return -1;
+        while (q[i] < r[x] && i < nq - 1) i++;
+        if (q[i] == r[x]) common++;
+        total++;
+    }
+    *containment = (double)common / (double)total;                               /* NaN for an empty reference */
+    *jaccard = (double)common / (double)(common + 2 * (total - common));
+    *common_out = common; *total_out = total;
+    return 0;
+}
 double fo_mash_distance(double jaccard, uint8_t k) {
     double md = -1.0 * log((2.0 * jaccard) / (1.0 + jaccard)) / (double)k;
     /* f64::min(1, f64::max(0, md)) -- Rust's max/min ignore NaN operands */

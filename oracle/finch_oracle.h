@@ -118,6 +118,8 @@ int fo_sketch_stream(const uint8_t *data, size_t len, const fo_sketch_params *sp
 void fo_sketch_free(fo_sketch *sk);
 
 /* ---- distance.rs:9-126 ---------------------------------------------------------------- */
+int fo_old_distance(const uint64_t *q, size_t nq, const uint64_t *r, size_t nr,
+                    double *containment, double *jaccard, uint64_t *common_out, uint64_t *total_out);
 void fo_raw_distance(const uint64_t *q, size_t nq, const uint64_t *r, size_t nr, double scale,
                      double *containment, double *jaccard, uint64_t *common, uint64_t *total);
 double fo_mash_distance(double jaccard, uint8_t k); /* distance.rs:35-41 */

@@ -94,6 +94,8 @@ def lib():
     L.fo_sketch_free.argtypes = [C.POINTER(Sketch)]
     L.fo_raw_distance.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double,
                                   C.POINTER(C.c_double), C.POINTER(C.c_double), u64p, u64p]
+    L.fo_old_distance.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                  C.POINTER(C.c_double), C.POINTER(C.c_double), u64p, u64p]
     L.fo_mash_distance.argtypes = [C.c_double, C.c_uint8]
     L.fo_mash_distance.restype = C.c_double
     _lib = L
@@ -285,6 +287,16 @@ def raw_distance(q, r, scale=0.0):
     cont, jac, com, tot = C.c_double(), C.c_double(), C.c_uint64(), C.c_uint64()
     lib().fo_raw_distance(q.ctypes.data, q.size, r.ctypes.data, r.size, scale, C.byref(cont),
                           C.byref(jac), C.byref(com), C.byref(tot))
+    return cont.value, jac.value, com.value, tot.value
+
+
+def old_distance(q, r):
+    """distance.rs:136-157; None where the reference panics (empty query with a non-empty reference)."""
+    q, r = np.ascontiguousarray(q, np.uint64), np.ascontiguousarray(r, np.uint64)
+    cont, jac, com, tot = C.c_double(), C.c_double(), C.c_uint64(), C.c_uint64()
+    if lib().fo_old_distance(q.ctypes.data, q.size, r.ctypes.data, r.size, C.byref(cont), C.byref(jac),
+                             C.byref(com), C.byref(tot)) != 0:
+        return None
     return cont.value, jac.value, com.value, tot.value
 
 

@@ -118,7 +118,6 @@ def test_flag_rules(finch, tmp_path):
         (["sketch", "-o", "x", "-O", str(f)], "cannot be used with"),
         (["dist", str(f), "-p", "-q", "a"], "cannot be used with"),
         (["sketch", "-b", "-O", str(f)], "not supported by the B200 build"),
-        (["dist", "--old-dist", str(f)], "not supported by the B200 build"),
         (["sketch", str(f)], "is not a sequence file?"),                                                          # main.rs:213-219
         (["sketch", "-O", str(tmp_path / "missing.sk")], "Error opening"),
         (["frobnicate", "x"], "wasn't expected"),
@@ -212,6 +211,11 @@ def test_sketch_in_place_then_dist(finch, tmp_path):
     dp = json.loads(finch("dist", "-p", str(tmp_path / "a.fa.sk"), str(b)).stdout)
     assert [(x["query"], x["reference"]) for x in dp] == [(str(b), str(a)), (str(a), str(b))]
     assert json.loads(finch("dist", "-p", "-d", "0.0", str(tmp_path / "a.fa.sk"), str(b)).stdout) == []
+    # --old-dist: old_distance (distance.rs:136-157) = |Q n R| over the whole reference
+    do = json.loads(finch("dist", "--old-dist", str(tmp_path / "a.fa.sk"), str(b)).stdout)
+    ocont, ojac, ocom, otot = o.old_distance(ha, hb)
+    assert (do[0]["commonHashes"], do[0]["totalHashes"], do[0]["containment"], do[0]["jaccard"]) == (ocom, otot, ocont, ojac)
+    assert abs(do[0]["mashDistance"] - o.mash_distance(ojac, 21)) < 1e-15
     # queries by name
     dq = json.loads(finch("dist", "-q", str(b), "--", str(tmp_path / "a.fa.sk"), str(b)).stdout)
     assert [(x["query"], x["reference"]) for x in dq] == [(str(b), str(a))]

@@ -534,6 +534,24 @@ def test_distance_scaled_end_to_end(fb):  # distance.rs:312-337
     assert (d.jaccard, d.containment, d.common_hashes) == (1.0, 1.0, 3)
 
 
+def test_distance_old_mode(fb, oracle):
+    """distance(.., old_mode=True) = old_distance (distance.rs:136-157) + the mash distance of distance.rs:35-41."""
+    rng = np.random.default_rng(41)
+    g = rand = gen.rand_seq(rng, 20000)
+    mut = bytearray(rand)
+    for pos in rng.choice(len(mut), size=400, replace=False):
+        mut[pos] = b"ACGT"[int(rng.integers(0, 4))]
+    sp = fb.SketchParams.mash(300, 300, True, 21, 0)
+    fp = fb.FilterParams(False, (None, None), 0.21, 0.1)
+    a = fb.sketch_stream(b">a\n" + g + b"\n", "a", sp, fp)
+    b = fb.sketch_stream(b">b\n" + bytes(mut) + b"\n", "b", sp, fp)
+    d = fb.distance(a, b, True)
+    cont, jac, com, tot = oracle.old_distance(a.hashes_u64, b.hashes_u64)
+    assert (d.containment, d.jaccard, d.common_hashes, d.total_hashes) == (cont, jac, com, tot)
+    assert d.mash_distance == oracle.mash_distance(jac, 21)
+    assert 0 < com < 300 and tot == 300
+
+
 def test_symbol_regions_match_normalize(fb, oracle):
     """pack_kernel output == per-record BREAK + normalize(false) (mash.rs:73), region by region."""
     rng = np.random.default_rng(99)

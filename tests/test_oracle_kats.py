@@ -167,3 +167,20 @@ def test_kat_hist(oracle):  # statistics.rs:53-129 incl. issue #63's sparse coun
     assert len(h) == 126497
     assert (h[0], h[1], h[2], h[3], h[126497 - 1]) == (0, 1, 1, 2, 1)
     assert list(oracle.hist([])) == []
+
+
+def test_old_distance_closed_form(oracle):
+    """distance.rs:136-157 has no test upstream (unpinned): the literal pointer walk equals |Q n R| over |R|
+    for sorted distinct lists, which is what the product computes from the GPU's intersection count."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    pool = np.unique(rng.integers(0, 2**63, size=400, dtype=np.uint64))
+    for _ in range(300):
+        q = np.sort(rng.choice(pool, size=int(rng.integers(1, 120)), replace=False))
+        r = np.sort(rng.choice(pool, size=int(rng.integers(0, 120)), replace=False))
+        got = oracle.old_distance(q, r)
+        com, tot = len(np.intersect1d(q, r)), len(r)
+        assert got[2:] == (com, tot)
+        if tot:
+            assert got[0] == com / tot and got[1] == com / (com + 2 * (tot - com))
+    assert oracle.old_distance(np.zeros(0, np.uint64), np.array([1], np.uint64)) is None      # the reference panics here
