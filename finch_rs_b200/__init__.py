@@ -61,7 +61,7 @@ class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("chunks", C.c_uint64), ("prunes", C.c_uint64), ("hash_launches", C.c_uint64),
                 ("hash_kernel_ms", C.c_double), ("parse_kernel_ms", C.c_double),
-                ("hash_symbols", C.c_uint64), ("provisional_redos", C.c_uint64)]
+                ("hash_symbols", C.c_uint64), ("provisional_redos", C.c_uint64), ("band_passes", C.c_uint64)]
 
 
 class _PairOut(C.Structure):

@@ -133,6 +133,7 @@ typedef struct fb2_stats {
     double parse_kernel_ms;  /* CUDA-event time of the parse/pack kernels */
     uint64_t hash_symbols;   /* symbols (bases + record breaks) the hash kernel walked */
     uint64_t provisional_redos; /* chunks redone because the provisional first threshold was too low */
+    uint64_t band_passes;       /* passes of the banded absorb over a candidate log */
 } fb2_stats;
 int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out);
 /* Inspection hook for tests: geometry (7 x u32), per-region symbol counts and the raw symbol buffer of the
