@@ -450,6 +450,23 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
                     const uint32_t t = w[3 + q] & 0x04040404u;
                     if (t) brk = 4 * (3 + q) + ((31 - __clz(t)) >> 3) - 32;
                 }
+            } else if (K == 31) {
+                // same for k = 31: the 30 symbols in front are bytes 2..31 of the halo
+                uint32_t y[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) y[q] = ((w[q] & 0x03030303u) * 0x01041040u) >> 24;
+                const uint32_t plo = y[0] | (y[1] << 8) | (y[2] << 16) | (y[3] << 24);
+                const uint32_t phi = y[4] | (y[5] << 8) | (y[6] << 16) | (y[7] << 24);     // code of byte i at bits [2i, 2i+1]
+                r.A.lo = __funnelshift_r(plo, phi, 2) & ~3u; r.A.hi = phi >> 2;            // codes 2..31 at pairs 1..30
+                uint32_t rhi = __brev(plo), rlo = __brev(phi);
+                rhi = ((rhi >> 1) & 0x55555555u) | ((rhi & 0x55555555u) << 1);
+                rlo = ((rlo >> 1) & 0x55555555u) | ((rlo & 0x55555555u) << 1);
+                r.B.lo = ~rlo; r.B.hi = ~rhi & 0x0FFFFFFFu;                                 // complement of code i at pair 31 - i, i >= 2
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t t = w[q] & (q == 0 ? 0x04040000u : 0x04040404u);
+                    if (t) brk = 4 * q + ((31 - __clz(t)) >> 3) - 32;
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
