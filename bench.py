@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K, N_HASHES, OVERSKETCH, READ_LEN = 21, 1000, 200, 150
+JSON_OUT = sys.stdout   # replaced in main(): the real stdout, kept apart from library chatter on fd 1
 GENOME_LEN, ERR_RATE = 5_000_000, 0.005
 ERR_FILTER, STRAND_FILTER = 1.0 * K / 100.0, 0.1   # cli.rs:264-265, :142
 
@@ -199,7 +200,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 def workload_name(args):
@@ -245,6 +246,12 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=6_000_000, help="--impl reference sample per step (all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 (NCCL prints its version
+    # there): keep the real stdout aside for the JSON line and send everything else to stderr.
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -413,7 +420,7 @@ def main():
     if rank == 0:
         if world > 1:
             assert len(gathered) == world and np.array_equal(gathered[0][0].cpu().numpy().view(np.uint64), hh)
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     sk.close()
     if dist is not None:
         dist.destroy_process_group()
