@@ -55,6 +55,42 @@ def test_number_formatting_matches_serde_and_rust_display(finch):
     assert finch("fmt-f64", *vals).stdout.split("\n")[:-1] == want
 
 
+def _ryu_like(v):
+    """serde_json / Ryu layout from Python's shortest round-trip digits (repr)."""
+    import decimal
+    if v == 0:
+        return "-0.0" if str(v).startswith("-") else "0.0"
+    sign, digits, exp = decimal.Decimal(repr(abs(v))).as_tuple()
+    d = "".join(map(str, digits)).rstrip("0") or "0"
+    kk = len(digits) + exp                      # v = 0.d1d2.. * 10^kk
+    neg = "-" if v < 0 else ""
+    if len(d) <= kk <= 16:
+        return neg + d + "0" * (kk - len(d)) + ".0"
+    if 0 < kk <= 16:
+        return neg + d[:kk] + "." + d[kk:]
+    if -5 < kk <= 0:
+        return neg + "0." + "0" * (-kk) + d
+    return neg + d[0] + ("." + d[1:] if len(d) > 1 else "") + "e" + str(kk - 1)
+
+
+def test_json_f64_random_values(finch):
+    """1000 random doubles over many magnitudes: same text as Ryu would print, and it parses back exactly."""
+    import random
+    import struct
+    rnd = random.Random(11)
+    vals = []
+    for _ in range(1000):
+        m = rnd.choice([rnd.random(), rnd.random() * 10 ** rnd.randint(-12, 20), rnd.randint(0, 10 ** 9) / 10 ** rnd.randint(0, 9)])
+        vals.append(-m if rnd.random() < 0.2 else m)
+    vals += [struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(62)))[0] for _ in range(200)]   # arbitrary bit patterns
+    out = finch("fmt-f64", *[repr(v) for v in vals]).stdout.split("\n")[:-1]
+    assert len(out) == len(vals)
+    for v, line in zip(vals, out):
+        got = line.split(" ")[0]
+        assert float(got) == v, (v, got)
+        assert got == _ryu_like(v), (v, got, _ryu_like(v))
+
+
 def test_sk_json_round_trip_is_byte_identical(finch, tmp_path):
     """json.rs:64-89,141-158: field order, quoted-decimal hashes, escaped names, `scale: null`."""
     f = tmp_path / "a.sk"
