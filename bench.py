@@ -3,22 +3,26 @@
 
 One "step" = one pass of the sketching hot path over one synthetic FASTQ of `--reads` x 150 bp
 reads (BASELINE.json configs[1]: 10 M reads, 1.5 Gbases, ~3.1 GB of FASTQ text; 300x coverage of a
-5 Mbp genome, 0.5 % substitution errors), with the CLI's resolved parameters for
+5 Mbp genome, 0.5 % substitution errors; tools/workloads.py), with the CLI's resolved parameters for
 `finch sketch -k 21 -n 1000 -f`:  MashSketcher heap 200 000, strand filter 0.1, err filter 0.21,
 final size 1000, strict.
 
   value  : whole-job Gbases/s, FASTQ bytes already resident in HBM when the timed region starts
            (fb2_sketcher_feed_device), result read back to the host and filtered every step.
   e2e    : the same through the host-facing C-ABI call (fb2_sketcher_feed_fastx) from a PINNED
-           host buffer, host->device copies inside the timed region.
+           host buffer, host->device copies inside the timed region; `h2d_ceiling_gbs` is the
+           platform's measured H2D rate for the same buffers at the same N with no kernels running.
   N > 1  : one rank per GPU (torchrun), every rank sketches its own file (independent files shard
            with no data-path collective) and one NCCL gather per step brings the finished
            1000-entry sketches to rank 0; weak scaling.
+  bit_exact : EVERY rank's full-size result (hashes, counts, extra counts, k-mer bytes, totals) is compared
+           with the sha256 digest of the CPU oracle's result on the same bytes, committed under
+           tests/golden/full_digests.json (made by tests/golden/make_full_digests.py).
   --impl reference : the CPU path of the reference (oracle port; the Rust reference cannot be built
-           here) on all host cores, a bounded sample per step.
+           here) on all host cores, on the same workload (one file slice per core, as rayon would).
 """
 import argparse
-import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -31,11 +35,14 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-K, N_HASHES, OVERSKETCH, READ_LEN = 21, 1000, 200, 150
+import workloads as W   # noqa: E402  (tools/workloads.py: the configs as seeded synthetic inputs)
+
+K, N_HASHES, OVERSKETCH, READ_LEN = W.K_C2, W.N_HASHES, W.OVERSKETCH, W.READ_LEN
 JSON_OUT = sys.stdout   # replaced in main(): the real stdout, kept apart from library chatter on fd 1
-GENOME_LEN, ERR_RATE = 5_000_000, 0.005
 ERR_FILTER, STRAND_FILTER = 1.0 * K / 100.0, 0.1   # cli.rs:264-265, :142
+METRIC = "Gbases/s sketched (k=21, n=1000, 150bp FASTQ)"
 
 
 def load_oracle():
@@ -46,35 +53,57 @@ def load_oracle():
     return oracle
 
 
-def gen_fastq(fb, genome, n_reads, seed, first_id=0, out_ptr=None, threads=None):
-    """Deterministic synthetic FASTQ, generated in parallel slices (per-read RNG streams)."""
-    threads = threads or min(32, os.cpu_count() or 1)
-    need = fb.fastq_nbytes(n_reads, READ_LEN, first_id)
-    if out_ptr is None:
-        buf = np.empty(need, np.uint8)
-        base = buf.ctypes.data
-    else:
-        buf, base = None, out_ptr
-    per = (n_reads + threads - 1) // threads
-    jobs, off = [], 0
-    for t in range(threads):
-        a, b = t * per, min(n_reads, (t + 1) * per)
-        if a >= b:
-            break
-        nb = fb.fastq_nbytes(b - a, READ_LEN, first_id + a)
-        jobs.append((a, b - a, off, nb))
-        off += nb
-    assert off == need
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
-    def work(a, n, o, nb):
-        got = fb.lib().fb2_synth_fastq(base + o, nb, genome.ctypes.data, genome.size, n, READ_LEN, ERR_RATE, seed,
-                                       first_id + a, None)
-        assert got == nb
 
-    ths = [threading.Thread(target=work, args=j) for j in jobs]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    return buf, need, n_reads * READ_LEN
+def config_of(args, world):
+    """The `config` object: identical in the b200 arm and the reference arm for the same command line."""
+    nbytes = W.synth.fastq_nbytes(args.reads, READ_LEN, 0)
+    return {"workload": (f"configs[1]: single synthetic FASTQ {args.reads} x {READ_LEN} bp reads (5 Mbp genome, 0.5% errors), "
+                         f"k={K}, n={N_HASHES}, --filter on (heap {N_HASHES * OVERSKETCH}), per GPU"),
+            "reads_per_gpu": args.reads, "read_len": READ_LEN, "fastq_bytes_per_gpu": nbytes,
+            "bases_per_gpu": args.reads * READ_LEN,
+            "l2": "inputs (3.1 GB per step) are far larger than the 126 MB L2; no explicit flush",
+            "parallelism": (f"files x {world} (one file per GPU, NCCL gather of finished sketches)" if world > 1 else "1 GPU")}
+
+
+def load_digests():
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "full_digests.json")))
+    except Exception:
+        return {}
+
+
+def kernel_src_sha16():
+    """Identity of the hash kernel's source: profiles/*_ncu_hash.json entries are only valid for the same source."""
+    h = hashlib.sha256()
+    for f in ("hash.cu", "common.cuh", "device_types.cuh"):
+        h.update(open(os.path.join(ROOT, "finch_rs_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def profiled_traffic():
+    """dram bytes per launch of the hash kernel from the newest committed ncu capture of THIS kernel source."""
+    pdir = os.path.join(ROOT, "profiles")
+    sha = kernel_src_sha16()
+    best = None
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if not (name.endswith(".json") and "ncu_hash" in name):
+            continue
+        try:
+            d = json.load(open(os.path.join(pdir, name)))
+        except Exception:
+            continue
+        if d.get("kernel_src_sha16") == sha:
+            best = (d, name)
+    if not best:
+        return None, f"no profiles/*ncu_hash*.json for kernel source {sha}"
+    d, name = best
+    return d, name
 
 
 class ClockSampler:
@@ -151,51 +180,62 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_baseline(fb, oracle, genome, seed, n_reads, threads):
-    """Oracle port timed on the host cores on a bounded sample of the same workload.
-    threads > 1 mirrors rayon's only parallelism: one sketcher per file (lib.rs:34-36)."""
-    per = n_reads // threads
-    bufs = [gen_fastq(fb, genome, per, seed, first_id=i * per, threads=1)[0].tobytes() for i in range(threads)]
+def cpu_sketch_slices(oracle, slices):
+    """Oracle port over `slices` (one FASTQ byte buffer per thread) concurrently -- rayon's only parallelism is
+    one sketcher per file (lib.rs:34-36).  -> (seconds, results)"""
     sp = oracle.mash_params(N_HASHES * OVERSKETCH, N_HASHES, True, K, 0)
-    res = [None] * threads
+    res = [None] * len(slices)
 
     def work(i):
-        res[i] = oracle.sketch_stream(bufs[i], sp, oracle.make_filter(True, (None, None), ERR_FILTER, STRAND_FILTER))
+        res[i] = oracle.sketch_stream(slices[i], sp, oracle.make_filter(True, (None, None), ERR_FILTER, STRAND_FILTER))
 
     t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(slices))]
     [t.start() for t in ths]
     [t.join() for t in ths]
     dt = time.perf_counter() - t0
     assert all(r[0] == oracle.OK for r in res)
-    bases = per * threads * READ_LEN
-    return bases / dt / 1e9, dt, bufs[0], res[0][1]
+    return dt, res
+
+
+def fastq_slices(genome, seed, n_reads, parts):
+    """The workload's FASTQ cut into `parts` files of whole reads (same reads, same bytes per read)."""
+    per = (n_reads + parts - 1) // parts
+    out, first = [], 0
+    while first < n_reads:
+        n = min(per, n_reads - first)
+        out.append(W.synth.synth_fastq(genome, n, READ_LEN, W.ERR_RATE, seed, first_read_id=first)[0])
+        first += n
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) on all host
-    cores; each step sketches a bounded sample (cores x sample_reads reads) of the same workload."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on all host cores over
+    the SAME workload as the b200 arm (args.reads reads per step), cut into one file per core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import finch_rs_b200 as fb   # only for the synthetic generator (host code in the product lib)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     oracle = load_oracle()
-    cores = os.cpu_count() or 1
-    genome = fb.synth_genome(GENOME_LEN, 2)
-    per_core = max(2000, args.ref_reads // cores)
+    cores = host_cores()
+    genome = W.c2_genome()
+    n_reads = args.ref_reads or args.reads
+    slices = fastq_slices(genome, W.c2_seed(0), n_reads, cores)     # generated once, outside the timed steps
     vals = []
     for it in range(args.warmup + args.steps):
-        v, dt, _, _ = cpu_baseline(fb, oracle, genome, 3, per_core * cores, cores)
+        dt, _ = cpu_sketch_slices(oracle, slices)
         if it >= args.warmup:
-            vals.append((v, dt))
-    value = float(np.mean([v for v, _ in vals]))
-    ms = float(np.mean([dt for _, dt in vals])) * 1e3
-    sample = f"{per_core * cores} reads x {READ_LEN} bp per step ({per_core} per core, one file per core as rayon would)"
+            vals.append(dt)
+    bases = n_reads * READ_LEN
+    ms = float(np.mean(vals)) * 1e3
+    value = bases / (ms * 1e-3) / 1e9
+    sample = (f"{n_reads} reads x {READ_LEN} bp per step = the whole workload of one GPU, as {len(slices)} files of "
+              f"{(n_reads + cores - 1) // cores} reads, one per core (rayon's file-level parallelism; upstream runs ONE file on one core)")
     line = {
-        "impl": "reference", "metric": "Gbases/s sketched (k=21, n=1000, 150bp FASTQ)", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "CPU reference arm: bounded sample of the workload"},
+        "config": config_of(args, world),
         "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -203,22 +243,15 @@ def run_reference(args):
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
-def workload_name(args):
-    return (f"configs[1]: single synthetic FASTQ {args.reads} x {READ_LEN} bp reads (5 Mbp genome, 0.5% errors), "
-            f"k={K}, n={N_HASHES}, --filter on (heap {N_HASHES * OVERSKETCH}), per GPU")
-
-
 def bind_to_gpu_numa_node(torch, local):
     """Multi-rank runs: keep this rank's threads (and so its pinned host buffers, first-touch) on the NUMA
     node its GPU hangs off, like `numactl --cpunodebind --membind`.  Best effort: None when unknown."""
     try:
-        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        if bdf is None:
-            import ctypes as C
-            buf = C.create_string_buffer(32)
-            if C.CDLL("libcudart.so.12").cudaDeviceGetPCIBusId(buf, 32, local) != 0:
-                return None
-            bdf = buf.value.decode()
+        import ctypes as C
+        buf = C.create_string_buffer(32)
+        if C.CDLL("libcudart.so.12").cudaDeviceGetPCIBusId(buf, 32, local) != 0:
+            return None
+        bdf = buf.value.decode()
         node = int(open(f"/sys/bus/pci/devices/{bdf.lower()}/numa_node").read())
         if node < 0:
             return None
@@ -241,9 +274,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000)
-    ap.add_argument("--cpu-reads", type=int, default=150_000, help="cpu_baseline sample (reads, 1 core)")
-    ap.add_argument("--ref-reads", type=int, default=6_000_000, help="--impl reference sample per step (all cores)")
+    ap.add_argument("--reads", type=int, default=W.C2_READS)
+    ap.add_argument("--cpu-reads", type=int, default=600_000, help="cpu_baseline sample (reads, 1 core)")
+    ap.add_argument("--ref-reads", type=int, default=0, help="--impl reference reads per step (0 = --reads: same config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 (NCCL prints its version
@@ -254,6 +287,7 @@ def main():
     os.dup2(2, 1)
     if args.warmup < 3:
         args.warmup = 3
+    W.synth.build()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -274,10 +308,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic input: pinned host copy + HBM-resident copy -------------------------------
-    genome = fb.synth_genome(GENOME_LEN, 2)
-    need = fb.fastq_nbytes(args.reads, READ_LEN, 0)
+    genome = W.c2_genome()
+    need = W.synth.fastq_nbytes(args.reads, READ_LEN, 0)
     host = torch.empty(need, dtype=torch.uint8, pin_memory=True)
-    _, nbytes, nbases = gen_fastq(fb, genome, args.reads, seed=3 + 1000 * rank, out_ptr=host.data_ptr())
+    _, nbytes, nbases = W.c2_fastq(rank, args.reads, genome, out_ptr=host.data_ptr(),
+                                   threads=max(1, min(32, host_cores() // max(1, world))))
     devbuf = host.to(dev, non_blocking=False)
     torch.cuda.synchronize()
 
@@ -287,13 +322,6 @@ def main():
     stream = torch.cuda.Stream(dev)   # a real (non-legacy) stream: kernels and the timing events share it
     torch.cuda.set_stream(stream)
     sk = sp.create_sketcher(stream=stream.cuda_stream)
-    L = fb.lib()
-
-    def finish(h, c, x):
-        """host filter + truncate (filter_counts + process_post_filter), as sketch_stream does"""
-        hh, cc, xx, _ = fb.filter_counts(fp, h, c, x, fb.FORMAT_FASTQ)
-        assert len(hh) >= N_HASHES, "strict: too few kmers"
-        return hh[:N_HASHES], cc[:N_HASHES], xx[:N_HASHES]
 
     gathered = []
 
@@ -304,14 +332,14 @@ def main():
         else:
             sk.feed_fastx_ptr(host.data_ptr(), nbytes, final=True)
         res = sk.sketch("bench.fq", fp)   # to_vec + filter_counts + process_post_filter (lib.rs:78-82)
-        hh, cc, xx, seq_len, n_kmers = res.hashes_u64, res.counts, res.extra_counts, res.seq_length, res.num_valid_kmers
         if dist is not None:  # one NCCL gather of the finished sketch (hash, count, extra) to rank 0
-            t = torch.from_numpy(np.stack([hh.view(np.int64), cc.astype(np.int64), xx.astype(np.int64)])).to(dev)
+            t = torch.from_numpy(np.stack([res.hashes_u64.view(np.int64), res.counts.astype(np.int64),
+                                           res.extra_counts.astype(np.int64)])).to(dev)
             outl = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
             dist.gather(t, outl, dst=0)
             if rank == 0:
                 gathered[:] = outl
-        return hh, cc, xx, seq_len, n_kmers
+        return res
 
     def timed(resident, steps, warmup, sample_clocks=False):
         sampler = ClockSampler(local) if sample_clocks else None
@@ -347,76 +375,125 @@ def main():
         return ms, last, {k: st1[k] - st0[k] for k in st1}, clocks
 
     ms_res, last_res, stats_res, clocks = timed(True, args.steps, args.warmup, sample_clocks=True)
-    ms_e2e, last_e2e, stats_e2e, _ = timed(False, max(3, args.steps // 2), 1)
     e2e_steps = max(3, args.steps // 2)
+    ms_e2e, last_e2e, stats_e2e, _ = timed(False, e2e_steps, 1)
 
-    # ---- roofline of the dominant kernel (k-mer hash kernel), CUDA events on its own stream ----
+    # ---- platform H2D ceiling: the same pinned buffers, all N ranks at once, no kernels ---------------------
+    def h2d_ceiling(reps=3):
+        for _ in range(1):
+            devbuf.copy_(host, non_blocking=True)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            devbuf.copy_(host, non_blocking=True)
+        e1.record(stream)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return nbytes * reps * world / (ms * 1e-3) / 1e9     # aggregate GB/s over all ranks
+    h2d_gbs = h2d_ceiling()
+
+    # ---- roofline of the dominant kernel (k-mer hash kernel): CUDA events around every launch of the SAME
+    # asynchronous path the timed region ran (events are read back when the chunk is settled) -------------------
+    ROOF_STEPS = 3
     sk.enable_timing(True)
+    step(True)
+    torch.cuda.synchronize()
     s0 = sk.stats()
-    for _ in range(2):
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(stream)
+    for _ in range(ROOF_STEPS):
         step(True)
+    r1.record(stream)
+    torch.cuda.synchronize()
     s1 = sk.stats()
     sk.enable_timing(False)
+    roof_ms_per_step = r0.elapsed_time(r1) / ROOF_STEPS
     hash_ms = s1["hash_kernel_ms"] - s0["hash_kernel_ms"]
     hash_syms = s1["hash_symbols"] - s0["hash_symbols"]
     hash_launches = s1["hash_launches"] - s0["hash_launches"]
     parse_ms = s1["parse_kernel_ms"] - s0["parse_kernel_ms"]
     peak, peak_src = measured_peak()
     achieved = hash_syms * 1.0 / (hash_ms * 1e-3) / 1e9 if hash_ms > 0 else 0.0   # 1 B per base
+    prof, prof_name = profiled_traffic()
 
-    # ---- correctness at full size: size-independent properties ----------------------------------
-    hh, cc, xx, seq_len, n_kmers = last_res
-    assert seq_len == nbases, (seq_len, nbases)
-    assert n_kmers == args.reads * (READ_LEN - K + 1), n_kmers           # no N in the synthetic reads
+    # ---- correctness at FULL size: oracle digest of this rank's input + size-independent properties --------------
+    res = last_res
+    hh, cc, xx = res.hashes_u64, res.counts, res.extra_counts
+    assert res.seq_length == nbases, (res.seq_length, nbases)
+    assert res.num_valid_kmers == args.reads * (READ_LEN - K + 1), res.num_valid_kmers   # no N in the synthetic reads
     assert np.all(hh[1:] > hh[:-1]) and len(hh) == N_HASHES               # strictly ascending, final size
     assert np.all(xx <= cc) and np.all(cc >= 1)
-    assert all(np.array_equal(a, b) for a, b in zip(last_res[:3], last_e2e[:3])), "resident and e2e paths disagree"
+    dig = lambda r: W.sketch_digest(r.hashes_u64, r.counts, r.extra_counts, r.kmers[:, :K], r.seq_length, r.num_valid_kmers)
+    mine, mine_e2e = dig(last_res), dig(last_e2e)
+    assert mine == mine_e2e, "resident and e2e paths disagree"
+    want = load_digests().get(f"c2/reads={args.reads}/rank={rank}")
+    exact = None
+    if want is not None:
+        exact = all(mine[k] == want[k] for k in ("n", "sha256", "seq_length", "num_valid_kmers"))
+    if dist is not None:
+        t = torch.tensor([-1 if exact is None else int(exact)], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        exact = None if int(t.item()) < 0 else bool(int(t.item()))
 
     total_bases = nbases * world
     value = total_bases * args.steps / (ms_res * 1e-3) / 1e9
     e2e_value = total_bases * e2e_steps / (ms_e2e * 1e-3) / 1e9
+    e2e_gbs = nbytes * world * e2e_steps / (ms_e2e * 1e-3) / 1e9
 
     line = {
-        "metric": "Gbases/s sketched (k=21, n=1000, 150bp FASTQ)", "value": value, "unit": "Gbases/s",
+        "metric": METRIC, "value": value, "unit": "Gbases/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "fastq_bytes_per_gpu": nbytes, "bases_per_gpu": nbases,
-                   "l2": "inputs (3.1 GB per step) are far larger than the 126 MB L2; no explicit flush",
-                   "parallelism": f"files x {world} (one file per GPU, NCCL gather of finished sketches)" if world > 1 else "1 GPU",
-                   "numa_node_rank0": numa,
-                   "chunk_mb": int(os.environ.get("FB2_CHUNK_MB", "128"))},
+        "config": config_of(args, world),
         "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(stats_e2e["h2d_bytes"] // e2e_steps),
                 "d2h_bytes_per_step": int(stats_e2e["d2h_bytes"] // e2e_steps), "ms_per_step": ms_e2e / e2e_steps,
-                "steps": e2e_steps},
+                "steps": e2e_steps, "h2d_gbs": e2e_gbs, "h2d_ceiling_gbs": h2d_gbs,
+                "frac_of_h2d_ceiling": e2e_gbs / h2d_gbs if h2d_gbs else None,
+                "h2d_ceiling_how": f"{world} rank(s) copying the same pinned buffers concurrently, no kernels, max over ranks"},
         "gpu_launches": int(stats_res["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch (61.0 M symbols of a
-                     # 128 MiB chunk), ncu --set full: profiles/r01_ncu_full_v10_hash_fullsize.txt  => 1.08 B/symbol
-                     "traffic": 66.04e6, "traffic_unit": "bytes per launch (61.0e6 algorithmic bytes)",
-                     "kernel": "fb2::hash_kernel<21>", "peak_source": peak_src,
+                     "traffic": (prof or {}).get("dram_bytes_per_launch"), "traffic_source": prof_name,
+                     "traffic_unit": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)",
+                     "kernel": "fb2::hash_kernel<21>", "kernel_src_sha16": kernel_src_sha16(), "peak_source": peak_src,
                      "algorithmic_bytes_per_unit": "1 B per base (symbol) walked by the hash kernel",
-                     "avg_launch_ms": hash_ms / max(1, hash_launches), "launches_per_step": hash_launches / 2,
-                     "hash_kernel_share_of_step": (hash_ms / 2) / (ms_res / args.steps),
-                     "parse_kernels_ms_per_step": parse_ms / 2,
-                     "note": "integer-issue-bound, not HBM-bound: ~100 SASS instr per k-mer split over the two half-rate integer pipes (ALU ~60%, IMAD ~60% busy, issue ~70% in ncu); see DESIGN.md"},
-        "bit_exact": None,
+                     "algorithmic_bytes_per_launch": hash_syms / max(1, hash_launches),
+                     "avg_launch_ms": hash_ms / max(1, hash_launches), "launches_per_step": hash_launches / ROOF_STEPS,
+                     "hash_kernel_share_of_step": (hash_ms / ROOF_STEPS) / roof_ms_per_step,
+                     "parse_kernels_ms_per_step": parse_ms / ROOF_STEPS, "ms_per_step_with_events": roof_ms_per_step,
+                     "how": "CUDA events around every hash / parse launch of the asynchronous (timed) path, read back at settle",
+                     "note": "integer-issue-bound, not HBM-bound (~100 SASS instr per k-mer on two half-rate integer pipes); see DESIGN.md"},
+        "bit_exact": exact,
+        "bit_exact_how": "sha256(hashes|counts|extras|kmers) + totals of every rank's FULL-size result vs tests/golden/full_digests.json (CPU oracle on the same bytes)",
         "aux": {"prunes_per_step": stats_res["prunes"] / args.steps, "chunks_per_step": stats_res["chunks"] / args.steps,
                 "hash_launches_per_step": stats_res["hash_launches"] / args.steps,
-                "kernel_launches_per_step": stats_res["kernel_launches"] / args.steps},
+                "kernel_launches_per_step": stats_res["kernel_launches"] / args.steps,
+                "numa_node_rank0": numa, "chunk_mb": int(os.environ.get("FB2_CHUNK_MB", "128")), "host_cores": host_cores()},
     }
 
-    # ---- CPU baseline (oracle port, 1 core, bounded sample) + bit-exactness on that sample ------
+    # ---- CPU baseline (oracle port, 1 core, bounded sample) + bit-exactness on that sample too ------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         oracle = load_oracle()
-        v, dt, sample_bytes, osk = cpu_baseline(fb, oracle, genome, 3, args.cpu_reads, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "Gbases/s", "cores": 1, "kind": "port",
-                                "sample": f"first {args.cpu_reads} reads x {READ_LEN} bp of the workload, {dt:.1f} s"}
-        gsk = fb.sketch_stream(sample_bytes, "sample.fq", fb.SketchParams.mash(N_HASHES * OVERSKETCH, N_HASHES, True, K, 0, local), fp)
-        line["bit_exact"] = bool(np.array_equal(gsk.hashes_u64, osk["hashes"]) and np.array_equal(gsk.counts, osk["counts"])
-                                 and np.array_equal(gsk.extra_counts, osk["extras"])
-                                 and (gsk.seq_length, gsk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"]))
+        n_s = min(args.cpu_reads, args.reads)
+        sample = fastq_slices(genome, W.c2_seed(0), n_s, 1)[0]
+        dt, ores = cpu_sketch_slices(oracle, [sample])
+        osk = ores[0][1]
+        line["cpu_baseline"] = {"value": n_s * READ_LEN / dt / 1e9, "unit": "Gbases/s", "cores": 1, "kind": "port",
+                                "sample": f"first {n_s} reads x {READ_LEN} bp of the workload, {dt:.1f} s"}
+        gsk = fb.sketch_stream(sample, "sample.fq", fb.SketchParams.mash(N_HASHES * OVERSKETCH, N_HASHES, True, K, 0, local), fp)
+        line["bit_exact_sample"] = bool(np.array_equal(gsk.hashes_u64, osk["hashes"]) and np.array_equal(gsk.counts, osk["counts"])
+                                        and np.array_equal(gsk.extra_counts, osk["extras"])
+                                        and (gsk.seq_length, gsk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"]))
     if rank == 0:
         if world > 1:
             assert len(gathered) == world and np.array_equal(gathered[0][0].cpu().numpy().view(np.uint64), hh)

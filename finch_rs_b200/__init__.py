@@ -75,7 +75,6 @@ EXPORTS = [
     "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_filter_counts", "fb2_process_post_filter",
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_release_pool", "fb2_dist_batch",
     "fb2_dist_all_pairs", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_old_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
-    "fb2_synth_genome", "fb2_synth_fasta", "fb2_synth_fastq",
 ]
 
 _lib = None
@@ -125,13 +124,6 @@ def lib():
     L.fb2_dist_last_kernel_ms.restype = C.c_double
     L.fb2_last_error.restype = C.c_char_p
     L.fb2_version.restype = C.c_char_p
-    L.fb2_synth_genome.argtypes = [vp, sz, C.c_uint64]
-    L.fb2_synth_genome.restype = sz
-    L.fb2_synth_fasta.argtypes = [vp, sz, sz, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_uint64]
-    L.fb2_synth_fasta.restype = sz
-    L.fb2_synth_fastq.argtypes = [vp, sz, vp, sz, C.c_uint64, C.c_uint32, C.c_double, C.c_uint64, C.c_uint64,
-                                  C.POINTER(C.c_uint64)]
-    L.fb2_synth_fastq.restype = sz
     _lib = L
     return L
 
@@ -545,42 +537,3 @@ def distance(query: Sketch, ref: Sketch, old_mode=False) -> SketchDistance:
     out = dist_batch([query.hashes_u64, ref.hashes_u64], [0], [1], min_scale)
     cont, jac, md, com, tot = _finish_pair(out[0], query.sketch_params.kmer_length)
     return SketchDistance(cont, jac, md, com, tot, query.name, ref.name)
-
-
-# ---- synthetic inputs ---------------------------------------------------------------
-def synth_genome(n_bases, seed):
-    out = np.empty(n_bases, np.uint8)
-    lib().fb2_synth_genome(out.ctypes.data, n_bases, seed)
-    return out
-
-
-def synth_fasta(n_bases, n_records=1, line_width=80, lower_frac=0.0, n_frac=0.0, seed=1):
-    need = lib().fb2_synth_fasta(None, 0, n_bases, n_records, line_width, lower_frac, n_frac, seed)
-    out = np.empty(need, np.uint8)
-    lib().fb2_synth_fasta(out.ctypes.data, need, n_bases, n_records, line_width, lower_frac, n_frac, seed)
-    return out
-
-
-def fastq_nbytes(n_reads, read_len, first_read_id=0):
-    """Exact size of synth_fastq's output: '@r<id>\\n' + seq + '\\n+\\n' + qual + '\\n' per read."""
-    total, lo, digits = 0, first_read_id, None
-    hi = first_read_id + n_reads
-    while lo < hi:
-        digits = len(str(lo))
-        nxt = min(hi, 10 ** digits)
-        total += (nxt - lo) * (2 + digits + 1 + read_len + 1 + 2 + read_len + 1)
-        lo = nxt
-    return total
-
-
-def synth_fastq(genome, n_reads, read_len=150, err_rate=0.005, seed=3, first_read_id=0, out=None):
-    genome = np.ascontiguousarray(genome, np.uint8)
-    need = fastq_nbytes(n_reads, read_len, first_read_id)
-    if out is None:
-        out = np.empty(need, np.uint8)
-    addr = out.ctypes.data if isinstance(out, np.ndarray) else int(out)
-    nb = C.c_uint64()
-    got = lib().fb2_synth_fastq(addr, need, genome.ctypes.data, genome.size, n_reads, read_len, err_rate, seed,
-                                first_read_id, C.byref(nb))
-    assert got == need, (got, need)
-    return out, int(nb.value)

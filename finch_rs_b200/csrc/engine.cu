@@ -95,7 +95,7 @@ struct fb2_sketcher {
     bool st2_dirty = false;          // work was queued on st2 since the last join
     bool skip_provisional = false;   // hash_range: the provisional threshold failed for this chunk, use the exact ramp
     bool own_stream = false;
-    cudaEvent_t ev_h2d[2]{}, ev_rawfree[2]{}, ev_t0 = nullptr, ev_t1 = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
+    cudaEvent_t ev_h2d[2]{}, ev_rawfree[2]{};
     bool rawfree_pending[2] = {false, false};
 
     size_t chunk_bytes = 0;
@@ -141,7 +141,30 @@ struct fb2_sketcher {
     uint32_t next_launch = 0;
     fb2_stats stats{};
     bool timing = false;
+    // kernel timing (fb2_sketcher_enable_timing): event pairs recorded around the hash / parse launches of
+    // whichever path runs (the asynchronous path stays asynchronous); resolved lazily by fb2_sketcher_stats
+    struct EvPair { cudaEvent_t a = nullptr, b = nullptr; };
+    std::vector<EvPair> ev_free, ev_hash_pending, ev_parse_pending;
 };
+
+static bool timing_begin(fb2_sketcher *s, fb2_sketcher::EvPair &p) {
+    if (!s->timing) return false;
+    if (!s->ev_free.empty()) { p = s->ev_free.back(); s->ev_free.pop_back(); }
+    else if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return false;
+    cudaEventRecord(p.a, s->st);
+    return true;
+}
+static void timing_end(fb2_sketcher *s, fb2_sketcher::EvPair &p, std::vector<fb2_sketcher::EvPair> &pending) {
+    cudaEventRecord(p.b, s->st);
+    pending.push_back(p);
+}
+static void timing_resolve(fb2_sketcher *s) {
+    if (s->ev_hash_pending.empty() && s->ev_parse_pending.empty()) return;
+    cudaStreamSynchronize(s->st);
+    for (auto &p : s->ev_hash_pending) { float ms = 0; if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) s->stats.hash_kernel_ms += ms; s->ev_free.push_back(p); }
+    for (auto &p : s->ev_parse_pending) { float ms = 0; if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) s->stats.parse_kernel_ms += ms; s->ev_free.push_back(p); }
+    s->ev_hash_pending.clear(); s->ev_parse_pending.clear();
+}
 
 // ---- small helpers ---------------------------------------------------------------------------
 static LogView log_view(fb2_sketcher *s, int par) {
@@ -274,8 +297,6 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
         CU(cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s->ev_rawfree[i], cudaEventDisableTiming));
     }
-    CU(cudaEventCreate(&s->ev_t0)); CU(cudaEventCreate(&s->ev_t1));
-    CU(cudaEventCreate(&s->ev_p0)); CU(cudaEventCreate(&s->ev_p1));
 
     s->chunk_bytes = env_size("FB2_CHUNK_MB", 128) << 20;
     if (s->chunk_bytes < (1u << 20)) s->chunk_bytes = 1u << 20;
@@ -326,10 +347,8 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
         if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
         if (s->ev_rawfree[i]) cudaEventDestroy(s->ev_rawfree[i]);
     }
-    if (s->ev_t0) cudaEventDestroy(s->ev_t0);
-    if (s->ev_t1) cudaEventDestroy(s->ev_t1);
-    if (s->ev_p0) cudaEventDestroy(s->ev_p0);
-    if (s->ev_p1) cudaEventDestroy(s->ev_p1);
+    timing_resolve(s);
+    for (auto &p : s->ev_free) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int i = 0; i < 2; ++i) {
         s->d_sym[i].release(); s->d_rcount[i].release(); s->log_hash[i].release(); s->log_kmer[i].release(); s->log_posx[i].release();
         if (s->h_snap[i]) cudaFreeHost(s->h_snap[i]);
@@ -606,7 +625,7 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
         // (also when the chunk would fit one infinite-threshold launch: ~16 * size candidates instead of N)
         // only on an EMPTY table: the fallback below clears it, which must not lose keys of earlier chunks
         const bool empty = s->h_state->occupied == 0 && s->h_state->has_max_key == 0;
-        if (empty && !s->skip_provisional && !s->timing && s->size > 0 && want + want / 8 <= s->log_cap / 2 && N > 4 * want &&
+        if (empty && !s->skip_provisional && s->size > 0 && want + want / 8 <= s->log_cap / 2 && N > 4 * want &&
             !getenv("FB2_NO_PROVISIONAL")) {
             unsigned long long T0 = (~0ULL / N) * want;
             if (s->scaled && T0 < s->max_hash) T0 = s->max_hash;
@@ -624,18 +643,14 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
         uint32_t nb = std::max<uint32_t>(s->next_launch / per_blk, 1u);
         nb = std::min(nb, total_blocks - b);
         CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
-        if (s->timing) CU(cudaEventRecord(s->ev_t0, s->st));
+        fb2_sketcher::EvPair evp;
+        const bool timed = timing_begin(s, evp);
         // candidate-dense launches (infinite / provisional threshold, early ramp) reserve log slots in big batches
         launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, b, b + nb, s->d_rcount[par].as<uint32_t>(),
                     (const ParseCarry *)s->d_carry.p, ord_base, dst, slot, log_view(s, par), s->prm.hash_seed, 31u, s->st);
-        if (s->timing) CU(cudaEventRecord(s->ev_t1, s->st));
+        if (timed) timing_end(s, evp, s->ev_hash_pending);
         s->stats.kernel_launches++; s->stats.hash_launches++;
         TRY(pull_state(s));
-        if (s->timing) {
-            float ms = 0;
-            CU(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
-            s->stats.hash_kernel_ms += ms;
-        }
         if (!known) {
             known = true;
             s->stats.hash_symbols += s->h_carry->chunk_syms;
@@ -733,11 +748,12 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     ParseCarry *dc = (ParseCarry *)s->d_carry.p;
     SketchState *dst = (SketchState *)s->d_state.p;
     uint8_t *tail_in = s->d_tail.as<uint8_t>() + 32 * s->tail_sel, *tail_out = s->d_tail.as<uint8_t>() + 32 * (s->tail_sel ^ 1);
-    if (s->timing) CU(cudaEventRecord(s->ev_p0, s->st));
+    fb2_sketcher::EvPair evparse;
+    const bool parse_timed = timing_begin(s, evparse);
     launch_phase(mode, d_raw, g, dc, s->d_stmap.as<uint32_t>(), s->d_ststate.as<uint32_t>(), s->st);
     launch_pack(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym[par].as<uint8_t>(), s->d_rcount[par].as<uint32_t>(),
                 tail_in, tail_out, s->st);
-    if (s->timing) CU(cudaEventRecord(s->ev_p1, s->st));
+    if (parse_timed) timing_end(s, evparse, s->ev_parse_pending);
     if (rawbuf >= 0) { CU(cudaEventRecord(s->ev_rawfree[rawbuf], s->st)); s->rawfree_pending[rawbuf] = true; }
     s->tail_sel ^= 1;
     s->stats.kernel_launches += (mode == MODE_LINES ? 3 : 4); s->stats.chunks++;
@@ -747,8 +763,8 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
 
     const uint32_t total_blocks = g.n_st;      // regions
     const double positions = (double)g.n_st * g.st_bytes;
-    if (!s->timing && positions <= (double)s->next_launch) s->steady = true;
-    if (s->steady && !s->timing && positions <= (double)s->next_launch) {
+    if (positions <= (double)s->next_launch) s->steady = true;
+    if (s->steady && positions <= (double)s->next_launch) {
         // asynchronous: hash the whole chunk, let the device decide about absorbing, snapshot the
         // state; the host looks at the outcome while the next chunk is already running
         // main stream: parse (above) and hash; absorb stream: log -> table, soft threshold, snapshot.
@@ -758,8 +774,11 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
         cudaStream_t ab = getenv("FB2_NO_ABSORB_STREAM") ? s->st : s->st2;
         CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
         launch_note_chunk_syms(slot, dc, s->st);
+        fb2_sketcher::EvPair evp;
+        const bool timed = timing_begin(s, evp);
         launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, total_blocks, s->d_rcount[par].as<uint32_t>(), dc, ord_base, dst,
                     slot, log_view(s, par), s->prm.hash_seed, 3u, s->st);
+        if (timed) timing_end(s, evp, s->ev_hash_pending);
         if (ab != s->st) {
             CU(cudaEventRecord(s->ev_hash[par], s->st));
             CU(cudaStreamWaitEvent(ab, s->ev_hash[par], 0));
@@ -780,11 +799,6 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
         TRY(settle(s, par ^ 1));
         TRY(pull_state(s));
         TRY(hash_range(s, g, ord_base, par));
-    }
-    if (s->timing) {
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, s->ev_p0, s->ev_p1));
-        s->stats.parse_kernel_ms += ms;
     }
     return FB2_OK;
 }
@@ -1269,6 +1283,8 @@ extern "C" int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint
 
 extern "C" int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out) {
     if (!s || !out) return fb2_fail(FB2_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    timing_resolve(s);
     *out = s->stats;
     return FB2_OK;
 }

@@ -355,97 +355,3 @@ extern "C" int fb2_old_distance_finish(uint64_t common, uint64_t query_len, uint
     if (total_hashes) *total_hashes = total;
     return FB2_OK;
 }
-
-// ---- synthetic inputs ------------------------------------------------------------------
-static inline uint64_t splitmix64(uint64_t &x) {
-    uint64_t z = (x += 0x9E3779B97F4A7C15ULL);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
-struct Rng {
-    uint64_t s;
-    explicit Rng(uint64_t seed) : s(seed) {}
-    uint64_t next() { return splitmix64(s); }
-    double unif() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
-};
-
-extern "C" size_t fb2_synth_genome(uint8_t *out, size_t n_bases, uint64_t seed) {
-    if (!out) return n_bases;
-    Rng r(seed);
-    size_t i = 0;
-    while (i < n_bases) {
-        uint64_t w = r.next();
-        for (int b = 0; b < 32 && i < n_bases; ++b, w >>= 2) out[i++] = (uint8_t)"ACGT"[w & 3];
-    }
-    return n_bases;
-}
-
-extern "C" size_t fb2_synth_fasta(uint8_t *out, size_t cap, size_t n_bases, uint32_t n_records,
-                                  uint32_t line_width, double lower_frac, double n_frac, uint64_t seed) {
-    if (n_records == 0) n_records = 1;
-    if (line_width == 0) line_width = 80;
-    Rng r(seed);
-    size_t o = 0;
-    auto put = [&](uint8_t c) { if (out && o < cap) out[o] = c; ++o; };
-    const size_t per = n_bases / n_records;
-    for (uint32_t rec = 0; rec < n_records; ++rec) {
-        const size_t len = rec + 1 == n_records ? n_bases - per * (n_records - 1) : per;
-        char hdr[64];
-        const int hl = snprintf(hdr, sizeof hdr, ">contig%u len=%zu\n", rec + 1, len);
-        for (int i = 0; i < hl; ++i) put((uint8_t)hdr[i]);
-        size_t i = 0, col = 0;
-        int run_kind = 0;        // 0 plain, 1 lowercase run, 2 N run
-        size_t run_left = 0;
-        uint64_t w = 0; int wb = 0;
-        while (i < len) {
-            if (run_left == 0) {
-                const double u = r.unif();
-                // runs of ~200 bases; fractions are of bases
-                if (u < n_frac) run_kind = 2; else if (u < n_frac + lower_frac) run_kind = 1; else run_kind = 0;
-                run_left = 100 + (size_t)(r.next() % 200);
-            }
-            if (wb == 0) { w = r.next(); wb = 32; }
-            uint8_t c = (uint8_t)"ACGT"[w & 3]; w >>= 2; --wb;
-            if (run_kind == 1) c = (uint8_t)(c | 0x20);
-            else if (run_kind == 2) c = 'N';
-            put(c); ++i; --run_left;
-            if (++col == line_width) { put('\n'); col = 0; }
-        }
-        if (col) put('\n');
-    }
-    return o;
-}
-
-extern "C" size_t fb2_synth_fastq(uint8_t *out, size_t cap, const uint8_t *genome, size_t genome_len,
-                                  uint64_t n_reads, uint32_t read_len, double err_rate, uint64_t seed,
-                                  uint64_t first_read_id, uint64_t *n_bases_out) {
-    if (!genome || genome_len < read_len) return 0;
-    size_t o = 0;
-    auto put = [&](uint8_t c) { if (out && o < cap) out[o] = c; ++o; };
-    const uint32_t err_thr = (uint32_t)(err_rate * 4294967296.0);
-    for (uint64_t i = 0; i < n_reads; ++i) {
-        Rng r(seed ^ ((first_read_id + i) * 0xD1342543DE82EF95ULL + 0x2545F4914F6CDD1DULL));  // per-read stream
-        const uint64_t id = first_read_id + i;
-        char hdr[32];
-        const int hl = snprintf(hdr, sizeof hdr, "@r%llu\n", (unsigned long long)id);
-        for (int j = 0; j < hl; ++j) put((uint8_t)hdr[j]);
-        const size_t start = (size_t)(r.next() % (genome_len - read_len + 1));
-        const bool rev = r.next() & 1;
-        for (uint32_t j = 0; j < read_len; ++j) {
-            uint8_t c = rev ? genome[start + read_len - 1 - j] : genome[start + j];
-            if (rev) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A';
-            const uint64_t w = r.next();
-            if ((uint32_t)w < err_thr) {  // substitution by one of the three other bases
-                const uint8_t alt = (uint8_t)"ACGT"[(w >> 32) & 3];
-                c = alt != c ? alt : (uint8_t)"ACGT"[((w >> 32) + 1) & 3];
-            }
-            put(c);
-        }
-        put('\n'); put('+'); put('\n');
-        for (uint32_t j = 0; j < read_len; ++j) put('I');
-        put('\n');
-    }
-    if (n_bases_out) *n_bases_out = n_reads * read_len;
-    return o;
-}

@@ -195,15 +195,6 @@ const char *fb2_last_error(void);
 int fb2_device_count(void);
 const char *fb2_version(void);
 
-/* Deterministic synthetic inputs, written into caller memory.  Return bytes
- * written, or the required size when out == NULL. */
-size_t fb2_synth_genome(uint8_t *out, size_t n_bases, uint64_t seed); /* ACGT, no framing */
-size_t fb2_synth_fasta(uint8_t *out, size_t cap, size_t n_bases, uint32_t n_records,
-                       uint32_t line_width, double lower_frac, double n_frac, uint64_t seed);
-size_t fb2_synth_fastq(uint8_t *out, size_t cap, const uint8_t *genome, size_t genome_len,
-                       uint64_t n_reads, uint32_t read_len, double err_rate, uint64_t seed,
-                       uint64_t first_read_id, uint64_t *n_bases_out);
-
 #ifdef __cplusplus
 }
 #endif

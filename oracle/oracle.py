@@ -258,8 +258,8 @@ def scaled_params(kmers_to_sketch=1000, kmer_length=21, scale=0.001, hash_seed=0
     return SketchParams(1, kmers_to_sketch, 0, 0, kmer_length, hash_seed, scale)
 
 
-def sketch_stream(data, sp, fp):
-    """lib.rs:51-94.  -> (rc, dict or None)"""
+def sketch_stream(data, sp, fp, kmers_array=False):
+    """lib.rs:51-94.  -> (rc, dict or None).  kmers_array: k-mers as one [n, k] uint8 array (large sketches)."""
     addr, n, keep = _buf(data)
     sk = Sketch()
     rc = lib().fo_sketch_stream(addr, n, C.byref(sp), C.byref(fp), C.byref(sk))
@@ -272,7 +272,9 @@ def sketch_stream(data, sp, fp):
         "hashes": np.ctypeslib.as_array(sk.hashes, (m,)).copy() if m else np.zeros(0, np.uint64),
         "counts": np.ctypeslib.as_array(sk.counts, (m,)).copy() if m else np.zeros(0, np.uint32),
         "extras": np.ctypeslib.as_array(sk.extras, (m,)).copy() if m else np.zeros(0, np.uint32),
-        "kmers": [bytes(np.ctypeslib.as_array(sk.kmers, (m * k,))[i * k:(i + 1) * k]) for i in range(m)] if m else [],
+        "kmers": ((np.ctypeslib.as_array(sk.kmers, (m * k,)).copy().reshape(m, k) if m else np.zeros((0, k), np.uint8))
+                  if kmers_array else
+                  [bytes(np.ctypeslib.as_array(sk.kmers, (m * k,))[i * k:(i + 1) * k]) for i in range(m)] if m else []),
         "format": sk.format,
         "filter_on": bool(sk.filters.filter_on == 1),
         "min_copies": int(sk.filters.abun_low) if sk.filters.has_abun_low else None,

@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
 def pytest_configure(config):
@@ -47,6 +48,14 @@ def have_gpu():
         return fb.lib().fb2_device_count() > 0
     except Exception:
         return False
+
+
+@pytest.fixture(scope="session")
+def synth():
+    """tools/synth.py: synthetic-input generators (test / bench infrastructure, not in the product library)."""
+    import synth as s
+    s.lib()
+    return s
 
 
 @pytest.fixture(scope="session")

@@ -84,18 +84,18 @@ def test_distance_finish_matches_oracle(fb, oracle):
         assert md == oracle.mash_distance(jac, 21)
 
 
-def test_generators_are_deterministic_and_parseable(fb, oracle):
-    g = fb.synth_genome(5000, 2)
-    assert set(np.unique(g).tolist()) <= set(b"ACGT") and np.array_equal(g, fb.synth_genome(5000, 2))
-    fq, nb = fb.synth_fastq(g, 1234, 150, 0.005, 3, first_read_id=95)
-    assert nb == 1234 * 150 and len(fq) == fb.fastq_nbytes(1234, 150, 95)
+def test_generators_are_deterministic_and_parseable(fb, synth, oracle):
+    g = synth.synth_genome(5000, 2)
+    assert set(np.unique(g).tolist()) <= set(b"ACGT") and np.array_equal(g, synth.synth_genome(5000, 2))
+    fq, nb = synth.synth_fastq(g, 1234, 150, 0.005, 3, first_read_id=95)
+    assert nb == 1234 * 150 and len(fq) == synth.fastq_nbytes(1234, 150, 95)
     rc, fmt, recs = oracle.parse_fastx(fq.tobytes())
     assert rc == oracle.OK and fmt == oracle.FMT_FASTQ and len(recs) == 1234 and all(len(r) == 150 for r in recs)
     # slices by read id compose to the same bytes
-    a, _ = fb.synth_fastq(g, 600, 150, 0.005, 3, first_read_id=95)
-    b, _ = fb.synth_fastq(g, 634, 150, 0.005, 3, first_read_id=695)
+    a, _ = synth.synth_fastq(g, 600, 150, 0.005, 3, first_read_id=95)
+    b, _ = synth.synth_fastq(g, 634, 150, 0.005, 3, first_read_id=695)
     assert np.array_equal(np.concatenate([a, b]), fq)
-    fa = fb.synth_fasta(100_000, n_records=3, line_width=60, lower_frac=0.02, n_frac=0.01, seed=4).tobytes()
+    fa = synth.synth_fasta(100_000, n_records=3, line_width=60, lower_frac=0.02, n_frac=0.01, seed=4).tobytes()
     rc, fmt, recs = oracle.parse_fastx(fa)
     assert rc == oracle.OK and fmt == oracle.FMT_FASTA and len(recs) == 3
     assert sum(len(oracle.normalize(r)) for r in recs) == 100_000

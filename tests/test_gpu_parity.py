@@ -175,19 +175,19 @@ def test_process_records_api(fb, oracle):
 
 @pytest.mark.parametrize("kind,size,k,scale", [("mash", 1000, 21, 0), ("mash", 200000, 21, 0),
                                                ("scaled", 1000, 31, 0.001), ("scaled", 0, 21, 0.01)])
-def test_medium_fasta(fb, oracle, kind, size, k, scale):
+def test_medium_fasta(fb, synth, oracle, kind, size, k, scale):
     """~3 Mbp multi-record FASTA with lowercase and N runs (C1/C4-shaped, reduced)."""
-    data = fb.synth_fasta(3_000_000, n_records=3, line_width=80, lower_frac=0.02, n_frac=0.01, seed=4).tobytes()
+    data = synth.synth_fasta(3_000_000, n_records=3, line_width=80, lower_frac=0.02, n_frac=0.01, seed=4).tobytes()
     ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, k, 0, scale or 0.001)
     gres, gtotals, _ = gpu_sketch(fb, data, kind, size, k, 0, scale or 0.001)
     assert gtotals == ototals
     assert_same(gres, ovec, k)
 
 
-def test_medium_fastq_with_coverage(fb, oracle):
+def test_medium_fastq_with_coverage(fb, synth, oracle):
     """C2-shaped, reduced: 40k x 150 bp reads from a 20 kbp genome (300x), 0.5% errors, heap 200000."""
-    genome = fb.synth_genome(20_000, 2)
-    data, nb = fb.synth_fastq(genome, 40_000, 150, 0.005, 3)
+    genome = synth.synth_genome(20_000, 2)
+    data, nb = synth.synth_fastq(genome, 40_000, 150, 0.005, 3)
     data = data.tobytes()
     ovec, ototals, _ = oracle_sketch(oracle, data, "mash", 200000, 21, 0)
     gres, gtotals, _ = gpu_sketch(fb, data, "mash", 200000, 21, 0)
@@ -205,11 +205,11 @@ def test_medium_fastq_with_coverage(fb, oracle):
     assert len(sk) == 1000
 
 
-def test_multi_chunk_stream(fb, oracle, monkeypatch):
+def test_multi_chunk_stream(fb, synth, oracle, monkeypatch):
     """Chunks of 1 MiB so one stream crosses many chunk seams inside the engine."""
     monkeypatch.setenv("FB2_CHUNK_MB", "1")
-    genome = fb.synth_genome(300_000, 9)
-    data, _ = fb.synth_fastq(genome, 25_000, 100, 0.01, 5)
+    genome = synth.synth_genome(300_000, 9)
+    data, _ = synth.synth_fastq(genome, 25_000, 100, 0.01, 5)
     data = data.tobytes()
     assert len(data) > 5 * (1 << 20)
     ovec, ototals, _ = oracle_sketch(oracle, data, "mash", 5000, 21, 0)
@@ -226,14 +226,14 @@ def test_multi_chunk_stream(fb, oracle, monkeypatch):
 
 
 @pytest.mark.parametrize("kind,size,scale", [("mash", 20000, 0.0), ("scaled", 1000, 0.01), ("scaled", 0, 0.02)])
-def test_many_chunks_steady_state(fb, oracle, monkeypatch, kind, size, scale):
+def test_many_chunks_steady_state(fb, synth, oracle, monkeypatch, kind, size, scale):
     """~40 chunks of 1 MiB: most of the stream runs through the asynchronous steady-state path (absorb on
     its own stream under the next chunk's parse kernels, soft threshold updates from the live table
     histogram after every chunk, occasional rebuilds).  High coverage so counts, strand counts and
     first-occurrence k-mers of hot keys accumulate across many chunks."""
     monkeypatch.setenv("FB2_CHUNK_MB", "1")
-    genome = fb.synth_genome(150_000, 21)
-    data, nb = fb.synth_fastq(genome, 130_000, 150, 0.01, 23)
+    genome = synth.synth_genome(150_000, 21)
+    data, nb = synth.synth_fastq(genome, 130_000, 150, 0.01, 23)
     data = data.tobytes()
     assert len(data) > 38 * (1 << 20)
     ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, 21, 0, scale or 0.001)
@@ -276,13 +276,13 @@ def test_sketch_files_gzip(fb, oracle, tmp_path):
     assert "gzip" in str(ei.value)
 
 
-def test_provisional_first_threshold(fb, oracle, monkeypatch):
+def test_provisional_first_threshold(fb, synth, oracle, monkeypatch):
     """A first chunk too large for one infinite-threshold launch starts from a provisional finite threshold
     (16 * size expected candidates) and is hashed in one launch; if fewer than `size` distinct keys lie
     below it the chunk is redone with the exact ramp.  Smallest log so that small inputs take this path."""
     monkeypatch.setenv("FB2_LOG_M", "0")
-    genome = fb.synth_genome(400_000, 31)
-    data, nb = fb.synth_fastq(genome, 14_000, 150, 0.01, 33)
+    genome = synth.synth_genome(400_000, 31)
+    data, nb = synth.synth_fastq(genome, 14_000, 150, 0.01, 33)
     data = data.tobytes()
     for kind, size, scale in (("mash", 2000, 0.0), ("scaled", 500, 0.002)):
         ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, 21, 0, scale or 0.001)
@@ -576,10 +576,10 @@ def test_symbol_regions_match_normalize(fb, oracle):
 
 @pytest.mark.parametrize("kind,size,k,scale", [("scaled", 1000, 21, 0.05), ("scaled", 0, 31, 0.2),
                                                ("mash", 5_000_000, 21, 0)])
-def test_table_growth(fb, oracle, kind, size, k, scale):
+def test_table_growth(fb, synth, oracle, kind, size, k, scale):
     """Sketches far larger than the initial table (Scaled keeps ~scale * distinct k-mers; a Mash heap larger
     than the input keeps everything): the table must grow and stay exact."""
-    data = fb.synth_fasta(2_000_000, n_records=2, line_width=70, lower_frac=0.05, n_frac=0.002, seed=11).tobytes()
+    data = synth.synth_fasta(2_000_000, n_records=2, line_width=70, lower_frac=0.05, n_frac=0.002, seed=11).tobytes()
     ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, k, 0, scale or 0.001)
     gres, gtotals, _ = gpu_sketch(fb, data, kind, size, k, 0, scale or 0.001)
     assert gtotals == ototals

@@ -3,7 +3,8 @@ import sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
 import finch_rs_b200 as fb
-data = fb.synth_fasta(5_000_000, n_records=1, line_width=80, seed=1)
+sys.path.insert(0, "tools"); import synth
+data = synth.synth_fasta(5_000_000, n_records=1, line_width=80, seed=1)
 sp = fb.SketchParams.from_cli("mash", n_hashes=1000, kmer_length=21)
 fp = fb.FilterParams(None, (None, None), 0.21, 0.1)
 host = torch.from_numpy(data).pin_memory()

@@ -3,10 +3,11 @@ import sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
 import finch_rs_b200 as fb
+sys.path.insert(0, "tools"); import synth
 import bench
 n_reads = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
-genome = fb.synth_genome(bench.GENOME_LEN, 2)
-buf, need, nbases = bench.gen_fastq(fb, genome, n_reads, 3)
+genome = synth.synth_genome(bench.GENOME_LEN, 2)
+buf, need, nbases = synth.synth_fastq_parallel(genome, n_reads, 150, 0.005, 3)
 d = torch.from_numpy(buf).cuda()
 sp = fb.SketchParams.from_cli("mash", n_hashes=1000, kmer_length=21, filters_enabled=True)
 fp = fb.FilterParams(True, (None, None), 0.21, 0.1)

@@ -3,8 +3,9 @@ import sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
 import finch_rs_b200 as fb
+sys.path.insert(0, "tools"); import synth
 nb = int(float(sys.argv[1])) if len(sys.argv) > 1 else 300_000_000
-big = fb.synth_fasta(nb, n_records=24, line_width=60, lower_frac=0.02, n_frac=0.01, seed=4)
+big = synth.synth_fasta(nb, n_records=24, line_width=60, lower_frac=0.02, n_frac=0.01, seed=4)
 sp4 = fb.SketchParams.scaled(1000, 31, 0.001, 0)
 fp4 = fb.FilterParams(None, (None, None), 0.31, 0.1)
 d = torch.from_numpy(big).cuda()
