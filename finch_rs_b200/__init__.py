@@ -13,6 +13,7 @@ The names and argument meanings follow the reference (paths relative to the refe
 Every compute call goes to the GPU through the C ABI.  There is no CPU fallback: importing works
 anywhere, but creating a sketcher without the built library or without a CUDA device raises.
 """
+import atexit
 import ctypes as C
 import os
 from dataclasses import dataclass, field
@@ -72,7 +73,7 @@ EXPORTS = [
     "fb2_sketcher_create", "fb2_sketcher_destroy", "fb2_sketcher_reset", "fb2_sketcher_process",
     "fb2_sketcher_push", "fb2_sketcher_feed_fastx", "fb2_sketcher_feed_device", "fb2_sketcher_format",
     "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats",
-    "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_filter_counts", "fb2_process_post_filter",
+    "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_sketcher_debug_bump", "fb2_filter_counts", "fb2_process_post_filter",
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_release_pool", "fb2_dist_batch",
     "fb2_dist_all_pairs", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_old_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
 ]
@@ -107,6 +108,7 @@ def lib():
     L.fb2_sketcher_stats.argtypes = [vp, C.POINTER(_Stats)]
     L.fb2_sketcher_enable_timing.argtypes = [vp, C.c_int]
     L.fb2_sketcher_debug_symbols.argtypes = [vp, vp, vp, sz, vp, sz]
+    L.fb2_sketcher_debug_bump.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
     L.fb2_filter_counts.argtypes = [C.POINTER(_Result), C.POINTER(_Filter)]
     L.fb2_process_post_filter.argtypes = [C.POINTER(_Result), C.POINTER(_Params), C.c_char_p]
     L.fb2_guess_filter_threshold.argtypes = [vp, sz, C.c_double]
@@ -125,6 +127,7 @@ def lib():
     L.fb2_last_error.restype = C.c_char_p
     L.fb2_version.restype = C.c_char_p
     _lib = L
+    atexit.register(L.fb2_sketch_files_release_pool)   # idle worker handles of sketch_files (bounded, see finch_b200.h)
     return L
 
 
@@ -359,11 +362,15 @@ class _Sketcher:
         names = ("len", "n_tiles", "st_tiles", "n_st", "st_bytes", "region_stride", "hash_tiles")
         geom = dict(zip(names, (int(x) for x in g)))
         counts = np.zeros(geom["n_st"], np.uint32)
-        buf = np.zeros(64 + geom["n_st"] * geom["region_stride"] + 64, np.uint8)
+        front = geom["region_stride"] - geom["st_bytes"]      # SYM_FRONT: pad in front of every region
+        buf = np.zeros(front + geom["n_st"] * geom["region_stride"] + 64, np.uint8)
         _check(lib().fb2_sketcher_debug_symbols(self._h, g.ctypes.data, counts.ctypes.data, counts.size,
                                                 buf.ctypes.data, buf.size))
-        regs = [buf[64 + r * geom["region_stride"]: 64 + r * geom["region_stride"] + int(counts[r])] for r in range(geom["n_st"])]
+        regs = [buf[front + r * geom["region_stride"]: front + r * geom["region_stride"] + int(counts[r])] for r in range(geom["n_st"])]
         return geom, counts, regs, buf
+
+    def debug_bump(self, hash_, add_count, add_extra):
+        _check(lib().fb2_sketcher_debug_bump(self._h, hash_, add_count, add_extra))
 
     def enable_timing(self, on=True):
         _check(lib().fb2_sketcher_enable_timing(self._h, int(on)))

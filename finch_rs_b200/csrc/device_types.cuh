@@ -7,7 +7,10 @@ namespace fb2 {
 
 constexpr int TILE_THREADS = 256;   // parse: threads per tile
 constexpr int TILE_BYTES = 4096;    // parse: raw bytes per tile (16 per thread)
-constexpr int SYM_FRONT = 64;       // symbols carried in front of each chunk's symbol buffer
+constexpr int SYM_FRONT = 256;      // pad in front of every symbol region: holds the `halo` symbols that precede it in stream order
+constexpr int HALO_SMALL = 32;      // halo (symbols carried across region / chunk seams) for k <= 32
+constexpr int HALO_BIG = 256;       // ... for 33 <= k <= 255 (k - 1 <= 254 symbols)
+constexpr int KMER_WORDS_MAX = 8;   // 64-bit words of 2-bit codes per k-mer: 1 for k <= 32, ceil(k / 32) otherwise
 constexpr int HASH_THREADS = 256;
 constexpr int HASH_W = 64;          // k-mer end positions per thread
 constexpr uint32_t HASH_TILE = HASH_THREADS * HASH_W;  // symbols per block
@@ -41,7 +44,16 @@ struct ParseCarry {
     uint32_t chunk_syms;     // symbols produced by the current chunk (all regions)
     uint32_t cprev1, cprev2; // prev1 / prev2 as they were at the start of the current chunk
     uint32_t max_region_syms;// largest region of the current chunk (symbols): bounds the hash kernel's item space
+    // FASTQ: needletail rejects a record whose sequence and quality lines differ in length (lib.rs:63 panics).
+    uint64_t len_bad_pos;    // min stream position of the header-line newline of such a record (~0: none)
+    uint64_t last_nl[2][3];  // the last three newlines of the stream before / after the current chunk (ascending;
+                             // stream position, bit 63 = preceded by a CR; ~0 = none); halves alternate per chunk
 };
+constexpr unsigned long long NL_NONE = ~0ULL;
+
+// FASTQ length check across supertile seams: the first and the last (up to) three newlines of a supertile,
+// chunk-relative position, bit 31 = the byte before the newline is a CR.  n = newlines in the supertile.
+struct SeamNl { uint32_t first[3], last[3]; uint32_t n, pad; };
 
 // Counters of one hash launch (two slots: chunk c+1 may be hashed while chunk c is verified).
 struct LaunchSlot {
@@ -69,18 +81,21 @@ struct SketchState {
 
 struct LogView {
     unsigned long long *hash;   // murmur h1
-    unsigned long long *kmer;   // LSB-first 2-bit codes, or arena index for pushed k-mers
+    unsigned long long *kmer;   // kw words per entry: LSB-first 2-bit codes (base i in bits [2i, 2i+1] of the multi-word),
+                                // or the arena index of a pushed k-mer in word 0
     unsigned long long *posx;   // position id << 9 | is_arena << 8 | extra_count (u8)
     unsigned int cap;
+    unsigned int kw;            // words per k-mer (1 for k <= 32)
 };
 struct TableView {
     unsigned long long *key;    // EMPTY_KEY when free; slot `cap` is the side slot for u64::MAX
     unsigned long long *cnt;
     unsigned long long *ext;
     unsigned long long *posx;   // min posx over occurrences (first occurrence wins the kmer)
-    unsigned long long *kmer;
+    unsigned long long *kmer;   // kw words per slot
     unsigned int cap;           // power of two
     unsigned int shift;         // 64 - log2(cap)
+    unsigned int kw;            // words per k-mer (1 for k <= 32)
 };
 constexpr unsigned long long EMPTY_KEY = ~0ULL;
 

@@ -62,11 +62,11 @@ struct DevBuf {
 
 struct Table {
     DevBuf key, cnt, ext, posx, kmer;
-    uint32_t cap = 0;
+    uint32_t cap = 0, kw = 1;            // kw: 64-bit words of 2-bit codes per k-mer (1 for k <= 32)
     int alloc(uint32_t c) {
         const size_t n = (size_t)c + 1;  // + side slot for hash == u64::MAX
         TRY(key.ensure(n * 8)); TRY(cnt.ensure(n * 8)); TRY(ext.ensure(n * 8));
-        TRY(posx.ensure(n * 8)); TRY(kmer.ensure(n * 8));
+        TRY(posx.ensure(n * 8)); TRY(kmer.ensure(n * 8 * kw));
         cap = c;
         return FB2_OK;
     }
@@ -75,7 +75,7 @@ struct Table {
         v.key = key.as<unsigned long long>(); v.cnt = cnt.as<unsigned long long>();
         v.ext = ext.as<unsigned long long>(); v.posx = posx.as<unsigned long long>();
         v.kmer = kmer.as<unsigned long long>();
-        v.cap = cap;
+        v.cap = cap; v.kw = kw;
         uint32_t lg = 0; while ((1u << lg) < cap) ++lg;
         v.shift = 64u - lg;
         return v;
@@ -89,6 +89,7 @@ struct fb2_sketcher {
     bool scaled = false;
     uint64_t size = 0, max_hash = 0;
     int k = 0;
+    uint32_t kw = 1, halo = HALO_SMALL;   // words per k-mer; symbols carried across region / chunk seams
     cudaStream_t st = nullptr, copy_st = nullptr;
     cudaStream_t st2 = nullptr;      // absorb stream: log -> table of chunk c overlaps the parse kernels of chunk c+1
     cudaEvent_t ev_hash[2]{}, ev_st2 = nullptr;
@@ -99,7 +100,7 @@ struct fb2_sketcher {
     bool rawfree_pending[2] = {false, false};
 
     size_t chunk_bytes = 0;
-    DevBuf d_raw[2], d_sym[2], d_stmap, d_ststate, d_rcount[2], d_tail, d_carry, d_state;
+    DevBuf d_raw[2], d_sym[2], d_stmap, d_ststate, d_rcount[2], d_tail, d_carry, d_state, d_seam;
     int tail_sel = 0;               // which half of d_tail holds the symbols carried into the next chunk
     uint64_t ordinal = 0;           // next position id (symbols of all regions so far + pushed k-mers)
     DevBuf log_hash[2], log_kmer[2], log_posx[2];   // one candidate log per in-flight chunk
@@ -136,7 +137,10 @@ struct fb2_sketcher {
 
     int format = FB2_FORMAT_UNKNOWN;
     bool stream_open = false;        // a FASTX stream has begun and not yet seen `final`
-    uint8_t sniff[2] = {0, 0};
+    std::vector<uint8_t> presniff;   // a first piece shorter than 2 bytes waits here until the format can be sniffed
+    // fb2_sketcher_hint_finish: the caller will finish with fb2_sketcher_sketch(final_size, filter) and nothing else,
+    // so a Mash heap larger than final_size is only needed when the filter ends up on
+    bool hint_set = false; uint64_t hint_final = 0; int hint_filter = 0;
     uint64_t lines_bases = 0, total_kmers = 0;
     uint32_t next_launch = 0;
     fb2_stats stats{};
@@ -170,7 +174,7 @@ static void timing_resolve(fb2_sketcher *s) {
 static LogView log_view(fb2_sketcher *s, int par) {
     LogView l;
     l.hash = s->log_hash[par].as<unsigned long long>(); l.kmer = s->log_kmer[par].as<unsigned long long>();
-    l.posx = s->log_posx[par].as<unsigned long long>(); l.cap = s->log_cap;
+    l.posx = s->log_posx[par].as<unsigned long long>(); l.cap = s->log_cap; l.kw = s->kw;
     return l;
 }
 static inline LaunchSlot *dev_slot(fb2_sketcher *s, int par) { return &((SketchState *)s->d_state.p)->slot[par]; }
@@ -228,7 +232,37 @@ static int refresh_live_hist(fb2_sketcher *s) {
     return FB2_OK;
 }
 
+// Candidate-log capacity for the current sketch size.  The provisional first launch lets ~16 * size candidates
+// through and wants them in half the log; steady Scaled chunks log chunk_symbols * max_hash / 2^64 candidates and
+// the asynchronous path wants a chunk's candidates in a quarter of the log.  FB2_LOG_M (Mi entries) overrides.
+static void size_logs(fb2_sketcher *s) {
+    uint64_t cap;
+    if (const size_t m = env_size("FB2_LOG_M", 0)) cap = (uint64_t)m << 20;
+    else {
+        uint64_t want = 36ull * s->size;
+        if (s->scaled) want = std::max<uint64_t>(want, (uint64_t)(8.0 * (double)s->chunk_bytes * ((double)s->max_hash / 18446744073709551616.0)));
+        cap = next_pow2(std::min<uint64_t>(want, 8ull << 20));
+        if (cap > (8u << 20)) cap = 8u << 20;
+    }
+    if (cap < 32ull * HASH_TILE) cap = 32ull * HASH_TILE;
+    s->log_cap = (uint32_t)cap;
+    // First launch of a stream: the threshold is still infinite, every k-mer is a candidate.  Take as
+    // many positions as the log holds (a warp reserves 35 slots per 32 candidates) so that a small
+    // file is hashed in ONE launch and the banded absorb picks the bottom band from the whole log.
+    s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (s->log_cap / 8u * 7u) / HASH_TILE * HASH_TILE);
+}
+// The logs are allocated at first use (a handle that only ever sees small sketches stays small).
+static int ensure_logs(fb2_sketcher *s) {
+    for (int i = 0; i < 2; ++i) {
+        TRY(s->log_hash[i].ensure((size_t)s->log_cap * 8));
+        TRY(s->log_kmer[i].ensure((size_t)s->log_cap * 8 * s->kw));
+        TRY(s->log_posx[i].ensure((size_t)s->log_cap * 8));
+    }
+    return FB2_OK;
+}
+
 static int reset_sketch_state(fb2_sketcher *s) {
+    s->size = s->prm.kmers_to_sketch;   // a finish hint may have lowered it for the previous stream
     memset(s->h_state, 0, sizeof(SketchState));
     s->h_state->threshold = (s->scaled && s->size == 0) ? s->max_hash : ~0ULL;
     TRY(s->d_live_bins.ensure(4096 * sizeof(uint32_t)));
@@ -239,20 +273,19 @@ static int reset_sketch_state(fb2_sketcher *s) {
     TRY(push_state(s));
     memset(s->h_carry, 0, sizeof(ParseCarry));
     s->h_carry->prev1 = s->h_carry->prev2 = '\n';
-    s->h_carry->first_bad_pos = ~0ULL;
+    s->h_carry->first_bad_pos = ~0ULL; s->h_carry->len_bad_pos = ~0ULL;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 3; ++b) s->h_carry->last_nl[a][b] = NL_NONE;
     TRY(push_carry(s));
     launch_table_clear(s->tab[s->cur].view(), s->st);
-    launch_fill_bytes(s->d_tail.as<uint8_t>(), 64, SYM_BREAK, s->st);
+    launch_fill_bytes(s->d_tail.as<uint8_t>(), 2 * HALO_BIG, SYM_BREAK, s->st);
     s->stats.kernel_launches += 2;
     CU(cudaStreamSynchronize(s->st));
     s->tail_sel = 0; s->ordinal = 0; s->par = 0; s->steady = false;
     s->pend[0].valid = s->pend[1].valid = false;
     s->format = FB2_FORMAT_UNKNOWN; s->stream_open = false;
     s->lines_bases = 0; s->total_kmers = 0; s->stage_fill = 0; s->stage_mode = -1;
-    // First launch of a stream: the threshold is still infinite, every k-mer is a candidate.  Take as
-    // many positions as the log holds (a warp reserves 35 slots per 32 candidates) so that a small
-    // file is hashed in ONE launch and the banded absorb picks the bottom band from the whole log.
-    s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (s->log_cap / 8u * 7u) / HASH_TILE * HASH_TILE);
+    size_logs(s);
+    s->presniff.clear();
     s->push_bytes.clear(); s->push_extra.clear(); s->push_offs.assign(1, 0u);
     s->arena.clear(); s->arena_flushed = 0;
     return FB2_OK;
@@ -263,8 +296,7 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
     if (!p || !out) return fb2_fail(FB2_EINVAL, "null argument");
     *out = nullptr;
     if (p->kind != FB2_KIND_MASH && p->kind != FB2_KIND_SCALED) return fb2_fail(FB2_EINVAL, "unknown sketch kind");
-    if (p->kmer_length < 1 || p->kmer_length > 32)
-        return fb2_fail(FB2_EUNSUPPORTED, "kmer_length must be in 1..=32 on this build");
+    if (p->kmer_length < 1) return fb2_fail(FB2_EINVAL, "kmer_length must be in 1..=255");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
@@ -275,6 +307,10 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
 
     fb2_sketcher *s = new fb2_sketcher();
     s->prm = *p; s->device = dev; s->k = p->kmer_length;
+    // k <= 32: the k-mer is one 64-bit word of 2-bit codes and the fast kernels apply; 33..=255: exact multi-word path
+    s->kw = s->k <= 32 ? 1u : (uint32_t)(s->k + 31) / 32u;
+    s->halo = s->k <= 32 ? HALO_SMALL : HALO_BIG;
+    s->tab[0].kw = s->tab[1].kw = s->kw;
     s->scaled = p->kind == FB2_KIND_SCALED;
     s->size = p->kmers_to_sketch;
     if (s->scaled) {
@@ -301,22 +337,17 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
     s->chunk_bytes = env_size("FB2_CHUNK_MB", 128) << 20;
     if (s->chunk_bytes < (1u << 20)) s->chunk_bytes = 1u << 20;
     if (s->chunk_bytes > (1ull << 30)) s->chunk_bytes = 1ull << 30;
-    s->log_cap = (uint32_t)(env_size("FB2_LOG_M", 8) << 20);
-    if (s->log_cap < 32u * HASH_TILE) s->log_cap = 32u * HASH_TILE;
 
     int rc = FB2_OK;
     do {
         if ((rc = s->d_carry.ensure(sizeof(ParseCarry))) != FB2_OK) break;
         if ((rc = s->d_state.ensure(sizeof(SketchState))) != FB2_OK) break;
-        if ((rc = s->d_tail.ensure(64)) != FB2_OK) break;
+        if ((rc = s->d_tail.ensure(2 * HALO_BIG)) != FB2_OK) break;
         if (cudaHostAlloc((void **)&s->h_carry, sizeof(ParseCarry), cudaHostAllocDefault) != cudaSuccess ||
             cudaHostAlloc((void **)&s->h_state, sizeof(SketchState), cudaHostAllocDefault) != cudaSuccess) {
             rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed"); break;
         }
         for (int i = 0; i < 2 && rc == FB2_OK; ++i) {
-            if ((rc = s->log_hash[i].ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
-            if ((rc = s->log_kmer[i].ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
-            if ((rc = s->log_posx[i].ensure((size_t)s->log_cap * 8)) != FB2_OK) break;
             if (cudaHostAlloc((void **)&s->h_snap[i], sizeof(SketchState), cudaHostAllocDefault) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) {
                 rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc/cudaEventCreate failed");
@@ -354,7 +385,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
         if (s->h_snap[i]) cudaFreeHost(s->h_snap[i]);
         if (s->ev_chunk[i]) cudaEventDestroy(s->ev_chunk[i]);
     }
-    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release();
+    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release(); s->d_seam.release();
     s->d_carry.release(); s->d_state.release();
     s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release(); s->d_bins.release(); s->d_live_bins.release();
     s->out_hash.release(); s->out_cnt.release(); s->out_ext.release(); s->out_kmer.release(); s->out_posx.release();
@@ -586,6 +617,8 @@ static ChunkGeom make_geom(uint32_t len) {
     g.len = len;
     g.n_tiles = cdivu(len, TILE_BYTES);
     uint32_t stt = g.n_tiles / 4096u;  // ~4096 supertiles per full chunk: several waves of blocks, small tails
+    const uint32_t forced = (uint32_t)env_size("FB2_ST_TILES", 0);   // tests: supertile size whatever the chunk size
+    if (forced) stt = forced;
     if (stt < 1) stt = 1;
     if (stt > 32) stt = 32;
     g.st_tiles = stt;
@@ -739,20 +772,22 @@ static int settle_all(fb2_sketcher *s) {
 static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mode, int rawbuf /* -1: not ours */) {
     if (!len) return FB2_OK;
     const int par = s->par;
+    TRY(ensure_logs(s));
     TRY(settle(s, par));           // its buffers are about to be reused (normally already settled)
     const ChunkGeom g = make_geom(len);
     s->last_geom = g;
     TRY(s->d_stmap.ensure((size_t)g.n_st * 4)); TRY(s->d_ststate.ensure((size_t)g.n_st * 4));
     TRY(s->d_rcount[par].ensure((size_t)g.n_st * 4));
+    if (mode == MODE_FASTQ) TRY(s->d_seam.ensure((size_t)g.n_st * sizeof(SeamNl)));
     TRY(s->d_sym[par].ensure((size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + 2 * HASH_TILE));
     ParseCarry *dc = (ParseCarry *)s->d_carry.p;
     SketchState *dst = (SketchState *)s->d_state.p;
-    uint8_t *tail_in = s->d_tail.as<uint8_t>() + 32 * s->tail_sel, *tail_out = s->d_tail.as<uint8_t>() + 32 * (s->tail_sel ^ 1);
+    uint8_t *tail_in = s->d_tail.as<uint8_t>() + s->halo * s->tail_sel, *tail_out = s->d_tail.as<uint8_t>() + s->halo * (s->tail_sel ^ 1);
     fb2_sketcher::EvPair evparse;
     const bool parse_timed = timing_begin(s, evparse);
     launch_phase(mode, d_raw, g, dc, s->d_stmap.as<uint32_t>(), s->d_ststate.as<uint32_t>(), s->st);
     launch_pack(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym[par].as<uint8_t>(), s->d_rcount[par].as<uint32_t>(),
-                tail_in, tail_out, s->st);
+                tail_in, tail_out, s->d_seam.as<SeamNl>(), s->tail_sel, s->halo, s->st);
     if (parse_timed) timing_end(s, evparse, s->ev_parse_pending);
     if (rawbuf >= 0) { CU(cudaEventRecord(s->ev_rawfree[rawbuf], s->st)); s->rawfree_pending[rawbuf] = true; }
     s->tail_sel ^= 1;
@@ -853,6 +888,7 @@ static int flush_push(fb2_sketcher *s) {
     const uint32_t n = (uint32_t)s->push_extra.size();
     if (!n) return FB2_OK;
     TRY(settle_all(s));
+    TRY(ensure_logs(s));
     const int par = s->par;
     TRY(s->d_push_bytes.ensure(s->push_bytes.size() + 16));
     TRY(s->d_push_offs.ensure((size_t)(n + 1) * 4));
@@ -939,10 +975,19 @@ static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
     else return fb2_fail(FB2_EFORMAT, "could not detect FASTA/FASTQ: first byte is neither '>' nor '@'");
     TRY(flush_all(s));
     TRY(pull_state(s));
+    if (s->hint_set && !s->scaled && s->hint_final < s->size && s->h_state->occupied == 0 && s->h_state->has_max_key == 0 &&
+        s->total_kmers == 0 && (s->hint_filter == 0 || (s->hint_filter < 0 && s->format == FB2_FORMAT_FASTA))) {
+        // the filter resolves to off (lib.rs:71-76) and the result is truncated to final_size: the bottom final_size
+        // of the bottom kmers_to_sketch is the bottom final_size -- sketch with the small heap
+        s->size = s->hint_final;
+        size_logs(s);
+    }
     ParseCarry *c_ = s->h_carry;
     c_->state = s->format == FB2_FORMAT_FASTA ? 1u : 0u;  // FASTA: pretend a header line precedes byte 0
     c_->prev1 = c_->prev2 = '\n';
     c_->raw_total = 0; c_->n_records = 0; c_->first_bad_pos = ~0ULL; c_->last_sig = 0; c_->error = 0;
+    c_->len_bad_pos = ~0ULL;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 3; ++b) c_->last_nl[a][b] = NL_NONE;
     TRY(push_carry(s));
     s->stream_open = true;
     s->tail_host.clear();
@@ -981,12 +1026,30 @@ static int end_stream(fb2_sketcher *s) {
             else if (c->first_bad_pos != ~0ULL && c->first_bad_pos <= last_sig_pos)
                 rc = fb2_fail(FB2_ERECORD, "invalid FASTQ record: line at byte " + std::to_string(c->first_bad_pos) +
                                                " does not start with the expected '@' / '+'");
+            else {
+                // needletail: sequence and quality line of a record have the same length (lib.rs:63 panics otherwise).
+                // The kernels checked every quality line that ends in a newline; a last one that does not is checked
+                // here from the stream's last three newlines (the header, sequence and '+' line ends of that record).
+                uint64_t bad = c->len_bad_pos;
+                if (nl_trail == 0) {
+                    const uint64_t *e = c->last_nl[s->tail_sel];   // as left by the last chunk
+                    const unsigned long long PM = ~(1ULL << 63);
+                    if (e[0] != NL_NONE && e[1] != NL_NONE && e[2] != NL_NONE) {
+                        const uint64_t ls = (e[1] & PM) - (e[0] & PM) - 1 - (e[1] >> 63);
+                        const uint64_t lq = L - (e[2] & PM) - 1 - (t.back() == '\r' ? 1 : 0);
+                        if (ls != lq) bad = std::min<uint64_t>(bad, e[0] & PM);
+                    }
+                }
+                if (bad != ~0ULL && bad <= last_sig_pos)
+                    rc = fb2_fail(FB2_ERECORD, "invalid FASTQ record: sequence and quality lengths differ (record whose header ends at byte " +
+                                                   std::to_string(bad) + ")");
+            }
         }
     }
     // a later stream or record must not join this one: break the carried symbols
     c->state = 0; c->prev1 = c->prev2 = '\n';
     TRY(push_carry(s));
-    launch_fill_bytes(s->d_tail.as<uint8_t>(), 64, SYM_BREAK, s->st);
+    launch_fill_bytes(s->d_tail.as<uint8_t>(), 2 * HALO_BIG, SYM_BREAK, s->st);
     s->stats.kernel_launches++;
     s->stream_open = false;
     return rc;
@@ -995,6 +1058,20 @@ static int end_stream(fb2_sketcher *s) {
 extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, size_t len, int final) {
     if (!s || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
     CU(cudaSetDevice(s->device));
+    if (!s->stream_open) {
+        // format sniffing looks at two bytes (compressed-input magic): a shorter first piece waits for the next one
+        const size_t have = s->presniff.size();
+        if (have + len < 2 && !final) {
+            if (len) s->presniff.insert(s->presniff.end(), bytes, bytes + len);
+            return FB2_OK;
+        }
+        if (have) {
+            std::vector<uint8_t> joined(s->presniff);
+            s->presniff.clear();
+            joined.insert(joined.end(), bytes, bytes + len);
+            return fb2_sketcher_feed_fastx(s, joined.data(), joined.size(), final);
+        }
+    }
     if (len) {
         if (!s->stream_open) TRY(begin_stream(s, bytes, len));
         const int mode = s->format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ;
@@ -1064,6 +1141,13 @@ extern "C" int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev, siz
     return FB2_OK;
 }
 
+// Internal (hostlogic.cpp): the caller promises to finish this handle's streams with
+// fb2_sketcher_sketch(final_size, filter) only; see begin_stream.  Survives reset.
+void fb2_sketcher_hint_finish(fb2_sketcher *s, uint64_t final_size, int filter_on) {
+    s->hint_set = true; s->hint_final = final_size; s->hint_filter = filter_on;
+}
+size_t fb2_sketcher_chunk_bytes(const fb2_sketcher *s) { return s->chunk_bytes; }
+
 extern "C" int fb2_sketcher_format(fb2_sketcher *s, int32_t *format) {
     if (!s || !format) return fb2_fail(FB2_EINVAL, "null argument");
     *format = s->format;
@@ -1124,7 +1208,7 @@ static int export_sorted(fb2_sketcher *s, uint32_t *keep_out) {
     TRY(sort_table(s, &n));
     const uint32_t keep = s->h_state->keep_count;
     if (keep) {
-        TRY(s->out_hash.ensure((size_t)keep * 8)); TRY(s->out_kmer.ensure((size_t)keep * 8));
+        TRY(s->out_hash.ensure((size_t)keep * 8)); TRY(s->out_kmer.ensure((size_t)keep * 8 * s->kw));
         TRY(s->out_posx.ensure((size_t)keep * 8));
         TRY(s->out_cnt.ensure((size_t)keep * 4)); TRY(s->out_ext.ensure((size_t)keep * 4));
         launch_export(s->sort_keys.as<unsigned long long>(), s->sort_slots.as<uint32_t>(), keep, s->tab[s->cur].view(),
@@ -1159,7 +1243,7 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
             s->stats.h2d_bytes += (size_t)m * 4;
             d_idx = s->sel_idx.as<uint32_t>();
         }
-        launch_select_rows(d_idx, m, s->k, (uint32_t)stride, s->out_hash.as<unsigned long long>(), s->out_cnt.as<uint32_t>(),
+        launch_select_rows(d_idx, m, s->k, (uint32_t)stride, s->kw, s->out_hash.as<unsigned long long>(), s->out_cnt.as<uint32_t>(),
                            s->out_ext.as<uint32_t>(), s->out_kmer.as<unsigned long long>(), s->out_posx.as<unsigned long long>(),
                            s->sel_hash.as<unsigned long long>(), s->sel_cnt.as<uint32_t>(), s->sel_ext.as<uint32_t>(),
                            s->sel_kmer.as<unsigned long long>(), s->sel_posx.as<unsigned long long>(),
@@ -1278,6 +1362,19 @@ extern "C" int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint
     if (counts && counts_cap >= g.n_st) CU(cudaMemcpy(counts, s->d_rcount[par].p, (size_t)g.n_st * 4, cudaMemcpyDeviceToHost));
     const size_t need = (size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + HASH_W;
     if (sym && sym_cap >= need) CU(cudaMemcpy(sym, s->d_sym[par].p, need, cudaMemcpyDeviceToHost));
+    return FB2_OK;
+}
+
+// Test hook: add (add_count, add_extra) to the 64-bit totals the table keeps for `hash` (which must be present).
+extern "C" int fb2_sketcher_debug_bump(fb2_sketcher *s, uint64_t hash, uint64_t add_count, uint64_t add_extra) {
+    if (!s) return fb2_fail(FB2_EINVAL, "null handle");
+    CU(cudaSetDevice(s->device));
+    TRY(flush_all(s));
+    TRY(pull_state(s));
+    unsigned int *found = &((SketchState *)s->d_state.p)->gather_count;   // scratch word of the state block
+    launch_debug_bump(s->tab[s->cur].view(), hash, add_count, add_extra, found, s->st);
+    TRY(pull_state(s));
+    if (!s->h_state->gather_count) return fb2_fail(FB2_EINVAL, "hash not in the table");
     return FB2_OK;
 }
 

@@ -522,7 +522,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
                         if (idx < log.cap) {
                             const uint32_t p = p0 + 4u * (uint32_t)j + (uint32_t)b;
                             log.hash[idx] = hv;
-                            log.kmer[idx] = ((unsigned long long)codes.hi << 32) | codes.lo;
+                            log.kmer[idx] = ((unsigned long long)codes.hi << 32) | codes.lo;   // k <= 32: log.kw == 1
                             log.posx[idx] = ((ord_region + p) << 9) | (is_rc ? 1ull : 0ull);
                         }
                     }
@@ -542,6 +542,105 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
     if (lane == 0 && nvalid) atomicAdd(&slot->launch_kmers, (unsigned long long)nvalid);
 }
 
+// ---- 33 <= k <= 255: the exact, slower kernel -------------------------------------------------------
+// The reference takes any u8 k-mer length (sketch_schemes/mod.rs:59, cli.rs:161-166).  Beyond 32 bases the
+// strands no longer fit one 64-bit word, so this kernel does what needletail's canonical_kmers and the murmur3
+// crate do, literally, per position: byte-wise lexicographic compare of the forward window against its reverse
+// complement (first difference decides; a palindrome reports rc), then murmur3_x64_128 over the k ASCII bytes of
+// the chosen strand, 16-byte block by block.  A thread owns HB_W consecutive k-mer end positions and carries the
+// position of the last non-base symbol; symbols are read straight from the region (the 256-symbol front pad holds
+// what precedes it in stream order).  Candidates carry their k-mer as ceil(k / 32) words of 2-bit codes.
+constexpr int HB_THREADS = 256, HB_W = 16;
+__device__ __forceinline__ uint32_t ascii_of(uint32_t code) { return (0x54474341u >> (8u * code)) & 0xFFu; }
+__global__ void __launch_bounds__(HB_THREADS)
+hash_big_kernel(const uint8_t *__restrict__ symbuf, ChunkGeom g, uint32_t r0, const uint32_t *__restrict__ region_count,
+                uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log, int k, uint64_t seed) {
+    const uint32_t region = r0 + blockIdx.y, lane = threadIdx.x & 31u;
+    const int end = (int)region_count[region];
+    if ((int)(blockIdx.x * HB_THREADS * HB_W) >= end) return;          // block-uniform
+    const uint8_t *sym = symbuf + (size_t)SYM_FRONT + (size_t)region * g.region_stride;
+    const uint64_t ord_region = ord_base + (uint64_t)region * g.st_bytes;
+    const unsigned long long T = st->threshold;
+    const int p0 = (int)((blockIdx.x * HB_THREADS + threadIdx.x) * HB_W);
+    int lastb = p0 - k;                                               // last non-base symbol before the current position
+    if (p0 < end)
+        for (int i = p0 - 1; i > p0 - k; --i) if (sym[i] >= 4u) { lastb = i; break; }
+    uint32_t nvalid = 0;
+    for (int j = 0; j < HB_W; ++j) {
+        const int p = p0 + j;
+        const bool live = p < end;
+        bool ok = false;
+        if (live) {
+            if (sym[p] >= 4u) lastb = p;
+            ok = p - lastb >= k;
+        }
+        unsigned long long h1 = 0;
+        bool is_rc = false;
+        if (ok) {
+            const uint8_t *f = sym + (p - k + 1);                     // forward window: f[i]; reverse complement: 3 - f[k-1-i]
+            is_rc = true;                                             // tie (palindrome) => rc, as needletail's `fwd < rc` test
+            for (int i = 0; i < k; ++i) {
+                const uint32_t a = f[i], b = 3u - f[k - 1 - i];
+                if (a != b) { is_rc = !(a < b); break; }
+            }
+            auto byte_at = [&](int i) -> unsigned long long {
+                return (unsigned long long)ascii_of(is_rc ? 3u - f[k - 1 - i] : (uint32_t)f[i]);
+            };
+            unsigned long long h2 = seed;
+            h1 = seed;
+            const int nblocks = k / 16;
+            for (int blk = 0; blk < nblocks; ++blk) {
+                unsigned long long k1 = 0, k2 = 0;
+                for (int q = 7; q >= 0; --q) { k1 = (k1 << 8) | byte_at(16 * blk + q); k2 = (k2 << 8) | byte_at(16 * blk + 8 + q); }
+                k1 *= MM_C1; k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
+                h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+                k2 *= MM_C2; k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
+                h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+            }
+            const int t = k & 15, tb = 16 * nblocks;
+            if (t > 8) {
+                unsigned long long k2 = 0;
+                for (int q = t - 1; q >= 8; --q) k2 = (k2 << 8) | byte_at(tb + q);
+                k2 *= MM_C2; k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
+            }
+            if (t > 0) {
+                unsigned long long k1 = 0;
+                for (int q = (t > 8 ? 8 : t) - 1; q >= 0; --q) k1 = (k1 << 8) | byte_at(tb + q);
+                k1 *= MM_C1; k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
+            }
+            h1 ^= (unsigned long long)k; h2 ^= (unsigned long long)k;
+            h1 += h2; h2 += h1;
+            h1 = fmix64(h1); h2 = fmix64(h2);
+            h1 += h2;
+            ++nvalid;
+        }
+        const bool emit = ok && h1 <= T;
+        const uint32_t em = __ballot_sync(0xffffffffu, emit);
+        if (em) {
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(em) - 1)) base = atomicAdd(&slot->log_count, (unsigned int)__popc(em));
+            base = __shfl_sync(0xffffffffu, base, __ffs(em) - 1);
+            if (emit) {
+                const uint32_t idx = base + __popc(em & lanemask_lt());
+                if (idx < log.cap) {
+                    const uint8_t *f = sym + (p - k + 1);
+                    log.hash[idx] = h1;
+                    log.posx[idx] = ((ord_region + (uint64_t)p) << 9) | (is_rc ? 1ull : 0ull);
+                    unsigned long long *kw = log.kmer + (size_t)idx * log.kw;
+                    for (uint32_t w = 0; w < log.kw; ++w) {
+                        unsigned long long acc = 0;
+                        for (int i = 32 * (int)w; i < k && i < 32 * (int)w + 32; ++i)
+                            acc |= (unsigned long long)(is_rc ? 3u - f[k - 1 - i] : (uint32_t)f[i]) << (2 * (i & 31));
+                        kw[w] = acc;
+                    }
+                }
+            }
+        }
+    }
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+    if (lane == 0 && nvalid) atomicAdd(&slot->launch_kmers, (unsigned long long)nvalid);
+}
+
 // `push` unit-test surface (mash.rs:34 / scaled.rs:37): hash arbitrary byte strings.
 __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32_t *__restrict__ offs,
                                  const uint8_t *__restrict__ extra, uint32_t n, uint64_t arena_base,
@@ -555,7 +654,7 @@ __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32
         const uint32_t idx = atomicAdd(&slot->log_count, 1u);
         if (idx < log.cap) {
             log.hash[idx] = h;
-            log.kmer[idx] = arena_base + i;
+            log.kmer[(size_t)idx * log.kw] = arena_base + i;
             log.posx[idx] = ((ord_base + i) << 9) | (1ull << 8) | (unsigned long long)extra[i];
         }
     }
@@ -596,6 +695,11 @@ void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t r0, uint32_
                  const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
                  uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
     if (r1 <= r0) return;
+    if (k > 32) {
+        const dim3 grid((g.st_bytes + HB_THREADS * HB_W - 1) / (HB_THREADS * HB_W), r1 - r0);
+        hash_big_kernel<<<grid, HB_THREADS, 0, stream>>>(symbuf, g, r0, region_count, ord_base, st, slot, log, k, seed);
+        return;
+    }
     if (k == 21) launch_hash_k<21>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
     else if (k == 31) launch_hash_k<31>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
     else launch_hash_k<0>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);

@@ -26,6 +26,7 @@
 #include "../../include/finch_b200.h"
 
 int fb2_fail(int code, const std::string &msg);  // engine.cu
+void fb2_sketcher_hint_finish(fb2_sketcher *s, uint64_t final_size, int filter_on);   // engine.cu (internal)
 
 // ---- filters ---------------------------------------------------------------------------------
 static void compact(fb2_result *r, const std::vector<uint8_t> &keep) {
@@ -155,6 +156,7 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
     fb2_sketcher *s = nullptr;
     int rc = fb2_sketcher_create(p, &s);
     if (rc != FB2_OK) return rc;
+    if (p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
     rc = fb2_sketcher_feed_fastx(s, bytes, len, 1);
     if (rc == FB2_OK) rc = finish_sketch(s, name, p, f, out);
     fb2_sketcher_destroy(s);
@@ -171,6 +173,7 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
     FILE *fp = is_stdin ? stdin : fopen(path, "rb");
     if (!fp) return fb2_fail(FB2_EIO, std::string(path) + ": No such file or directory");
     int rc = reuse ? fb2_sketcher_reset(s) : FB2_OK;
+    if (p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
     bool any = false;
     // sniff the first two bytes
     unsigned char magic[2] = {0, 0};
@@ -225,14 +228,23 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
     return rc;
 }
 
-// Idle worker handles (sketcher + pinned read buffer) kept between sketch_files calls: creating a
-// handle allocates its logs and tables (tens of ms, serialised by the driver), which would otherwise
-// dominate batches of small files.  At most FB2_POOL_MAX entries; fb2_sketch_files_release_pool()
-// frees them.
-struct PoolEntry { fb2_params p; fb2_sketcher *s; uint8_t *buf; };
+// Idle worker handles (sketcher + pinned read buffer) kept between sketch_files calls: creating a handle
+// allocates device buffers and a pinned read buffer (tens of ms, serialised by the driver), which would otherwise
+// dominate batches of small files.  The reference API has no release call, so retention is bounded: at most
+// FB2_POOL_MAX handles (default 2; 0 disables pooling) stay behind a call, whatever the worker count was, and a
+// handle is only re-used under the chunk / log settings it was created with.  fb2_sketch_files_release_pool()
+// frees them (the Python mirror registers it with atexit).
+struct PoolEntry { fb2_params p; fb2_sketcher *s; uint8_t *buf; std::string env; };
 static std::mutex g_pool_mu;
 static std::vector<PoolEntry> g_pool;
-static const size_t FB2_POOL_MAX = 32;
+static size_t pool_max() {
+    if (const char *e = getenv("FB2_POOL_MAX")) { const long v = atol(e); if (v >= 0 && v <= 64) return (size_t)v; }
+    return 2;
+}
+static std::string pool_env_key() {
+    const char *a = getenv("FB2_CHUNK_MB"), *b = getenv("FB2_LOG_M"), *c = getenv("FB2_TABLE_MULT");
+    return std::string(a ? a : "") + "/" + (b ? b : "") + "/" + (c ? c : "");
+}
 static bool same_sketcher_params(const fb2_params &a, const fb2_params &b) {
     return a.kind == b.kind && a.kmers_to_sketch == b.kmers_to_sketch && a.kmer_length == b.kmer_length &&
            a.hash_seed == b.hash_seed && a.scale == b.scale && a.device == b.device && a.stream == nullptr &&
@@ -240,8 +252,9 @@ static bool same_sketcher_params(const fb2_params &a, const fb2_params &b) {
 }
 static bool pool_acquire(const fb2_params *p, fb2_sketcher **s, uint8_t **buf) {
     std::lock_guard<std::mutex> g(g_pool_mu);
+    const std::string key = pool_env_key();
     for (size_t i = 0; i < g_pool.size(); ++i)
-        if (same_sketcher_params(g_pool[i].p, *p)) {
+        if (same_sketcher_params(g_pool[i].p, *p) && g_pool[i].env == key) {
             *s = g_pool[i].s; *buf = g_pool[i].buf;
             g_pool.erase(g_pool.begin() + (long)i);
             return true;
@@ -250,8 +263,8 @@ static bool pool_acquire(const fb2_params *p, fb2_sketcher **s, uint8_t **buf) {
 }
 static bool pool_release(const fb2_params *p, fb2_sketcher *s, uint8_t *buf) {
     std::lock_guard<std::mutex> g(g_pool_mu);
-    if (g_pool.size() >= FB2_POOL_MAX || p->stream) return false;
-    g_pool.push_back(PoolEntry{*p, s, buf});
+    if (g_pool.size() >= pool_max() || p->stream) return false;
+    g_pool.push_back(PoolEntry{*p, s, buf, pool_env_key()});
     return true;
 }
 extern "C" void fb2_sketch_files_release_pool(void) {

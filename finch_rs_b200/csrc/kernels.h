@@ -9,7 +9,8 @@ namespace fb2 {
 void launch_phase(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_map, uint32_t *st_state,
                   cudaStream_t s);
 void launch_pack(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, const uint32_t *st_state, uint8_t *sym,
-                 uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, cudaStream_t s);
+                 uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, SeamNl *seam, int nl_in, uint32_t halo,
+                 cudaStream_t s);
 void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t st);
 
 // hash.cu
@@ -40,7 +41,7 @@ uint32_t bucket_cap();
 void launch_prune_select(TableView t, SketchState *st, uint32_t shift, uint32_t *bins, int scaled,
                          unsigned long long size, unsigned long long max_hash, unsigned long long *keys,
                          uint32_t *slots, cudaStream_t s);
-void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride, const unsigned long long *i_hash,
+void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride, uint32_t kw, const unsigned long long *i_hash,
                         const uint32_t *i_cnt, const uint32_t *i_ext, const unsigned long long *i_kmer,
                         const unsigned long long *i_posx, unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext,
                         unsigned long long *o_kmer, unsigned long long *o_posx, uint8_t *o_bytes, cudaStream_t s);
@@ -55,6 +56,9 @@ void launch_rebuild(const unsigned long long *keys, const uint32_t *slots, uint3
 void launch_export(const unsigned long long *keys, const uint32_t *slots, uint32_t keep, TableView t,
                    unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext, unsigned long long *o_kmer,
                    unsigned long long *o_posx, cudaStream_t s);
+
+void launch_debug_bump(TableView t, unsigned long long key, unsigned long long add_cnt, unsigned long long add_ext,
+                       unsigned int *found, cudaStream_t s);
 
 // dist.cu
 void launch_dist_pairs(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, const uint32_t *q_idx,

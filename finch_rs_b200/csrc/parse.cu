@@ -343,6 +343,19 @@ phase_scan_kernel(const uint32_t *__restrict__ st_map, ChunkGeom g, ParseCarry *
     }
 }
 
+// ---- FASTQ record check: sequence line and quality line must have the same length (needletail's reader;
+// lib.rs:63 panics on the error).  With E0..E3 the newlines that end the header, sequence, '+' and quality line
+// (chunk-relative position, bit 31 = preceded by a CR, which the reader trims):
+//   len(seq) = E1 - E0 - 1 - cr(E1),  len(qual) = E3 - E2 - 1 - cr(E3).
+// Returns the chunk-relative position of E0 when the record is invalid, else ~0.
+__device__ __forceinline__ uint32_t fastq_len_check(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3) {
+    const uint32_t M = 0x7FFFFFFFu;
+    const uint32_t ls = (e1 & M) - (e0 & M) - 1u - (e1 >> 31), lq = (e3 & M) - (e2 & M) - 1u - (e3 >> 31);
+    return ls == lq ? 0xFFFFFFFFu : (e0 & M);
+}
+// The block's window of the last three newlines seen so far in its supertile (c_nl[2] the most recent).
+__device__ __forceinline__ void nl_window_push(uint32_t *c_nl, uint32_t v) { c_nl[0] = c_nl[1]; c_nl[1] = c_nl[2]; c_nl[2] = v; }
+
 // ------------------------------------------------------------------------------------------------
 // Exact tile walk of one supertile: 16 raw bytes per thread, every byte classified, line state by
 // block scans, symbols written byte by byte.  Handles anything (blanks / CRs inside sequence lines,
@@ -352,7 +365,8 @@ __device__ __forceinline__ void pack_exact(const uint8_t *__restrict__ raw, cons
                                            uint64_t raw_base, uint32_t cprev1, uint32_t cprev2, uint32_t state,
                                            uint8_t *__restrict__ region, const uint8_t *lut, uint32_t *sh8,
                                            uint32_t &out_off, long long &bases_delta, uint32_t &recs,
-                                           unsigned long long &bad_pos) {
+                                           unsigned long long &bad_pos, uint16_t *t_nl, uint32_t *c_nl,
+                                           uint32_t &nl_before, uint32_t &lbad, SeamNl *seam_st) {
     const int tid = threadIdx.x;
     uint4 nextv = fetch_raw(raw, t0 * (uint32_t)TILE_BYTES + (uint32_t)tid * 16u, g.len);
     for (uint32_t t = t0; t < t1; ++t) {
@@ -393,6 +407,39 @@ __device__ __forceinline__ void pack_exact(const uint8_t *__restrict__ raw, cons
                 bool ok = true;
                 if (ph == 0u || ph == 2u) ok = raw[off + (uint32_t)i] == (ph == 0u ? '@' : '+');
                 if (!ok) bad_pos = min(bad_pos, (unsigned long long)(raw_base + off + (uint32_t)i));
+            }
+            // sequence / quality length check (see fastq_len_check): this tile's newlines as a sorted list in
+            // shared memory (t_nl: tile-relative position, bit 15 = preceded by a CR)
+            {
+                uint32_t m = r.nl, at = rel;
+                while (m) {
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const uint32_t pb = i >= 1 ? raw_byte(r, i - 1) : p1;
+                    t_nl[at++] = (uint16_t)(((uint32_t)tid * 16u + (uint32_t)i) | (pb == '\r' ? 0x8000u : 0u));
+                }
+                __syncthreads();
+                const uint32_t tile_off = t * (uint32_t)TILE_BYTES;
+                auto nlq = [&](int j) -> uint32_t {      // j-th newline of the tile, or (j < 0) of the carried window
+                    if (j >= 0) { const uint32_t v = t_nl[j]; return (tile_off + (v & 0x7FFFu)) | ((v >> 15) << 31); }
+                    return c_nl[3 + j];
+                };
+                m = r.nl;
+                int j = (int)rel;
+                while (m) {
+                    m &= m - 1u;
+                    const uint32_t gidx = nl_before + (uint32_t)j;            // index of this newline in the supertile
+                    if (gidx < 3u) seam_st->first[gidx] = nlq(j);
+                    else if (((state + (uint32_t)j) & 3u) == 3u) lbad = min(lbad, fastq_len_check(nlq(j - 3), nlq(j - 2), nlq(j - 1), nlq(j)));
+                    ++j;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    const uint32_t n0 = total_nl > 3u ? total_nl - 3u : 0u;
+                    for (uint32_t q = n0; q < total_nl; ++q) nl_window_push(c_nl, nlq((int)q));
+                }
+                nl_before += total_nl;
+                __syncthreads();
             }
             state = (state + total_nl) & 3u;
         } else {  // MODE_FASTA
@@ -491,7 +538,7 @@ __device__ __forceinline__ void ones128(uint32_t nbytes, uint64_t &lo, uint64_t 
 template <int MODE>
 __global__ void __launch_bounds__(TILE_THREADS)
 pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, const uint32_t *__restrict__ st_state,
-            uint8_t *__restrict__ sym, uint32_t *__restrict__ region_count) {
+            uint8_t *__restrict__ sym, uint32_t *__restrict__ region_count, SeamNl *__restrict__ seam) {
     __shared__ uint8_t lut[256];
     __shared__ uint32_t sh8[8];
     __shared__ unsigned long long sh8l[8];
@@ -500,6 +547,7 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
     __shared__ uint16_t e_src[PB_NLCAP + 1], e_len[PB_NLCAP + 1], e_out[PB_NLCAP + 1];
     __shared__ uint16_t s_first[PB_BYTES / 16 + 2];
     __shared__ uint32_t s_flag[2];   // [0] fast path declined, [1] FASTA: state after the batch
+    __shared__ uint32_t c_nl[3];     // FASTQ: the last three newlines of this supertile before the current batch
     const int tid = threadIdx.x;
     lut[tid] = classify_byte((uint8_t)tid);
     if (tid < 2) s_flag[tid] = 0;
@@ -518,6 +566,8 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
     long long bases_delta = 0;
     uint32_t recs = 0;
     unsigned long long bad_pos = ~0ULL;
+    uint32_t nl_before = 0, lbad = 0xFFFFFFFFu;               // FASTQ: newlines of this supertile so far; min bad record
+    SeamNl *seam_st = MODE == MODE_FASTQ ? seam + st : nullptr;
     uint8_t *rawb = s_rawbuf + 16;
     const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(s_rawbuf);
     bool declined = false;
@@ -596,6 +646,15 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
                     bases_delta += (long long)len - ((has_nl && pb == '\r') ? 1 : 0);
                     L = klen | (has_nl ? 0x8000u : 0u);
                 }
+                if (has_nl) {   // sequence / quality length check (see fastq_len_check)
+                    auto nlq = [&](int j) -> uint32_t {    // j-th newline of the batch, or (j < 0) of the carried window
+                        if (j >= 0) { const uint32_t q = s_nl[j]; return (b + q) | (rawb[(int)q - 1] == '\r' ? 0x80000000u : 0u); }
+                        return c_nl[3 + j];
+                    };
+                    const uint32_t gidx = nl_before + i;
+                    if (gidx < 3u) seam_st->first[gidx] = nlq((int)i);
+                    else if (ph == 3u) lbad = min(lbad, fastq_len_check(nlq((int)i - 3), nlq((int)i - 2), nlq((int)i - 1), nlq((int)i)));
+                }
             } else {  // MODE_FASTA
                 const bool hdr = line_start ? (start < blen && rawb[start] == '>') : ((state & 1u) != 0u);
                 if (line_start && hdr) {
@@ -639,6 +698,16 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
             }
         }
         __syncthreads();
+        if (MODE == MODE_FASTQ) {
+            if (tid == 0) {
+                const uint32_t n0 = N > 3u ? N - 3u : 0u;
+                for (uint32_t q = n0; q < N; ++q) {
+                    const uint32_t pos = s_nl[q];
+                    nl_window_push(c_nl, (b + pos) | (rawb[(int)pos - 1] == '\r' ? 0x80000000u : 0u));
+                }
+            }
+            nl_before += N;
+        }
         // ---- 4. aligned output words ------------------------------------------------------------
         const uint32_t W = (a + T + 15u) >> 4;
         uint8_t *obase = region + (out_off - a);
@@ -714,8 +783,13 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
 
     if (declined) {
         __syncthreads();
-        out_off = 0; bases_delta = 0; recs = 0; bad_pos = ~0ULL;
-        pack_exact<MODE>(raw, g, t0, t1, raw_base, cprev1, cprev2, state0, region, lut, sh8, out_off, bases_delta, recs, bad_pos);
+        out_off = 0; bases_delta = 0; recs = 0; bad_pos = ~0ULL; nl_before = 0; lbad = 0xFFFFFFFFu;
+        pack_exact<MODE>(raw, g, t0, t1, raw_base, cprev1, cprev2, state0, region, lut, sh8, out_off, bases_delta, recs, bad_pos,
+                         reinterpret_cast<uint16_t *>(s_rawbuf), c_nl, nl_before, lbad, seam_st);
+    }
+    if (MODE == MODE_FASTQ) {
+        __syncthreads();
+        if (tid == 0) { seam_st->last[0] = c_nl[0]; seam_st->last[1] = c_nl[1]; seam_st->last[2] = c_nl[2]; seam_st->n = nl_before; }
     }
 
     // the hash kernel walks up to HASH_W positions past the region's end: make them breaks
@@ -731,28 +805,77 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
         if (MODE == MODE_FASTQ) {
             const unsigned long long bmin = block_reduce64(bad_pos, sh8l, OpMin(), ~0ULL);
             if (tid == 0 && bmin != ~0ULL) atomicMin((unsigned long long *)&carry->first_bad_pos, bmin);
+            const unsigned long long lmin = block_reduce64(lbad == 0xFFFFFFFFu ? ~0ULL : raw_base + lbad, sh8l, OpMin(), ~0ULL);
+            if (tid == 0 && lmin != ~0ULL) atomicMin((unsigned long long *)&carry->len_bad_pos, lmin);
         }
     }
 }
 
-// Front pads: warp r fills the 32 bytes before region r (r < n_st) or the outgoing chunk tail
-// (r == n_st) with the last 32 symbols that precede it in stream order -- lane t fetches the symbol
-// 32 - t places back, walking back over short or empty regions and finally into the incoming chunk tail.
+// Front pads: warp r fills the `halo` bytes before region r (r < n_st) or the outgoing chunk tail
+// (r == n_st) with the last `halo` symbols that precede it in stream order -- every lane fetches halo / 32 of
+// them, walking back over short or empty regions and finally into the incoming chunk tail.  halo = 32 covers
+// k <= 32; k up to 255 carries 256 symbols.
+// FASTQ: warp r also runs the sequence / quality length check of the (up to three) newlines at the front of
+// supertile r whose preceding newlines lie in earlier supertiles or chunks, and warp n_st leaves the stream's last
+// three newlines in the carry for the next chunk.
+__device__ __forceinline__ unsigned long long seam_stream_nl(uint32_t v, unsigned long long raw_base) {
+    return (raw_base + (v & 0x7FFFFFFFu)) | ((unsigned long long)(v >> 31) << 63);
+}
+// the `want` (<= 3) newlines that precede supertile r's newline number j, most recent first
+__device__ __forceinline__ int seam_collect(const SeamNl *seam, uint32_t r, int j, const ParseCarry *carry, int nl_in,
+                                            unsigned long long raw_base, unsigned long long out[3]) {
+    int got = 0;
+    for (int q = j - 1; q >= 0 && got < 3; --q) out[got++] = seam_stream_nl(seam[r].first[q], raw_base);
+    for (int t = (int)r - 1; t >= 0 && got < 3; --t) {
+        const uint32_t n = min(seam[t].n, 3u);
+        for (uint32_t q = 0; q < n && got < 3; ++q) out[got++] = seam_stream_nl(seam[t].last[2u - q], raw_base);
+    }
+    for (int q = 2; q >= 0 && got < 3; --q) {
+        const unsigned long long v = carry->last_nl[nl_in][q];
+        if (v == NL_NONE) return got;
+        out[got++] = v;
+    }
+    return got;
+}
 __global__ void front_fix_kernel(uint8_t *__restrict__ sym, ChunkGeom g, const uint32_t *__restrict__ region_count,
-                                 const uint8_t *__restrict__ tail_in, uint8_t *__restrict__ tail_out) {
+                                 const uint8_t *__restrict__ tail_in, uint8_t *__restrict__ tail_out,
+                                 const SeamNl *__restrict__ seam, const uint32_t *__restrict__ st_state, ParseCarry *carry,
+                                 int nl_in, uint32_t halo) {
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (r > g.n_st) return;
-    uint8_t *dst = r < g.n_st ? (sym + (size_t)SYM_FRONT + (size_t)r * g.region_stride - 32) : tail_out;
-    uint32_t back = 31u - lane;                      // symbols between the wanted one and the end of the stream so far
-    uint8_t v = 0;
-    bool found = false;
-    for (int j = (int)r - 1; j >= 0; --j) {
-        const uint32_t n = region_count[j];
-        if (back < n) { v = sym[(size_t)SYM_FRONT + (size_t)j * g.region_stride + (n - 1u - back)]; found = true; break; }
-        back -= n;
+    if (seam != nullptr && lane < 3u) {
+        const unsigned long long raw_base = carry->chunk_raw_base;
+        const unsigned long long PM = ~(1ULL << 63);
+        if (r < g.n_st) {
+            const int j = (int)lane;
+            if ((uint32_t)j < min(seam[r].n, 3u) && ((st_state[r] + (uint32_t)j) & 3u) == 3u) {
+                unsigned long long e[3];
+                if (seam_collect(seam, r, j, carry, nl_in, raw_base, e) == 3) {
+                    const unsigned long long e3 = seam_stream_nl(seam[r].first[j], raw_base);
+                    const unsigned long long ls = (e[1] & PM) - (e[2] & PM) - 1ULL - (e[1] >> 63);
+                    const unsigned long long lq = (e3 & PM) - (e[0] & PM) - 1ULL - (e3 >> 63);
+                    if (ls != lq) atomicMin((unsigned long long *)&carry->len_bad_pos, e[2] & PM);
+                }
+            }
+        } else if (lane == 0u) {
+            unsigned long long e[3];
+            const int got = seam_collect(seam, g.n_st, 0, carry, nl_in, raw_base, e);
+            for (int q = 0; q < 3; ++q) carry->last_nl[nl_in ^ 1][2 - q] = q < got ? e[q] : NL_NONE;
+        }
     }
-    if (!found) v = tail_in[31u - back];             // back < 32 here: the incoming tail holds the 32 symbols before the chunk
-    dst[lane] = v;
+    uint8_t *dst = r < g.n_st ? (sym + (size_t)SYM_FRONT + (size_t)r * g.region_stride - halo) : tail_out;
+    for (uint32_t i = lane; i < halo; i += 32u) {
+        uint32_t back = halo - 1u - i;               // symbols between the wanted one and the end of the stream so far
+        uint8_t v = 0;
+        bool found = false;
+        for (int j = (int)r - 1; j >= 0; --j) {
+            const uint32_t n = region_count[j];
+            if (back < n) { v = sym[(size_t)SYM_FRONT + (size_t)j * g.region_stride + (n - 1u - back)]; found = true; break; }
+            back -= n;
+        }
+        if (!found) v = tail_in[halo - 1u - back];   // back < halo here: the incoming tail holds the halo symbols before the chunk
+        dst[i] = v;
+    }
 }
 
 __global__ void fill_bytes_kernel(uint8_t *p, uint32_t n, uint8_t v) {
@@ -768,11 +891,13 @@ void launch_phase(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, 
     phase_scan_kernel<<<1, 1024, 0, s>>>(st_map, g, carry, st_state, raw, mode == MODE_LINES ? 0 : 1);
 }
 void launch_pack(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, const uint32_t *st_state, uint8_t *sym,
-                 uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, cudaStream_t s) {
-    if (mode == MODE_LINES) pack_kernel<MODE_LINES><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
-    else if (mode == MODE_FASTA) pack_kernel<MODE_FASTA><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
-    else pack_kernel<MODE_FASTQ><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count);
-    front_fix_kernel<<<(g.n_st + 1 + 7) / 8, 256, 0, s>>>(sym, g, region_count, tail_in, tail_out);
+                 uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, SeamNl *seam, int nl_in, uint32_t halo,
+                 cudaStream_t s) {
+    if (mode == MODE_LINES) pack_kernel<MODE_LINES><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count, nullptr);
+    else if (mode == MODE_FASTA) pack_kernel<MODE_FASTA><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count, nullptr);
+    else pack_kernel<MODE_FASTQ><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count, seam);
+    front_fix_kernel<<<(g.n_st + 1 + 7) / 8, 256, 0, s>>>(sym, g, region_count, tail_in, tail_out,
+                                                        mode == MODE_FASTQ ? seam : nullptr, st_state, carry, nl_in, halo);
 }
 void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t s) {
     if (n) fill_bytes_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);

@@ -63,6 +63,12 @@ __device__ __forceinline__ uint32_t table_find(const TableView &t, unsigned long
     }
 }
 
+// k-mer codes are kw 64-bit words per entry (kw = 1 for k <= 32: the hot configuration keeps its single-word copy)
+__device__ __forceinline__ void copy_kmer(unsigned long long *dst, const unsigned long long *src, uint32_t kw) {
+    dst[0] = src[0];
+    for (uint32_t w = 1; w < kw; ++w) dst[w] = src[w];
+}
+
 // Pass 1: counts, strand counts and the minimum position per key.  Entries above the current
 // threshold (logged under an older, larger threshold) are dropped.
 // Optional hash band (lo, hi]: only entries inside it are absorbed (banded absorb of large logs).
@@ -97,7 +103,7 @@ __global__ void absorb_kmer_kernel(LogView log, uint32_t i0, uint32_t i1, TableV
     if (key > st->threshold || !in_band(band, key)) return;
     const uint32_t slot = table_find(t, key);
     if (slot == 0xFFFFFFFFu) return;
-    if (t.posx[slot] == px) t.kmer[slot] = log.kmer[i];
+    if (t.posx[slot] == px) copy_kmer(t.kmer + (size_t)slot * t.kw, log.kmer + (size_t)i * log.kw, t.kw);
 }
 
 // ---- device-decided absorb (asynchronous chunks) ---------------------------------------------------
@@ -148,14 +154,15 @@ __global__ void absorb_kmer_guarded_kernel(LogView log, const LaunchSlot *slot, 
         if (key > thr) continue;
         const uint32_t s = table_find(t, key);
         if (s == 0xFFFFFFFFu) continue;
-        if (t.posx[s] == px) t.kmer[s] = log.kmer[i];
+        if (t.posx[s] == px) copy_kmer(t.kmer + (size_t)s * t.kw, log.kmer + (size_t)i * log.kw, t.kw);
     }
 }
 
 __global__ void table_clear_kernel(TableView t) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= t.cap) {  // includes the side slot
-        t.key[i] = EMPTY_KEY; t.cnt[i] = 0; t.ext[i] = 0; t.posx[i] = ~0ULL; t.kmer[i] = 0;
+        t.key[i] = EMPTY_KEY; t.cnt[i] = 0; t.ext[i] = 0; t.posx[i] = ~0ULL;
+        for (uint32_t w = 0; w < t.kw; ++w) t.kmer[(size_t)i * t.kw + w] = 0;
     }
 }
 
@@ -478,7 +485,8 @@ __global__ void rebuild_kernel(const unsigned long long *__restrict__ keys, cons
     if (i >= keep) return;
     const uint32_t src = slots[i];
     to.cnt[dst] = from.cnt[src]; to.ext[dst] = from.ext[src];
-    to.posx[dst] = from.posx[src]; to.kmer[dst] = from.kmer[src];
+    to.posx[dst] = from.posx[src];
+    copy_kmer(to.kmer + (size_t)dst * to.kw, from.kmer + (size_t)src * from.kw, to.kw);
 }
 __global__ void reset_occupancy_kernel(SketchState *st) { st->occupied = 0; st->has_max_key = 0; }
 __global__ void reset_gather_kernel(SketchState *st) { st->gather_count = 0; }
@@ -494,13 +502,13 @@ __global__ void export_kernel(const unsigned long long *__restrict__ keys, const
     o_hash[i] = keys[i];
     o_cnt[i] = c > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)c;
     o_ext[i] = e > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)e;
-    o_kmer[i] = t.kmer[s];
+    copy_kmer(o_kmer + (size_t)i * t.kw, t.kmer + (size_t)s * t.kw, t.kw);
     o_posx[i] = t.posx[s];
 }
 
 // Select rows of the exported SoA by index (idx == nullptr: the first m rows) and expand the 2-bit
 // k-mer codes to the ASCII bytes KmerCount::kmer holds.  Pushed k-mers (arena flag) keep their index.
-__global__ void select_rows_kernel(const uint32_t *__restrict__ idx, uint32_t m, int k, uint32_t stride,
+__global__ void select_rows_kernel(const uint32_t *__restrict__ idx, uint32_t m, int k, uint32_t stride, uint32_t kw,
                                    const unsigned long long *__restrict__ i_hash, const uint32_t *__restrict__ i_cnt,
                                    const uint32_t *__restrict__ i_ext, const unsigned long long *__restrict__ i_kmer,
                                    const unsigned long long *__restrict__ i_posx, unsigned long long *o_hash,
@@ -509,14 +517,29 @@ __global__ void select_rows_kernel(const uint32_t *__restrict__ idx, uint32_t m,
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     const uint32_t i = idx ? idx[j] : j;
-    const unsigned long long codes = i_kmer[i], px = i_posx[i];
-    o_hash[j] = i_hash[i]; o_cnt[j] = i_cnt[i]; o_ext[j] = i_ext[i]; o_kmer[j] = codes; o_posx[j] = px;
+    const unsigned long long *codes = i_kmer + (size_t)i * kw;
+    const unsigned long long px = i_posx[i];
+    o_hash[j] = i_hash[i]; o_cnt[j] = i_cnt[i]; o_ext[j] = i_ext[i]; o_kmer[j] = codes[0]; o_posx[j] = px;
     uint8_t *dst = o_bytes + (size_t)j * stride;
     if (px & (1ULL << 8)) { for (uint32_t t = 0; t < stride; ++t) dst[t] = 0; }
     else {
-        for (int t = 0; t < k; ++t) dst[t] = (uint8_t)"ACGT"[(codes >> (2 * t)) & 3ULL];
+        for (int t = 0; t < k; ++t) dst[t] = (uint8_t)"ACGT"[(codes[t >> 5] >> (2 * (t & 31))) & 3ULL];
         for (uint32_t t = (uint32_t)k; t < stride; ++t) dst[t] = 0;
     }
+}
+
+// Test hook (fb2_sketcher_debug_bump): add to the 64-bit totals of an existing key, so a test can bring a count to
+// the edge of u32 without pushing 2^32 k-mers (mash.rs:48-49 saturate; export_kernel clamps).
+__global__ void debug_bump_kernel(TableView t, unsigned long long key, unsigned long long add_cnt, unsigned long long add_ext,
+                                  unsigned int *found) {
+    const uint32_t slot = table_find(t, key);
+    if (slot == 0xFFFFFFFFu) { *found = 0u; return; }
+    t.cnt[slot] += add_cnt; t.ext[slot] += add_ext;
+    *found = 1u;
+}
+void launch_debug_bump(TableView t, unsigned long long key, unsigned long long add_cnt, unsigned long long add_ext,
+                       unsigned int *found, cudaStream_t s) {
+    debug_bump_kernel<<<1, 1, 0, s>>>(t, key, add_cnt, add_ext, found);
 }
 
 // ---- launchers ---------------------------------------------------------------------------------
@@ -596,11 +619,11 @@ void launch_bucket_sort(const unsigned long long *keys, const uint32_t *vals, un
 uint32_t bucket_cap() { return BUCKET_CAP; }
 uint32_t radix_hist_words(uint32_t n) { return 256u * cdiv(n ? n : 1, SORT_SEG); }
 
-void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride, const unsigned long long *i_hash,
+void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride, uint32_t kw, const unsigned long long *i_hash,
                         const uint32_t *i_cnt, const uint32_t *i_ext, const unsigned long long *i_kmer,
                         const unsigned long long *i_posx, unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext,
                         unsigned long long *o_kmer, unsigned long long *o_posx, uint8_t *o_bytes, cudaStream_t s) {
-    if (m) select_rows_kernel<<<cdiv(m, 128), 128, 0, s>>>(idx, m, k, stride, i_hash, i_cnt, i_ext, i_kmer, i_posx, o_hash,
+    if (m) select_rows_kernel<<<cdiv(m, 128), 128, 0, s>>>(idx, m, k, stride, kw, i_hash, i_cnt, i_ext, i_kmer, i_posx, o_hash,
                                                           o_cnt, o_ext, o_kmer, o_posx, o_bytes);
 }
 void launch_select_keep(const unsigned long long *keys, uint32_t n, int scaled, unsigned long long size,

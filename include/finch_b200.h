@@ -37,7 +37,7 @@ extern "C" {
 #define FB2_ERECORD (-4)      /* invalid / truncated FASTQ record    (lib.rs:63 panics) */
 #define FB2_EEMPTY (-5)       /* no records in the stream            (lib.rs:72 panics) */
 #define FB2_ETOOFEW (-6)      /* "<name> had too few kmers (<n>) to sketch" (mod.rs:115-128) */
-#define FB2_EUNSUPPORTED (-7) /* kmer_length outside 1..=32, compressed input */
+#define FB2_EUNSUPPORTED (-7) /* bz2 / xz input, compressed bytes handed to the raw feed calls */
 #define FB2_EIO (-8)          /* file could not be opened / read     (lib.rs:43) */
 #define FB2_ENOMEM (-9)
 
@@ -54,7 +54,7 @@ typedef struct fb2_params {
     uint64_t kmers_to_sketch; /* Mash: heap size; Scaled: fill-up size (0 = pure scaled) */
     uint64_t final_size;      /* Mash only: process_post_filter truncation */
     int32_t no_strict;        /* Mash only */
-    uint8_t kmer_length;      /* 1..=32 on this build */
+    uint8_t kmer_length;      /* 1..=255 like the reference (mod.rs:59); 33..=255 run the exact multi-word kernel */
     uint64_t hash_seed;
     double scale;             /* Scaled only */
     int32_t device;           /* CUDA ordinal; -1 = current device */
@@ -141,6 +141,9 @@ int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out);
 int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint32_t *counts, size_t counts_cap,
                                uint8_t *sym, size_t sym_cap);
 int fb2_sketcher_enable_timing(fb2_sketcher *s, int on);
+/* Test hook: add to the 64-bit totals kept for `hash` (must be present), to reach the u32 saturation of
+ * mash.rs:48-49 without 2^32 pushes. */
+int fb2_sketcher_debug_bump(fb2_sketcher *s, uint64_t hash, uint64_t add_count, uint64_t add_extra);
 
 /* ---- FilterParams::filter_counts + SketchParams::process_post_filter ---------------------- */
 /* (filtering.rs:60-87, mod.rs:115-128).  In place on `r`; `f` is updated like the reference

@@ -81,6 +81,26 @@ def test_pure_scaled_property(fb):  # scaled.rs:202-213
     assert all(e.hash <= (2**64 - 1) // 100 for e in q.to_vec(4))
 
 
+def test_counts_saturate_at_u32_max(fb):  # mash.rs:48-49: count.0.saturating_add(1), count.1.saturating_add(extra)
+    for mk in ("mash", "scaled"):
+        q = fb.MashSketcher(3, 2, 42) if mk == "mash" else fb.ScaledSketcher(3, 1.0, 2, 42)
+        q.push(b"ac", 1); q.push(b"ac", 1); q.push(b"ca", 0)
+        v = {e.kmer: e for e in q.to_vec(2)}
+        assert (v[b"ac"].count, v[b"ac"].extra_count) == (2, 2)
+        q.debug_bump(v[b"ac"].hash, 2**32 - 4, 2**32 - 5)            # totals now (2^32 - 2, 2^32 - 3)
+        v = {e.kmer: e for e in q.to_vec(2)}
+        assert (v[b"ac"].count, v[b"ac"].extra_count) == (2**32 - 2, 2**32 - 3)
+        q.push(b"ac", 1)                                             # (2^32 - 1, 2^32 - 2): the largest u32, exact
+        v = {e.kmer: e for e in q.to_vec(2)}
+        assert (v[b"ac"].count, v[b"ac"].extra_count) == (2**32 - 1, 2**32 - 2)
+        for _ in range(3):
+            q.push(b"ac", 1)                                         # saturated: stays at u32::MAX
+        v = {e.kmer: e for e in q.to_vec(2)}
+        assert (v[b"ac"].count, v[b"ac"].extra_count) == (2**32 - 1, 2**32 - 1)
+        assert (v[b"ca"].count, v[b"ca"].extra_count) == (1, 0)
+        q.close()
+
+
 def test_longer_sequence_seed42(fb):  # mash.rs:136-154
     q = fb.MashSketcher(100, 21, 42)
     q.process(b"ACACGGAAATCCTCACGTCGCGGCGCCGGGC")
@@ -112,7 +132,10 @@ def test_cli_golden_query_fa(fb, kind):  # cli/tests/test_cli.rs:80-149
 CASES = []
 for i, (kind, size, k) in enumerate([("mash", 50, 21), ("mash", 1000, 21), ("mash", 7, 5), ("mash", 300, 31),
                                      ("mash", 100, 32), ("mash", 100, 16), ("mash", 64, 1), ("scaled", 20, 21),
-                                     ("scaled", 0, 11), ("scaled", 500, 31), ("mash", 100000, 13)]):
+                                     ("scaled", 0, 11), ("scaled", 500, 31), ("mash", 100000, 13),
+                                     # k > 32 (the reference takes any u8, mod.rs:59): exact multi-word kernel
+                                     ("mash", 200, 33), ("mash", 100, 48), ("scaled", 50, 64), ("mash", 300, 255),
+                                     ("mash", 100, 100)]):
     CASES.append((i, kind, size, k))
 
 
@@ -151,6 +174,41 @@ def test_chunk_seams_anywhere(fb, oracle, fmt):
         gres, gtotals, _ = gpu_sketch(fb, data, "mash", 200, 21, 0, pieces=pieces)
         assert gtotals == ototals
         assert_same(gres, ovec, 21)
+
+
+def test_gt_inside_fasta_sequence_line(fb, oracle):
+    """'>' only starts a record at a line start; inside a sequence line it is just a non-base byte."""
+    rng = np.random.default_rng(9)
+    lines = []
+    for r in range(40):
+        lines.append(b">rec%d" % r)
+        for _ in range(int(rng.integers(1, 6))):
+            s = bytearray(gen.rand_seq(rng, int(rng.integers(30, 90)), 0.0))
+            for pos in rng.integers(1, len(s), size=int(rng.integers(0, 3))):
+                s[int(pos)] = ord(">")
+            lines.append(bytes(s))
+    data = b"\n".join(lines) + b"\n"
+    for k in (5, 21):
+        ovec, ototals, ofmt = oracle_sketch(oracle, data, "mash", 400, k, 0)
+        gres, gtotals, gfmt = gpu_sketch(fb, data, "mash", 400, k, 0)
+        assert (gfmt, gtotals) == (ofmt, ototals)
+        assert_same(gres, ovec, k)
+
+
+def test_one_byte_first_piece_is_sniffed_with_the_next(fb, oracle):
+    """Format sniffing waits for two bytes: a gzip magic split over two pieces is still reported as compressed
+    input, and a 1-byte first piece of a plain file changes nothing."""
+    sp = fb.SketchParams.mash(50, 50, True, 11, 0)
+    with sp.create_sketcher() as s:
+        s.feed_fastx(b"\x1f", final=False)
+        with pytest.raises(fb.FinchError) as e:
+            s.feed_fastx(b"\x8b\x08\x00", final=True)
+        assert e.value.code == fb.EUNSUPPORTED
+    data = gen.fasta(np.random.default_rng(3), n_records=3, max_len=400)
+    ovec, ototals, _ = oracle_sketch(oracle, data, "mash", 50, 11, 0)
+    gres, gtotals, _ = gpu_sketch(fb, data, "mash", 50, 11, 0, pieces=[1, 1, 5])
+    assert gtotals == ototals
+    assert_same(gres, ovec, 11)
 
 
 def test_process_records_api(fb, oracle):
@@ -378,11 +436,92 @@ def test_errors(fb):
         fb.sketch_stream(b">a\nACGTACGTACGTACGTACGTACGTAAAC\n", "few", sp, fb.FilterParams())
     assert e.value.code == fb.ETOOFEW and "few had too few kmers (" in e.value.message
     with pytest.raises(fb.FinchError) as e:
-        fb.SketchParams.mash(10, 10, False, 33, 0).create_sketcher()
-    assert e.value.code == fb.EUNSUPPORTED
+        fb.SketchParams.mash(10, 10, False, 0, 0).create_sketcher()
+    assert e.value.code == fb.EINVAL
     with pytest.raises(fb.FinchError) as e:
         fb.sketch_files(["/nonexistent/file.fa"], sp, fb.FilterParams())
     assert e.value.code == fb.EIO and "No such file or directory" in e.value.message  # test_cli.rs:9-18
+
+
+@pytest.mark.parametrize("k,fmt", [(40, "fasta"), (64, "fastq"), (255, "fasta")])
+def test_big_k_multi_chunk(fb, synth, oracle, monkeypatch, k, fmt):
+    """k > 32 across chunk and region seams (1 MiB chunks: the 256-symbol halo carries k - 1 symbols), with the
+    CLI's filter tail on the FASTQ case."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    if fmt == "fasta":
+        data = synth.synth_fasta(2_600_000, n_records=3, line_width=60, lower_frac=0.03, n_frac=0.004, seed=40 + k).tobytes()
+    else:
+        genome = synth.synth_genome(60_000, 5)
+        data = synth.synth_fastq(genome, 9_000, 150, 0.01, 7)[0].tobytes()
+    for kind, size, scale in (("mash", 3000, 0.0), ("scaled", 100, 0.01)):
+        ovec, ototals, _ = oracle_sketch(oracle, data, kind, size, k, 0, scale or 0.001)
+        gres, gtotals, _ = gpu_sketch(fb, data, kind, size, k, 0, scale or 0.001)
+        assert gtotals == ototals
+        assert_same(gres, ovec, k)
+
+
+def _fastq_records(rng, n, crlf):
+    nl = b"\r\n" if crlf else b"\n"
+    recs = []
+    for r in range(n):
+        m = int(rng.integers(0, 260))
+        s = gen.rand_seq(rng, m, 0.01)
+        q = bytes(rng.integers(33, 74, size=m).astype(np.uint8))
+        recs.append([b"@r%d" % r, s, b"+", q])
+    return recs, nl
+
+
+def _join(recs, nl, final_newline=True):
+    data = b"".join(nl.join(r) + nl for r in recs)
+    return data if final_newline else data[:-len(nl)]
+
+
+@pytest.mark.parametrize("st_tiles", ["1", "8"])
+@pytest.mark.parametrize("crlf", [False, True])
+def test_fastq_seq_qual_length_mismatch(fb, oracle, monkeypatch, st_tiles, crlf):
+    """needletail rejects a record whose sequence and quality lengths differ (the reference panics, lib.rs:63);
+    the oracle returns E_RECORD.  Records are broken one at a time: at chunk seams (1 MiB chunks), supertile
+    seams, batch seams inside a supertile, the first and the last record, with and without a final newline."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    monkeypatch.setenv("FB2_ST_TILES", st_tiles)
+    rng = np.random.default_rng(5 + int(st_tiles) + 2 * crlf)
+    recs, nl = _fastq_records(rng, 9000, crlf)
+    sp = fb.SketchParams.mash(500, 500, True, 21, 0)
+    osp = oracle.mash_params(500, 500, True, 21, 0)
+    good = _join(recs, nl)
+    assert len(good) > (2 << 20)
+    rc, osk = oracle.sketch_stream(good, osp, oracle.make_filter(False))
+    assert rc == oracle.OK
+    sk = fb.sketch_stream(good, "good", sp, fb.FilterParams(False))
+    assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+    # record offsets, to aim at the seams
+    offs = np.cumsum([0] + [sum(len(x) for x in r) + 4 * len(nl) for r in recs])
+    targets = {0, 1, len(recs) - 1, len(recs) - 2}
+    for seam in (1 << 20, 2 << 20, 4096 * 7, 16384 * 3, 32768 * 5):
+        i = int(np.searchsorted(offs, seam))
+        targets.update({max(0, i - 2), max(0, i - 1), min(len(recs) - 1, i)})
+    targets.update(int(x) for x in rng.integers(0, len(recs), size=6))
+    for trial, i in enumerate(sorted(targets)):
+        bad = [list(r) for r in recs]
+        how = trial % 4
+        if how == 0: bad[i][3] = bad[i][3] + b"I"                # quality one longer
+        elif how == 1: bad[i][1] = bad[i][1] + b"A"              # sequence one longer
+        elif how == 2: bad[i][3] = bad[i][3][:-1] if bad[i][3] else b"II"
+        else: bad[i][1] = bad[i][1][:-1] if bad[i][1] else b"AC"
+        for final_newline in ((True, False) if i >= len(recs) - 2 else (True,)):
+            data = _join(bad, nl, final_newline)
+            rc, _ = oracle.sketch_stream(data, osp, oracle.make_filter(False))
+            assert rc == oracle.E_RECORD, (i, how)
+            with pytest.raises(fb.FinchError) as e:
+                fb.sketch_stream(data, "bad", sp, fb.FilterParams(False))
+            assert e.value.code == fb.ERECORD, (i, how, final_newline, e.value.message)
+    # no false positives without a final newline / with a CR-less last line / trailing blank lines
+    for tail in (b"", nl, nl + nl + b"\r\n\n"):
+        data = _join(recs, nl, final_newline=False) + tail
+        rc, osk = oracle.sketch_stream(data, osp, oracle.make_filter(False))
+        assert rc == oracle.OK
+        sk = fb.sketch_stream(data, "good", sp, fb.FilterParams(False))
+        assert np.array_equal(sk.hashes_u64, osk["hashes"]) and sk.seq_length == osk["seq_length"]
 
 
 def test_sketch_files(fb, oracle, tmp_path):
