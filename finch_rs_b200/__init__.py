@@ -74,7 +74,8 @@ EXPORTS = [
     "fb2_sketcher_push", "fb2_sketcher_feed_fastx", "fb2_sketcher_feed_device", "fb2_sketcher_format",
     "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats",
     "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_sketcher_debug_bump", "fb2_filter_counts", "fb2_process_post_filter",
-    "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_release_pool", "fb2_dist_batch",
+    "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_multi", "fb2_sketch_stream_multi",
+    "fb2_sketch_files_release_pool", "fb2_dist_batch",
     "fb2_dist_all_pairs", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_old_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
 ]
 
@@ -115,6 +116,8 @@ def lib():
     L.fb2_guess_filter_threshold.restype = C.c_uint32
     L.fb2_sketch_stream.argtypes = [vp, sz, C.c_char_p, C.POINTER(_Params), C.POINTER(_Filter), C.POINTER(_Result)]
     L.fb2_sketch_files.argtypes = [C.POINTER(C.c_char_p), sz, C.POINTER(_Params), C.POINTER(_Filter), C.POINTER(_Result)]
+    L.fb2_sketch_files_multi.argtypes = [C.POINTER(C.c_char_p), sz, C.POINTER(_Params), C.POINTER(_Filter), C.POINTER(_Result), C.c_int]
+    L.fb2_sketch_stream_multi.argtypes = [vp, sz, C.c_char_p, C.POINTER(_Params), C.POINTER(_Filter), C.POINTER(_Result), C.c_int]
     L.fb2_dist_batch.argtypes = [vp, vp, sz, sz, C.c_double, vp, vp, sz, vp, C.c_int32]
     L.fb2_dist_all_pairs.argtypes = [vp, vp, sz, sz, C.c_double, sz, sz, vp, C.c_int32]
     L.fb2_distance_finish.argtypes = [C.POINTER(_PairOut), C.c_uint8, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -435,13 +438,28 @@ def sketch_stream(data, name: str, sketch_params: SketchParams, filters: FilterP
     return _finish(r, name, sketch_params)
 
 
-def sketch_files(filenames, sketch_params: SketchParams, filters: FilterParams) -> List[Sketch]:
-    """lib/src/lib.rs:29-49; results in input order."""
+def sketch_stream_multi(data, name: str, sketch_params: SketchParams, filters: FilterParams, ngpus=0) -> Sketch:
+    """sketch_stream of one file cut into byte ranges over `ngpus` GPUs (0 = all), united exactly on the first."""
+    if isinstance(data, int):
+        raise TypeError("pass a buffer, or use sketch_stream_multi_ptr(ptr, nbytes, ...)")
+    addr, n, keep = _addr(data)
+    return sketch_stream_multi_ptr(addr, n, name, sketch_params, filters, ngpus)
+
+
+def sketch_stream_multi_ptr(host_ptr, nbytes, name, sketch_params, filters, ngpus=0) -> Sketch:
+    r = _Result()
+    cp, cf = sketch_params._c(), filters._c()
+    _check(lib().fb2_sketch_stream_multi(host_ptr, nbytes, name.encode(), C.byref(cp), C.byref(cf), C.byref(r), ngpus))
+    return _finish(r, name, sketch_params)
+
+
+def sketch_files(filenames, sketch_params: SketchParams, filters: FilterParams, ngpus=1) -> List[Sketch]:
+    """lib/src/lib.rs:29-49; results in input order.  ngpus: shard the files over that many GPUs (0 = all)."""
     n = len(filenames)
     arr = (C.c_char_p * n)(*[f.encode() for f in filenames])
     outs = (_Result * n)()
     cp, cf = sketch_params._c(), filters._c()
-    _check(lib().fb2_sketch_files(arr, n, C.byref(cp), C.byref(cf), outs))
+    _check(lib().fb2_sketch_files_multi(arr, n, C.byref(cp), C.byref(cf), outs, ngpus))
     return [_finish(outs[i], filenames[i], sketch_params) for i in range(n)]
 
 

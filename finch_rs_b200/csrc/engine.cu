@@ -251,6 +251,7 @@ static void size_logs(fb2_sketcher *s) {
     // file is hashed in ONE launch and the banded absorb picks the bottom band from the whole log.
     s->next_launch = std::max<uint32_t>(32u * HASH_TILE, (s->log_cap / 8u * 7u) / HASH_TILE * HASH_TILE);
 }
+static void apply_finish_hint(fb2_sketcher *s);
 // The logs are allocated at first use (a handle that only ever sees small sketches stays small).
 static int ensure_logs(fb2_sketcher *s) {
     for (int i = 0; i < 2; ++i) {
@@ -975,13 +976,7 @@ static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
     else return fb2_fail(FB2_EFORMAT, "could not detect FASTA/FASTQ: first byte is neither '>' nor '@'");
     TRY(flush_all(s));
     TRY(pull_state(s));
-    if (s->hint_set && !s->scaled && s->hint_final < s->size && s->h_state->occupied == 0 && s->h_state->has_max_key == 0 &&
-        s->total_kmers == 0 && (s->hint_filter == 0 || (s->hint_filter < 0 && s->format == FB2_FORMAT_FASTA))) {
-        // the filter resolves to off (lib.rs:71-76) and the result is truncated to final_size: the bottom final_size
-        // of the bottom kmers_to_sketch is the bottom final_size (SURVEY Q1) -- sketch with the small heap
-        s->size = s->hint_final;
-        size_logs(s);
-    }
+    apply_finish_hint(s);
     ParseCarry *c_ = s->h_carry;
     c_->state = s->format == FB2_FORMAT_FASTA ? 1u : 0u;  // FASTA: pretend a header line precedes byte 0
     c_->prev1 = c_->prev2 = '\n';
@@ -1021,7 +1016,32 @@ static int end_stream(fb2_sketcher *s) {
         else {
             const uint32_t phase_last = (c->state + 4u - (uint32_t)(nl_trail % 4)) & 3u;
             const uint64_t last_sig_pos = L - n_trail - 1;
-            if (phase_last != 3u)
+            // A last record with an EMPTY quality line: the last significant byte then lies in its '+' line.  The
+            // reader accepts it when the '+' line is terminated and the sequence is as long as what follows (nothing,
+            // or carriage returns: one is trimmed).  Decided here from the host's copy of the stream's last bytes.
+            bool empty_qual_ok = false, empty_qual_lens_differ = false;
+            if (phase_last == 2u && nl_trail >= 1) {
+                const size_t sig = t.size() - 1 - n_trail;                 // index of the last significant byte in t
+                size_t l3 = sig + 1;
+                while (t[l3] != '\n') ++l3;                                 // newline of the '+' line (exists: nl_trail >= 1)
+                size_t crs = 0;
+                for (size_t j = l3 + 1; j < t.size() && t[j] != '\n'; ++j) ++crs;
+                const uint64_t qual_len = crs ? crs - 1 : 0;
+                long e1 = (long)sig;
+                while (e1 >= 0 && t[(size_t)e1] != '\n') --e1;              // newline that ends the sequence line
+                if (e1 >= 0) {
+                    long e0 = e1 - 1;
+                    while (e0 >= 0 && t[(size_t)e0] != '\n') --e0;          // newline that ends the header line
+                    if (e0 >= 0) {
+                        const uint64_t seq_len = (uint64_t)(e1 - e0 - 1) - ((e1 - 1 > e0 && t[(size_t)e1 - 1] == '\r') ? 1 : 0);
+                        empty_qual_ok = seq_len == qual_len;
+                        empty_qual_lens_differ = !empty_qual_ok;
+                    } else if ((uint64_t)e1 > qual_len + 1) empty_qual_lens_differ = true;   // sequence longer than the host's tail copy
+                }
+            }
+            if (empty_qual_lens_differ)
+                rc = fb2_fail(FB2_ERECORD, "invalid FASTQ record: sequence and quality lengths differ (last record)");
+            else if (phase_last != 3u && !empty_qual_ok)
                 rc = fb2_fail(FB2_ERECORD, "truncated FASTQ record at end of input");
             else if (c->first_bad_pos != ~0ULL && c->first_bad_pos <= last_sig_pos)
                 rc = fb2_fail(FB2_ERECORD, "invalid FASTQ record: line at byte " + std::to_string(c->first_bad_pos) +
@@ -1031,7 +1051,7 @@ static int end_stream(fb2_sketcher *s) {
                 // The kernels checked every quality line that ends in a newline; a last one that does not is checked
                 // here from the stream's last three newlines (the header, sequence and '+' line ends of that record).
                 uint64_t bad = c->len_bad_pos;
-                if (nl_trail == 0) {
+                if (nl_trail == 0 && phase_last == 3u) {
                     const uint64_t *e = c->last_nl[s->tail_sel];   // as left by the last chunk
                     const unsigned long long PM = ~(1ULL << 63);
                     if (e[0] != NL_NONE && e[1] != NL_NONE && e[2] != NL_NONE) {
@@ -1138,6 +1158,120 @@ extern "C" int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev, siz
         if (!s->stream_open) return fb2_fail(FB2_EEMPTY, "empty input: no records");
         TRY(end_stream(s));
     }
+    return FB2_OK;
+}
+
+// ---- one FASTX stream split into byte ranges over several sketchers (hostlogic.cpp: fb2_sketch_stream_multi) ------
+// Internal API.  A range starts at a line start chosen by the host, which supplies what the parser would have
+// carried to that point: the line state, the two previous raw bytes, the `halo` symbols that precede the range in
+// stream order (k-mers span the cut), the stream offset and a position-id base (later ranges get larger ids so the
+// first occurrence of a hash in stream order survives the merge).
+static void apply_finish_hint(fb2_sketcher *s) {
+    if (s->hint_set && !s->scaled && s->hint_final < s->size && s->h_state->occupied == 0 && s->h_state->has_max_key == 0 &&
+        s->total_kmers == 0 && (s->hint_filter == 0 || (s->hint_filter < 0 && s->format == FB2_FORMAT_FASTA))) {
+        // the filter resolves to off (lib.rs:71-76) and the result is truncated to final_size: the bottom final_size
+        // of the bottom kmers_to_sketch is the bottom final_size (SURVEY Q1) -- sketch with the small heap
+        s->size = s->hint_final;
+        size_logs(s);
+    }
+}
+int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32_t prev1, uint32_t prev2,
+                             const uint8_t *tail_syms /* halo symbols, may be null = all breaks */, uint64_t raw_base,
+                             uint64_t ord_base) {
+    if (!s || s->stream_open) return fb2_fail(FB2_EINVAL, "begin_range: bad handle state");
+    CU(cudaSetDevice(s->device));
+    s->format = format;
+    TRY(flush_all(s));
+    TRY(pull_state(s));
+    apply_finish_hint(s);
+    ParseCarry *c = s->h_carry;
+    c->state = state; c->prev1 = prev1; c->prev2 = prev2;
+    c->raw_total = raw_base; c->n_records = 0; c->first_bad_pos = ~0ULL; c->last_sig = 0; c->error = 0;
+    c->len_bad_pos = ~0ULL;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 3; ++b) c->last_nl[a][b] = NL_NONE;
+    TRY(push_carry(s));
+    if (tail_syms) {
+        CU(cudaMemcpyAsync(s->d_tail.as<uint8_t>() + s->halo * s->tail_sel, tail_syms, s->halo, cudaMemcpyHostToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));
+    }
+    s->ordinal = ord_base;
+    s->stream_open = true;
+    s->tail_host.clear();
+    return FB2_OK;
+}
+// End of a range that is NOT the end of the stream: everything queued is done, no end-of-stream rules applied.
+// Reports the parser state the next range must have started from, and the first record errors seen (~0: none).
+int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_byte, uint64_t *first_bad_pos, uint64_t *len_bad_pos) {
+    if (!s) return fb2_fail(FB2_EINVAL, "null handle");
+    CU(cudaSetDevice(s->device));
+    TRY(flush_stage(s));
+    TRY(settle_all(s));
+    TRY(pull_state(s));
+    if (end_state) *end_state = s->h_carry->state;
+    if (last_byte) *last_byte = s->h_carry->prev1;
+    if (first_bad_pos) *first_bad_pos = s->h_carry->first_bad_pos;
+    if (len_bad_pos) *len_bad_pos = s->h_carry->len_bad_pos;
+    s->stream_open = false;
+    return FB2_OK;
+}
+uint32_t fb2_sketcher_halo(const fb2_sketcher *s) { return s->halo; }
+int fb2_sketcher_device(const fb2_sketcher *s) { return s->device; }
+
+// Exact union of `src`'s sketch state into `dst` (both idle, same parameters): the live entries of src's table are
+// merged into dst's table by kernels running on dst's GPU that read src's table through peer access (NVLink); when
+// the devices cannot address each other the table is first copied with cudaMemcpyPeer.  Totals add up.
+int fb2_sketcher_merge_from(fb2_sketcher *dst, fb2_sketcher *src) {
+    if (!dst || !src || dst == src) return fb2_fail(FB2_EINVAL, "merge: bad handles");
+    if (dst->k != src->k || dst->scaled != src->scaled || dst->size != src->size || dst->prm.hash_seed != src->prm.hash_seed ||
+        (dst->scaled && dst->max_hash != src->max_hash))
+        return fb2_fail(FB2_EINVAL, "merge: sketchers differ in parameters");
+    CU(cudaSetDevice(src->device));
+    TRY(flush_all(src));
+    TRY(pull_state(src));
+    const SketchState ss = *src->h_state;
+    const TableView sv = src->tab[src->cur].view();
+    CU(cudaSetDevice(dst->device));
+    TRY(flush_all(dst));
+    TRY(pull_state(dst));
+    // room for every live source entry (upper bound: its occupancy)
+    {
+        const uint64_t need = (uint64_t)ss.occupied + 1;
+        const uint32_t cap = dst->tab[dst->cur].cap;
+        if ((uint64_t)dst->h_state->occupied + need > (uint64_t)cap / 4 * 3) TRY(prune(dst, (uint32_t)std::min<uint64_t>(need, 1u << 30)));
+    }
+    if (ss.threshold < dst->h_state->threshold) {      // both are valid admission thresholds of the whole stream: keep the lower
+        dst->h_state->threshold = ss.threshold;
+        TRY(push_state(dst));
+    }
+    TableView from = sv;
+    DevBuf cp[5];
+    if (src->device != dst->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, dst->device, src->device);
+        bool direct = can != 0 && !getenv("FB2_NO_PEER_ACCESS");
+        if (direct) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) direct = false;
+            cudaGetLastError();
+        }
+        if (!direct) {   // staged: peer copies of the five table arrays into scratch on dst's device
+            const size_t n = (size_t)sv.cap + 1;
+            const void *srcp[5] = {sv.key, sv.cnt, sv.ext, sv.posx, sv.kmer};
+            for (int a = 0; a < 5; ++a) {
+                const size_t bytes = n * 8 * (a == 4 ? sv.kw : 1);
+                TRY(cp[a].ensure(bytes));
+                CU(cudaMemcpyPeerAsync(cp[a].p, dst->device, srcp[a], src->device, bytes, dst->st));
+            }
+            from.key = cp[0].as<unsigned long long>(); from.cnt = cp[1].as<unsigned long long>(); from.ext = cp[2].as<unsigned long long>();
+            from.posx = cp[3].as<unsigned long long>(); from.kmer = cp[4].as<unsigned long long>();
+        }
+    }
+    launch_merge_tables(from, ss.threshold, ss.has_max_key, dst->tab[dst->cur].view(), (SketchState *)dst->d_state.p, dst->st);
+    dst->stats.kernel_launches += 2;
+    TRY(pull_state(dst));
+    for (auto &b : cp) b.release();
+    dst->total_kmers += src->total_kmers;
+    dst->lines_bases += src->h_carry->total_bases + src->lines_bases;   // host-side sum: seq_length = carry + lines_bases
     return FB2_OK;
 }
 

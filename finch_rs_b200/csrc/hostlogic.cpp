@@ -21,12 +21,21 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <sys/stat.h>
 #include <zlib.h>
+
+#include "common.cuh"
 
 #include "../../include/finch_b200.h"
 
 int fb2_fail(int code, const std::string &msg);  // engine.cu
-void fb2_sketcher_hint_finish(fb2_sketcher *s, uint64_t final_size, int filter_on);   // engine.cu (internal)
+// engine.cu (internal API, not exported in the header)
+void fb2_sketcher_hint_finish(fb2_sketcher *s, uint64_t final_size, int filter_on);
+int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32_t prev1, uint32_t prev2,
+                             const uint8_t *tail_syms, uint64_t raw_base, uint64_t ord_base);
+int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_byte, uint64_t *first_bad_pos, uint64_t *len_bad_pos);
+uint32_t fb2_sketcher_halo(const fb2_sketcher *s);
+int fb2_sketcher_merge_from(fb2_sketcher *dst, fb2_sketcher *src);
 
 // ---- filters ---------------------------------------------------------------------------------
 static void compact(fb2_result *r, const std::vector<uint8_t> &keep) {
@@ -263,31 +272,56 @@ static bool pool_acquire(const fb2_params *p, fb2_sketcher **s, uint8_t **buf) {
 }
 static bool pool_release(const fb2_params *p, fb2_sketcher *s, uint8_t *buf) {
     std::lock_guard<std::mutex> g(g_pool_mu);
-    if (g_pool.size() >= pool_max() || p->stream) return false;
+    size_t on_device = 0;
+    for (const auto &e : g_pool) on_device += e.p.device == p->device;
+    if (on_device >= pool_max() || p->stream) return false;
     g_pool.push_back(PoolEntry{*p, s, buf, pool_env_key()});
     return true;
 }
 extern "C" void fb2_sketch_files_release_pool(void) {
     std::vector<PoolEntry> old;
     { std::lock_guard<std::mutex> g(g_pool_mu); old.swap(g_pool); }
-    for (auto &e : old) { cudaFreeHost(e.buf); fb2_sketcher_destroy(e.s); }
+    for (auto &e : old) { if (e.buf) cudaFreeHost(e.buf); fb2_sketcher_destroy(e.s); }
 }
 
 // sketch_files (lib.rs:29-49): the reference fans the files out over a rayon pool, one sketcher per task.
-// Here a few host threads each own one sketcher handle (its own CUDA streams and buffers) and pull
-// file indices from a shared counter, so the small kernels and host<->device round trips of different
-// files overlap on the GPU; results land in input order.  FB2_FILE_WORKERS overrides the thread count.
-extern "C" int fb2_sketch_files(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
-                                fb2_result *outs) {
-    if (!p || !f || (n && (!paths || !outs))) return fb2_fail(FB2_EINVAL, "null argument");
+// Here every GPU gets a few host threads, each owning one sketcher handle (its own CUDA streams and buffers);
+// files are assigned to GPUs longest-first (LPT by file size) and a GPU's threads pull from its own list, so the
+// small kernels and host<->device round trips of different files overlap on each GPU; results land in input
+// order.  The finished sketches need no device-side gather: this is ONE process driving all GPUs, every worker
+// copies its 24 KB result straight into the caller's host array (a gather to one GPU followed by a copy to the
+// host would move the same bytes twice; the NCCL gather lives where there is one process per GPU: bench.py).
+// FB2_FILE_WORKERS overrides the thread count per GPU.
+static int sketch_files_on(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
+                           fb2_result *outs, const std::vector<int> &devices) {
     for (size_t i = 0; i < n; ++i) memset(&outs[i], 0, sizeof(fb2_result));
     if (!n) return FB2_OK;
+    const size_t G = devices.size();
     size_t workers = 8;
     if (const char *e = getenv("FB2_FILE_WORKERS")) { const long v = atol(e); if (v >= 1 && v <= 64) workers = (size_t)v; }
-    workers = std::min(workers, n);
-    for (size_t i = 0; i < n; ++i) if (strcmp(paths[i], "-") == 0) workers = 1;   // stdin is consumed in order
+    bool has_stdin = false;
+    for (size_t i = 0; i < n; ++i) if (strcmp(paths[i], "-") == 0) has_stdin = true;   // stdin is consumed in order
+    // LPT: files by decreasing size onto the least loaded GPU; each GPU's list stays in that order
+    std::vector<std::vector<size_t>> lists(G);
+    if (G == 1 || has_stdin) { for (size_t i = 0; i < n; ++i) lists[0].push_back(i); }
+    else {
+        std::vector<std::pair<uint64_t, size_t>> sized(n);
+        for (size_t i = 0; i < n; ++i) {
+            struct stat sb;
+            sized[i] = {stat(paths[i], &sb) == 0 ? (uint64_t)sb.st_size : 0ull, i};
+        }
+        std::stable_sort(sized.begin(), sized.end(), [](const std::pair<uint64_t, size_t> &x, const std::pair<uint64_t, size_t> &y) { return x.first > y.first; });
+        std::vector<uint64_t> load(G, 0);
+        for (const auto &fz : sized) {
+            size_t g = 0;
+            for (size_t j = 1; j < G; ++j) if (load[j] < load[g]) g = j;
+            lists[g].push_back(fz.second);
+            load[g] += fz.first + 4096;
+        }
+    }
     const size_t piece = 32u << 20;
-    std::atomic<size_t> next{0};
+    std::vector<std::atomic<size_t>> next(G);
+    for (auto &a : next) a.store(0);
     std::atomic<int> first_rc{FB2_OK};
     std::mutex mu;
     std::string first_msg;
@@ -295,39 +329,234 @@ extern "C" int fb2_sketch_files(const char *const *paths, size_t n, const fb2_pa
         std::lock_guard<std::mutex> g(mu);
         if (first_rc.load() == FB2_OK) { first_rc.store(rc); first_msg = fb2_last_error(); }
     };
-    auto work = [&]() {
+    auto work = [&](size_t g) {
+        fb2_params pd = *p;
+        pd.device = devices[g];
         fb2_sketcher *s = nullptr;
         uint8_t *buf = nullptr;
-        bool reuse = pool_acquire(p, &s, &buf);     // an idle handle of an earlier call, same parameters
+        bool reuse = pool_acquire(&pd, &s, &buf);     // an idle handle of an earlier call, same parameters and device
         int rc = FB2_OK;
-        if (!reuse) {
-            rc = fb2_sketcher_create(p, &s);        // selects the device for this thread
-            if (rc == FB2_OK && cudaHostAlloc((void **)&buf, piece, cudaHostAllocDefault) != cudaSuccess)
+        if (!reuse) rc = fb2_sketcher_create(&pd, &s);   // selects the device for this thread
+        if (rc == FB2_OK && !buf) {                      // (handles pooled by fb2_sketch_stream_multi carry no read buffer)
+            cudaSetDevice(pd.device);
+            if (cudaHostAlloc((void **)&buf, piece, cudaHostAllocDefault) != cudaSuccess)
                 rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed (file read buffer)");
         }
         while (rc == FB2_OK && first_rc.load() == FB2_OK) {
-            const size_t i = next.fetch_add(1);
-            if (i >= n) break;
-            rc = sketch_one_file(s, reuse, paths[i], buf, piece, p, f, &outs[i]);
+            const size_t q = next[g].fetch_add(1);
+            if (q >= lists[g].size()) break;
+            const size_t i = lists[g][q];
+            rc = sketch_one_file(s, reuse, paths[i], buf, piece, &pd, f, &outs[i]);
             reuse = true;
         }
         if (rc != FB2_OK) fail(rc);
-        if (rc == FB2_OK && s && buf && pool_release(p, s, buf)) return;   // kept for the next call
+        if (rc == FB2_OK && s && buf && pool_release(&pd, s, buf)) return;   // kept for the next call
         if (buf) cudaFreeHost(buf);
         if (s) fb2_sketcher_destroy(s);
     };
-    if (workers <= 1) work();
-    else {
-        std::vector<std::thread> th;
-        for (size_t w = 0; w < workers; ++w) th.emplace_back(work);
-        for (auto &t : th) t.join();
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g) {
+        const size_t w = has_stdin ? 1 : std::min(workers, lists[g].size());
+        for (size_t k = 0; k < w; ++k) th.emplace_back(work, g);
     }
+    if (th.size() == 1) { th[0].join(); }
+    else for (auto &t : th) t.join();
     const int rc = first_rc.load();
     if (rc != FB2_OK) {
         for (size_t i = 0; i < n; ++i) fb2_result_free(&outs[i]);
         return fb2_fail(rc, first_msg);
     }
     return FB2_OK;
+}
+
+static int device_list(const fb2_params *p, int ngpus, std::vector<int> &devices) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
+    devices.clear();
+    if (ngpus == 1 || (ngpus <= 0 && ndev == 1) || (ndev == 1 && !getenv("FB2_MULTI_OVERSUBSCRIBE"))) {   // one GPU: the one the parameters name (or the current one)
+        int d = p->device;
+        if (d < 0 && cudaGetDevice(&d) != cudaSuccess) d = 0;
+        if (d >= ndev) return fb2_fail(FB2_EINVAL, "device ordinal out of range");
+        devices.push_back(d);
+        return FB2_OK;
+    }
+    // FB2_MULTI_OVERSUBSCRIBE=1 (tests on a one-GPU box): more "GPUs" than devices wrap around onto the visible ones
+    const bool wrap = getenv("FB2_MULTI_OVERSUBSCRIBE") != nullptr;
+    const int G = ngpus <= 0 ? ndev : (wrap ? ngpus : std::min(ngpus, ndev));
+    for (int d = 0; d < G; ++d) devices.push_back(d % ndev);
+    return FB2_OK;
+}
+
+extern "C" int fb2_sketch_files(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
+                                fb2_result *outs) {
+    return fb2_sketch_files_multi(paths, n, p, f, outs, 1);
+}
+extern "C" int fb2_sketch_files_multi(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
+                                      fb2_result *outs, int ngpus) {
+    if (!p || !f || (n && (!paths || !outs))) return fb2_fail(FB2_EINVAL, "null argument");
+    std::vector<int> devices;
+    const int rc = device_list(p, ngpus, devices);
+    if (rc != FB2_OK) return rc;
+    return sketch_files_on(paths, n, p, f, outs, devices);
+}
+
+// ---- one stream, several GPUs (second mode) ----------------------------------------------------
+// sketch_stream (lib.rs:51-94) of ONE file with its bytes cut into one range per GPU: every range is parsed and
+// sketched by its own GPU (the host->device copies run on every GPU's own PCIe link), then the tables are united
+// exactly on the first GPU by kernels that read the peers' tables over NVLink (fb2_sketcher_merge_from) and the
+// usual to_vec / filter / truncate tail runs there.
+//   FASTQ: ranges start at record starts ('@' line whose third line starts with '+').  Whether a cut really is a
+//          record start is VERIFIED, not assumed: every range but the last must end with its parser back in the
+//          header phase right after a newline -- by induction from the first range all cuts are then true record
+//          starts.  If not (pathological input), the stream is sketched on one GPU instead.
+//   FASTA: ranges start at any line start; the host hands the next GPU the parser state there: whether the previous
+//          line was a header, the two previous bytes, and the last `halo` symbols (k-mers span the cut).
+static size_t find_fastq_record_start(const uint8_t *b, size_t len, size_t from) {
+    size_t p = from;
+    while (p < len) {
+        const uint8_t *nl = (const uint8_t *)memchr(b + p, '\n', len - p);
+        if (!nl) return len;
+        const size_t q = (size_t)(nl - b) + 1;
+        if (q >= len) return len;
+        if (b[q] == '@') {
+            const uint8_t *l1 = (const uint8_t *)memchr(b + q, '\n', len - q);
+            if (!l1) return len;
+            const size_t s1 = (size_t)(l1 - b) + 1;                       // would-be sequence line
+            const uint8_t *l2 = s1 < len ? (const uint8_t *)memchr(b + s1, '\n', len - s1) : nullptr;
+            if (!l2) return len;
+            const size_t s2 = (size_t)(l2 - b) + 1;                       // would-be '+' line
+            if (s2 < len && b[s2] == '+' && b[s1] != '@') return q;
+        }
+        p = q;
+    }
+    return len;
+}
+// The parser's carry at line start P (0 < P < len) of a FASTA stream.
+static void fasta_carry_at(const uint8_t *b, size_t P, uint32_t halo, uint32_t *state, uint32_t *prev2,
+                           std::vector<uint8_t> &syms) {
+    syms.assign(halo, fb2::SYM_BREAK);
+    *prev2 = P >= 2 ? b[P - 2] : (uint32_t)'\n';
+    long idx = (long)halo - 1;
+    size_t le = P - 1;                                   // position of the newline that ends the line before P
+    bool first = true;
+    while (true) {
+        const void *r = le ? memrchr(b, '\n', le) : nullptr;
+        const size_t ls = r ? (size_t)((const uint8_t *)r - b) + 1 : 0;
+        const bool hdr = b[ls] == '>';
+        if (first) { *state = hdr ? 1u : 0u; first = false; }
+        if (hdr) break;                                  // a header start is a break symbol: nothing before it matters
+        bool stop = false;
+        for (size_t i = le; i > ls && idx >= 0; --i) {
+            const uint8_t cls = fb2::classify_byte(b[i - 1]);
+            if (cls <= 3) syms[(size_t)idx--] = cls;
+            else if (cls == fb2::CLS_WS || cls == fb2::CLS_CR || cls == fb2::CLS_NL) continue;
+            else { stop = true; break; }                 // a non-base byte is a break symbol
+        }
+        if (stop || idx < 0 || ls == 0) break;
+        le = ls - 1;
+    }
+}
+
+extern "C" int fb2_sketch_stream_multi(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
+                                       const fb2_filter *f, fb2_result *out, int ngpus) {
+    if (!p || !f || !out || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
+    std::vector<int> devices;
+    int rc = device_list(p, ngpus, devices);
+    if (rc != FB2_OK) return rc;
+    size_t min_range = 8u << 20;
+    if (const char *e = getenv("FB2_MIN_RANGE_KB")) min_range = (size_t)std::max(1L, atol(e)) << 10;
+    const bool fasta = len && bytes[0] == '>', fastq = len && bytes[0] == '@';
+    size_t G = std::min(devices.size(), std::max<size_t>(1, len / min_range));
+    if (G <= 1 || !(fasta || fastq)) {                   // also: unknown / compressed formats get the usual errors
+        fb2_params pd = *p;
+        pd.device = devices[0];
+        return fb2_sketch_stream(bytes, len, name, &pd, f, out);
+    }
+    memset(out, 0, sizeof(*out));
+    // ---- cuts ----
+    std::vector<size_t> cut(1, 0);
+    for (size_t g = 1; g < G; ++g) {
+        const size_t target = len / G * g;
+        size_t q;
+        if (fastq) q = find_fastq_record_start(bytes, len, std::max(target, cut.back()));
+        else {
+            const uint8_t *nl = (const uint8_t *)memchr(bytes + target, '\n', len - target);
+            q = nl ? (size_t)(nl - bytes) + 1 : len;
+        }
+        if (q < len && q > cut.back()) cut.push_back(q);
+    }
+    G = cut.size();
+    cut.push_back(len);
+    if (G <= 1) { fb2_params pd = *p; pd.device = devices[0]; return fb2_sketch_stream(bytes, len, name, &pd, f, out); }
+    // ---- one handle and one host thread per range ----
+    std::vector<fb2_sketcher *> hs(G, nullptr);
+    std::vector<uint8_t *> bufs(G, nullptr);
+    std::vector<int> rcs(G, FB2_OK);
+    std::vector<std::string> msgs(G);
+    std::vector<uint32_t> end_state(G, 0), last_byte(G, '\n');
+    std::vector<uint64_t> bad1(G, ~0ULL), bad2(G, ~0ULL);
+    const int fmt = fasta ? FB2_FORMAT_FASTA : FB2_FORMAT_FASTQ;
+    auto work = [&](size_t g) {
+        fb2_params pd = *p;
+        pd.device = devices[g]; pd.stream = nullptr;
+        int r = FB2_OK;
+        bool pooled = pool_acquire(&pd, &hs[g], &bufs[g]);
+        if (pooled) r = fb2_sketcher_reset(hs[g]);
+        else r = fb2_sketcher_create(&pd, &hs[g]);
+        if (r == FB2_OK && p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(hs[g], p->final_size, f->filter_on);
+        if (r == FB2_OK) {
+            uint32_t state = fasta ? 1u : 0u, prev2 = '\n';
+            std::vector<uint8_t> syms;
+            if (g > 0 && fasta) fasta_carry_at(bytes, cut[g], fb2_sketcher_halo(hs[g]), &state, &prev2, syms);
+            r = fb2_sketcher_begin_range(hs[g], fmt, state, '\n', prev2, syms.empty() ? nullptr : syms.data(), cut[g],
+                                         (uint64_t)g << 44);
+        }
+        if (r == FB2_OK) r = fb2_sketcher_feed_fastx(hs[g], bytes + cut[g], cut[g + 1] - cut[g], g + 1 == G ? 1 : 0);
+        if (r == FB2_OK && g + 1 < G) r = fb2_sketcher_end_range(hs[g], &end_state[g], &last_byte[g], &bad1[g], &bad2[g]);
+        rcs[g] = r;
+        if (r != FB2_OK) msgs[g] = fb2_last_error();
+    };
+    {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; ++g) th.emplace_back(work, g);
+        for (auto &t : th) t.join();
+    }
+    auto release_all = [&](bool keep) {
+        for (size_t g = 0; g < G; ++g) {
+            if (!hs[g]) continue;
+            fb2_params pd = *p;
+            pd.device = devices[g]; pd.stream = nullptr;
+            if (keep && pool_release(&pd, hs[g], bufs[g])) continue;
+            if (bufs[g]) cudaFreeHost(bufs[g]);
+            fb2_sketcher_destroy(hs[g]);
+        }
+    };
+    // a cut that is not a record start shows as a range that does not end in the header phase: redo on one GPU
+    bool cuts_ok = true;
+    if (fastq) for (size_t g = 0; g + 1 < G; ++g) if (rcs[g] == FB2_OK && (end_state[g] != 0u || last_byte[g] != '\n')) cuts_ok = false;
+    if (!cuts_ok) {
+        release_all(false);
+        fb2_params pd = *p;
+        pd.device = devices[0];
+        return fb2_sketch_stream(bytes, len, name, &pd, f, out);
+    }
+    for (size_t g = 0; g < G && rc == FB2_OK; ++g) {     // first error in stream order
+        if (rcs[g] != FB2_OK) {
+            // a blank last range (trailing newlines longer than a range) cannot be judged alone: one GPU decides
+            if (g + 1 == G && rcs[g] == FB2_EEMPTY) { release_all(false); fb2_params pd = *p; pd.device = devices[0]; return fb2_sketch_stream(bytes, len, name, &pd, f, out); }
+            rc = fb2_fail(rcs[g], msgs[g]);
+        } else if (g + 1 < G && fastq && (bad1[g] != ~0ULL || bad2[g] != ~0ULL)) {
+            rc = fb2_fail(FB2_ERECORD, bad1[g] <= bad2[g]
+                              ? "invalid FASTQ record: line at byte " + std::to_string(bad1[g]) + " does not start with the expected '@' / '+'"
+                              : "invalid FASTQ record: sequence and quality lengths differ (record whose header ends at byte " + std::to_string(bad2[g]) + ")");
+        }
+    }
+    for (size_t g = 1; g < G && rc == FB2_OK; ++g) rc = fb2_sketcher_merge_from(hs[0], hs[g]);
+    if (rc == FB2_OK) rc = fb2_sketcher_sketch(hs[0], name, p, f, out);
+    std::string msg = rc != FB2_OK ? fb2_last_error() : "";
+    release_all(rc == FB2_OK);
+    return rc == FB2_OK ? FB2_OK : fb2_fail(rc, msg);
 }
 
 // ---- distance epilogue ---------------------------------------------------------------------------

@@ -57,6 +57,8 @@ void launch_export(const unsigned long long *keys, const uint32_t *slots, uint32
                    unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext, unsigned long long *o_kmer,
                    unsigned long long *o_posx, cudaStream_t s);
 
+void launch_merge_tables(TableView src, unsigned long long src_thr, unsigned int src_has_max, TableView dst, SketchState *st,
+                         cudaStream_t s);
 void launch_debug_bump(TableView t, unsigned long long key, unsigned long long add_cnt, unsigned long long add_ext,
                        unsigned int *found, cudaStream_t s);
 

@@ -528,6 +528,56 @@ __global__ void select_rows_kernel(const uint32_t *__restrict__ idx, uint32_t m,
     }
 }
 
+// ---- exact union of two sketch tables (one file split across GPUs) ------------------------------
+// `src` is the table of another sketcher -- on a PEER GPU: the kernels below run on the destination GPU and read the
+// source table straight out of the peer's HBM over NVLink (peer access), so the gather of the peer's entries and
+// their merge into the local table are one pass.  Every live entry of src (key <= both thresholds) is upserted:
+// totals add (64-bit), the smaller position id wins and donates the k-mer (position ids of later byte ranges are
+// larger, so "first occurrence in stream order" survives the merge).  Exact because a hash of the global bottom-s is
+// live in every local table that saw it, with complete local totals.
+__global__ void merge_count_kernel(TableView src, unsigned long long src_thr, unsigned int src_has_max, TableView dst,
+                                   SketchState *st) {
+    const uint32_t stride = gridDim.x * blockDim.x, lane = threadIdx.x & 31u;
+    const unsigned long long thr = st->threshold < src_thr ? st->threshold : src_thr;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base <= src.cap; base += stride) {
+        const uint32_t i = base + lane;
+        unsigned long long key = EMPTY_KEY;
+        bool valid = false;
+        if (i < src.cap) { key = src.key[i]; valid = key != EMPTY_KEY && key <= thr; }
+        else if (i == src.cap) valid = src_has_max != 0u && thr == EMPTY_KEY;
+        bool ins = false;
+        uint32_t d = 0;
+        if (valid) d = table_upsert(dst, key, st, ins);
+        commit_inserted(st, ins);
+        if (!valid) continue;
+        atomicAdd(&dst.cnt[d], src.cnt[i]);
+        const unsigned long long e = src.ext[i];
+        if (e) atomicAdd(&dst.ext[d], e);
+        atomicMin(&dst.posx[d], src.posx[i]);
+    }
+}
+__global__ void merge_kmer_kernel(TableView src, unsigned long long src_thr, unsigned int src_has_max, TableView dst,
+                                  const SketchState *st) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const unsigned long long thr = st->threshold < src_thr ? st->threshold : src_thr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= src.cap; i += stride) {
+        unsigned long long key = EMPTY_KEY;
+        bool valid = false;
+        if (i < src.cap) { key = src.key[i]; valid = key != EMPTY_KEY && key <= thr; }
+        else valid = src_has_max != 0u && thr == EMPTY_KEY;
+        if (!valid) continue;
+        const uint32_t d = table_find(dst, key);
+        if (d == 0xFFFFFFFFu) continue;
+        if (dst.posx[d] == src.posx[i]) copy_kmer(dst.kmer + (size_t)d * dst.kw, src.kmer + (size_t)i * src.kw, dst.kw);
+    }
+}
+void launch_merge_tables(TableView src, unsigned long long src_thr, unsigned int src_has_max, TableView dst, SketchState *st,
+                         cudaStream_t s) {
+    const uint32_t blocks = min((src.cap + 256u) / 256u, 2368u);
+    merge_count_kernel<<<blocks, 256, 0, s>>>(src, src_thr, src_has_max, dst, st);
+    merge_kmer_kernel<<<blocks, 256, 0, s>>>(src, src_thr, src_has_max, dst, st);
+}
+
 // Test hook (fb2_sketcher_debug_bump): add to the 64-bit totals of an existing key, so a test can bring a count to
 // the edge of u32 without pushing 2^32 k-mers (mash.rs:48-49 saturate; export_kernel clamps).
 __global__ void debug_bump_kernel(TableView t, unsigned long long key, unsigned long long add_cnt, unsigned long long add_ext,

@@ -160,8 +160,20 @@ int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *name, const 
 int fb2_sketch_files(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
                      fb2_result *outs);
 
-/* fb2_sketch_files keeps its idle worker handles (device buffers, pinned read buffers) for the next
- * call with the same parameters; this frees them. */
+/* ---- the same over several GPUs of this process ------------------------------------------------ */
+/* sketch_files with the files sharded over `ngpus` devices (0 = all visible; devices 0..ngpus-1): longest-first
+ * assignment by file size, a few worker handles per GPU, results in input order (the rayon fan-out of lib.rs:34-36
+ * across GPUs).  fb2_sketch_files == ngpus 1 on p->device. */
+int fb2_sketch_files_multi(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
+                           fb2_result *outs, int ngpus);
+/* sketch_stream of ONE file cut into byte ranges over `ngpus` devices: every range is parsed and sketched on its own
+ * GPU, the tables are united exactly on the first GPU over peer memory, then the usual filter / truncate tail.
+ * Bit-identical to fb2_sketch_stream (hashes, counts, extra counts, first-occurrence k-mers, totals). */
+int fb2_sketch_stream_multi(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
+                            const fb2_filter *f, fb2_result *out, int ngpus);
+
+/* The sketch_* calls keep at most FB2_POOL_MAX (default 2) idle worker handles per device (device buffers, a 32 MiB
+ * pinned read buffer) for the next call with the same parameters; this frees them. */
 void fb2_sketch_files_release_pool(void);
 
 /* ---- raw_distance (distance.rs:66-126), integer part, batched ----------------------------- */

@@ -524,6 +524,108 @@ def test_fastq_seq_qual_length_mismatch(fb, oracle, monkeypatch, st_tiles, crlf)
         assert np.array_equal(sk.hashes_u64, osk["hashes"]) and sk.seq_length == osk["seq_length"]
 
 
+def test_fastq_end_of_input_corner_cases(fb, oracle):
+    """What the reader accepts / rejects at the end of a FASTQ stream, against the oracle's verdict: empty last
+    quality line, CR-only lines, unterminated lines, trailing blank lines."""
+    sp = fb.SketchParams.mash(50, 50, True, 3, 0)
+    osp = oracle.mash_params(50, 50, True, 3, 0)
+    body = b"@a\nACGTAC\n+\nIIIIII\n"
+    cases = [b"@r\n\n+\n", b"@r\n\n+\n\n", b"@r\n\n+\n\n\n\r\n", body + b"@r\n\n+\n\n", body + b"@r\n\n+\n",
+             b"@r\nA\n+\n", b"@r\nA\n+\n\n", b"@r\nA\n+\n\r\r\n", b"@r\nA\n+\n\r\r", b"@r\nA\n+\n\r\n", b"@r\nAC\n+\n\r\r\n",
+             b"@r\n\r\n+\r\n\r\n", b"@r\r\n\r\n+\r\n", body + b"@r\nACG\n+\nII", body + b"@r\nACG\n+\nIII", body + b"@r\nACG\n+\nIII\r",
+             body + b"@r\nACG\n+\nIIII\r", body + b"@r\nACG\n+", body + b"@r\nACG\n+\r", body + b"@r\nACG\n", body + b"\n\n\n",
+             body + b"@r\nACG\r\n+\r\nIII", body + b"@r\nACG\r\n+\r\nIIII"]
+    for data in cases:
+        rc, osk = oracle.sketch_stream(data, osp, oracle.make_filter(False))
+        if rc == oracle.OK:
+            sk = fb.sketch_stream(data, "x", sp, fb.FilterParams(False))
+            assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"]), data
+            assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"]), data
+        else:
+            assert rc == oracle.E_RECORD, data
+            with pytest.raises(fb.FinchError) as e:
+                fb.sketch_stream(data, "x", sp, fb.FilterParams(False))
+            assert e.value.code == fb.ERECORD, (data, e.value.message)
+
+
+@pytest.mark.parametrize("fmt,kind,size,k,scale", [("fastq", "mash", 20000, 21, 0.0), ("fasta", "mash", 1000, 21, 0.0),
+                                                   ("fasta", "scaled", 100, 31, 0.01), ("fasta", "mash", 500, 64, 0.0),
+                                                   ("fastq_crlf", "scaled", 0, 21, 0.02)])
+def test_one_stream_split_over_gpus(fb, synth, oracle, monkeypatch, fmt, kind, size, k, scale):
+    """fb2_sketch_stream_multi: one file cut into byte ranges, one range per GPU, tables united exactly over peer
+    memory (SURVEY 8e second mode).  On a one-GPU box the ranges share the device (FB2_MULTI_OVERSUBSCRIBE): the
+    cuts, the carried parser state / halo symbols, the position-id bases and the merge are the same code."""
+    monkeypatch.setenv("FB2_MULTI_OVERSUBSCRIBE", "1")
+    monkeypatch.setenv("FB2_MIN_RANGE_KB", "64")
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    rng = np.random.default_rng(len(fmt) + size + k)
+    if fmt == "fasta":
+        data = gen.fasta(rng, n_records=4, min_len=100_000, max_len=400_000, width=61, messy=0.004, crlf=bool(size % 2 == 0 and k == 31))
+        data += synth.synth_fasta(700_000, n_records=2, line_width=80, lower_frac=0.05, n_frac=0.01, seed=9).tobytes()
+    else:
+        genome = synth.synth_genome(30_000, 4)
+        data = synth.synth_fastq(genome, 8_000, 150, 0.01, 11)[0].tobytes()
+        if fmt == "fastq_crlf":
+            data = data.replace(b"\n", b"\r\n")
+        data += gen.fastq(rng, n_records=300, max_len=300, messy=0.01, crlf=fmt == "fastq_crlf", final_newline=False)
+    sp = fb.SketchParams.mash(size, min(size, 1000), True, k, 0) if kind == "mash" else fb.SketchParams.scaled(size, k, scale, 0)
+    osp = oracle.mash_params(size, min(size, 1000), True, k, 0) if kind == "mash" else oracle.scaled_params(size, k, scale, 0)
+    for filt in ((True, 0.21, 0.1), (None, 0.21, 0.1)):
+        fp = fb.FilterParams(filt[0], (None, None), filt[1], filt[2])
+        rc, osk = oracle.sketch_stream(data, osp, oracle.make_filter(filt[0], (None, None), filt[1], filt[2]))
+        assert rc == oracle.OK
+        for ngpus in (2, 3, 5):
+            sk = fb.sketch_stream_multi(data, "split", sp, fp, ngpus)
+            assert np.array_equal(sk.hashes_u64, osk["hashes"]), (ngpus, filt)
+            assert np.array_equal(sk.counts, osk["counts"]) and np.array_equal(sk.extra_counts, osk["extras"])
+            assert [sk.kmer_bytes(i) for i in range(len(sk))] == osk["kmers"]
+            assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+
+
+def test_split_stream_reports_record_errors(fb, oracle, monkeypatch):
+    monkeypatch.setenv("FB2_MULTI_OVERSUBSCRIBE", "1")
+    monkeypatch.setenv("FB2_MIN_RANGE_KB", "64")
+    rng = np.random.default_rng(4)
+    recs, nl = _fastq_records(rng, 3000, False)
+    sp = fb.SketchParams.mash(500, 500, True, 21, 0)
+    for i in (5, 1500, 2995):
+        bad = [list(r) for r in recs]
+        bad[i][3] = bad[i][3] + b"I"
+        with pytest.raises(fb.FinchError) as e:
+            fb.sketch_stream_multi(_join(bad, nl), "bad", sp, fb.FilterParams(False), 4)
+        assert e.value.code == fb.ERECORD
+    # a quality line that looks like a header ('@' first) right where a cut would go must not fool the split
+    tricky = [list(r) for r in recs]
+    for r in tricky:
+        if len(r[3]) > 2:
+            r[3] = b"@" + r[3][1:]
+    data = _join(tricky, nl)
+    rc, osk = oracle.sketch_stream(data, oracle.mash_params(500, 500, True, 21, 0), oracle.make_filter(False))
+    sk = fb.sketch_stream_multi(data, "tricky", sp, fb.FilterParams(False), 4)
+    assert rc == oracle.OK and np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+
+
+def test_sketch_files_multi_gpu_assignment(fb, oracle, tmp_path, monkeypatch):
+    """fb2_sketch_files_multi: LPT over the devices, results in input order."""
+    monkeypatch.setenv("FB2_MULTI_OVERSUBSCRIBE", "1")
+    rng = np.random.default_rng(8)
+    paths, datas = [], []
+    for i in range(11):
+        d = gen.fasta(rng, n_records=2, max_len=int(rng.integers(500, 30000)), width=80) if i % 3 else gen.fastq(rng, n_records=int(rng.integers(5, 200)))
+        p = tmp_path / f"m{i}.fx"
+        p.write_bytes(d)
+        paths.append(str(p)); datas.append(d)
+    sp = fb.SketchParams.mash(300, 30, True, 21, 0)
+    fp = fb.FilterParams(None, (None, None), 0.21, 0.1)
+    for ngpus in (1, 3):
+        sks = fb.sketch_files(paths, sp, fp, ngpus=ngpus)
+        for p, d, sk in zip(paths, datas, sks):
+            rc, osk = oracle.sketch_stream(d, oracle.mash_params(300, 30, True, 21, 0), oracle.make_filter(None, (None, None), 0.21, 0.1))
+            assert rc == oracle.OK and sk.name == p
+            assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+            assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+
+
 def test_sketch_files(fb, oracle, tmp_path):
     rng = np.random.default_rng(21)
     paths, datas = [], []
