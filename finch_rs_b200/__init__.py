@@ -76,7 +76,7 @@ EXPORTS = [
     "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_sketcher_debug_bump", "fb2_filter_counts", "fb2_process_post_filter",
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_multi", "fb2_sketch_stream_multi",
     "fb2_sketch_files_release_pool", "fb2_dist_batch",
-    "fb2_dist_all_pairs", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_old_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
+    "fb2_dist_all_pairs", "fb2_dist_all_pairs_cut", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_old_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
 ]
 
 _lib = None
@@ -120,6 +120,8 @@ def lib():
     L.fb2_sketch_stream_multi.argtypes = [vp, sz, C.c_char_p, C.POINTER(_Params), C.POINTER(_Filter), C.POINTER(_Result), C.c_int]
     L.fb2_dist_batch.argtypes = [vp, vp, sz, sz, C.c_double, vp, vp, sz, vp, C.c_int32]
     L.fb2_dist_all_pairs.argtypes = [vp, vp, sz, sz, C.c_double, sz, sz, vp, C.c_int32]
+    L.fb2_dist_all_pairs_cut.argtypes = [vp, vp, sz, sz, C.c_double, sz, sz, C.c_uint8, C.c_double, C.c_int, vp, sz,
+                                         C.POINTER(C.c_uint64), C.c_int32, C.c_int]
     L.fb2_distance_finish.argtypes = [C.POINTER(_PairOut), C.c_uint8, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.fb2_distance_finish.restype = None
@@ -529,6 +531,41 @@ def dist_all_pairs(mat, lens, scale=0.0, q0=0, q1=None, device=-1, out=None):
     _check(lib().fb2_dist_all_pairs(mat.ctypes.data, lens.ctypes.data, n, stride, scale, q0, q1,
                                     out.ctypes.data, device))
     return out.reshape(q1 - q0, n, 3)
+
+
+HIT_DTYPE = np.dtype([("q", np.uint32), ("r", np.uint32), ("common", np.uint32), ("i", np.uint32), ("j", np.uint32)])
+
+
+def dist_all_pairs_cut(mat, lens, kmer_length, max_distance, scale=0.0, q0=0, q1=None, skip_self=True, device=-1, ngpus=1,
+                       cap=1 << 20):
+    """calc_sketch_distances with the max_distance cut (cli/src/main.rs:315-334): all ordered pairs (q in [q0, q1),
+    r) whose mash distance can be <= max_distance, ascending by (q, r), as a structured array (q, r, common, i, j).
+    The device cut is conservative; finish with distance_of_hits() and apply `mash_distance <= max_distance`."""
+    mat = np.ascontiguousarray(mat, np.uint64)
+    lens = np.ascontiguousarray(lens, np.uint32)
+    n, stride = mat.shape
+    q1 = n if q1 is None else q1
+    while True:
+        hits = np.zeros(max(1, cap), HIT_DTYPE)
+        nh = C.c_uint64()
+        rc = lib().fb2_dist_all_pairs_cut(mat.ctypes.data, lens.ctypes.data, n, stride, scale, q0, q1, kmer_length, max_distance,
+                                          int(bool(skip_self)), hits.ctypes.data, hits.size, C.byref(nh), device, ngpus)
+        if rc == ENOMEM and nh.value > hits.size:
+            cap = int(nh.value)
+            continue
+        _check(rc)
+        return hits[:nh.value]
+
+
+def distance_of_hits(hits, kmer_length):
+    """(containment, jaccard, mash_distance, common, total) arrays for a hit list, exactly as fb2_distance_finish
+    (distance.rs:117-125, :35-41) computes them one pair at a time."""
+    n = len(hits)
+    cont, jac, md = np.zeros(n), np.zeros(n), np.zeros(n)
+    com, tot = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    for t in range(n):
+        cont[t], jac[t], md[t], com[t], tot[t] = _finish_pair((hits["common"][t], hits["i"][t], hits["j"][t]), kmer_length)
+    return cont, jac, md, com, tot
 
 
 def _finish_pair(row, k):

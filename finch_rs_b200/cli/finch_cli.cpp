@@ -21,6 +21,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/finch_b200.h"
@@ -369,36 +370,87 @@ void output_to(const std::string &payload, const char *output, const std::string
     out.write(payload.data(), (std::streamsize)payload.size());
 }
 
-// distance() for every (query, reference) pair that calc_sketch_distances keeps (main.rs:315-334,
-// distance.rs:9-47): the integer part of raw_distance runs as ONE batched GPU call per distinct scale.
+// distance() for every (query, reference) pair that calc_sketch_distances keeps (main.rs:315-334, distance.rs:9-47).
+// Queries are always elements of `refs` (main.rs:92-113 picks them out of the parsed sketches), so every sketch is
+// one row of the hash matrix.  Usual case (one scale for every pair, contiguous query rows: --pairwise, the default
+// first-sketch query): the tiled all-pairs kernel with the max_distance cut applied on the device
+// (fb2_dist_all_pairs_cut); the host finishes the f64 fields of the survivors and applies main.rs:328 exactly.
+// Mixed scales, scattered --queries and --old-dist take the pair-list kernel (fb2_dist_batch).
 std::vector<SketchDistance> calc_sketch_distances(const std::vector<const Sketch *> &queries, const std::vector<Sketch> &refs, bool old_mode, double max_dist) {
+    std::vector<SketchDistance> out;
+    if (queries.empty() || refs.empty()) return out;
+    std::unordered_map<const Sketch *, uint32_t> row_of;
+    for (size_t r = 0; r < refs.size(); ++r) row_of.emplace(&refs[r], (uint32_t)r);
+    std::vector<uint32_t> qrow(queries.size());
+    for (size_t i = 0; i < queries.size(); ++i) {
+        auto it = row_of.find(queries[i]);
+        if (it == row_of.end()) bail("internal: query sketch is not one of the parsed sketches");
+        qrow[i] = it->second;
+    }
+    size_t stride = 1;
+    for (auto &s : refs) stride = std::max(stride, s.hashes.size());
+    std::vector<uint64_t> mat(refs.size() * stride, 0);
+    std::vector<uint32_t> lens(refs.size());
+    for (size_t i = 0; i < refs.size(); ++i) {
+        lens[i] = (uint32_t)refs[i].hashes.size();
+        std::copy(refs[i].hashes.begin(), refs[i].hashes.end(), mat.begin() + (long)(i * stride));
+    }
+    auto pair_scale = [&](const Sketch &q, const Sketch &r) -> double {   // distance.rs:23-28 (old mode: no scale)
+        if (!old_mode && q.sketch_params.has_scale() && r.sketch_params.has_scale()) return std::min(q.sketch_params.scale, r.sketch_params.scale);
+        return 0.0;
+    };
+    auto emit = [&](const Sketch &q, const Sketch &r, const fb2_pair_out &po) {
+        SketchDistance d;
+        if (old_mode) {                                                   // old_distance (distance.rs:136-157)
+            if (fb2_old_distance_finish(po.common, q.hashes.size(), r.hashes.size(), q.sketch_params.kmer_length,
+                                        &d.containment, &d.jaccard, &d.mash_distance, &d.common_hashes, &d.total_hashes) != FB2_OK)
+                bail(fb2_last_error());
+        } else
+            fb2_distance_finish(&po, q.sketch_params.kmer_length, &d.containment, &d.jaccard, &d.mash_distance, &d.common_hashes, &d.total_hashes);
+        if (!(d.mash_distance <= max_dist)) return;                       // main.rs:328
+        d.query = q.name; d.reference = r.name;
+        out.push_back(std::move(d));
+    };
+    // ---- fast path ----
+    bool uniform = !old_mode, contiguous = true;
+    const bool sc0 = refs[0].sketch_params.has_scale();
+    for (auto &s : refs)
+        if (s.sketch_params.has_scale() != sc0 || (sc0 && s.sketch_params.scale != refs[0].sketch_params.scale) ||
+            s.sketch_params.kmer_length != refs[0].sketch_params.kmer_length) { uniform = false; break; }
+    for (size_t i = 1; i < qrow.size(); ++i) if (qrow[i] != qrow[i - 1] + 1) contiguous = false;
+    if (uniform && contiguous && !getenv("FINCH_DIST_PAIR_LIST")) {
+        const double scale = sc0 ? refs[0].sketch_params.scale : 0.0;
+        const size_t q0 = qrow.front(), q1 = (size_t)qrow.back() + 1;
+        std::vector<fb2_pair_hit> hits((size_t)1 << 16);
+        uint64_t n_hits = 0;
+        int rc;
+        while ((rc = fb2_dist_all_pairs_cut(mat.data(), lens.data(), refs.size(), stride, scale, q0, q1, refs[0].sketch_params.kmer_length,
+                                            max_dist, 1, hits.data(), hits.size(), &n_hits, -1, 0)) == FB2_ENOMEM && n_hits > hits.size())
+            hits.resize((size_t)n_hits);
+        if (rc != FB2_OK) bail(fb2_last_error());
+        hits.resize((size_t)n_hits);
+        // reference-major, query-minor (main.rs:321-323): stable counting sort of the (q, r)-ordered hits by r
+        std::vector<uint64_t> start(refs.size() + 1, 0);
+        for (auto &h : hits) start[h.r + 1]++;
+        for (size_t r = 0; r < refs.size(); ++r) start[r + 1] += start[r];
+        std::vector<fb2_pair_hit> by_ref(hits.size());
+        for (auto &h : hits) by_ref[start[h.r]++] = h;
+        for (auto &h : by_ref) {
+            const Sketch &q = refs[h.q], &r = refs[h.r];
+            if (q == r) continue;                                         // main.rs:324: equal BY VALUE (Q12); q == r by index never comes back
+            emit(q, r, fb2_pair_out{h.common, h.i, h.j});
+        }
+        return out;
+    }
+    // ---- pair list ----
     struct Pair { uint32_t q, r; double scale; };
     std::vector<Pair> pairs;
-    // one row per distinct sketch object: references first, then queries that are not references
-    std::vector<const Sketch *> rows;
-    for (auto &r : refs) rows.push_back(&r);
-    auto row_of = [&](const Sketch *s) -> uint32_t {
-        for (size_t i = 0; i < rows.size(); ++i) if (rows[i] == s) return (uint32_t)i;
-        rows.push_back(s);
-        return (uint32_t)(rows.size() - 1);
-    };
     for (size_t r = 0; r < refs.size(); ++r)
-        for (const Sketch *q : queries) {
-            if (*q == refs[r]) continue;                                  // main.rs:324: equal BY VALUE (Q12)
-            double min_scale = 0.0;                                       // distance.rs:23-28 (old mode: no scale)
-            if (!old_mode && q->sketch_params.has_scale() && refs[r].sketch_params.has_scale()) min_scale = std::min(q->sketch_params.scale, refs[r].sketch_params.scale);
-            pairs.push_back({row_of(q), (uint32_t)r, min_scale});
+        for (size_t i = 0; i < queries.size(); ++i) {
+            if (qrow[i] == r || *queries[i] == refs[r]) continue;         // main.rs:324: equal BY VALUE (Q12)
+            pairs.push_back({qrow[i], (uint32_t)r, pair_scale(*queries[i], refs[r])});
         }
-    std::vector<SketchDistance> out;
     if (pairs.empty()) return out;
-    size_t stride = 1;
-    for (auto *s : rows) stride = std::max(stride, s->hashes.size());
-    std::vector<uint64_t> mat(rows.size() * stride, 0);
-    std::vector<uint32_t> lens(rows.size());
-    for (size_t i = 0; i < rows.size(); ++i) {
-        lens[i] = (uint32_t)rows[i]->hashes.size();
-        std::copy(rows[i]->hashes.begin(), rows[i]->hashes.end(), mat.begin() + (long)(i * stride));
-    }
     std::vector<fb2_pair_out> po(pairs.size());
     std::set<double> scales;
     for (auto &p : pairs) scales.insert(p.scale);
@@ -406,22 +458,11 @@ std::vector<SketchDistance> calc_sketch_distances(const std::vector<const Sketch
         std::vector<uint32_t> qi, ri, where;
         for (size_t i = 0; i < pairs.size(); ++i) if (pairs[i].scale == sc) { qi.push_back(pairs[i].q); ri.push_back(pairs[i].r); where.push_back((uint32_t)i); }
         std::vector<fb2_pair_out> tmp(qi.size());
-        if (fb2_dist_batch(mat.data(), lens.data(), rows.size(), stride, sc, qi.data(), ri.data(), qi.size(), tmp.data(), -1) != FB2_OK)
+        if (fb2_dist_batch(mat.data(), lens.data(), refs.size(), stride, sc, qi.data(), ri.data(), qi.size(), tmp.data(), -1) != FB2_OK)
             bail(fb2_last_error());
         for (size_t i = 0; i < where.size(); ++i) po[where[i]] = tmp[i];
     }
-    for (size_t i = 0; i < pairs.size(); ++i) {
-        const Sketch *q = rows[pairs[i].q];
-        SketchDistance d;
-        if (old_mode) {                                                   // old_distance (distance.rs:136-157)
-            if (fb2_old_distance_finish(po[i].common, q->hashes.size(), refs[pairs[i].r].hashes.size(), q->sketch_params.kmer_length,
-                                        &d.containment, &d.jaccard, &d.mash_distance, &d.common_hashes, &d.total_hashes) != FB2_OK)
-                bail(fb2_last_error());
-        } else
-        fb2_distance_finish(&po[i], q->sketch_params.kmer_length, &d.containment, &d.jaccard, &d.mash_distance, &d.common_hashes, &d.total_hashes);
-        d.query = q->name; d.reference = refs[pairs[i].r].name;
-        if (d.mash_distance <= max_dist) out.push_back(std::move(d));
-    }
+    for (size_t i = 0; i < pairs.size(); ++i) emit(refs[pairs[i].q], refs[pairs[i].r], po[i]);
     return out;
 }
 

@@ -101,10 +101,23 @@ __device__ __forceinline__ uint32_t lower_bound_sm(const unsigned long long *a, 
     return lo;
 }
 
+// CUT mode (`finch dist --max-dist`, cli/src/main.rs:326-330 keeps a pair iff mash_distance <= max_dist): instead of
+// the dense (q, r) matrix the kernel appends only the pairs whose jaccard reaches `jlow` -- a bound placed slightly
+// BELOW the exact one, so no pair the host's exact f64 test would keep is lost; the host re-checks every hit -- to a
+// compact list with one atomic per warp.  10^10 pairs cannot be returned densely; their hits can.
+struct DistCut {
+    fb2_pair_hit *hits;            // compacted survivors (unordered)
+    unsigned long long *keys;      // (q << 32) | r per hit, for the sort that follows
+    unsigned int *counter;         // hits appended so far (may run past cap: the host then retries with fewer rows)
+    uint32_t cap;
+    int skip_self;                 // drop q == r
+    double jlow;                   // keep iff jaccard >= jlow (negative: keep all)
+};
+template <bool CUT>
 __global__ void __launch_bounds__(DT_WARPS * 32, 1)
 dist_tile_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *__restrict__ lens, uint32_t stride,
                  uint32_t n_sk, uint32_t q0, uint32_t q1, uint32_t r_chunk, int scaled, unsigned long long max_hash,
-                 fb2_pair_out *__restrict__ out) {
+                 fb2_pair_out *__restrict__ out, DistCut cut) {
     extern __shared__ __align__(16) unsigned char dt_raw[];
     DistTileSmem &S = *reinterpret_cast<DistTileSmem *>(dt_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -183,6 +196,8 @@ dist_tile_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *
             const uint32_t c = __reduce_add_sync(0xffffffffu, cnt[q]);
             if (lane == (uint32_t)q) mine = c;
         }
+        bool pass = false;
+        fb2_pair_out o; o.common = 0; o.i = 0; o.j = 0;
         if (lane < nq) {
             const uint32_t q = lane, na = S.na[q];
             uint32_t i = 0, j = 0;
@@ -192,8 +207,29 @@ dist_tile_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *
                 else { j = nb; i = lower_bound_sm(S.keys[q], na, mb + 1ULL); }
             } else mine = 0;
             if (scaled) { i = max(i, S.lb[q]); j = max(j, lower_bound_u64(B, nb, max_hash)); }
-            fb2_pair_out o; o.common = mine; o.i = i; o.j = j;
-            out[(uint64_t)(qb + q - q0) * n_sk + r] = o;
+            o.common = mine; o.i = i; o.j = j;
+            if (!CUT) out[(uint64_t)(qb + q - q0) * n_sk + r] = o;
+            else {
+                const uint32_t total = i - mine + j;
+                const double jac = total == 0u ? 1.0 : (double)mine / (double)total;      // distance.rs:119-125
+                pass = !(cut.skip_self && qb + q == r) && (cut.jlow < 0.0 || jac >= cut.jlow);
+            }
+        }
+        if (CUT) {
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                uint32_t base = 0;
+                if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(cut.counter, (unsigned int)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (pass) {
+                    const uint32_t idx = base + __popc(m & ((1u << lane) - 1u));
+                    if (idx < cut.cap) {
+                        fb2_pair_hit h; h.q = qb + lane; h.r = r; h.common = o.common; h.i = o.i; h.j = o.j;
+                        cut.hits[idx] = h;
+                        cut.keys[idx] = ((unsigned long long)(qb + lane) << 32) | r;
+                    }
+                }
+            }
         }
     }
 }
@@ -215,14 +251,16 @@ void launch_dist_all(const unsigned long long *hashes, const uint32_t *lens, uin
 
 uint32_t dist_tile_max_len() { return DT_MAXLEN; }
 // All ordered pairs (q, r), q in [q0, q1), r in [0, n_sk); every query sketch must be <= dist_tile_max_len() long.
-int launch_dist_tile(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
-                     uint32_t q1, int scaled, unsigned long long max_hash, fb2_pair_out *out, cudaStream_t s) {
+static int dist_tile_launch(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
+                            uint32_t q1, int scaled, unsigned long long max_hash, fb2_pair_out *out, const DistCut *cut,
+                            cudaStream_t s) {
     if (q1 <= q0 || !n_sk) return 0;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        if (cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DistTileSmem)) != cudaSuccess)
+        if (cudaFuncSetAttribute(dist_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DistTileSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(dist_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DistTileSmem)) != cudaSuccess)
             return -1;
         attr_set[dev] = true;
     }
@@ -235,9 +273,36 @@ int launch_dist_tile(const unsigned long long *hashes, const uint32_t *lens, uin
     splits = std::min<uint32_t>(splits, 65535u);
     const uint32_t r_chunk = (n_sk + splits - 1) / splits;
     const dim3 grid(q_tiles, (n_sk + r_chunk - 1) / r_chunk);
-    dist_tile_kernel<<<grid, DT_WARPS * 32, sizeof(DistTileSmem), s>>>(hashes, lens, stride, n_sk, q0, q1, r_chunk, scaled,
-                                                                    max_hash, out);
+    if (cut) dist_tile_kernel<true><<<grid, DT_WARPS * 32, sizeof(DistTileSmem), s>>>(hashes, lens, stride, n_sk, q0, q1, r_chunk, scaled,
+                                                                                   max_hash, nullptr, *cut);
+    else dist_tile_kernel<false><<<grid, DT_WARPS * 32, sizeof(DistTileSmem), s>>>(hashes, lens, stride, n_sk, q0, q1, r_chunk, scaled,
+                                                                                max_hash, out, DistCut{});
     return 0;
+}
+int launch_dist_tile(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
+                     uint32_t q1, int scaled, unsigned long long max_hash, fb2_pair_out *out, cudaStream_t s) {
+    return dist_tile_launch(hashes, lens, stride, n_sk, q0, q1, scaled, max_hash, out, nullptr, s);
+}
+// CUT mode: survivors of rows [q0, q1) appended to hits / keys (see DistCut).
+int launch_dist_tile_cut(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
+                         uint32_t q1, int scaled, unsigned long long max_hash, fb2_pair_hit *hits, unsigned long long *keys,
+                         unsigned int *counter, uint32_t cap, int skip_self, double jlow, cudaStream_t s) {
+    DistCut c; c.hits = hits; c.keys = keys; c.counter = counter; c.cap = cap; c.skip_self = skip_self; c.jlow = jlow;
+    return dist_tile_launch(hashes, lens, stride, n_sk, q0, q1, scaled, max_hash, nullptr, &c, s);
+}
+// hits[order[i]] -> sorted[i]
+__global__ void gather_hits_kernel(const fb2_pair_hit *__restrict__ hits, const uint32_t *__restrict__ order, uint32_t n,
+                                   fb2_pair_hit *__restrict__ sorted) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sorted[i] = hits[order[i]];
+}
+__global__ void iota_kernel(uint32_t *v, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+void launch_iota(uint32_t *v, uint32_t n, cudaStream_t s) { if (n) iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(v, n); }
+void launch_gather_hits(const fb2_pair_hit *hits, const uint32_t *order, uint32_t n, fb2_pair_hit *sorted, cudaStream_t s) {
+    if (n) gather_hits_kernel<<<(n + 255) / 256, 256, 0, s>>>(hits, order, n, sorted);
 }
 
 }  // namespace fb2

@@ -8,9 +8,12 @@
 //   total_kmers        ->  host counter fed by the hash kernel's per-launch count
 //   total_bases        ->  ParseCarry::total_bases (FASTX) + host sum (process())
 #include <algorithm>
+#include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1674,6 +1677,210 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
     if (st_c) cudaStreamDestroy(st_c);
     d_h.release(); d_l.release();
     return rc;
+}
+
+// ---- dist with the max_distance cut ---------------------------------------------------------------------------
+// jaccard bound for mash_distance <= d (distance.rs:36-41): -ln(2j / (1 + j)) / k <= d  <=>  j >= x / (2 - x) with
+// x = exp(-d k); placed a hair BELOW the exact value so that rounding can only let extra pairs through (the caller
+// applies the exact test).  d >= 1 keeps everything (the distance is clamped to 1).
+static double dist_cut_jlow(double max_distance, uint8_t k) {
+    if (!(max_distance < 1.0)) return -1.0;
+    if (max_distance < 0.0) return 2.0;                       // nothing can pass (distances are >= 0)
+    const double x = std::exp(-max_distance * (double)k);
+    const double j = x / (2.0 - x);
+    return j * (1.0 - 1e-9) - 1e-12;
+}
+static bool host_passes_cut(const fb2_pair_out &o, double jlow) {
+    const uint32_t total = o.i - o.common + o.j;
+    const double jac = total == 0u ? 1.0 : (double)o.common / (double)total;
+    return jlow < 0.0 || jac >= jlow;
+}
+// Rows [qa, qb) against all n_sk sketches on the current device; d_h / d_l hold the matrix.  Hits ascending by (q, r).
+static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, const uint32_t *lens, size_t n_sk, size_t stride,
+                         int scaled, unsigned long long max_hash, size_t qa, size_t qb, int skip_self, double jlow,
+                         std::vector<fb2_pair_hit> &out, double *kernel_ms) {
+    if (qb <= qa || !n_sk) return FB2_OK;
+    uint32_t max_qlen = 0;
+    for (size_t q = qa; q < qb; ++q) max_qlen = std::max(max_qlen, lens[q]);
+    const bool tiled = max_qlen <= dist_tile_max_len() && !getenv("FB2_DIST_NO_TILE");
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t rows = env_size("FB2_DIST_ROWS", (size_t)sms * 9 * 2);    // query rows per launch: two 9-row tiles per SM
+    uint32_t cap = (uint32_t)env_size("FB2_DIST_HITS_M", 8) << 20;      // hit capacity per launch
+    if (!tiled) rows = std::max<size_t>(1, (1u << 22) / n_sk);          // dense fallback: small slabs
+    cudaStream_t st = nullptr;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DevBuf hits, sorted, keys, tkeys, vals, tvals, hist, counter, dense;
+    fb2_pair_hit *h_pin = nullptr;
+    unsigned int *h_cnt = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = FB2_OK;
+    auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == FB2_OK) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e)); };
+    cu(cudaEventCreate(&e0)); cu(cudaEventCreate(&e1));
+    cu(cudaHostAlloc((void **)&h_cnt, sizeof(unsigned int), cudaHostAllocDefault));
+    if (rc == FB2_OK) rc = counter.ensure(sizeof(unsigned int));
+    size_t pin_cap = 0;
+    double kms = 0.0;
+    std::vector<fb2_pair_out> h_dense;
+    for (size_t q = qa; q < qb && rc == FB2_OK;) {
+        const size_t m = std::min(rows, qb - q);
+        if (tiled) {
+            if ((rc = hits.ensure((size_t)cap * sizeof(fb2_pair_hit))) != FB2_OK) break;
+            if ((rc = sorted.ensure((size_t)cap * sizeof(fb2_pair_hit))) != FB2_OK) break;
+            if ((rc = keys.ensure((size_t)cap * 8 + 512)) != FB2_OK || (rc = tkeys.ensure((size_t)cap * 8 + 512)) != FB2_OK) break;
+            if ((rc = vals.ensure((size_t)cap * 4 + 256)) != FB2_OK || (rc = tvals.ensure((size_t)cap * 4 + 256)) != FB2_OK) break;
+            if ((rc = hist.ensure((size_t)radix_hist_words(cap) * 4)) != FB2_OK) break;
+            cu(cudaMemsetAsync(counter.p, 0, sizeof(unsigned int), st));
+            cu(cudaEventRecord(e0, st));
+            if (launch_dist_tile_cut(d_h, d_l, (uint32_t)stride, (uint32_t)n_sk, (uint32_t)q, (uint32_t)(q + m), scaled, max_hash,
+                                     hits.as<fb2_pair_hit>(), keys.as<unsigned long long>(), counter.as<unsigned int>(), cap, skip_self,
+                                     jlow, st) != 0) { rc = fb2_fail(FB2_ECUDA, "dist_tile_kernel: could not reserve shared memory"); break; }
+            cu(cudaEventRecord(e1, st));
+            cu(cudaMemcpyAsync(h_cnt, counter.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            cu(cudaStreamSynchronize(st));
+            if (rc != FB2_OK) break;
+            const unsigned int n = *h_cnt;
+            if (n > cap) {                       // more survivors than the buffer holds: fewer rows, then a larger buffer
+                if (m > 9) { rows = std::max<size_t>(9, (m / 2 + 8) / 9 * 9); continue; }
+                if (cap >= (1u << 30)) { rc = fb2_fail(FB2_ENOMEM, "dist: too many surviving pairs for one query tile"); break; }
+                cap <<= 1;
+                continue;
+            }
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) kms += ms;
+            if (n) {
+                launch_iota(vals.as<uint32_t>(), n, st);
+                launch_radix_sort(keys.as<unsigned long long>(), vals.as<uint32_t>(), tkeys.as<unsigned long long>(), tvals.as<uint32_t>(),
+                                  n, hist.as<uint32_t>(), st);
+                launch_gather_hits(hits.as<fb2_pair_hit>(), vals.as<uint32_t>(), n, sorted.as<fb2_pair_hit>(), st);
+                if ((size_t)n > pin_cap) {
+                    if (h_pin) cudaFreeHost(h_pin);
+                    h_pin = nullptr;
+                    pin_cap = (size_t)n + n / 4 + 4096;
+                    cu(cudaHostAlloc((void **)&h_pin, pin_cap * sizeof(fb2_pair_hit), cudaHostAllocDefault));
+                }
+                if (rc != FB2_OK) break;
+                cu(cudaMemcpyAsync(h_pin, sorted.p, (size_t)n * sizeof(fb2_pair_hit), cudaMemcpyDeviceToHost, st));
+                cu(cudaStreamSynchronize(st));
+                if (rc != FB2_OK) break;
+                out.insert(out.end(), h_pin, h_pin + n);
+            }
+        } else {                                 // sketches longer than the tile kernel takes: dense slab, cut on the host
+            const uint64_t np = (uint64_t)m * n_sk;
+            if ((rc = dense.ensure(np * sizeof(fb2_pair_out))) != FB2_OK) break;
+            h_dense.resize(np);
+            cu(cudaEventRecord(e0, st));
+            launch_dist_all(d_h, d_l, (uint32_t)stride, (uint32_t)n_sk, (uint32_t)q, np, scaled, max_hash, dense.as<fb2_pair_out>(), st);
+            cu(cudaEventRecord(e1, st));
+            cu(cudaMemcpyAsync(h_dense.data(), dense.p, np * sizeof(fb2_pair_out), cudaMemcpyDeviceToHost, st));
+            cu(cudaStreamSynchronize(st));
+            if (rc != FB2_OK) break;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) kms += ms;
+            for (size_t a = 0; a < m; ++a)
+                for (size_t r = 0; r < n_sk; ++r) {
+                    const fb2_pair_out &o = h_dense[a * n_sk + r];
+                    if ((skip_self && q + a == r) || !host_passes_cut(o, jlow)) continue;
+                    out.push_back(fb2_pair_hit{(uint32_t)(q + a), (uint32_t)r, o.common, o.i, o.j});
+                }
+        }
+        q += m;
+    }
+    if (kernel_ms) *kernel_ms = kms;
+    if (h_pin) cudaFreeHost(h_pin);
+    if (h_cnt) cudaFreeHost(h_cnt);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    hits.release(); sorted.release(); keys.release(); tkeys.release(); vals.release(); tvals.release(); hist.release();
+    counter.release(); dense.release();
+    return rc;
+}
+
+extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride, double scale,
+                                      size_t q0, size_t q1, uint8_t kmer_length, double max_distance, int skip_self,
+                                      fb2_pair_hit *hits, size_t cap, uint64_t *n_hits, int32_t device, int ngpus) {
+    if ((!hashes && n_sk * stride) || !lens || q0 > q1 || q1 > n_sk || !n_hits || (cap && !hits)) return fb2_fail(FB2_EINVAL, "bad argument");
+    if (n_sk > 0xFFFFFFFFull || kmer_length == 0) return fb2_fail(FB2_EINVAL, "bad argument");
+    for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
+    *n_hits = 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
+    std::vector<int> devs;
+    if (ngpus == 1 || ndev == 1) {
+        int d = device;
+        if (d < 0 && cudaGetDevice(&d) != cudaSuccess) d = 0;
+        if (d >= ndev) return fb2_fail(FB2_EINVAL, "device ordinal out of range");
+        devs.push_back(d);
+    } else for (int d = 0; d < (ngpus <= 0 ? ndev : std::min(ngpus, ndev)); ++d) devs.push_back(d);
+    const size_t G = std::min<size_t>(devs.size(), std::max<size_t>(1, (q1 - q0 + 8) / 9));
+    const int scaled = scale > 0.0;
+    const unsigned long long max_hash = scaled ? dist_max_hash(scale) : 0;
+    const double jlow = dist_cut_jlow(max_distance, kmer_length);
+    const size_t mat_bytes = std::max<size_t>(8, n_sk * stride * 8), len_bytes = std::max<size_t>(4, n_sk * 4);
+    std::vector<std::vector<fb2_pair_hit>> found(G);
+    std::vector<int> rcs(G, FB2_OK);
+    std::vector<std::string> msgs(G);
+    std::vector<double> kms(G, 0.0);
+    std::vector<DevBuf> d_h(G), d_l(G);
+    // the matrix goes host -> first GPU once; the others take it from there over peer copies (NVLink)
+    std::mutex mu;
+    std::condition_variable cv;
+    int src_ready = 0;   // 0 not yet, 1 ok, -1 failed
+    // row blocks in multiples of the 9-row query tile
+    const size_t rows_total = q1 - q0;
+    size_t per = ((rows_total + G - 1) / G + 8) / 9 * 9;
+    auto work = [&](size_t g) {
+        int r = FB2_OK;
+        do {
+            if (cudaSetDevice(devs[g]) != cudaSuccess) { r = fb2_fail(FB2_ECUDA, "cudaSetDevice failed"); break; }
+            if ((r = d_h[g].ensure(mat_bytes)) != FB2_OK || (r = d_l[g].ensure(len_bytes)) != FB2_OK) break;
+            if (g == 0) {
+                cudaError_t e = cudaMemcpy(d_h[0].p, hashes, n_sk * stride * 8, cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) e = cudaMemcpy(d_l[0].p, lens, n_sk * 4, cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) r = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+                { std::lock_guard<std::mutex> lk(mu); src_ready = r == FB2_OK ? 1 : -1; }
+                cv.notify_all();
+                if (r != FB2_OK) break;
+            } else {
+                { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return src_ready != 0; }); }
+                if (src_ready < 0) { r = fb2_fail(FB2_ECUDA, "matrix upload failed on the first GPU"); break; }
+                cudaError_t e = cudaMemcpyPeer(d_h[g].p, devs[g], d_h[0].p, devs[0], n_sk * stride * 8);
+                if (e == cudaSuccess) e = cudaMemcpyPeer(d_l[g].p, devs[g], d_l[0].p, devs[0], n_sk * 4);
+                if (e != cudaSuccess) r = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+                if (r != FB2_OK) break;
+            }
+            const size_t qa = std::min(q1, q0 + g * per), qb = std::min(q1, qa + per);
+            r = dist_cut_rows(d_h[g].as<unsigned long long>(), d_l[g].as<uint32_t>(), lens, n_sk, stride, scaled, max_hash, qa, qb,
+                              skip_self, jlow, found[g], &kms[g]);
+        } while (0);
+        if (g == 0 && src_ready == 0) { { std::lock_guard<std::mutex> lk(mu); src_ready = -1; } cv.notify_all(); }
+        rcs[g] = r;
+        if (r != FB2_OK) msgs[g] = fb2_last_error();
+    };
+    if (G == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; ++g) th.emplace_back(work, g);
+        for (auto &t : th) t.join();
+    }
+    for (size_t g = 0; g < G; ++g) { cudaSetDevice(devs[g]); d_h[g].release(); d_l[g].release(); }
+    if (device >= 0 && device < ndev) cudaSetDevice(device);
+    for (size_t g = 0; g < G; ++g) if (rcs[g] != FB2_OK) return fb2_fail(rcs[g], msgs[g]);
+    uint64_t total = 0;
+    double kmax = 0.0;
+    for (size_t g = 0; g < G; ++g) {
+        const size_t room = total < cap ? cap - (size_t)total : 0, n = std::min(room, found[g].size());
+        if (n) memcpy(hits + total, found[g].data(), n * sizeof(fb2_pair_hit));
+        total += found[g].size();
+        kmax = std::max(kmax, kms[g]);
+    }
+    g_dist_kernel_ms = kmax;     // the slowest GPU's summed kernel time
+    *n_hits = total;
+    if (total > cap) return fb2_fail(FB2_ENOMEM, "dist: " + std::to_string(total) + " surviving pairs, room for " + std::to_string(cap));
+    return FB2_OK;
 }
 
 extern "C" int fb2_device_count(void) {

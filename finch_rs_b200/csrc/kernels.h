@@ -69,6 +69,11 @@ void launch_dist_pairs(const unsigned long long *hashes, const uint32_t *lens, u
 uint32_t dist_tile_max_len();
 int launch_dist_tile(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
                      uint32_t q1, int scaled, unsigned long long max_hash, fb2_pair_out *out, cudaStream_t s);
+int launch_dist_tile_cut(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
+                         uint32_t q1, int scaled, unsigned long long max_hash, fb2_pair_hit *hits, unsigned long long *keys,
+                         unsigned int *counter, uint32_t cap, int skip_self, double jlow, cudaStream_t s);
+void launch_iota(uint32_t *v, uint32_t n, cudaStream_t s);
+void launch_gather_hits(const fb2_pair_hit *hits, const uint32_t *order, uint32_t n, fb2_pair_hit *sorted, cudaStream_t s);
 void launch_dist_all(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk,
                      uint32_t q0, uint64_t n_pairs, int scaled, unsigned long long max_hash, fb2_pair_out *out,
                      cudaStream_t s);

@@ -192,6 +192,22 @@ int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, si
  * array (cudaHostAlloc / cudaHostRegister) receives the device copies directly, pageable memory goes through staging. */
 int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
                        double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device);
+/* ---- calc_sketch_distances with the max_distance cut (cli/src/main.rs:315-334) --------------------------- */
+/* One surviving pair: query row q, reference row r and raw_distance's integers. */
+typedef struct fb2_pair_hit {
+    uint32_t q, r, common, i, j;
+} fb2_pair_hit;
+/* All ordered pairs (q in [q0,q1), r in [0,n_sk)) whose mash distance (distance.rs:36-41, k = kmer_length) can be
+ * <= max_distance, ascending by (q, r).  The device applies the cut conservatively (jaccard bound slightly below the
+ * exact one) and compacts the survivors; the caller finishes each with fb2_distance_finish and applies the exact
+ * `mash_distance <= max_distance` test of main.rs:328 -- nothing that test keeps is missing.  skip_self drops q == r.
+ * `hits` has room for `cap` entries; *n_hits receives the number found -- when it exceeds cap the call returns
+ * FB2_ENOMEM with *n_hits = the required capacity and the first `cap` hits written.
+ * ngpus > 1 (0 = all): the query rows are cut into one block per GPU, the hash matrix is loaded once and handed to
+ * the other GPUs over peer copies (replicas + row blocks). */
+int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride, double scale,
+                           size_t q0, size_t q1, uint8_t kmer_length, double max_distance, int skip_self,
+                           fb2_pair_hit *hits, size_t cap, uint64_t *n_hits, int32_t device, int ngpus);
 /* Measurement aid: summed device time (ms) of the kernels of this thread's last fb2_dist_all_pairs. */
 double fb2_dist_last_kernel_ms(void);
 /* distance.rs:117-125 and :35-41 from the integers of one pair. */

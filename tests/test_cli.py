@@ -26,8 +26,9 @@ def finch():
     if not os.path.exists(FINCH):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "finch_rs_b200", "csrc"), "-j8"])
 
-    def run(*args, cwd=None, check=True):
-        p = subprocess.run([FINCH, *args], capture_output=True, text=True, cwd=cwd)
+    def run(*args, cwd=None, check=True, env=None):
+        p = subprocess.run([FINCH, *args], capture_output=True, text=True, cwd=cwd,
+                           env=None if env is None else {**os.environ, **env})
         if check:
             assert p.returncode == 0, p.stderr
         return p
@@ -255,3 +256,33 @@ def test_sketch_in_place_then_dist(finch, tmp_path):
     # queries by name
     dq = json.loads(finch("dist", "-q", str(b), "--", str(tmp_path / "a.fa.sk"), str(b)).stdout)
     assert [(x["query"], x["reference"]) for x in dq] == [(str(b), str(a))]
+
+
+@pytest.mark.gpu
+def test_dist_pairwise_cut_equals_pair_list(finch, tmp_path):
+    """`finch dist -p -d X` over a collection: the tiled all-pairs kernel with the device-side max_distance cut
+    (fb2_dist_all_pairs_cut) prints byte for byte what the pair-list kernel + host filter prints
+    (calc_sketch_distances, cli/src/main.rs:315-334: reference-major order, equal-by-value pairs skipped)."""
+    rng = np.random.default_rng(17)
+    base = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=20000)
+    files = []
+    for i in range(14):
+        g = base.copy() if i % 2 else rng.choice(np.frombuffer(b"ACGT", np.uint8), size=20000)
+        pos = rng.choice(len(g), size=40 * (i + 1), replace=False)
+        g[pos] = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=len(pos))
+        p = tmp_path / f"g{i}.fa"
+        with open(p, "wb") as fh:
+            fh.write(b">g%d\n" % i)
+            for a in range(0, len(g), 60):
+                fh.write(g[a:a + 60].tobytes() + b"\n")
+        files.append(str(p))
+    files.append(files[3])                       # the same file twice: equal by value, skipped (Q12)
+    finch("sketch", "-n", "300", "-o", str(tmp_path / "all"), *files)
+    sk = str(tmp_path / "all.sk")
+    for extra in (["-p"], ["-p", "-d", "0.05"], ["-p", "-d", "0.0"], [], ["-d", "0.2"]):
+        fast = finch("dist", *extra, sk).stdout
+        slow = finch("dist", *extra, sk, env={"FINCH_DIST_PAIR_LIST": "1"}).stdout
+        assert fast == slow, extra
+    d = json.loads(finch("dist", "-p", "-d", "0.05", sk).stdout)
+    assert 0 < len(d) < 15 * 14 and all(x["mashDistance"] <= 0.05 for x in d)
+    assert all(x["query"] != x["reference"] for x in d)

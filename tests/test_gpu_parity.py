@@ -766,6 +766,53 @@ def test_dist_all_pairs_multi_slab(fb):
     assert np.array_equal(got[np.arange(n), np.arange(n)], np.tile(np.array([m, m, m], np.uint32), (n, 1)))
 
 
+@pytest.mark.parametrize("scale", [0.0, 0.002])
+def test_dist_all_pairs_cut(fb, synth, oracle, monkeypatch, scale):
+    """fb2_dist_all_pairs_cut == the dense all-pairs result filtered with main.rs:328's exact test, in (q, r) order;
+    small launches / tiny hit buffers force the retry paths; q sub-ranges; the > 1023-hash fallback."""
+    n = 600
+    mat = synth.synth_sketches(n, 1000, 6, 5)
+    lens = np.full(n, 1000, np.uint32)
+    lens[7] = 0; lens[11] = 3; lens[500] = 999
+    if scale:
+        mat = mat >> np.uint64(8)        # about half of every row below u64::MAX * scale: the scaled tail matters
+        assert np.all(np.diff(mat.astype(np.int64), axis=1) > 0)
+    dense = fb.dist_all_pairs(mat, lens, scale)
+    k = 21
+    for max_d, rows, (q0, q1) in ((0.05, "27", (0, n)), (0.3, "9", (100, 350)), (1.0, "45", (0, 40)), (0.0, "", (0, n))):
+        if rows:
+            monkeypatch.setenv("FB2_DIST_ROWS", rows)
+        else:
+            monkeypatch.delenv("FB2_DIST_ROWS", raising=False)
+        hits = fb.dist_all_pairs_cut(mat, lens, k, max_d, scale, q0, q1, skip_self=True, cap=64)
+        key = hits["q"].astype(np.int64) * n + hits["r"]
+        assert np.all(np.diff(key) > 0)                                   # ascending by (q, r), no duplicates
+        got = {}
+        cont, jac, md, com, tot = fb.distance_of_hits(hits, k)
+        for t in range(len(hits)):
+            assert tuple(dense[hits["q"][t], hits["r"][t]]) == (hits["common"][t], hits["i"][t], hits["j"][t])
+            if md[t] <= max_d:
+                got[(int(hits["q"][t]), int(hits["r"][t]))] = md[t]
+        want = {}
+        for q in range(q0, q1):
+            for r in range(n):
+                if q == r:
+                    continue
+                m = fb._finish_pair(dense[q, r], k)[2]
+                if m <= max_d:
+                    want[(q, r)] = m
+        assert got == want, (max_d, len(got), len(want))
+    # sketches longer than the tiled kernel takes: dense fallback with the same cut
+    big = np.sort(np.random.default_rng(1).integers(0, 2**62, size=(12, 1500), dtype=np.uint64), axis=1)
+    big[5, :700] = big[4, :700]; big[5] = np.sort(big[5])
+    bl = np.full(12, 1500, np.uint32)
+    hits = fb.dist_all_pairs_cut(big, bl, 21, 0.1, 0.0)
+    d2 = fb.dist_all_pairs(big, bl, 0.0)
+    want = {(q, r) for q in range(12) for r in range(12) if q != r and fb._finish_pair(d2[q, r], 21)[2] <= 0.1}
+    md = fb.distance_of_hits(hits, 21)[2]
+    assert {(int(h["q"]), int(h["r"])) for h, m in zip(hits, md) if m <= 0.1} == want and len(want) >= 2
+
+
 def test_distance_scaled_end_to_end(fb):  # distance.rs:312-337
     def mk():
         q = fb.ScaledSketcher(3, 0.001, 2, 42)
