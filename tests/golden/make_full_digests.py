@@ -69,6 +69,9 @@ def task(t):
         for p in range(n_pairs):
             _, _, com, tot = oracle.raw_distance(rows[int(q[p])], rows[int(r[p])], 0.0)
             out[p] = (com, tot)
+        # the per-pair values too (bench_configs.py checks the hit list of the cut kernel against them)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"c5_sample_n{n_sk}.npz"),
+                            common=out[:, 0].astype(np.uint16), total=out[:, 1].astype(np.uint16))
         return f"c5/n={n_sk}/pairs={n_pairs}", {"sha256_common_total": hashlib.sha256(out.tobytes()).hexdigest(),
                                                  "sum_common": int(out[:, 0].sum()), "oracle_s": round(time.time() - t0, 2)}
     raise ValueError(kind)
