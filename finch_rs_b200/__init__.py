@@ -55,7 +55,8 @@ class _Result(C.Structure):
     _fields_ = [("n", C.c_uint64), ("hashes", C.POINTER(C.c_uint64)), ("counts", C.POINTER(C.c_uint32)),
                 ("extras", C.POINTER(C.c_uint32)), ("kmers", C.POINTER(C.c_uint8)),
                 ("kmer_stride", C.c_uint32), ("seq_length", C.c_uint64),
-                ("num_valid_kmers", C.c_uint64), ("format", C.c_int32), ("filters", _Filter)]
+                ("num_valid_kmers", C.c_uint64), ("format", C.c_int32), ("filters", _Filter),
+                ("kmer_lens", C.POINTER(C.c_uint32))]
 
 
 class _Stats(C.Structure):
@@ -315,7 +316,15 @@ class _Sketcher:
         return a.value, b.value
 
     def parameters(self):
-        return self.params
+        """SketchScheme::parameters as the reference's sketchers report them (quirks Q7 / Q8): MashSketcher answers
+        final_size = size, no_strict = false whatever it was created from (mash.rs:104-112); ScaledSketcher
+        recomputes the scale from its integer max_hash (scaled.rs:102-109)."""
+        p = self.params
+        if p.kind == KIND_MASH:
+            return SketchParams.mash(p.kmers_to_sketch, p.kmers_to_sketch, False, p.kmer_length, p.hash_seed, p.device)
+        iscale = int(1.0 / p.scale)                       # scaled.rs:23: (1. / scale) as u64
+        max_hash = (2**64 - 1) // iscale                  # scaled.rs:31
+        return SketchParams.scaled(p.kmers_to_sketch, p.kmer_length, 1.0 / (float(2**64 - 1) / float(max_hash)), p.hash_seed, p.device)
 
     def to_arrays(self):
         """(hashes u64[n], counts u32[n], extras u32[n], kmers u8[n, stride], seq_length, n_kmers, format)"""
@@ -335,7 +344,7 @@ class _Sketcher:
     def to_sketch(self) -> Sketch:
         """mod.rs:33-50: name "", default filters."""
         h, c, x, km, sl, nk, fmt = self.to_arrays()
-        return Sketch("", sl, nk, "", h, c, x, km, FilterParams(), self.params, fmt)
+        return Sketch("", sl, nk, "", h, c, x, km, FilterParams(), self.parameters(), fmt)
 
     def sketch(self, name: str, filters: "FilterParams") -> "Sketch":
         """The tail of sketch_stream (lib.rs:78-93): to_vec + filter_counts + process_post_filter."""
@@ -473,7 +482,7 @@ def filter_counts(filters: FilterParams, hashes, counts, extras, fmt=FORMAT_FAST
     km = np.zeros(max(1, len(h)), np.uint8)
     r = _Result(len(h), h.ctypes.data_as(C.POINTER(C.c_uint64)), c.ctypes.data_as(C.POINTER(C.c_uint32)),
                 x.ctypes.data_as(C.POINTER(C.c_uint32)), km.ctypes.data_as(C.POINTER(C.c_uint8)), 1, 0, 0, fmt,
-                _Filter())
+                _Filter(), None)
     cf = filters._c()
     _check(lib().fb2_filter_counts(C.byref(r), C.byref(cf)))
     n = int(r.n)

@@ -1284,6 +1284,19 @@ void fb2_sketcher_hint_finish(fb2_sketcher *s, uint64_t final_size, int filter_o
     s->hint_set = true; s->hint_final = final_size; s->hint_filter = filter_on;
 }
 size_t fb2_sketcher_chunk_bytes(const fb2_sketcher *s) { return s->chunk_bytes; }
+// Device memory this handle holds right now (its pooled retention cost, hostlogic.cpp).
+size_t fb2_sketcher_device_bytes(const fb2_sketcher *s) {
+    size_t n = 0;
+    const DevBuf *bufs[] = {&s->d_raw[0], &s->d_raw[1], &s->d_sym[0], &s->d_sym[1], &s->d_stmap, &s->d_ststate, &s->d_rcount[0],
+                            &s->d_rcount[1], &s->d_tail, &s->d_carry, &s->d_state, &s->d_seam, &s->log_hash[0], &s->log_hash[1],
+                            &s->log_kmer[0], &s->log_kmer[1], &s->log_posx[0], &s->log_posx[1], &s->sort_keys, &s->sort_slots,
+                            &s->sort_tkeys, &s->sort_tslots, &s->sort_hist, &s->d_bins, &s->d_live_bins, &s->out_hash, &s->out_cnt,
+                            &s->out_ext, &s->out_kmer, &s->out_posx, &s->sel_hash, &s->sel_cnt, &s->sel_ext, &s->sel_kmer, &s->sel_posx,
+                            &s->sel_bytes, &s->sel_idx, &s->d_push_bytes, &s->d_push_offs, &s->d_push_extra};
+    for (const DevBuf *b : bufs) n += b->cap;
+    for (int t = 0; t < 2; ++t) n += s->tab[t].key.cap + s->tab[t].cnt.cap + s->tab[t].ext.cap + s->tab[t].posx.cap + s->tab[t].kmer.cap;
+    return n;
+}
 
 extern "C" int fb2_sketcher_format(fb2_sketcher *s, int32_t *format) {
     if (!s || !format) return fb2_fail(FB2_EINVAL, "null argument");
@@ -1304,8 +1317,8 @@ extern "C" int fb2_sketcher_totals(fb2_sketcher *s, uint64_t *total_bases, uint6
 
 extern "C" void fb2_result_free(fb2_result *r) {
     if (!r) return;
-    free(r->hashes); free(r->counts); free(r->extras); free(r->kmers);
-    r->hashes = nullptr; r->counts = nullptr; r->extras = nullptr; r->kmers = nullptr; r->n = 0;
+    free(r->hashes); free(r->counts); free(r->extras); free(r->kmers); free(r->kmer_lens);
+    r->hashes = nullptr; r->counts = nullptr; r->extras = nullptr; r->kmers = nullptr; r->kmer_lens = nullptr; r->n = 0;
 }
 
 // hostlogic.cpp
@@ -1421,11 +1434,15 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
         if (m) parallel_memcpy(out->kmers, h_bytes, (size_t)m * stride);
     } else {
         out->kmers = (uint8_t *)calloc(std::max<size_t>(1, (size_t)m * ostride), 1);
-        if (!out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
+        out->kmer_lens = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
+        if (!out->kmers || !out->kmer_lens) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
         for (uint32_t i = 0; i < m; ++i) {
             uint8_t *dst = out->kmers + (size_t)i * ostride;
-            if (h_posx[i] & (1ULL << 8)) { const std::string &a = s->arena[(size_t)h_kmer[i]]; memcpy(dst, a.data(), a.size()); }
-            else memcpy(dst, h_bytes + (size_t)i * stride, stride);
+            if (h_posx[i] & (1ULL << 8)) {
+                const std::string &a = s->arena[(size_t)h_kmer[i]];
+                memcpy(dst, a.data(), a.size());
+                out->kmer_lens[i] = (uint32_t)a.size();
+            } else { memcpy(dst, h_bytes + (size_t)i * stride, stride); out->kmer_lens[i] = (uint32_t)stride; }
         }
     }
     out->seq_length = s->h_carry->total_bases + s->lines_bases;

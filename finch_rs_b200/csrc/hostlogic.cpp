@@ -36,6 +36,7 @@ int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32
 int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_byte, uint64_t *first_bad_pos, uint64_t *len_bad_pos);
 uint32_t fb2_sketcher_halo(const fb2_sketcher *s);
 int fb2_sketcher_merge_from(fb2_sketcher *dst, fb2_sketcher *src);
+size_t fb2_sketcher_device_bytes(const fb2_sketcher *s);
 
 // ---- filters ---------------------------------------------------------------------------------
 static void compact(fb2_result *r, const std::vector<uint8_t> &keep) {
@@ -153,6 +154,8 @@ extern "C" int fb2_process_post_filter(fb2_result *r, const fb2_params *p, const
 }
 
 // ---- sketch_stream / sketch_files ----------------------------------------------------------------
+static bool pool_acquire(const fb2_params *p, fb2_sketcher **s, uint8_t **buf);
+static bool pool_release(const fb2_params *p, fb2_sketcher *s, uint8_t *buf);
 static int finish_sketch(fb2_sketcher *s, const char *name, const fb2_params *p, const fb2_filter *f,
                          fb2_result *out) {
     return fb2_sketcher_sketch(s, name, p, f, out);
@@ -162,14 +165,24 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
                                  const fb2_filter *f, fb2_result *out) {
     if (!p || !f || !out || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
     memset(out, 0, sizeof(*out));
+    fb2_params pd = *p;
+    if (pd.device < 0 && cudaGetDevice(&pd.device) != cudaSuccess) pd.device = -1;   // pool entries are keyed by device
     fb2_sketcher *s = nullptr;
-    int rc = fb2_sketcher_create(p, &s);
-    if (rc != FB2_OK) return rc;
-    if (p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
-    rc = fb2_sketcher_feed_fastx(s, bytes, len, 1);
+    uint8_t *buf = nullptr;
+    int rc;
+    if (pool_acquire(&pd, &s, &buf)) rc = fb2_sketcher_reset(s);
+    else rc = fb2_sketcher_create(&pd, &s);
+    if (rc == FB2_OK && p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
+    if (rc == FB2_OK) rc = fb2_sketcher_feed_fastx(s, bytes, len, 1);
     if (rc == FB2_OK) rc = finish_sketch(s, name, p, f, out);
-    fb2_sketcher_destroy(s);
-    return rc;
+    if (rc != FB2_OK) {   // keep the message across the clean-up calls
+        const std::string msg = fb2_last_error();
+        if (buf) cudaFreeHost(buf);
+        if (s) fb2_sketcher_destroy(s);
+        return fb2_fail(rc, msg);
+    }
+    if (!pool_release(&pd, s, buf)) { if (buf) cudaFreeHost(buf); fb2_sketcher_destroy(s); }
+    return FB2_OK;
 }
 
 // One file through handle `s` (lib.rs:51-94 per file): read in pieces into the worker's pinned buffer,
@@ -237,18 +250,23 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
     return rc;
 }
 
-// Idle worker handles (sketcher + pinned read buffer) kept between sketch_files calls: creating a handle
-// allocates device buffers and a pinned read buffer (tens of ms, serialised by the driver), which would otherwise
-// dominate batches of small files.  The reference API has no release call, so retention is bounded: at most
-// FB2_POOL_MAX handles (default 2; 0 disables pooling) stay behind a call, whatever the worker count was, and a
-// handle is only re-used under the chunk / log settings it was created with.  fb2_sketch_files_release_pool()
+// Idle worker handles (sketcher + pinned read buffer) kept between sketch_* calls: creating a handle allocates
+// device buffers, pinned mirrors, streams and events (10+ ms, partly serialised by the driver), which would otherwise
+// dominate small files.  The reference API has no release call, so retention is bounded PER DEVICE: at most
+// FB2_POOL_MAX handles (default 16; 0 disables pooling) holding at most FB2_POOL_MB of device memory together
+// (default 2048 MiB: a handle that sketched a 5 Mbp FASTA holds ~100 MB, one that streamed a large FASTQ ~1 GB), and
+// a handle is only re-used under the chunk / log settings it was created with.  fb2_sketch_files_release_pool()
 // frees them (the Python mirror registers it with atexit).
 struct PoolEntry { fb2_params p; fb2_sketcher *s; uint8_t *buf; std::string env; };
 static std::mutex g_pool_mu;
 static std::vector<PoolEntry> g_pool;
 static size_t pool_max() {
     if (const char *e = getenv("FB2_POOL_MAX")) { const long v = atol(e); if (v >= 0 && v <= 64) return (size_t)v; }
-    return 2;
+    return 16;
+}
+static size_t pool_max_bytes() {
+    if (const char *e = getenv("FB2_POOL_MB")) { const long v = atol(e); if (v >= 0) return (size_t)v << 20; }
+    return (size_t)2048 << 20;
 }
 static std::string pool_env_key() {
     const char *a = getenv("FB2_CHUNK_MB"), *b = getenv("FB2_LOG_M"), *c = getenv("FB2_TABLE_MULT");
@@ -272,9 +290,9 @@ static bool pool_acquire(const fb2_params *p, fb2_sketcher **s, uint8_t **buf) {
 }
 static bool pool_release(const fb2_params *p, fb2_sketcher *s, uint8_t *buf) {
     std::lock_guard<std::mutex> g(g_pool_mu);
-    size_t on_device = 0;
-    for (const auto &e : g_pool) on_device += e.p.device == p->device;
-    if (on_device >= pool_max() || p->stream) return false;
+    size_t on_device = 0, bytes = fb2_sketcher_device_bytes(s);
+    for (const auto &e : g_pool) if (e.p.device == p->device) { ++on_device; bytes += fb2_sketcher_device_bytes(e.s); }
+    if (on_device >= pool_max() || bytes > pool_max_bytes() || p->stream) return false;
     g_pool.push_back(PoolEntry{*p, s, buf, pool_env_key()});
     return true;
 }

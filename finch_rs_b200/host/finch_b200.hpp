@@ -4,6 +4,7 @@
 //   SketchScheme::{process,total_bases_and_kmers,to_vec}  (mod.rs:24-51)
 //   MashSketcher::push / ScaledSketcher::push             (mash.rs:34, scaled.rs:37)
 //   sketch_stream                                          (lib/src/lib.rs:51-94)
+// Compiled and run by tests/hpp_mirror_test.cpp (tests/test_abi_cpu.py builds it, tests/test_gpu_parity.py runs it).
 #pragma once
 #include <cstdint>
 #include <memory>
@@ -48,12 +49,25 @@ public:
         std::vector<KmerCount> v(r.n);
         for (uint64_t i = 0; i < r.n; ++i) {
             v[i].hash = r.hashes[i]; v[i].count = r.counts[i]; v[i].extra_count = r.extras[i];
-            v[i].kmer.assign(r.kmers + i * r.kmer_stride, r.kmers + i * r.kmer_stride + params_.kmer_length);
+            const size_t kl = r.kmer_lens ? r.kmer_lens[i] : params_.kmer_length;   // pushed k-mers keep their own length
+            v[i].kmer.assign(r.kmers + i * r.kmer_stride, r.kmers + i * r.kmer_stride + kl);
         }
         fb2_result_free(&r);
         return v;
     }
-    const fb2_params &parameters() const { return params_; }
+    // SketchScheme::parameters as the reference's sketchers answer it (quirks Q7 / Q8): MashSketcher reports
+    // final_size = size, no_strict = false (mash.rs:104-112); ScaledSketcher recomputes the scale from its integer
+    // max_hash (scaled.rs:23,31,102-109).
+    fb2_params parameters() const {
+        fb2_params p = params_;
+        if (p.kind == FB2_KIND_MASH) { p.final_size = p.kmers_to_sketch; p.no_strict = 0; }
+        else {
+            const uint64_t iscale = (uint64_t)(1.0 / p.scale);
+            const uint64_t max_hash = UINT64_MAX / iscale;
+            p.scale = 1.0 / ((double)UINT64_MAX / (double)max_hash);
+        }
+        return p;
+    }
 
 private:
     fb2_sketcher *h_ = nullptr;

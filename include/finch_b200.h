@@ -83,6 +83,8 @@ typedef struct fb2_result {
     uint64_t num_valid_kmers;  /* total_kmers  (mash.rs:35) */
     int32_t format;            /* FB2_FORMAT_* seen by the parser */
     fb2_filter filters;        /* FilterParams as updated by filter_counts (sketch_* calls only) */
+    uint32_t *kmer_lens;       /* NULL: every k-mer is kmer_length bytes.  Else n byte lengths: entries that came through
+                                  fb2_sketcher_push keep the caller's bytes, of any length up to kmer_stride (mash.rs:52-55) */
 } fb2_result;
 
 typedef struct fb2_sketcher fb2_sketcher;

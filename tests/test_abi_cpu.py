@@ -118,3 +118,35 @@ def test_oracle_literal_equals_closed_form(oracle):
         small = int(np.searchsorted(uniq, sc.max_hash(), side="right"))
         keep = small if s == 0 else max(small, min(s, len(uniq)))
         assert np.array_equal(v["hashes"], uniq[:keep]) and np.array_equal(v["counts"], cnt[:keep])
+
+
+def build_hpp_mirror_test():
+    """tests/hpp_mirror_test.cpp: the header-only C++ mirror (finch_rs_b200/host/finch_b200.hpp) compiled for real."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "hpp_mirror_test.cpp")
+    exe = os.path.join(ROOT, "tests", "_hpp_mirror_test")
+    libdir = os.path.join(ROOT, "finch_rs_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-o", exe, src, "-L" + libdir, "-lfinch_b200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_mirror_header_compiles_and_links(fb):
+    import subprocess
+    exe = build_hpp_mirror_test()
+    out = subprocess.run([exe, "--link-only"], capture_output=True, text=True)
+    assert out.returncode == 0 and "sm_100a" in out.stdout, out.stderr
+
+
+def test_parameters_reports_what_the_reference_sketchers_report():
+    """Quirks Q7 / Q8 (mash.rs:104-112, scaled.rs:102-109) in the mirror's parameters(), without a device."""
+    import finch_rs_b200 as m
+
+    class Fake(m._Sketcher):
+        def __init__(self, params):
+            self.params = params
+    p = Fake(m.SketchParams.mash(200000, 1000, True, 21, 7)).parameters()
+    assert (p.kmers_to_sketch, p.final_size, p.no_strict, p.kmer_length, p.hash_seed) == (200000, 200000, False, 21, 7)
+    p = Fake(m.SketchParams.scaled(10, 31, 0.003, 3)).parameters()
+    max_hash = (2**64 - 1) // 333                     # (1. / 0.003) as u64 == 333
+    assert p.scale == 1.0 / (float(2**64 - 1) / float(max_hash)) and p.scale != 0.003 and p.kmers_to_sketch == 10

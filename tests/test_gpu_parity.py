@@ -101,6 +101,23 @@ def test_counts_saturate_at_u32_max(fb):  # mash.rs:48-49: count.0.saturating_ad
         q.close()
 
 
+def test_cpp_mirror_runs_the_reference_unit_tests(fb):
+    """finch_rs_b200/host/finch_b200.hpp through tests/hpp_mirror_test.cpp: mash.rs:115-134, scaled.rs:118-176."""
+    import subprocess
+    from test_abi_cpu import build_hpp_mirror_test
+    out = subprocess.run([build_hpp_mirror_test()], capture_output=True, text=True)
+    assert out.returncode == 0 and "hpp mirror ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_pushed_kmers_keep_their_length(fb):
+    q = fb.MashSketcher(5, 2, 0)
+    q.push(b"ACGTACGT", 0); q.push(b"ac", 1)
+    h, c, x, km, *_ = q.to_arrays()
+    got = {bytes(km[i]).rstrip(b"\0") for i in range(len(h))}
+    assert got == {b"ACGTACGT", b"ac"}
+    q.close()
+
+
 def test_longer_sequence_seed42(fb):  # mash.rs:136-154
     q = fb.MashSketcher(100, 21, 42)
     q.process(b"ACACGGAAATCCTCACGTCGCGGCGCCGGGC")
