@@ -278,6 +278,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=600_000, help="cpu_baseline sample (reads, 1 core)")
     ap.add_argument("--ref-reads", type=int, default=0, help="--impl reference reads per step (0 = --reads: same config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-strip", action="store_true", help="do not try the FB2_HOST_STRIP=1 mode of the e2e call")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 (NCCL prints its version
     # there): keep the real stdout aside for the JSON line and send everything else to stderr.
@@ -376,7 +377,23 @@ def main():
 
     ms_res, last_res, stats_res, clocks = timed(True, args.steps, args.warmup, sample_clocks=True)
     e2e_steps = max(3, args.steps // 2)
+    os.environ["FB2_HOST_STRIP"] = "0"
     ms_e2e, last_e2e, stats_e2e, _ = timed(False, e2e_steps, 1)
+    e2e_plain = {"value": nbases * world * e2e_steps / (ms_e2e * 1e-3) / 1e9, "ms_per_step": ms_e2e / e2e_steps,
+                 "h2d_bytes_per_step": int(stats_e2e["h2d_bytes"] // e2e_steps)}
+    # The same call with the host pre-strip (FB2_HOST_STRIP=1, strip.cpp): worker threads frame the FASTQ records and
+    # only the sequence lines cross PCIe.  Needs host cores: used when this rank has >= 8 of them to itself.
+    strip_threads = min(16, host_cores() // max(1, world))
+    e2e_strip = None
+    if strip_threads >= 8 and not args.no_host_strip:
+        os.environ["FB2_HOST_STRIP"] = "1"
+        os.environ["FB2_STRIP_THREADS"] = str(strip_threads)
+        ms_s, last_s, stats_s, _ = timed(False, e2e_steps, 2)
+        os.environ["FB2_HOST_STRIP"] = "0"
+        e2e_strip = {"value": nbases * world * e2e_steps / (ms_s * 1e-3) / 1e9, "ms_per_step": ms_s / e2e_steps,
+                     "h2d_bytes_per_step": int(stats_s["h2d_bytes"] // e2e_steps), "threads": strip_threads}
+        if ms_s < ms_e2e:      # the headline e2e is the better of the two modes of the same public call
+            ms_e2e, last_e2e, stats_e2e = ms_s, last_s, stats_s
 
     # ---- platform H2D ceiling: the same pinned buffers, all N ranks at once, no kernels ---------------------
     def h2d_ceiling(reps=3):
@@ -447,7 +464,7 @@ def main():
     total_bases = nbases * world
     value = total_bases * args.steps / (ms_res * 1e-3) / 1e9
     e2e_value = total_bases * e2e_steps / (ms_e2e * 1e-3) / 1e9
-    e2e_gbs = nbytes * world * e2e_steps / (ms_e2e * 1e-3) / 1e9
+    e2e_gbs = int(stats_e2e["h2d_bytes"] // e2e_steps) * world * e2e_steps / (ms_e2e * 1e-3) / 1e9
 
     line = {
         "metric": METRIC, "value": value, "unit": "Gbases/s",
@@ -458,7 +475,10 @@ def main():
                 "d2h_bytes_per_step": int(stats_e2e["d2h_bytes"] // e2e_steps), "ms_per_step": ms_e2e / e2e_steps,
                 "steps": e2e_steps, "h2d_gbs": e2e_gbs, "h2d_ceiling_gbs": h2d_gbs,
                 "frac_of_h2d_ceiling": e2e_gbs / h2d_gbs if h2d_gbs else None,
-                "h2d_ceiling_how": f"{world} rank(s) copying the same pinned buffers concurrently, no kernels, max over ranks"},
+                "h2d_ceiling_how": f"{world} rank(s) copying the same pinned buffers concurrently, no kernels, max over ranks",
+                "mode": "host pre-strip (FB2_HOST_STRIP=1): FASTQ framing on the host cores, sequence lines only over PCIe"
+                        if (e2e_strip and e2e_strip["ms_per_step"] * e2e_steps == ms_e2e) else "raw FASTQ bytes over PCIe, parsed on the GPU",
+                "raw_bytes": e2e_plain, "host_strip": e2e_strip},
         "gpu_launches": int(stats_res["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "strip.h"
 
 using namespace fb2;
 
@@ -140,6 +141,17 @@ struct fb2_sketcher {
 
     int format = FB2_FORMAT_UNKNOWN;
     bool stream_open = false;        // a FASTX stream has begun and not yet seen `final`
+    // FB2_HOST_STRIP=1: FASTQ record framing on the host, only the sequence lines cross PCIe (strip.cpp)
+    bool strip_on = false;               // active for the open stream
+    unsigned strip_threads = 1;
+    std::vector<uint8_t> strip_carry;    // the incomplete record at the end of the previous piece
+    uint64_t strip_off = 0;              // stream offset of the next unprocessed byte (of strip_carry[0] when it is not empty)
+    uint8_t *strip_pin[2] = {nullptr, nullptr};   // two staging sets of strip_threads buffers each
+    size_t strip_pin_each = 0;           // capacity of one thread's buffer
+    cudaEvent_t ev_strip_free[2]{};
+    bool strip_free_pending[2] = {false, false};
+    int strip_set = 0;
+    uint64_t strip_bad = ~0ULL, strip_len_bad = ~0ULL, strip_first_blank = ~0ULL, strip_last_nonblank = 0, strip_records = 0;
     std::vector<uint8_t> presniff;   // a first piece shorter than 2 bytes waits here until the format can be sniffed
     // fb2_sketcher_hint_finish: the caller will finish with fb2_sketcher_sketch(final_size, filter) and nothing else,
     // so a Mash heap larger than final_size is only needed when the filter ends up on
@@ -400,6 +412,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     if (s->h_carry) cudaFreeHost(s->h_carry);
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->h_stage) cudaFreeHost(s->h_stage);
+    for (int i = 0; i < 2; ++i) { if (s->strip_pin[i]) cudaFreeHost(s->strip_pin[i]); if (s->ev_strip_free[i]) cudaEventDestroy(s->ev_strip_free[i]); }
     if (s->own_stream && s->st) cudaStreamDestroy(s->st);
     if (s->copy_st) cudaStreamDestroy(s->copy_st);
     if (s->st2) cudaStreamDestroy(s->st2);
@@ -989,8 +1002,166 @@ static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
     TRY(push_carry(s));
     s->stream_open = true;
     s->tail_host.clear();
+    s->strip_on = false;
+    if (s->format == FB2_FORMAT_FASTQ) {
+        const char *e = getenv("FB2_HOST_STRIP");
+        if (e && *e == '1') {
+            s->strip_on = true;
+            s->strip_threads = (unsigned)std::min<size_t>(64, std::max<size_t>(1, env_size("FB2_STRIP_THREADS", std::min(16u, std::max(1u, std::thread::hardware_concurrency())))));
+            s->strip_carry.clear(); s->strip_off = 0;
+            s->strip_bad = s->strip_len_bad = s->strip_first_blank = ~0ULL; s->strip_last_nonblank = 0; s->strip_records = 0;
+        }
+    }
     return FB2_OK;
 }
+
+// ---- FASTQ with the host pre-strip (strip.cpp) ------------------------------------------------------------------
+static void strip_note(fb2_sketcher *s, const StripOut &o) {
+    s->strip_bad = std::min(s->strip_bad, o.bad_pos); s->strip_len_bad = std::min(s->strip_len_bad, o.len_bad_pos);
+    s->strip_first_blank = std::min(s->strip_first_blank, o.first_blank);
+    s->strip_last_nonblank = std::max(s->strip_last_nonblank, o.last_nonblank);
+    s->strip_records += o.records;
+    s->lines_bases += o.bases;          // mash.rs:72: total_bases += seq.sequence().len()
+}
+// append already stripped lines to the pinned staging of the MODE_LINES path (small pieces)
+static int stage_lines(fb2_sketcher *s, const uint8_t *data, size_t n) {
+    TRY(ensure_stage(s));
+    if (s->stage_mode != MODE_LINES) { TRY(flush_stage(s)); s->stage_mode = MODE_LINES; }
+    size_t done = 0;
+    while (done < n) {
+        if (s->stage_fill == s->stage_cap) { TRY(flush_stage(s)); s->stage_mode = MODE_LINES; }
+        const size_t m = std::min(n - done, s->stage_cap - s->stage_fill);
+        memcpy(s->h_stage + s->stage_fill, data + done, m);
+        s->stage_fill += m; done += m;
+    }
+    return FB2_OK;
+}
+// strip [p, q) (whole records from a record start) on this thread and stage the lines
+static int strip_small(fb2_sketcher *s, const uint8_t *p, const uint8_t *q, uint64_t off, const uint8_t **stopped) {
+    StripOut o;
+    o.origin = p;
+    o.spill.resize((size_t)(q - p) / 2 + 16);
+    o.spilled = true;
+    *stopped = strip_records(p, q, nullptr, off, o);
+    strip_note(s, o);
+    return stage_lines(s, o.spill.data(), o.out_len);
+}
+static int feed_fastq_stripped(fb2_sketcher *s, const uint8_t *bytes, size_t len, int final) {
+    const uint8_t *p = bytes, *end = bytes + len;
+    // 1. the record left incomplete by the previous piece
+    if (!s->strip_carry.empty() && len) {
+        const uint8_t *q = complete_record(s->strip_carry, p, end);
+        if (!q) { s->strip_carry.insert(s->strip_carry.end(), p, end); p = end; }
+        else {
+            std::vector<uint8_t> joined(s->strip_carry);
+            joined.insert(joined.end(), p, q);
+            const uint8_t *st = nullptr;
+            TRY(strip_small(s, joined.data(), joined.data() + joined.size(), s->strip_off, &st));
+            s->strip_off += joined.size();
+            s->strip_carry.clear();
+            p = q;
+        }
+    }
+    // 2. whole records of this piece
+    if (p < end && s->strip_carry.empty()) {
+        if ((size_t)(end - p) < (1u << 20)) {
+            const uint8_t *st = nullptr;
+            TRY(strip_small(s, p, end, s->strip_off, &st));
+            s->strip_off += (uint64_t)(st - p);
+            p = st;
+        } else {
+            TRY(flush_stage(s));                         // staged (older) lines go first: stream order = position order
+            const unsigned T = s->strip_threads;
+            size_t block = 2 * s->chunk_bytes;           // stripped, a block is under half its size: one device chunk
+            const size_t each = (block / T) / 2 + (1u << 20);
+            if (!s->strip_pin[0] || s->strip_pin_each < each) {
+                for (int i = 0; i < 2; ++i) {
+                    if (s->strip_pin[i]) cudaFreeHost(s->strip_pin[i]);
+                    s->strip_pin[i] = nullptr;
+                    CU(cudaHostAlloc((void **)&s->strip_pin[i], each * T, cudaHostAllocDefault));
+                    if (!s->ev_strip_free[i]) CU(cudaEventCreateWithFlags(&s->ev_strip_free[i], cudaEventDisableTiming));
+                    s->strip_free_pending[i] = false;
+                }
+                s->strip_pin_each = each;
+            }
+            std::vector<StripOut> outs(T);
+            while (p < end) {
+                const uint8_t *blk_end = (size_t)(end - p) > block ? p + block : end;
+                const int set = s->strip_set;
+                if (s->strip_free_pending[set]) { CU(cudaEventSynchronize(s->ev_strip_free[set])); s->strip_free_pending[set] = false; }
+                for (unsigned t = 0; t < T; ++t) {
+                    outs[t] = StripOut();
+                    outs[t].out = s->strip_pin[set] + (size_t)t * s->strip_pin_each;
+                    outs[t].out_cap = s->strip_pin_each;
+                }
+                const uint8_t *e = strip_parallel(p, blk_end, s->strip_off, T, outs);
+                size_t total = 0;
+                for (auto &o : outs) { strip_note(s, o); total += o.out_len; }
+                if (total) {
+                    if (total > s->chunk_bytes) return fb2_fail(FB2_EINVAL, "internal: stripped block exceeds a chunk");
+                    const int b = set;                   // raw buffer b pairs with staging set b
+                    TRY(s->d_raw[b].ensure(std::min(s->chunk_bytes, (total + 4095) / 4096 * 4096) + 64));
+                    if (s->rawfree_pending[b]) { CU(cudaStreamWaitEvent(s->copy_st, s->ev_rawfree[b], 0)); s->rawfree_pending[b] = false; }
+                    size_t at = 0;
+                    for (auto &o : outs) {
+                        if (!o.out_len) continue;
+                        CU(cudaMemcpyAsync(s->d_raw[b].as<uint8_t>() + at, o.data(), o.out_len, cudaMemcpyHostToDevice, s->copy_st));
+                        at += o.out_len;
+                        if (o.spilled) CU(cudaStreamSynchronize(s->copy_st));   // pageable source: gone after this iteration
+                    }
+                    CU(cudaEventRecord(s->ev_h2d[b], s->copy_st));
+                    CU(cudaEventRecord(s->ev_strip_free[set], s->copy_st));
+                    s->strip_free_pending[set] = true;
+                    s->stats.h2d_bytes += total;
+                    CU(cudaStreamWaitEvent(s->st, s->ev_h2d[b], 0));
+                    TRY(run_chunk(s, s->d_raw[b].as<uint8_t>(), (uint32_t)total, MODE_LINES, b));
+                    s->strip_set ^= 1;
+                }
+                s->strip_off += (uint64_t)(e - p);
+                if (e == p) {                            // not one complete record in the block
+                    if (blk_end == end) break;
+                    block *= 2;                          // a very long record: look further
+                    continue;
+                }
+                p = e;
+            }
+        }
+        if (p < end) s->strip_carry.assign(p, end);      // the incomplete record waits for the next piece
+    }
+    if (!final) return FB2_OK;
+    // 3. end of the stream: the reader's end-of-input rules on what is left
+    int bad_tail = 0;
+    if (!s->strip_carry.empty()) {
+        StripOut o;
+        o.origin = s->strip_carry.data();
+        o.spill.resize(s->strip_carry.size() / 2 + 16);
+        o.spilled = true;
+        bad_tail = strip_final(s->strip_carry.data(), s->strip_carry.data() + s->strip_carry.size(), s->strip_off, o);
+        strip_note(s, o);
+        TRY(stage_lines(s, o.spill.data(), o.out_len));
+        s->strip_carry.clear();
+    }
+    TRY(flush_stage(s));
+    TRY(settle_all(s));
+    TRY(pull_state(s));
+    s->h_carry->state = 0; s->h_carry->prev1 = s->h_carry->prev2 = '\n';
+    TRY(push_carry(s));
+    launch_fill_bytes(s->d_tail.as<uint8_t>(), 2 * HALO_BIG, SYM_BREAK, s->st);
+    s->stats.kernel_launches++;
+    s->stream_open = false;
+    s->strip_on = false;
+    if (s->strip_bad != ~0ULL)
+        return fb2_fail(FB2_ERECORD, "invalid FASTQ record: line at byte " + std::to_string(s->strip_bad) + " does not start with the expected '@' / '+'");
+    if (s->strip_len_bad != ~0ULL)
+        return fb2_fail(FB2_ERECORD, "invalid FASTQ record: sequence and quality lengths differ (record whose header ends at byte " +
+                                         std::to_string(s->strip_len_bad) + ")");
+    if (s->strip_first_blank != ~0ULL && s->strip_first_blank < s->strip_last_nonblank)
+        return fb2_fail(FB2_ERECORD, "invalid FASTQ record: blank lines at byte " + std::to_string(s->strip_first_blank) + " inside the stream");
+    if (bad_tail) return fb2_fail(FB2_ERECORD, "truncated or invalid FASTQ record at end of input");
+    if (s->strip_records == 0) return fb2_fail(FB2_EEMPTY, "no records in FASTQ stream");
+    return FB2_OK;
+}
+
 static int end_stream(fb2_sketcher *s) {
     TRY(flush_stage(s));
     TRY(settle_all(s));
@@ -1098,6 +1269,11 @@ extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, si
     if (len) {
         if (!s->stream_open) TRY(begin_stream(s, bytes, len));
         const int mode = s->format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ;
+        if (s->strip_on) {
+            TRY(feed_fastq_stripped(s, bytes, len, final));
+            if (len >= (1u << 20)) CU(cudaStreamSynchronize(s->copy_st));   // (staging sets are ours; the caller's bytes were only read by the CPU)
+            return FB2_OK;
+        }
         note_tail(s, bytes, len);
         if (len < (1u << 20)) {  // small piece: gather in pinned staging
             TRY(ensure_stage(s));
@@ -1117,6 +1293,7 @@ extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, si
     }
     if (final) {
         if (!s->stream_open) return fb2_fail(FB2_EEMPTY, "empty input: no records");
+        if (s->strip_on) return feed_fastq_stripped(s, nullptr, 0, 1);
         TRY(end_stream(s));
     }
     return FB2_OK;

@@ -150,3 +150,28 @@ def test_parameters_reports_what_the_reference_sketchers_report():
     p = Fake(m.SketchParams.scaled(10, 31, 0.003, 3)).parameters()
     max_hash = (2**64 - 1) // 333                     # (1. / 0.003) as u64 == 333
     assert p.scale == 1.0 / (float(2**64 - 1) / float(max_hash)) and p.scale != 0.003 and p.kmers_to_sketch == 10
+
+
+def test_host_strip_framing_cpu(oracle):
+    """strip.cpp (FB2_HOST_STRIP) on the CPU, no device: the lines it ships are exactly the records' sequence()
+    slices the oracle's reader yields, its verdict on malformed streams is the reader's, for any thread count."""
+    import subprocess
+    import gen
+    exe = os.path.join(ROOT, "tests", "_strip_host_test")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "strip_host_test.cpp"),
+                           os.path.join(ROOT, "finch_rs_b200", "csrc", "strip.cpp"), "-lpthread"])
+    rng = np.random.default_rng(2)
+    body = gen.fastq(rng, n_records=3000, max_len=400, messy=0.02)
+    cases = [body, body.replace(b"\n", b"\r\n"), body[:-1], gen.fastq(rng, n_records=40, max_len=60_000, messy=0.0),
+             b"@r\n\n+\n", b"@r\nAC\n+\nII", body + b"\n\r\n\n", b"@r\nA\n+\n\r\r", body + b"@r\nA\n+\n", body + b"@x\nACGT\n+\nII\n" + body,
+             body[:5000] + b"\n\n\n\n" + body[5000:], body + b"@q\nAC\n-\nII\n", b"@a\nAC\n+\nII\n\n\n\n\n\n\n\n\n"]
+    for data in cases:
+        rc, fmt, recs = oracle.parse_fastx(data)
+        for threads in (1, 3, 8):
+            out = subprocess.run([exe, str(threads)], input=data, capture_output=True).stdout
+            head, _, lines = out.partition(b"\n")
+            n, bases, invalid = (int(x) for x in head.split())
+            assert bool(invalid) == (rc != oracle.OK), (data[-30:], threads)
+            if rc == oracle.OK:
+                assert lines == b"".join(r + b"\n" for r in recs)
+                assert bases == sum(len(r) for r in recs)

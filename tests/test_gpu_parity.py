@@ -643,6 +643,61 @@ def test_sketch_files_multi_gpu_assignment(fb, oracle, tmp_path, monkeypatch):
             assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
 
 
+def test_host_strip_matches_device_parse(fb, synth, oracle, monkeypatch):
+    """FB2_HOST_STRIP=1: FASTQ record framing on the host (strip.cpp), sequence lines only over PCIe.  Same sketches,
+    same totals, same verdict on malformed input as the device parse -- i.e. as the oracle."""
+    monkeypatch.setenv("FB2_HOST_STRIP", "1")
+    monkeypatch.setenv("FB2_STRIP_THREADS", "5")
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    sp = fb.SketchParams.mash(2000, 2000, True, 21, 0)
+    osp = oracle.mash_params(2000, 2000, True, 21, 0)
+    rng = np.random.default_rng(12)
+    genome = synth.synth_genome(40_000, 6)
+    big = synth.synth_fastq(genome, 30_000, 150, 0.01, 8)[0].tobytes()          # 9 MB: parallel blocks, several chunks
+    inputs = [big, big.replace(b"\n", b"\r\n"), big[:-1],
+              gen.fastq(rng, n_records=400, max_len=300, messy=0.03, final_newline=False),
+              gen.fastq(rng, n_records=300, max_len=120, messy=0.05, crlf=True),
+              gen.fastq(rng, n_records=50, max_len=50_000, messy=0.001),          # long reads: records larger than a range
+              b"@r\n\n+\n", b"@r\nACGTTGCA\n+\nIIIIIIII", big + b"\n\n\r\n"]
+    for data in inputs:
+        rc, osk = oracle.sketch_stream(data, osp, oracle.make_filter(False))
+        assert rc == oracle.OK
+        for pieces in (None, [3, 1, 700_001, 5], [1 << 20, 1 << 20]):
+            with sp.create_sketcher() as s:
+                if pieces is None:
+                    s.feed_fastx(data, final=True)
+                else:
+                    pos = 0
+                    for pc in pieces:
+                        s.feed_fastx(data[pos:pos + pc], final=False)
+                        pos += pc
+                    s.feed_fastx(data[pos:], final=True)
+                sk = s.sketch("x", fb.FilterParams(False))
+                assert s.stats()["h2d_bytes"] < 0.62 * len(data) + 4096          # the quality / header lines stayed on the host
+            assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+            assert np.array_equal(sk.extra_counts, osk["extras"]) and [sk.kmer_bytes(i) for i in range(len(sk))] == osk["kmers"]
+            assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+    # malformed input: the verdicts of the reader
+    recs, nl = _fastq_records(rng, 4000, False)
+    bad_inputs = []
+    for i, how in ((0, 0), (1999, 1), (3999, 2), (2500, 3)):
+        bad = [list(r) for r in recs]
+        if how == 0: bad[i][3] += b"I"
+        elif how == 1: bad[i][1] += b"A"
+        elif how == 2: bad[i][2] = b"-"
+        else: bad[i][0] = b"r" + bad[i][0][1:]
+        bad_inputs.append(_join(bad, nl))
+    good = _join(recs, nl)
+    bad_inputs += [good + b"@r\nACG\n+\n", good + b"@r\nACG\n+\nII", good[:len(good) // 2] + b"\n\n\n\n" + good[len(good) // 2:],
+                   good + b"@r\nACG\n", b"@r\nA\n+\n"]
+    for data in bad_inputs:
+        rc, _ = oracle.sketch_stream(data, osp, oracle.make_filter(False))
+        assert rc == oracle.E_RECORD
+        with pytest.raises(fb.FinchError) as e:
+            fb.sketch_stream(data, "bad", sp, fb.FilterParams(False))
+        assert e.value.code == fb.ERECORD, e.value.message
+
+
 def test_sketch_files(fb, oracle, tmp_path):
     rng = np.random.default_rng(21)
     paths, datas = [], []
