@@ -384,7 +384,7 @@ def main():
     # The same call with the host pre-strip (FB2_HOST_STRIP=1, strip.cpp): worker threads frame the FASTQ records and
     # only the sequence lines cross PCIe.  Needs host cores: used when this rank has >= 8 of them to itself.
     strip_threads = min(16, host_cores() // max(1, world))
-    e2e_strip = None
+    e2e_strip, used_strip = None, False
     if strip_threads >= 8 and not args.no_host_strip:
         os.environ["FB2_HOST_STRIP"] = "1"
         os.environ["FB2_STRIP_THREADS"] = str(strip_threads)
@@ -393,7 +393,7 @@ def main():
         e2e_strip = {"value": nbases * world * e2e_steps / (ms_s * 1e-3) / 1e9, "ms_per_step": ms_s / e2e_steps,
                      "h2d_bytes_per_step": int(stats_s["h2d_bytes"] // e2e_steps), "threads": strip_threads}
         if ms_s < ms_e2e:      # the headline e2e is the better of the two modes of the same public call
-            ms_e2e, last_e2e, stats_e2e = ms_s, last_s, stats_s
+            ms_e2e, last_e2e, stats_e2e, used_strip = ms_s, last_s, stats_s, True
 
     # ---- platform H2D ceiling: the same pinned buffers, all N ranks at once, no kernels ---------------------
     def h2d_ceiling(reps=3):
@@ -477,7 +477,7 @@ def main():
                 "frac_of_h2d_ceiling": e2e_gbs / h2d_gbs if h2d_gbs else None,
                 "h2d_ceiling_how": f"{world} rank(s) copying the same pinned buffers concurrently, no kernels, max over ranks",
                 "mode": "host pre-strip (FB2_HOST_STRIP=1): FASTQ framing on the host cores, sequence lines only over PCIe"
-                        if (e2e_strip and e2e_strip["ms_per_step"] * e2e_steps == ms_e2e) else "raw FASTQ bytes over PCIe, parsed on the GPU",
+                        if used_strip else "raw FASTQ bytes over PCIe, parsed on the GPU",
                 "raw_bytes": e2e_plain, "host_strip": e2e_strip},
         "gpu_launches": int(stats_res["kernel_launches"]),
         "clocks": clocks,
