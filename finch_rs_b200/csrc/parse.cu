@@ -536,7 +536,7 @@ __device__ __forceinline__ void ones128(uint32_t nbytes, uint64_t &lo, uint64_t 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 4)   // 64 registers: four blocks per SM
 pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, const uint32_t *__restrict__ st_state,
             uint8_t *__restrict__ sym, uint32_t *__restrict__ region_count, SeamNl *__restrict__ seam) {
     __shared__ uint8_t lut[256];
@@ -717,6 +717,29 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
             uint32_t pos = 16u * w + filled - a;               // output position within the batch
             uint32_t i = s_first[w];
             uint32_t d = pos - (uint32_t)e_out[i];
+            // Common case (9 of 10 words of 150 bp reads): the whole word comes out of ONE line.  No masks, no merging:
+            // unaligned 16-byte read, SIMD-in-register codes, one aligned store.  Anything but ACGTacgt in it takes the
+            // general path below.
+            if (f0 == 0u && d + 16u <= ((uint32_t)e_len[i] & 0x7FFFu)) {
+                const uint32_t A = 16u + (uint32_t)e_src[i] + d;                  // s_rawbuf offset of output byte 0
+                const uint32_t wi = A >> 2, sel = 0x3210u + 0x1111u * (A & 3u);
+                uint32_t x[5], cw[4], diff = 0;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) x[j] = raw32[wi + j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t u = __byte_perm(x[j], x[j + 1], sel) & 0xDFDFDFDFu;
+                    const uint32_t c2 = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+                    cw[j] = c2;
+                    uint32_t z = (c2 | (c2 >> 4)) & 0x00FF00FFu;
+                    z = (z | (z >> 8)) & 0xFFFFu;
+                    diff |= __byte_perm(0x54474341u, 0u, z) ^ u;
+                }
+                if (diff == 0u) {
+                    *reinterpret_cast<uint4 *>(obase + 16u * w) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                    continue;
+                }
+            }
             uint64_t alo = 0, ahi = 0;
             while (filled < 16u && pos < T) {
                 const uint32_t L = e_len[i], len = L & 0x7FFFu, brk = L >> 15;

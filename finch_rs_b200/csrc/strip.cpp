@@ -94,12 +94,37 @@ static inline bool take_record(const uint8_t *p, const uint8_t *l1, const uint8_
 }
 
 #if defined(__x86_64__)
+// Output of the AVX2 path goes through a small cache-resident buffer and leaves it with non-temporal stores: the
+// stripped lines are written once and next read by the DMA engine, so they should neither be read for ownership
+// nor displace the input stream from the caches.
+struct WcOut {
+    static constexpr size_t CAP = 8192;
+    alignas(64) uint8_t buf[CAP + 64];
+    size_t fill = 0;
+    uint8_t *dst;                 // next 32-byte aligned position of the real output
+    size_t head = 0;              // bytes in front of dst that were written directly (unaligned start)
+};
+__attribute__((target("avx2")))
+static inline void wc_flush(WcOut &w, bool all) {
+    size_t n = all ? w.fill : (w.fill & ~(size_t)31);
+    size_t i = 0;
+    if (((uintptr_t)w.dst & 31u) == 0) {
+        for (; i + 32 <= n; i += 32) _mm256_stream_si256((__m256i *)(w.dst + i), _mm256_load_si256((const __m256i *)(w.buf + i)));
+    }
+    if (i < n) { memcpy(w.dst + i, w.buf + i, n - i); i = n; }
+    w.dst += n;
+    const size_t rest = w.fill - n;
+    if (rest) memmove(w.buf, w.buf + n, rest);
+    w.fill = rest;
+}
 // Single pass: 64 bytes per step -> a 64-bit newline mask; every set bit is a line end, every fourth one a record.
 __attribute__((target("avx2,bmi,bmi2,lzcnt,popcnt")))
 static const uint8_t *strip_records_avx2(const uint8_t *p, const uint8_t *end, const uint8_t *stop_at, uint64_t base_off, StripOut &o) {
     uint8_t *const obase = o.spilled ? o.spill.data() : o.out;
     const size_t ocap = o.spilled ? o.spill.size() : o.out_cap;
     size_t olen = o.out_len;
+    WcOut w;
+    w.dst = obase + olen;
     const __m256i nlv = _mm256_set1_epi8('\n');
     const uint8_t *rec = p;                 // start of the record being framed
     const uint8_t *nl[3];                   // its newlines so far
@@ -114,17 +139,45 @@ static const uint8_t *strip_records_avx2(const uint8_t *p, const uint8_t *end, c
             const uint8_t *e = q + __builtin_ctzll(m);
             m &= m - 1;
             if (have < 3) { nl[have++] = e; continue; }
-            if (!take_record(rec, nl[0], nl[1], nl[2], e, base_off, o, obase, ocap, olen)) { done = true; break; }
+            // ---- a complete record: rec .. e ----
+            const uint8_t *seq = nl[0] + 1, *sep = nl[1] + 1, *qual = nl[2] + 1;
+            size_t sl = (size_t)(nl[1] - seq), ql = (size_t)(e - qual);
+            if (sl && seq[sl - 1] == '\r') --sl;
+            if (ql && qual[ql - 1] == '\r') --ql;
+            if (olen + sl + 1 > ocap) { done = true; break; }
+            const uint64_t off = base_off + (uint64_t)(rec - o.origin);
+            if (*rec != '@' && all_blank(rec, e)) {
+                if (off < o.first_blank) o.first_blank = off;
+            } else {
+                if (off + 1 > o.last_nonblank) o.last_nonblank = off + 1;
+                if (*rec != '@') { if (off < o.bad_pos) o.bad_pos = off; }
+                if (*sep != '+') { const uint64_t so = base_off + (uint64_t)(sep - o.origin); if (so < o.bad_pos) o.bad_pos = so; }
+                if (sl != ql) { const uint64_t ho = base_off + (uint64_t)(nl[0] - o.origin); if (ho < o.len_bad_pos) o.len_bad_pos = ho; }
+                if (sl + 1 > WcOut::CAP) {              // a very long line: around the staging buffer
+                    wc_flush(w, true);
+                    memcpy(w.dst, seq, sl);
+                    w.dst[sl] = '\n';
+                    w.dst += sl + 1;
+                } else {
+                    if (w.fill + sl + 1 > WcOut::CAP) wc_flush(w, false);
+                    memcpy(w.buf + w.fill, seq, sl);
+                    w.buf[w.fill + sl] = '\n';
+                    w.fill += sl + 1;
+                }
+                olen += sl + 1;
+                o.bases += sl;
+                o.records += 1;
+            }
             rec = e + 1;
             have = 0;
             if (stop_at && rec >= stop_at) { done = true; break; }
         }
         q += 64;
     }
+    wc_flush(w, true);
+    _mm_sfence();
     o.out_len = olen;
-    if (done) return rec;
-    // the last < 64 bytes (and whatever of the open record lies before them): the generic loop, from the record start
-    return rec;
+    return rec;     // the caller's generic loop takes the last < 64 bytes (from the start of the open record)
 }
 #endif
 
