@@ -10,6 +10,7 @@
 // computes h1 and appends (hash, k-mer codes, position|strand) to the log when h1 <= threshold.
 // Order-independence of the sketch makes the unordered log exact.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "device_types.cuh"
 
@@ -19,8 +20,8 @@
 #ifndef FMIX_HI_B
 #define FMIX_HI_B 1
 #endif
-#ifndef MUL5_LEA
-#define MUL5_LEA 1
+#ifndef HASH_VAR_DEFAULT
+#define HASH_VAR_DEFAULT 0      // see murmur_kmer_h1_lut: which arithmetic form each step takes
 #endif
 
 namespace fb2 {
@@ -119,11 +120,12 @@ constexpr int HP_R32 = 8;               // copies of the 32-bit tables (low word
 struct HashConsts {                     // kernel parameters: values ptxas must not fold away
     uint32_t stride64, stride32, stride1;   // HP_R64 * 8, HP_R32 * 4, 8 (bytes between consecutive entries)
     uint32_t one;                           // 1: multiplier that keeps the table-word adds on the FMA pipe
+    uint32_t five;                          // 5: the multiplier of h * 5 + c in its IMAD form
     uint32_t log_reserve;                   // extra log slots a warp reserves per atomic, <= 31 (candidate-dense launches: 31)
 };
 struct MulLut {                         // per-lane shared-window byte addresses (copy l % R already applied)
     uint32_t c1_64, c2_64, c1_32, c2_32, t1;
-    uint32_t stride64, stride32, stride1, one;
+    uint32_t stride64, stride32, stride1, one, five;
     U2 add1, add2;                      // the +c of h * 5 + c
 };
 
@@ -142,15 +144,20 @@ __device__ __forceinline__ U2 add_one(U2 a, U2 b, uint32_t /*one*/) {   // a + b
     U2 t; t.lo = (uint32_t)s; t.hi = (uint32_t)(s >> 32);
     return t;
 }
-__device__ __forceinline__ U2 mul5add_r(U2 x, U2 c) {                     // x * 5 + c
-    const uint64_t v = ((uint64_t)x.hi << 32) | x.lo;
-#if MUL5_LEA
-    const uint64_t s = (v << 2) + v + (((uint64_t)c.hi << 32) | c.lo);       // LEA + LEA.HI.X (ALU) instead of IMAD.WIDE (4 FMA cycles)
-#else
-    const uint64_t s = v * 5ULL + (((uint64_t)c.hi << 32) | c.lo);
-#endif
-    U2 t; t.lo = (uint32_t)s; t.hi = (uint32_t)(s >> 32);
-    return t;
+// x * 5 + c.  LEA form: LEA + LEA.HI.X + the add (3 ALU + 1 FMA-pipe carry); IMAD form: IMAD.WIDE + IMAD (FMA pipe only,
+// 6 issue cycles there, two instructions fewer).  Which one wins depends on which integer pipe is the longer pole of the
+// whole body: chosen per use (hash_kernel's VAR).
+template <bool LEA>
+__device__ __forceinline__ U2 mul5add_r(U2 x, U2 c, uint32_t five) {
+    if (LEA) {
+        const uint64_t v = ((uint64_t)x.hi << 32) | x.lo;
+        const uint64_t s = (v << 2) + v + (((uint64_t)c.hi << 32) | c.lo);
+        U2 t; t.lo = (uint32_t)s; t.hi = (uint32_t)(s >> 32);
+        return t;
+    }
+    U2 w = mad_wide(x.lo, five, c);          // `five` is a kernel parameter: ptxas keeps the multiply instead of rewriting it as shifts
+    w.hi = mad_lo(x.hi, five, w.hi);
+    return w;
 }
 
 // (NB bases, 1..8, of the 32-bit codes word cw starting at byte BYTE0) * c.  Bits of cw above the
@@ -179,9 +186,13 @@ __device__ __forceinline__ U2 word_mul(uint32_t cw, const MulLut &L) {
     return r;
 }
 
-template <int K, bool SEED0>
+// VAR: bit 0 / bit 1 = h1 / h2 take the IMAD form of x * 5 + c; bits 2-3 / 4-5 = how many of the three ">> 1" of the
+// first / second fmix go through IMAD.HI (default 1 each).
+template <int K, bool SEED0, int VAR>
 __device__ __forceinline__ U2 murmur_kmer_h1_lut(U2 codes, U2 seed, const MulLut &L) {
     static_assert(K >= 1 && K <= 32, "k out of range");
+    constexpr bool LEA1 = !(VAR & 1), LEA2 = !(VAR & 2);
+    constexpr int NHI_A = ((VAR >> 2) & 3) == 0 ? FMIX_HI_A : ((VAR >> 2) & 3) - 1, NHI_B = ((VAR >> 4) & 3) == 0 ? FMIX_HI_B : ((VAR >> 4) & 3) - 1;
     constexpr int NB = K / 16, T = K & 15;
     U2 h1 = seed, h2 = seed;
     if (NB >= 1) {
@@ -189,18 +200,18 @@ __device__ __forceinline__ U2 murmur_kmer_h1_lut(U2 codes, U2 seed, const MulLut
         U2 k2 = word_mul<false, 2, 8>(codes.lo, L);
         k1 = rotl_u2<31>(k1); k1 = mul_u2<MM_C2>(k1);
         if (SEED0) { h1 = k1; } else { h1.lo ^= k1.lo; h1.hi ^= k1.hi; }
-        h1 = rotl_u2<27>(h1); if (!SEED0) h1 = add_one(h1, h2, L.one); h1 = mul5add_r(h1, L.add1);
+        h1 = rotl_u2<27>(h1); if (!SEED0) h1 = add_one(h1, h2, L.one); h1 = mul5add_r<LEA1>(h1, L.add1, L.five);
         k2 = rotl_u2<33>(k2); k2 = mul_u2<MM_C1>(k2);
         if (SEED0) { h2 = k2; } else { h2.lo ^= k2.lo; h2.hi ^= k2.hi; }
-        h2 = rotl_u2<31>(h2); h2 = add_one(h2, h1, L.one); h2 = mul5add_r(h2, L.add2);
+        h2 = rotl_u2<31>(h2); h2 = add_one(h2, h1, L.one); h2 = mul5add_r<LEA2>(h2, L.add2, L.five);
     }
     if (NB >= 2) {
         U2 k1 = word_mul<true, 0, 8>(codes.hi, L);
         U2 k2 = word_mul<false, 2, 8>(codes.hi, L);
         k1 = rotl_u2<31>(k1); k1 = mul_u2<MM_C2>(k1); h1.lo ^= k1.lo; h1.hi ^= k1.hi;
-        h1 = rotl_u2<27>(h1); h1 = add_one(h1, h2, L.one); h1 = mul5add_r(h1, L.add1);
+        h1 = rotl_u2<27>(h1); h1 = add_one(h1, h2, L.one); h1 = mul5add_r<LEA1>(h1, L.add1, L.five);
         k2 = rotl_u2<33>(k2); k2 = mul_u2<MM_C1>(k2); h2.lo ^= k2.lo; h2.hi ^= k2.hi;
-        h2 = rotl_u2<31>(h2); h2 = add_one(h2, h1, L.one); h2 = mul5add_r(h2, L.add2);
+        h2 = rotl_u2<31>(h2); h2 = add_one(h2, h1, L.one); h2 = mul5add_r<LEA2>(h2, L.add2, L.five);
     }
     // tail: 16-bit groups (k1-type first, then k2-type) of the next codes word; NB == 2 has none
     const uint32_t tword = (NB == 0) ? codes.lo : codes.hi;
@@ -218,7 +229,7 @@ __device__ __forceinline__ U2 murmur_kmer_h1_lut(U2 codes, U2 seed, const MulLut
     }
     h1.lo ^= (uint32_t)K; h2.lo ^= (uint32_t)K;
     h1 = add_one(h1, h2, L.one); h2 = add_one(h2, h1, L.one);
-    h1 = fmix_u2<FMIX_HI_A>(h1); h2 = fmix_u2<FMIX_HI_B>(h2);
+    h1 = fmix_u2<NHI_A>(h1); h2 = fmix_u2<NHI_B>(h2);
     return add_one(h1, h2, L.one);
 }
 
@@ -311,7 +322,7 @@ constexpr uint32_t HP_SMEM = HP_OFF_BUF + HP_WARPS * HP_NBUF * HP_BUF;
 static_assert(HP_SMEM <= 232448u, "hash kernel shared memory exceeds 227 KB");
 static_assert(HP_BUF % 16u == 0, "TMA size granularity");
 
-template <int K, bool SEED0>
+template <int K, bool SEED0, int VAR>
 __global__ void __launch_bounds__(HP_WARPS * 32, 1)
 hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r starts at SYM_FRONT + r * region_stride
             ChunkGeom g, uint32_t r0, uint32_t n_regions, // regions [r0, r0 + n_regions) of this launch
@@ -357,7 +368,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
     L.c1_32 = smem_u32(hp_smem + HP_OFF_C1_32) + (lane % HP_R32) * 4u;
     L.c2_32 = smem_u32(hp_smem + HP_OFF_C2_32) + (lane % HP_R32) * 4u;
     L.t1 = smem_u32(hp_smem + HP_OFF_T1);
-    L.stride64 = hc.stride64; L.stride32 = hc.stride32; L.stride1 = hc.stride1; L.one = hc.one;
+    L.stride64 = hc.stride64; L.stride32 = hc.stride32; L.stride1 = hc.stride1; L.one = hc.one; L.five = hc.five;
     L.add1.lo = 0x52dce729u; L.add1.hi = 0u; L.add2.lo = 0x38495ab5u; L.add2.hi = 0u;
 
     const int k = K > 0 ? K : k_rt;
@@ -493,7 +504,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
                 const bool is_rc = (((uint64_t)r.A.hi << 32) | r.A.lo) >= (((uint64_t)r.B.hi << 32) | r.B.lo);
                 U2 codes; codes.lo = is_rc ? r.B.lo : r.A.lo; codes.hi = is_rc ? r.B.hi : r.A.hi;
                 U2 h;
-                if (K > 0) h = murmur_kmer_h1_lut<(K > 0 ? K : 1), SEED0>(codes, seed2, L);
+                if (K > 0) h = murmur_kmer_h1_lut<(K > 0 ? K : 1), SEED0, VAR>(codes, seed2, L);
                 else {
                     const uint64_t hv = murmur_kmer_h1<0>(((uint64_t)codes.hi << 32) | codes.lo, k, seed);
                     h.lo = (uint32_t)hv; h.hi = (uint32_t)(hv >> 32);
@@ -661,7 +672,7 @@ __global__ void push_hash_kernel(const uint8_t *__restrict__ bytes, const uint32
 }
 __global__ void push_commit_kernel(LaunchSlot *slot, uint32_t n) { slot->launch_kmers += n; }
 
-template <int K, bool SEED0>
+template <int K, bool SEED0, int VAR>
 static void launch_hash_ks(uint32_t r0, uint32_t n_regions, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
                            const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
                            int k, uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
@@ -670,25 +681,33 @@ static void launch_hash_ks(uint32_t r0, uint32_t n_regions, const uint8_t *symbu
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!sms[dev]) {
-        cudaFuncSetAttribute(hash_kernel<K, SEED0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HP_SMEM);
+        cudaFuncSetAttribute(hash_kernel<K, SEED0, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HP_SMEM);
         int n = 148;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         sms[dev] = n > 0 ? n : 148;
     }
     HashConsts hc;
-    hc.stride64 = HP_R64 * 8u; hc.stride32 = HP_R32 * 4u; hc.stride1 = 8u; hc.one = 1u;
+    hc.stride64 = HP_R64 * 8u; hc.stride32 = HP_R32 * 4u; hc.stride1 = 8u; hc.one = 1u; hc.five = 5u;
     hc.log_reserve = log_reserve;
     const uint64_t items_ub = (uint64_t)n_regions * ((g.st_bytes + HP_SLICE - 1u) / HP_SLICE);   // the device cuts it at the largest region
     const uint32_t ctas = (uint32_t)std::min<uint64_t>((uint64_t)sms[dev], (items_ub + HP_WARPS - 1) / HP_WARPS);
-    hash_kernel<K, SEED0><<<ctas, HP_WARPS * 32, HP_SMEM, stream>>>(symbuf, g, r0, n_regions, region_count, carry, ord_base, st,
+    hash_kernel<K, SEED0, VAR><<<ctas, HP_WARPS * 32, HP_SMEM, stream>>>(symbuf, g, r0, n_regions, region_count, carry, ord_base, st,
                                                                    slot, log, k, seed, hc);
 }
 template <int K>
 static void launch_hash_k(uint32_t r0, uint32_t n_regions, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
                           const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
                           int k, uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
-    if (seed == 0 && K > 0) launch_hash_ks<K, true>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
-    else launch_hash_ks<K, false>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
+#ifdef FB2_HASH_VARIANTS   // A/B builds: FB2_HASH_VAR picks the arithmetic variant of the k = 21 / seed 0 kernel at run time
+    if (seed == 0 && K == 21) {
+        static const int var = getenv("FB2_HASH_VAR") ? atoi(getenv("FB2_HASH_VAR")) : HASH_VAR_DEFAULT;
+#define FB2_V(V) case V: launch_hash_ks<K, true, V>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream); return;
+        switch (var) { FB2_V(0) FB2_V(1) FB2_V(2) FB2_V(3) FB2_V(12) FB2_V(15) FB2_V(60) FB2_V(63) default: break; }
+#undef FB2_V
+    }
+#endif
+    if (seed == 0 && K > 0) launch_hash_ks<K, true, HASH_VAR_DEFAULT>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    else launch_hash_ks<K, false, HASH_VAR_DEFAULT>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
 }
 // Hash the symbol regions [r0, r1) of a chunk.
 void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t r0, uint32_t r1, const uint32_t *region_count,

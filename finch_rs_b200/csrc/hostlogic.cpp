@@ -11,6 +11,7 @@
 // <= kmers_to_sketch entries.  Written independently of oracle/ (which is test infrastructure).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -189,12 +190,19 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
 // feed the raw bytes, finish the sketch.  gzip input (needletail sniffs the 1f 8b magic, lib.rs:60 via
 // parse_fastx_reader) is inflated on the host by this worker thread, concatenated members included;
 // bz2 / xz stay unsupported (no headers for them in this image) and are reported by the engine.
+// FB2_TRACE_FILES=1: where the workers of sketch_files spend their time (summed over files, printed per call)
+static std::atomic<uint64_t> g_ns_reset{0}, g_ns_read{0}, g_ns_feed{0}, g_ns_finish{0}, g_n_files{0};
+static inline uint64_t now_ns() {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_t *buf, size_t piece,
                            const fb2_params *p, const fb2_filter *f, fb2_result *out) {
     const bool is_stdin = strcmp(path, "-") == 0;  // lib.rs:38-40
     FILE *fp = is_stdin ? stdin : fopen(path, "rb");
     if (!fp) return fb2_fail(FB2_EIO, std::string(path) + ": No such file or directory");
+    uint64_t t0 = now_ns();
     int rc = reuse ? fb2_sketcher_reset(s) : FB2_OK;
+    g_ns_reset += now_ns() - t0;
     if (p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
     bool any = false;
     // sniff the first two bytes
@@ -237,16 +245,25 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
         size_t fill = nmagic;
         if (nmagic) memcpy(buf, magic, nmagic);
         while (rc == FB2_OK) {
+            t0 = now_ns();
             const size_t got = fread(buf + fill, 1, piece - fill, fp) + fill;
+            const uint64_t t1 = now_ns();
+            g_ns_read += t1 - t0;
             fill = 0;
             if (got) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, got, 0); }
+            g_ns_feed += now_ns() - t1;
             if (got < piece) break;
         }
     }
     if (!is_stdin) fclose(fp);
     if (rc == FB2_OK && !any) rc = fb2_fail(FB2_EEMPTY, std::string(path) + ": empty input");
+    t0 = now_ns();
     if (rc == FB2_OK) rc = fb2_sketcher_feed_fastx(s, nullptr, 0, 1);
+    g_ns_feed += now_ns() - t0;
+    t0 = now_ns();
     if (rc == FB2_OK) rc = finish_sketch(s, path, p, f, out);
+    g_ns_finish += now_ns() - t0;
+    g_n_files += 1;
     return rc;
 }
 
@@ -379,6 +396,13 @@ static int sketch_files_on(const char *const *paths, size_t n, const fb2_params 
     }
     if (th.size() == 1) { th[0].join(); }
     else for (auto &t : th) t.join();
+    if (getenv("FB2_TRACE_FILES")) {
+        const double nf = (double)std::max<uint64_t>(1, g_n_files.load());
+        fprintf(stderr, "sketch_files: %llu files, %zu threads; per file (worker time, us): reset %.0f  read %.0f  feed %.0f  finish %.0f\n",
+                (unsigned long long)g_n_files.load(), th.size(), g_ns_reset.load() / nf / 1e3, g_ns_read.load() / nf / 1e3,
+                g_ns_feed.load() / nf / 1e3, g_ns_finish.load() / nf / 1e3);
+        g_ns_reset = 0; g_ns_read = 0; g_ns_feed = 0; g_ns_finish = 0; g_n_files = 0;
+    }
     const int rc = first_rc.load();
     if (rc != FB2_OK) {
         for (size_t i = 0; i < n; ++i) fb2_result_free(&outs[i]);

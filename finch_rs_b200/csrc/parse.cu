@@ -651,9 +651,17 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
                         if (j >= 0) { const uint32_t q = s_nl[j]; return (b + q) | (rawb[(int)q - 1] == '\r' ? 0x80000000u : 0u); }
                         return c_nl[3 + j];
                     };
-                    const uint32_t gidx = nl_before + i;
-                    if (gidx < 3u) seam_st->first[gidx] = nlq((int)i);
-                    else if (ph == 3u) lbad = min(lbad, fastq_len_check(nlq((int)i - 3), nlq((int)i - 2), nlq((int)i - 1), nlq((int)i)));
+                    if (i >= 3u) {   // the usual case: the record's four newlines are all in this batch (klen is the quality's length)
+                        if (ph == 3u) {
+                            const uint32_t e1 = s_nl[i - 2], e0 = s_nl[i - 3];
+                            const uint32_t ls = e1 - e0 - 1u - (rawb[(int)e1 - 1] == '\r' ? 1u : 0u);
+                            if (ls != klen) lbad = min(lbad, b + e0);
+                        }
+                    } else {         // the first three pieces: newlines carried from earlier batches, or left to the seam check
+                        const uint32_t gidx = nl_before + i;
+                        if (gidx < 3u) seam_st->first[gidx] = nlq((int)i);
+                        else if (ph == 3u) lbad = min(lbad, fastq_len_check(nlq((int)i - 3), nlq((int)i - 2), nlq((int)i - 1), nlq((int)i)));
+                    }
                 }
             } else {  // MODE_FASTA
                 const bool hdr = line_start ? (start < blen && rawb[start] == '>') : ((state & 1u) != 0u);

@@ -1,13 +1,11 @@
-"""C2-shaped resident run, feed vs sketch() time split (where the end-of-stream cost goes)."""
+"""C2-shaped resident run, feed vs sketch() time split (where the end-of-stream cost goes); also the ncu target."""
 import sys, time
-sys.path.insert(0, ".")
+sys.path.insert(0, "."); sys.path.insert(0, "tools")
 import numpy as np, torch
 import finch_rs_b200 as fb
-sys.path.insert(0, "tools"); import synth
-import bench
-n_reads = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
-genome = synth.synth_genome(bench.GENOME_LEN, 2)
-buf, need, nbases = synth.synth_fastq_parallel(genome, n_reads, 150, 0.005, 3)
+import workloads as W
+n_reads = int(float(sys.argv[1])) if len(sys.argv) > 1 else W.C2_READS
+buf, need, nbases = W.c2_fastq(0, n_reads)
 d = torch.from_numpy(buf).cuda()
 sp = fb.SketchParams.from_cli("mash", n_hashes=1000, kmer_length=21, filters_enabled=True)
 fp = fb.FilterParams(True, (None, None), 0.21, 0.1)

@@ -3,12 +3,13 @@
 import collections, re, subprocess, sys
 obj = sys.argv[1]
 k = sys.argv[2] if len(sys.argv) > 2 else "21"
+var = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3].isdigit() else "0"
 out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
 # split per function
 funcs = re.split(r"\n\s*Function : ", out)
 for f in funcs:
     name = f.split("\n", 1)[0]
-    if f"hash_kernelILi{k}ELb1E" not in name:
+    if f"hash_kernelILi{k}ELb1ELi{var}E" not in name:
         continue
     ins = []
     for line in f.split("\n"):
@@ -34,6 +35,6 @@ for f in funcs:
         alu = sum(v for k_, v in h.items() if k_ in ("LOP3", "SHF", "ISETP", "IADD3", "LEA", "SEL", "VIADD", "PRMT", "PLOP3", "IABS", "FLO", "POPC", "MOV", "VOTE"))
         fma = sum(v for k_, v in h.items() if k_ in ("IMAD", "FFMA", "FMUL", "FADD"))
         print("body len", len(body), "ALU", alu, "FMA", fma, dict(h.most_common()))
-        if len(sys.argv) > 3:
+        if len(sys.argv) > 4:
             for ad, t in body:
                 print(f"{ad:05x} {t}")
