@@ -37,6 +37,22 @@ extern "C" const char *fb2_last_error(void) { return g_err.c_str(); }
     } while (0)
 #define TRY(x) do { int r_ = (x); if (r_ != FB2_OK) return r_; } while (0)
 
+// Every entry point works on its handle's device and leaves the calling thread's current device as it found it
+// (a caller that mixes this library with other CUDA code, e.g. torch, must not find its device changed).
+struct DeviceScope {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (dev >= 0 && dev != prev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceScope() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+#define ON_DEVICE(dev) DeviceScope dev_scope_(dev); if (!dev_scope_.ok) return fb2_fail(FB2_ECUDA, "cudaSetDevice failed")
+
 static size_t env_size(const char *name, size_t dflt) {
     const char *v = getenv(name);
     if (!v || !*v) return dflt;
@@ -319,7 +335,7 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
     int dev = p->device;
     if (dev < 0) { CU(cudaGetDevice(&dev)); }
     if (dev >= ndev) return fb2_fail(FB2_EINVAL, "device ordinal out of range");
-    CU(cudaSetDevice(dev));
+    ON_DEVICE(dev);
 
     fb2_sketcher *s = new fb2_sketcher();
     s->prm = *p; s->device = dev; s->k = p->kmer_length;
@@ -385,7 +401,7 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
 
 extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     if (!s) return;
-    cudaSetDevice(s->device);
+    DeviceScope dev_scope_(s->device);
     if (s->st) cudaStreamSynchronize(s->st);
     if (s->copy_st) cudaStreamSynchronize(s->copy_st);
     if (s->st2) cudaStreamSynchronize(s->st2);
@@ -423,7 +439,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
 
 extern "C" int fb2_sketcher_reset(fb2_sketcher *s) {
     if (!s) return fb2_fail(FB2_EINVAL, "null handle");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     CU(cudaStreamSynchronize(s->st));
     CU(cudaStreamSynchronize(s->copy_st));
     CU(cudaStreamSynchronize(s->st2));
@@ -938,7 +954,7 @@ static int flush_all(fb2_sketcher *s) {
 // ---- SketchScheme::process ------------------------------------------------------------------------
 extern "C" int fb2_sketcher_process(fb2_sketcher *s, const uint8_t *seq, size_t len) {
     if (!s || (!seq && len)) return fb2_fail(FB2_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     if (s->stream_open) return fb2_fail(FB2_EINVAL, "process() while a FASTX stream is open");
     TRY(flush_push(s));
     TRY(ensure_stage(s));
@@ -963,7 +979,7 @@ extern "C" int fb2_sketcher_process(fb2_sketcher *s, const uint8_t *seq, size_t 
 extern "C" int fb2_sketcher_push(fb2_sketcher *s, const uint8_t *kmer, size_t k, uint8_t extra_count) {
     if (!s || (!kmer && k)) return fb2_fail(FB2_EINVAL, "null argument");
     if (k > 255) return fb2_fail(FB2_EINVAL, "k-mer longer than 255 bytes");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     TRY(flush_stage(s));
     s->push_bytes.insert(s->push_bytes.end(), kmer, kmer + k);
     s->push_offs.push_back((uint32_t)s->push_bytes.size());
@@ -1251,7 +1267,7 @@ static int end_stream(fb2_sketcher *s) {
 
 extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, size_t len, int final) {
     if (!s || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     if (!s->stream_open) {
         // format sniffing looks at two bytes (compressed-input magic): a shorter first piece waits for the next one
         const size_t have = s->presniff.size();
@@ -1301,7 +1317,7 @@ extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, si
 
 extern "C" int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev, size_t len, int final) {
     if (!s || (!dev && len)) return fb2_fail(FB2_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     if (len) {
         if (!s->stream_open) {
             uint8_t first[2] = {0, 0};
@@ -1359,7 +1375,7 @@ int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32
                              const uint8_t *tail_syms /* halo symbols, may be null = all breaks */, uint64_t raw_base,
                              uint64_t ord_base) {
     if (!s || s->stream_open) return fb2_fail(FB2_EINVAL, "begin_range: bad handle state");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     s->format = format;
     TRY(flush_all(s));
     TRY(pull_state(s));
@@ -1383,7 +1399,7 @@ int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32
 // Reports the parser state the next range must have started from, and the first record errors seen (~0: none).
 int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_byte, uint64_t *first_bad_pos, uint64_t *len_bad_pos) {
     if (!s) return fb2_fail(FB2_EINVAL, "null handle");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     TRY(flush_stage(s));
     TRY(settle_all(s));
     TRY(pull_state(s));
@@ -1405,6 +1421,7 @@ int fb2_sketcher_merge_from(fb2_sketcher *dst, fb2_sketcher *src) {
     if (dst->k != src->k || dst->scaled != src->scaled || dst->size != src->size || dst->prm.hash_seed != src->prm.hash_seed ||
         (dst->scaled && dst->max_hash != src->max_hash))
         return fb2_fail(FB2_EINVAL, "merge: sketchers differ in parameters");
+    DeviceScope dev_scope_(dst->device);      // restores the caller's device on every return path
     CU(cudaSetDevice(src->device));
     TRY(flush_all(src));
     TRY(pull_state(src));
@@ -1484,7 +1501,7 @@ extern "C" int fb2_sketcher_format(fb2_sketcher *s, int32_t *format) {
 // ---- totals / result -------------------------------------------------------------------------------
 extern "C" int fb2_sketcher_totals(fb2_sketcher *s, uint64_t *total_bases, uint64_t *total_kmers) {
     if (!s) return fb2_fail(FB2_EINVAL, "null handle");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     TRY(flush_all(s));
     TRY(pull_state(s));
     if (total_bases) *total_bases = s->h_carry->total_bases + s->lines_bases;
@@ -1631,7 +1648,7 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
 
 extern "C" int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out) {
     if (!s || !out) return fb2_fail(FB2_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     memset(out, 0, sizeof(*out));
     TRY(flush_all(s));
     uint32_t keep = 0;
@@ -1644,7 +1661,7 @@ extern "C" int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out) {
 extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_params *p, const fb2_filter *f,
                                    fb2_result *out) {
     if (!s || !p || !f || !out) return fb2_fail(FB2_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     memset(out, 0, sizeof(*out));
     TRY(flush_all(s));
     uint32_t keep = 0;
@@ -1684,7 +1701,7 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
 extern "C" int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint32_t *counts, size_t counts_cap,
                                           uint8_t *sym, size_t sym_cap) {
     if (!s || !geom7) return fb2_fail(FB2_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     CU(cudaStreamSynchronize(s->st));
     const int par = s->par ^ 1;   // the chunk that ran last
     const ChunkGeom g = s->last_geom;
@@ -1699,7 +1716,7 @@ extern "C" int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint
 // Test hook: add (add_count, add_extra) to the 64-bit totals the table keeps for `hash` (which must be present).
 extern "C" int fb2_sketcher_debug_bump(fb2_sketcher *s, uint64_t hash, uint64_t add_count, uint64_t add_extra) {
     if (!s) return fb2_fail(FB2_EINVAL, "null handle");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     TRY(flush_all(s));
     TRY(pull_state(s));
     unsigned int *found = &((SketchState *)s->d_state.p)->gather_count;   // scratch word of the state block
@@ -1711,7 +1728,7 @@ extern "C" int fb2_sketcher_debug_bump(fb2_sketcher *s, uint64_t hash, uint64_t 
 
 extern "C" int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out) {
     if (!s || !out) return fb2_fail(FB2_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     timing_resolve(s);
     *out = s->stats;
     return FB2_OK;
@@ -1734,7 +1751,7 @@ static int dist_common(const uint64_t *hashes, const uint32_t *lens, size_t n_sk
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
-    if (device >= 0) CU(cudaSetDevice(device));
+    if (device >= 0) CU(cudaSetDevice(device));   // (the callers hold a DeviceScope)
     TRY(d_h.ensure(std::max<size_t>(8, n_sk * stride * 8)));
     TRY(d_l.ensure(std::max<size_t>(4, n_sk * 4)));
     CU(cudaMemcpy(d_h.p, hashes, n_sk * stride * 8, cudaMemcpyHostToDevice));
@@ -1749,6 +1766,7 @@ extern "C" int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size
     for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
     for (size_t i = 0; i < n_pairs; ++i)
         if (q_idx[i] >= n_sk || r_idx[i] >= n_sk) return fb2_fail(FB2_EINVAL, "pair index out of range");
+    DeviceScope dev_scope_(-1);   // dist_common may select `device`: the caller's device comes back on return
     DevBuf d_h, d_l, d_q, d_r, d_o;
     int rc = dist_common(hashes, lens, n_sk, stride, device, d_h, d_l);
     if (rc == FB2_OK && n_pairs) {
@@ -1777,6 +1795,7 @@ extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, 
     for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
     const uint64_t n_pairs = (uint64_t)(q1 - q0) * n_sk;
     if (n_pairs && !out) return fb2_fail(FB2_EINVAL, "null output");
+    DeviceScope dev_scope_(-1);   // dist_common may select `device`: the caller's device comes back on return
     DevBuf d_h, d_l, d_o[2];
     fb2_pair_out *h_pin[2] = {nullptr, nullptr};
     cudaStream_t st_k = nullptr, st_c = nullptr;
@@ -2002,6 +2021,7 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
+    DeviceScope dev_scope_(-1);   // the single-GPU path runs on this thread and selects its device
     std::vector<int> devs;
     if (ngpus == 1 || ndev == 1) {
         int d = device;
@@ -2060,8 +2080,10 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
         for (size_t g = 0; g < G; ++g) th.emplace_back(work, g);
         for (auto &t : th) t.join();
     }
-    for (size_t g = 0; g < G; ++g) { cudaSetDevice(devs[g]); d_h[g].release(); d_l[g].release(); }
-    if (device >= 0 && device < ndev) cudaSetDevice(device);
+    {
+        DeviceScope restore(-1);
+        for (size_t g = 0; g < G; ++g) { cudaSetDevice(devs[g]); d_h[g].release(); d_l[g].release(); }
+    }
     for (size_t g = 0; g < G; ++g) if (rcs[g] != FB2_OK) return fb2_fail(rcs[g], msgs[g]);
     uint64_t total = 0;
     double kmax = 0.0;

@@ -548,6 +548,8 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
     __shared__ uint16_t s_first[PB_BYTES / 16 + 2];
     __shared__ uint32_t s_flag[2];   // [0] fast path declined, [1] FASTA: state after the batch
     __shared__ uint32_t c_nl[3];     // FASTQ: the last three newlines of this supertile before the current batch
+    __shared__ uint16_t s_bw[PB_BYTES / 16 + 8];   // output words that need the general (multi-entry) path
+    __shared__ uint32_t s_nbw;
     const int tid = threadIdx.x;
     lut[tid] = classify_byte((uint8_t)tid);
     if (tid < 2) s_flag[tid] = 0;
@@ -591,6 +593,7 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
             nlm[p] = r.nl;
         }
         if (tid == 0) {   // the two bytes in front of the batch
+            s_nbw = 0;
             rawb[-1] = (uint8_t)(b >= 1u ? raw[b - 1] : cprev1);
             rawb[-2] = (uint8_t)(b >= 2u ? raw[b - 2] : (b == 1u ? cprev1 : cprev2));
         }
@@ -719,15 +722,15 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
         // ---- 4. aligned output words ------------------------------------------------------------
         const uint32_t W = (a + T + 15u) >> 4;
         uint8_t *obase = region + (out_off - a);
+        // Pass A: every word that comes out of ONE line whole (9 of 10 words of 150 bp reads): no masks, no merging --
+        // unaligned 16-byte read, SIMD-in-register codes, one aligned store.  The others (words holding a line end, the
+        // ragged first / last word of the batch, anything but ACGTacgt) are only LISTED here and done in pass B by as
+        // few warps as it takes: inside a warp they would drag all 32 lanes through the general path.
         for (uint32_t w = tid; w < W; w += TILE_THREADS) {
             const uint32_t f0 = w == 0u ? a : 0u;
-            uint32_t filled = f0;
-            uint32_t pos = 16u * w + filled - a;               // output position within the batch
-            uint32_t i = s_first[w];
-            uint32_t d = pos - (uint32_t)e_out[i];
-            // Common case (9 of 10 words of 150 bp reads): the whole word comes out of ONE line.  No masks, no merging:
-            // unaligned 16-byte read, SIMD-in-register codes, one aligned store.  Anything but ACGTacgt in it takes the
-            // general path below.
+            const uint32_t pos = 16u * w + f0 - a;             // output position within the batch
+            const uint32_t i = s_first[w];
+            const uint32_t d = pos - (uint32_t)e_out[i];
             if (f0 == 0u && d + 16u <= ((uint32_t)e_len[i] & 0x7FFFu)) {
                 const uint32_t A = 16u + (uint32_t)e_src[i] + d;                  // s_rawbuf offset of output byte 0
                 const uint32_t wi = A >> 2, sel = 0x3210u + 0x1111u * (A & 3u);
@@ -748,6 +751,18 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
                     continue;
                 }
             }
+            s_bw[atomicAdd(&s_nbw, 1u)] = (uint16_t)w;
+        }
+        __syncthreads();
+        // Pass B: the listed words, densely over the threads
+        const uint32_t nbw = s_nbw;
+        for (uint32_t idx = tid; idx < nbw; idx += TILE_THREADS) {
+            const uint32_t w = s_bw[idx];
+            const uint32_t f0 = w == 0u ? a : 0u;
+            uint32_t filled = f0;
+            uint32_t pos = 16u * w + filled - a;               // output position within the batch
+            uint32_t i = s_first[w];
+            uint32_t d = pos - (uint32_t)e_out[i];
             uint64_t alo = 0, ahi = 0;
             while (filled < 16u && pos < T) {
                 const uint32_t L = e_len[i], len = L & 0x7FFFu, brk = L >> 15;

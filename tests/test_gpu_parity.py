@@ -599,6 +599,29 @@ def test_one_stream_split_over_gpus(fb, synth, oracle, monkeypatch, fmt, kind, s
             assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
 
 
+def test_library_leaves_the_callers_device_alone(fb, synth, monkeypatch):
+    """Multi-GPU calls work on several devices from several threads; the calling thread's current CUDA device must
+    be what it was (a caller mixing this library with torch would otherwise allocate on the wrong GPU)."""
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+    ndev = fb.lib().fb2_device_count()
+    monkeypatch.setenv("FB2_MULTI_OVERSUBSCRIBE", "1")
+    monkeypatch.setenv("FB2_MIN_RANGE_KB", "64")
+    data = synth.synth_fasta(900_000, n_records=2, line_width=70, seed=3).tobytes()
+    sp = fb.SketchParams.mash(500, 500, True, 21, 0)
+    for want in range(min(ndev, 2)):
+        assert rt.cudaSetDevice(want) == 0
+        fb.sketch_stream_multi(data, "x", sp, fb.FilterParams(False), 3)
+        fb.dist_all_pairs_cut(np.sort(np.random.default_rng(1).integers(0, 2**60, size=(40, 50), dtype=np.uint64), axis=1),
+                              np.full(40, 50, np.uint32), 21, 0.5, ngpus=0)
+        with fb.SketchParams.mash(10, 10, True, 5, 0, device=ndev - 1).create_sketcher() as s:
+            s.feed_fastx(b">a\nACGTACGTAC\n", final=True)
+            s.to_arrays()
+        cur = C.c_int(-1)
+        assert rt.cudaGetDevice(C.byref(cur)) == 0 and cur.value == want
+    rt.cudaSetDevice(0)
+
+
 def test_split_stream_reports_record_errors(fb, oracle, monkeypatch):
     monkeypatch.setenv("FB2_MULTI_OVERSUBSCRIBE", "1")
     monkeypatch.setenv("FB2_MIN_RANGE_KB", "64")
