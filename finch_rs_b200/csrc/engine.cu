@@ -8,6 +8,7 @@
 //   total_kmers        ->  host counter fed by the hash kernel's per-launch count
 //   total_bases        ->  ParseCarry::total_bases (FASTX) + host sum (process())
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -1663,9 +1664,14 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
     if (!s || !p || !f || !out) return fb2_fail(FB2_EINVAL, "null argument");
     ON_DEVICE(s->device);
     memset(out, 0, sizeof(*out));
+    const bool trace = getenv("FB2_TRACE_SKETCH") != nullptr;   // where the end-of-stream time goes (stderr)
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0.0;
     TRY(flush_all(s));
+    const double t1 = trace ? now() : 0.0;
     uint32_t keep = 0;
     TRY(export_sorted(s, &keep));
+    const double t2 = trace ? now() : 0.0;
     fb2_filter ff = *f;
     if (ff.filter_on < 0) {  // lib.rs:71-76
         if (s->format == FB2_FORMAT_FASTA) ff.filter_on = 0;
@@ -1682,10 +1688,13 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
         CU(cudaMemcpyAsync(hx, s->out_ext.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaStreamSynchronize(s->st));
         s->stats.d2h_bytes += (size_t)keep * 8;
+        const double t3 = trace ? now() : 0.0;
         TRY(fb2_filter_select(hc, hx, keep, &ff, s->format, sel));
+        if (trace) fprintf(stderr, "sketch(): counts D2H %.0f us, host filter %.0f us (%u entries)\n", t3 - t2, now() - t3, keep);
         m = (uint32_t)sel.size();
         idx = sel.data();
     }
+    const double t4 = trace ? now() : 0.0;
     if (p->kind == FB2_KIND_MASH) {  // process_post_filter (mod.rs:115-128)
         if (m > p->final_size) m = (uint32_t)p->final_size;
         if (!p->no_strict && m < p->final_size)
@@ -1693,6 +1702,8 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
                                              ") to sketch");
     }
     const int rc = collect_rows(s, idx, m, out);
+    if (trace) fprintf(stderr, "sketch(): flush/settle %.0f us, sort+export %.0f us, filter stage %.0f us, collect %.0f us\n",
+                       t1 - t0, t2 - t1, t4 - t2, now() - t4);
     if (rc == FB2_OK) out->filters = ff;
     return rc;
 }
