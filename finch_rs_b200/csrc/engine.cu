@@ -1518,7 +1518,7 @@ extern "C" void fb2_result_free(fb2_result *r) {
 
 // hostlogic.cpp
 int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, fb2_filter *f, int format,
-                      std::vector<uint32_t> &keep);
+                      std::vector<uint32_t> &keep, size_t limit);
 
 // Pinned host staging for result read-back (grown on demand).
 // Copy `n` bytes with a few host threads (the result slabs are large; one memcpy thread cannot keep
@@ -1689,7 +1689,7 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
         CU(cudaStreamSynchronize(s->st));
         s->stats.d2h_bytes += (size_t)keep * 8;
         const double t3 = trace ? now() : 0.0;
-        TRY(fb2_filter_select(hc, hx, keep, &ff, s->format, sel));
+        TRY(fb2_filter_select(hc, hx, keep, &ff, s->format, sel, p->kind == FB2_KIND_MASH ? (size_t)p->final_size : SIZE_MAX));
         if (trace) fprintf(stderr, "sketch(): counts D2H %.0f us, host filter %.0f us (%u entries)\n", t3 - t2, now() - t3, keep);
         m = (uint32_t)sel.size();
         idx = sel.data();

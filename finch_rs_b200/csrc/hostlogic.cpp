@@ -54,16 +54,21 @@ static void compact(fb2_result *r, const std::vector<uint8_t> &keep) {
     r->n = m;
 }
 
+static uint32_t threshold_from_hist(const std::vector<uint64_t> &hist, double filter_level);
 extern "C" uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n, double filter_level) {
     // histogram of counts: hist[c-1] = number of k-mers seen c times (statistics.rs:30-47)
     uint32_t max_count = 0;
     for (size_t i = 0; i < n; ++i) max_count = std::max(max_count, counts[i]);
     std::vector<uint64_t> hist(max_count, 0);
     for (size_t i = 0; i < n; ++i) if (counts[i]) hist[counts[i] - 1]++;
+    return threshold_from_hist(hist, filter_level);
+}
+
+// guess_filter_threshold (filtering.rs:154-195) from the histogram of counts: hist[c-1] = number of k-mers seen c times.
+static uint32_t threshold_from_hist(const std::vector<uint64_t> &hist, double filter_level) {
     uint64_t total = 0;
     for (size_t c = 0; c < hist.size(); ++c) total += (uint64_t)(c + 1) * hist[c];
     const double cutoff_amt = filter_level * (double)total;
-    // coverage index below which `filter_level` of the weighted data lies
     size_t wgt_cutoff = 0;
     uint64_t cum = 0;
     for (size_t c = 0; c < hist.size(); ++c) {
@@ -72,7 +77,6 @@ extern "C" uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n,
         ++wgt_cutoff;
     }
     if (wgt_cutoff == 0) return 1;
-    // minimum of the sliding window sum left of the cutoff (ties: the right-most window)
     const size_t win = std::max<size_t>(1, wgt_cutoff / 20);
     uint64_t sum = 0;
     for (size_t c = 0; c < win; ++c) sum += hist[c];
@@ -86,47 +90,54 @@ extern "C" uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n,
     return (uint32_t)lowest_idx + 1;
 }
 
-// Core of FilterParams::filter_counts on bare (count, extra) columns: writes the indices that
-// survive, ascending, and updates `f` like the reference (filter_on resolved, abun_low raised).
+// Core of FilterParams::filter_counts on bare (count, extra) columns: writes the indices that survive, ascending,
+// and updates `f` like the reference (filter_on resolved, abun_low raised).  `limit`: stop after that many survivors
+// (the caller truncates to final_size anyway, mod.rs:115-128; when fewer survive, all of them are returned, so the
+// "too few" count is exact).  Two light passes over the columns: strand decision + histogram, then the abundance cut.
 int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, fb2_filter *f, int format,
-                      std::vector<uint32_t> &keep) {
+                      std::vector<uint32_t> &keep, size_t limit) {
     if (f->filter_on < 0) {  // lib.rs:71-76
         if (format == FB2_FORMAT_FASTA) f->filter_on = 0;
         else if (format == FB2_FORMAT_FASTQ) f->filter_on = 1;
         else return fb2_fail(FB2_EEMPTY, "Should have got a type");
     }
-    keep.resize(n);
-    for (size_t i = 0; i < n; ++i) keep[i] = (uint32_t)i;
+    keep.clear();
     const bool on = f->filter_on == 1;
-    if (on && f->strand_filter > 0.0) {  // filter_strands (filtering.rs:413-432)
-        size_t m = 0;
-        for (size_t j = 0; j < keep.size(); ++j) {
-            const uint32_t i = keep[j], c = counts[i];
-            bool ok = true;
-            if (c >= 16) {  // fewer observations are too noisy to call an adapter
+    const bool strand = on && f->strand_filter > 0.0, err = on && f->err_filter > 0.0;
+    static thread_local std::vector<uint8_t> ok;           // strand survivors (reused across calls)
+    static thread_local std::vector<uint64_t> hist;
+    if (strand) ok.resize(n);
+    if (err) hist.assign(1024, 0);
+    if (strand || err) {
+        const double cut = f->strand_filter;
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t c = counts[i];
+            bool pass = true;
+            if (strand && c >= 16) {  // filter_strands (filtering.rs:413-432): fewer observations are too noisy to call an adapter
                 const uint32_t lowest = std::min(extras[i], c - extras[i]);
-                ok = ((double)lowest / (double)c) >= f->strand_filter;
+                pass = ((double)lowest / (double)c) >= cut;
             }
-            if (ok) keep[m++] = i;
+            if (strand) ok[i] = pass;
+            if (err && pass && c) {   // hist of what is left (statistics.rs:30-47; filtering.rs:68-79)
+                if (c > hist.size()) hist.resize(std::max<size_t>(c, hist.size() * 2), 0);
+                hist[c - 1]++;
+            }
         }
-        keep.resize(m);
     }
-    if (on && f->err_filter > 0.0) {     // guess_filter_threshold on what is left (filtering.rs:68-79)
-        std::vector<uint32_t> c(keep.size());
-        for (size_t j = 0; j < keep.size(); ++j) c[j] = counts[keep[j]];
-        const uint32_t cutoff = fb2_guess_filter_threshold(c.data(), c.size(), f->err_filter);
+    if (err) {
+        size_t max_count = hist.size();
+        while (max_count && hist[max_count - 1] == 0) --max_count;
+        hist.resize(max_count);
+        const uint32_t cutoff = threshold_from_hist(hist, f->err_filter);
         if (f->has_abun_low) { if (cutoff > f->abun_low) f->abun_low = cutoff; }
         else { f->has_abun_low = 1; f->abun_low = cutoff; }
     }
-    if (on && (f->has_abun_low || f->has_abun_high)) {  // filter_abundance (filtering.rs:329-343)
-        const uint32_t lo = f->has_abun_low ? f->abun_low : 0u;
-        const uint32_t hi = f->has_abun_high ? f->abun_high : UINT32_MAX;
-        size_t m = 0;
-        for (size_t j = 0; j < keep.size(); ++j) {
-            const uint32_t c = counts[keep[j]];
-            if (lo <= c && c <= hi) keep[m++] = keep[j];
-        }
-        keep.resize(m);
+    const bool abun = on && (f->has_abun_low || f->has_abun_high);   // filter_abundance (filtering.rs:329-343)
+    const uint32_t lo = f->has_abun_low ? f->abun_low : 0u, hi = f->has_abun_high ? f->abun_high : UINT32_MAX;
+    for (size_t i = 0; i < n && keep.size() < limit; ++i) {
+        if (strand && !ok[i]) continue;
+        if (abun && !(lo <= counts[i] && counts[i] <= hi)) continue;
+        keep.push_back((uint32_t)i);
     }
     return FB2_OK;
 }
@@ -134,7 +145,7 @@ int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, 
 extern "C" int fb2_filter_counts(fb2_result *r, fb2_filter *f) {
     if (!r || !f) return fb2_fail(FB2_EINVAL, "null argument");
     std::vector<uint32_t> keep;
-    const int rc = fb2_filter_select(r->counts, r->extras, (size_t)r->n, f, r->format, keep);
+    const int rc = fb2_filter_select(r->counts, r->extras, (size_t)r->n, f, r->format, keep, SIZE_MAX);
     if (rc != FB2_OK) return rc;
     std::vector<uint8_t> flag((size_t)r->n, 0);
     for (uint32_t i : keep) flag[i] = 1;
