@@ -134,6 +134,18 @@ def main():
                   "h2d_gbs": nbytes / med / 1e9,
                   "bit_exact": matches(digest_of(sk, 21), digests.get(f"c2/reads={reads}/rank=0")),
                   "bit_exact_on": "whole result vs oracle digest of the full file"})
+        # the same FASTQ as a FILE (tmpfs) through fb2_sketch_files: what `finch sketch reads.fq` does
+        if os.path.isdir("/dev/shm") and not args.quick:
+            path = os.path.join(tempfile.mkdtemp(prefix="fb2c2_", dir="/dev/shm"), "c2.fq")
+            try:
+                host.numpy().tofile(path)
+                med, best, sks = timed(torch, lambda: fb.sketch_files([path], sp, fp), 3, 1)
+                emit({"config": f"C2 the same FASTQ as one file on tmpfs: fb2_sketch_files (parallel pread, double-buffered pieces)",
+                      "n_gpus": 1, "ms": med * 1e3, "gbases_per_s_e2e": nbases / med / 1e9, "file_gbs": nbytes / med / 1e9,
+                      "bit_exact": matches(digest_of(sks[0], 21), digests.get(f"c2/reads={reads}/rank=0")),
+                      "bit_exact_on": "whole result vs oracle digest of the full file"})
+            finally:
+                shutil.rmtree(os.path.dirname(path), ignore_errors=True)
         del host
         fb.lib().fb2_sketch_files_release_pool()
 

@@ -257,9 +257,17 @@ phase_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, const ParseCarry *__r
         Raw16 r;
         const uint4 curv = nextv;
         if (t + 1 < t1) nextv = fetch_raw(raw, off + (uint32_t)TILE_BYTES, g.len);
-        load_raw(raw, off, g.len, r, &curv);
+        uint32_t nl_count = 0;
+        if (MODE == MODE_FASTQ && off + 16u <= g.len) {
+            // a full piece only needs its newline COUNT here: one flag per byte, no gather into a position mask
+            nl_count = __popc(zero_bytes80(curv.x ^ 0x0A0A0A0Au)) + __popc(zero_bytes80(curv.y ^ 0x0A0A0A0Au)) +
+                       __popc(zero_bytes80(curv.z ^ 0x0A0A0A0Au)) + __popc(zero_bytes80(curv.w ^ 0x0A0A0A0Au));
+        } else {
+            load_raw(raw, off, g.len, r, &curv);
+            nl_count = __popc(r.nl);
+        }
         if (MODE == MODE_FASTQ) {
-            acc += __popc(r.nl);
+            acc += nl_count;
         } else {
             const uint32_t p1 = prev_byte(r, raw, off, carry->prev1);
             const uint32_t ls = ((r.nl << 1) | (p1 == '\n' ? 1u : 0u)) & r.valid;

@@ -721,6 +721,22 @@ def test_host_strip_matches_device_parse(fb, synth, oracle, monkeypatch):
         assert e.value.code == fb.ERECORD, e.value.message
 
 
+def test_sketch_files_large_file_is_read_in_parallel(fb, synth, tmp_path):
+    """Files of 64 MiB and more are read by several threads (pread slices of 32 MiB pieces, double-buffered against
+    the copies to the GPU): same sketch as the bytes handed over in one piece."""
+    genome = synth.synth_genome(200_000, 3)
+    data = synth.synth_fastq(genome, 240_000, 150, 0.005, 9)[0]
+    assert data.size > (70 << 20)
+    p = tmp_path / "big.fq"
+    data.tofile(p)
+    sp = fb.SketchParams.from_cli("mash", n_hashes=500, kmer_length=21, filters_enabled=True)
+    fp = fb.FilterParams(True, (None, None), 0.21, 0.1)
+    a = fb.sketch_files([str(p)], sp, fp)[0]
+    b = fb.sketch_stream(data, str(p), sp, fp)
+    assert np.array_equal(a.hashes_u64, b.hashes_u64) and np.array_equal(a.counts, b.counts) and np.array_equal(a.extra_counts, b.extra_counts)
+    assert (a.seq_length, a.num_valid_kmers) == (b.seq_length, b.num_valid_kmers) == (240_000 * 150, 240_000 * 130)
+
+
 def test_sketch_files(fb, oracle, tmp_path):
     rng = np.random.default_rng(21)
     paths, datas = [], []
