@@ -105,12 +105,18 @@ int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, 
     keep.clear();
     const bool on = f->filter_on == 1;
     const bool strand = on && f->strand_filter > 0.0, err = on && f->err_filter > 0.0;
-    static thread_local std::vector<uint8_t> ok;           // strand survivors (reused across calls)
-    static thread_local std::vector<uint64_t> hist;
+    static thread_local std::vector<uint8_t> ok_tls;       // strand survivors (reused across calls)
+    static thread_local std::vector<uint64_t> hist_tls;
+    std::vector<uint8_t> &ok = ok_tls;                     // (one TLS look-up, not one per loop iteration)
+    std::vector<uint64_t> &hist = hist_tls;
     if (strand) ok.resize(n);
-    if (err) hist.assign(1024, 0);
+    if (err) hist.assign(4096, 0);
     if (strand || err) {
         const double cut = f->strand_filter;
+        uint8_t *okp = ok.data();
+        uint64_t *hp = hist.data();
+        size_t hcap = hist.size();
+        uint64_t small[4][64] = {};
         for (size_t i = 0; i < n; ++i) {
             const uint32_t c = counts[i];
             bool pass = true;
@@ -118,12 +124,16 @@ int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, 
                 const uint32_t lowest = std::min(extras[i], c - extras[i]);
                 pass = ((double)lowest / (double)c) >= cut;
             }
-            if (strand) ok[i] = pass;
+            if (strand) okp[i] = pass;
             if (err && pass && c) {   // hist of what is left (statistics.rs:30-47; filtering.rs:68-79)
-                if (c > hist.size()) hist.resize(std::max<size_t>(c, hist.size() * 2), 0);
-                hist[c - 1]++;
+                if (c <= 64) small[i & 3][c - 1]++;   // most counts are 1 or 2: four copies break the store-to-load chain
+                else {
+                    if (c > hcap) { hist.resize(std::max<size_t>(c, hcap * 2), 0); hp = hist.data(); hcap = hist.size(); }
+                    hp[c - 1]++;
+                }
             }
         }
+        if (err) for (int q = 0; q < 4; ++q) for (int c = 0; c < 64; ++c) hp[c] += small[q][c];
     }
     if (err) {
         size_t max_count = hist.size();
@@ -135,8 +145,9 @@ int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, 
     }
     const bool abun = on && (f->has_abun_low || f->has_abun_high);   // filter_abundance (filtering.rs:329-343)
     const uint32_t lo = f->has_abun_low ? f->abun_low : 0u, hi = f->has_abun_high ? f->abun_high : UINT32_MAX;
+    const uint8_t *okp = strand ? ok.data() : nullptr;
     for (size_t i = 0; i < n && keep.size() < limit; ++i) {
-        if (strand && !ok[i]) continue;
+        if (okp && !okp[i]) continue;
         if (abun && !(lo <= counts[i] && counts[i] <= hi)) continue;
         keep.push_back((uint32_t)i);
     }
