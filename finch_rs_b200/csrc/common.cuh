@@ -29,7 +29,7 @@ enum : uint8_t {
 };
 constexpr uint8_t SYM_BREAK = 4;  // symbol-stream code for "not a base" (N, record break)
 
-FB2_HD uint8_t classify_byte(uint8_t c) {
+constexpr FB2_HD uint8_t classify_byte(uint8_t c) {
     switch (c) {
     case 'A': case 'a': return CLS_A;
     case 'C': case 'c': return CLS_C;

@@ -48,6 +48,8 @@ struct ParseCarry {
     uint64_t len_bad_pos;    // min stream position of the header-line newline of such a record (~0: none)
     uint64_t last_nl[2][3];  // the last three newlines of the stream before / after the current chunk (ascending;
                              // stream position, bit 63 = preceded by a CR; ~0 = none); halves alternate per chunk
+    uint32_t state_next;     // fused parse: line state after the current chunk (its last supertile writes it while other
+    uint32_t pad_;           // blocks may still read `state`; front_fix_kernel commits it to `state`)
 };
 constexpr unsigned long long NL_NONE = ~0ULL;
 

@@ -122,6 +122,11 @@ struct fb2_sketcher {
 
     size_t chunk_bytes = 0;
     DevBuf d_raw[2], d_sym[2], d_stmap, d_ststate, d_rcount[2], d_tail, d_carry, d_state, d_seam;
+    // fused single-pass parse (parse.cu, parse_fused_kernel): d_stmap holds the look-back status words
+    DevBuf d_ticket;                 // supertile ticket counter (never reset: launches pass its value so far)
+    uint32_t ticket_total = 0;
+    uint32_t parse_epoch = 0;        // 1..65535, one per chunk; the status words are cleared when it wraps
+    bool parse_fused = true;         // FB2_PARSE_V1=1: the three-kernel pipeline (phase / scan / pack)
     int tail_sel = 0;               // which half of d_tail holds the symbols carried into the next chunk
     uint64_t ordinal = 0;           // next position id (symbols of all regions so far + pushed k-mers)
     DevBuf log_hash[2], log_kmer[2], log_posx[2];   // one candidate log per in-flight chunk
@@ -368,6 +373,7 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
     }
 
     s->chunk_bytes = env_size("FB2_CHUNK_MB", 128) << 20;
+    s->parse_fused = !getenv("FB2_PARSE_V1");
     if (s->chunk_bytes < (1u << 20)) s->chunk_bytes = 1u << 20;
     if (s->chunk_bytes > (1ull << 30)) s->chunk_bytes = 1ull << 30;
 
@@ -418,7 +424,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
         if (s->h_snap[i]) cudaFreeHost(s->h_snap[i]);
         if (s->ev_chunk[i]) cudaEventDestroy(s->ev_chunk[i]);
     }
-    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release(); s->d_seam.release();
+    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release(); s->d_seam.release(); s->d_ticket.release();
     s->d_carry.release(); s->d_state.release();
     s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release(); s->d_bins.release(); s->d_live_bins.release();
     s->out_hash.release(); s->out_cnt.release(); s->out_ext.release(); s->out_kmer.release(); s->out_posx.release();
@@ -654,7 +660,7 @@ static ChunkGeom make_geom(uint32_t len) {
     const uint32_t forced = (uint32_t)env_size("FB2_ST_TILES", 0);   // tests: supertile size whatever the chunk size
     if (forced) stt = forced;
     if (stt < 1) stt = 1;
-    if (stt > 32) stt = 32;
+    if (stt > (uint32_t)parse_fused_max_tiles()) stt = (uint32_t)parse_fused_max_tiles();   // one supertile = one batch of the fused parse
     g.st_tiles = stt;
     g.n_st = cdivu(g.n_tiles, stt);
     g.st_bytes = stt * TILE_BYTES;
@@ -810,7 +816,9 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     TRY(settle(s, par));           // its buffers are about to be reused (normally already settled)
     const ChunkGeom g = make_geom(len);
     s->last_geom = g;
+    const void *stmap_was = s->d_stmap.p;
     TRY(s->d_stmap.ensure((size_t)g.n_st * 4)); TRY(s->d_ststate.ensure((size_t)g.n_st * 4));
+    const bool status_fresh = s->d_stmap.p != stmap_was;
     TRY(s->d_rcount[par].ensure((size_t)g.n_st * 4));
     if (mode == MODE_FASTQ) TRY(s->d_seam.ensure((size_t)g.n_st * sizeof(SeamNl)));
     TRY(s->d_sym[par].ensure((size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + 2 * HASH_TILE));
@@ -819,13 +827,29 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     uint8_t *tail_in = s->d_tail.as<uint8_t>() + s->halo * s->tail_sel, *tail_out = s->d_tail.as<uint8_t>() + s->halo * (s->tail_sel ^ 1);
     fb2_sketcher::EvPair evparse;
     const bool parse_timed = timing_begin(s, evparse);
-    launch_phase(mode, d_raw, g, dc, s->d_stmap.as<uint32_t>(), s->d_ststate.as<uint32_t>(), s->st);
-    launch_pack(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym[par].as<uint8_t>(), s->d_rcount[par].as<uint32_t>(),
-                tail_in, tail_out, s->d_seam.as<SeamNl>(), s->tail_sel, s->halo, s->st);
+    if (s->parse_fused) {
+        if (!s->d_ticket.p) {
+            TRY(s->d_ticket.ensure(4));
+            CU(cudaMemsetAsync(s->d_ticket.p, 0, 4, s->st));
+            s->ticket_total = 0;
+        }
+        if (status_fresh || ++s->parse_epoch > 0xFFFFu) {   // new words, or the epoch wrapped: no stale word may match
+            CU(cudaMemsetAsync(s->d_stmap.p, 0, s->d_stmap.cap, s->st));
+            s->parse_epoch = 1;
+        }
+        launch_parse_fused(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym[par].as<uint8_t>(), s->d_rcount[par].as<uint32_t>(),
+                           tail_in, tail_out, s->d_seam.as<SeamNl>(), s->tail_sel, s->halo, s->d_stmap.as<uint32_t>(), s->parse_epoch,
+                           s->d_ticket.as<uint32_t>(), s->ticket_total, s->st);
+        s->ticket_total += g.n_st;
+    } else {
+        launch_phase(mode, d_raw, g, dc, s->d_stmap.as<uint32_t>(), s->d_ststate.as<uint32_t>(), s->st);
+        launch_pack(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym[par].as<uint8_t>(), s->d_rcount[par].as<uint32_t>(),
+                    tail_in, tail_out, s->d_seam.as<SeamNl>(), s->tail_sel, s->halo, s->st);
+    }
     if (parse_timed) timing_end(s, evparse, s->ev_parse_pending);
     if (rawbuf >= 0) { CU(cudaEventRecord(s->ev_rawfree[rawbuf], s->st)); s->rawfree_pending[rawbuf] = true; }
     s->tail_sel ^= 1;
-    s->stats.kernel_launches += (mode == MODE_LINES ? 3 : 4); s->stats.chunks++;
+    s->stats.kernel_launches += s->parse_fused ? 3 : (mode == MODE_LINES ? 3 : 4); s->stats.chunks++;
     const uint64_t ord_base = s->ordinal;
     s->ordinal += (uint64_t)g.n_st * g.st_bytes;
     s->par ^= 1;

@@ -122,7 +122,13 @@ int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, 
             bool pass = true;
             if (strand && c >= 16) {  // filter_strands (filtering.rs:413-432): fewer observations are too noisy to call an adapter
                 const uint32_t lowest = std::min(extras[i], c - extras[i]);
-                pass = ((double)lowest / (double)c) >= cut;
+                // lowest / c >= cut, decided by a multiply when it is not within 1e-12 of the boundary (rounding is
+                // monotonic, so away from the boundary the rounded quotient compares like the real one); the
+                // division itself (the reference's expression, ~20 cycles) only for the borderline entries
+                const double prod = cut * (double)c, lw = (double)lowest;
+                if (lw >= prod * (1.0 + 1e-12)) pass = true;
+                else if (lw <= prod * (1.0 - 1e-12)) pass = false;
+                else pass = (lw / (double)c) >= cut;
             }
             if (strand) okp[i] = pass;
             if (err && pass && c) {   // hist of what is left (statistics.rs:30-47; filtering.rs:68-79)

@@ -11,6 +11,10 @@ void launch_phase(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, 
 void launch_pack(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, const uint32_t *st_state, uint8_t *sym,
                  uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, SeamNl *seam, int nl_in, uint32_t halo,
                  cudaStream_t s);
+int parse_fused_max_tiles();
+void launch_parse_fused(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_state, uint8_t *sym,
+                        uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, SeamNl *seam, int nl_in, uint32_t halo,
+                        uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base, cudaStream_t s);
 void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t st);
 
 // hash.cu

@@ -865,6 +865,485 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
     }
 }
 
+// ================================================================================================
+// parse_fused_kernel: phase + scan + pack in ONE pass over the raw bytes.
+//
+// The three-kernel pipeline above reads every raw byte twice (phase_kernel counts newlines so that pack_kernel can
+// start each supertile in the right line state) and pays two launches for a 2-bit piece of information.  Here a
+// block owns one supertile of <= 32 KiB, stages it in shared memory once, and learns its start state from its
+// predecessors while it works -- a decoupled look-back on a per-supertile status word:
+//     status[st] = epoch << 16 | kind << 8 | value
+//     kind 1 (aggregate): what the supertile does to the line state -- FASTQ: its newline count mod 4;
+//                         FASTA: 0 = holds no line start (identity), 2 | h = its last line start is (h = 1) or is
+//                         not (h = 0) a header line
+//     kind 2 (inclusive): the line state AFTER the supertile (the state of the line holding its last byte)
+// Supertile indices are handed out by a ticket counter, so every predecessor of a running block is running or done
+// (no deadlock whatever the block scheduling order); `epoch` (the chunk number) makes stale words of earlier chunks
+// invisible without clearing the array.  The whole supertile is ONE batch: one newline list, one piece pass, one
+// output pass, symbols start at the region's first byte (no ragged first word).
+//
+// Everything else is pack_kernel's scheme (line pieces -> entries -> aligned 16-byte output words; words cut by a
+// line end or holding anything but ACGTacgt are listed and done densely in a second pass; blanks / CRs inside
+// sequence lines or more than PF_NLCAP newlines make the block redo its supertile with pack_exact).
+constexpr int PF_MAX_TILES = 8;
+constexpr int PF_BYTES = PF_MAX_TILES * TILE_BYTES;      // 32 KiB
+constexpr int PF_NLCAP = 2047;
+constexpr int PF_LIST = 2064;                            // newline list (PF_NLCAP + 1), later the listed output words (PF_BYTES / 16 + 1)
+constexpr int PF_ENT = 2050;                             // entries (PF_NLCAP + 1 pieces)
+constexpr int PF_FIRST = PF_BYTES / 16 + 2;
+constexpr uint32_t PF_SMEM = 16u + PF_BYTES + 32u + 2u * (PF_LIST + 3 * PF_ENT + PF_FIRST);
+static_assert(PF_LIST >= PF_NLCAP + 1 && PF_LIST >= PF_BYTES / 16 + 1 && PF_ENT >= PF_NLCAP + 2, "list sizes");
+static_assert(4 * (PF_SMEM + 1024 + 256) <= 228 * 1024, "four blocks per SM");
+
+struct ClsTable {
+    uint8_t v[256];
+    constexpr ClsTable() : v{} { for (int i = 0; i < 256; ++i) v[i] = classify_byte((uint8_t)i); }
+};
+__device__ const ClsTable g_cls_table{};
+
+__device__ __forceinline__ uint32_t nl_mask16(const uint4 v) {
+    return gather4(zero_bytes80(v.x ^ 0x0A0A0A0Au)) | (gather4(zero_bytes80(v.y ^ 0x0A0A0A0Au)) << 4) |
+           (gather4(zero_bytes80(v.z ^ 0x0A0A0A0Au)) << 8) | (gather4(zero_bytes80(v.w ^ 0x0A0A0A0Au)) << 12);
+}
+// two packed (4 x 16-bit) counters scanned together: one pair of barriers
+__device__ __forceinline__ void block_exscan_add64x2(unsigned long long &a, unsigned long long &b, unsigned long long *sh16l,
+                                                     unsigned long long &ta, unsigned long long &tb) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long xa = a, xb = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long na = __shfl_up_sync(0xffffffffu, xa, d), nb = __shfl_up_sync(0xffffffffu, xb, d);
+        if (lane >= d) { xa += na; xb += nb; }
+    }
+    __syncthreads();  // protect sh16l from a previous use
+    if (lane == 31) { sh16l[wid] = xa; sh16l[8 + wid] = xb; }
+    __syncthreads();
+    unsigned long long basea = 0, baseb = 0, tota = 0, totb = 0;
+#pragma unroll
+    for (int i = 0; i < TILE_THREADS / 32; ++i) {
+        const unsigned long long sa = sh16l[i], sb = sh16l[8 + i];
+        if (i < wid) { basea += sa; baseb += sb; }
+        tota += sa; totb += sb;
+    }
+    ta = tota; tb = totb;
+    a = basea + xa - a; b = baseb + xb - b;
+}
+__device__ __forceinline__ uint32_t ld_status(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_status(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+// Line state at the start of supertile st (whole warp; see the status word above).  The entry in front of the
+// chunk's first supertile is the carried state of the stream.
+template <int MODE>
+__device__ __forceinline__ uint32_t lookback_state(const uint32_t *status, uint32_t st, uint32_t epoch, uint32_t carry_state,
+                                                   uint32_t lane) {
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    uint32_t near_const = NONE;   // FASTA: state set by the nearest predecessor that holds a line start
+    uint32_t add = 0;             // FASTQ: newlines of the predecessors folded so far
+    int j0 = (int)st - 1;         // nearest predecessor not folded yet
+    while (true) {
+        const int j = j0 - (int)lane;
+        uint32_t v;
+        if (j < 0) v = (2u << 8) | carry_state;
+        else {
+            do { v = ld_status(status + j); } while ((v >> 16) != epoch);
+            v &= 0xFFFFu;
+        }
+        const uint32_t kind = v >> 8, val = v & 0xFFu;
+        const uint32_t inc = __ballot_sync(0xffffffffu, kind == 2u);
+        const uint32_t upto = inc ? (uint32_t)(__ffs(inc) - 1) : 32u;     // lanes [0, upto) are aggregates; lane upto is the base
+        if (MODE == MODE_FASTQ) {
+            add += __reduce_add_sync(0xffffffffu, lane < upto ? val : 0u);
+            if (inc) return (__shfl_sync(0xffffffffu, val, (int)upto) + add) & 3u;
+        } else {
+            const uint32_t nonid = __ballot_sync(0xffffffffu, lane < upto && (val & 2u));
+            if (near_const == NONE && nonid) near_const = __shfl_sync(0xffffffffu, val, __ffs(nonid) - 1) & 1u;
+            if (inc) return near_const != NONE ? near_const : (__shfl_sync(0xffffffffu, val, (int)upto) & 1u);
+        }
+        j0 -= 32;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, uint32_t *__restrict__ st_state,
+                   uint8_t *__restrict__ sym, uint32_t *__restrict__ region_count, SeamNl *__restrict__ seam,
+                   uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base) {
+    extern __shared__ __align__(16) uint8_t pf_smem[];
+    __shared__ unsigned long long sh16l[16];
+    __shared__ uint32_t sh8[8];
+    __shared__ uint32_t c_nl[3];
+    __shared__ uint32_t s_misc[12];
+    enum { M_ST = 0, M_DECL = 1, M_NBW = 2, M_STATE = 3, M_LASTNL = 4, M_BASES = 5, M_RECS = 6, M_BAD = 7, M_LBAD = 8 };
+    uint8_t *rawb = pf_smem + 16;                                          // [16 front pad | supertile | back pad]
+    const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(pf_smem);
+    uint16_t *s_nl = reinterpret_cast<uint16_t *>(pf_smem + 16 + PF_BYTES + 32);
+    uint16_t *e_src = s_nl + PF_LIST, *e_len = e_src + PF_ENT, *e_out = e_len + PF_ENT, *s_first = e_out + PF_ENT;
+    uint16_t *s_bw = s_nl;                                                 // the newline list is dead by then
+    const uint8_t *lut = g_cls_table.v;
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31u, wid = tid >> 5;
+    if (tid == 0) {
+        s_misc[M_ST] = atomicAdd(ticket, 1u) - ticket_base;
+        s_misc[M_DECL] = 0; s_misc[M_NBW] = 0; s_misc[M_STATE] = 0; s_misc[M_LASTNL] = 0;
+        s_misc[M_BASES] = 0; s_misc[M_RECS] = 0; s_misc[M_BAD] = 0xFFFFFFFFu; s_misc[M_LBAD] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    const uint32_t st = s_misc[M_ST];
+    const uint32_t B0 = st * g.st_bytes, B1 = min(B0 + g.st_bytes, g.len), blen = B1 - B0;
+    const uint64_t raw_base = carry->chunk_raw_base;
+    const uint32_t cprev1 = carry->cprev1, cprev2 = carry->cprev2;
+    const uint32_t carry_state = MODE == MODE_LINES ? 0u : (carry->state & 3u);
+    uint8_t *region = sym + (size_t)SYM_FRONT + (size_t)st * g.region_stride;
+    SeamNl *seam_st = MODE == MODE_FASTQ ? seam + st : nullptr;
+    constexpr uint32_t STEP = MODE == MODE_FASTQ ? 4u : 1u;              // FASTQ: only every 4th piece emits
+
+    // ---- 1. stage the supertile, newline masks --------------------------------------------------------
+    uint32_t nlm[PF_MAX_TILES];
+    if (blen == (uint32_t)PF_BYTES) {                                    // the usual supertile of a large chunk
+        uint4 v[PF_MAX_TILES];
+#pragma unroll
+        for (int p = 0; p < PF_MAX_TILES; ++p)
+            v[p] = __ldg(reinterpret_cast<const uint4 *>(raw + B0 + (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u));
+#pragma unroll
+        for (int p = 0; p < PF_MAX_TILES; ++p) {
+            *reinterpret_cast<uint4 *>(rawb + (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u) = v[p];
+            nlm[p] = nl_mask16(v[p]);
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < PF_MAX_TILES; ++p) {
+            nlm[p] = 0;
+            const uint32_t po = (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u;
+            if ((uint32_t)p * TILE_BYTES < blen) {
+                Raw16 r;
+                if (po < blen) load_raw(raw, B0 + po, B1, r);
+                else { r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0; r.nl = 0; }
+                *reinterpret_cast<uint4 *>(rawb + po) = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
+                nlm[p] = r.nl;
+            }
+        }
+    }
+    if (tid == 0) {   // the two bytes in front of the supertile
+        rawb[-1] = (uint8_t)(B0 >= 1u ? raw[B0 - 1] : cprev1);
+        rawb[-2] = (uint8_t)(B0 >= 2u ? raw[B0 - 2] : (B0 == 1u ? cprev1 : cprev2));
+    }
+    if (MODE == MODE_FASTA) {   // position after the last newline that is followed by a byte of this supertile
+        uint32_t mx = 0;
+#pragma unroll
+        for (int p = 0; p < PF_MAX_TILES; ++p) {
+            const uint32_t po = (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u;
+            uint32_t m = nlm[p];
+            if (m) {
+                const uint32_t room = blen - 1u - po;                    // bits below `room` are followed by a byte
+                if (room < 16u) m &= (1u << room) - 1u;
+                if (m) mx = po + (uint32_t)(31 - __clz(m)) + 1u;
+            }
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0 && mx) atomicMax(&s_misc[M_LASTNL], mx);
+    }
+    // ---- 2. newline positions ----------------------------------------------------------------------------
+    unsigned long long exa = 0, exb = 0, tota, totb;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        exa |= (unsigned long long)__popc(nlm[p]) << (16 * p);
+        exb |= (unsigned long long)__popc(nlm[4 + p]) << (16 * p);
+    }
+    block_exscan_add64x2(exa, exb, sh16l, tota, totb);                   // (its barriers also publish the staged bytes)
+    uint32_t N = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) N += ((uint32_t)(tota >> (16 * p)) & 0xFFFFu) + ((uint32_t)(totb >> (16 * p)) & 0xFFFFu);
+    bool declined = N > (uint32_t)PF_NLCAP;                              // uniform
+    // what this supertile does to the line state
+    uint32_t agg = 0, after_const = 0;
+    bool agg_const = false;
+    if (MODE == MODE_FASTQ) agg = N & 3u;
+    if (MODE == MODE_FASTA) {
+        const uint32_t ln = s_misc[M_LASTNL];
+        const bool has_ls = ln != 0u || rawb[-1] == '\n';
+        if (has_ls) { after_const = rawb[ln] == '>' ? 1u : 0u; agg = 2u | after_const; agg_const = true; }
+    }
+    if (MODE != MODE_LINES && tid == 0) st_status(status + st, (epoch << 16) | (1u << 8) | agg);
+    if (!declined) {
+        uint32_t before = 0;                                             // newlines of the tiles in front
+#pragma unroll
+        for (int p = 0; p < PF_MAX_TILES; ++p) {
+            const unsigned long long ex = p < 4 ? exa : exb, tot = p < 4 ? tota : totb;
+            uint32_t m = nlm[p], at = before + ((uint32_t)(ex >> (16 * (p & 3))) & 0xFFFFu);
+            before += (uint32_t)(tot >> (16 * (p & 3))) & 0xFFFFu;
+            const uint32_t po = (uint32_t)p * TILE_BYTES + (uint32_t)tid * 16u;
+            while (m) {
+                s_nl[at++] = (uint16_t)(po + (uint32_t)(__ffs(m) - 1));
+                m &= m - 1u;
+            }
+        }
+    }
+    if (MODE != MODE_LINES && wid == 0) {
+        const uint32_t s0 = lookback_state<MODE>(status, st, epoch, carry_state, lane);
+        if (lane == 0) {
+            const uint32_t after = MODE == MODE_FASTQ ? ((s0 + N) & 3u) : (agg_const ? after_const : s0);
+            st_status(status + st, (epoch << 16) | (2u << 8) | after);
+            st_state[st] = s0;
+            s_misc[M_STATE] = s0;
+            if (st == g.n_st - 1u) carry->state_next = after;
+        }
+    }
+    __syncthreads();
+    const uint32_t state0 = MODE == MODE_LINES ? 0u : s_misc[M_STATE];   // state of the line holding the previous byte
+
+    uint32_t out_off = 0;
+    int bases_delta = 0;
+    uint32_t recs = 0, bad_rel = 0xFFFFFFFFu, lbad = 0xFFFFFFFFu;        // chunk-relative positions
+    if (!declined) {
+        // ---- 3. pieces -> entries ---------------------------------------------------------------------
+        const uint32_t NP = N + 1u;
+        const uint32_t G = (NP + TILE_THREADS - 1u) / TILE_THREADS;
+        const uint32_t i_lo = min((uint32_t)tid * G, NP), i_hi = min(i_lo + G, NP);
+        const bool ls0 = rawb[-1] == '\n';
+        uint32_t sum = 0;
+        for (uint32_t i = i_lo; i < i_hi; ++i) {
+            const uint32_t start = i ? (uint32_t)s_nl[i - 1] + 1u : 0u;
+            const bool has_nl = i < N;
+            const uint32_t end = has_nl ? (uint32_t)s_nl[i] : blen;
+            const uint32_t len = end - start;
+            const bool line_start = i > 0u || ls0;
+            const uint32_t pb = rawb[(int)end - 1];            // byte in front of the piece's end
+            const uint32_t klen = len - ((len > 0u && pb == '\r') ? 1u : 0u);   // one trailing CR goes
+            uint32_t L = 0, brk = 0;
+            if (MODE == MODE_LINES) {
+                L = klen; brk = has_nl ? 1u : 0u;
+            } else if (MODE == MODE_FASTQ) {
+                const uint32_t ph = (state0 + i) & 3u;
+                if (line_start && start < blen) {
+                    if (ph == 0u) recs++;
+                    if ((ph == 0u || ph == 2u) && rawb[start] != (ph == 0u ? '@' : '+')) bad_rel = min(bad_rel, B0 + start);
+                }
+                if (ph == 1u) {
+                    // sequence().len(): the line without its '\n' and without one CR right before it
+                    bases_delta += (int)len - ((has_nl && pb == '\r') ? 1 : 0);
+                    L = klen; brk = has_nl ? 1u : 0u;
+                }
+                if (has_nl) {   // sequence / quality length check (see fastq_len_check)
+                    if (i >= 3u) {   // the record's four newlines are all in this supertile (klen is the quality's length)
+                        if (ph == 3u) {
+                            const uint32_t e1 = s_nl[i - 2], e0 = s_nl[i - 3];
+                            const uint32_t ls = e1 - e0 - 1u - (rawb[(int)e1 - 1] == '\r' ? 1u : 0u);
+                            if (ls != klen) lbad = min(lbad, B0 + e0);
+                        }
+                    } else {         // the first three newlines: left to the seam check of front_fix_kernel
+                        seam_st->first[i] = (B0 + end) | (pb == '\r' ? 0x80000000u : 0u);
+                    }
+                }
+            } else {  // MODE_FASTA
+                const bool hdr = line_start ? (start < blen && rawb[start] == '>') : ((state0 & 1u) != 0u);
+                if (line_start && hdr) {
+                    recs++;
+                    brk = 1u;                                  // the header start is a record break
+                    bool prev_in_hdr;
+                    if (i == 0u) prev_in_hdr = state0 != 0u;
+                    else {
+                        const uint32_t ps = i > 1u ? (uint32_t)s_nl[i - 2] + 1u : 0u;
+                        prev_in_hdr = (i > 1u || ls0) ? rawb[ps] == '>' : ((state0 & 1u) != 0u);
+                    }
+                    // a new header ends the previous record: its raw sequence loses the final '\n'
+                    // (and one CR before it) when that newline closed a sequence line
+                    if (!prev_in_hdr) {
+                        bases_delta -= 1;
+                        if (rawb[(int)start - 2] == '\r') bases_delta -= 1;
+                    }
+                } else if (!hdr) {
+                    bases_delta += (int)len + (has_nl ? 1 : 0);
+                    L = klen;
+                }
+            }
+            e_src[i] = (uint16_t)((start & 0x7FFFu) | (brk << 15));
+            e_len[i] = (uint16_t)L;
+            e_out[i] = (uint16_t)sum;
+            sum += L + brk;
+        }
+        if (MODE == MODE_FASTQ && tid == 0) {   // the supertile's last three newlines, for the seam checks
+            const uint32_t n0 = N > 3u ? N - 3u : 0u;
+            for (uint32_t q = n0; q < N; ++q) {
+                const uint32_t pos = s_nl[q];
+                seam_st->last[3u - (N - q)] = (B0 + pos) | (rawb[(int)pos - 1] == '\r' ? 0x80000000u : 0u);
+            }
+            seam_st->n = N;
+        }
+        uint32_t T;
+        const uint32_t exo = block_exscan_add(sum, sh8, T);
+        for (uint32_t i = i_lo; i < i_hi; ++i) {
+            const uint32_t eo = (uint32_t)e_out[i] + exo;
+            const uint32_t outlen = (uint32_t)e_len[i] + ((uint32_t)e_src[i] >> 15);
+            e_out[i] = (uint16_t)eo;
+            if (outlen) {   // words whose first byte this entry provides
+                const uint32_t w_hi = (eo + outlen - 1u) >> 4;
+                for (uint32_t w = (eo + 15u) >> 4; w <= w_hi; ++w) s_first[w] = (uint16_t)i;
+            }
+        }
+        __syncthreads();
+        // ---- 4. aligned output words ------------------------------------------------------------------
+        // Pass A: every word that comes out of ONE line whole: unaligned 16-byte read, SIMD-in-register codes, one
+        // aligned store.  The others are listed and done in pass B by as few warps as it takes.
+        const uint32_t W = (T + 15u) >> 4;
+        for (uint32_t w = tid; w < W; w += TILE_THREADS) {
+            const uint32_t i = s_first[w];
+            const uint32_t d = 16u * w - (uint32_t)e_out[i];
+            if (d + 16u <= (uint32_t)e_len[i]) {
+                const uint32_t A = 16u + ((uint32_t)e_src[i] & 0x7FFFu) + d;      // pf_smem offset of output byte 0
+                const uint32_t wi = A >> 2, sel = 0x3210u + 0x1111u * (A & 3u);
+                uint32_t x[5], cw[4], diff = 0;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) x[j] = raw32[wi + j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t u = __byte_perm(x[j], x[j + 1], sel) & 0xDFDFDFDFu;
+                    const uint32_t c2 = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+                    cw[j] = c2;
+                    uint32_t z = (c2 | (c2 >> 4)) & 0x00FF00FFu;
+                    z = (z | (z >> 8)) & 0xFFFFu;
+                    diff |= __byte_perm(0x54474341u, 0u, z) ^ u;
+                }
+                if (diff == 0u) {
+                    *reinterpret_cast<uint4 *>(region + 16u * w) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                    continue;
+                }
+            }
+            s_bw[atomicAdd(&s_misc[M_NBW], 1u)] = (uint16_t)w;
+        }
+        __syncthreads();
+        // Pass B: the listed words, densely over the threads
+        const uint32_t nbw = s_misc[M_NBW];
+        for (uint32_t idx = tid; idx < nbw; idx += TILE_THREADS) {
+            const uint32_t w = s_bw[idx];
+            uint32_t filled = 0;
+            uint32_t pos = 16u * w;                            // output position within the region
+            uint32_t i = s_first[w];
+            uint32_t d = pos - (uint32_t)e_out[i];
+            uint64_t alo = 0, ahi = 0;
+            while (filled < 16u && pos < T) {
+                const uint32_t len = e_len[i], brk = (uint32_t)e_src[i] >> 15;
+                if (d < len) {
+                    const uint32_t n = min(16u - filled, len - d);
+                    const uint32_t A = 16u + ((uint32_t)e_src[i] & 0x7FFFu) + d - filled;   // pf_smem offset of output byte 0
+                    const uint32_t wi = A >> 2, sel = 0x3210u + 0x1111u * (A & 3u);
+                    uint32_t x[5], v[4];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) x[j] = raw32[wi + j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = __byte_perm(x[j], x[j + 1], sel);
+                    uint64_t l0, h0, l1, h1;
+                    ones128(filled, l0, h0);
+                    ones128(filled + n, l1, h1);
+                    const uint64_t mlo = l1 & ~l0, mhi = h1 & ~h0;
+                    const uint32_t m[4] = {(uint32_t)mlo, (uint32_t)(mlo >> 32), (uint32_t)mhi, (uint32_t)(mhi >> 32)};
+                    uint32_t cw[4], diff = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t u = v[j] & 0xDFDFDFDFu;
+                        const uint32_t c2 = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+                        cw[j] = c2;
+                        uint32_t z = (c2 | (c2 >> 4)) & 0x00FF00FFu;
+                        z = (z | (z >> 8)) & 0xFFFFu;
+                        diff |= (__byte_perm(0x54474341u, 0u, z) ^ u) & m[j];
+                    }
+                    if (diff) {   // exact per-byte classes (needletail normalize(false))
+                        bool blank = false;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const uint32_t k = lut[(v[q >> 2] >> (8 * (q & 3))) & 0xFFu];
+                            const bool in = (uint32_t)q >= filled && (uint32_t)q < filled + n;
+                            blank |= in && (k == CLS_WS || k == CLS_CR);
+                            cw[q >> 2] = (cw[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | ((k < 4u ? k : (uint32_t)SYM_BREAK) << (8 * (q & 3)));
+                        }
+                        if (blank) s_misc[M_DECL] = 1u;
+                    }
+                    alo |= ((uint64_t)cw[0] | ((uint64_t)cw[1] << 32)) & mlo;
+                    ahi |= ((uint64_t)cw[2] | ((uint64_t)cw[3] << 32)) & mhi;
+                    filled += n; pos += n; d += n;
+                }
+                if (filled < 16u && d == len && brk) {
+                    if (filled < 8u) alo |= (uint64_t)SYM_BREAK << (8u * filled);
+                    else ahi |= (uint64_t)SYM_BREAK << (8u * (filled - 8u));
+                    filled++; pos++; d++;
+                }
+                if (d >= len + brk) { i += STEP; d = 0; }
+            }
+            if (filled < 16u) {   // the region's last word: the symbols past its end are breaks anyway (see below)
+                uint64_t l0, h0;
+                ones128(filled, l0, h0);
+                alo |= 0x0404040404040404ULL & ~l0;
+                ahi |= 0x0404040404040404ULL & ~h0;
+            }
+            *reinterpret_cast<uint4 *>(region + 16u * w) = make_uint4((uint32_t)alo, (uint32_t)(alo >> 32), (uint32_t)ahi, (uint32_t)(ahi >> 32));
+        }
+        out_off = T;
+        __syncthreads();
+        if (s_misc[M_DECL]) declined = true;                   // uniform: read after the barrier
+    }
+
+    if (declined) {   // anything the fast path does not do: the exact tile walk, from the supertile's start state
+        __syncthreads();
+        long long bd = 0;
+        unsigned long long bp = ~0ULL;
+        uint32_t nl_before = 0;
+        out_off = 0; recs = 0; lbad = 0xFFFFFFFFu;
+        const uint32_t t0 = st * g.st_tiles, t1 = min(t0 + g.st_tiles, g.n_tiles);
+        pack_exact<MODE>(raw, g, t0, t1, raw_base, cprev1, cprev2, state0, region, lut, sh8, out_off, bd, recs, bp,
+                         reinterpret_cast<uint16_t *>(pf_smem), c_nl, nl_before, lbad, seam_st);
+        bases_delta = (int)bd;
+        bad_rel = bp == ~0ULL ? 0xFFFFFFFFu : (uint32_t)(bp - raw_base);
+        if (MODE == MODE_FASTQ) {
+            __syncthreads();
+            if (tid == 0) { seam_st->last[0] = c_nl[0]; seam_st->last[1] = c_nl[1]; seam_st->last[2] = c_nl[2]; seam_st->n = nl_before; }
+        }
+    }
+
+    // the hash kernel walks up to HASH_W positions past the region's end: make them breaks
+    if (tid < HASH_W) region[out_off + tid] = SYM_BREAK;
+    if (MODE != MODE_LINES) {
+        const int bsum = __reduce_add_sync(0xffffffffu, bases_delta);
+        const uint32_t rsum = __reduce_add_sync(0xffffffffu, recs);
+        if (lane == 0) {
+            if (bsum) atomicAdd(reinterpret_cast<int *>(&s_misc[M_BASES]), bsum);
+            if (rsum) atomicAdd(&s_misc[M_RECS], rsum);
+        }
+        if (MODE == MODE_FASTQ) {
+            const uint32_t bmin = __reduce_min_sync(0xffffffffu, bad_rel), lmin = __reduce_min_sync(0xffffffffu, lbad);
+            if (lane == 0) {
+                if (bmin != 0xFFFFFFFFu) atomicMin(&s_misc[M_BAD], bmin);
+                if (lmin != 0xFFFFFFFFu) atomicMin(&s_misc[M_LBAD], lmin);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        region_count[st] = out_off;
+        atomicAdd(&carry->chunk_syms, out_off);
+        atomicMax(&carry->max_region_syms, out_off);
+        if (MODE != MODE_LINES) {
+            const long long bsum = (long long)(int)s_misc[M_BASES];
+            if (bsum) atomicAdd((unsigned long long *)&carry->total_bases, (unsigned long long)bsum);
+            if (s_misc[M_RECS]) atomicAdd((unsigned long long *)&carry->n_records, (unsigned long long)s_misc[M_RECS]);
+            if (MODE == MODE_FASTQ) {
+                if (s_misc[M_BAD] != 0xFFFFFFFFu) atomicMin((unsigned long long *)&carry->first_bad_pos, raw_base + s_misc[M_BAD]);
+                if (s_misc[M_LBAD] != 0xFFFFFFFFu) atomicMin((unsigned long long *)&carry->len_bad_pos, raw_base + s_misc[M_LBAD]);
+            }
+        }
+    }
+}
+
+// What phase_scan_kernel does to the carry besides the state: the stream's last two bytes and the chunk counters.
+__global__ void chunk_begin_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    carry->cprev1 = carry->prev1; carry->cprev2 = carry->prev2;
+    if (g.len >= 2) { carry->prev2 = raw[g.len - 2]; carry->prev1 = raw[g.len - 1]; }
+    else if (g.len == 1) { carry->prev2 = carry->prev1; carry->prev1 = raw[0]; }
+    carry->chunk_syms = 0;
+    carry->max_region_syms = 0;
+    carry->chunk_raw_base = carry->raw_total;
+    carry->raw_total += g.len;
+}
+
 // Front pads: warp r fills the `halo` bytes before region r (r < n_st) or the outgoing chunk tail
 // (r == n_st) with the last `halo` symbols that precede it in stream order -- every lane fetches halo / 32 of
 // them, walking back over short or empty regions and finally into the incoming chunk tail.  halo = 32 covers
@@ -894,9 +1373,10 @@ __device__ __forceinline__ int seam_collect(const SeamNl *seam, uint32_t r, int 
 __global__ void front_fix_kernel(uint8_t *__restrict__ sym, ChunkGeom g, const uint32_t *__restrict__ region_count,
                                  const uint8_t *__restrict__ tail_in, uint8_t *__restrict__ tail_out,
                                  const SeamNl *__restrict__ seam, const uint32_t *__restrict__ st_state, ParseCarry *carry,
-                                 int nl_in, uint32_t halo) {
+                                 int nl_in, uint32_t halo, int commit_state) {
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (r > g.n_st) return;
+    if (commit_state && r == g.n_st && lane == 0u) carry->state = carry->state_next;   // fused parse: see parse_fused_kernel
     if (seam != nullptr && lane < 3u) {
         const unsigned long long raw_base = carry->chunk_raw_base;
         const unsigned long long PM = ~(1ULL << 63);
@@ -951,7 +1431,37 @@ void launch_pack(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, c
     else if (mode == MODE_FASTA) pack_kernel<MODE_FASTA><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count, nullptr);
     else pack_kernel<MODE_FASTQ><<<g.n_st, TILE_THREADS, 0, s>>>(raw, g, carry, st_state, sym, region_count, seam);
     front_fix_kernel<<<(g.n_st + 1 + 7) / 8, 256, 0, s>>>(sym, g, region_count, tail_in, tail_out,
-                                                        mode == MODE_FASTQ ? seam : nullptr, st_state, carry, nl_in, halo);
+                                                        mode == MODE_FASTQ ? seam : nullptr, st_state, carry, nl_in, halo, 0);
+}
+// The fused single-pass parse of a chunk (g.st_tiles <= PF_MAX_TILES): chunk_begin + parse_fused + front_fix.
+// `status`: g.n_st words, zeroed when allocated; `epoch`: 1..65535, different from the previous 65534 launches over
+// the same words; `ticket`: a device counter whose value before this launch is `ticket_base`.
+int parse_fused_max_tiles() { return PF_MAX_TILES; }
+template <int MODE>
+static void launch_parse_fused_m(const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_state, uint8_t *sym,
+                                 uint32_t *region_count, SeamNl *seam, uint32_t *status, uint32_t epoch, uint32_t *ticket,
+                                 uint32_t ticket_base, cudaStream_t s) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attr_set[dev]) {
+        cudaFuncSetAttribute(parse_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM);
+        attr_set[dev] = true;
+    }
+    parse_fused_kernel<MODE><<<g.n_st, TILE_THREADS, PF_SMEM, s>>>(raw, g, carry, st_state, sym, region_count, seam, status, epoch,
+                                                                   ticket, ticket_base);
+}
+void launch_parse_fused(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_state, uint8_t *sym,
+                        uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, SeamNl *seam, int nl_in, uint32_t halo,
+                        uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base, cudaStream_t s) {
+    chunk_begin_kernel<<<1, 32, 0, s>>>(raw, g, carry);
+    if (mode == MODE_LINES) launch_parse_fused_m<MODE_LINES>(raw, g, carry, st_state, sym, region_count, nullptr, status, epoch, ticket, ticket_base, s);
+    else if (mode == MODE_FASTA) launch_parse_fused_m<MODE_FASTA>(raw, g, carry, st_state, sym, region_count, nullptr, status, epoch, ticket, ticket_base, s);
+    else launch_parse_fused_m<MODE_FASTQ>(raw, g, carry, st_state, sym, region_count, seam, status, epoch, ticket, ticket_base, s);
+    front_fix_kernel<<<(g.n_st + 1 + 7) / 8, 256, 0, s>>>(sym, g, region_count, tail_in, tail_out,
+                                                        mode == MODE_FASTQ ? seam : nullptr, st_state, carry, nl_in, halo,
+                                                        mode == MODE_LINES ? 0 : 1);
 }
 void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t s) {
     if (n) fill_bytes_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
