@@ -888,12 +888,13 @@ pack_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, con
 constexpr int PF_MAX_TILES = 8;
 constexpr int PF_BYTES = PF_MAX_TILES * TILE_BYTES;      // 32 KiB
 constexpr int PF_NLCAP = 2047;
-constexpr int PF_LIST = 2064;                            // newline list (PF_NLCAP + 1), later the listed output words (PF_BYTES / 16 + 1)
+constexpr int PF_LIST = 3900;                            // newline list (<= PF_NLCAP + 1 entries), then the listed output words (<= PF_BYTES / 16 + 1):
+                                                         // behind the newlines while the state is a guess (a redo needs them again), else over them
 constexpr int PF_ENT = 2050;                             // entries (PF_NLCAP + 1 pieces)
 constexpr int PF_FIRST = PF_BYTES / 16 + 2;
 constexpr uint32_t PF_SMEM = 16u + PF_BYTES + 32u + 2u * (PF_LIST + 3 * PF_ENT + PF_FIRST);
 static_assert(PF_LIST >= PF_NLCAP + 1 && PF_LIST >= PF_BYTES / 16 + 1 && PF_ENT >= PF_NLCAP + 2, "list sizes");
-static_assert(4 * (PF_SMEM + 1024 + 256) <= 228 * 1024, "four blocks per SM");
+static_assert(4 * (PF_SMEM + 1024 + 256) <= 228 * 1024 && PF_SMEM + 256 <= 227 * 1024 / 4 + 1024, "four blocks per SM");
 
 struct ClsTable {
     uint8_t v[256];
@@ -928,38 +929,66 @@ __device__ __forceinline__ void block_exscan_add64x2(unsigned long long &a, unsi
     ta = tota; tb = totb;
     a = basea + xa - a; b = baseb + xb - b;
 }
-__device__ __forceinline__ uint32_t ld_status(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ uint4 ld_status4(const uint32_t *p) {   // 16-byte aligned, straight from L2
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_status(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// Line state at the start of supertile st (whole warp; see the status word above).  The entry in front of the
-// chunk's first supertile is the carried state of the stream.
+// Line state at the start of supertile st (whole warp; see the status word above).  A lane takes one aligned group
+// of four status words per round (128 predecessors per round); the entry in front of the chunk's first supertile is
+// the carried state of the stream.  Within a lane and across lanes the walk goes from the nearest predecessor back
+// to the first inclusive word.
 template <int MODE>
 __device__ __forceinline__ uint32_t lookback_state(const uint32_t *status, uint32_t st, uint32_t epoch, uint32_t carry_state,
                                                    uint32_t lane) {
-    constexpr uint32_t NONE = 0xFFFFFFFFu;
-    uint32_t near_const = NONE;   // FASTA: state set by the nearest predecessor that holds a line start
-    uint32_t add = 0;             // FASTQ: newlines of the predecessors folded so far
-    int j0 = (int)st - 1;         // nearest predecessor not folded yet
+    if (st == 0u) return carry_state;
+    uint32_t add = 0;                       // FASTQ: newlines of the nearer predecessors folded so far
+    int q0 = (int)((st - 1u) >> 2);         // group of the nearest predecessor not folded yet
     while (true) {
-        const int j = j0 - (int)lane;
-        uint32_t v;
-        if (j < 0) v = (2u << 8) | carry_state;
+        const int q = q0 - (int)lane;
+        // lane summary: res = 1 when the lane's group settles the state (an inclusive word; FASTA: also a supertile
+        // holding a line start), `val` = that state with the lane's nearer aggregates applied; else val = the
+        // lane's aggregates alone (FASTQ: their newline sum)
+        uint32_t res, val;
+        if (q < 0) { res = 1u; val = carry_state; }
         else {
-            do { v = ld_status(status + j); } while ((v >> 16) != epoch);
-            v &= 0xFFFFu;
+            uint32_t w[4];
+            const uint32_t hi = min(3u, st - 1u - 4u * (uint32_t)q);     // entries above st - 1 are not predecessors
+            while (true) {
+                const uint4 v = ld_status4(status + 4 * q);
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                bool ready = true;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ready &= (uint32_t)e > hi || (w[e] >> 16) == epoch;
+                if (ready) break;
+            }
+            res = 0u; val = 0u;
+#pragma unroll
+            for (int e = 3; e >= 0; --e) {
+                if ((uint32_t)e <= hi && !res) {
+                    const uint32_t kind = (w[e] >> 8) & 0xFFu, x = w[e] & 0xFFu;
+                    if (MODE == MODE_FASTQ) {
+                        if (kind == 2u) { res = 1u; val = (x + val) & 3u; }
+                        else val += x;
+                    } else {
+                        if (kind == 2u || (x & 2u)) { res = 1u; val = x & 1u; }
+                    }
+                }
+            }
         }
-        const uint32_t kind = v >> 8, val = v & 0xFFu;
-        const uint32_t inc = __ballot_sync(0xffffffffu, kind == 2u);
-        const uint32_t upto = inc ? (uint32_t)(__ffs(inc) - 1) : 32u;     // lanes [0, upto) are aggregates; lane upto is the base
+        const uint32_t done = __ballot_sync(0xffffffffu, res != 0u);
+        const uint32_t upto = done ? (uint32_t)(__ffs(done) - 1) : 32u;   // lanes [0, upto) only add; lane upto settles
         if (MODE == MODE_FASTQ) {
             add += __reduce_add_sync(0xffffffffu, lane < upto ? val : 0u);
-            if (inc) return (__shfl_sync(0xffffffffu, val, (int)upto) + add) & 3u;
+            if (done) return (__shfl_sync(0xffffffffu, val, (int)upto) + add) & 3u;
         } else {
-            const uint32_t nonid = __ballot_sync(0xffffffffu, lane < upto && (val & 2u));
-            if (near_const == NONE && nonid) near_const = __shfl_sync(0xffffffffu, val, __ffs(nonid) - 1) & 1u;
-            if (inc) return near_const != NONE ? near_const : (__shfl_sync(0xffffffffu, val, (int)upto) & 1u);
+            if (done) return __shfl_sync(0xffffffffu, val, (int)upto) & 1u;
         }
-        j0 -= 32;
+        q0 -= 32;
     }
 }
 
@@ -973,12 +1002,11 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
     __shared__ uint32_t sh8[8];
     __shared__ uint32_t c_nl[3];
     __shared__ uint32_t s_misc[12];
-    enum { M_ST = 0, M_DECL = 1, M_NBW = 2, M_STATE = 3, M_LASTNL = 4, M_BASES = 5, M_RECS = 6, M_BAD = 7, M_LBAD = 8 };
+    enum { M_ST = 0, M_DECL = 1, M_NBW = 2, M_STATE = 3, M_LASTNL = 4, M_BASES = 5, M_RECS = 6, M_BAD = 7, M_LBAD = 8, M_T = 9, M_GUESS = 10 };
     uint8_t *rawb = pf_smem + 16;                                          // [16 front pad | supertile | back pad]
     const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(pf_smem);
     uint16_t *s_nl = reinterpret_cast<uint16_t *>(pf_smem + 16 + PF_BYTES + 32);
     uint16_t *e_src = s_nl + PF_LIST, *e_len = e_src + PF_ENT, *e_out = e_len + PF_ENT, *s_first = e_out + PF_ENT;
-    uint16_t *s_bw = s_nl;                                                 // the newline list is dead by then
     const uint8_t *lut = g_cls_table.v;
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u, wid = tid >> 5;
@@ -1063,7 +1091,10 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
         const bool has_ls = ln != 0u || rawb[-1] == '\n';
         if (has_ls) { after_const = rawb[ln] == '>' ? 1u : 0u; agg = 2u | after_const; agg_const = true; }
     }
-    if (MODE != MODE_LINES && tid == 0) st_status(status + st, (epoch << 16) | (1u << 8) | agg);
+    // Warp PF_LB (the last one) is the look-back warp: it publishes the aggregate, and while the other seven warps
+    // frame the pieces (3a, which does not need the state) it walks back over the predecessors' status words.
+    constexpr uint32_t PF_LB = TILE_THREADS / 32 - 1, PF_WT = PF_LB * 32;   // worker threads
+    if (MODE != MODE_LINES && tid == (int)PF_WT) st_status(status + st, (epoch << 16) | (1u << 8) | agg);
     if (!declined) {
         uint32_t before = 0;                                             // newlines of the tiles in front
 #pragma unroll
@@ -1078,29 +1109,110 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
             }
         }
     }
-    if (MODE != MODE_LINES && wid == 0) {
-        const uint32_t s0 = lookback_state<MODE>(status, st, epoch, carry_state, lane);
-        if (lane == 0) {
-            const uint32_t after = MODE == MODE_FASTQ ? ((s0 + N) & 3u) : (agg_const ? after_const : s0);
-            st_status(status + st, (epoch << 16) | (2u << 8) | after);
-            st_state[st] = s0;
-            s_misc[M_STATE] = s0;
-            if (st == g.n_st - 1u) carry->state_next = after;
+    // Pieces: N newlines -> N + 1 pieces, G consecutive ones per worker thread.  Geometry of piece i (both passes).
+    const uint32_t NP = N + 1u;
+    const uint32_t G = (NP + PF_WT - 1u) / PF_WT;
+    const uint32_t i_lo = min((uint32_t)tid * G, NP), i_hi = wid == PF_LB ? i_lo : min(i_lo + G, NP);
+    unsigned long long vsum = 0, vex = 0, vtot = 0;   // output lengths per variant of the unknown state (16-bit fields)
+    uint32_t state0 = 0;                             // state of the line holding the byte in front of the supertile
+    bool have_state = MODE == MODE_LINES;            // false: state0 is a guess, verified when the look-back is in
+    if (wid == PF_LB) {
+        named_arrive(1, TILE_THREADS);               // this warp's newlines are in the list
+        if (MODE != MODE_LINES) {
+            state0 = lookback_state<MODE>(status, st, epoch, carry_state, lane);
+            have_state = true;
+            if (lane == 0) {
+                const uint32_t after = MODE == MODE_FASTQ ? ((state0 + N) & 3u) : (agg_const ? after_const : state0);
+                st_status(status + st, (epoch << 16) | (2u << 8) | after);
+                st_state[st] = state0;
+                s_misc[M_STATE] = state0;
+                if (st == g.n_st - 1u) carry->state_next = after;
+            }
+            __syncwarp();
+            named_arrive(3, TILE_THREADS);           // the workers pick the state up when they need it
+        }
+    } else {
+        named_sync(1, TILE_THREADS);                 // the newline list is complete
+        if (!declined) {
+            // ---- 3a. output length of every piece, for each state the supertile may start in -----------
+            //   FASTQ: piece i emits iff (state0 + i) % 4 == 1: field i % 4;  FASTA: only piece 0 (when it continues
+            //   a line of the previous supertile) depends on the state: field 0 = sequence, field 1 = header
+            const bool ls0 = rawb[-1] == '\n';
+            for (uint32_t i = i_lo; i < i_hi; ++i) {
+                const uint32_t start = i ? (uint32_t)s_nl[i - 1] + 1u : 0u;
+                const bool has_nl = i < N;
+                const uint32_t end = has_nl ? (uint32_t)s_nl[i] : blen;
+                const uint32_t len = end - start;
+                const uint32_t pb = rawb[(int)end - 1];
+                const uint32_t klen = len - ((len > 0u && pb == '\r') ? 1u : 0u);
+                if (MODE == MODE_LINES) vsum += klen + (has_nl ? 1u : 0u);
+                else if (MODE == MODE_FASTQ) {
+                    vsum += (unsigned long long)(klen + (has_nl ? 1u : 0u)) << (16u * (i & 3u));
+                    if (has_nl && i < 3u) seam_st->first[i] = (B0 + end) | (pb == '\r' ? 0x80000000u : 0u);   // for front_fix_kernel's seam check
+                } else {
+                    const unsigned long long both = 0x0000000000010001ULL;
+                    if (i > 0u || ls0) vsum += ((start < blen && rawb[start] == '>') ? 1u : klen) * both;
+                    else vsum += klen;
+                }
+            }
+            if (MODE == MODE_FASTQ && tid == 0) {   // the supertile's last three newlines, for the seam checks
+                const uint32_t n0 = N > 3u ? N - 3u : 0u;
+                for (uint32_t q = n0; q < N; ++q) {
+                    const uint32_t pos = s_nl[q];
+                    seam_st->last[3u - (N - q)] = (B0 + pos) | (rawb[(int)pos - 1] == '\r' ? 0x80000000u : 0u);
+                }
+                seam_st->n = N;
+            }
+            // The workers do not wait for the look-back: they go on with a GUESS of the state and check it at the end
+            // (wrong: 3b and 4 are redone).  FASTQ: a line that starts with '@' and whose second next line starts with
+            // '+' is a header line in any well-formed file; FASTA: the supertile rarely starts inside a header line.
+            if (MODE != MODE_LINES && tid == (int)PF_WT - 1) {
+                uint32_t guess = MODE == MODE_FASTA ? 0u : 0xFFu;
+                if (MODE == MODE_FASTQ) {
+                    for (uint32_t i = ls0 ? 0u : 1u; i + 2u <= N && i < 12u; ++i) {
+                        const uint32_t s_i = i ? (uint32_t)s_nl[i - 1] + 1u : 0u, s_i2 = (uint32_t)s_nl[i + 1] + 1u;
+                        if (s_i2 < blen && rawb[s_i] == '@' && rawb[s_i2] == '+') { guess = (4u - (i & 3u)) & 3u; break; }
+                    }
+                }
+                s_misc[M_GUESS] = guess;
+            }
+            // exclusive scan over the worker threads
+            unsigned long long x = vsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long n = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += n;
+            }
+            named_sync(2, PF_WT);                    // sh16l: the first scan's reads are over
+            if (lane == 31u) sh16l[wid] = x;
+            named_sync(2, PF_WT);
+            unsigned long long base = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < PF_LB; ++w) {
+                const unsigned long long sv = sh16l[w];
+                if (w < wid) base += sv;
+                vtot += sv;
+            }
+            vex = base + x - vsum;
         }
     }
-    __syncthreads();
-    const uint32_t state0 = MODE == MODE_LINES ? 0u : s_misc[M_STATE];   // state of the line holding the previous byte
-
     uint32_t out_off = 0;
     int bases_delta = 0;
     uint32_t recs = 0, bad_rel = 0xFFFFFFFFu, lbad = 0xFFFFFFFFu;        // chunk-relative positions
-    if (!declined) {
-        // ---- 3. pieces -> entries ---------------------------------------------------------------------
-        const uint32_t NP = N + 1u;
-        const uint32_t G = (NP + TILE_THREADS - 1u) / TILE_THREADS;
-        const uint32_t i_lo = min((uint32_t)tid * G, NP), i_hi = min(i_lo + G, NP);
+    // the listed words of pass A go behind the newline list when a redo may need the newlines again
+    const bool spec_room = N + 2u + (uint32_t)PF_BYTES / 16u <= (uint32_t)PF_LIST;
+    uint16_t *s_bw = spec_room ? s_nl + N + 1u : s_nl;
+    if (wid != PF_LB && MODE != MODE_LINES) {
+        const uint32_t guess = (declined || !spec_room) ? 0xFFu : s_misc[M_GUESS];
+        if (guess == 0xFFu) { named_sync(3, TILE_THREADS); state0 = s_misc[M_STATE]; have_state = true; }
+        else state0 = guess;
+    }
+    while (wid != PF_LB && !declined) {
+        // ---- 3b. pieces -> entries, with the state known (or guessed) ---------------------------------
+        const uint32_t vsel = MODE == MODE_FASTQ ? 16u * ((1u - state0) & 3u) : (MODE == MODE_FASTA ? 16u * (state0 & 1u) : 0u);
+        if (tid == 0) s_misc[M_T] = (uint32_t)(vtot >> vsel) & 0xFFFFu;
         const bool ls0 = rawb[-1] == '\n';
-        uint32_t sum = 0;
+        uint32_t sum = (uint32_t)(vex >> vsel) & 0xFFFFu;                // output offset of this thread's first piece
         for (uint32_t i = i_lo; i < i_hi; ++i) {
             const uint32_t start = i ? (uint32_t)s_nl[i - 1] + 1u : 0u;
             const bool has_nl = i < N;
@@ -1123,16 +1235,12 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
                     bases_delta += (int)len - ((has_nl && pb == '\r') ? 1 : 0);
                     L = klen; brk = has_nl ? 1u : 0u;
                 }
-                if (has_nl) {   // sequence / quality length check (see fastq_len_check)
-                    if (i >= 3u) {   // the record's four newlines are all in this supertile (klen is the quality's length)
-                        if (ph == 3u) {
-                            const uint32_t e1 = s_nl[i - 2], e0 = s_nl[i - 3];
-                            const uint32_t ls = e1 - e0 - 1u - (rawb[(int)e1 - 1] == '\r' ? 1u : 0u);
-                            if (ls != klen) lbad = min(lbad, B0 + e0);
-                        }
-                    } else {         // the first three newlines: left to the seam check of front_fix_kernel
-                        seam_st->first[i] = (B0 + end) | (pb == '\r' ? 0x80000000u : 0u);
-                    }
+                // sequence / quality length check (see fastq_len_check) of a record whose four newlines are all in
+                // this supertile (klen is the quality's length); the first three newlines: front_fix_kernel
+                if (has_nl && i >= 3u && ph == 3u) {
+                    const uint32_t e1 = s_nl[i - 2], e0 = s_nl[i - 3];
+                    const uint32_t ls = e1 - e0 - 1u - (rawb[(int)e1 - 1] == '\r' ? 1u : 0u);
+                    if (ls != klen) lbad = min(lbad, B0 + e0);
                 }
             } else {  // MODE_FASTA
                 const bool hdr = line_start ? (start < blen && rawb[start] == '>') : ((state0 & 1u) != 0u);
@@ -1159,33 +1267,20 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
             e_src[i] = (uint16_t)((start & 0x7FFFu) | (brk << 15));
             e_len[i] = (uint16_t)L;
             e_out[i] = (uint16_t)sum;
-            sum += L + brk;
-        }
-        if (MODE == MODE_FASTQ && tid == 0) {   // the supertile's last three newlines, for the seam checks
-            const uint32_t n0 = N > 3u ? N - 3u : 0u;
-            for (uint32_t q = n0; q < N; ++q) {
-                const uint32_t pos = s_nl[q];
-                seam_st->last[3u - (N - q)] = (B0 + pos) | (rawb[(int)pos - 1] == '\r' ? 0x80000000u : 0u);
-            }
-            seam_st->n = N;
-        }
-        uint32_t T;
-        const uint32_t exo = block_exscan_add(sum, sh8, T);
-        for (uint32_t i = i_lo; i < i_hi; ++i) {
-            const uint32_t eo = (uint32_t)e_out[i] + exo;
-            const uint32_t outlen = (uint32_t)e_len[i] + ((uint32_t)e_src[i] >> 15);
-            e_out[i] = (uint16_t)eo;
+            const uint32_t outlen = L + brk;
             if (outlen) {   // words whose first byte this entry provides
-                const uint32_t w_hi = (eo + outlen - 1u) >> 4;
-                for (uint32_t w = (eo + 15u) >> 4; w <= w_hi; ++w) s_first[w] = (uint16_t)i;
+                const uint32_t w_hi = (sum + outlen - 1u) >> 4;
+                for (uint32_t w = (sum + 15u) >> 4; w <= w_hi; ++w) s_first[w] = (uint16_t)i;
             }
+            sum += outlen;
         }
-        __syncthreads();
+        named_sync(2, PF_WT);
+        const uint32_t T = s_misc[M_T];
         // ---- 4. aligned output words ------------------------------------------------------------------
         // Pass A: every word that comes out of ONE line whole: unaligned 16-byte read, SIMD-in-register codes, one
         // aligned store.  The others are listed and done in pass B by as few warps as it takes.
         const uint32_t W = (T + 15u) >> 4;
-        for (uint32_t w = tid; w < W; w += TILE_THREADS) {
+        for (uint32_t w = tid; w < W; w += PF_WT) {
             const uint32_t i = s_first[w];
             const uint32_t d = 16u * w - (uint32_t)e_out[i];
             if (d + 16u <= (uint32_t)e_len[i]) {
@@ -1210,10 +1305,10 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
             }
             s_bw[atomicAdd(&s_misc[M_NBW], 1u)] = (uint16_t)w;
         }
-        __syncthreads();
+        named_sync(2, PF_WT);
         // Pass B: the listed words, densely over the threads
         const uint32_t nbw = s_misc[M_NBW];
-        for (uint32_t idx = tid; idx < nbw; idx += TILE_THREADS) {
+        for (uint32_t idx = tid; idx < nbw; idx += PF_WT) {
             const uint32_t w = s_bw[idx];
             uint32_t filled = 0;
             uint32_t pos = 16u * w;                            // output position within the region
@@ -1277,9 +1372,19 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
             *reinterpret_cast<uint4 *>(region + 16u * w) = make_uint4((uint32_t)alo, (uint32_t)(alo >> 32), (uint32_t)ahi, (uint32_t)(ahi >> 32));
         }
         out_off = T;
-        __syncthreads();
-        if (s_misc[M_DECL]) declined = true;                   // uniform: read after the barrier
+        if (have_state) break;
+        // the guess against the look-back's answer
+        named_sync(3, TILE_THREADS);
+        have_state = true;
+        if (s_misc[M_STATE] == state0) break;
+        state0 = s_misc[M_STATE];
+        bases_delta = 0; recs = 0; bad_rel = 0xFFFFFFFFu; lbad = 0xFFFFFFFFu;
+        named_sync(2, PF_WT);                                  // everyone has read the pass-B list and the flags
+        if (tid == 0) { s_misc[M_NBW] = 0; s_misc[M_DECL] = 0; }
+        named_sync(2, PF_WT);
     }
+    __syncthreads();
+    if (s_misc[M_DECL]) declined = true;                       // uniform: read after the barrier
 
     if (declined) {   // anything the fast path does not do: the exact tile walk, from the supertile's start state
         __syncthreads();

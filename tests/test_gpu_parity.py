@@ -995,3 +995,65 @@ def test_repetitive_input(fb, oracle):
     assert gtotals == ototals
     assert_same(gres, ovec, 21)
     assert int(ovec["counts"].max()) >= 40000 - 1
+
+
+# ---- fused single-pass parse: the workers' guess of a supertile's start state ---------------------
+@pytest.mark.parametrize("st_tiles", ["1", "8"])
+def test_fused_parse_wrong_fastq_guess_is_redone(fb, oracle, monkeypatch, st_tiles):
+    """parse_fused_kernel guesses the line phase at the start of a supertile from the first '@' line whose second next
+    line starts with '+', and checks the guess against the look-back.  Here every quality line starts with '@' and
+    every sequence line with '+' (a kept non-base), so the first candidate is a QUALITY line for about half of the
+    supertiles: the guess is wrong there and the supertile must be redone."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    monkeypatch.setenv("FB2_ST_TILES", st_tiles)
+    rng = np.random.default_rng(77 + int(st_tiles))
+    recs = []
+    for r in range(14000):
+        m = int(rng.integers(30, 120))
+        s = b"+" + gen.rand_seq(rng, m, 0.0)
+        q = b"@" + bytes(rng.integers(33, 74, size=m).astype(np.uint8))
+        recs.append(b"@r%d\n" % r + s + b"\n+\n" + q + b"\n")
+    data = b"".join(recs)
+    assert len(data) > (2 << 20)
+    want, totals, _ = oracle_sketch(oracle, data, "mash", 5000, 21, 0)
+    got = gpu_sketch(fb, data, "mash", 5000, 21, 0)
+    assert_same(got[0], want, 21)
+    assert got[1] == totals
+
+
+@pytest.mark.parametrize("st_tiles", ["1", "8"])
+def test_fused_parse_header_lines_across_supertiles(fb, oracle, monkeypatch, st_tiles):
+    """FASTA: the guess is 'the supertile does not start inside a header line'; header lines of several KiB make it
+    wrong (and some supertiles hold no line start at all: identity in the look-back)."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    monkeypatch.setenv("FB2_ST_TILES", st_tiles)
+    rng = np.random.default_rng(91 + int(st_tiles))
+    parts = []
+    for r in range(60):
+        hdr = b">" + bytes(rng.integers(65, 91, size=int(rng.integers(10, 70000))).astype(np.uint8))   # ACGT in headers too
+        seq = gen.rand_seq(rng, int(rng.integers(100, 90000)), 0.001)
+        width = int(rng.integers(40, 50000))
+        lines = [seq[i:i + width] for i in range(0, len(seq), width)]
+        parts.append(hdr + b"\n" + b"\n".join(lines) + b"\n")
+    data = b"".join(parts)
+    assert len(data) > (2 << 20)
+    want, totals, _ = oracle_sketch(oracle, data, "mash", 5000, 21, 0)
+    got = gpu_sketch(fb, data, "mash", 5000, 21, 0)
+    assert_same(got[0], want, 21)
+    assert got[1] == totals
+
+
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+def test_three_kernel_parse_still_matches(fb, synth, oracle, monkeypatch, fmt):
+    """FB2_PARSE_V1=1: the phase / scan / pack pipeline the fused kernel replaced (kept as the A/B baseline)."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    monkeypatch.setenv("FB2_PARSE_V1", "1")
+    genome = synth.synth_genome(300_000, 5)
+    if fmt == "fastq":
+        data = synth.synth_fastq(genome, 20000, 150, 0.005, 6)[0].tobytes()
+    else:
+        data = synth.synth_fasta(400_000, n_records=7, line_width=70, lower_frac=0.05, n_frac=0.001, seed=9).tobytes()
+    want, totals, _ = oracle_sketch(oracle, data, "mash", 2000, 21, 0)
+    got = gpu_sketch(fb, data, "mash", 2000, 21, 0)
+    assert_same(got[0], want, 21)
+    assert got[1] == totals
