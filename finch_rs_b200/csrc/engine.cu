@@ -123,6 +123,7 @@ struct fb2_sketcher {
     size_t chunk_bytes = 0;
     DevBuf d_raw[2], d_sym[2], d_stmap, d_ststate, d_rcount[2], d_tail, d_carry, d_state, d_seam;
     // fused single-pass parse (parse.cu, parse_fused_kernel): d_stmap holds the look-back status words
+    DevBuf d_fhist, d_fok;           // device-side sketch filters: histogram of counts (+ 4 meta words), strand flags
     DevBuf d_ticket;                 // supertile ticket counter (never reset: launches pass its value so far)
     uint32_t ticket_total = 0;
     uint32_t parse_epoch = 0;        // 1..65535, one per chunk; the status words are cleared when it wraps
@@ -424,7 +425,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
         if (s->h_snap[i]) cudaFreeHost(s->h_snap[i]);
         if (s->ev_chunk[i]) cudaEventDestroy(s->ev_chunk[i]);
     }
-    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release(); s->d_seam.release(); s->d_ticket.release();
+    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release(); s->d_seam.release(); s->d_ticket.release(); s->d_fhist.release(); s->d_fok.release();
     s->d_carry.release(); s->d_state.release();
     s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release(); s->d_bins.release(); s->d_live_bins.release();
     s->out_hash.release(); s->out_cnt.release(); s->out_ext.release(); s->out_kmer.release(); s->out_posx.release();
@@ -1541,6 +1542,7 @@ extern "C" void fb2_result_free(fb2_result *r) {
 }
 
 // hostlogic.cpp
+uint32_t fb2_threshold_from_hist(const std::vector<uint64_t> &hist, double filter_level);
 int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, fb2_filter *f, int format,
                       std::vector<uint32_t> &keep, size_t limit);
 
@@ -1590,7 +1592,7 @@ static int export_sorted(fb2_sketcher *s, uint32_t *keep_out) {
 }
 
 // Bring m exported rows to the host as an fb2_result: rows idx[0..m) (device indices) or the first m.
-static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_result *out) {
+static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_result *out, bool idx_on_device = false) {
     const size_t stride = (size_t)s->k;   // pushed k-mers may be longer: fixed up below
     out->n = m;
     out->hashes = (uint64_t *)malloc(std::max<size_t>(1, (size_t)m * 8));
@@ -1605,8 +1607,8 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
     if (m) {
         TRY(s->sel_hash.ensure((size_t)m * 8)); TRY(s->sel_kmer.ensure((size_t)m * 8)); TRY(s->sel_posx.ensure((size_t)m * 8));
         TRY(s->sel_cnt.ensure((size_t)m * 4)); TRY(s->sel_ext.ensure((size_t)m * 4)); TRY(s->sel_bytes.ensure((size_t)m * stride));
-        const uint32_t *d_idx = nullptr;
-        if (h_idx) {
+        const uint32_t *d_idx = idx_on_device ? s->sel_idx.as<uint32_t>() : nullptr;   // left there by filter_select_kernel
+        if (h_idx && !idx_on_device) {
             TRY(s->sel_idx.ensure((size_t)m * 4));
             CU(cudaMemcpyAsync(s->sel_idx.p, h_idx, (size_t)m * 4, cudaMemcpyHostToDevice, s->st));
             s->stats.h2d_bytes += (size_t)m * 4;
@@ -1705,7 +1707,58 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
     std::vector<uint32_t> sel;
     const uint32_t *idx = nullptr;
     uint32_t m = keep;
-    if (ff.filter_on == 1 && keep) {
+    bool idx_on_device = false;
+    if (ff.filter_on == 1 && keep && !getenv("FB2_HOST_FILTER")) {
+        // the filters on the device (table.cu, filter_pass / filter_select): per-entry decisions in parallel, the
+        // host only walks the histogram of counts (guess_filter_threshold); counts past FILTER_HCAP: host path below
+        constexpr uint32_t FILTER_HCAP = 1u << 16;
+        const bool strand = ff.strand_filter > 0.0, err = ff.err_filter > 0.0;
+        TRY(s->d_fhist.ensure((size_t)FILTER_HCAP * 4 + 16)); TRY(s->d_fok.ensure(keep));
+        uint32_t *d_hist = s->d_fhist.as<uint32_t>(), *d_meta = d_hist + FILTER_HCAP;
+        bool device_ok = true;
+        if (strand || err) {
+            CU(cudaMemsetAsync(d_hist, 0, (size_t)FILTER_HCAP * 4 + 16, s->st));
+            launch_filter_pass(s->out_cnt.as<uint32_t>(), s->out_ext.as<uint32_t>(), keep, strand ? 1 : 0, ff.strand_filter,
+                               err ? 1 : 0, d_hist, FILTER_HCAP, s->d_fok.as<uint8_t>(), d_meta, s->st);
+            s->stats.kernel_launches++;
+        }
+        if (err) {
+            TRY(ensure_hres(s, (size_t)FILTER_HCAP * 4 + 16));
+            uint32_t *h_meta = (uint32_t *)s->h_res, *h_hist = h_meta + 4;
+            CU(cudaMemcpyAsync(h_meta, d_meta, 8, cudaMemcpyDeviceToHost, s->st));
+            CU(cudaMemcpyAsync(h_hist, d_hist, 4096 * 4, cudaMemcpyDeviceToHost, s->st));    // nearly always enough
+            CU(cudaStreamSynchronize(s->st));
+            const uint32_t over = h_meta[0], maxc = h_meta[1];
+            if (over) device_ok = false;
+            else {
+                if (maxc > 4096u) {
+                    CU(cudaMemcpyAsync(h_hist, d_hist, (size_t)maxc * 4, cudaMemcpyDeviceToHost, s->st));
+                    CU(cudaStreamSynchronize(s->st));
+                }
+                s->stats.d2h_bytes += 8 + (size_t)std::max(maxc, 4096u) * 4;
+                std::vector<uint64_t> hist(maxc);
+                for (uint32_t c = 0; c < maxc; ++c) hist[c] = h_hist[c];
+                const uint32_t cutoff = fb2_threshold_from_hist(hist, ff.err_filter);    // filtering.rs:68-79
+                if (ff.has_abun_low) { if (cutoff > ff.abun_low) ff.abun_low = cutoff; }
+                else { ff.has_abun_low = 1; ff.abun_low = cutoff; }
+            }
+        }
+        if (device_ok) {
+            const uint32_t limit = p->kind == FB2_KIND_MASH ? (uint32_t)std::min<uint64_t>(p->final_size, keep) : keep;
+            TRY(s->sel_idx.ensure((size_t)std::max(limit, 1u) * 4));
+            launch_filter_select(s->out_cnt.as<uint32_t>(), s->d_fok.as<uint8_t>(), keep, strand ? 1 : 0,
+                                 (ff.has_abun_low || ff.has_abun_high) ? 1 : 0, ff.has_abun_low ? ff.abun_low : 0u,
+                                 ff.has_abun_high ? ff.abun_high : UINT32_MAX, limit, s->sel_idx.as<uint32_t>(), d_meta, s->st);
+            s->stats.kernel_launches++;
+            TRY(ensure_hres(s, 16));
+            CU(cudaMemcpyAsync(s->h_res, d_meta + 2, 4, cudaMemcpyDeviceToHost, s->st));
+            CU(cudaStreamSynchronize(s->st));
+            m = *(uint32_t *)s->h_res;
+            idx_on_device = true;
+            if (trace) fprintf(stderr, "sketch(): device filter %.0f us (%u entries -> %u)\n", now() - t2, keep, m);
+        }
+    }
+    if (ff.filter_on == 1 && keep && !idx_on_device) {
         TRY(ensure_hres(s, (size_t)keep * 8));
         uint32_t *hc = (uint32_t *)s->h_res, *hx = hc + keep;
         CU(cudaMemcpyAsync(hc, s->out_cnt.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
@@ -1725,7 +1778,7 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
             return fb2_fail(FB2_ETOOFEW, std::string(name ? name : "") + " had too few kmers (" + std::to_string(m) +
                                              ") to sketch");
     }
-    const int rc = collect_rows(s, idx, m, out);
+    const int rc = collect_rows(s, idx, m, out, idx_on_device);
     if (trace) fprintf(stderr, "sketch(): flush/settle %.0f us, sort+export %.0f us, filter stage %.0f us, collect %.0f us\n",
                        t1 - t0, t2 - t1, t4 - t2, now() - t4);
     if (rc == FB2_OK) out->filters = ff;

@@ -55,18 +55,18 @@ static void compact(fb2_result *r, const std::vector<uint8_t> &keep) {
     r->n = m;
 }
 
-static uint32_t threshold_from_hist(const std::vector<uint64_t> &hist, double filter_level);
+uint32_t fb2_threshold_from_hist(const std::vector<uint64_t> &hist, double filter_level);
 extern "C" uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n, double filter_level) {
     // histogram of counts: hist[c-1] = number of k-mers seen c times (statistics.rs:30-47)
     uint32_t max_count = 0;
     for (size_t i = 0; i < n; ++i) max_count = std::max(max_count, counts[i]);
     std::vector<uint64_t> hist(max_count, 0);
     for (size_t i = 0; i < n; ++i) if (counts[i]) hist[counts[i] - 1]++;
-    return threshold_from_hist(hist, filter_level);
+    return fb2_threshold_from_hist(hist, filter_level);
 }
 
 // guess_filter_threshold (filtering.rs:154-195) from the histogram of counts: hist[c-1] = number of k-mers seen c times.
-static uint32_t threshold_from_hist(const std::vector<uint64_t> &hist, double filter_level) {
+uint32_t fb2_threshold_from_hist(const std::vector<uint64_t> &hist, double filter_level) {
     uint64_t total = 0;
     for (size_t c = 0; c < hist.size(); ++c) total += (uint64_t)(c + 1) * hist[c];
     const double cutoff_amt = filter_level * (double)total;
@@ -145,7 +145,7 @@ int fb2_filter_select(const uint32_t *counts, const uint32_t *extras, size_t n, 
         size_t max_count = hist.size();
         while (max_count && hist[max_count - 1] == 0) --max_count;
         hist.resize(max_count);
-        const uint32_t cutoff = threshold_from_hist(hist, f->err_filter);
+        const uint32_t cutoff = fb2_threshold_from_hist(hist, f->err_filter);
         if (f->has_abun_low) { if (cutoff > f->abun_low) f->abun_low = cutoff; }
         else { f->has_abun_low = 1; f->abun_low = cutoff; }
     }

@@ -61,6 +61,11 @@ void launch_export(const unsigned long long *keys, const uint32_t *slots, uint32
                    unsigned long long *o_hash, uint32_t *o_cnt, uint32_t *o_ext, unsigned long long *o_kmer,
                    unsigned long long *o_posx, cudaStream_t s);
 
+void launch_filter_pass(const uint32_t *cnt, const uint32_t *ext, uint32_t n, int strand, double cut, int err, uint32_t *hist,
+                        uint32_t hcap, uint8_t *ok, uint32_t *meta, cudaStream_t s);
+void launch_filter_select(const uint32_t *cnt, const uint8_t *ok, uint32_t n, int use_ok, int abun, uint32_t lo, uint32_t hi,
+                          uint32_t limit, uint32_t *idx_out, uint32_t *meta, cudaStream_t s);
+
 void launch_merge_tables(TableView src, unsigned long long src_thr, unsigned int src_has_max, TableView dst, SketchState *st,
                          cudaStream_t s);
 void launch_debug_bump(TableView t, unsigned long long key, unsigned long long add_cnt, unsigned long long add_ext,

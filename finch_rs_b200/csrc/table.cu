@@ -708,4 +708,80 @@ void launch_export(const unsigned long long *keys, const uint32_t *slots, uint32
     if (keep) export_kernel<<<cdiv(keep, 256), 256, 0, s>>>(keys, slots, keep, t, o_hash, o_cnt, o_ext, o_kmer, o_posx);
 }
 
+// ---- sketch filters on the exported columns (FilterParams::filter_counts, filtering.rs:60-87) -------------------
+// The host version (hostlogic.cpp, fb2_filter_select) walks 200 000 counts per C2 sketch; at the end of a stream
+// that is half a millisecond of an idle device.  Same decisions here, per entry in parallel:
+//   filter_pass_kernel  : strand filter flag (filter_strands, filtering.rs:413-432: the same f64 division, correctly
+//                         rounded on both sides) and the histogram of the counts that pass (statistics.rs:30-47),
+//                         up to FILTER_HCAP bins; larger counts are only counted -- the caller then takes the host path
+//   (host)              : guess_filter_threshold over that histogram (a walk over max-count bins)
+//   filter_select_kernel: abundance cut (filter_abundance, filtering.rs:329-343) and the first `limit` survivors,
+//                         in order, as row indices for select_rows
+constexpr uint32_t FILTER_SMEM_BINS = 2048;
+__global__ void filter_pass_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ ext, uint32_t n, int strand,
+                                   double cut, int err, uint32_t *__restrict__ hist, uint32_t hcap, uint8_t *__restrict__ ok,
+                                   uint32_t *meta /* [0] counts above hcap, [1] largest count that passed */) {
+    __shared__ uint32_t sh[FILTER_SMEM_BINS];
+    for (uint32_t i = threadIdx.x; i < FILTER_SMEM_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    uint32_t mx = 0, over = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = cnt[i];
+        bool pass = true;
+        if (strand && c >= 16u) {   // fewer observations are too noisy to call an adapter
+            const uint32_t e = ext[i], lowest = min(e, c - e);
+            pass = __ddiv_rn((double)lowest, (double)c) >= cut;
+        }
+        if (strand) ok[i] = pass ? 1 : 0;
+        if (err && pass && c) {
+            if (c <= FILTER_SMEM_BINS) atomicAdd(&sh[c - 1u], 1u);
+            else if (c <= hcap) atomicAdd(&hist[c - 1u], 1u);
+            else ++over;
+            mx = max(mx, c);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < FILTER_SMEM_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    over = __reduce_add_sync(0xffffffffu, over);
+    if ((threadIdx.x & 31u) == 0u) {
+        if (mx) atomicMax(&meta[1], mx);
+        if (over) atomicAdd(&meta[0], over);
+    }
+}
+// One block: the first `limit` rows that pass, ascending.  meta[2] = how many were written.
+__global__ void __launch_bounds__(1024)
+filter_select_kernel(const uint32_t *__restrict__ cnt, const uint8_t *__restrict__ ok, uint32_t n, int use_ok, int abun,
+                     uint32_t lo, uint32_t hi, uint32_t limit, uint32_t *__restrict__ idx_out, uint32_t *meta) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    uint32_t base = 0;
+    for (uint32_t tile = 0; tile < n && base < limit; tile += 1024u) {
+        const uint32_t i = tile + tid;
+        bool f = i < n;
+        if (f && use_ok) f = ok[i] != 0;
+        if (f && abun) { const uint32_t c = cnt[i]; f = lo <= c && c <= hi; }
+        const uint32_t b = __ballot_sync(0xffffffffu, f);
+        __syncthreads();                       // wsum from the previous tile
+        if (lane == 0u) wsum[wid] = __popc(b);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (uint32_t w = 0; w < 32u; ++w) { const uint32_t v = wsum[w]; if (w < wid) before += v; total += v; }
+        const uint32_t pos = base + before + __popc(b & ((1u << lane) - 1u));
+        if (f && pos < limit) idx_out[pos] = i;
+        base += total;
+    }
+    if (tid == 0u) meta[2] = min(base, limit);
+}
+void launch_filter_pass(const uint32_t *cnt, const uint32_t *ext, uint32_t n, int strand, double cut, int err, uint32_t *hist,
+                        uint32_t hcap, uint8_t *ok, uint32_t *meta, cudaStream_t s) {
+    if (!n) return;
+    filter_pass_kernel<<<min(cdiv(n, 256), 296u), 256, 0, s>>>(cnt, ext, n, strand, cut, err, hist, hcap, ok, meta);
+}
+void launch_filter_select(const uint32_t *cnt, const uint8_t *ok, uint32_t n, int use_ok, int abun, uint32_t lo, uint32_t hi,
+                          uint32_t limit, uint32_t *idx_out, uint32_t *meta, cudaStream_t s) {
+    filter_select_kernel<<<1, 1024, 0, s>>>(cnt, ok, n, use_ok, abun, lo, hi, limit, idx_out, meta);
+}
+
 }  // namespace fb2
