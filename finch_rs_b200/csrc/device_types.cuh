@@ -49,7 +49,24 @@ struct ParseCarry {
     uint64_t last_nl[2][3];  // the last three newlines of the stream before / after the current chunk (ascending;
                              // stream position, bit 63 = preceded by a CR; ~0 = none); halves alternate per chunk
     uint32_t state_next;     // fused parse: line state after the current chunk (its last supertile writes it while other
-    uint32_t pad_;           // blocks may still read `state`; front_fix_kernel commits it to `state`)
+                             // blocks may still read `state`; front_fix_kernel commits it to `state`)
+    uint32_t max_region_pieces;  // largest hash-piece count of a region of the current chunk: bounds the hash kernel's item space
+};
+// Hash pieces: what a lane of the hash kernel walks.  The parse kernel lists, per region, runs of k-mer END positions
+// (p0 | n << 16: positions [p0, p0 + n) of the region) that together hold every position a valid k-mer can end at,
+// each exactly once.  For records with short sequences (reads) a run never starts inside the k - 1 positions after a
+// record break -- those windows all hold the break -- and a record's positions are cut into runs of nearly equal
+// length <= pmax, so that 32 consecutive runs span at most PIECE_SPAN symbols (= what a warp stages at once);
+// otherwise runs are the uniform 64-position slices of the region.
+constexpr uint32_t PIECE_STRIDE = 1024;     // table entries per region (uniform slices need 512)
+constexpr uint32_t PIECE_SPAN = 2144;       // 32 * (pmax + k): bound on the symbols under 32 consecutive pieces of records
+struct PiecePlan {
+    uint32_t *table;         // n_st * stride entries (nullptr: no plan, k > 32)
+    uint32_t *count;         // pieces per region
+    uint32_t stride;         // PIECE_STRIDE
+    uint32_t k;              // k-mer length
+    uint32_t pmax;           // longest run of a record: PIECE_SPAN / 32 - k
+    uint32_t pmax_inv;       // ceil(2^22 / pmax): x / pmax == (x * pmax_inv) >> 22 for x < 2^15 + pmax
 };
 constexpr unsigned long long NL_NONE = ~0ULL;
 

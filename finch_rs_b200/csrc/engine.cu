@@ -123,6 +123,8 @@ struct fb2_sketcher {
     size_t chunk_bytes = 0;
     DevBuf d_raw[2], d_sym[2], d_stmap, d_ststate, d_rcount[2], d_tail, d_carry, d_state, d_seam;
     // fused single-pass parse (parse.cu, parse_fused_kernel): d_stmap holds the look-back status words
+    DevBuf d_ptab[2], d_pcount[2];   // hash pieces planned by the parse kernel (PiecePlan), per chunk parity
+    bool rec_pieces = true;          // FB2_PIECES=0: uniform 64-position pieces only (A/B)
     DevBuf d_fhist, d_fok;           // device-side sketch filters: histogram of counts (+ 4 meta words), strand flags
     DevBuf d_ticket;                 // supertile ticket counter (never reset: launches pass its value so far)
     uint32_t ticket_total = 0;
@@ -375,6 +377,7 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
 
     s->chunk_bytes = env_size("FB2_CHUNK_MB", 128) << 20;
     s->parse_fused = !getenv("FB2_PARSE_V1");
+    s->rec_pieces = !(getenv("FB2_PIECES") && atoi(getenv("FB2_PIECES")) == 0);
     if (s->chunk_bytes < (1u << 20)) s->chunk_bytes = 1u << 20;
     if (s->chunk_bytes > (1ull << 30)) s->chunk_bytes = 1ull << 30;
 
@@ -421,7 +424,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     timing_resolve(s);
     for (auto &p : s->ev_free) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int i = 0; i < 2; ++i) {
-        s->d_sym[i].release(); s->d_rcount[i].release(); s->log_hash[i].release(); s->log_kmer[i].release(); s->log_posx[i].release();
+        s->d_sym[i].release(); s->d_rcount[i].release(); s->d_ptab[i].release(); s->d_pcount[i].release(); s->log_hash[i].release(); s->log_kmer[i].release(); s->log_posx[i].release();
         if (s->h_snap[i]) cudaFreeHost(s->h_snap[i]);
         if (s->ev_chunk[i]) cudaEventDestroy(s->ev_chunk[i]);
     }
@@ -653,6 +656,17 @@ static int absorb_log(fb2_sketcher *s, int par, uint32_t cnt) {
 }
 
 // ---- one chunk of raw bytes resident in HBM ---------------------------------------------------------
+// The hash pieces of a chunk (device_types.cuh, PiecePlan): the parse kernel fills the table, the hash kernel walks it.
+static PiecePlan piece_plan(const fb2_sketcher *s, int par) {
+    PiecePlan pp;
+    memset(&pp, 0, sizeof(pp));
+    if (s->k > 32) return pp;                      // hash_big_kernel walks the regions itself
+    pp.table = s->d_ptab[par].as<uint32_t>(); pp.count = s->d_pcount[par].as<uint32_t>();
+    pp.stride = PIECE_STRIDE; pp.k = (uint32_t)s->k;
+    pp.pmax = s->rec_pieces ? PIECE_SPAN / 32u - (uint32_t)s->k : 0u;   // 0: uniform pieces only
+    pp.pmax_inv = pp.pmax ? ((1u << 22) + pp.pmax - 1u) / pp.pmax : 0u;
+    return pp;
+}
 static ChunkGeom make_geom(uint32_t len) {
     ChunkGeom g;
     g.len = len;
@@ -721,7 +735,7 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
         const bool timed = timing_begin(s, evp);
         // candidate-dense launches (infinite / provisional threshold, early ramp) reserve log slots in big batches
         launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, b, b + nb, s->d_rcount[par].as<uint32_t>(),
-                    (const ParseCarry *)s->d_carry.p, ord_base, dst, slot, log_view(s, par), s->prm.hash_seed, 31u, s->st);
+                    (const ParseCarry *)s->d_carry.p, ord_base, dst, slot, log_view(s, par), s->prm.hash_seed, 31u, piece_plan(s, par), s->st);
         if (timed) timing_end(s, evp, s->ev_hash_pending);
         s->stats.kernel_launches++; s->stats.hash_launches++;
         TRY(pull_state(s));
@@ -821,6 +835,8 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     TRY(s->d_stmap.ensure((size_t)g.n_st * 4)); TRY(s->d_ststate.ensure((size_t)g.n_st * 4));
     const bool status_fresh = s->d_stmap.p != stmap_was;
     TRY(s->d_rcount[par].ensure((size_t)g.n_st * 4));
+    if (s->k <= 32) { TRY(s->d_ptab[par].ensure((size_t)g.n_st * PIECE_STRIDE * 4)); TRY(s->d_pcount[par].ensure((size_t)g.n_st * 4)); }
+    const PiecePlan pp = piece_plan(s, par);
     if (mode == MODE_FASTQ) TRY(s->d_seam.ensure((size_t)g.n_st * sizeof(SeamNl)));
     TRY(s->d_sym[par].ensure((size_t)SYM_FRONT + (size_t)g.n_st * g.region_stride + 2 * HASH_TILE));
     ParseCarry *dc = (ParseCarry *)s->d_carry.p;
@@ -840,12 +856,13 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
         }
         launch_parse_fused(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym[par].as<uint8_t>(), s->d_rcount[par].as<uint32_t>(),
                            tail_in, tail_out, s->d_seam.as<SeamNl>(), s->tail_sel, s->halo, s->d_stmap.as<uint32_t>(), s->parse_epoch,
-                           s->d_ticket.as<uint32_t>(), s->ticket_total, s->st);
+                           s->d_ticket.as<uint32_t>(), s->ticket_total, pp, s->st);
         s->ticket_total += g.n_st;
     } else {
         launch_phase(mode, d_raw, g, dc, s->d_stmap.as<uint32_t>(), s->d_ststate.as<uint32_t>(), s->st);
         launch_pack(mode, d_raw, g, dc, s->d_ststate.as<uint32_t>(), s->d_sym[par].as<uint8_t>(), s->d_rcount[par].as<uint32_t>(),
                     tail_in, tail_out, s->d_seam.as<SeamNl>(), s->tail_sel, s->halo, s->st);
+        launch_uniform_pieces(s->d_rcount[par].as<uint32_t>(), g.n_st, pp, dc, s->st);
     }
     if (parse_timed) timing_end(s, evparse, s->ev_parse_pending);
     if (rawbuf >= 0) { CU(cudaEventRecord(s->ev_rawfree[rawbuf], s->st)); s->rawfree_pending[rawbuf] = true; }
@@ -871,7 +888,7 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
         fb2_sketcher::EvPair evp;
         const bool timed = timing_begin(s, evp);
         launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, total_blocks, s->d_rcount[par].as<uint32_t>(), dc, ord_base, dst,
-                    slot, log_view(s, par), s->prm.hash_seed, 3u, s->st);
+                    slot, log_view(s, par), s->prm.hash_seed, 3u, pp, s->st);
         if (timed) timing_end(s, evp, s->ev_hash_pending);
         if (ab != s->st) {
             CU(cudaEventRecord(s->ev_hash[par], s->st));
@@ -1508,7 +1525,7 @@ size_t fb2_sketcher_chunk_bytes(const fb2_sketcher *s) { return s->chunk_bytes; 
 size_t fb2_sketcher_device_bytes(const fb2_sketcher *s) {
     size_t n = 0;
     const DevBuf *bufs[] = {&s->d_raw[0], &s->d_raw[1], &s->d_sym[0], &s->d_sym[1], &s->d_stmap, &s->d_ststate, &s->d_rcount[0],
-                            &s->d_rcount[1], &s->d_tail, &s->d_carry, &s->d_state, &s->d_seam, &s->log_hash[0], &s->log_hash[1],
+                            &s->d_rcount[1], &s->d_ptab[0], &s->d_ptab[1], &s->d_pcount[0], &s->d_pcount[1], &s->d_tail, &s->d_carry, &s->d_state, &s->d_seam, &s->log_hash[0], &s->log_hash[1],
                             &s->log_kmer[0], &s->log_kmer[1], &s->log_posx[0], &s->log_posx[1], &s->sort_keys, &s->sort_slots,
                             &s->sort_tkeys, &s->sort_tslots, &s->sort_hist, &s->d_bins, &s->d_live_bins, &s->out_hash, &s->out_cnt,
                             &s->out_ext, &s->out_kmer, &s->out_posx, &s->sel_hash, &s->sel_cnt, &s->sel_ext, &s->sel_kmer, &s->sel_posx,

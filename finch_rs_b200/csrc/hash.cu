@@ -307,10 +307,12 @@ struct Roll2 {
 // the copy of the next item is in flight while the current one is hashed; there is no block-wide
 // synchronisation after the table build.
 constexpr int HP_WARPS = 32;
-constexpr int HP_NBUF = 2;
-constexpr uint32_t HP_SLICE = 32u * HASH_W;                  // positions per item
-constexpr uint32_t HP_BUF = 32u + HP_SLICE;                  // bytes per warp buffer (multiple of 16)
-constexpr uint32_t HP_ITEMS_PER_TILE = HASH_TILE / HP_SLICE; // launch ranges are given in HASH_TILE blocks
+constexpr int HP_NBUF = 2;               // (the main loop is written for two)
+constexpr uint32_t HP_SLICE = 32u * HASH_W;                  // positions per item of uniform 64-position pieces
+constexpr uint32_t HP_BUF = 2208u;                           // bytes per warp buffer (multiple of 16): 32-symbol halo + up to 15
+                                                             // symbols of alignment + PIECE_SPAN symbols + rounding
+constexpr uint32_t HP_SPAN_MAX = HP_BUF - 32u - 16u;         // symbols from the aligned start a staged group may cover
+static_assert(HP_SPAN_MAX >= PIECE_SPAN + 15u && HP_SPAN_MAX >= HP_SLICE + 15u, "a full group of planned pieces must fit the buffer");
 constexpr uint32_t HP_OFF_C1_64 = 0;
 constexpr uint32_t HP_OFF_C2_64 = HP_OFF_C1_64 + 256u * HP_R64 * 8u;
 constexpr uint32_t HP_OFF_C1_32 = HP_OFF_C2_64 + 256u * HP_R64 * 8u;
@@ -328,7 +330,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
             ChunkGeom g, uint32_t r0, uint32_t n_regions, // regions [r0, r0 + n_regions) of this launch
             const uint32_t *__restrict__ region_count, const ParseCarry *__restrict__ carry, uint64_t ord_base,
             const SketchState *st,
-            LaunchSlot *slot, LogView log, int k_rt, uint64_t seed, HashConsts hc) {
+            LaunchSlot *slot, LogView log, int k_rt, uint64_t seed, HashConsts hc, PiecePlan pp) {
     extern __shared__ __align__(128) uint8_t hp_smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // ---- tables (once per CTA) and the warps' mbarriers ----
@@ -377,34 +379,46 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
     const uint32_t T_hi = (uint32_t)(T >> 32);
     U2 seed2; seed2.lo = (uint32_t)seed; seed2.hi = (uint32_t)(seed >> 32);
 
-    // Work items in SLICE-major order: item it = slice (it / n_regions) of region r0 + it % n_regions.  Regions are
-    // rarely full (FASTQ: ~48 % of the raw bytes are symbols), so the item space is cut at the largest
-    // region of the chunk (pack_kernel keeps the maximum): slices past it are never claimed, and the items
-    // a warp does claim are live except in the last slice of shorter regions.  Items are claimed from a
-    // per-launch counter (dynamic balance; a static round-robin would resonate with the region layout).
-    const uint32_t slices = min((carry->max_region_syms + HP_SLICE - 1u) / HP_SLICE, (g.st_bytes + HP_SLICE - 1u) / HP_SLICE);
-    const uint32_t w1 = slices * n_regions;      // one past the last item
-    uint32_t it_region = 0, it_pb = 0, it_end = 0;
-    auto next_live = [&]() -> uint32_t {
-        while (true) {
+    // Work: the hash pieces the parse kernel planned (PiecePlan, device_types.cuh): runs of k-mer end positions, a
+    // lane walks one.  An item is a group of 32 consecutive pieces of one region, in GROUP-major order (item it = group
+    // it / n_regions of region r0 + it % n_regions) so that concurrently running warps spread over the regions; the item
+    // space is cut at the chunk's largest piece count, and items are claimed from a per-launch counter.  The symbols
+    // under a group (from 32 in front of its first position, 16-byte aligned, to its last position) are staged with
+    // one TMA copy; a group whose pieces lie further apart than the buffer (records without any k-mer in between) is
+    // taken in several rounds.
+    const uint32_t groups = min((carry->max_region_pieces + 31u) / 32u, (pp.stride + 31u) / 32u);
+    const uint32_t w1 = groups * n_regions;      // one past the last item
+    uint32_t it_region = 0, it_i0 = 0, it_i1 = 0;                 // pieces [it_i0, it_i1) of the claimed item not staged yet
+    uint32_t nx_region = 0, nx_pbal = 0, nx_bytes = 0, nx_piece = 0;   // the group staged next (nx_piece: this lane's piece, 0 = none)
+    auto next_group = [&]() -> bool {
+        while (it_i0 >= it_i1) {
             uint32_t it = 0;
             if (lane == 0) it = atomicAdd(&slot->next_item, 1u);
             it = __shfl_sync(0xffffffffu, it, 0);
-            if (it >= w1) return w1;
-            const uint32_t slice = it / n_regions, region = r0 + (it - slice * n_regions);
-            const uint32_t pb = slice * HP_SLICE, end = region_count[region];
-            if (pb < end) { it_region = region; it_pb = pb; it_end = end; return it; }
+            if (it >= w1) return false;
+            const uint32_t grp = it / n_regions, region = r0 + (it - grp * n_regions);
+            const uint32_t np = min(pp.count[region], pp.stride);
+            if (32u * grp < np) { it_region = region; it_i0 = 32u * grp; it_i1 = min(np, 32u * grp + 32u); }
         }
+        const uint32_t idx = it_i0 + lane;
+        uint32_t piece = idx < it_i1 ? pp.table[(size_t)it_region * pp.stride + idx] : 0u;
+        const uint32_t pbal = (__shfl_sync(0xffffffffu, piece, 0) & 0xFFFFu) & ~15u;
+        const uint32_t endl = (piece & 0xFFFFu) + (piece >> 16);
+        const uint32_t fits = __ballot_sync(0xffffffffu, idx < it_i1 && endl - pbal <= HP_SPAN_MAX);
+        const uint32_t cnt = fits == 0xffffffffu ? 32u : (uint32_t)(__ffs(~fits) - 1);   // >= 1: one piece always fits
+        if (lane >= cnt) piece = 0u;
+        const uint32_t last_end = __shfl_sync(0xffffffffu, endl, (int)cnt - 1);
+        nx_region = it_region; nx_pbal = pbal; nx_piece = piece;
+        nx_bytes = (32u + (last_end - pbal) + 15u) & ~15u;
+        it_i0 += cnt;
+        return true;
     };
-    // stage [pb - 32, min(end + HASH_W, pb + HP_SLICE)) of the region into buffer n
-    // (positions in [end, end + HASH_W) hold SYM_BREAK, written by pack_kernel)
+    // stage [pbal - 32, last position of the group] of the region into buffer n
     auto issue = [&](int n) {
         if (lane == 0) {
-            const uint32_t npos = min(it_end + (uint32_t)HASH_W - it_pb, HP_SLICE);
-            const uint32_t bytes = (32u + npos + 15u) & ~15u;
-            const uint8_t *src = symbuf + (size_t)SYM_FRONT + (size_t)it_region * g.region_stride + it_pb - 32;
-            mbar_arrive_expect_tx(&bars[n], bytes);
-            tma_load_1d(bufs + n * HP_BUF, src, bytes, &bars[n]);
+            const uint8_t *src = symbuf + (size_t)SYM_FRONT + (size_t)nx_region * g.region_stride + nx_pbal - 32;
+            mbar_arrive_expect_tx(&bars[n], nx_bytes);
+            tma_load_1d(bufs + n * HP_BUF, src, nx_bytes, &bars[n]);
         }
     };
 
@@ -412,35 +426,40 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
     uint32_t res_base = 0, res_left = 0;   // warp-uniform: this warp's reserved slice of the log
     uint32_t phases = 0;                   // bit n: parity to wait for on buffer n
     int cb = 0;
-    uint32_t cur = next_live();
-    if (cur < w1) issue(0);
-    while (cur < w1) {
-        const uint32_t region = it_region, pb = it_pb, end = it_end;
-        uint32_t nxt = w1;
-        if (HP_NBUF > 1) {                 // prefetch the next live item into the other buffer
-            nxt = next_live();
-            if (nxt < w1) issue(cb ^ 1);
-        }
+    bool have = next_group();
+    if (have) issue(0);
+    while (have) {
+        const uint32_t region = nx_region, pbal = nx_pbal, piece = nx_piece;
+        const bool have_next = next_group();           // the next group's copy is in flight while this one is hashed
+        if (have_next) issue(cb ^ 1);
         mbar_wait(&bars[cb], (phases >> cb) & 1u);
         phases ^= 1u << cb;
-        const uint8_t *tile = bufs + cb * HP_BUF;
+        const uint8_t *tile = bufs + cb * HP_BUF;       // tile[32 + x] = symbol pbal + x of the region
         const uint64_t ord_region = ord_base + (uint64_t)region * g.st_bytes;
-        const uint32_t t0 = lane * (uint32_t)HASH_W;          // this thread's first position within the item
-        const uint32_t p0 = pb + t0;
-        // lanes past the end of the region never read: they walk SYM_BREAK words.  Live lanes stay
-        // inside [p0 - 32, p0 + HASH_W), which was staged.
-        const bool live = p0 < end;
+        // this lane's run [p0, p0 + n): walked from p0 exactly, four symbols per step -- the staged bytes are read as
+        // aligned words and shifted into place (one PRMT per step), so a run costs ceil(n / 4) steps wherever it starts
+        const uint32_t n = piece >> 16, off = (piece & 0xFFFFu) - pbal;
+        const bool live = n != 0u;
+        const uint32_t t0 = live ? off : 0u;
+        const int nend = (int)n;                        // walk positions [0, nend) are the lane's
+        const uint32_t nw4 = ((uint32_t)__reduce_max_sync(0xffffffffu, nend) + 3u) >> 2;
+        const uint32_t pw = pbal + t0;                  // region position of the walk's first symbol
+        const uint32_t sel = 0x3210u + 0x1111u * (t0 & 3u);   // PRMT selector: bytes (t0 & 3) .. (t0 & 3) + 3 of a word pair
 
         Roll2<K> r; r.A.lo = r.A.hi = r.B.lo = r.B.hi = 0;
         // brk = position (relative to the current group of 4) of the last non-base symbol; the window
         // ending at relative position b is valid  <=>  brk <= b - k.
         int brk = -k;
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + 32 + t0);
-        // ---- warm-up on the 32 symbols before p0 (only the last k-1 matter) -------------------
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + 32 + (t0 & ~3u));   // aligned word holding the walk's first symbol
+        // ---- warm-up on the 32 symbols before the walk (only the last k-1 matter) -------------------
         if (live) {
-            const uint4 a = *reinterpret_cast<const uint4 *>(tile + t0);
-            const uint4 b = *reinterpret_cast<const uint4 *>(tile + t0 + 16);
-            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            const uint32_t *hw = reinterpret_cast<const uint32_t *>(tile + (t0 & ~3u));
+            uint32_t w[8];
+            {
+                uint32_t a = hw[0];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { const uint32_t b2 = hw[q + 1]; w[q] = __byte_perm(a, b2, sel); a = b2; }
+            }
             if (K == 21) {
                 // The 20 symbols in front are the words w[3..7]: build both rolling words at once instead of
                 // 20 pushes.  pack4: the 2-bit codes of 4 symbol bytes -> one byte (multiply gathers them).
@@ -488,19 +507,23 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
                     if ((s & 0xFFu) >= 4u) brk = i - 32;
                 }
             }
-        } else {
-            brk = -1;
         }
-        uint32_t word = live ? wp[0] : 0x04040404u;
+        uint32_t wlo = nend > 0 ? wp[0] : 0u, whi = nend > 0 ? wp[1] : 0u;
+        uint32_t word = nend > 0 ? __byte_perm(wlo, whi, sel) : 0x04040404u;
+        int lim = nend;                                 // positions of the current group of 4 below lim are the lane's
 #pragma unroll 1
-        for (int j = 0; j < HASH_W / 4; ++j) {
+        for (uint32_t j = 0; j < nw4; ++j) {
             const uint32_t cw = word;
-            if (j + 1 < HASH_W / 4) word = live ? wp[j + 1] : 0x04040404u;  // next 4 symbols
+            if (j + 1u < nw4) {                         // next 4 symbols (lanes past their run read nothing)
+                wlo = whi;
+                if (lim > 4) whi = wp[j + 2];
+                word = lim > 4 ? __byte_perm(wlo, whi, sel) : 0x04040404u;
+            }
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 r.push(cw >> (8 * b), k, mask);
                 if (cw & (0xFCu << (8 * b))) brk = b;
-                const bool ok = brk <= b - k;
+                const bool ok = brk <= b - k && b < lim;
                 const bool is_rc = (((uint64_t)r.A.hi << 32) | r.A.lo) >= (((uint64_t)r.B.hi << 32) | r.B.lo);
                 U2 codes; codes.lo = is_rc ? r.B.lo : r.A.lo; codes.hi = is_rc ? r.B.hi : r.A.hi;
                 U2 h;
@@ -531,7 +554,7 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
                     if (emit) {
                         const uint32_t idx = res_base + __popc(em & lanemask_lt());
                         if (idx < log.cap) {
-                            const uint32_t p = p0 + 4u * (uint32_t)j + (uint32_t)b;
+                            const uint32_t p = pw + 4u * j + (uint32_t)b;
                             log.hash[idx] = hv;
                             log.kmer[idx] = ((unsigned long long)codes.hi << 32) | codes.lo;   // k <= 32: log.kw == 1
                             log.posx[idx] = ((ord_region + p) << 9) | (is_rc ? 1ull : 0ull);
@@ -541,11 +564,10 @@ hash_kernel(const uint8_t *__restrict__ symbuf,   // symbol buffer: region r sta
                   }
                 }
             }
-            brk -= 4;
+            brk -= 4; lim -= 4;
         }
         __syncwarp();                      // every lane is done with this buffer before it is refilled
-        if (HP_NBUF > 1) { cur = nxt; cb ^= 1; }
-        else { cur = next_live(); if (cur < w1) issue(0); }
+        have = have_next; cb ^= 1;
     }
     if (lane < res_left && res_base + lane < log.cap) log.posx[res_base + lane] = ~0ULL;  // unused tail of the reservation
     // valid-window count of this launch (committed to total_kmers by the host on success)
@@ -675,7 +697,7 @@ __global__ void push_commit_kernel(LaunchSlot *slot, uint32_t n) { slot->launch_
 template <int K, bool SEED0, int VAR>
 static void launch_hash_ks(uint32_t r0, uint32_t n_regions, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
                            const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
-                           int k, uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
+                           int k, uint64_t seed, uint32_t log_reserve, PiecePlan pp, cudaStream_t stream) {
     static int sms[64] = {};   // per device: SM count, set once the shared-memory attribute is in place
     int dev = 0;
     cudaGetDevice(&dev);
@@ -689,39 +711,39 @@ static void launch_hash_ks(uint32_t r0, uint32_t n_regions, const uint8_t *symbu
     HashConsts hc;
     hc.stride64 = HP_R64 * 8u; hc.stride32 = HP_R32 * 4u; hc.stride1 = 8u; hc.one = 1u; hc.five = 5u;
     hc.log_reserve = log_reserve;
-    const uint64_t items_ub = (uint64_t)n_regions * ((g.st_bytes + HP_SLICE - 1u) / HP_SLICE);   // the device cuts it at the largest region
+    const uint64_t items_ub = (uint64_t)n_regions * ((pp.stride + 31u) / 32u);   // the device cuts it at the chunk's largest piece count
     const uint32_t ctas = (uint32_t)std::min<uint64_t>((uint64_t)sms[dev], (items_ub + HP_WARPS - 1) / HP_WARPS);
     hash_kernel<K, SEED0, VAR><<<ctas, HP_WARPS * 32, HP_SMEM, stream>>>(symbuf, g, r0, n_regions, region_count, carry, ord_base, st,
-                                                                   slot, log, k, seed, hc);
+                                                                   slot, log, k, seed, hc, pp);
 }
 template <int K>
 static void launch_hash_k(uint32_t r0, uint32_t n_regions, const uint8_t *symbuf, ChunkGeom g, const uint32_t *region_count,
                           const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
-                          int k, uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
+                          int k, uint64_t seed, uint32_t log_reserve, PiecePlan pp, cudaStream_t stream) {
 #ifdef FB2_HASH_VARIANTS   // A/B builds: FB2_HASH_VAR picks the arithmetic variant of the k = 21 / seed 0 kernel at run time
     if (seed == 0 && K == 21) {
         static const int var = getenv("FB2_HASH_VAR") ? atoi(getenv("FB2_HASH_VAR")) : HASH_VAR_DEFAULT;
-#define FB2_V(V) case V: launch_hash_ks<K, true, V>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream); return;
+#define FB2_V(V) case V: launch_hash_ks<K, true, V>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, pp, stream); return;
         switch (var) { FB2_V(0) FB2_V(1) FB2_V(2) FB2_V(3) FB2_V(12) FB2_V(15) FB2_V(60) FB2_V(63) default: break; }
 #undef FB2_V
     }
 #endif
-    if (seed == 0 && K > 0) launch_hash_ks<K, true, HASH_VAR_DEFAULT>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
-    else launch_hash_ks<K, false, HASH_VAR_DEFAULT>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    if (seed == 0 && K > 0) launch_hash_ks<K, true, HASH_VAR_DEFAULT>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, pp, stream);
+    else launch_hash_ks<K, false, HASH_VAR_DEFAULT>(r0, n_regions, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, pp, stream);
 }
 // Hash the symbol regions [r0, r1) of a chunk.
 void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t r0, uint32_t r1, const uint32_t *region_count,
                  const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
-                 uint64_t seed, uint32_t log_reserve, cudaStream_t stream) {
+                 uint64_t seed, uint32_t log_reserve, PiecePlan pp, cudaStream_t stream) {
     if (r1 <= r0) return;
     if (k > 32) {
         const dim3 grid((g.st_bytes + HB_THREADS * HB_W - 1) / (HB_THREADS * HB_W), r1 - r0);
         hash_big_kernel<<<grid, HB_THREADS, 0, stream>>>(symbuf, g, r0, region_count, ord_base, st, slot, log, k, seed);
         return;
     }
-    if (k == 21) launch_hash_k<21>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
-    else if (k == 31) launch_hash_k<31>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
-    else launch_hash_k<0>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, stream);
+    if (k == 21) launch_hash_k<21>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, pp, stream);
+    else if (k == 31) launch_hash_k<31>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, pp, stream);
+    else launch_hash_k<0>(r0, r1 - r0, symbuf, g, region_count, carry, ord_base, st, slot, log, k, seed, log_reserve, pp, stream);
 }
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
                       uint64_t arena_base, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,

@@ -14,13 +14,14 @@ void launch_pack(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, c
 int parse_fused_max_tiles();
 void launch_parse_fused(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_state, uint8_t *sym,
                         uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, SeamNl *seam, int nl_in, uint32_t halo,
-                        uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base, cudaStream_t s);
+                        uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base, PiecePlan pp, cudaStream_t s);
+void launch_uniform_pieces(const uint32_t *region_count, uint32_t n_st, PiecePlan pp, ParseCarry *carry, cudaStream_t s);
 void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t st);
 
 // hash.cu
 void launch_hash(int k, const uint8_t *symbuf, ChunkGeom g, uint32_t r0, uint32_t r1, const uint32_t *region_count,
                  const ParseCarry *carry, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
-                 uint64_t seed, uint32_t log_reserve, cudaStream_t stream);
+                 uint64_t seed, uint32_t log_reserve, PiecePlan pp, cudaStream_t stream);
 void launch_push_hash(const uint8_t *bytes, const uint32_t *offs, const uint8_t *extra, uint32_t n,
                       uint64_t arena_base, uint64_t ord_base, const SketchState *st, LaunchSlot *slot, LogView log,
                       uint64_t seed, cudaStream_t stream);

@@ -346,6 +346,7 @@ phase_scan_kernel(const uint32_t *__restrict__ st_map, ChunkGeom g, ParseCarry *
         else if (g.len == 1) { carry->prev2 = carry->prev1; carry->prev1 = raw[0]; }
         carry->chunk_syms = 0;
         carry->max_region_syms = 0;
+        carry->max_region_pieces = 0;
         carry->chunk_raw_base = carry->raw_total;
         carry->raw_total += g.len;
     }
@@ -996,13 +997,13 @@ template <int MODE>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *carry, uint32_t *__restrict__ st_state,
                    uint8_t *__restrict__ sym, uint32_t *__restrict__ region_count, SeamNl *__restrict__ seam,
-                   uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base) {
+                   uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base, PiecePlan pp) {
     extern __shared__ __align__(16) uint8_t pf_smem[];
     __shared__ unsigned long long sh16l[16];
     __shared__ uint32_t sh8[8];
     __shared__ uint32_t c_nl[3];
     __shared__ uint32_t s_misc[12];
-    enum { M_ST = 0, M_DECL = 1, M_NBW = 2, M_STATE = 3, M_LASTNL = 4, M_BASES = 5, M_RECS = 6, M_BAD = 7, M_LBAD = 8, M_T = 9, M_GUESS = 10 };
+    enum { M_ST = 0, M_DECL = 1, M_NBW = 2, M_STATE = 3, M_LASTNL = 4, M_BASES = 5, M_RECS = 6, M_BAD = 7, M_LBAD = 8, M_T = 9, M_GUESS = 10, M_NP = 11 };
     uint8_t *rawb = pf_smem + 16;                                          // [16 front pad | supertile | back pad]
     const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(pf_smem);
     uint16_t *s_nl = reinterpret_cast<uint16_t *>(pf_smem + 16 + PF_BYTES + 32);
@@ -1114,6 +1115,7 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
     const uint32_t G = (NP + PF_WT - 1u) / PF_WT;
     const uint32_t i_lo = min((uint32_t)tid * G, NP), i_hi = wid == PF_LB ? i_lo : min(i_lo + G, NP);
     unsigned long long vsum = 0, vex = 0, vtot = 0;   // output lengths per variant of the unknown state (16-bit fields)
+    unsigned long long psum = 0, pex = 0, ptot = 0;   // hash pieces, likewise
     uint32_t state0 = 0;                             // state of the line holding the byte in front of the supertile
     bool have_state = MODE == MODE_LINES;            // false: state0 is a guess, verified when the look-back is in
     if (wid == PF_LB) {
@@ -1145,6 +1147,13 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
                 const uint32_t len = end - start;
                 const uint32_t pb = rawb[(int)end - 1];
                 const uint32_t klen = len - ((len > 0u && pb == '\r') ? 1u : 0u);
+                // hash pieces of the line if it is a record's sequence (see PiecePlan): its valid k-mer end positions in
+                // runs of <= pp.pmax; a line continued from the previous supertile has no dead prefix here
+                if (MODE != MODE_FASTA && pp.pmax) {
+                    const uint32_t nv = (i == 0u && !ls0) ? klen : (klen >= pp.k ? klen - (pp.k - 1u) : 0u);
+                    const uint32_t np = ((nv + pp.pmax - 1u) * pp.pmax_inv) >> 22;
+                    psum += (unsigned long long)np << (MODE == MODE_FASTQ ? 16u * (i & 3u) : 0u);
+                }
                 if (MODE == MODE_LINES) vsum += klen + (has_nl ? 1u : 0u);
                 else if (MODE == MODE_FASTQ) {
                     vsum += (unsigned long long)(klen + (has_nl ? 1u : 0u)) << (16u * (i & 3u));
@@ -1176,24 +1185,25 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
                 }
                 s_misc[M_GUESS] = guess;
             }
-            // exclusive scan over the worker threads
-            unsigned long long x = vsum;
+            // exclusive scan over the worker threads (output lengths and piece counts together)
+            unsigned long long x = vsum, y = psum;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long n = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= (uint32_t)d) x += n;
+                const unsigned long long n = __shfl_up_sync(0xffffffffu, x, d), m = __shfl_up_sync(0xffffffffu, y, d);
+                if (lane >= (uint32_t)d) { x += n; y += m; }
             }
             named_sync(2, PF_WT);                    // sh16l: the first scan's reads are over
-            if (lane == 31u) sh16l[wid] = x;
+            if (lane == 31u) { sh16l[wid] = x; sh16l[8 + wid] = y; }
             named_sync(2, PF_WT);
-            unsigned long long base = 0;
+            unsigned long long base = 0, pbase = 0;
 #pragma unroll
             for (uint32_t w = 0; w < PF_LB; ++w) {
-                const unsigned long long sv = sh16l[w];
-                if (w < wid) base += sv;
-                vtot += sv;
+                const unsigned long long sv = sh16l[w], pv = sh16l[8 + w];
+                if (w < wid) { base += sv; pbase += pv; }
+                vtot += sv; ptot += pv;
             }
             vex = base + x - vsum;
+            pex = pbase + y - psum;
         }
     }
     uint32_t out_off = 0;
@@ -1211,6 +1221,11 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
         // ---- 3b. pieces -> entries, with the state known (or guessed) ---------------------------------
         const uint32_t vsel = MODE == MODE_FASTQ ? 16u * ((1u - state0) & 3u) : (MODE == MODE_FASTA ? 16u * (state0 & 1u) : 0u);
         if (tid == 0) s_misc[M_T] = (uint32_t)(vtot >> vsel) & 0xFFFFu;
+        // hash pieces: one per record run when they fit the region's table, else (and for FASTA) uniform ones below
+        const uint32_t n_rec_pieces = (uint32_t)(ptot >> vsel) & 0xFFFFu;
+        const bool rec_pieces = MODE != MODE_FASTA && pp.table != nullptr && pp.pmax != 0u && n_rec_pieces <= pp.stride;
+        uint32_t pslot = (uint32_t)(pex >> vsel) & 0xFFFFu;
+        uint32_t *ptab = pp.table ? pp.table + (size_t)st * pp.stride : nullptr;
         const bool ls0 = rawb[-1] == '\n';
         uint32_t sum = (uint32_t)(vex >> vsel) & 0xFFFFu;                // output offset of this thread's first piece
         for (uint32_t i = i_lo; i < i_hi; ++i) {
@@ -1267,6 +1282,20 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
             e_src[i] = (uint16_t)((start & 0x7FFFu) | (brk << 15));
             e_len[i] = (uint16_t)L;
             e_out[i] = (uint16_t)sum;
+            if (MODE != MODE_FASTA && rec_pieces && (MODE == MODE_LINES || ((state0 + i) & 3u) == 1u)) {
+                const uint32_t nv = (i == 0u && !ls0) ? L : (L >= pp.k ? L - (pp.k - 1u) : 0u);
+                const uint32_t np = ((nv + pp.pmax - 1u) * pp.pmax_inv) >> 22;
+                if (np) {   // nv positions in np runs whose lengths differ by at most one
+                    const uint32_t q0 = nv / np, rem = nv - q0 * np;
+                    uint32_t ppos = sum + L - nv;
+                    for (uint32_t q = 0; q < np; ++q) {
+                        const uint32_t pl = q0 + (q < rem ? 1u : 0u);
+                        ptab[pslot + q] = ppos | (pl << 16);
+                        ppos += pl;
+                    }
+                    pslot += np;
+                }
+            }
             const uint32_t outlen = L + brk;
             if (outlen) {   // words whose first byte this entry provides
                 const uint32_t w_hi = (sum + outlen - 1u) >> 4;
@@ -1372,6 +1401,14 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
             *reinterpret_cast<uint4 *>(region + 16u * w) = make_uint4((uint32_t)alo, (uint32_t)(alo >> 32), (uint32_t)ahi, (uint32_t)(ahi >> 32));
         }
         out_off = T;
+        if (pp.table) {
+            uint32_t np_region = n_rec_pieces;
+            if (!rec_pieces) {
+                np_region = (T + 63u) >> 6;
+                for (uint32_t j = tid; j < np_region; j += PF_WT) ptab[j] = (64u * j) | (min(64u, T - 64u * j) << 16);
+            }
+            if (tid == 0) s_misc[M_NP] = np_region;
+        }
         if (have_state) break;
         // the guess against the look-back's answer
         named_sync(3, TILE_THREADS);
@@ -1397,6 +1434,12 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
                          reinterpret_cast<uint16_t *>(pf_smem), c_nl, nl_before, lbad, seam_st);
         bases_delta = (int)bd;
         bad_rel = bp == ~0ULL ? 0xFFFFFFFFu : (uint32_t)(bp - raw_base);
+        if (pp.table) {
+            const uint32_t np_region = (out_off + 63u) >> 6;
+            uint32_t *ptab = pp.table + (size_t)st * pp.stride;
+            for (uint32_t j = tid; j < np_region; j += TILE_THREADS) ptab[j] = (64u * j) | (min(64u, out_off - 64u * j) << 16);
+            if (tid == 0) s_misc[M_NP] = np_region;
+        }
         if (MODE == MODE_FASTQ) {
             __syncthreads();
             if (tid == 0) { seam_st->last[0] = c_nl[0]; seam_st->last[1] = c_nl[1]; seam_st->last[2] = c_nl[2]; seam_st->n = nl_before; }
@@ -1425,6 +1468,7 @@ parse_fused_kernel(const uint8_t *__restrict__ raw, ChunkGeom g, ParseCarry *car
         region_count[st] = out_off;
         atomicAdd(&carry->chunk_syms, out_off);
         atomicMax(&carry->max_region_syms, out_off);
+        if (pp.table) { pp.count[st] = s_misc[M_NP]; atomicMax(&carry->max_region_pieces, s_misc[M_NP]); }
         if (MODE != MODE_LINES) {
             const long long bsum = (long long)(int)s_misc[M_BASES];
             if (bsum) atomicAdd((unsigned long long *)&carry->total_bases, (unsigned long long)bsum);
@@ -1445,8 +1489,19 @@ __global__ void chunk_begin_kernel(const uint8_t *__restrict__ raw, ChunkGeom g,
     else if (g.len == 1) { carry->prev2 = carry->prev1; carry->prev1 = raw[0]; }
     carry->chunk_syms = 0;
     carry->max_region_syms = 0;
+    carry->max_region_pieces = 0;
     carry->chunk_raw_base = carry->raw_total;
     carry->raw_total += g.len;
+}
+
+// Uniform hash pieces (64 positions each) for the regions of a chunk parsed by the three-kernel pipeline.
+__global__ void uniform_pieces_kernel(const uint32_t *__restrict__ region_count, uint32_t n_st, PiecePlan pp, ParseCarry *carry) {
+    const uint32_t st = blockIdx.x;
+    if (st >= n_st) return;
+    const uint32_t T = region_count[st], np = (T + 63u) >> 6;
+    uint32_t *ptab = pp.table + (size_t)st * pp.stride;
+    for (uint32_t j = threadIdx.x; j < np; j += blockDim.x) ptab[j] = (64u * j) | (min(64u, T - 64u * j) << 16);
+    if (threadIdx.x == 0) { pp.count[st] = np; atomicMax(&carry->max_region_pieces, np); }
 }
 
 // Front pads: warp r fills the `halo` bytes before region r (r < n_st) or the outgoing chunk tail
@@ -1545,7 +1600,7 @@ int parse_fused_max_tiles() { return PF_MAX_TILES; }
 template <int MODE>
 static void launch_parse_fused_m(const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_state, uint8_t *sym,
                                  uint32_t *region_count, SeamNl *seam, uint32_t *status, uint32_t epoch, uint32_t *ticket,
-                                 uint32_t ticket_base, cudaStream_t s) {
+                                 uint32_t ticket_base, PiecePlan pp, cudaStream_t s) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1555,18 +1610,21 @@ static void launch_parse_fused_m(const uint8_t *raw, ChunkGeom g, ParseCarry *ca
         attr_set[dev] = true;
     }
     parse_fused_kernel<MODE><<<g.n_st, TILE_THREADS, PF_SMEM, s>>>(raw, g, carry, st_state, sym, region_count, seam, status, epoch,
-                                                                   ticket, ticket_base);
+                                                                   ticket, ticket_base, pp);
 }
 void launch_parse_fused(int mode, const uint8_t *raw, ChunkGeom g, ParseCarry *carry, uint32_t *st_state, uint8_t *sym,
                         uint32_t *region_count, const uint8_t *tail_in, uint8_t *tail_out, SeamNl *seam, int nl_in, uint32_t halo,
-                        uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base, cudaStream_t s) {
+                        uint32_t *status, uint32_t epoch, uint32_t *ticket, uint32_t ticket_base, PiecePlan pp, cudaStream_t s) {
     chunk_begin_kernel<<<1, 32, 0, s>>>(raw, g, carry);
-    if (mode == MODE_LINES) launch_parse_fused_m<MODE_LINES>(raw, g, carry, st_state, sym, region_count, nullptr, status, epoch, ticket, ticket_base, s);
-    else if (mode == MODE_FASTA) launch_parse_fused_m<MODE_FASTA>(raw, g, carry, st_state, sym, region_count, nullptr, status, epoch, ticket, ticket_base, s);
-    else launch_parse_fused_m<MODE_FASTQ>(raw, g, carry, st_state, sym, region_count, seam, status, epoch, ticket, ticket_base, s);
+    if (mode == MODE_LINES) launch_parse_fused_m<MODE_LINES>(raw, g, carry, st_state, sym, region_count, nullptr, status, epoch, ticket, ticket_base, pp, s);
+    else if (mode == MODE_FASTA) launch_parse_fused_m<MODE_FASTA>(raw, g, carry, st_state, sym, region_count, nullptr, status, epoch, ticket, ticket_base, pp, s);
+    else launch_parse_fused_m<MODE_FASTQ>(raw, g, carry, st_state, sym, region_count, seam, status, epoch, ticket, ticket_base, pp, s);
     front_fix_kernel<<<(g.n_st + 1 + 7) / 8, 256, 0, s>>>(sym, g, region_count, tail_in, tail_out,
                                                         mode == MODE_FASTQ ? seam : nullptr, st_state, carry, nl_in, halo,
                                                         mode == MODE_LINES ? 0 : 1);
+}
+void launch_uniform_pieces(const uint32_t *region_count, uint32_t n_st, PiecePlan pp, ParseCarry *carry, cudaStream_t s) {
+    if (pp.table && n_st) uniform_pieces_kernel<<<n_st, 128, 0, s>>>(region_count, n_st, pp, carry);
 }
 void launch_fill_bytes(uint8_t *p, uint32_t n, uint8_t v, cudaStream_t s) {
     if (n) fill_bytes_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);

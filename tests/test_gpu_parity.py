@@ -1057,3 +1057,33 @@ def test_three_kernel_parse_still_matches(fb, synth, oracle, monkeypatch, fmt):
     got = gpu_sketch(fb, data, "mash", 2000, 21, 0)
     assert_same(got[0], want, 21)
     assert got[1] == totals
+
+
+# ---- hash pieces planned by the parse kernel ---------------------------------------------------------
+@pytest.mark.parametrize("k", [21, 31, 7, 32])
+@pytest.mark.parametrize("pieces_env", ["1", "0"])
+def test_hash_pieces_of_records(fb, oracle, monkeypatch, k, pieces_env):
+    """The hash kernel walks the runs of k-mer end positions the parse kernel plans per record (no run starts inside
+    the k - 1 positions after a record break).  Read lengths around every boundary of the plan (shorter than k, exactly
+    k, one run / two runs / many runs), long stretches of reads without any k-mer between normal ones (their pieces lie
+    further apart than a staged group may span), Ns inside reads, CRLF.  FB2_PIECES=0: uniform pieces, same result."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    monkeypatch.setenv("FB2_PIECES", pieces_env)
+    rng = np.random.default_rng(1000 + k)
+    pm = 67 - k
+    lens = [0, 1, k - 1, k, k + 1, pm, pm + k - 2, pm + k - 1, pm + k, 2 * pm + k - 1, 2 * pm + k, 150, 151, 300, 5000, 40000]
+    recs = []
+    r = 0
+    while sum(len(x) for x in recs) < (3 << 20):
+        if rng.random() < 0.02:                       # a stretch of reads too short for any k-mer
+            for _ in range(int(rng.integers(50, 900))):
+                m = int(rng.integers(0, k))
+                recs.append(b"@t%d\n" % r + gen.rand_seq(rng, m, 0.0) + b"\n+\n" + b"I" * m + b"\n"); r += 1
+        m = int(lens[int(rng.integers(0, len(lens)))]) if rng.random() < 0.5 else int(rng.integers(0, 400))
+        nl = b"\r\n" if rng.random() < 0.1 else b"\n"
+        recs.append(b"@r%d" % r + nl + gen.rand_seq(rng, m, 0.02) + nl + b"+" + nl + b"I" * m + nl); r += 1
+    data = b"".join(recs)
+    want, totals, _ = oracle_sketch(oracle, data, "mash", 4000, k, 0)
+    got = gpu_sketch(fb, data, "mash", 4000, k, 0)
+    assert_same(got[0], want, k)
+    assert got[1] == totals
