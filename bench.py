@@ -392,8 +392,51 @@ def main():
         os.environ["FB2_HOST_STRIP"] = "0"
         e2e_strip = {"value": nbases * world * e2e_steps / (ms_s * 1e-3) / 1e9, "ms_per_step": ms_s / e2e_steps,
                      "h2d_bytes_per_step": int(stats_s["h2d_bytes"] // e2e_steps), "threads": strip_threads}
-        if ms_s < ms_e2e:      # the headline e2e is the better of the two modes of the same public call
+        if ms_s < ms_e2e:      # the headline e2e is the best of the modes of the same public call
             ms_e2e, last_e2e, stats_e2e, used_strip = ms_s, last_s, stats_s, True
+    # Both at once (FB2_HOST_STRIP=2, hostlogic.cpp sketch_stream_two_ended): host cores frame records from the front
+    # of the stream while the link carries raw bytes from its back; fb2_sketch_stream on the same pinned buffer.
+    e2e_two, used_two = None, False
+    if not args.no_host_strip:
+        os.environ["FB2_HOST_STRIP"] = "2"
+        os.environ["FB2_STRIP_THREADS"] = str(max(1, strip_threads))
+
+        def step_stream():
+            res = fb.sketch_stream_ptr(host.data_ptr(), nbytes, "bench.fq", sp, fp)
+            if dist is not None:
+                t = torch.from_numpy(np.stack([res.hashes_u64.view(np.int64), res.counts.astype(np.int64),
+                                               res.extra_counts.astype(np.int64)])).to(dev)
+                outl = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+                dist.gather(t, outl, dst=0)
+            return res
+        for _ in range(2):
+            step_stream()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        acc = {"h2d_bytes": 0, "d2h_bytes": 0, "kernel_launches": 0}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        last_t = None
+        for _ in range(e2e_steps):
+            last_t = step_stream()
+            stt = fb.last_stream_stats()
+            for kx in acc:
+                acc[kx] += stt[kx]
+        e1.record(stream)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms_t = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms_t], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_t = float(t.item())
+        os.environ["FB2_HOST_STRIP"] = "0"
+        e2e_two = {"value": nbases * world * e2e_steps / (ms_t * 1e-3) / 1e9, "ms_per_step": ms_t / e2e_steps,
+                   "h2d_bytes_per_step": int(acc["h2d_bytes"] // e2e_steps), "threads": max(1, strip_threads)}
+        if ms_t < ms_e2e:
+            ms_e2e, last_e2e, stats_e2e, used_strip, used_two = ms_t, last_t, acc, False, True
 
     # ---- platform H2D ceiling: the same pinned buffers, all N ranks at once, no kernels ---------------------
     def h2d_ceiling(reps=3):
@@ -476,9 +519,11 @@ def main():
                 "steps": e2e_steps, "h2d_gbs": e2e_gbs, "h2d_ceiling_gbs": h2d_gbs,
                 "frac_of_h2d_ceiling": e2e_gbs / h2d_gbs if h2d_gbs else None,
                 "h2d_ceiling_how": f"{world} rank(s) copying the same pinned buffers concurrently, no kernels, max over ranks",
-                "mode": "host pre-strip (FB2_HOST_STRIP=1): FASTQ framing on the host cores, sequence lines only over PCIe"
-                        if used_strip else "raw FASTQ bytes over PCIe, parsed on the GPU",
-                "raw_bytes": e2e_plain, "host_strip": e2e_strip},
+                "mode": ("two-ended (FB2_HOST_STRIP=2): host cores frame FASTQ records from the front of the stream while raw bytes "
+                         "from its back cross PCIe; the two tables are united exactly on the device") if used_two else
+                        ("host pre-strip (FB2_HOST_STRIP=1): FASTQ framing on the host cores, sequence lines only over PCIe"
+                         if used_strip else "raw FASTQ bytes over PCIe, parsed on the GPU"),
+                "raw_bytes": e2e_plain, "host_strip": e2e_strip, "two_ended": e2e_two},
         "gpu_launches": int(stats_res["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

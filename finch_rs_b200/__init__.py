@@ -73,7 +73,7 @@ class _PairOut(C.Structure):
 EXPORTS = [
     "fb2_sketcher_create", "fb2_sketcher_destroy", "fb2_sketcher_reset", "fb2_sketcher_process",
     "fb2_sketcher_push", "fb2_sketcher_feed_fastx", "fb2_sketcher_feed_device", "fb2_sketcher_format",
-    "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats",
+    "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats", "fb2_last_stream_stats",
     "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_sketcher_debug_bump", "fb2_filter_counts", "fb2_process_post_filter",
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_multi", "fb2_sketch_stream_multi",
     "fb2_sketch_files_release_pool", "fb2_dist_batch",
@@ -108,6 +108,7 @@ def lib():
     L.fb2_result_free.argtypes = [C.POINTER(_Result)]
     L.fb2_result_free.restype = None
     L.fb2_sketcher_stats.argtypes = [vp, C.POINTER(_Stats)]
+    L.fb2_last_stream_stats.argtypes = [C.POINTER(_Stats)]
     L.fb2_sketcher_enable_timing.argtypes = [vp, C.c_int]
     L.fb2_sketcher_debug_symbols.argtypes = [vp, vp, vp, sz, vp, sz]
     L.fb2_sketcher_debug_bump.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
@@ -447,6 +448,21 @@ def sketch_stream(data, name: str, sketch_params: SketchParams, filters: FilterP
     cp, cf = sketch_params._c(), filters._c()
     _check(lib().fb2_sketch_stream(addr, n, name.encode(), C.byref(cp), C.byref(cf), C.byref(r)))
     return _finish(r, name, sketch_params)
+
+
+def sketch_stream_ptr(host_ptr: int, nbytes: int, name: str, sketch_params: SketchParams, filters: FilterParams) -> Sketch:
+    """sketch_stream over host memory given by address (e.g. a pinned buffer)."""
+    r = _Result()
+    cp, cf = sketch_params._c(), filters._c()
+    _check(lib().fb2_sketch_stream(host_ptr, nbytes, name.encode(), C.byref(cp), C.byref(cf), C.byref(r)))
+    return _finish(r, name, sketch_params)
+
+
+def last_stream_stats() -> dict:
+    """Counters of the calling thread's most recent sketch_stream call (kernel launches, bytes over PCIe, ...)."""
+    st = _Stats()
+    _check(lib().fb2_last_stream_stats(C.byref(st)))
+    return {k: getattr(st, k) for k, _ in _Stats._fields_}
 
 
 def sketch_stream_multi(data, name: str, sketch_params: SketchParams, filters: FilterParams, ngpus=0) -> Sketch:

@@ -8,6 +8,7 @@
 //   total_kmers        ->  host counter fed by the hash kernel's per-launch count
 //   total_bases        ->  ParseCarry::total_bases (FASTX) + host sum (process())
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -168,6 +169,10 @@ struct fb2_sketcher {
     bool stream_open = false;        // a FASTX stream has begun and not yet seen `final`
     // FB2_HOST_STRIP=1: FASTQ record framing on the host, only the sequence lines cross PCIe (strip.cpp)
     bool strip_on = false;               // active for the open stream
+    unsigned polite_copy = 0;            // > 0: raw host-to-device copies go in pieces of that many MiB, one in flight (see feed_host_chunks)
+    std::atomic<int> *link_flag = nullptr;   // two-ended streams: copies of the host-framed handle in flight (it raises the flag,
+    bool link_owner = false;                 // the raw handle waits for zero before every piece: the framed lines go first)
+    bool range_mode = false;             // the open stream is a range of a larger one (begin_range): several feed calls, no sync between them
     unsigned strip_threads = 1;
     std::vector<uint8_t> strip_carry;    // the incomplete record at the end of the previous piece
     uint64_t strip_off = 0;              // stream offset of the next unprocessed byte (of strip_carry[0] when it is not empty)
@@ -925,8 +930,22 @@ static int feed_host_chunks(fb2_sketcher *s, const uint8_t *bytes, size_t len, i
         const size_t off = c * chunk, n = std::min(chunk, len - off);
         TRY(s->d_raw[b].ensure(bufsz));
         if (s->rawfree_pending[b]) { CU(cudaStreamWaitEvent(s->copy_st, s->ev_rawfree[b], 0)); s->rawfree_pending[b] = false; }
-        CU(cudaMemcpyAsync(s->d_raw[b].p, bytes + off, n, cudaMemcpyHostToDevice, s->copy_st));
-        CU(cudaEventRecord(s->ev_h2d[b], s->copy_st));
+        if (s->polite_copy) {
+            // Another handle's (smaller, host-framed) copies share the link: hand it over after every piece instead of
+            // queueing whole chunks ahead of them (hostlogic.cpp, sketch_stream_two_ended)
+            const size_t piece = (size_t)s->polite_copy << 20;
+            for (size_t q = 0; q < n; q += piece) {
+                const size_t m = std::min(piece, n - q);
+                if (s->link_flag && !s->link_owner)
+                    while (s->link_flag->load(std::memory_order_acquire) > 0) std::this_thread::sleep_for(std::chrono::microseconds(20));
+                CU(cudaMemcpyAsync(s->d_raw[b].as<uint8_t>() + q, bytes + off + q, m, cudaMemcpyHostToDevice, s->copy_st));
+                CU(cudaEventRecord(s->ev_h2d[b], s->copy_st));
+                if (q + m < n) CU(cudaEventSynchronize(s->ev_h2d[b]));
+            }
+        } else {
+            CU(cudaMemcpyAsync(s->d_raw[b].p, bytes + off, n, cudaMemcpyHostToDevice, s->copy_st));
+            CU(cudaEventRecord(s->ev_h2d[b], s->copy_st));
+        }
         s->stats.h2d_bytes += n;
         return FB2_OK;
     };
@@ -1060,6 +1079,7 @@ static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 3; ++b) c_->last_nl[a][b] = NL_NONE;
     TRY(push_carry(s));
     s->stream_open = true;
+    s->range_mode = false;
     s->tail_host.clear();
     s->strip_on = false;
     if (s->format == FB2_FORMAT_FASTQ) {
@@ -1169,6 +1189,10 @@ static int feed_fastq_stripped(fb2_sketcher *s, const uint8_t *bytes, size_t len
                         if (o.spilled) CU(cudaStreamSynchronize(s->copy_st));   // pageable source: gone after this iteration
                     }
                     CU(cudaEventRecord(s->ev_h2d[b], s->copy_st));
+                    if (s->link_flag && s->link_owner) {   // lowered by the driver when these copies are through
+                        s->link_flag->fetch_add(1, std::memory_order_acq_rel);
+                        CU(cudaLaunchHostFunc(s->copy_st, [](void *f) { ((std::atomic<int> *)f)->fetch_sub(1, std::memory_order_acq_rel); }, s->link_flag));
+                    }
                     CU(cudaEventRecord(s->ev_strip_free[set], s->copy_st));
                     s->strip_free_pending[set] = true;
                     s->stats.h2d_bytes += total;
@@ -1330,7 +1354,7 @@ extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, si
         const int mode = s->format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ;
         if (s->strip_on) {
             TRY(feed_fastq_stripped(s, bytes, len, final));
-            if (len >= (1u << 20)) CU(cudaStreamSynchronize(s->copy_st));   // (staging sets are ours; the caller's bytes were only read by the CPU)
+            if (len >= (1u << 20) && !s->range_mode) CU(cudaStreamSynchronize(s->copy_st));   // (staging sets are ours; the caller's bytes were only read by the CPU)
             return FB2_OK;
         }
         note_tail(s, bytes, len);
@@ -1416,7 +1440,7 @@ static void apply_finish_hint(fb2_sketcher *s) {
 }
 int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32_t prev1, uint32_t prev2,
                              const uint8_t *tail_syms /* halo symbols, may be null = all breaks */, uint64_t raw_base,
-                             uint64_t ord_base) {
+                             uint64_t ord_base, int strip /* FASTQ range at a record start: frame the records on the host */) {
     if (!s || s->stream_open) return fb2_fail(FB2_EINVAL, "begin_range: bad handle state");
     ON_DEVICE(s->device);
     s->format = format;
@@ -1435,7 +1459,15 @@ int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32
     }
     s->ordinal = ord_base;
     s->stream_open = true;
+    s->range_mode = true;
     s->tail_host.clear();
+    s->strip_on = false;
+    if (strip && format == FB2_FORMAT_FASTQ) {
+        s->strip_on = true;
+        s->strip_threads = (unsigned)std::min<size_t>(64, std::max<size_t>(1, env_size("FB2_STRIP_THREADS", std::min(16u, std::max(1u, std::thread::hardware_concurrency())))));
+        s->strip_carry.clear(); s->strip_off = raw_base;
+        s->strip_bad = s->strip_len_bad = s->strip_first_blank = ~0ULL; s->strip_last_nonblank = 0; s->strip_records = 0;
+    }
     return FB2_OK;
 }
 // End of a range that is NOT the end of the stream: everything queued is done, no end-of-stream rules applied.
@@ -1446,6 +1478,23 @@ int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_
     TRY(flush_stage(s));
     TRY(settle_all(s));
     TRY(pull_state(s));
+    if (s->strip_on) {
+        // host-framed range: it ends at a record start iff no bytes of an incomplete record are left over; blank
+        // "records" are reported as a framing error (only the end of the whole stream may hold them)
+        const bool clean = s->strip_carry.empty() && s->strip_first_blank == ~0ULL;
+        if (end_state) *end_state = clean ? 0u : 1u;
+        if (last_byte) *last_byte = '\n';
+        if (first_bad_pos) *first_bad_pos = s->strip_bad;
+        if (len_bad_pos) *len_bad_pos = s->strip_len_bad;
+        s->strip_carry.clear();
+        s->strip_on = false;
+        s->h_carry->state = 0; s->h_carry->prev1 = s->h_carry->prev2 = '\n';
+        TRY(push_carry(s));
+        launch_fill_bytes(s->d_tail.as<uint8_t>(), 2 * HALO_BIG, SYM_BREAK, s->st);
+        s->stats.kernel_launches++;
+        s->stream_open = false;
+        return FB2_OK;
+    }
     if (end_state) *end_state = s->h_carry->state;
     if (last_byte) *last_byte = s->h_carry->prev1;
     if (first_bad_pos) *first_bad_pos = s->h_carry->first_bad_pos;
@@ -1453,6 +1502,8 @@ int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_
     s->stream_open = false;
     return FB2_OK;
 }
+void fb2_sketcher_set_polite_copy(fb2_sketcher *s, unsigned piece_mb) { if (s) s->polite_copy = piece_mb; }
+void fb2_sketcher_set_link_flag(fb2_sketcher *s, std::atomic<int> *flag, int owner) { if (s) { s->link_flag = flag; s->link_owner = owner != 0; } }
 uint32_t fb2_sketcher_halo(const fb2_sketcher *s) { return s->halo; }
 int fb2_sketcher_device(const fb2_sketcher *s) { return s->device; }
 

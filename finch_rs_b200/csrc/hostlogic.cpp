@@ -34,9 +34,11 @@ int fb2_fail(int code, const std::string &msg);  // engine.cu
 // engine.cu (internal API, not exported in the header)
 void fb2_sketcher_hint_finish(fb2_sketcher *s, uint64_t final_size, int filter_on);
 int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32_t prev1, uint32_t prev2,
-                             const uint8_t *tail_syms, uint64_t raw_base, uint64_t ord_base);
+                             const uint8_t *tail_syms, uint64_t raw_base, uint64_t ord_base, int strip);
 int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_byte, uint64_t *first_bad_pos, uint64_t *len_bad_pos);
 uint32_t fb2_sketcher_halo(const fb2_sketcher *s);
+void fb2_sketcher_set_polite_copy(fb2_sketcher *s, unsigned piece_mb);
+void fb2_sketcher_set_link_flag(fb2_sketcher *s, std::atomic<int> *flag, int owner);
 int fb2_sketcher_merge_from(fb2_sketcher *dst, fb2_sketcher *src);
 size_t fb2_sketcher_device_bytes(const fb2_sketcher *s);
 
@@ -191,10 +193,39 @@ static int finish_sketch(fb2_sketcher *s, const char *name, const fb2_params *p,
     return fb2_sketcher_sketch(s, name, p, f, out);
 }
 
+static int sketch_stream_two_ended(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
+                                   const fb2_filter *f, fb2_result *out);
+static thread_local fb2_stats g_last_stream_stats;
+static void stats_add_delta(fb2_stats &acc, const fb2_stats &a, const fb2_stats &b) {   // acc += b - a
+    acc.kernel_launches += b.kernel_launches - a.kernel_launches; acc.h2d_bytes += b.h2d_bytes - a.h2d_bytes;
+    acc.d2h_bytes += b.d2h_bytes - a.d2h_bytes; acc.chunks += b.chunks - a.chunks; acc.prunes += b.prunes - a.prunes;
+    acc.hash_launches += b.hash_launches - a.hash_launches; acc.hash_symbols += b.hash_symbols - a.hash_symbols;
+    acc.provisional_redos += b.provisional_redos - a.provisional_redos; acc.band_passes += b.band_passes - a.band_passes;
+}
+extern "C" int fb2_last_stream_stats(fb2_stats *out) {
+    if (!out) return fb2_fail(FB2_EINVAL, "null argument");
+    *out = g_last_stream_stats;
+    return FB2_OK;
+}
+static size_t env_size_h(const char *name, size_t dflt) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    const long long v = atoll(e);
+    return v > 0 ? (size_t)v : dflt;
+}
 extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
                                  const fb2_filter *f, fb2_result *out) {
     if (!p || !f || !out || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
     memset(out, 0, sizeof(*out));
+    {   // FB2_HOST_STRIP=2: a large FASTQ stream from both ends, host-framed and raw at once (sketch_stream_two_ended)
+        const char *e = getenv("FB2_HOST_STRIP");
+        if (e && *e == '2' && len >= (env_size_h("FB2_TWO_ENDED_MIN_KB", 256u << 10) << 10) && bytes[0] == '@') {
+            const int rc2 = sketch_stream_two_ended(bytes, len, name, p, f, out);
+            if (rc2 == FB2_OK) return FB2_OK;
+            fb2_result_free(out);
+            memset(out, 0, sizeof(*out));          // anything else: the plain path below
+        }
+    }
     fb2_params pd = *p;
     if (pd.device < 0 && cudaGetDevice(&pd.device) != cudaSuccess) pd.device = -1;   // pool entries are keyed by device
     fb2_sketcher *s = nullptr;
@@ -202,9 +233,17 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
     int rc;
     if (pool_acquire(&pd, &s, &buf)) rc = fb2_sketcher_reset(s);
     else rc = fb2_sketcher_create(&pd, &s);
+    fb2_stats st0, st1;
+    memset(&st0, 0, sizeof(st0)); memset(&st1, 0, sizeof(st1));
+    if (rc == FB2_OK) fb2_sketcher_stats(s, &st0);
     if (rc == FB2_OK && p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
     if (rc == FB2_OK) rc = fb2_sketcher_feed_fastx(s, bytes, len, 1);
     if (rc == FB2_OK) rc = finish_sketch(s, name, p, f, out);
+    if (rc == FB2_OK) {
+        fb2_sketcher_stats(s, &st1);
+        memset(&g_last_stream_stats, 0, sizeof(g_last_stream_stats));
+        stats_add_delta(g_last_stream_stats, st0, st1);
+    }
     if (rc != FB2_OK) {   // keep the message across the clean-up calls
         const std::string msg = fb2_last_error();
         if (buf) cudaFreeHost(buf);
@@ -354,7 +393,8 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
 // device buffers, pinned mirrors, streams and events (10+ ms, partly serialised by the driver), which would otherwise
 // dominate small files.  The reference API has no release call, so retention is bounded PER DEVICE: at most
 // FB2_POOL_MAX handles (default 16; 0 disables pooling) holding at most FB2_POOL_MB of device memory together
-// (default 2048 MiB: a handle that sketched a 5 Mbp FASTA holds ~100 MB, one that streamed a large FASTQ ~1 GB), and
+// (default 4096 MiB: a handle that sketched a 5 Mbp FASTA holds ~100 MB, one that streamed a large FASTQ ~1.3 GB -- the
+// two-ended stream mode keeps two of those), and
 // a handle is only re-used under the chunk / log settings it was created with.  fb2_sketch_files_release_pool()
 // frees them (the Python mirror registers it with atexit).
 struct PoolEntry { fb2_params p; fb2_sketcher *s; uint8_t *buf; std::string env; };
@@ -366,7 +406,7 @@ static size_t pool_max() {
 }
 static size_t pool_max_bytes() {
     if (const char *e = getenv("FB2_POOL_MB")) { const long v = atol(e); if (v >= 0) return (size_t)v << 20; }
-    return (size_t)2048 << 20;
+    return (size_t)4096 << 20;
 }
 static std::string pool_env_key() {
     const char *a = getenv("FB2_CHUNK_MB"), *b = getenv("FB2_LOG_M"), *c = getenv("FB2_TABLE_MULT");
@@ -640,7 +680,7 @@ extern "C" int fb2_sketch_stream_multi(const uint8_t *bytes, size_t len, const c
             std::vector<uint8_t> syms;
             if (g > 0 && fasta) fasta_carry_at(bytes, cut[g], fb2_sketcher_halo(hs[g]), &state, &prev2, syms);
             r = fb2_sketcher_begin_range(hs[g], fmt, state, '\n', prev2, syms.empty() ? nullptr : syms.data(), cut[g],
-                                         (uint64_t)g << 44);
+                                         (uint64_t)g << 44, 0);
         }
         if (r == FB2_OK) r = fb2_sketcher_feed_fastx(hs[g], bytes + cut[g], cut[g + 1] - cut[g], g + 1 == G ? 1 : 0);
         if (r == FB2_OK && g + 1 < G) r = fb2_sketcher_end_range(hs[g], &end_state[g], &last_byte[g], &bad1[g], &bad2[g]);
@@ -685,6 +725,151 @@ extern "C" int fb2_sketch_stream_multi(const uint8_t *bytes, size_t len, const c
     for (size_t g = 1; g < G && rc == FB2_OK; ++g) rc = fb2_sketcher_merge_from(hs[0], hs[g]);
     if (rc == FB2_OK) rc = fb2_sketcher_sketch(hs[0], name, p, f, out);
     std::string msg = rc != FB2_OK ? fb2_last_error() : "";
+    release_all(rc == FB2_OK);
+    return rc == FB2_OK ? FB2_OK : fb2_fail(rc, msg);
+}
+
+// ---- one FASTQ stream, host cores AND the PCIe link (FB2_HOST_STRIP=2) ---------------------------------------------
+// End to end from host memory a FASTQ stream is bound by the link (2.09 raw bytes per base); with the host pre-strip
+// (strip.cpp) it is bound by the host cores instead and the link idles half of the time.  Here both work at once, from
+// the two ends of the stream: handle A takes spans from the FRONT and frames their records on the host cores (one
+// continuous stream: its spans follow each other), handle B takes spans from the BACK and copies them raw (each one a
+// range of its own, begun at a guessed record start and VERIFIED to end on one, like fb2_sketch_stream_multi's cuts).
+// They stop where they meet -- whichever resource is faster takes more -- and the two tables are united exactly
+// (fb2_sketcher_merge_from; position ids ascend with the stream offset whatever the processing order).  Anything out of
+// the ordinary (a cut that is no record start, any record error, blank stretches) sends the stream through the plain
+// single-mode path, which produces the authoritative result or error.
+static int sketch_stream_two_ended(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
+                                   const fb2_filter *f, fb2_result *out) {
+    fb2_params pd = *p;
+    if (pd.device < 0 && cudaGetDevice(&pd.device) != cudaSuccess) pd.device = 0;
+    pd.stream = nullptr;
+    // cuts at guessed record starts, about `unit` bytes apart
+    // (four units stay under the 2 x chunk of raw bytes the host framing takes per block: one block per claim of A)
+    const size_t unit = std::max<size_t>(64u << 10, env_size_h("FB2_TWO_ENDED_UNIT_KB", 60u << 10) << 10);
+    std::vector<size_t> cut(1, 0);
+    for (size_t target = unit; target + unit / 2 < len; target += unit) {
+        const size_t q = find_fastq_record_start(bytes, len, std::max(target, cut.back()));
+        if (q < len && q > cut.back()) cut.push_back(q);
+    }
+    const size_t N = cut.size();          // ranges [cut[g], cut[g + 1])
+    cut.push_back(len);
+    if (N < 4 || N > 1500) return FB2_EUNSUPPORTED;   // too small to be worth it (or position ids would not fit): the plain path
+    fb2_sketcher *hs[2] = {nullptr, nullptr};
+    uint8_t *bufs[2] = {nullptr, nullptr};
+    int rcs[2] = {FB2_OK, FB2_OK};
+    bool clean[2] = {true, true};
+    std::mutex mu;
+    // FB2_TWO_ENDED_PRIORITY=1 (A/B switch; measured no gain on the 16-core box): A's copies in flight, B's pieces wait
+    // for them.  Process-wide and never destroyed: the driver lowers it from a stream callback that may run after this
+    // call has returned.
+    static std::atomic<int> link_flag{0};
+    const size_t claim_div = std::max<size_t>(1, env_size_h("FB2_TWO_ENDED_DIV", 3)), back_max = std::max<size_t>(1, env_size_h("FB2_TWO_ENDED_BACK_MAX", 8));
+    size_t lo = 0, hi = N;                // unclaimed ranges [lo, hi)
+    auto claim = [&](bool front, size_t *a, size_t *b) -> bool {
+        std::lock_guard<std::mutex> lk(mu);
+        if (lo >= hi) return false;
+        const size_t left = hi - lo, take = std::max<size_t>(1, std::min<size_t>(front ? 4 : back_max, left / claim_div));   // smaller claims towards the end
+        if (front) { *a = lo; *b = lo + take; lo += take; }
+        else { *a = hi - take; *b = hi; hi -= take; }
+        return true;
+    };
+    fb2_stats st0[2];
+    memset(st0, 0, sizeof(st0));
+    auto open = [&](int w) -> int {
+        int r;
+        if (pool_acquire(&pd, &hs[w], &bufs[w])) r = fb2_sketcher_reset(hs[w]);
+        else r = fb2_sketcher_create(&pd, &hs[w]);
+        if (r == FB2_OK) fb2_sketcher_stats(hs[w], &st0[w]);
+        if (r == FB2_OK && p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(hs[w], p->final_size, f->filter_on);
+        return r;
+    };
+    const char *only = getenv("FB2_TWO_ENDED_ONLY");   // diagnosis: "front" / "back" = the other side takes the minimum
+    const bool only_front = only && only[0] == 'f', only_back = only && only[0] == 'b';
+    size_t b_first = N, b_last_a = N;     // B's first claim is [b_first, N): it holds the end of the stream
+    {
+        size_t a, b;
+        claim(false, &a, &b);
+        b_first = a; b_last_a = a;
+        (void)b;
+    }
+    auto front_work = [&]() {             // A: host-framed, one continuous stream from byte 0
+        int r = open(0);
+        if (r == FB2_OK && getenv("FB2_TWO_ENDED_PRIORITY")) fb2_sketcher_set_link_flag(hs[0], &link_flag, 1);
+        if (r == FB2_OK) r = fb2_sketcher_begin_range(hs[0], FB2_FORMAT_FASTQ, 0u, '\n', '\n', nullptr, 0, 0, 1);
+        size_t a, b;
+        while (r == FB2_OK && !only_back && claim(true, &a, &b)) r = fb2_sketcher_feed_fastx(hs[0], bytes + cut[a], cut[b] - cut[a], 0);
+        if (r == FB2_OK) {
+            uint32_t st = 0, lb = '\n';
+            uint64_t b1 = ~0ULL, b2 = ~0ULL;
+            r = fb2_sketcher_end_range(hs[0], &st, &lb, &b1, &b2);
+            if (r == FB2_OK && (st != 0u || b1 != ~0ULL || b2 != ~0ULL)) clean[0] = false;
+        }
+        rcs[0] = r;
+    };
+    auto back_work = [&]() {              // B: raw bytes over the link, spans from the back
+        int r = open(1);
+        if (r == FB2_OK) {
+            fb2_sketcher_set_polite_copy(hs[1], (unsigned)env_size_h("FB2_TWO_ENDED_PIECE_MB", 64));
+            if (getenv("FB2_TWO_ENDED_PRIORITY")) fb2_sketcher_set_link_flag(hs[1], &link_flag, 0);
+        }
+        size_t a = b_first, b = N;
+        bool have = r == FB2_OK;
+        while (have) {
+            r = fb2_sketcher_begin_range(hs[1], FB2_FORMAT_FASTQ, 0u, '\n', '\n', nullptr, cut[a], (uint64_t)(a + 1) << 44, 0);
+            if (r == FB2_OK) r = fb2_sketcher_feed_fastx(hs[1], bytes + cut[a], cut[b] - cut[a], b == N ? 1 : 0);
+            if (r == FB2_OK && b != N) {
+                uint32_t st = 0, lb = '\n';
+                uint64_t b1 = ~0ULL, b2 = ~0ULL;
+                r = fb2_sketcher_end_range(hs[1], &st, &lb, &b1, &b2);
+                if (r == FB2_OK && (st != 0u || lb != '\n' || b1 != ~0ULL || b2 != ~0ULL)) clean[1] = false;
+            }
+            if (r != FB2_OK || !clean[1]) break;
+            have = !only_front && claim(false, &a, &b);
+        }
+        rcs[1] = r;
+    };
+    const bool trace2 = getenv("FB2_TRACE_TWO_ENDED") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now_ms();
+    double t_front = 0, t_back = 0;
+    {
+        std::thread tb([&] { back_work(); t_back = now_ms(); });
+        front_work();
+        t_front = now_ms();
+        tb.join();
+    }
+    const double t_joined = now_ms();
+    (void)b_last_a;
+    auto release_all = [&](bool keep) {
+        for (int w = 0; w < 2; ++w) {
+            if (!hs[w]) continue;
+            fb2_sketcher_set_polite_copy(hs[w], 0);
+            fb2_sketcher_set_link_flag(hs[w], nullptr, 0);
+            if (keep && pool_release(&pd, hs[w], bufs[w])) continue;
+            if (bufs[w]) cudaFreeHost(bufs[w]);
+            fb2_sketcher_destroy(hs[w]);
+        }
+    };
+    if (rcs[0] != FB2_OK || rcs[1] != FB2_OK || !clean[0] || !clean[1]) {
+        release_all(false);
+        return FB2_EUNSUPPORTED;          // the plain path decides (and words the error, if there is one)
+    }
+    int rc = fb2_sketcher_merge_from(hs[0], hs[1]);
+    if (rc == FB2_OK) rc = fb2_sketcher_sketch(hs[0], name, p, f, out);
+    if (rc == FB2_OK) {
+        memset(&g_last_stream_stats, 0, sizeof(g_last_stream_stats));
+        for (int w = 0; w < 2; ++w) {
+            fb2_stats st1;
+            memset(&st1, 0, sizeof(st1));
+            fb2_sketcher_stats(hs[w], &st1);
+            stats_add_delta(g_last_stream_stats, st0[w], st1);
+        }
+        if (trace2)
+            fprintf(stderr, "two-ended: %zu ranges, host-framed [0, %zu), raw [%zu, %zu); front done +%.1f ms, back done +%.1f ms, "
+                            "merge + sketch %.1f ms\n", N, lo, lo, N, t_front - t_start, t_back - t_start, now_ms() - t_joined);
+    }
+    const std::string msg = rc != FB2_OK ? fb2_last_error() : "";
     release_all(rc == FB2_OK);
     return rc == FB2_OK ? FB2_OK : fb2_fail(rc, msg);
 }

@@ -138,6 +138,9 @@ typedef struct fb2_stats {
     uint64_t band_passes;       /* passes of the banded absorb over a candidate log */
 } fb2_stats;
 int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out);
+/* The same counters for the most recent fb2_sketch_stream call of the calling thread (summed over the handles it
+ * used: the two-ended mode FB2_HOST_STRIP=2 drives two). */
+int fb2_last_stream_stats(fb2_stats *out);
 /* Inspection hook for tests: geometry (7 x u32), per-region symbol counts and the raw symbol buffer of the
  * most recent chunk (see finch_rs_b200/csrc/parse.cu for the layout). */
 int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint32_t *counts, size_t counts_cap,

@@ -1087,3 +1087,42 @@ def test_hash_pieces_of_records(fb, oracle, monkeypatch, k, pieces_env):
     got = gpu_sketch(fb, data, "mash", 4000, k, 0)
     assert_same(got[0], want, k)
     assert got[1] == totals
+
+
+# ---- one FASTQ stream from both ends: host-framed front, raw back (FB2_HOST_STRIP=2) ----------------------
+@pytest.mark.parametrize("crlf", [False, True])
+def test_two_ended_stream(fb, synth, oracle, monkeypatch, crlf):
+    """sketch_stream_two_ended (hostlogic.cpp): handle A frames records on the host from the front of the stream,
+    handle B takes raw ranges from its back, the tables are united exactly.  Same sketch as the oracle's, and the
+    same errors as the plain path for malformed input (which the two-ended path hands back to it)."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    monkeypatch.setenv("FB2_HOST_STRIP", "2")
+    monkeypatch.setenv("FB2_TWO_ENDED_UNIT_KB", "512")
+    monkeypatch.setenv("FB2_TWO_ENDED_MIN_KB", "1024")
+    monkeypatch.setenv("FB2_TRACE_TWO_ENDED", "1")
+    genome = synth.synth_genome(200_000, 11)
+    data = synth.synth_fastq(genome, 30000, 150, 0.005, 12)[0].tobytes()
+    if crlf:
+        data = data.replace(b"\n", b"\r\n")
+    assert len(data) > (8 << 20)
+    sp = fb.SketchParams.from_cli("mash", n_hashes=1000, kmer_length=21, filters_enabled=True)
+    fp = fb.FilterParams(True, (None, None), 0.21, 0.1)
+    sk = fb.sketch_stream(data, "two.fq", sp, fp)
+    rc, osk = oracle.sketch_stream(data, oracle.mash_params(200000, 1000, False, 21, 0), oracle.make_filter(True, (None, None), 0.21, 0.1))
+    assert rc == oracle.OK
+    assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+    assert np.array_equal(sk.extra_counts, osk["extras"])
+    assert [sk.kmers[i, :21].tobytes() for i in range(len(sk))] == osk["kmers"]
+    assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+    st = fb.last_stream_stats()
+    assert st["h2d_bytes"] > 0 and st["kernel_launches"] > 0
+    # a record with unequal sequence / quality lengths somewhere in the middle: the reader's verdict, as always
+    nl = b"\r\n" if crlf else b"\n"
+    lines = data.split(nl)
+    lines[4 * 15000 + 3] += b"I"
+    bad = nl.join(lines)
+    rc, _ = oracle.sketch_stream(bad, oracle.mash_params(200000, 1000, False, 21, 0), oracle.make_filter(True, (None, None), 0.21, 0.1))
+    assert rc == oracle.E_RECORD
+    with pytest.raises(fb.FinchError) as ei:
+        fb.sketch_stream(bad, "bad.fq", sp, fp)
+    assert ei.value.code == fb.ERECORD
