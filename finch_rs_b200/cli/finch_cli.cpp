@@ -8,8 +8,7 @@
 //   calc_sketch_distances     cli/src/main.rs:315-334   (ref-major order, skip equal sketches, max-dist)
 //   update_sketch_params      cli/src/main.rs:336-441
 // The sequence work (sketch_files) and the sorted-hash intersections (raw_distance) run on the GPU
-// through libfinch_b200.so; there is no CPU fallback.  Not supported by this build (clear errors):
-// `.bsk` / `.msh` Cap'n Proto files (-b / -B), `--sketch-type none`, bz2 / xz input (gzip works).
+// through libfinch_b200.so; there is no CPU fallback.  `.bsk` / `.msh` Cap'n Proto files: host/sketch_capnp.hpp.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -26,6 +25,7 @@
 
 #include "../../include/finch_b200.h"
 #include "../host/sketch_json.hpp"
+#include "../host/sketch_capnp.hpp"
 
 using namespace fb2host;
 
@@ -102,7 +102,7 @@ void usage(FILE *f) {
             "    --max-abun-filter <n>   --strand-filter <0.1>   --err-filter <1>   -s, --sketch-type <mash|scaled|none>\n"
             "    -k, --kmer-length <21>   -n, --n-hashes <1000>   --scale <0.001>   --seed <0>   --oversketch <200>\n"
             "    -N, --no-strict   [dist] -p, --pairwise   -q, --queries <name>...   -d, --max-dist <1.0>   --old-dist\n"
-            "    [sketch] -b, --finch-binary-format   -B, --mash-binary-format   (not supported by this build)\n");
+            "    [sketch] -b, --finch-binary-format (.bsk)   -B, --mash-binary-format (.msh)\n");
 }
 Matches parse_args(int argc, char **argv) {
     Matches m;
@@ -285,12 +285,19 @@ std::string read_file(const std::string &path) {
     std::ostringstream ss; ss << in.rdbuf();
     return ss.str();
 }
-std::vector<Sketch> open_sketch_file(const std::string &path) {          // lib/src/lib.rs:96-117
-    if (ends_with(path, MASH_EXT) || ends_with(path, FINCH_BIN_EXT))
-        bail("Cap'n Proto sketch files (*.bsk, *.msh) are not supported by the B200 build: " + path);
+std::vector<Sketch> open_sketch_file(const std::string &path) {          // lib/src/lib.rs:96-117: by extension
     const std::string data = read_file(path);
-    try { return read_multisketch_json(data.data(), data.size()); }
-    catch (const std::exception &e) { bail("Error parsing \"" + path + "\" (" + e.what() + ")"); }
+    try {
+        if (ends_with(path, MASH_EXT)) return read_mash_file(data.data(), data.size());
+        if (ends_with(path, FINCH_BIN_EXT)) return read_finch_file(data.data(), data.size());
+        return read_multisketch_json(data.data(), data.size());
+    } catch (const std::exception &e) { bail("Error parsing \"" + path + "\" (" + e.what() + ")"); }
+}
+// the three sketch file formats (main.rs:52-84): by the extension the flags picked
+std::string serialize_sketches(const std::vector<Sketch> &sk, const std::string &ext) {
+    if (ext == FINCH_BIN_EXT) return write_finch_file(sk);
+    if (ext == MASH_EXT) return write_mash_file(sk, params_from_sketches(sk));
+    return write_multisketch_json(sk);
 }
 
 // FilterParams::filter_sketch (filtering.rs:20-52): the filtered hashes are computed and DROPPED by
@@ -469,11 +476,10 @@ std::vector<SketchDistance> calc_sketch_distances(const std::vector<const Sketch
 int run(int argc, char **argv) {
     const Matches m = parse_args(argc, argv);
     if (m.sub == "sketch") {
-        if (m.is_present("binary_format") || m.is_present("mash_binary_format"))
-            bail("Cap'n Proto output (-b / -B) is not supported by the B200 build; use the JSON .sk format");
+        const std::string file_ext = m.is_present("binary_format") ? FINCH_BIN_EXT : (m.is_present("mash_binary_format") ? MASH_EXT : FINCH_EXT);
         if (m.is_present("output_file") || m.is_present("std_out")) {
             const std::vector<Sketch> sk = parse_mash_files(m);
-            output_to(write_multisketch_json(sk), m.is_present("output_file") ? m.value_of("output_file") : nullptr, FINCH_EXT);
+            output_to(serialize_sketches(sk, file_ext), m.is_present("output_file") ? m.value_of("output_file") : nullptr, file_ext);
         } else {                                                          // generate_sketch_files (main.rs:201-235)
             const uint8_t k = (uint8_t)get_int_arg(m, "kmer_length", 255);
             const FilterParams filters = parse_filter_options(m, k);
@@ -481,9 +487,9 @@ int run(int argc, char **argv) {
             for (auto &fn : m.inputs) {
                 if (is_sketch_file(fn)) bail("Filename " + fn + " is not a sequence file?");
                 const std::vector<Sketch> sk = sketch_files({fn}, params, filters);
-                std::ofstream out(fn + FINCH_EXT, std::ios::binary);
-                if (!out) bail("Could not open " + fn + FINCH_EXT);
-                const std::string js = write_multisketch_json(sk);
+                std::ofstream out(fn + file_ext, std::ios::binary);
+                if (!out) bail("Could not open " + fn + file_ext);
+                const std::string js = serialize_sketches(sk, file_ext);
                 out.write(js.data(), (std::streamsize)js.size());
             }
         }

@@ -217,9 +217,11 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
                                  const fb2_filter *f, fb2_result *out) {
     if (!p || !f || !out || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
     memset(out, 0, sizeof(*out));
-    {   // FB2_HOST_STRIP=2: a large FASTQ stream from both ends, host-framed and raw at once (sketch_stream_two_ended)
+    {   // A large FASTQ stream from both ends, host-framed and raw at once (sketch_stream_two_ended): the default on a host
+        // with >= 8 cores (FB2_HOST_STRIP unset), forced by FB2_HOST_STRIP=2; 0 / 1 pick the single-mode paths
         const char *e = getenv("FB2_HOST_STRIP");
-        if (e && *e == '2' && len >= (env_size_h("FB2_TWO_ENDED_MIN_KB", 256u << 10) << 10) && bytes[0] == '@') {
+        const bool two = e ? *e == '2' : std::thread::hardware_concurrency() >= 8;
+        if (two && len >= (env_size_h("FB2_TWO_ENDED_MIN_KB", 256u << 10) << 10) && bytes[0] == '@') {
             const int rc2 = sketch_stream_two_ended(bytes, len, name, p, f, out);
             if (rc2 == FB2_OK) return FB2_OK;
             fb2_result_free(out);

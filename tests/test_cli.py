@@ -154,7 +154,7 @@ def test_flag_rules(finch, tmp_path):
         (["sketch", "-f", "--no-filter", "-O", str(f)], "cannot be used with"),
         (["sketch", "-o", "x", "-O", str(f)], "cannot be used with"),
         (["dist", str(f), "-p", "-q", "a"], "cannot be used with"),
-        (["sketch", "-b", "-O", str(f)], "not supported by the B200 build"),
+        (["sketch", "-b", "-B", "-O", str(f)], "cannot be used with"),                                          # cli.rs: conflicts_with
         (["sketch", str(f)], "is not a sequence file?"),                                                          # main.rs:213-219
         (["sketch", "-O", str(tmp_path / "missing.sk")], "Error opening"),
         (["frobnicate", "x"], "wasn't expected"),
@@ -286,3 +286,170 @@ def test_dist_pairwise_cut_equals_pair_list(finch, tmp_path):
     d = json.loads(finch("dist", "-p", "-d", "0.05", sk).stdout)
     assert 0 < len(d) < 15 * 14 and all(x["mashDistance"] <= 0.05 for x in d)
     assert all(x["query"] != x["reference"] for x in d)
+
+
+# ---- `.bsk` / `.msh`: Cap'n Proto sketch files (finch_rs_b200/host/sketch_capnp.hpp) --------------------
+def _capnp_words(raw):
+    """capnp::serialize framing -> list of segments (lists of u64 words)."""
+    import struct
+    nseg = struct.unpack_from("<I", raw, 0)[0] + 1
+    sizes = struct.unpack_from("<%dI" % nseg, raw, 4)
+    pos = (4 + 4 * nseg + 7) // 8 * 8
+    segs = []
+    for n in sizes:
+        segs.append(list(struct.unpack_from("<%dQ" % n, raw, pos)))
+        pos += 8 * n
+    assert pos == len(raw)
+    return segs
+
+
+class _Walk:
+    """An independent reader of the published wire format, just enough for single-segment messages: the test's
+    yardstick for the C++ writer (the reference has no golden .bsk / .msh files)."""
+    def __init__(self, words):
+        self.w = words
+
+    def struct(self, p):
+        v = self.w[p]
+        assert v & 3 == 0, "struct pointer expected"
+        off = ((v & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000 >> 2
+        return p + 1 + off, (v >> 32) & 0xFFFF, v >> 48
+
+    def list(self, p):
+        v = self.w[p]
+        if v == 0:
+            return 0, 0, 0, 0, 0
+        assert v & 3 == 1, "list pointer expected"
+        off = ((v & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000 >> 2
+        start, code, count = p + 1 + off, (v >> 32) & 7, v >> 35
+        if code == 7:
+            tag = self.w[start]
+            return start + 1, 7, (tag & 0xFFFFFFFF) >> 2, (tag >> 32) & 0xFFFF, tag >> 48
+        return start, code, count, 0, 0
+
+    def bytes(self, p, text):
+        start, code, count, _, _ = self.list(p)
+        if count == 0:
+            return b""
+        assert code == 2
+        import struct
+        raw = struct.pack("<%dQ" % ((count + 7) // 8), *self.w[start:start + (count + 7) // 8])[:count]
+        if text:
+            assert raw[-1] == 0
+            raw = raw[:-1]
+        return raw
+
+
+def test_bsk_round_trip_and_wire_layout(finch, tmp_path):
+    import struct
+    f = tmp_path / "in.sk"
+    f.write_text(json.dumps(SK))
+    finch("sketch", "-b", "-o", str(tmp_path / "out"), str(f))
+    raw = (tmp_path / "out.bsk").read_bytes()
+    # JSON -> .bsk -> JSON: nothing lost (filters, k-mers, counts, the u64::MAX hash, the quoted name)
+    back = json.loads(finch("sketch", "-O", str(tmp_path / "out.bsk")).stdout)
+    assert back == SK
+    # the bytes, read by the test's own walker with the layouts capnpc generated for finch.capnp
+    segs = _capnp_words(raw)
+    assert len(segs) == 1
+    w = _Walk(segs[0])
+    root, d, p = w.struct(0)
+    assert (d, p) == (0, 1)                                           # Multisketch
+    sk0, code, n, sd, sp = w.list(root)
+    assert (code, n, sd, sp) == (7, 1, 2, 5)                          # List(Sketch), one element of 2 data + 5 pointer words
+    assert w.w[sk0] == 405 and w.w[sk0 + 1] == 339                    # seqLength, numValidKmers
+    assert w.bytes(sk0 + 2, True) == 'a "q"\n.fa'.encode() and w.bytes(sk0 + 3, True) == b""
+    h0, code, n, hd, hp = w.list(sk0 + 4)
+    assert (code, n, hd, hp) == (7, 3, 2, 2)                          # List(KmerCount)
+    for j in range(3):
+        h = h0 + 4 * j
+        assert w.w[h] == int(SK["sketches"][0]["hashes"][j])
+        count, extra = w.w[h + 1] & 0xFFFFFFFF, w.w[h + 1] >> 32
+        assert count == SK["sketches"][0]["counts"][j] and extra == count // 2    # JSON reader: extra_count = count / 2
+        assert w.bytes(h + 2, False) == SK["sketches"][0]["kmers"][j].encode()
+        assert w.w[h + 3] == 0                                        # label: None -> null pointer
+    fp, d, p = w.struct(sk0 + 5)
+    assert (d, p) == (4, 0)
+    assert w.w[fp] & 1 == 1 and (w.w[fp] >> 32) == 2 and (w.w[fp + 1] & 0xFFFFFFFF) == 0xFFFFFFFF   # filtered, low 2, high None
+    assert struct.unpack("<d", struct.pack("<Q", w.w[fp + 2]))[0] == 0.21 and struct.unpack("<d", struct.pack("<Q", w.w[fp + 3]))[0] == 0.1
+    spp, d, p = w.struct(sk0 + 6)
+    assert (d, p) == (5, 0)
+    assert w.w[spp] & 0xFFFF == 0 and (w.w[spp] >> 16) & 0xFF == 21   # murmurHash3, k
+    assert w.w[spp + 3] == 3                                          # finalSize (the JSON's sketchSize)
+
+
+def test_msh_round_trip(finch, tmp_path):
+    f = tmp_path / "in.sk"
+    f.write_text(json.dumps(SK))
+    finch("sketch", "-B", "-o", str(tmp_path / "out"), str(f))
+    raw = (tmp_path / "out.msh").read_bytes()
+    back = json.loads(finch("sketch", "-O", str(tmp_path / "out.msh")).stdout)
+    # what the Mash schema keeps (serialization/mash.rs:60-132, quirk Q10): hashes and counts; no k-mers, no filters,
+    # kmers_to_sketch = final_size = 0
+    want = json.loads(json.dumps(SK))
+    want["sketchSize"] = 0
+    want["sketches"][0]["filters"] = {}
+    want["sketches"][0]["kmers"] = ["", "", ""]
+    assert back == want
+    w = _Walk(_capnp_words(raw)[0])
+    root, d, p = w.struct(0)
+    assert (d, p) == (3, 4)                                           # MinHash
+    assert w.w[root] & 0xFFFFFFFF == 21 and w.w[root] >> 32 == 21     # kmerSize, windowSize
+    assert w.w[root + 1] & 0xFFFFFFFF == 3 and (w.w[root + 1] >> 32) & 7 == 1   # minHashesPerWindow, concatenated only
+    assert w.w[root + 2] >> 32 == 42                                  # hashSeed 0, stored XOR its default 42
+    assert w.bytes(root + 3 + 2, True) == b"ACGT"
+    rl, d, p = w.struct(root + 3 + 3)
+    r0, code, n, rd, rp = w.list(rl)
+    assert (code, n, rd, rp) == (7, 1, 3, 7)
+    assert w.w[r0 + 1] == 405 and w.w[r0 + 2] == 339
+    hs, code, n, _, _ = w.list(r0 + 3 + 5)
+    assert (code, n) == (5, 3) and w.w[hs:hs + 3] == [int(x) for x in SK["sketches"][0]["hashes"]]
+    cs, code, n, _, _ = w.list(r0 + 3 + 6)
+    assert (code, n) == (4, 3) and w.w[cs] == 1 | (3 << 32) and w.w[cs + 1] & 0xFFFFFFFF == 3
+
+
+def test_capnp_reader_takes_segments_and_far_pointers(finch, tmp_path):
+    """The reference's builder spreads large messages over several segments; its files then hold far pointers."""
+    import struct
+    f = tmp_path / "in.sk"
+    f.write_text(json.dumps(SK))
+    finch("sketch", "-b", "-o", str(tmp_path / "one"), str(f))
+    words = _capnp_words((tmp_path / "one.bsk").read_bytes())[0]
+
+    def frame(segs):
+        hdr = struct.pack("<I%dI" % len(segs), len(segs) - 1, *[len(s) for s in segs])
+        hdr += b"\0" * (-len(hdr) % 8)
+        return hdr + b"".join(struct.pack("<%dQ" % len(s), *s) for s in segs)
+    # (1) root = far pointer to a landing pad in segment 1 (the original message, whose word 0 is the root pointer)
+    far = 2 | (0 << 3) | (1 << 32)
+    (tmp_path / "far.bsk").write_bytes(frame([[far], words]))
+    assert json.loads(finch("sketch", "-O", str(tmp_path / "far.bsk")).stdout) == SK
+    # (2) double-far: pad in segment 2 = far pointer to the struct's first word (segment 1, word 1) + its tag word
+    dfar = 2 | (1 << 2) | (0 << 3) | (2 << 32)
+    pad = [2 | (1 << 3) | (1 << 32), (0 << 32) | (1 << 48)]
+    (tmp_path / "dfar.bsk").write_bytes(frame([[dfar], words, pad]))
+    assert json.loads(finch("sketch", "-O", str(tmp_path / "dfar.bsk")).stdout) == SK
+    # damaged files are parse errors, not crashes
+    raw = (tmp_path / "one.bsk").read_bytes()
+    for bad in (raw[:40], raw[:8] + b"\xff" * 8 + raw[16:], b"", raw[:-9]):
+        (tmp_path / "bad.bsk").write_bytes(bad)
+        p = finch("info", str(tmp_path / "bad.bsk"), check=False)
+        assert p.returncode == 1 and "Error parsing" in p.stderr, p.stderr
+
+
+@pytest.mark.gpu
+def test_finch_sketch_bin_and_msh(finch, tmp_path):                  # test_cli.rs:39-78
+    for flag, ext in (("-b", ".bsk"), ("-B", ".msh")):
+        out = tmp_path / ("q" + ext)
+        p = subprocess.run([FINCH, "sketch", "--n-hashes", "10", flag, "-O", QUERY], capture_output=True)
+        assert p.returncode == 0, p.stderr
+        out.write_bytes(p.stdout)
+        sk = json.loads(finch("sketch", "-O", str(out)).stdout)       # read_finch_file / read_mash_file, shown as JSON
+        assert len(sk["sketches"]) == 1 and sk["kmer"] == 21
+        assert len(sk["sketches"][0]["hashes"]) == 10
+        if ext == ".bsk":
+            assert sk["sketchSize"] == 10 and sk["sketches"][0]["kmers"] == GOLDEN_KMERS
+    # dist reads them like .sk files
+    a = tmp_path / "q.bsk"
+    d = json.loads(finch("dist", str(a), str(tmp_path / "q.msh")).stdout)
+    assert len(d) == 1 and d[0]["jaccard"] == 1.0 and d[0]["mashDistance"] == 0.0
