@@ -16,12 +16,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -256,10 +258,115 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
     return FB2_OK;
 }
 
+// ---- compressed input (needletail's parse_fastx_reader sniffs two magic bytes: gzip 1f 8b, bzip2 "BZ", xz fd 37) -------
+// gzip through zlib (linked).  bzip2 and xz through the system's libbz2.so.1.0 / liblzma.so.5, loaded at first use: the
+// image carries the shared objects (Python's bz2 / lzma modules use them) but not their headers, so the few
+// declarations needed are restated here from the libraries' stable public ABI.
+struct StreamDecoder {
+    virtual ~StreamDecoder() {}
+    virtual const char *name() const = 0;
+    // consume from [in, in + avail_in), produce into [out, out + avail_out); 0 = go on, 1 = end of a stream, -1 = corrupt
+    virtual int step(const uint8_t *&in, size_t &avail_in, uint8_t *&out, size_t &avail_out) = 0;
+    virtual bool next_member() { return false; }     // more input after a stream end: decode it as another stream?
+};
+struct GzipDecoder : StreamDecoder {
+    z_stream zs;
+    bool open = false;
+    ~GzipDecoder() override { if (open) inflateEnd(&zs); }
+    const char *name() const override { return "gzip"; }
+    bool init() { memset(&zs, 0, sizeof zs); open = inflateInit2(&zs, 15 + 32) == Z_OK; return open; }
+    int step(const uint8_t *&in, size_t &avail_in, uint8_t *&out, size_t &avail_out) override {
+        zs.next_in = const_cast<Bytef *>(in); zs.avail_in = (uInt)std::min<size_t>(avail_in, 1u << 30);
+        zs.next_out = out; zs.avail_out = (uInt)std::min<size_t>(avail_out, 1u << 30);
+        const uInt in0 = zs.avail_in, out0 = zs.avail_out;
+        const int zr = inflate(&zs, Z_NO_FLUSH);
+        in += in0 - zs.avail_in; avail_in -= in0 - zs.avail_in; out += out0 - zs.avail_out; avail_out -= out0 - zs.avail_out;
+        if (zr == Z_STREAM_END) return 1;
+        return (zr == Z_OK || zr == Z_BUF_ERROR) ? 0 : -1;
+    }
+    bool next_member() override { return inflateReset(&zs) == Z_OK; }   // MultiGzDecoder: concatenated members
+};
+static std::unique_ptr<StreamDecoder> make_gzip_decoder(std::string &why) {
+    std::unique_ptr<GzipDecoder> d(new GzipDecoder());
+    if (!d->init()) { why = "zlib initialisation failed"; return nullptr; }
+    return d;
+}
+// bzlib.h: bz_stream and the three decompression entry points
+struct Bz2Stream {
+    char *next_in; unsigned int avail_in, total_in_lo32, total_in_hi32;
+    char *next_out; unsigned int avail_out, total_out_lo32, total_out_hi32;
+    void *state; void *(*bzalloc)(void *, int, int); void (*bzfree)(void *, void *); void *opaque;
+};
+struct Bz2Decoder : StreamDecoder {
+    Bz2Stream bs;
+    int (*fn_init)(Bz2Stream *, int, int) = nullptr;
+    int (*fn_run)(Bz2Stream *) = nullptr;
+    int (*fn_end)(Bz2Stream *) = nullptr;
+    bool open = false;
+    ~Bz2Decoder() override { if (open) fn_end(&bs); }
+    const char *name() const override { return "bzip2"; }
+    int step(const uint8_t *&in, size_t &avail_in, uint8_t *&out, size_t &avail_out) override {
+        bs.next_in = reinterpret_cast<char *>(const_cast<uint8_t *>(in)); bs.avail_in = (unsigned)std::min<size_t>(avail_in, 1u << 30);
+        bs.next_out = reinterpret_cast<char *>(out); bs.avail_out = (unsigned)std::min<size_t>(avail_out, 1u << 30);
+        const unsigned in0 = bs.avail_in, out0 = bs.avail_out;
+        const int r = fn_run(&bs);                   // BZ_OK 0, BZ_STREAM_END 4, errors negative
+        in += in0 - bs.avail_in; avail_in -= in0 - bs.avail_in; out += out0 - bs.avail_out; avail_out -= out0 - bs.avail_out;
+        return r == 4 ? 1 : (r == 0 ? 0 : -1);
+    }
+};
+static std::unique_ptr<StreamDecoder> make_bz2_decoder(std::string &why) {
+    static void *lib = dlopen("libbz2.so.1.0", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) lib = dlopen("libbz2.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) { why = "bzip2 input needs libbz2.so.1.0, which this system does not have"; return nullptr; }
+    std::unique_ptr<Bz2Decoder> d(new Bz2Decoder());
+    d->fn_init = reinterpret_cast<int (*)(Bz2Stream *, int, int)>(dlsym(lib, "BZ2_bzDecompressInit"));
+    d->fn_run = reinterpret_cast<int (*)(Bz2Stream *)>(dlsym(lib, "BZ2_bzDecompress"));
+    d->fn_end = reinterpret_cast<int (*)(Bz2Stream *)>(dlsym(lib, "BZ2_bzDecompressEnd"));
+    memset(&d->bs, 0, sizeof d->bs);
+    if (!d->fn_init || !d->fn_run || !d->fn_end || d->fn_init(&d->bs, 0, 0) != 0) { why = "libbz2 initialisation failed"; return nullptr; }
+    d->open = true;
+    return d;
+}
+// lzma/base.h: lzma_stream and the stream decoder
+struct XzStream {
+    const uint8_t *next_in; size_t avail_in; uint64_t total_in;
+    uint8_t *next_out; size_t avail_out; uint64_t total_out;
+    const void *allocator; void *internal;
+    void *reserved_ptr1, *reserved_ptr2, *reserved_ptr3, *reserved_ptr4;
+    uint64_t reserved_int1, reserved_int2; size_t reserved_int3, reserved_int4;
+    int reserved_enum1, reserved_enum2;
+};
+struct XzDecoder : StreamDecoder {
+    XzStream xs;
+    int (*fn_init)(XzStream *, uint64_t, uint32_t) = nullptr;
+    int (*fn_code)(XzStream *, int) = nullptr;
+    void (*fn_end)(XzStream *) = nullptr;
+    bool open = false;
+    ~XzDecoder() override { if (open) fn_end(&xs); }
+    const char *name() const override { return "xz"; }
+    int step(const uint8_t *&in, size_t &avail_in, uint8_t *&out, size_t &avail_out) override {
+        xs.next_in = in; xs.avail_in = avail_in; xs.next_out = out; xs.avail_out = avail_out;
+        const int r = fn_code(&xs, 0 /* LZMA_RUN */);   // LZMA_OK 0, LZMA_STREAM_END 1, LZMA_BUF_ERROR 10
+        in = xs.next_in; avail_in = xs.avail_in; out = xs.next_out; avail_out = xs.avail_out;
+        return r == 1 ? 1 : ((r == 0 || r == 10) ? 0 : -1);
+    }
+};
+static std::unique_ptr<StreamDecoder> make_xz_decoder(std::string &why) {
+    static void *lib = dlopen("liblzma.so.5", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) { why = "xz input needs liblzma.so.5, which this system does not have"; return nullptr; }
+    std::unique_ptr<XzDecoder> d(new XzDecoder());
+    d->fn_init = reinterpret_cast<int (*)(XzStream *, uint64_t, uint32_t)>(dlsym(lib, "lzma_stream_decoder"));
+    d->fn_code = reinterpret_cast<int (*)(XzStream *, int)>(dlsym(lib, "lzma_code"));
+    d->fn_end = reinterpret_cast<void (*)(XzStream *)>(dlsym(lib, "lzma_end"));
+    memset(&d->xs, 0, sizeof d->xs);                 // LZMA_STREAM_INIT
+    if (!d->fn_init || !d->fn_code || !d->fn_end || d->fn_init(&d->xs, UINT64_MAX, 0) != 0) { why = "liblzma initialisation failed"; return nullptr; }
+    d->open = true;
+    return d;
+}
+
 // One file through handle `s` (lib.rs:51-94 per file): read in pieces into the worker's pinned buffer,
 // feed the raw bytes, finish the sketch.  gzip input (needletail sniffs the 1f 8b magic, lib.rs:60 via
-// parse_fastx_reader) is inflated on the host by this worker thread, concatenated members included;
-// bz2 / xz stay unsupported (no headers for them in this image) and are reported by the engine.
+// parse_fastx_reader), bzip2 and xz input are decompressed on the host by this worker thread (StreamDecoder above).
 // FB2_TRACE_FILES=1: where the workers of sketch_files spend their time (summed over files, printed per call)
 static std::atomic<uint64_t> g_ns_reset{0}, g_ns_read{0}, g_ns_feed{0}, g_ns_finish{0}, g_n_files{0};
 static inline uint64_t now_ns() {
@@ -283,39 +390,43 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
     // sniff the first two bytes
     unsigned char magic[2] = {0, 0};
     const size_t nmagic = rc == FB2_OK ? fread(magic, 1, 2, fp) : 0;
-    if (rc == FB2_OK && nmagic == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+    std::unique_ptr<StreamDecoder> dec;
+    if (rc == FB2_OK && nmagic == 2) {
+        std::string why;
+        if (magic[0] == 0x1f && magic[1] == 0x8b) dec = make_gzip_decoder(why);
+        else if (magic[0] == 'B' && magic[1] == 'Z') dec = make_bz2_decoder(why);
+        else if (magic[0] == 0xFD && magic[1] == '7') dec = make_xz_decoder(why);
+        if (!why.empty()) rc = fb2_fail(FB2_EUNSUPPORTED, std::string(path) + ": " + why);
+    }
+    if (rc == FB2_OK && dec) {
         std::vector<unsigned char> in(1u << 20);
         memcpy(in.data(), magic, 2);
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (inflateInit2(&zs, 15 + 32) != Z_OK) rc = fb2_fail(FB2_EIO, std::string(path) + ": zlib initialisation failed");
-        bool zopen = rc == FB2_OK;
-        zs.next_in = in.data(); zs.avail_in = 2;
-        size_t fill = 0;
+        const uint8_t *next_in = in.data();
+        size_t avail_in = 2, fill = 0;
         bool eof = false, member_done = false;
         while (rc == FB2_OK) {
-            if (zs.avail_in == 0 && !eof) {
+            if (avail_in == 0 && !eof) {
                 const size_t got = fread(in.data(), 1, in.size(), fp);
                 if (got == 0) eof = true;
-                zs.next_in = in.data(); zs.avail_in = (uInt)got;
+                next_in = in.data(); avail_in = got;
             }
-            if (zs.avail_in == 0 && eof) {
-                if (!member_done) rc = fb2_fail(FB2_EIO, std::string(path) + ": truncated gzip stream");
+            if (avail_in == 0 && eof) {
+                if (!member_done) rc = fb2_fail(FB2_EIO, std::string(path) + ": truncated " + dec->name() + " stream");
                 break;
             }
-            if (member_done) {                      // another gzip member follows (MultiGzDecoder semantics)
-                if (inflateReset(&zs) != Z_OK) { rc = fb2_fail(FB2_EIO, std::string(path) + ": zlib reset failed"); break; }
-                member_done = false;
+            if (member_done) {                      // more bytes after the end of a stream
+                if (!dec->next_member()) break;     // bz2 / xz: one stream, the rest is ignored (BzDecoder / XzDecoder)
+                member_done = false;                // gzip: another member follows (MultiGzDecoder)
             }
-            zs.next_out = buf + fill; zs.avail_out = (uInt)std::min<size_t>(piece - fill, 1u << 30);
-            const int zr = inflate(&zs, Z_NO_FLUSH);
-            fill = (size_t)(zs.next_out - buf);
-            if (zr == Z_STREAM_END) member_done = true;
-            else if (zr != Z_OK && zr != Z_BUF_ERROR) { rc = fb2_fail(FB2_EIO, std::string(path) + ": corrupt gzip stream"); break; }
+            uint8_t *next_out = buf + fill;
+            size_t avail_out = std::min<size_t>(piece - fill, 1u << 30);
+            const int st = dec->step(next_in, avail_in, next_out, avail_out);
+            fill = (size_t)(next_out - buf);
+            if (st == 1) member_done = true;
+            else if (st < 0) { rc = fb2_fail(FB2_EIO, std::string(path) + ": corrupt " + dec->name() + " stream"); break; }
             if (fill == piece) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, fill, 0); fill = 0; }
         }
         if (rc == FB2_OK && fill) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, fill, 0); }
-        if (zopen) inflateEnd(&zs);
     } else if (rc == FB2_OK && !is_stdin && big_regular_file(fp)) {
         // A large plain file: one thread copying it out of the page cache (~5 GB/s) would be 10x slower than the PCIe
         // link it feeds.  Several threads pread() slices of the next 32 MiB piece into a second pinned buffer while the

@@ -351,6 +351,33 @@ def test_sketch_files_gzip(fb, oracle, tmp_path):
     assert "gzip" in str(ei.value)
 
 
+def test_sketch_files_bz2_xz(fb, oracle, tmp_path):
+    """bzip2 ("BZ") and xz (fd 37) input, decompressed on the host through the system's libbz2 / liblzma (loaded at
+    first use); one stream each, as needletail's BzDecoder / XzDecoder read them; truncated streams are errors."""
+    import bz2
+    import lzma
+    rng = np.random.default_rng(92)
+    fa = gen.fasta(rng, n_records=3, max_len=60000, width=70)
+    fq = gen.fastq(rng, n_records=900, max_len=250)
+    p1, p2, p3, p4 = (tmp_path / n for n in ("a.fa.bz2", "b.fq.xz", "bad.fa.bz2", "bad.fq.xz"))
+    p1.write_bytes(bz2.compress(fa))
+    p2.write_bytes(lzma.compress(fq))
+    p3.write_bytes(bz2.compress(fa)[:-100])
+    p4.write_bytes(lzma.compress(fq)[:-100])
+    sp = fb.SketchParams.mash(3000, 200, True, 21, 0)
+    fp = fb.FilterParams(False, (None, None), 0.21, 0.1)
+    sks = fb.sketch_files([str(p1), str(p2)], sp, fp)
+    for sk, data in zip(sks, (fa, fq)):
+        rc, osk = oracle.sketch_stream(data, oracle.mash_params(3000, 200, True, 21, 0), oracle.make_filter(False, (None, None), 0.21, 0.1))
+        assert rc == oracle.OK
+        assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+        assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+    for bad, word in ((p3, "bzip2"), (p4, "xz")):
+        with pytest.raises(fb.FinchError) as ei:
+            fb.sketch_files([str(bad)], sp, fp)
+        assert word in str(ei.value)
+
+
 def test_provisional_first_threshold(fb, synth, oracle, monkeypatch):
     """A first chunk too large for one infinite-threshold launch starts from a provisional finite threshold
     (16 * size expected candidates) and is hashed in one launch; if fewer than `size` distinct keys lie
