@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libfinch_b200.so")
 
 OK = 0
 EINVAL, ECUDA, EFORMAT, ERECORD, EEMPTY, ETOOFEW, EUNSUPPORTED, EIO, ENOMEM = range(-1, -10, -1)
-KIND_MASH, KIND_SCALED = 0, 1
+KIND_MASH, KIND_SCALED, KIND_ALLCOUNTS = 0, 1, 2
 FORMAT_UNKNOWN, FORMAT_FASTA, FORMAT_FASTQ = 0, 1, 2
 
 
@@ -76,7 +76,7 @@ EXPORTS = [
     "fb2_sketcher_totals", "fb2_sketcher_result", "fb2_sketcher_sketch", "fb2_result_free", "fb2_sketcher_stats", "fb2_last_stream_stats",
     "fb2_sketcher_enable_timing", "fb2_sketcher_debug_symbols", "fb2_sketcher_debug_bump", "fb2_filter_counts", "fb2_process_post_filter",
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_multi", "fb2_sketch_stream_multi",
-    "fb2_sketch_files_release_pool", "fb2_dist_batch",
+    "fb2_sketch_files_release_pool", "fb2_dist_batch", "fb2_minmer_matrix",
     "fb2_dist_all_pairs", "fb2_dist_all_pairs_cut", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_old_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
 ]
 
@@ -109,6 +109,7 @@ def lib():
     L.fb2_result_free.restype = None
     L.fb2_sketcher_stats.argtypes = [vp, C.POINTER(_Stats)]
     L.fb2_last_stream_stats.argtypes = [C.POINTER(_Stats)]
+    L.fb2_minmer_matrix.argtypes = [vp, sz, vp, vp, vp, sz, vp, C.c_int32]
     L.fb2_sketcher_enable_timing.argtypes = [vp, C.c_int]
     L.fb2_sketcher_debug_symbols.argtypes = [vp, vp, vp, sz, vp, sz]
     L.fb2_sketcher_debug_bump.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
@@ -206,6 +207,11 @@ class SketchParams:
         return SketchParams(KIND_SCALED, kmers_to_sketch, 0, False, kmer_length, hash_seed, scale, device)
 
     @staticmethod
+    def allcounts(kmer_length=4, device=-1):
+        """SketchParams::AllCounts (mod.rs:68-70): counts of all 4^k k-mers (sketch_schemes/counts.rs), k <= 16."""
+        return SketchParams(KIND_ALLCOUNTS, 0, 0, False, kmer_length, 0, 0.0, device)
+
+    @staticmethod
     def from_cli(sketch_type="mash", n_hashes=1000, kmer_length=21, seed=0, oversketch=200, scale=0.001,
                  no_strict=False, filters_enabled: Optional[bool] = None, device=-1):
         """parse_sketch_options (cli/src/cli.rs:277-340): Mash over-sketches n*200 unless --no-filter."""
@@ -214,12 +220,16 @@ class SketchParams:
             return SketchParams.mash(size, n_hashes, no_strict, kmer_length, seed, device)
         if sketch_type == "scaled":
             return SketchParams.scaled(n_hashes, kmer_length, scale, seed, device)
+        if sketch_type == "none":                          # cli.rs:336
+            return SketchParams.allcounts(kmer_length, device)
         raise FinchError(EINVAL, "A unknown sketch type was selected")
 
     def k(self):
         return self.kmer_length
 
     def expected_size(self):  # mod.rs:148-156
+        if self.kind == KIND_ALLCOUNTS:
+            return 4 ** self.kmer_length
         return self.final_size if self.kind == KIND_MASH else self.kmers_to_sketch
 
     def _c(self, stream=None):
@@ -321,6 +331,8 @@ class _Sketcher:
         final_size = size, no_strict = false whatever it was created from (mash.rs:104-112); ScaledSketcher
         recomputes the scale from its integer max_hash (scaled.rs:102-109)."""
         p = self.params
+        if p.kind == KIND_ALLCOUNTS:                      # counts.rs:65-69
+            return SketchParams.allcounts(p.kmer_length, p.device)
         if p.kind == KIND_MASH:
             return SketchParams.mash(p.kmers_to_sketch, p.kmers_to_sketch, False, p.kmer_length, p.hash_seed, p.device)
         iscale = int(1.0 / p.scale)                       # scaled.rs:23: (1. / scale) as u64
@@ -399,6 +411,11 @@ class _Sketcher:
 def MashSketcher(size, kmer_length, seed, device=-1):
     """MashSketcher::new(size, kmer_length, seed)  (mash.rs:21)"""
     return SketchParams.mash(size, size, False, kmer_length, seed, device).create_sketcher()
+
+
+def AllCountsSketcher(kmer_length, device=-1):
+    """AllCountsSketcher::new(k)  (counts.rs:14-21): process / total_bases_and_kmers / to_vec / parameters, no push."""
+    return SketchParams.allcounts(kmer_length, device).create_sketcher()
 
 
 def ScaledSketcher(size, scale, kmer_length, seed, device=-1):
@@ -599,6 +616,28 @@ def _finish_pair(row, k):
     com, tot = C.c_uint64(), C.c_uint64()
     lib().fb2_distance_finish(C.byref(p), k, C.byref(cont), C.byref(jac), C.byref(md), C.byref(com), C.byref(tot))
     return cont.value, jac.value, md.value, com.value, tot.value
+
+
+def minmer_matrix(ref_sketch, sketches, device=-1):
+    """distance.rs:344-364 (the reference's `numpy` feature): an int32 array [len(sketches), len(ref_sketch)] holding,
+    for every sketch, its count of each of the reference sketch's hashes (0 where it does not hold the hash).
+    `ref_sketch`: a Sketch or an ascending u64 array; `sketches`: Sketch objects or (hashes, counts) pairs."""
+    ref = np.ascontiguousarray(getattr(ref_sketch, "hashes_u64", ref_sketch), np.uint64)
+    hs, cs = [], []
+    for sk in sketches:
+        h, c = (sk.hashes_u64, sk.counts) if hasattr(sk, "hashes_u64") else sk
+        hs.append(np.ascontiguousarray(h, np.uint64)); cs.append(np.ascontiguousarray(c, np.uint32))
+        if len(hs[-1]) != len(cs[-1]):
+            raise FinchError(EINVAL, "hashes and counts differ in length")
+    off = np.zeros(len(hs) + 1, np.uint64)
+    if hs:
+        off[1:] = np.cumsum([len(h) for h in hs])
+    allh = np.concatenate(hs) if hs else np.zeros(0, np.uint64)
+    allc = np.concatenate(cs) if cs else np.zeros(0, np.uint32)
+    out = np.zeros((len(hs), len(ref)), np.int32)
+    _check(lib().fb2_minmer_matrix(ref.ctypes.data, len(ref), allh.ctypes.data, allc.ctypes.data, off.ctypes.data, len(hs),
+                                   out.ctypes.data, device))
+    return out
 
 
 def raw_distance(query_hashes, ref_hashes, scale=0.0):

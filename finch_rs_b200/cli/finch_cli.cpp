@@ -236,7 +236,7 @@ SketchParams parse_sketch_options(const Matches &m, uint8_t k, int filters_enabl
 // ---- the GPU calls ----------------------------------------------------------------------------------
 fb2_params to_c(const SketchParams &p) {
     fb2_params c; memset(&c, 0, sizeof c);
-    c.kind = p.kind == Kind::Scaled ? FB2_KIND_SCALED : FB2_KIND_MASH;
+    c.kind = p.kind == Kind::Scaled ? FB2_KIND_SCALED : (p.kind == Kind::AllCounts ? FB2_KIND_ALLCOUNTS : FB2_KIND_MASH);
     c.kmers_to_sketch = p.kmers_to_sketch; c.final_size = p.final_size; c.no_strict = p.no_strict;
     c.kmer_length = p.kmer_length; c.hash_seed = p.hash_seed; c.scale = p.scale; c.device = -1; c.stream = nullptr;
     return c;
@@ -257,7 +257,6 @@ FilterParams from_c(const fb2_filter &c) {
 std::vector<Sketch> sketch_files(const std::vector<std::string> &files, const SketchParams &p, const FilterParams &f) {
     std::vector<Sketch> out;
     if (files.empty()) return out;
-    if (p.kind == Kind::AllCounts) bail("`--sketch-type none` (AllCountsSketcher) is not supported by the B200 build");
     std::vector<const char *> paths;
     for (auto &s : files) paths.push_back(s.c_str());
     std::vector<fb2_result> res(files.size());

@@ -305,4 +305,28 @@ void launch_gather_hits(const fb2_pair_hit *hits, const uint32_t *order, uint32_
     if (n) gather_hits_kernel<<<(n + 255) / 256, 256, 0, s>>>(hits, order, n, sorted);
 }
 
+// ---- minmer_matrix (lib/src/distance.rs:344-364) ---------------------------------------------------------------------
+// result[i][c] = the count sketch i holds for reference hash c (0 when it does not hold it).  The reference walks a
+// pointer along the reference for every sketch; for ascending, distinct hashes that is a membership test, done here
+// per (sketch, hash) with a binary search of the reference list.
+__global__ void minmer_matrix_kernel(const unsigned long long *__restrict__ ref, uint32_t n_ref,
+                                     const unsigned long long *__restrict__ sk_hash, const uint32_t *__restrict__ sk_cnt,
+                                     const unsigned long long *__restrict__ sk_off, uint32_t n_sk, int32_t *__restrict__ result) {
+    const uint32_t i = blockIdx.y;
+    if (i >= n_sk) return;
+    const unsigned long long a = sk_off[i], b = sk_off[i + 1];
+    for (unsigned long long j = a + blockIdx.x * blockDim.x + threadIdx.x; j < b; j += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long h = sk_hash[j];
+        uint32_t lo = 0, hi = n_ref;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ref[mid] < h) lo = mid + 1; else hi = mid; }
+        if (lo < n_ref && ref[lo] == h) result[(size_t)i * n_ref + lo] = (int32_t)sk_cnt[j];
+    }
+}
+void launch_minmer_matrix(const unsigned long long *ref, uint32_t n_ref, const unsigned long long *sk_hash, const uint32_t *sk_cnt,
+                          const unsigned long long *sk_off, uint32_t n_sk, uint32_t max_len, int32_t *result, cudaStream_t s) {
+    if (!n_sk || !n_ref || !max_len) return;
+    const dim3 grid(std::min<uint32_t>((max_len + 255u) / 256u, 64u), n_sk);
+    minmer_matrix_kernel<<<grid, 256, 0, s>>>(ref, n_ref, sk_hash, sk_cnt, sk_off, n_sk, result);
+}
+
 }  // namespace fb2

@@ -126,6 +126,8 @@ struct fb2_sketcher {
     // fused single-pass parse (parse.cu, parse_fused_kernel): d_stmap holds the look-back status words
     DevBuf d_ptab[2], d_pcount[2];   // hash pieces planned by the parse kernel (PiecePlan), per chunk parity
     bool rec_pieces = true;          // FB2_PIECES=0: uniform 64-position pieces only (A/B)
+    bool allcounts = false;          // FB2_KIND_ALLCOUNTS: d_ac holds counts[4^k] (counts.rs), no table / log / hashing
+    DevBuf d_ac, d_ac_off, d_ac_meta;
     DevBuf d_fhist, d_fok;           // device-side sketch filters: histogram of counts (+ 4 meta words), strand flags
     DevBuf d_ticket;                 // supertile ticket counter (never reset: launches pass its value so far)
     uint32_t ticket_total = 0;
@@ -308,7 +310,8 @@ static int ensure_logs(fb2_sketcher *s) {
 }
 
 static int reset_sketch_state(fb2_sketcher *s) {
-    s->size = s->prm.kmers_to_sketch;   // a finish hint may have lowered it for the previous stream
+    s->size = s->allcounts ? 0 : s->prm.kmers_to_sketch;   // a finish hint may have lowered it for the previous stream
+    if (s->allcounts) CU(cudaMemsetAsync(s->d_ac.p, 0, ((size_t)1 << (2 * s->k)) * 4, s->st));
     memset(s->h_state, 0, sizeof(SketchState));
     s->h_state->threshold = (s->scaled && s->size == 0) ? s->max_hash : ~0ULL;
     TRY(s->d_live_bins.ensure(4096 * sizeof(uint32_t)));
@@ -341,8 +344,10 @@ static int reset_sketch_state(fb2_sketcher *s) {
 extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
     if (!p || !out) return fb2_fail(FB2_EINVAL, "null argument");
     *out = nullptr;
-    if (p->kind != FB2_KIND_MASH && p->kind != FB2_KIND_SCALED) return fb2_fail(FB2_EINVAL, "unknown sketch kind");
+    if (p->kind != FB2_KIND_MASH && p->kind != FB2_KIND_SCALED && p->kind != FB2_KIND_ALLCOUNTS) return fb2_fail(FB2_EINVAL, "unknown sketch kind");
     if (p->kmer_length < 1) return fb2_fail(FB2_EINVAL, "kmer_length must be in 1..=255");
+    // AllCountsSketcher::new allocates 4^k counters (counts.rs:15-21): 16 GiB at k = 16 is where this build stops
+    if (p->kind == FB2_KIND_ALLCOUNTS && p->kmer_length > 16) return fb2_fail(FB2_ENOMEM, "AllCounts: 4^k counters do not fit for k > 16");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
@@ -358,7 +363,8 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
     s->halo = s->k <= 32 ? HALO_SMALL : HALO_BIG;
     s->tab[0].kw = s->tab[1].kw = s->kw;
     s->scaled = p->kind == FB2_KIND_SCALED;
-    s->size = p->kmers_to_sketch;
+    s->allcounts = p->kind == FB2_KIND_ALLCOUNTS;
+    s->size = s->allcounts ? 0 : p->kmers_to_sketch;
     if (s->scaled) {
         // scaled.rs:23,31: iscale = (1./scale) as u64 (saturating); max_hash = u64::MAX / iscale
         const double inv = 1.0 / p->scale;
@@ -408,6 +414,7 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
         if (want > (1u << 22)) want = 1u << 22;  // grows on demand
         if ((rc = ensure_table(s, 0, next_pow2(want))) != FB2_OK) break;
         s->cur = 0;
+        if (s->allcounts && (rc = s->d_ac.ensure(((size_t)1 << (2 * s->k)) * 4)) != FB2_OK) break;
         if ((rc = reset_sketch_state(s)) != FB2_OK) break;
     } while (0);
     if (rc != FB2_OK) { fb2_sketcher_destroy(s); return rc; }
@@ -433,7 +440,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
         if (s->h_snap[i]) cudaFreeHost(s->h_snap[i]);
         if (s->ev_chunk[i]) cudaEventDestroy(s->ev_chunk[i]);
     }
-    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release(); s->d_seam.release(); s->d_ticket.release(); s->d_fhist.release(); s->d_fok.release();
+    s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release(); s->d_seam.release(); s->d_ticket.release(); s->d_fhist.release(); s->d_fok.release(); s->d_ac.release(); s->d_ac_off.release(); s->d_ac_meta.release();
     s->d_carry.release(); s->d_state.release();
     s->sort_keys.release(); s->sort_slots.release(); s->sort_tkeys.release(); s->sort_tslots.release(); s->sort_hist.release(); s->d_bins.release(); s->d_live_bins.release();
     s->out_hash.release(); s->out_cnt.release(); s->out_ext.release(); s->out_kmer.release(); s->out_posx.release();
@@ -877,6 +884,11 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     s->ordinal += (uint64_t)g.n_st * g.st_bytes;
     s->par ^= 1;
 
+    if (s->allcounts) {   // AllCountsSketcher::process (counts.rs:24-36): every valid window bumps its counter
+        launch_count_kmers(s->d_sym[par].as<uint8_t>(), g, g.n_st, pp, (uint32_t)s->k, s->d_ac.as<uint32_t>(), s->st);
+        s->stats.kernel_launches++;
+        return FB2_OK;
+    }
     const uint32_t total_blocks = g.n_st;      // regions
     const double positions = (double)g.n_st * g.st_bytes;
     if (positions <= (double)s->next_launch) s->steady = true;
@@ -1039,6 +1051,7 @@ extern "C" int fb2_sketcher_process(fb2_sketcher *s, const uint8_t *seq, size_t 
 
 // ---- push -----------------------------------------------------------------------------------------
 extern "C" int fb2_sketcher_push(fb2_sketcher *s, const uint8_t *kmer, size_t k, uint8_t extra_count) {
+    if (s && s->allcounts) return fb2_fail(FB2_EUNSUPPORTED, "AllCountsSketcher has no push (counts.rs)");
     if (!s || (!kmer && k)) return fb2_fail(FB2_EINVAL, "null argument");
     if (k > 255) return fb2_fail(FB2_EINVAL, "k-mer longer than 255 bytes");
     ON_DEVICE(s->device);
@@ -1593,11 +1606,63 @@ extern "C" int fb2_sketcher_format(fb2_sketcher *s, int32_t *format) {
 }
 
 // ---- totals / result -------------------------------------------------------------------------------
+static int ensure_hres(fb2_sketcher *s, size_t bytes);
+// AllCountsSketcher::to_vec (counts.rs:38-63) on the device: which indices make an entry, where it goes (two-level
+// scan, index order kept), then hash = index, count, extra_count and the k-mer's bytes.  out == nullptr: only the sum
+// of the counters (total_bases_and_kmers).
+static int allcounts_result(fb2_sketcher *s, fb2_result *out, uint64_t *sum_out) {
+    const uint64_t n = (uint64_t)1 << (2 * s->k);
+    const uint32_t nb = allcounts_blocks(n);
+    TRY(s->d_ac_off.ensure((size_t)nb * 4)); TRY(s->d_ac_meta.ensure(16));
+    CU(cudaMemsetAsync(s->d_ac_meta.p, 0, 16, s->st));
+    launch_allcounts_plan(s->d_ac.as<uint32_t>(), n, (uint32_t)s->k, s->d_ac_off.as<uint32_t>(), s->d_ac_meta.as<unsigned long long>(), s->st);
+    s->stats.kernel_launches += 2;
+    TRY(ensure_hres(s, 16));
+    CU(cudaMemcpyAsync(s->h_res, s->d_ac_meta.p, 16, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    const uint64_t m = ((uint64_t *)s->h_res)[0], sum = ((uint64_t *)s->h_res)[1];
+    if (sum_out) *sum_out = sum;
+    if (!out) return FB2_OK;
+    if (m > 0xFFFFFFFFull) return fb2_fail(FB2_ENOMEM, "AllCounts: too many entries to return");
+    const size_t k = (size_t)s->k;
+    out->n = m;
+    out->kmer_stride = (uint32_t)k;
+    out->hashes = (uint64_t *)malloc(std::max<size_t>(1, (size_t)m * 8));
+    out->counts = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
+    out->extras = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
+    out->kmers = (uint8_t *)malloc(std::max<size_t>(1, (size_t)m * k));
+    if (!out->hashes || !out->counts || !out->extras || !out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
+    if (m) {
+        TRY(s->out_hash.ensure((size_t)m * 8)); TRY(s->out_cnt.ensure((size_t)m * 4)); TRY(s->out_ext.ensure((size_t)m * 4));
+        TRY(s->sel_bytes.ensure((size_t)m * k));
+        launch_allcounts_emit(s->d_ac.as<uint32_t>(), n, (uint32_t)s->k, s->d_ac_off.as<uint32_t>(), s->out_hash.as<unsigned long long>(),
+                              s->out_cnt.as<uint32_t>(), s->out_ext.as<uint32_t>(), s->sel_bytes.as<uint8_t>(), s->st);
+        s->stats.kernel_launches++;
+        CU(cudaMemcpyAsync(out->hashes, s->out_hash.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(out->counts, s->out_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(out->extras, s->out_ext.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(out->kmers, s->sel_bytes.p, (size_t)m * k, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        s->stats.d2h_bytes += (size_t)m * (16 + k);
+    }
+    out->seq_length = 0;                 // counts.rs never adds to total_bases
+    out->num_valid_kmers = sum;
+    out->format = s->format;
+    out->filters.filter_on = 0;
+    return FB2_OK;
+}
 extern "C" int fb2_sketcher_totals(fb2_sketcher *s, uint64_t *total_bases, uint64_t *total_kmers) {
     if (!s) return fb2_fail(FB2_EINVAL, "null handle");
     ON_DEVICE(s->device);
     TRY(flush_all(s));
     TRY(pull_state(s));
+    if (s->allcounts) {   // counts.rs:38-43: total_bases is never updated there; the k-mer total is the sum of the counters
+        uint64_t sum = 0;
+        TRY(allcounts_result(s, nullptr, &sum));
+        if (total_bases) *total_bases = 0;
+        if (total_kmers) *total_kmers = sum;
+        return FB2_OK;
+    }
     if (total_bases) *total_bases = s->h_carry->total_bases + s->lines_bases;
     if (total_kmers) *total_kmers = s->total_kmers;
     return FB2_OK;
@@ -1746,6 +1811,7 @@ extern "C" int fb2_sketcher_result(fb2_sketcher *s, fb2_result *out) {
     ON_DEVICE(s->device);
     memset(out, 0, sizeof(*out));
     TRY(flush_all(s));
+    if (s->allcounts) return allcounts_result(s, out, nullptr);
     uint32_t keep = 0;
     TRY(export_sorted(s, &keep));
     return collect_rows(s, nullptr, keep, out);
@@ -1762,6 +1828,19 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
     auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = trace ? now() : 0.0;
     TRY(flush_all(s));
+    if (s->allcounts) {   // to_vec, then the generic tail of sketch_stream (lib.rs:78-82): filters if they are on
+        TRY(allcounts_result(s, out, nullptr));
+        fb2_filter ff = *f;
+        if (ff.filter_on < 0) ff.filter_on = s->format == FB2_FORMAT_FASTQ ? 1 : 0;
+        if (s->format == FB2_FORMAT_UNKNOWN && f->filter_on < 0) { fb2_result_free(out); return fb2_fail(FB2_EEMPTY, "Should have got a type"); }
+        if (ff.filter_on == 1) {
+            out->format = s->format;
+            const int rcf = fb2_filter_counts(out, &ff);
+            if (rcf != FB2_OK) { fb2_result_free(out); return rcf; }
+        }
+        out->filters = ff;
+        return FB2_OK;
+    }
     const double t1 = trace ? now() : 0.0;
     uint32_t keep = 0;
     TRY(export_sorted(s, &keep));
@@ -1913,6 +1992,43 @@ static int dist_common(const uint64_t *hashes, const uint32_t *lens, size_t n_sk
     CU(cudaMemcpy(d_h.p, hashes, n_sk * stride * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_l.p, lens, n_sk * 4, cudaMemcpyHostToDevice));
     return FB2_OK;
+}
+// minmer_matrix (distance.rs:344-364): n_sk x n_ref, row-major; sketch i's hashes / counts are
+// sk_hashes[sk_off[i] .. sk_off[i + 1]) (ascending), ref_hashes ascending and distinct.
+extern "C" int fb2_minmer_matrix(const uint64_t *ref_hashes, size_t n_ref, const uint64_t *sk_hashes, const uint32_t *sk_counts,
+                                 const uint64_t *sk_off, size_t n_sk, int32_t *result, int32_t device) {
+    if ((n_ref && !ref_hashes) || (n_sk && (!sk_off || !result)) || (n_sk && sk_off[n_sk] && (!sk_hashes || !sk_counts)))
+        return fb2_fail(FB2_EINVAL, "null argument");
+    if (n_ref >= (1ull << 31) || n_sk >= (1ull << 31)) return fb2_fail(FB2_EINVAL, "matrix too large");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fb2_fail(FB2_ECUDA, "no CUDA device: finch_b200 has no CPU fallback");
+    if (!n_sk || !n_ref) return FB2_OK;
+    DeviceScope dev_scope_(device);
+    const uint64_t total = sk_off[n_sk];
+    uint32_t max_len = 0;
+    for (size_t i = 0; i < n_sk; ++i) {
+        if (sk_off[i + 1] < sk_off[i]) return fb2_fail(FB2_EINVAL, "sketch offsets must ascend");
+        max_len = (uint32_t)std::max<uint64_t>(max_len, std::min<uint64_t>(sk_off[i + 1] - sk_off[i], 0xFFFFFFFFull));
+    }
+    DevBuf d_ref, d_h, d_c, d_o, d_r;
+    int rc = FB2_OK;
+    do {
+        if ((rc = d_ref.ensure(n_ref * 8)) != FB2_OK) break;
+        if ((rc = d_h.ensure(std::max<uint64_t>(1, total) * 8)) != FB2_OK) break;
+        if ((rc = d_c.ensure(std::max<uint64_t>(1, total) * 4)) != FB2_OK) break;
+        if ((rc = d_o.ensure((n_sk + 1) * 8)) != FB2_OK) break;
+        if ((rc = d_r.ensure(n_sk * n_ref * 4)) != FB2_OK) break;
+        cudaMemcpy(d_ref.p, ref_hashes, n_ref * 8, cudaMemcpyHostToDevice);
+        if (total) { cudaMemcpy(d_h.p, sk_hashes, total * 8, cudaMemcpyHostToDevice); cudaMemcpy(d_c.p, sk_counts, total * 4, cudaMemcpyHostToDevice); }
+        cudaMemcpy(d_o.p, sk_off, (n_sk + 1) * 8, cudaMemcpyHostToDevice);
+        cudaMemset(d_r.p, 0, n_sk * n_ref * 4);
+        launch_minmer_matrix(d_ref.as<unsigned long long>(), (uint32_t)n_ref, d_h.as<unsigned long long>(), d_c.as<uint32_t>(),
+                             d_o.as<unsigned long long>(), (uint32_t)n_sk, max_len, d_r.as<int32_t>(), 0);
+        const cudaError_t e = cudaMemcpy(result, d_r.p, n_sk * n_ref * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+    } while (0);
+    d_ref.release(); d_h.release(); d_c.release(); d_o.release(); d_r.release();
+    return rc;
 }
 extern "C" int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride, double scale,
                               const uint32_t *q_idx, const uint32_t *r_idx, size_t n_pairs, fb2_pair_out *out,

@@ -222,7 +222,7 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
     {   // A large FASTQ stream from both ends, host-framed and raw at once (sketch_stream_two_ended): the default on a host
         // with >= 8 cores (FB2_HOST_STRIP unset), forced by FB2_HOST_STRIP=2; 0 / 1 pick the single-mode paths
         const char *e = getenv("FB2_HOST_STRIP");
-        const bool two = e ? *e == '2' : std::thread::hardware_concurrency() >= 8;
+        const bool two = p->kind != FB2_KIND_ALLCOUNTS && (e ? *e == '2' : std::thread::hardware_concurrency() >= 8);
         if (two && len >= (env_size_h("FB2_TWO_ENDED_MIN_KB", 256u << 10) << 10) && bytes[0] == '@') {
             const int rc2 = sketch_stream_two_ended(bytes, len, name, p, f, out);
             if (rc2 == FB2_OK) return FB2_OK;
@@ -751,7 +751,7 @@ extern "C" int fb2_sketch_stream_multi(const uint8_t *bytes, size_t len, const c
     if (const char *e = getenv("FB2_MIN_RANGE_KB")) min_range = (size_t)std::max(1L, atol(e)) << 10;
     const bool fasta = len && bytes[0] == '>', fastq = len && bytes[0] == '@';
     size_t G = std::min(devices.size(), std::max<size_t>(1, len / min_range));
-    if (G <= 1 || !(fasta || fastq)) {                   // also: unknown / compressed formats get the usual errors
+    if (G <= 1 || !(fasta || fastq) || p->kind == FB2_KIND_ALLCOUNTS) {   // (counter arrays are not merged across GPUs)                   // also: unknown / compressed formats get the usual errors
         fb2_params pd = *p;
         pd.device = devices[0];
         return fb2_sketch_stream(bytes, len, name, &pd, f, out);

@@ -67,6 +67,12 @@ void launch_filter_pass(const uint32_t *cnt, const uint32_t *ext, uint32_t n, in
 void launch_filter_select(const uint32_t *cnt, const uint8_t *ok, uint32_t n, int use_ok, int abun, uint32_t lo, uint32_t hi,
                           uint32_t limit, uint32_t *idx_out, uint32_t *meta, cudaStream_t s);
 
+void launch_count_kmers(const uint8_t *symbuf, ChunkGeom g, uint32_t n_regions, PiecePlan pp, uint32_t k, uint32_t *counts, cudaStream_t s);
+uint32_t allcounts_blocks(uint64_t n);
+void launch_allcounts_plan(const uint32_t *counts, uint64_t n, uint32_t k, uint32_t *block_off, unsigned long long *meta, cudaStream_t s);
+void launch_allcounts_emit(const uint32_t *counts, uint64_t n, uint32_t k, const uint32_t *block_off, unsigned long long *o_hash,
+                           uint32_t *o_cnt, uint32_t *o_ext, uint8_t *o_kmer, cudaStream_t s);
+
 void launch_merge_tables(TableView src, unsigned long long src_thr, unsigned int src_has_max, TableView dst, SketchState *st,
                          cudaStream_t s);
 void launch_debug_bump(TableView t, unsigned long long key, unsigned long long add_cnt, unsigned long long add_ext,
@@ -82,6 +88,8 @@ int launch_dist_tile(const unsigned long long *hashes, const uint32_t *lens, uin
 int launch_dist_tile_cut(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
                          uint32_t q1, int scaled, unsigned long long max_hash, fb2_pair_hit *hits, unsigned long long *keys,
                          unsigned int *counter, uint32_t cap, int skip_self, double jlow, cudaStream_t s);
+void launch_minmer_matrix(const unsigned long long *ref, uint32_t n_ref, const unsigned long long *sk_hash, const uint32_t *sk_cnt,
+                          const unsigned long long *sk_off, uint32_t n_sk, uint32_t max_len, int32_t *result, cudaStream_t s);
 void launch_iota(uint32_t *v, uint32_t n, cudaStream_t s);
 void launch_gather_hits(const fb2_pair_hit *hits, const uint32_t *order, uint32_t n, fb2_pair_hit *sorted, cudaStream_t s);
 void launch_dist_all(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk,

@@ -8,6 +8,7 @@
 //   Scaled(s, m):     the max(|{h <= m}|, s) smallest (just {h <= m} when s == 0)
 // The admission threshold only ever decreases, so a key that survives to the result was never
 // rejected or purged and its totals are complete.
+#include <algorithm>
 #include "common.cuh"
 #include "device_types.cuh"
 
@@ -782,6 +783,121 @@ void launch_filter_pass(const uint32_t *cnt, const uint32_t *ext, uint32_t n, in
 void launch_filter_select(const uint32_t *cnt, const uint8_t *ok, uint32_t n, int use_ok, int abun, uint32_t lo, uint32_t hi,
                           uint32_t limit, uint32_t *idx_out, uint32_t *meta, cudaStream_t s) {
     filter_select_kernel<<<1, 1024, 0, s>>>(cnt, ok, n, use_ok, abun, lo, hi, limit, idx_out, meta);
+}
+
+// ---- AllCountsSketcher (lib/src/sketch_schemes/counts.rs:7-70): `--sketch-type none` ---------------------------------
+// counts[ix] over ALL 4^k forward k-mers, ix = the k-mer's 2-bit codes MSB-first (needletail's BitKmer: A, C, G, T =
+// 0..3, first base in the highest pair), one saturating increment per valid window (bit_kmers(k, false): windows
+// holding anything but ACGT are skipped, like canonical_kmers).  A thread walks one hash piece of the parse kernel's
+// plan straight out of the symbol region (this is not the headline path: no staging, no persistent blocks).
+__global__ void count_kmers_kernel(const uint8_t *__restrict__ symbuf, ChunkGeom g, uint32_t n_regions, PiecePlan pp, uint32_t k,
+                                   uint32_t *__restrict__ counts) {
+    const uint64_t mask = k >= 32u ? ~0ULL : ((1ULL << (2u * k)) - 1ULL);
+    const uint64_t items = (uint64_t)n_regions * pp.stride;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t region = (uint32_t)(item / pp.stride), j = (uint32_t)(item % pp.stride);
+        if (j >= pp.count[region]) continue;
+        const uint32_t piece = pp.table[(size_t)region * pp.stride + j];
+        const int p0 = (int)(piece & 0xFFFFu), n = (int)(piece >> 16);
+        const uint8_t *sym = symbuf + (size_t)SYM_FRONT + (size_t)region * g.region_stride;   // sym[-1 .. -halo]: what precedes the region
+        uint64_t fwd = 0;
+        uint32_t run = 0;
+        for (int i = p0 - (int)k + 1; i < p0 + n; ++i) {
+            const uint32_t c = sym[i];
+            if (c < 4u) { fwd = ((fwd << 2) | c) & mask; ++run; } else run = 0;
+            if (i >= p0 && run >= k) {
+                const uint32_t old = atomicAdd(&counts[fwd], 1u);
+                if (old == 0xFFFFFFFFu) atomicSub(&counts[fwd], 1u);      // saturating_add: a wrapping add undoes itself
+            }
+        }
+    }
+}
+__device__ __forceinline__ uint64_t revcomp_msb(uint64_t ix, uint32_t k) {       // needletail bitkmer::reverse_complement
+    uint64_t x = ~ix;
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+    x = (x >> 32) | (x << 32);
+    return x >> (64u - 2u * k);
+}
+// to_vec (counts.rs:38-63): walking ix upwards, an entry is made for ix when its count is not zero and its reverse
+// complement has not been folded into an earlier entry -- i.e. ix <= rc(ix), or counts[rc(ix)] == 0.
+__device__ __forceinline__ bool allcounts_keeps(const uint32_t *counts, uint64_t ix, uint32_t k) {
+    if (counts[ix] == 0u) return false;
+    const uint64_t rc = revcomp_msb(ix, k);
+    return ix <= rc || counts[rc] == 0u;
+}
+constexpr uint32_t AC_BLOCK = 1024;
+__global__ void __launch_bounds__(AC_BLOCK)
+allcounts_flag_kernel(const uint32_t *__restrict__ counts, uint64_t n, uint32_t k, uint32_t *__restrict__ block_kept,
+                      unsigned long long *total) {
+    const uint64_t ix = (uint64_t)blockIdx.x * AC_BLOCK + threadIdx.x;
+    const bool keep = ix < n && allcounts_keeps(counts, ix, k);
+    const uint32_t kept = __syncthreads_count(keep);
+    unsigned long long c = ix < n ? counts[ix] : 0u;                      // total_bases_and_kmers: the sum of the counts
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31u) == 0u && c) atomicAdd(total, c);
+    if (threadIdx.x == 0) block_kept[blockIdx.x] = kept;
+}
+__global__ void __launch_bounds__(1024)
+allcounts_scan_kernel(uint32_t *block_kept, uint32_t n_blocks, unsigned long long *n_out) {   // exclusive scan in place, one block
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += 1024u) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < n_blocks ? block_kept[i] : 0u;
+        unsigned long long x = v;
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31u) >= (uint32_t)d) x += y; }
+        if ((threadIdx.x & 31u) == 31u) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        unsigned long long before = carry;
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) before += wsum[w];
+        // offsets are written as 32-bit values: more than 2^32 - 1 entries cannot be returned anyway (checked by the host)
+        if (i < n_blocks) block_kept[i] = (uint32_t)min(before + x - v, 0xFFFFFFFFull);
+        __syncthreads();
+        if (threadIdx.x == 1023u) carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+__global__ void __launch_bounds__(AC_BLOCK)
+allcounts_emit_kernel(const uint32_t *__restrict__ counts, uint64_t n, uint32_t k, const uint32_t *__restrict__ block_off,
+                      unsigned long long *__restrict__ o_hash, uint32_t *__restrict__ o_cnt, uint32_t *__restrict__ o_ext,
+                      uint8_t *__restrict__ o_kmer) {
+    __shared__ uint32_t wsum[32];
+    const uint64_t ix = (uint64_t)blockIdx.x * AC_BLOCK + threadIdx.x;
+    const bool keep = ix < n && allcounts_keeps(counts, ix, k);
+    const uint32_t b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31u) == 0u) wsum[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    uint32_t before = block_off[blockIdx.x];
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) before += wsum[w];
+    if (!keep) return;
+    const size_t at = (size_t)before + __popc(b & ((1u << (threadIdx.x & 31u)) - 1u));
+    const uint32_t extra = counts[revcomp_msb(ix, k)];
+    o_hash[at] = ix;
+    o_ext[at] = extra;
+    o_cnt[at] = counts[ix] + extra;                                       // `count += extra_count`
+    for (uint32_t i = 0; i < k; ++i) o_kmer[at * k + i] = (uint8_t)"ACGT"[(ix >> (2u * (k - 1u - i))) & 3u];   // bitmer_to_bytes
+}
+void launch_count_kmers(const uint8_t *symbuf, ChunkGeom g, uint32_t n_regions, PiecePlan pp, uint32_t k, uint32_t *counts, cudaStream_t s) {
+    if (!n_regions) return;
+    const uint64_t items = (uint64_t)n_regions * pp.stride;
+    count_kmers_kernel<<<(uint32_t)std::min<uint64_t>((items + 255) / 256, 148u * 32u), 256, 0, s>>>(symbuf, g, n_regions, pp, k, counts);
+}
+uint32_t allcounts_blocks(uint64_t n) { return (uint32_t)((n + AC_BLOCK - 1) / AC_BLOCK); }
+void launch_allcounts_plan(const uint32_t *counts, uint64_t n, uint32_t k, uint32_t *block_off, unsigned long long *meta /* [0] entries, [1] sum */,
+                           cudaStream_t s) {
+    const uint32_t nb = allcounts_blocks(n);
+    allcounts_flag_kernel<<<nb, AC_BLOCK, 0, s>>>(counts, n, k, block_off, meta + 1);
+    allcounts_scan_kernel<<<1, 1024, 0, s>>>(block_off, nb, meta);
+}
+void launch_allcounts_emit(const uint32_t *counts, uint64_t n, uint32_t k, const uint32_t *block_off, unsigned long long *o_hash,
+                           uint32_t *o_cnt, uint32_t *o_ext, uint8_t *o_kmer, cudaStream_t s) {
+    allcounts_emit_kernel<<<allcounts_blocks(n), AC_BLOCK, 0, s>>>(counts, n, k, block_off, o_hash, o_cnt, o_ext, o_kmer);
 }
 
 }  // namespace fb2

@@ -43,6 +43,8 @@ extern "C" {
 
 #define FB2_KIND_MASH 0   /* SketchParams::Mash   (mod.rs:55-61) */
 #define FB2_KIND_SCALED 1 /* SketchParams::Scaled (mod.rs:62-67) */
+#define FB2_KIND_ALLCOUNTS 2 /* SketchParams::AllCounts (mod.rs:68-70): counts of all 4^k k-mers (sketch_schemes/counts.rs), k <= 16;
+                              * process / feed / totals / result / sketch only (the reference type has no push) */
 
 #define FB2_FORMAT_UNKNOWN 0
 #define FB2_FORMAT_FASTA 1 /* needletail::parser::Format::Fasta */
@@ -219,6 +221,11 @@ double fb2_dist_last_kernel_ms(void);
 void fb2_distance_finish(const fb2_pair_out *p, uint8_t kmer_length, double *containment,
                          double *jaccard, double *mash_distance, uint64_t *common_hashes,
                          uint64_t *total_hashes);
+
+/* minmer_matrix (distance.rs:344-364): result[i * n_ref + c] = the count sketch i holds for reference hash c, 0 when it
+ * does not hold it.  Sketch i = sk_hashes / sk_counts[sk_off[i] .. sk_off[i + 1]); all hash lists ascending. */
+int fb2_minmer_matrix(const uint64_t *ref_hashes, size_t n_ref, const uint64_t *sk_hashes, const uint32_t *sk_counts,
+                      const uint64_t *sk_off, size_t n_sk, int32_t *result, int32_t device);
 
 /* old_distance (distance.rs:136-157, `--old-dist`) from `common` of a scale-0 fb2_dist_batch pair and the two
  * sketch lengths; FB2_EINVAL where the reference panics (empty query, non-empty reference). */

@@ -588,3 +588,73 @@ double fo_mash_distance(double jaccard, uint8_t k) {
     double m = (md != md) ? 0.0 : (md > 0.0 ? md : 0.0);
     return m < 1.0 ? m : 1.0;
 }
+
+/* ---- AllCountsSketcher (lib/src/sketch_schemes/counts.rs:7-70) ------------------------------------------------
+ * counts has 4^k entries.  process (counts.rs:24-36): seq.normalize(false).bit_kmers(k, false) -- needletail 0.5
+ * BitNuclKmer, canonical = false: one (position, forward BitKmer) per window of k bases that are all ACGT, the
+ * BitKmer's integer holding the first base in its highest pair (A, C, G, T = 0..3); counts[kmer] saturating += 1. */
+void fo_allcounts_process(uint32_t *counts, uint8_t k, const uint8_t *raw_seq, size_t len) {
+    uint8_t *norm = (uint8_t *)malloc(len ? len : 1);
+    const size_t n = fo_normalize(raw_seq, len, norm);
+    const uint64_t mask = k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+    uint64_t fwd = 0;
+    size_t run = 0;
+    for (size_t i = 0; i < n; ++i) {
+        int c;
+        switch (norm[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: c = -1; }
+        if (c < 0) { run = 0; continue; }
+        fwd = ((fwd << 2) | (uint64_t)c) & mask;
+        if (++run >= k) { if (counts[fwd] != 0xFFFFFFFFu) counts[fwd]++; }
+    }
+    free(norm);
+}
+static uint64_t fo_bit_revcomp(uint64_t ix, uint8_t k) {            /* needletail bitkmer::reverse_complement */
+    uint64_t r = 0;
+    for (uint8_t i = 0; i < k; ++i) { r = (r << 2) | (3 - (ix & 3)); ix >>= 2; }
+    return r;
+}
+/* to_vec (counts.rs:45-63), literally: a working copy is zeroed at the reverse complement of every emitted index.
+ * Returns the number of entries; kmers: k bytes each (bitmer_to_bytes: first base from the highest pair). */
+size_t fo_allcounts_to_vec(const uint32_t *self_counts, uint8_t k, uint64_t *hashes, uint32_t *cnt, uint32_t *ext,
+                           uint8_t *kmers, size_t cap) {
+    const uint64_t n = 1ULL << (2 * k);
+    uint32_t *counts = (uint32_t *)malloc((size_t)n * 4);
+    memcpy(counts, self_counts, (size_t)n * 4);
+    size_t m = 0;
+    for (uint64_t ix = 0; ix < n; ++ix) {
+        uint32_t count = counts[ix];
+        if (count == 0) continue;
+        const uint64_t rc = fo_bit_revcomp(ix, k);
+        const uint32_t extra = self_counts[rc];
+        counts[rc] = 0;
+        count += extra;                                             /* wraps in a release build */
+        if (m < cap) {
+            hashes[m] = ix; cnt[m] = count; ext[m] = extra;
+            for (uint8_t i = 0; i < k; ++i) kmers[m * k + i] = (uint8_t)"ACGT"[(ix >> (2 * (k - 1 - i))) & 3];
+        }
+        ++m;
+    }
+    free(counts);
+    return m;
+}
+uint64_t fo_allcounts_total(const uint32_t *counts, uint8_t k) {    /* total_bases_and_kmers().1 (counts.rs:38-43) */
+    uint64_t t = 0;
+    for (uint64_t ix = 0; ix < (1ULL << (2 * k)); ++ix) t += counts[ix];
+    return t;
+}
+
+/* ---- minmer_matrix (lib/src/distance.rs:344-364), literally: one row per sketch, one column per reference hash, the
+ * sketch's COUNT where it holds the hash (the pointer walk never passes the last reference entry). */
+void fo_minmer_matrix(const uint64_t *ref_hashes, size_t n_ref, const uint64_t *const *sk_hashes, const uint32_t *const *sk_counts,
+                      const size_t *sk_len, size_t n_sk, int32_t *result /* n_sk x n_ref, zeroed here */) {
+    memset(result, 0, n_sk * n_ref * sizeof(int32_t));
+    if (n_ref == 0) return;                                         /* (the reference would index out of bounds) */
+    for (size_t i = 0; i < n_sk; ++i) {
+        size_t ref_pos = 0;
+        for (size_t j = 0; j < sk_len[i]; ++j) {
+            const uint64_t h = sk_hashes[i][j];
+            while (h > ref_hashes[ref_pos] && ref_pos < n_ref - 1) ref_pos++;
+            if (h == ref_hashes[ref_pos]) result[i * n_ref + ref_pos] = (int32_t)sk_counts[i][j];
+        }
+    }
+}

@@ -127,4 +127,12 @@ double fo_mash_distance(double jaccard, uint8_t k); /* distance.rs:35-41 */
 #ifdef __cplusplus
 }
 #endif
+/* AllCountsSketcher (counts.rs) and minmer_matrix (distance.rs:344-364) */
+void fo_allcounts_process(uint32_t *counts, uint8_t k, const uint8_t *raw_seq, size_t len);
+size_t fo_allcounts_to_vec(const uint32_t *self_counts, uint8_t k, uint64_t *hashes, uint32_t *cnt, uint32_t *ext,
+                           uint8_t *kmers, size_t cap);
+uint64_t fo_allcounts_total(const uint32_t *counts, uint8_t k);
+void fo_minmer_matrix(const uint64_t *ref_hashes, size_t n_ref, const uint64_t *const *sk_hashes, const uint32_t *const *sk_counts,
+                      const size_t *sk_len, size_t n_sk, int32_t *result);
+
 #endif

@@ -96,6 +96,12 @@ def lib():
                                   C.POINTER(C.c_double), C.POINTER(C.c_double), u64p, u64p]
     L.fo_old_distance.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                   C.POINTER(C.c_double), C.POINTER(C.c_double), u64p, u64p]
+    L.fo_allcounts_process.argtypes = [C.c_void_p, C.c_uint8, C.c_void_p, C.c_size_t]
+    L.fo_allcounts_to_vec.argtypes = [C.c_void_p, C.c_uint8, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.fo_allcounts_to_vec.restype = C.c_size_t
+    L.fo_allcounts_total.argtypes = [C.c_void_p, C.c_uint8]
+    L.fo_allcounts_total.restype = C.c_uint64
+    L.fo_minmer_matrix.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.fo_mash_distance.argtypes = [C.c_double, C.c_uint8]
     L.fo_mash_distance.restype = C.c_double
     _lib = L
@@ -304,3 +310,40 @@ def old_distance(q, r):
 
 def mash_distance(jaccard, k):
     return float(lib().fo_mash_distance(jaccard, k))
+
+
+class AllCountsSketcher:
+    """Mirror of AllCountsSketcher (lib/src/sketch_schemes/counts.rs)."""
+
+    def __init__(self, k):
+        self.k = k
+        self.counts = np.zeros(4 ** k, np.uint32)
+
+    def process(self, raw_seq):
+        addr, n, keep = _buf(raw_seq)
+        lib().fo_allcounts_process(self.counts.ctypes.data, self.k, addr, n)
+
+    def total_bases_and_kmers(self):
+        return 0, int(lib().fo_allcounts_total(self.counts.ctypes.data, self.k))
+
+    def to_vec(self):
+        cap = int(np.count_nonzero(self.counts))
+        h, c, x = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        km = np.zeros((cap, self.k), np.uint8)
+        n = lib().fo_allcounts_to_vec(self.counts.ctypes.data, self.k, h.ctypes.data, c.ctypes.data, x.ctypes.data,
+                                      km.ctypes.data, cap)
+        return {"hashes": h[:n], "counts": c[:n], "extras": x[:n], "kmers": [km[i].tobytes() for i in range(n)]}
+
+
+def minmer_matrix(ref_hashes, sketches):
+    """distance.rs:344-364.  sketches: list of (hashes u64 ascending, counts u32)."""
+    ref = np.ascontiguousarray(ref_hashes, np.uint64)
+    hs = [np.ascontiguousarray(h, np.uint64) for h, _ in sketches]
+    cs = [np.ascontiguousarray(c, np.uint32) for _, c in sketches]
+    n = len(sketches)
+    hp = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in hs])
+    cp = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in cs])
+    ln = (C.c_size_t * max(1, n))(*[len(a) for a in hs])
+    out = np.zeros((n, len(ref)), np.int32)
+    lib().fo_minmer_matrix(ref.ctypes.data, len(ref), hp, cp, ln, n, out.ctypes.data)
+    return out

@@ -453,3 +453,18 @@ def test_finch_sketch_bin_and_msh(finch, tmp_path):                  # test_cli.
     a = tmp_path / "q.bsk"
     d = json.loads(finch("dist", str(a), str(tmp_path / "q.msh")).stdout)
     assert len(d) == 1 and d[0]["jaccard"] == 1.0 and d[0]["mashDistance"] == 0.0
+
+
+@pytest.mark.gpu
+def test_finch_sketch_type_none(finch, oracle):                      # cli.rs:336, counts.rs
+    sk = json.loads(finch("sketch", "--sketch-type", "none", "-k", "4", "-O", QUERY).stdout)
+    assert (sk["kmer"], sk["hashType"], sk["hashBits"], sk["hashSeed"], sk["sketchSize"], sk["scale"]) == (4, "None", 0, 0, 256, None)
+    o = oracle.AllCountsSketcher(4)
+    rc, _, recs = oracle.parse_fastx(open(QUERY, "rb").read())
+    for r in recs:
+        o.process(r)
+    want = o.to_vec()
+    s = sk["sketches"][0]
+    assert [int(h) for h in s["hashes"]] == [int(h) for h in want["hashes"]]
+    assert s["counts"] == [int(c) for c in want["counts"]] and s["kmers"] == [k.decode() for k in want["kmers"]]
+    assert s["seqLength"] == 0 and s["numValidKmers"] == o.total_bases_and_kmers()[1]

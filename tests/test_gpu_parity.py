@@ -1153,3 +1153,69 @@ def test_two_ended_stream(fb, synth, oracle, monkeypatch, crlf):
     with pytest.raises(fb.FinchError) as ei:
         fb.sketch_stream(bad, "bad.fq", sp, fp)
     assert ei.value.code == fb.ERECORD
+
+
+# ---- AllCountsSketcher (`--sketch-type none`, counts.rs) and minmer_matrix (distance.rs:344-364) -----------------
+@pytest.mark.parametrize("k", [1, 3, 4, 8, 11])
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+def test_allcounts_sketcher(fb, oracle, monkeypatch, k, fmt):
+    """Counts of all 4^k forward k-mers, folded with their reverse complements by to_vec exactly as counts.rs does
+    (palindromes count twice; an index whose reverse complement came first is skipped)."""
+    monkeypatch.setenv("FB2_CHUNK_MB", "1")
+    rng = np.random.default_rng(300 + k)
+    data = gen.fasta(rng, n_records=8, min_len=200000, max_len=400000, width=61, messy=0.01) if fmt == "fasta" else \
+        gen.fastq(rng, n_records=12000, max_len=300, messy=0.01)
+    assert len(data) > (1 << 20)
+    o = oracle.AllCountsSketcher(k)
+    rc, _, recs = oracle.parse_fastx(data)
+    assert rc == oracle.OK
+    for r in recs:
+        o.process(r)
+    want = o.to_vec()
+    with fb.AllCountsSketcher(k) as s:
+        s.feed_fastx(data, final=True)
+        h, c, x, km, seq_len, n_kmers, _ = s.to_arrays()
+        assert s.total_bases_and_kmers() == o.total_bases_and_kmers() == (0, n_kmers)
+        assert s.parameters().kind == fb.KIND_ALLCOUNTS and s.parameters().expected_size() == 4 ** k
+        with pytest.raises(fb.FinchError):
+            s.push(b"A" * k, 0)
+    assert np.array_equal(h, want["hashes"]) and np.array_equal(c, want["counts"]) and np.array_equal(x, want["extras"])
+    assert [km[i, :k].tobytes() for i in range(len(h))] == want["kmers"]
+    assert seq_len == 0
+    # the same through process(): one record at a time
+    with fb.AllCountsSketcher(k) as s:
+        for r in recs[:200]:
+            s.process(r)
+        o2 = oracle.AllCountsSketcher(k)
+        for r in recs[:200]:
+            o2.process(r)
+        h2, c2, x2, *_ = s.to_arrays()
+        w2 = o2.to_vec()
+        assert np.array_equal(h2, w2["hashes"]) and np.array_equal(c2, w2["counts"]) and np.array_equal(x2, w2["extras"])
+    # sketch_stream with the type taken from the command line (cli.rs:336)
+    sk = fb.sketch_stream(data, "all.fx", fb.SketchParams.from_cli("none", kmer_length=k), fb.FilterParams(False))
+    assert np.array_equal(sk.hashes_u64, want["hashes"]) and np.array_equal(sk.counts, want["counts"])
+
+
+def test_allcounts_refuses_large_k(fb):
+    with pytest.raises(fb.FinchError) as e:
+        fb.AllCountsSketcher(17)
+    assert e.value.code == fb.ENOMEM
+
+
+def test_minmer_matrix(fb, oracle):
+    rng = np.random.default_rng(17)
+    ref = np.unique(rng.integers(0, 1 << 62, size=5000, dtype=np.uint64))
+    sketches = []
+    for i in range(40):
+        own = np.unique(rng.integers(0, 1 << 62, size=int(rng.integers(0, 3000)), dtype=np.uint64))
+        shared = rng.choice(ref, size=int(rng.integers(0, 2000)), replace=False)
+        h = np.unique(np.concatenate([own, shared]))
+        sketches.append((h, rng.integers(1, 1000, size=len(h), dtype=np.uint32)))
+    sketches.append((np.zeros(0, np.uint64), np.zeros(0, np.uint32)))                  # an empty sketch
+    sketches.append((ref.copy(), np.full(len(ref), 7, np.uint32)))                     # the reference itself
+    got = fb.minmer_matrix(ref, sketches)
+    want = oracle.minmer_matrix(ref, sketches)
+    assert got.dtype == np.int32 and got.shape == (len(sketches), len(ref))
+    assert np.array_equal(got, want)
+    assert (got[-1] == 7).all() and not got[-2].any()
