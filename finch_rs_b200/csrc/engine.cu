@@ -126,6 +126,8 @@ struct fb2_sketcher {
     // fused single-pass parse (parse.cu, parse_fused_kernel): d_stmap holds the look-back status words
     DevBuf d_ptab[2], d_pcount[2];   // hash pieces planned by the parse kernel (PiecePlan), per chunk parity
     bool rec_pieces = true;          // FB2_PIECES=0: uniform 64-position pieces only (A/B)
+    bool fresh = false;              // nothing fed since create / reset (fb2_sketcher_sketch_small needs an untouched handle)
+    bool small_mode = false; int small_par = 0; uint64_t small_ord = 0;   // run_chunk stops after the parse kernels
     bool allcounts = false;          // FB2_KIND_ALLCOUNTS: d_ac holds counts[4^k] (counts.rs), no table / log / hashing
     DevBuf d_ac, d_ac_off, d_ac_meta;
     DevBuf d_fhist, d_fok;           // device-side sketch filters: histogram of counts (+ 4 meta words), strand flags
@@ -337,6 +339,7 @@ static int reset_sketch_state(fb2_sketcher *s) {
     s->presniff.clear();
     s->push_bytes.clear(); s->push_extra.clear(); s->push_offs.assign(1, 0u);
     s->arena.clear(); s->arena_flushed = 0;
+    s->fresh = true; s->small_mode = false;
     return FB2_OK;
 }
 
@@ -884,6 +887,7 @@ static int run_chunk(fb2_sketcher *s, const uint8_t *d_raw, uint32_t len, int mo
     s->ordinal += (uint64_t)g.n_st * g.st_bytes;
     s->par ^= 1;
 
+    if (s->small_mode) { s->small_par = par; s->small_ord = ord_base; return FB2_OK; }   // fb2_sketcher_sketch_small drives the rest
     if (s->allcounts) {   // AllCountsSketcher::process (counts.rs:24-36): every valid window bumps its counter
         launch_count_kmers(s->d_sym[par].as<uint8_t>(), g, g.n_st, pp, (uint32_t)s->k, s->d_ac.as<uint32_t>(), s->st);
         s->stats.kernel_launches++;
@@ -1030,6 +1034,7 @@ extern "C" int fb2_sketcher_process(fb2_sketcher *s, const uint8_t *seq, size_t 
     if (!s || (!seq && len)) return fb2_fail(FB2_EINVAL, "null argument");
     ON_DEVICE(s->device);
     if (s->stream_open) return fb2_fail(FB2_EINVAL, "process() while a FASTX stream is open");
+    s->fresh = false;
     TRY(flush_push(s));
     TRY(ensure_stage(s));
     if (s->stage_mode != MODE_LINES) { TRY(flush_stage(s)); s->stage_mode = MODE_LINES; }
@@ -1054,6 +1059,7 @@ extern "C" int fb2_sketcher_push(fb2_sketcher *s, const uint8_t *kmer, size_t k,
     if (s && s->allcounts) return fb2_fail(FB2_EUNSUPPORTED, "AllCountsSketcher has no push (counts.rs)");
     if (!s || (!kmer && k)) return fb2_fail(FB2_EINVAL, "null argument");
     if (k > 255) return fb2_fail(FB2_EINVAL, "k-mer longer than 255 bytes");
+    s->fresh = false;
     ON_DEVICE(s->device);
     TRY(flush_stage(s));
     s->push_bytes.insert(s->push_bytes.end(), kmer, kmer + k);
@@ -1258,10 +1264,10 @@ static int feed_fastq_stripped(fb2_sketcher *s, const uint8_t *bytes, size_t len
     return FB2_OK;
 }
 
-static int end_stream(fb2_sketcher *s) {
-    TRY(flush_stage(s));
-    TRY(settle_all(s));
-    TRY(pull_state(s));
+// What the reader makes of the stream now that its last byte is in: FASTA -- the last record's length; FASTQ -- the
+// end-of-input rules (truncated record, record errors seen by the kernels, the last record's length check).  Works on
+// the host mirror of the carry (pulled by the caller) and the host's copy of the stream's last bytes.
+static int stream_verdict(fb2_sketcher *s) {
     ParseCarry *c = s->h_carry;
     int rc = FB2_OK;
     if (s->format == FB2_FORMAT_FASTA) {
@@ -1336,6 +1342,14 @@ static int end_stream(fb2_sketcher *s) {
             }
         }
     }
+    return rc;
+}
+static int end_stream(fb2_sketcher *s) {
+    TRY(flush_stage(s));
+    TRY(settle_all(s));
+    TRY(pull_state(s));
+    ParseCarry *c = s->h_carry;
+    const int rc = stream_verdict(s);
     // a later stream or record must not join this one: break the carried symbols
     c->state = 0; c->prev1 = c->prev2 = '\n';
     TRY(push_carry(s));
@@ -1347,6 +1361,7 @@ static int end_stream(fb2_sketcher *s) {
 
 extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, size_t len, int final) {
     if (!s || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
+    s->fresh = false;
     ON_DEVICE(s->device);
     if (!s->stream_open) {
         // format sniffing looks at two bytes (compressed-input magic): a shorter first piece waits for the next one
@@ -1399,6 +1414,7 @@ extern "C" int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev, siz
     if (!s || (!dev && len)) return fb2_fail(FB2_EINVAL, "null argument");
     ON_DEVICE(s->device);
     if (len) {
+    s->fresh = false;
         if (!s->stream_open) {
             uint8_t first[2] = {0, 0};
             CU(cudaMemcpy(first, dev, std::min<size_t>(2, len), cudaMemcpyDeviceToHost));
@@ -1455,6 +1471,7 @@ int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32
                              const uint8_t *tail_syms /* halo symbols, may be null = all breaks */, uint64_t raw_base,
                              uint64_t ord_base, int strip /* FASTQ range at a record start: frame the records on the host */) {
     if (!s || s->stream_open) return fb2_fail(FB2_EINVAL, "begin_range: bad handle state");
+    s->fresh = false;
     ON_DEVICE(s->device);
     s->format = format;
     TRY(flush_all(s));
@@ -1959,6 +1976,120 @@ extern "C" int fb2_sketcher_debug_bump(fb2_sketcher *s, uint64_t hash, uint64_t 
     TRY(pull_state(s));
     if (!s->h_state->gather_count) return fb2_fail(FB2_EINVAL, "hash not in the table");
     return FB2_OK;
+}
+
+// ---- a whole small stream in one go ---------------------------------------------------------------------------------
+// sketch_stream (lib.rs:51-94) of a stream that fits ONE chunk, on an untouched handle, when the filters resolve to off
+// (a FASTA file with the command line's defaults: the heap is final_size then): the general path would walk
+// through ~24 host round trips (state pulls between the steps of the first-chunk ramp, the prune, the sort) for 0.2 ms
+// of kernels.  Here everything up to the gathered keys is queued without looking:
+//     H2D | parse | hash under the provisional threshold | guarded absorb | gather         -> pull A
+//     bucket sort | select                                                                 -> pull B
+//     export | rows | D2H                                                                  -> done
+// The provisional threshold T0 = 16 s 2^64 / len is hash_range's (there with the chunk's symbol count N <= len, so
+// this one is a little lower) and valid under the same condition, checked at pull A: at least s distinct keys lie at
+// or below it.  Returns 1 when the stream is not of that kind or anything unusual shows up (candidates past the log,
+// non-uniform keys, a threshold that turned out too low): the caller then resets the handle and takes the general path,
+// which decides.
+int fb2_sketcher_sketch_small(fb2_sketcher *s, const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
+                              const fb2_filter *f, fb2_result *out) {
+    if (!s || !bytes || !p || !f || !out) return 1;
+    if (!s->fresh || s->allcounts || s->scaled || s->k > 32 || s->stream_open || getenv("FB2_NO_SMALL_PATH")) return 1;
+    if (len < (64u << 10) || len > s->chunk_bytes || len >= (1ull << 31)) return 1;
+    const uint8_t c0 = bytes[0];
+    if (c0 != '>' && c0 != '@') return 1;
+    const int format = c0 == '>' ? FB2_FORMAT_FASTA : FB2_FORMAT_FASTQ;
+    if (format == FB2_FORMAT_FASTQ && getenv("FB2_HOST_STRIP") && *getenv("FB2_HOST_STRIP") == '1') return 1;
+    const int filter_on = f->filter_on >= 0 ? f->filter_on : (format == FB2_FORMAT_FASTQ ? 1 : 0);   // lib.rs:71-76
+    if (filter_on != 0 || p->kind != FB2_KIND_MASH) return 1;
+    ON_DEVICE(s->device);
+    memset(out, 0, sizeof(*out));
+    s->fresh = false;
+    s->format = format;
+    apply_finish_hint(s);                       // heap = final_size when the caller said so (fb2_sketcher_hint_finish)
+    const uint64_t size = s->size, want = 16ull * size;
+    if (size == 0 || want + want / 8 > s->log_cap / 2 || len < 16 * want) return 1;
+    if ((uint64_t)s->tab[s->cur].cap / 4 * 3 < 2 * want) return 1;   // room for every candidate as a new key
+    // begin_stream's carry, the provisional threshold
+    ParseCarry *c = s->h_carry;
+    c->state = format == FB2_FORMAT_FASTA ? 1u : 0u;
+    c->prev1 = c->prev2 = '\n';
+    c->raw_total = 0; c->n_records = 0; c->first_bad_pos = ~0ULL; c->last_sig = 0; c->error = 0; c->len_bad_pos = ~0ULL;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 3; ++b) c->last_nl[a][b] = NL_NONE;
+    s->h_state->threshold = (~0ULL / (unsigned long long)len) * want;
+    CU(cudaMemcpyAsync(s->d_carry.p, c, sizeof(ParseCarry), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_state.p, s->h_state, sizeof(SketchState), cudaMemcpyHostToDevice, s->st));
+    s->stream_open = true; s->range_mode = false; s->strip_on = false;
+    s->tail_host.clear();
+    note_tail(s, bytes, len);
+    // the bytes
+    const size_t bufsz = (len + 4095) / 4096 * 4096 + 64;
+    TRY(s->d_raw[0].ensure(bufsz));
+    CU(cudaMemcpyAsync(s->d_raw[0].p, bytes, len, cudaMemcpyHostToDevice, s->st));
+    s->stats.h2d_bytes += len + sizeof(ParseCarry) + sizeof(SketchState);
+    // parse (run_chunk stops after the parse kernels), hash, absorb, gather
+    s->small_mode = true;
+    const int rcp = run_chunk(s, s->d_raw[0].as<uint8_t>(), (uint32_t)len, format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ, -1);
+    s->small_mode = false;
+    if (rcp != FB2_OK) return rcp;
+    const int par = s->small_par;
+    const ChunkGeom g = s->last_geom;
+    SketchState *dst = (SketchState *)s->d_state.p;
+    ParseCarry *dc = (ParseCarry *)s->d_carry.p;
+    LaunchSlot *slot = dev_slot(s, par);
+    CU(cudaMemsetAsync(slot, 0, sizeof(LaunchSlot), s->st));
+    launch_hash(s->k, s->d_sym[par].as<uint8_t>(), g, 0, g.n_st, s->d_rcount[par].as<uint32_t>(), dc, s->small_ord, dst, slot,
+                log_view(s, par), s->prm.hash_seed, 31u, piece_plan(s, par), s->st);
+    launch_absorb_guarded(log_view(s, par), slot, s->tab[s->cur].view(), dst, dc, (uint32_t)want, s->st);
+    const uint32_t occ_ub = s->tab[s->cur].cap + 1;
+    TRY(ensure_sort(s, occ_ub));
+    TRY(s->d_bins.ensure(3 * 4096 * sizeof(uint32_t)));
+    unsigned long long *keys = s->sort_keys.as<unsigned long long>(), *tkeys = s->sort_tkeys.as<unsigned long long>();
+    uint32_t *slots = s->sort_slots.as<uint32_t>(), *tslots = s->sort_tslots.as<uint32_t>();
+    launch_gather(s->tab[s->cur].view(), dst, tkeys, tslots, s->st);
+    s->stats.kernel_launches += 6; s->stats.hash_launches++;
+    TRY(pull_state(s));                                                                           // ---- pull A
+    const LaunchSlot &sl = s->h_state->slot[par];
+    s->stats.hash_symbols += s->h_carry->chunk_syms;
+    const uint64_t have = (uint64_t)s->h_state->occupied + (s->h_state->has_max_key ? 1u : 0u);
+    if (sl.decision != DECIDE_GO || sl.log_count > s->log_cap || have < size) return 1;
+    s->total_kmers += sl.launch_kmers;
+    s->stream_open = false;
+    {
+        const int rcv = stream_verdict(s);       // the reader's end-of-input rules (and the last record's length)
+        if (rcv != FB2_OK) return rcv;
+        // (the verdict may have corrected the carry's totals: the device copy follows, like end_stream's push)
+        s->h_carry->state = 0; s->h_carry->prev1 = s->h_carry->prev2 = '\n';
+        CU(cudaMemcpyAsync(s->d_carry.p, s->h_carry, sizeof(ParseCarry), cudaMemcpyHostToDevice, s->st));
+    }
+    const uint32_t n = s->h_state->gather_count;
+    const unsigned long long thr = s->h_state->threshold;
+    if (n < 2) return 1;
+    const uint32_t shift = shift_for_threshold(thr);
+    uint32_t *bins = s->d_bins.as<uint32_t>();
+    launch_bucket_sort(tkeys, tslots, keys, slots, tkeys, tslots, n, shift, bins, bins + 4096, bins + 8192, dst, s->st);
+    CU(cudaMemcpyAsync(keys, tkeys, (size_t)n * 8, cudaMemcpyDeviceToDevice, s->st));
+    CU(cudaMemcpyAsync(slots, tslots, (size_t)n * 4, cudaMemcpyDeviceToDevice, s->st));
+    launch_select_keep(keys, n, 0, s->size, s->max_hash, dst, s->st);
+    s->stats.kernel_launches += 5;
+    TRY(pull_state(s));                                                                           // ---- pull B
+    if (s->h_state->gather_count > bucket_cap()) return 1;      // keys too uneven for the bucket sort: the general path sorts by radix
+    const uint32_t keep = s->h_state->keep_count;
+    if (keep) {
+        TRY(s->out_hash.ensure((size_t)keep * 8)); TRY(s->out_kmer.ensure((size_t)keep * 8 * s->kw));
+        TRY(s->out_posx.ensure((size_t)keep * 8));
+        TRY(s->out_cnt.ensure((size_t)keep * 4)); TRY(s->out_ext.ensure((size_t)keep * 4));
+        launch_export(keys, slots, keep, s->tab[s->cur].view(), s->out_hash.as<unsigned long long>(), s->out_cnt.as<uint32_t>(),
+                      s->out_ext.as<uint32_t>(), s->out_kmer.as<unsigned long long>(), s->out_posx.as<unsigned long long>(), s->st);
+        s->stats.kernel_launches++;
+    }
+    uint32_t m = keep;
+    if (m > p->final_size) m = (uint32_t)p->final_size;      // process_post_filter (mod.rs:115-128)
+    if (!p->no_strict && m < p->final_size)
+        return fb2_fail(FB2_ETOOFEW, std::string(name ? name : "") + " had too few kmers (" + std::to_string(m) + ") to sketch");
+    const int rc = collect_rows(s, nullptr, m, out);
+    if (rc == FB2_OK) { fb2_filter ff = *f; ff.filter_on = 0; out->filters = ff; }
+    return rc;
 }
 
 extern "C" int fb2_sketcher_stats(fb2_sketcher *s, fb2_stats *out) {

@@ -40,6 +40,8 @@ int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32
 int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_byte, uint64_t *first_bad_pos, uint64_t *len_bad_pos);
 uint32_t fb2_sketcher_halo(const fb2_sketcher *s);
 void fb2_sketcher_set_polite_copy(fb2_sketcher *s, unsigned piece_mb);
+int fb2_sketcher_sketch_small(fb2_sketcher *s, const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
+                              const fb2_filter *f, fb2_result *out);
 void fb2_sketcher_set_link_flag(fb2_sketcher *s, std::atomic<int> *flag, int owner);
 int fb2_sketcher_merge_from(fb2_sketcher *dst, fb2_sketcher *src);
 size_t fb2_sketcher_device_bytes(const fb2_sketcher *s);
@@ -241,8 +243,18 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
     memset(&st0, 0, sizeof(st0)); memset(&st1, 0, sizeof(st1));
     if (rc == FB2_OK) fb2_sketcher_stats(s, &st0);
     if (rc == FB2_OK && p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
-    if (rc == FB2_OK) rc = fb2_sketcher_feed_fastx(s, bytes, len, 1);
-    if (rc == FB2_OK) rc = finish_sketch(s, name, p, f, out);
+    bool done = false;
+    if (rc == FB2_OK) {   // a small stream in one go (engine.cu); 1 = not that kind of stream, or it wants the general path
+        const int rs = fb2_sketcher_sketch_small(s, bytes, len, name, p, f, out);
+        if (rs == 1) {
+            fb2_result_free(out);
+            memset(out, 0, sizeof(*out));
+            rc = fb2_sketcher_reset(s);
+            if (rc == FB2_OK && p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
+        } else { rc = rs; done = true; }
+    }
+    if (rc == FB2_OK && !done) rc = fb2_sketcher_feed_fastx(s, bytes, len, 1);
+    if (rc == FB2_OK && !done) rc = finish_sketch(s, name, p, f, out);
     if (rc == FB2_OK) {
         fb2_sketcher_stats(s, &st1);
         memset(&g_last_stream_stats, 0, sizeof(g_last_stream_stats));
@@ -479,12 +491,28 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
     } else {
         size_t fill = nmagic;
         if (nmagic) memcpy(buf, magic, nmagic);
+        bool first = true;
         while (rc == FB2_OK) {
             t0 = now_ns();
             const size_t got = fread(buf + fill, 1, piece - fill, fp) + fill;
             const uint64_t t1 = now_ns();
             g_ns_read += t1 - t0;
             fill = 0;
+            if (first && got && got < piece) {   // the whole file is here: the small-stream path (engine.cu), if it applies
+                const int rs = fb2_sketcher_sketch_small(s, buf, got, path, p, f, out);
+                if (rs != 1) {
+                    g_ns_feed += now_ns() - t1;
+                    if (!is_stdin) fclose(fp);
+                    g_n_files += 1;
+                    return rs;
+                }
+                fb2_result_free(out);
+                memset(out, 0, sizeof(*out));
+                rc = fb2_sketcher_reset(s);
+                if (rc == FB2_OK && p->kind == FB2_KIND_MASH) fb2_sketcher_hint_finish(s, p->final_size, f->filter_on);
+                if (rc != FB2_OK) break;
+            }
+            first = false;
             if (got) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, got, 0); }
             g_ns_feed += now_ns() - t1;
             if (got < piece) break;

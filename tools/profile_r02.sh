@@ -7,6 +7,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
     python tools/c2_once.py $R > gpurun_out/r02_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:hash_kernel -s 30 -c 2 -f -o gpurun_out/r02_ncu_hash \
     python tools/c2_once.py $R > gpurun_out/r02_ncu_hash.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:pack_kernel -s 30 -c 2 -f -o gpurun_out/r02_ncu_pack \
+ncu --set full --clock-control none --import-source on -k regex:"pack_kernel|parse_fused" -s 30 -c 2 -f -o gpurun_out/r02_ncu_pack \
     python tools/c2_once.py $R > gpurun_out/r02_ncu_pack.log 2>&1
 ls -la gpurun_out/*.ncu-rep
