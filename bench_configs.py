@@ -59,6 +59,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="reduced sizes (no digests exist for those: bit_exact null)")
     ap.add_argument("--out", default="")
     ap.add_argument("--max-dist", type=float, default=0.05)
+    ap.add_argument("--c3-workers", default="4,8,16", help="worker handles per GPU to try for C3")
+    ap.add_argument("--c3-files", type=int, default=0, help="C3 with the first N of its 1024 files (digests exist for all)")
     args = ap.parse_args()
     only = args.only.split(",")
     import torch
@@ -90,7 +92,7 @@ def main():
 
     # ---- C3 ------------------------------------------------------------------------------------------------
     if "c3" in only:
-        nfiles = 64 if args.quick else W.C3_FILES
+        nfiles = 64 if args.quick else (args.c3_files or W.C3_FILES)
         tdir = tempfile.mkdtemp(prefix="fb2c3_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
             paths = [os.path.join(tdir, f"g{i:04d}.fa") for i in range(nfiles)]
@@ -104,9 +106,12 @@ def main():
             [t.start() for t in ths]
             [t.join() for t in ths]
             total_bases = sum(W.c3_nbases(i) for i in range(nfiles))
-            for workers in ((8,) if args.quick else (4, 8, 16)):
+            for workers in ((8,) if args.quick else tuple(int(x) for x in args.c3_workers.split(","))):
                 os.environ["FB2_FILE_WORKERS"] = str(workers)
-                fb.sketch_files(paths[:8 * G], sp_cli, fp_auto, ngpus=G)          # warm-up: handles, page cache
+                # warm-up: every worker's handle exists (a worker creates its handle before it takes a file, so the call needs
+                # at least `workers` files per GPU), page cache.  Creating handles is the expensive part of a FIRST call:
+                # tools/c3_trace.py, tools/alloc_cost.cu
+                fb.sketch_files(paths[:min(nfiles, 4 * workers * G)], sp_cli, fp_auto, ngpus=G)
                 t0 = time.perf_counter()
                 sks = fb.sketch_files(paths, sp_cli, fp_auto, ngpus=G)
                 dt = time.perf_counter() - t0

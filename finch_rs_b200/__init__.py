@@ -66,6 +66,14 @@ class _Stats(C.Structure):
                 ("hash_symbols", C.c_uint64), ("provisional_redos", C.c_uint64), ("band_passes", C.c_uint64)]
 
 
+class _SketchView(C.Structure):
+    """fb2_sketch_view: one `Sketch` (serialization/mod.rs:45-55) of a sketch file as plain arrays"""
+    _fields_ = [("name", C.c_char_p), ("comment", C.c_char_p), ("seq_length", C.c_uint64), ("num_valid_kmers", C.c_uint64),
+                ("params", _Params), ("filter", _Filter), ("n", C.c_uint64), ("hashes", C.POINTER(C.c_uint64)),
+                ("counts", C.POINTER(C.c_uint32)), ("extras", C.POINTER(C.c_uint32)), ("kmers", C.POINTER(C.c_uint8)),
+                ("kmer_offs", C.POINTER(C.c_uint64))]
+
+
 class _PairOut(C.Structure):
     _fields_ = [("common", C.c_uint32), ("i", C.c_uint32), ("j", C.c_uint32)]
 
@@ -78,6 +86,8 @@ EXPORTS = [
     "fb2_guess_filter_threshold", "fb2_sketch_stream", "fb2_sketch_files", "fb2_sketch_files_multi", "fb2_sketch_stream_multi",
     "fb2_sketch_files_release_pool", "fb2_dist_batch", "fb2_minmer_matrix",
     "fb2_dist_all_pairs", "fb2_dist_all_pairs_cut", "fb2_dist_last_kernel_ms", "fb2_distance_finish", "fb2_old_distance_finish", "fb2_last_error", "fb2_device_count", "fb2_version",
+    "fb2_sketch_set_new", "fb2_sketch_set_open", "fb2_sketch_set_len", "fb2_sketch_set_get", "fb2_sketch_set_add", "fb2_sketch_set_remove",
+    "fb2_sketch_set_save", "fb2_sketch_set_close",
 ]
 
 _lib = None
@@ -134,6 +144,16 @@ def lib():
     L.fb2_dist_last_kernel_ms.restype = C.c_double
     L.fb2_last_error.restype = C.c_char_p
     L.fb2_version.restype = C.c_char_p
+    L.fb2_sketch_set_new.argtypes = [C.POINTER(vp)]
+    L.fb2_sketch_set_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.fb2_sketch_set_len.argtypes = [vp]
+    L.fb2_sketch_set_len.restype = C.c_uint64
+    L.fb2_sketch_set_get.argtypes = [vp, C.c_uint64, C.POINTER(_SketchView)]
+    L.fb2_sketch_set_add.argtypes = [vp, C.POINTER(_SketchView)]
+    L.fb2_sketch_set_remove.argtypes = [vp, C.c_uint64]
+    L.fb2_sketch_set_save.argtypes = [vp, C.c_char_p, C.c_int]
+    L.fb2_sketch_set_close.argtypes = [vp]
+    L.fb2_sketch_set_close.restype = None
     _lib = L
     atexit.register(L.fb2_sketch_files_release_pool)   # idle worker handles of sketch_files (bounded, see finch_b200.h)
     return L

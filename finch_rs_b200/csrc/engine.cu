@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -157,6 +158,7 @@ struct fb2_sketcher {
     size_t h_res_cap = 0;
     DevBuf d_push_bytes, d_push_offs, d_push_extra;
 
+    uint8_t *h_pinned = nullptr;    // one pinned allocation holding the mirrors below and h_snap[]
     ParseCarry *h_carry = nullptr;  // pinned mirrors
     SketchState *h_state = nullptr;
 
@@ -173,6 +175,7 @@ struct fb2_sketcher {
     bool stream_open = false;        // a FASTX stream has begun and not yet seen `final`
     // FB2_HOST_STRIP=1: FASTQ record framing on the host, only the sequence lines cross PCIe (strip.cpp)
     bool strip_on = false;               // active for the open stream
+    bool polite = false;                 // waits yield / sleep instead of spinning (fb2_sketcher_set_polite_sync)
     unsigned polite_copy = 0;            // > 0: raw host-to-device copies go in pieces of that many MiB, one in flight (see feed_host_chunks)
     std::atomic<int> *link_flag = nullptr;   // two-ended streams: copies of the host-framed handle in flight (it raises the flag,
     bool link_owner = false;                 // the raw handle waits for zero before every piece: the framed lines go first)
@@ -200,6 +203,27 @@ struct fb2_sketcher {
     std::vector<EvPair> ev_free, ev_hash_pending, ev_parse_pending;
 };
 
+// Host waits.  A worker thread normally spins in cudaStreamSynchronize (lowest latency); when fb2_sketch_files runs more
+// worker threads than the host has cores (FB2_FILE_WORKERS, many GPUs on few cores) a spinning wait takes the core a
+// sibling needs for its file read, and throughput collapsed (8 GPUs x 16 workers on 32 cores: 10x slower than x 4).
+// `polite` handles poll a few times and then sleep between polls.
+static cudaError_t polite_wait(const std::function<cudaError_t()> &query) {
+    for (int n = 0;; ++n) {
+        const cudaError_t e = query();
+        if (e != cudaErrorNotReady) return e;
+        if (n < 16) std::this_thread::yield();
+        else std::this_thread::sleep_for(std::chrono::microseconds(n < 64 ? 20 : 100));
+    }
+}
+static cudaError_t wait_stream(const fb2_sketcher *s, cudaStream_t st) {
+    if (!s->polite) return cudaStreamSynchronize(st);
+    return polite_wait([st] { return cudaStreamQuery(st); });
+}
+static cudaError_t wait_event(const fb2_sketcher *s, cudaEvent_t ev) {
+    if (!s->polite) return cudaEventSynchronize(ev);
+    return polite_wait([ev] { return cudaEventQuery(ev); });
+}
+
 static bool timing_begin(fb2_sketcher *s, fb2_sketcher::EvPair &p) {
     if (!s->timing) return false;
     if (!s->ev_free.empty()) { p = s->ev_free.back(); s->ev_free.pop_back(); }
@@ -213,7 +237,7 @@ static void timing_end(fb2_sketcher *s, fb2_sketcher::EvPair &p, std::vector<fb2
 }
 static void timing_resolve(fb2_sketcher *s) {
     if (s->ev_hash_pending.empty() && s->ev_parse_pending.empty()) return;
-    cudaStreamSynchronize(s->st);
+    wait_stream(s, s->st);
     for (auto &p : s->ev_hash_pending) { float ms = 0; if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) s->stats.hash_kernel_ms += ms; s->ev_free.push_back(p); }
     for (auto &p : s->ev_parse_pending) { float ms = 0; if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) s->stats.parse_kernel_ms += ms; s->ev_free.push_back(p); }
     s->ev_hash_pending.clear(); s->ev_parse_pending.clear();
@@ -239,18 +263,18 @@ static int pull_state(fb2_sketcher *s) {  // device -> pinned mirrors, then wait
     TRY(join_absorb_stream(s));           // every host decision starts here: the table must be quiescent
     CU(cudaMemcpyAsync(s->h_state, s->d_state.p, sizeof(SketchState), cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(s->h_carry, s->d_carry.p, sizeof(ParseCarry), cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));
+    CU(wait_stream(s, s->st));
     s->stats.d2h_bytes += sizeof(SketchState) + sizeof(ParseCarry);
     return FB2_OK;
 }
 static int push_carry(fb2_sketcher *s) {
     CU(cudaMemcpyAsync(s->d_carry.p, s->h_carry, sizeof(ParseCarry), cudaMemcpyHostToDevice, s->st));
-    CU(cudaStreamSynchronize(s->st));
+    CU(wait_stream(s, s->st));
     return FB2_OK;
 }
 static int push_state(fb2_sketcher *s) {
     CU(cudaMemcpyAsync(s->d_state.p, s->h_state, sizeof(SketchState), cudaMemcpyHostToDevice, s->st));
-    CU(cudaStreamSynchronize(s->st));
+    CU(wait_stream(s, s->st));
     return FB2_OK;
 }
 
@@ -330,7 +354,7 @@ static int reset_sketch_state(fb2_sketcher *s) {
     launch_table_clear(s->tab[s->cur].view(), s->st);
     launch_fill_bytes(s->d_tail.as<uint8_t>(), 2 * HALO_BIG, SYM_BREAK, s->st);
     s->stats.kernel_launches += 2;
-    CU(cudaStreamSynchronize(s->st));
+    CU(wait_stream(s, s->st));
     s->tail_sel = 0; s->ordinal = 0; s->par = 0; s->steady = false;
     s->pend[0].valid = s->pend[1].valid = false;
     s->format = FB2_FORMAT_UNKNOWN; s->stream_open = false;
@@ -400,16 +424,18 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
         if ((rc = s->d_carry.ensure(sizeof(ParseCarry))) != FB2_OK) break;
         if ((rc = s->d_state.ensure(sizeof(SketchState))) != FB2_OK) break;
         if ((rc = s->d_tail.ensure(2 * HALO_BIG)) != FB2_OK) break;
-        if (cudaHostAlloc((void **)&s->h_carry, sizeof(ParseCarry), cudaHostAllocDefault) != cudaSuccess ||
-            cudaHostAlloc((void **)&s->h_state, sizeof(SketchState), cudaHostAllocDefault) != cudaSuccess) {
-            rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed"); break;
-        }
-        for (int i = 0; i < 2 && rc == FB2_OK; ++i) {
-            if (cudaHostAlloc((void **)&s->h_snap[i], sizeof(SketchState), cudaHostAllocDefault) != cudaSuccess ||
-                cudaEventCreateWithFlags(&s->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) {
-                rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc/cudaEventCreate failed");
+        {   // the pinned mirrors in ONE allocation (pinning calls are serialised by the driver and queue behind each
+            // other when sketch_files starts its workers: tools/alloc_cost.cu)
+            const size_t a_carry = (sizeof(ParseCarry) + 255) & ~(size_t)255, a_state = (sizeof(SketchState) + 255) & ~(size_t)255;
+            if (cudaHostAlloc((void **)&s->h_pinned, a_carry + 3 * a_state, cudaHostAllocDefault) != cudaSuccess) {
+                rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed"); break;
             }
+            s->h_carry = reinterpret_cast<ParseCarry *>(s->h_pinned);
+            s->h_state = reinterpret_cast<SketchState *>(s->h_pinned + a_carry);
+            for (int i = 0; i < 2; ++i) s->h_snap[i] = reinterpret_cast<SketchState *>(s->h_pinned + a_carry + (size_t)(1 + i) * a_state);
         }
+        for (int i = 0; i < 2 && rc == FB2_OK; ++i)
+            if (cudaEventCreateWithFlags(&s->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) rc = fb2_fail(FB2_ECUDA, "cudaEventCreate failed");
         if (rc != FB2_OK) break;
         // 4 slots per kept key (FB2_TABLE_MULT: A/B switch; 8 measured no faster on the C2 workload)
         uint64_t want = s->size ? env_size("FB2_TABLE_MULT", 4) * s->size : 1;
@@ -428,9 +454,9 @@ extern "C" int fb2_sketcher_create(const fb2_params *p, fb2_sketcher **out) {
 extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     if (!s) return;
     DeviceScope dev_scope_(s->device);
-    if (s->st) cudaStreamSynchronize(s->st);
-    if (s->copy_st) cudaStreamSynchronize(s->copy_st);
-    if (s->st2) cudaStreamSynchronize(s->st2);
+    if (s->st) wait_stream(s, s->st);
+    if (s->copy_st) wait_stream(s, s->copy_st);
+    if (s->st2) wait_stream(s, s->st2);
     for (int i = 0; i < 2; ++i) {
         s->d_raw[i].release(); s->tab[i].release();
         if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
@@ -440,7 +466,6 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     for (auto &p : s->ev_free) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int i = 0; i < 2; ++i) {
         s->d_sym[i].release(); s->d_rcount[i].release(); s->d_ptab[i].release(); s->d_pcount[i].release(); s->log_hash[i].release(); s->log_kmer[i].release(); s->log_posx[i].release();
-        if (s->h_snap[i]) cudaFreeHost(s->h_snap[i]);
         if (s->ev_chunk[i]) cudaEventDestroy(s->ev_chunk[i]);
     }
     s->d_stmap.release(); s->d_ststate.release(); s->d_tail.release(); s->d_seam.release(); s->d_ticket.release(); s->d_fhist.release(); s->d_fok.release(); s->d_ac.release(); s->d_ac_off.release(); s->d_ac_meta.release();
@@ -451,8 +476,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     s->sel_bytes.release(); s->sel_idx.release();
     if (s->h_res) cudaFreeHost(s->h_res);
     s->d_push_bytes.release(); s->d_push_offs.release(); s->d_push_extra.release();
-    if (s->h_carry) cudaFreeHost(s->h_carry);
-    if (s->h_state) cudaFreeHost(s->h_state);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);   // h_carry, h_state, h_snap[]
     if (s->h_stage) cudaFreeHost(s->h_stage);
     for (int i = 0; i < 2; ++i) { if (s->strip_pin[i]) cudaFreeHost(s->strip_pin[i]); if (s->ev_strip_free[i]) cudaEventDestroy(s->ev_strip_free[i]); }
     if (s->own_stream && s->st) cudaStreamDestroy(s->st);
@@ -466,9 +490,9 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
 extern "C" int fb2_sketcher_reset(fb2_sketcher *s) {
     if (!s) return fb2_fail(FB2_EINVAL, "null handle");
     ON_DEVICE(s->device);
-    CU(cudaStreamSynchronize(s->st));
-    CU(cudaStreamSynchronize(s->copy_st));
-    CU(cudaStreamSynchronize(s->st2));
+    CU(wait_stream(s, s->st));
+    CU(wait_stream(s, s->copy_st));
+    CU(wait_stream(s, s->st2));
     s->st2_dirty = false;
     return reset_sketch_state(s);
 }
@@ -585,7 +609,7 @@ static int absorb_log_banded(fb2_sketcher *s, int par, uint32_t cnt, bool *done)
     s->stats.kernel_launches++;
     std::vector<uint32_t> bins(4096);
     CU(cudaMemcpyAsync(bins.data(), s->d_bins.p, 4096 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));
+    CU(wait_stream(s, s->st));
     s->stats.d2h_bytes += 4096 * sizeof(uint32_t);
     std::vector<uint64_t> cum(4096);
     uint64_t run = 0;
@@ -801,7 +825,7 @@ static int hash_range(fb2_sketcher *s, const ChunkGeom &g, uint64_t ord_base, in
 static int settle(fb2_sketcher *s, int q) {
     if (!s->pend[q].valid) return FB2_OK;
     s->pend[q].valid = false;
-    CU(cudaEventSynchronize(s->ev_chunk[q]));
+    CU(wait_event(s, s->ev_chunk[q]));
     const SketchState snap = *s->h_snap[q];
     const LaunchSlot sl = snap.slot[q];
     const ChunkGeom g = s->pend[q].g;
@@ -956,7 +980,7 @@ static int feed_host_chunks(fb2_sketcher *s, const uint8_t *bytes, size_t len, i
                     while (s->link_flag->load(std::memory_order_acquire) > 0) std::this_thread::sleep_for(std::chrono::microseconds(20));
                 CU(cudaMemcpyAsync(s->d_raw[b].as<uint8_t>() + q, bytes + off + q, m, cudaMemcpyHostToDevice, s->copy_st));
                 CU(cudaEventRecord(s->ev_h2d[b], s->copy_st));
-                if (q + m < n) CU(cudaEventSynchronize(s->ev_h2d[b]));
+                if (q + m < n) CU(wait_event(s, s->ev_h2d[b]));
             }
         } else {
             CU(cudaMemcpyAsync(s->d_raw[b].p, bytes + off, n, cudaMemcpyHostToDevice, s->copy_st));
@@ -985,7 +1009,7 @@ static int flush_stage(fb2_sketcher *s) {
     s->stage_fill = 0;
     TRY(feed_host_chunks(s, s->h_stage, n, mode));
     // the staging buffer is reused right away: wait for its H2D copies
-    CU(cudaStreamSynchronize(s->copy_st));
+    CU(wait_stream(s, s->copy_st));
     return FB2_OK;
 }
 static int ensure_stage(fb2_sketcher *s) {
@@ -1186,7 +1210,7 @@ static int feed_fastq_stripped(fb2_sketcher *s, const uint8_t *bytes, size_t len
             while (p < end) {
                 const uint8_t *blk_end = (size_t)(end - p) > block ? p + block : end;
                 const int set = s->strip_set;
-                if (s->strip_free_pending[set]) { CU(cudaEventSynchronize(s->ev_strip_free[set])); s->strip_free_pending[set] = false; }
+                if (s->strip_free_pending[set]) { CU(wait_event(s, s->ev_strip_free[set])); s->strip_free_pending[set] = false; }
                 for (unsigned t = 0; t < T; ++t) {
                     outs[t] = StripOut();
                     outs[t].out = s->strip_pin[set] + (size_t)t * s->strip_pin_each;
@@ -1205,7 +1229,7 @@ static int feed_fastq_stripped(fb2_sketcher *s, const uint8_t *bytes, size_t len
                         if (!o.out_len) continue;
                         CU(cudaMemcpyAsync(s->d_raw[b].as<uint8_t>() + at, o.data(), o.out_len, cudaMemcpyHostToDevice, s->copy_st));
                         at += o.out_len;
-                        if (o.spilled) CU(cudaStreamSynchronize(s->copy_st));   // pageable source: gone after this iteration
+                        if (o.spilled) CU(wait_stream(s, s->copy_st));   // pageable source: gone after this iteration
                     }
                     CU(cudaEventRecord(s->ev_h2d[b], s->copy_st));
                     if (s->link_flag && s->link_owner) {   // lowered by the driver when these copies are through
@@ -1382,7 +1406,7 @@ extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, si
         const int mode = s->format == FB2_FORMAT_FASTA ? MODE_FASTA : MODE_FASTQ;
         if (s->strip_on) {
             TRY(feed_fastq_stripped(s, bytes, len, final));
-            if (len >= (1u << 20) && !s->range_mode) CU(cudaStreamSynchronize(s->copy_st));   // (staging sets are ours; the caller's bytes were only read by the CPU)
+            if (len >= (1u << 20) && !s->range_mode) CU(wait_stream(s, s->copy_st));   // (staging sets are ours; the caller's bytes were only read by the CPU)
             return FB2_OK;
         }
         note_tail(s, bytes, len);
@@ -1399,7 +1423,7 @@ extern "C" int fb2_sketcher_feed_fastx(fb2_sketcher *s, const uint8_t *bytes, si
         } else {
             TRY(flush_stage(s));
             TRY(feed_host_chunks(s, bytes, len, mode));
-            CU(cudaStreamSynchronize(s->copy_st));  // caller may reuse `bytes` after we return
+            CU(wait_stream(s, s->copy_st));  // caller may reuse `bytes` after we return
         }
     }
     if (final) {
@@ -1438,12 +1462,12 @@ extern "C" int fb2_sketcher_feed_device(fb2_sketcher *s, const uint8_t *dev, siz
                 TRY(s->d_raw[0].ensure(n + 64));
                 CU(cudaMemcpyAsync(s->d_raw[0].p, dev + off, n, cudaMemcpyDeviceToDevice, s->st));
                 TRY(run_chunk(s, s->d_raw[0].as<uint8_t>(), (uint32_t)n, mode, -1));
-                CU(cudaStreamSynchronize(s->st));   // d_raw[0] is reused by the next piece
+                CU(wait_stream(s, s->st));   // d_raw[0] is reused by the next piece
             }
         }
         if (aligned) {  // the caller may release `dev` after we return: the parse kernels must be done
             CU(cudaEventRecord(s->ev_rawfree[0], s->st));
-            CU(cudaEventSynchronize(s->ev_rawfree[0]));
+            CU(wait_event(s, s->ev_rawfree[0]));
         }
     }
     if (final) {
@@ -1485,7 +1509,7 @@ int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32
     TRY(push_carry(s));
     if (tail_syms) {
         CU(cudaMemcpyAsync(s->d_tail.as<uint8_t>() + s->halo * s->tail_sel, tail_syms, s->halo, cudaMemcpyHostToDevice, s->st));
-        CU(cudaStreamSynchronize(s->st));
+        CU(wait_stream(s, s->st));
     }
     s->ordinal = ord_base;
     s->stream_open = true;
@@ -1533,6 +1557,7 @@ int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_
     return FB2_OK;
 }
 void fb2_sketcher_set_polite_copy(fb2_sketcher *s, unsigned piece_mb) { if (s) s->polite_copy = piece_mb; }
+void fb2_sketcher_set_polite_sync(fb2_sketcher *s, int on) { if (s) s->polite = on != 0; }
 void fb2_sketcher_set_link_flag(fb2_sketcher *s, std::atomic<int> *flag, int owner) { if (s) { s->link_flag = flag; s->link_owner = owner != 0; } }
 uint32_t fb2_sketcher_halo(const fb2_sketcher *s) { return s->halo; }
 int fb2_sketcher_device(const fb2_sketcher *s) { return s->device; }
@@ -1636,7 +1661,7 @@ static int allcounts_result(fb2_sketcher *s, fb2_result *out, uint64_t *sum_out)
     s->stats.kernel_launches += 2;
     TRY(ensure_hres(s, 16));
     CU(cudaMemcpyAsync(s->h_res, s->d_ac_meta.p, 16, cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));
+    CU(wait_stream(s, s->st));
     const uint64_t m = ((uint64_t *)s->h_res)[0], sum = ((uint64_t *)s->h_res)[1];
     if (sum_out) *sum_out = sum;
     if (!out) return FB2_OK;
@@ -1659,7 +1684,7 @@ static int allcounts_result(fb2_sketcher *s, fb2_result *out, uint64_t *sum_out)
         CU(cudaMemcpyAsync(out->counts, s->out_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(out->extras, s->out_ext.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(out->kmers, s->sel_bytes.p, (size_t)m * k, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaStreamSynchronize(s->st));
+        CU(wait_stream(s, s->st));
         s->stats.d2h_bytes += (size_t)m * (16 + k);
     }
     out->seq_length = 0;                 // counts.rs never adds to total_bases
@@ -1717,7 +1742,7 @@ static int ensure_hres(fb2_sketcher *s, size_t bytes) {
     if (bytes <= s->h_res_cap) return FB2_OK;
     if (s->h_res) cudaFreeHost(s->h_res);
     s->h_res = nullptr; s->h_res_cap = 0;
-    const size_t want = bytes + bytes / 4 + 4096;
+    const size_t want = std::max<size_t>(bytes + bytes / 4 + 4096, 256u << 10);   // (one allocation serves a usual sketch: pinning calls are slow)
     CU(cudaHostAlloc((void **)&s->h_res, want, cudaHostAllocDefault));
     s->h_res_cap = want;
     return FB2_OK;
@@ -1783,7 +1808,7 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
             CU(cudaMemcpyAsync(s->h_res + o_kmer, s->sel_kmer.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
             CU(cudaMemcpyAsync(s->h_res + o_posx, s->sel_posx.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
         }
-        CU(cudaStreamSynchronize(s->st));
+        CU(wait_stream(s, s->st));
         s->stats.d2h_bytes += total;
         parallel_memcpy(out->hashes, s->h_res + o_hash, (size_t)m * 8);
         parallel_memcpy(out->counts, s->h_res + o_cnt, (size_t)m * 4);
@@ -1891,13 +1916,13 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
             uint32_t *h_meta = (uint32_t *)s->h_res, *h_hist = h_meta + 4;
             CU(cudaMemcpyAsync(h_meta, d_meta, 8, cudaMemcpyDeviceToHost, s->st));
             CU(cudaMemcpyAsync(h_hist, d_hist, 4096 * 4, cudaMemcpyDeviceToHost, s->st));    // nearly always enough
-            CU(cudaStreamSynchronize(s->st));
+            CU(wait_stream(s, s->st));
             const uint32_t over = h_meta[0], maxc = h_meta[1];
             if (over) device_ok = false;
             else {
                 if (maxc > 4096u) {
                     CU(cudaMemcpyAsync(h_hist, d_hist, (size_t)maxc * 4, cudaMemcpyDeviceToHost, s->st));
-                    CU(cudaStreamSynchronize(s->st));
+                    CU(wait_stream(s, s->st));
                 }
                 s->stats.d2h_bytes += 8 + (size_t)std::max(maxc, 4096u) * 4;
                 std::vector<uint64_t> hist(maxc);
@@ -1916,7 +1941,7 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
             s->stats.kernel_launches++;
             TRY(ensure_hres(s, 16));
             CU(cudaMemcpyAsync(s->h_res, d_meta + 2, 4, cudaMemcpyDeviceToHost, s->st));
-            CU(cudaStreamSynchronize(s->st));
+            CU(wait_stream(s, s->st));
             m = *(uint32_t *)s->h_res;
             idx_on_device = true;
             if (trace) fprintf(stderr, "sketch(): device filter %.0f us (%u entries -> %u)\n", now() - t2, keep, m);
@@ -1927,7 +1952,7 @@ extern "C" int fb2_sketcher_sketch(fb2_sketcher *s, const char *name, const fb2_
         uint32_t *hc = (uint32_t *)s->h_res, *hx = hc + keep;
         CU(cudaMemcpyAsync(hc, s->out_cnt.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(hx, s->out_ext.p, (size_t)keep * 4, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaStreamSynchronize(s->st));
+        CU(wait_stream(s, s->st));
         s->stats.d2h_bytes += (size_t)keep * 8;
         const double t3 = trace ? now() : 0.0;
         TRY(fb2_filter_select(hc, hx, keep, &ff, s->format, sel, p->kind == FB2_KIND_MASH ? (size_t)p->final_size : SIZE_MAX));
@@ -1954,7 +1979,7 @@ extern "C" int fb2_sketcher_debug_symbols(fb2_sketcher *s, uint32_t *geom7, uint
                                           uint8_t *sym, size_t sym_cap) {
     if (!s || !geom7) return fb2_fail(FB2_EINVAL, "null argument");
     ON_DEVICE(s->device);
-    CU(cudaStreamSynchronize(s->st));
+    CU(wait_stream(s, s->st));
     const int par = s->par ^ 1;   // the chunk that ran last
     const ChunkGeom g = s->last_geom;
     const uint32_t gv[7] = {g.len, g.n_tiles, g.st_tiles, g.n_st, g.st_bytes, g.region_stride, g.hash_tiles};

@@ -40,6 +40,7 @@ int fb2_sketcher_begin_range(fb2_sketcher *s, int format, uint32_t state, uint32
 int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_byte, uint64_t *first_bad_pos, uint64_t *len_bad_pos);
 uint32_t fb2_sketcher_halo(const fb2_sketcher *s);
 void fb2_sketcher_set_polite_copy(fb2_sketcher *s, unsigned piece_mb);
+void fb2_sketcher_set_polite_sync(fb2_sketcher *s, int on);   // host waits yield / sleep instead of spinning
 int fb2_sketcher_sketch_small(fb2_sketcher *s, const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
                               const fb2_filter *f, fb2_result *out);
 void fb2_sketcher_set_link_flag(fb2_sketcher *s, std::atomic<int> *flag, int owner);
@@ -190,6 +191,18 @@ extern "C" int fb2_process_post_filter(fb2_result *r, const fb2_params *p, const
 }
 
 // ---- sketch_stream / sketch_files ----------------------------------------------------------------
+// Pinned file-read buffers of the sketch_files workers.  Pinning is the most expensive set-up call a worker makes and
+// the driver serialises it (tools/alloc_cost.cu on the 16-core B200 box: 14 ms per 32 MiB alone, 92 / 190 ms each when
+// 8 / 16 threads ask at once), so a buffer is only as large as the files need (rbuf_need) and says how large it is.
+static constexpr size_t RBUF_HDR = 64;
+static uint8_t *rbuf_alloc(size_t cap) {
+    uint8_t *base = nullptr;
+    if (cudaHostAlloc((void **)&base, cap + RBUF_HDR, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    *reinterpret_cast<size_t *>(base) = cap;
+    return base + RBUF_HDR;
+}
+static size_t rbuf_cap(const uint8_t *buf) { return buf ? *reinterpret_cast<const size_t *>(buf - RBUF_HDR) : 0; }
+static void rbuf_free(uint8_t *buf) { if (buf) cudaFreeHost(buf - RBUF_HDR); }
 static bool pool_acquire(const fb2_params *p, fb2_sketcher **s, uint8_t **buf);
 static bool pool_release(const fb2_params *p, fb2_sketcher *s, uint8_t *buf);
 static int finish_sketch(fb2_sketcher *s, const char *name, const fb2_params *p, const fb2_filter *f,
@@ -262,11 +275,11 @@ extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *n
     }
     if (rc != FB2_OK) {   // keep the message across the clean-up calls
         const std::string msg = fb2_last_error();
-        if (buf) cudaFreeHost(buf);
+        rbuf_free(buf);
         if (s) fb2_sketcher_destroy(s);
         return fb2_fail(rc, msg);
     }
-    if (!pool_release(&pd, s, buf)) { if (buf) cudaFreeHost(buf); fb2_sketcher_destroy(s); }
+    if (!pool_release(&pd, s, buf)) { rbuf_free(buf); fb2_sketcher_destroy(s); }
     return FB2_OK;
 }
 
@@ -380,7 +393,7 @@ static std::unique_ptr<StreamDecoder> make_xz_decoder(std::string &why) {
 // feed the raw bytes, finish the sketch.  gzip input (needletail sniffs the 1f 8b magic, lib.rs:60 via
 // parse_fastx_reader), bzip2 and xz input are decompressed on the host by this worker thread (StreamDecoder above).
 // FB2_TRACE_FILES=1: where the workers of sketch_files spend their time (summed over files, printed per call)
-static std::atomic<uint64_t> g_ns_reset{0}, g_ns_read{0}, g_ns_feed{0}, g_ns_finish{0}, g_n_files{0};
+static std::atomic<uint64_t> g_ns_reset{0}, g_ns_read{0}, g_ns_feed{0}, g_ns_finish{0}, g_n_files{0}, g_ns_create{0}, g_n_created{0};
 static inline uint64_t now_ns() {
     return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -580,7 +593,7 @@ static bool pool_release(const fb2_params *p, fb2_sketcher *s, uint8_t *buf) {
 extern "C" void fb2_sketch_files_release_pool(void) {
     std::vector<PoolEntry> old;
     { std::lock_guard<std::mutex> g(g_pool_mu); old.swap(g_pool); }
-    for (auto &e : old) { if (e.buf) cudaFreeHost(e.buf); fb2_sketcher_destroy(e.s); }
+    for (auto &e : old) { rbuf_free(e.buf); fb2_sketcher_destroy(e.s); }
 }
 
 // sketch_files (lib.rs:29-49): the reference fans the files out over a rayon pool, one sketcher per task.
@@ -591,6 +604,14 @@ extern "C" void fb2_sketch_files_release_pool(void) {
 // copies its 24 KB result straight into the caller's host array (a gather to one GPU followed by a copy to the
 // host would move the same bytes twice; the NCCL gather lives where there is one process per GPU: bench.py).
 // FB2_FILE_WORKERS overrides the thread count per GPU.
+// Read-buffer size for one file: whole small files in one read (+ 1 byte, so that the read sees the end of the file and
+// the small-stream path applies), in steps of 4 MiB; `piece` for large files, pipes and whatever cannot be stat'ed.
+static size_t rbuf_need(const char *path, size_t piece) {
+    struct stat sb;
+    if (strcmp(path, "-") == 0 || stat(path, &sb) != 0 || !S_ISREG(sb.st_mode)) return piece;
+    const uint64_t want = ((uint64_t)sb.st_size + (uint64_t)sb.st_size / 8 + 4096 + (4u << 20) - 1) / (4u << 20) * (4u << 20);
+    return (size_t)std::min<uint64_t>(piece, want);
+}
 static int sketch_files_on(const char *const *paths, size_t n, const fb2_params *p, const fb2_filter *f,
                            fb2_result *outs, const std::vector<int> &devices) {
     for (size_t i = 0; i < n; ++i) memset(&outs[i], 0, sizeof(fb2_result));
@@ -633,29 +654,40 @@ static int sketch_files_on(const char *const *paths, size_t n, const fb2_params 
         std::lock_guard<std::mutex> g(mu);
         if (first_rc.load() == FB2_OK) { first_rc.store(rc); first_msg = fb2_last_error(); }
     };
+    // more worker threads than cores (only by FB2_FILE_WORKERS, or many GPUs on a small host): waits must not spin
+    size_t n_threads = 0;
+    for (size_t g = 0; g < G; ++g) n_threads += has_stdin ? 1 : std::min(workers, lists[g].size());
+    const bool polite = getenv("FB2_POLITE_SYNC") ? atoi(getenv("FB2_POLITE_SYNC")) != 0 : n_threads > cores;
     auto work = [&](size_t g) {
         fb2_params pd = *p;
         pd.device = devices[g];
         fb2_sketcher *s = nullptr;
         uint8_t *buf = nullptr;
+        const uint64_t t_create = now_ns();
         bool reuse = pool_acquire(&pd, &s, &buf);     // an idle handle of an earlier call, same parameters and device
         int rc = FB2_OK;
+        if (!reuse) g_n_created += 1;
         if (!reuse) rc = fb2_sketcher_create(&pd, &s);   // selects the device for this thread
-        if (rc == FB2_OK && !buf) {                      // (handles pooled by fb2_sketch_stream_multi carry no read buffer)
-            cudaSetDevice(pd.device);
-            if (cudaHostAlloc((void **)&buf, piece, cudaHostAllocDefault) != cudaSuccess)
-                rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed (file read buffer)");
-        }
+        g_ns_create += now_ns() - t_create;
+        if (rc == FB2_OK) fb2_sketcher_set_polite_sync(s, polite ? 1 : 0);
         while (rc == FB2_OK && first_rc.load() == FB2_OK) {
             const size_t q = next[g].fetch_add(1);
             if (q >= lists[g].size()) break;
             const size_t i = lists[g][q];
-            rc = sketch_one_file(s, reuse, paths[i], buf, piece, &pd, f, &outs[i]);
+            const size_t need = rbuf_need(paths[i], piece);
+            if (need > rbuf_cap(buf)) {                  // (handles pooled by fb2_sketch_stream_multi carry no read buffer)
+                cudaSetDevice(pd.device);
+                rbuf_free(buf);
+                buf = rbuf_alloc(need);
+                if (!buf) { rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed (file read buffer)"); break; }
+            }
+            rc = sketch_one_file(s, reuse, paths[i], buf, rbuf_cap(buf), &pd, f, &outs[i]);
             reuse = true;
         }
+        if (s) fb2_sketcher_set_polite_sync(s, 0);       // pooled handles go back to spinning
         if (rc != FB2_OK) fail(rc);
         if (rc == FB2_OK && s && buf && pool_release(&pd, s, buf)) return;   // kept for the next call
-        if (buf) cudaFreeHost(buf);
+        rbuf_free(buf);
         if (s) fb2_sketcher_destroy(s);
     };
     std::vector<std::thread> th;
@@ -667,10 +699,12 @@ static int sketch_files_on(const char *const *paths, size_t n, const fb2_params 
     else for (auto &t : th) t.join();
     if (getenv("FB2_TRACE_FILES")) {
         const double nf = (double)std::max<uint64_t>(1, g_n_files.load());
-        fprintf(stderr, "sketch_files: %llu files, %zu threads; per file (worker time, us): reset %.0f  read %.0f  feed %.0f  finish %.0f\n",
-                (unsigned long long)g_n_files.load(), th.size(), g_ns_reset.load() / nf / 1e3, g_ns_read.load() / nf / 1e3,
-                g_ns_feed.load() / nf / 1e3, g_ns_finish.load() / nf / 1e3);
-        g_ns_reset = 0; g_ns_read = 0; g_ns_feed = 0; g_ns_finish = 0; g_n_files = 0;
+        fprintf(stderr, "sketch_files: %llu files, %zu threads%s; per file (worker time, us): reset %.0f  read %.0f  feed %.0f  finish %.0f; "
+                        "%llu handles created, %.1f ms per thread getting one\n",
+                (unsigned long long)g_n_files.load(), th.size(), polite ? " (polite waits)" : "", g_ns_reset.load() / nf / 1e3, g_ns_read.load() / nf / 1e3,
+                g_ns_feed.load() / nf / 1e3, g_ns_finish.load() / nf / 1e3, (unsigned long long)g_n_created.load(),
+                g_ns_create.load() / 1e6 / (double)std::max<size_t>(1, th.size()));
+        g_ns_reset = 0; g_ns_read = 0; g_ns_feed = 0; g_ns_finish = 0; g_n_files = 0; g_ns_create = 0; g_n_created = 0;
     }
     const int rc = first_rc.load();
     if (rc != FB2_OK) {
@@ -839,7 +873,7 @@ extern "C" int fb2_sketch_stream_multi(const uint8_t *bytes, size_t len, const c
             fb2_params pd = *p;
             pd.device = devices[g]; pd.stream = nullptr;
             if (keep && pool_release(&pd, hs[g], bufs[g])) continue;
-            if (bufs[g]) cudaFreeHost(bufs[g]);
+            rbuf_free(bufs[g]);
             fb2_sketcher_destroy(hs[g]);
         }
     };
@@ -988,7 +1022,7 @@ static int sketch_stream_two_ended(const uint8_t *bytes, size_t len, const char 
             fb2_sketcher_set_polite_copy(hs[w], 0);
             fb2_sketcher_set_link_flag(hs[w], nullptr, 0);
             if (keep && pool_release(&pd, hs[w], bufs[w])) continue;
-            if (bufs[w]) cudaFreeHost(bufs[w]);
+            rbuf_free(bufs[w]);
             fb2_sketcher_destroy(hs[w]);
         }
     };

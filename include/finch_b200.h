@@ -233,6 +233,43 @@ int fb2_old_distance_finish(uint64_t common, uint64_t query_len, uint64_t ref_le
                             double *containment, double *jaccard, double *mash_distance,
                             uint64_t *common_hashes, uint64_t *total_hashes);
 
+/* ---- sketch files ---------------------------------------------------------------------------
+ * Collections of finished sketches in the reference's three file formats; host only (no device is needed).
+ *   open  <- open_sketch_file (lib/src/lib.rs:96-117): the file SUFFIX decides -- *.msh Mash Cap'n Proto
+ *            (serialization/mash.rs:73-132), *.bsk finch Cap'n Proto (serialization/mod.rs:178-224), *.sk / *.json
+ *            Mash-compatible JSON (serialization/json.rs); anything else: "File suffix is not *.bsk, *.msh, or *.sk"
+ *   save  <- write_finch_file (serialization/mod.rs:123-176; what Multisketch.save of the Python module writes,
+ *            python.rs:180-186), write_mash_file (mash.rs:12-71), MultiSketch JSON (json.rs:64-89)
+ * This is what the Python mirror of the reference's `finch` module (finch_rs_b200/pyfinch.py) is built on. */
+#define FB2_FILE_SK 0  /* .sk  */
+#define FB2_FILE_BSK 1 /* .bsk */
+#define FB2_FILE_MSH 2 /* .msh */
+typedef struct fb2_sketch_set fb2_sketch_set;
+/* `Sketch` (serialization/mod.rs:45-55).  From fb2_sketch_set_get the pointers belong to the set and stay valid
+ * until its next _get / _add / _remove / _close. */
+typedef struct fb2_sketch_view {
+    const char *name;
+    const char *comment;
+    uint64_t seq_length;
+    uint64_t num_valid_kmers;
+    fb2_params params;         /* sketch_params (device / stream unused) */
+    fb2_filter filter;         /* filter_params */
+    uint64_t n;                /* hashes.len() */
+    const uint64_t *hashes;    /* ascending */
+    const uint32_t *counts;
+    const uint32_t *extras;
+    const uint8_t *kmers;      /* k-mer bytes back to back (files may hold none: all offsets equal) */
+    const uint64_t *kmer_offs; /* n + 1 offsets into kmers */
+} fb2_sketch_view;
+int fb2_sketch_set_new(fb2_sketch_set **out);
+int fb2_sketch_set_open(const char *path, fb2_sketch_set **out);
+uint64_t fb2_sketch_set_len(const fb2_sketch_set *set);
+int fb2_sketch_set_get(const fb2_sketch_set *set, uint64_t i, fb2_sketch_view *out);
+int fb2_sketch_set_add(fb2_sketch_set *set, const fb2_sketch_view *v); /* copies */
+int fb2_sketch_set_remove(fb2_sketch_set *set, uint64_t i);
+int fb2_sketch_set_save(const fb2_sketch_set *set, const char *path, int file_format);
+void fb2_sketch_set_close(fb2_sketch_set *set);
+
 /* ---- misc --------------------------------------------------------------------------------- */
 const char *fb2_last_error(void);
 int fb2_device_count(void);

@@ -347,3 +347,76 @@ def minmer_matrix(ref_hashes, sketches):
     out = np.zeros((n, len(ref)), np.int32)
     lib().fo_minmer_matrix(ref.ctypes.data, len(ref), hp, cp, ln, n, out.ctypes.data)
     return out
+
+
+# ---- the reference's Python module (lib/src/python.rs): literal restatements of its host loops -------------------
+# Entries are (hash, kmer, count, extra_count) tuples, ascending by hash, like `Sketch.hashes` returns them.
+def py_merge_sketches(hashes1, hashes2, size=None, scale=None):
+    """merge_sketches (python.rs:44-101): the two-pointer walk (it stops when EITHER list ends, the rest of the longer
+    list is dropped), then the clip by `size` / `scale`.  u32 additions wrap (release build)."""
+    new = []
+    i = j = 0
+    while i < len(hashes1) and j < len(hashes2):
+        if hashes1[i][0] < hashes2[j][0]:
+            new.append(hashes1[i]); i += 1
+        elif hashes2[j][0] < hashes1[i][0]:
+            new.append(hashes2[j]); j += 1
+        else:
+            new.append((hashes1[i][0], hashes1[i][1], (hashes1[i][2] + hashes2[j][2]) & 0xFFFFFFFF,
+                        (hashes1[i][3] + hashes2[j][3]) & 0xFFFFFFFF))
+            i += 1; j += 1
+    if scale is not None:
+        max_hash = ((1 << 64) - 1) // int(1.0 / scale)
+        out = []
+        for ix, h in enumerate(new):
+            if not (h[0] <= max_hash or (size is not None and ix < size)):
+                break
+            out.append(h)
+        new = out
+    elif size is not None:
+        new = new[:size]
+    return new
+
+
+def py_compare_counts(reference, query):
+    """Sketch.compare_counts (python.rs:496-561), statement by statement."""
+    common = ref_pos = ref_count = query_pos = query_count = 0
+    mean = m2 = m3 = m4 = 0.0
+    while ref_pos < len(reference) and query_pos < len(query):
+        if reference[ref_pos][0] < query[query_pos][0]:
+            ref_pos += 1
+        elif query[query_pos][0] < reference[ref_pos][0]:
+            query_pos += 1
+        else:
+            ref_count += reference[ref_pos][2]
+            query_count += query[query_pos][2]
+            n = float(common) + 1.0
+            float_count = float(query[query_pos][2])
+            delta = float_count - mean
+            delta_n = delta / n
+            delta_n2 = delta_n * delta_n
+            term1 = delta * delta_n * (n - 1.0)
+            mean += delta_n
+            m4 += term1 * delta_n2 * (n * n - 3.0 * n + 3.0) + 6.0 * delta_n2 * m2 - 4.0 * delta_n * m3
+            m3 += term1 * delta_n * (n - 2.0) - 3.0 * delta_n * m2
+            m2 += term1
+            ref_pos += 1; query_pos += 1; common += 1
+    f = np.float64
+    with np.errstate(all="ignore"):
+        var = f(m2) / f(common)
+        skew = np.sqrt(f(common)) * f(m3) / np.power(f(m2), f(1.5))
+        kurt = f(common) * f(m4) / (f(m2) * f(m2)) - f(3.0)
+    return (common, ref_pos, query_pos, ref_count, query_count, float(var), float(skew), float(kurt))
+
+
+def py_set_counts(hashes, values):
+    """Sketch.set_counts (python.rs:585-608) -> the new entries, or an error message"""
+    if len(values) != len(hashes):
+        return "counts must be same length as sketch"
+    new = []
+    for s, v in zip(hashes, values):
+        if v < 0:
+            return f"Negative count {v} not supported"
+        if v > 0:
+            new.append((s[0], s[1], int(v), s[3]))
+    return new
