@@ -43,11 +43,14 @@ if part(1):   # FASTQ, several chunks, filters on (the metric path in small)
     reads = []
     for i in range(9000):
         p = int(rng.integers(0, len(genome) - 150))
-        reads.append(b"@r%d\n" % i + genome[p:p + 150] + b"\n+\n" + b"I" * 150 + b"\n")
+        seq = genome[p:p + 150]
+        if rng.random() < 0.5:
+            seq = seq[::-1].translate(bytes.maketrans(b"ACGT", b"TGCA"))   # both strands, or the strand filter drops everything
+        reads.append(b"@r%d\n" % i + seq + b"\n+\n" + b"I" * 150 + b"\n")
     data = b"".join(reads)
-    sp = fb.SketchParams.mash(2000, 100, False, 21, 0)
+    sp = fb.SketchParams.mash(2000, 100, True, 21, 0)
     fp = fb.FilterParams(True, (None, None), 0.21, 0.1)
-    rc, osk = oracle.sketch_stream(data, oracle.mash_params(2000, 100, False, 21, 0), oracle.make_filter(True, (None, None), 0.21, 0.1))
+    rc, osk = oracle.sketch_stream(data, oracle.mash_params(2000, 100, True, 21, 0), oracle.make_filter(True, (None, None), 0.21, 0.1))
     assert rc == oracle.OK
     for mode in ("0", "1", "2"):
         os.environ["FB2_HOST_STRIP"] = mode
