@@ -179,8 +179,9 @@ int fb2_sketch_files_multi(const char *const *paths, size_t n, const fb2_params 
 int fb2_sketch_stream_multi(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
                             const fb2_filter *f, fb2_result *out, int ngpus);
 
-/* The sketch_* calls keep at most FB2_POOL_MAX (default 2) idle worker handles per device (device buffers, a 32 MiB
- * pinned read buffer) for the next call with the same parameters; this frees them. */
+/* The sketch_* calls keep idle worker handles (device buffers, a pinned read buffer sized by the files read so far) for
+ * the next call with the same parameters, bounded per device: at most FB2_POOL_MAX handles (default 16; 0 = none) holding
+ * at most FB2_POOL_MB MiB of device memory together (default 4096).  This frees them. */
 void fb2_sketch_files_release_pool(void);
 
 /* ---- raw_distance (distance.rs:66-126), integer part, batched ----------------------------- */
@@ -189,7 +190,8 @@ typedef struct fb2_pair_out {
     uint32_t i;      /* query hashes consumed */
     uint32_t j;      /* reference hashes consumed */
 } fb2_pair_out;
-/* hashes: n_sk sketches, sketch s occupies hashes[s*stride .. s*stride+lens[s]) ascending.
+/* hashes: n_sk sketches, sketch s occupies hashes[s*stride .. s*stride+lens[s]), STRICTLY ascending (what to_vec
+ * returns: the keys of a hash map, sorted; the merge loop's behaviour on repeated hashes is not reproduced).
  * For pair p: query q_idx[p], reference r_idx[p].  scale as raw_distance's (0 = none).
  * The f64 epilogue (containment, jaccard, mash distance) stays on the host: fb2_distance_finish. */
 int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,

@@ -817,6 +817,31 @@ def test_dist_batch_random(fb, oracle):
             assert tuple(allp[a, b]) == (c, i, j)
 
 
+def test_raw_distance_commutes(fb, oracle):
+    """distance.rs:176-185 (proptest): raw_distance(a, b, 0.) == raw_distance(b, a, 0.) for arbitrary sorted lists
+    (strictly ascending here: what a sketch holds), small values and u64::MAX included; every case also against the
+    oracle's literal loop."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    u64 = st.one_of(st.integers(0, 40), st.integers(0, 2**64 - 1), st.sampled_from([0, 1, 2**63, 2**64 - 2, 2**64 - 1]))
+    lists = st.lists(u64, max_size=60, unique=True).map(sorted)
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.lists(st.tuples(lists, lists), min_size=1, max_size=8))
+    def run(pairs):
+        sk = [np.array(x, np.uint64) for ab in pairs for x in ab]
+        q = np.arange(0, len(sk), 2); r = q + 1
+        fwd = fb.dist_batch(sk, q, r, 0.0)
+        rev = fb.dist_batch(sk, r, q, 0.0)
+        for t, (a, b) in enumerate(pairs):
+            lhs, rhs = fb._finish_pair(fwd[t], 21), fb._finish_pair(rev[t], 21)
+            assert (lhs[1], lhs[3], lhs[4]) == (rhs[1], rhs[3], rhs[4])       # jaccard, common, total commute
+            cont, jac, com, tot = oracle.raw_distance(sk[2 * t], sk[2 * t + 1], 0.0)
+            assert (lhs[0], lhs[1], lhs[3], lhs[4]) == (cont, jac, com, tot)
+            cont, jac, com, tot = oracle.raw_distance(sk[2 * t + 1], sk[2 * t], 0.0)
+            assert (rhs[0], rhs[1], rhs[3], rhs[4]) == (cont, jac, com, tot)
+    run()
+
+
 def _closed_form_pairs(sk, scale=0.0):
     """(common, i, j) per ordered pair from the closed form of the merge loop, numpy."""
     n = len(sk)
