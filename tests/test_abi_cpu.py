@@ -11,6 +11,16 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_rust_sys_crate_declares_every_entry_point():
+    """rust/finch_b200-sys is shipped uncompiled (no Rust toolchain here): at least its extern block must name every
+    function of the header, so that the two cannot drift apart unnoticed."""
+    hdr = open(os.path.join(ROOT, "include", "finch_b200.h")).read()
+    rs = open(os.path.join(ROOT, "rust", "finch_b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"\b(fb2_[a-z0-9_]+)\s*\(", hdr))
+    in_rust = set(re.findall(r"pub fn (fb2_[a-z0-9_]+)\s*\(", rs))
+    assert declared == in_rust, (sorted(declared - in_rust), sorted(in_rust - declared))
+
+
 def test_library_exports_every_declared_symbol(fb):
     hdr = open(os.path.join(ROOT, "include", "finch_b200.h")).read()
     declared = set(re.findall(r"\b(fb2_[a-z0-9_]+)\s*\(", hdr))
