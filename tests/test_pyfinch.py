@@ -338,3 +338,27 @@ def test_compare_best_match_filter_and_matrix(oracle):
     got = query.compare_matrix(*refs)
     assert got.dtype == np.int32 and got.shape == (len(refs), len(query))
     assert np.array_equal(got, oracle.minmer_matrix(query.s.hashes, [(r.s.hashes, r.s.counts) for r in refs]))
+
+
+@pytest.mark.gpu
+def test_open_files_written_by_the_command_line(tmp_path):
+    """`finch sketch` (-o .sk, -b .bsk, -B .msh) -> Multisketch.open: the same ten entries sketch_file returns"""
+    import subprocess
+    exe = os.path.join(ROOT, "finch_rs_b200", "finch")
+    want = finch.sketch_file(QUERY_FA, n_hashes=10, filter=False)
+    for flag, ext in ((None, ".sk"), ("-b", ".bsk"), ("-B", ".msh")):
+        out = tmp_path / ("q" + ext)
+        cmd = [exe, "sketch", "--n-hashes", "10"] + ([flag] if flag else []) + ["-O", QUERY_FA]
+        p = subprocess.run(cmd, capture_output=True)
+        assert p.returncode == 0, p.stderr
+        out.write_bytes(p.stdout)
+        ms = finch.Multisketch.open(str(out))
+        assert len(ms) == 1 and QUERY_FA in ms
+        got = ms[QUERY_FA]
+        assert [h for h, *_ in got.hashes] == [h for h, *_ in want.hashes]
+        assert (got.seq_length, got.num_valid_kmers) == (want.seq_length, want.num_valid_kmers) or ext == ".msh"
+        if ext != ".msh":                      # the Mash format keeps no k-mers
+            assert [k for _, k, _, _ in got.hashes] == [k for _, k, _, _ in want.hashes]
+            assert [c for _, _, c, _ in got.hashes] == [c for _, _, c, _ in want.hashes]
+        assert got.compare(want) == (1.0, 1.0) and want.compare(got) == (1.0, 1.0)
+        assert got.sketch_params["sketch_type"] == "mash" and got.sketch_params["kmer_length"] == 21
