@@ -518,7 +518,6 @@ static int sort_table(fb2_sketcher *s, uint32_t *n_out) {
     uint32_t bits = 0;
     while (bits < 64 && (thr >> bits) != 0ULL) ++bits;
     const uint32_t shift = bits > 12 ? bits - 12 : 0;
-    bool sorted = false;
     if (n >= 2) {
         uint32_t *bins = s->d_bins.as<uint32_t>();
         // scatter target: (keys, slots) as scratch is not possible (rank needs a third buffer): use
@@ -530,19 +529,15 @@ static int sort_table(fb2_sketcher *s, uint32_t *n_out) {
             // result is in (tkeys, tslots): copy to (keys, slots) where the consumers expect it
             CU(cudaMemcpyAsync(keys, tkeys, (size_t)n * 8, cudaMemcpyDeviceToDevice, s->st));
             CU(cudaMemcpyAsync(slots, tslots, (size_t)n * 4, cudaMemcpyDeviceToDevice, s->st));
-            sorted = true;
         } else {
             // non-uniform keys: (keys, slots) hold the bucket-scattered (complete) set: radix sort them
             launch_radix_sort(keys, slots, tkeys, tslots, n, s->sort_hist.as<uint32_t>(), s->st);
             s->stats.kernel_launches += 24;
-            sorted = true;
         }
     } else if (n == 1) {
         CU(cudaMemcpyAsync(keys, tkeys, 8, cudaMemcpyDeviceToDevice, s->st));
         CU(cudaMemcpyAsync(slots, tslots, 4, cudaMemcpyDeviceToDevice, s->st));
-        sorted = true;
     }
-    (void)sorted;
     launch_select_keep(keys, n, s->scaled ? 1 : 0, s->size, s->max_hash, dst, s->st);
     s->stats.kernel_launches += 1;
     TRY(pull_state(s));
@@ -2189,7 +2184,7 @@ extern "C" int fb2_minmer_matrix(const uint64_t *ref_hashes, size_t n_ref, const
 extern "C" int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride, double scale,
                               const uint32_t *q_idx, const uint32_t *r_idx, size_t n_pairs, fb2_pair_out *out,
                               int32_t device) {
-    if ((!hashes && n_sk * stride) || !lens || (n_pairs && (!q_idx || !r_idx || !out)))
+    if ((!hashes && n_sk && stride) || !lens || (n_pairs && (!q_idx || !r_idx || !out)))
         return fb2_fail(FB2_EINVAL, "null argument");
     for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
     for (size_t i = 0; i < n_pairs; ++i)
@@ -2219,7 +2214,7 @@ extern "C" double fb2_dist_last_kernel_ms(void) { return g_dist_kernel_ms; }
 
 extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
                                   double scale, size_t q0, size_t q1, fb2_pair_out *out, int32_t device) {
-    if ((!hashes && n_sk * stride) || !lens || q0 > q1 || q1 > n_sk) return fb2_fail(FB2_EINVAL, "bad argument");
+    if ((!hashes && n_sk && stride) || !lens || q0 > q1 || q1 > n_sk) return fb2_fail(FB2_EINVAL, "bad argument");
     for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
     const uint64_t n_pairs = (uint64_t)(q1 - q0) * n_sk;
     if (n_pairs && !out) return fb2_fail(FB2_EINVAL, "null output");
@@ -2442,7 +2437,7 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
 extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride, double scale,
                                       size_t q0, size_t q1, uint8_t kmer_length, double max_distance, int skip_self,
                                       fb2_pair_hit *hits, size_t cap, uint64_t *n_hits, int32_t device, int ngpus) {
-    if ((!hashes && n_sk * stride) || !lens || q0 > q1 || q1 > n_sk || !n_hits || (cap && !hits)) return fb2_fail(FB2_EINVAL, "bad argument");
+    if ((!hashes && n_sk && stride) || !lens || q0 > q1 || q1 > n_sk || !n_hits || (cap && !hits)) return fb2_fail(FB2_EINVAL, "bad argument");
     if (n_sk > 0xFFFFFFFFull || kmer_length == 0) return fb2_fail(FB2_EINVAL, "bad argument");
     for (size_t i = 0; i < n_sk; ++i) if (lens[i] > stride) return fb2_fail(FB2_EINVAL, "sketch length exceeds stride");
     *n_hits = 0;

@@ -961,12 +961,11 @@ static int sketch_stream_two_ended(const uint8_t *bytes, size_t len, const char 
     };
     const char *only = getenv("FB2_TWO_ENDED_ONLY");   // diagnosis: "front" / "back" = the other side takes the minimum
     const bool only_front = only && only[0] == 'f', only_back = only && only[0] == 'b';
-    size_t b_first = N, b_last_a = N;     // B's first claim is [b_first, N): it holds the end of the stream
+    size_t b_first = N;                   // B's first claim is [b_first, N): it holds the end of the stream
     {
-        size_t a, b;
+        size_t a = N, b = N;
         claim(false, &a, &b);
-        b_first = a; b_last_a = a;
-        (void)b;
+        b_first = a;
     }
     auto front_work = [&]() {             // A: host-framed, one continuous stream from byte 0
         int r = open(0);
@@ -1015,7 +1014,6 @@ static int sketch_stream_two_ended(const uint8_t *bytes, size_t len, const char 
         tb.join();
     }
     const double t_joined = now_ms();
-    (void)b_last_a;
     auto release_all = [&](bool keep) {
         for (int w = 0; w < 2; ++w) {
             if (!hs[w]) continue;
