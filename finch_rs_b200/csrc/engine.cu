@@ -21,6 +21,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/mman.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "strip.h"
@@ -154,6 +156,7 @@ struct fb2_sketcher {
     uint32_t live_shift = 52;    // its shift (host copy of SketchState::hist_shift)
     DevBuf out_hash, out_cnt, out_ext, out_kmer, out_posx;
     DevBuf sel_hash, sel_cnt, sel_ext, sel_kmer, sel_posx, sel_bytes, sel_idx;
+    std::vector<cudaEvent_t> ev_piece;   // one per piece of a large result on its way out (collect_rows)
     uint8_t *h_res = nullptr;        // pinned read-back staging
     size_t h_res_cap = 0;
     DevBuf d_push_bytes, d_push_offs, d_push_extra;
@@ -475,6 +478,7 @@ extern "C" void fb2_sketcher_destroy(fb2_sketcher *s) {
     s->sel_hash.release(); s->sel_cnt.release(); s->sel_ext.release(); s->sel_kmer.release(); s->sel_posx.release();
     s->sel_bytes.release(); s->sel_idx.release();
     if (s->h_res) cudaFreeHost(s->h_res);
+    for (cudaEvent_t e : s->ev_piece) cudaEventDestroy(e);
     s->d_push_bytes.release(); s->d_push_offs.release(); s->d_push_extra.release();
     if (s->h_pinned) cudaFreeHost(s->h_pinned);   // h_carry, h_state, h_snap[]
     if (s->h_stage) cudaFreeHost(s->h_stage);
@@ -1761,13 +1765,28 @@ static int export_sorted(fb2_sketcher *s, uint32_t *keep_out) {
     return FB2_OK;
 }
 
+// Result arrays.  A Scaled sketch of a whole genome has millions of entries (C4: 2.96 M, 139 MB): filling freshly
+// mapped 4 KiB pages was most of its end-of-stream time (26 of 30 ms, mostly page faults, and another 10 ms when the
+// caller freed them).  Large arrays are 2 MiB-aligned and marked for transparent huge pages; free() takes both kinds.
+static void *result_alloc(size_t n) {
+    if (n >= ((size_t)8 << 20)) {
+        const size_t a = (size_t)2 << 20, r = (n + a - 1) & ~(a - 1);
+        void *p = aligned_alloc(a, r);
+        if (p) { madvise(p, r, MADV_HUGEPAGE); return p; }
+    }
+    return malloc(std::max<size_t>(1, n));
+}
+// Large results leave the pinned staging block in pieces: every piece has its own device-to-host copy and event, and a
+// few host threads copy their stripe of a piece as soon as it has arrived, so the link and the host copies overlap.
+struct ResultPiece { void *dst; size_t off, len; };
+
 // Bring m exported rows to the host as an fb2_result: rows idx[0..m) (device indices) or the first m.
 static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_result *out, bool idx_on_device = false) {
     const size_t stride = (size_t)s->k;   // pushed k-mers may be longer: fixed up below
     out->n = m;
-    out->hashes = (uint64_t *)malloc(std::max<size_t>(1, (size_t)m * 8));
-    out->counts = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
-    out->extras = (uint32_t *)malloc(std::max<size_t>(1, (size_t)m * 4));
+    out->hashes = (uint64_t *)result_alloc((size_t)m * 8);
+    out->counts = (uint32_t *)result_alloc((size_t)m * 4);
+    out->extras = (uint32_t *)result_alloc((size_t)m * 4);
     if (!out->hashes || !out->counts || !out->extras) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
     // Entries that came through push() carry the caller's bytes (arena) and need their codes / position
     // words on the host; everything else is expanded to ASCII on the device and copied as one block.
@@ -1795,6 +1814,54 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
         const size_t o_kmer = (o_bytes + (size_t)m * stride + 7) & ~(size_t)7, o_posx = o_kmer + (size_t)m * 8;
         const size_t total = has_arena ? o_posx + (size_t)m * 8 : o_bytes + (size_t)m * stride;
         TRY(ensure_hres(s, total));
+        if (!has_arena && total >= ((size_t)32 << 20) && !getenv("FB2_NO_PIPED_RESULT")) {
+            // the pipelined way out (see ResultPiece)
+            out->kmers = (uint8_t *)result_alloc((size_t)m * stride);
+            if (!out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
+            out->kmer_stride = (uint32_t)stride;
+            std::vector<ResultPiece> pieces;
+            const size_t piece = (size_t)16 << 20;
+            auto add = [&](void *dst, const void *dev, size_t off, size_t len) -> int {
+                for (size_t a = 0; a < len; a += piece) {
+                    const size_t n = std::min(piece, len - a);
+                    CU(cudaMemcpyAsync(s->h_res + off + a, (const char *)dev + a, n, cudaMemcpyDeviceToHost, s->st));
+                    if (pieces.size() >= s->ev_piece.size()) {
+                        cudaEvent_t e;
+                        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        s->ev_piece.push_back(e);
+                    }
+                    CU(cudaEventRecord(s->ev_piece[pieces.size()], s->st));
+                    pieces.push_back(ResultPiece{(char *)dst + a, off + a, n});
+                }
+                return FB2_OK;
+            };
+            TRY(add(out->hashes, s->sel_hash.p, o_hash, (size_t)m * 8));
+            TRY(add(out->counts, s->sel_cnt.p, o_cnt, (size_t)m * 4));
+            TRY(add(out->extras, s->sel_ext.p, o_ext, (size_t)m * 4));
+            TRY(add(out->kmers, s->sel_bytes.p, o_bytes, (size_t)m * stride));
+            const unsigned T = std::max(1u, std::min(12u, std::thread::hardware_concurrency()));
+            std::atomic<int> bad{0};
+            auto work = [&](unsigned t) {
+                if (t) cudaSetDevice(s->device);
+                for (size_t q = 0; q < pieces.size(); ++q) {
+                    if (cudaEventSynchronize(s->ev_piece[q]) != cudaSuccess) { bad.store(1); return; }
+                    const ResultPiece &pc = pieces[q];
+                    const size_t per = (pc.len / T + 4095) & ~(size_t)4095, a = std::min(pc.len, per * t), b = std::min(pc.len, a + per);
+                    if (b > a) memcpy((char *)pc.dst + a, s->h_res + pc.off + a, b - a);
+                }
+            };
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto &x : th) x.join();
+            if (bad.load()) { fb2_result_free(out); return fb2_fail(FB2_ECUDA, "cudaEventSynchronize failed (result pieces)"); }
+            s->stats.d2h_bytes += total;
+            out->seq_length = s->h_carry->total_bases + s->lines_bases;
+            out->num_valid_kmers = s->total_kmers;
+            out->format = s->format;
+            out->filters.filter_on = 0;
+            return FB2_OK;
+        }
         CU(cudaMemcpyAsync(s->h_res + o_hash, s->sel_hash.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(s->h_res + o_cnt, s->sel_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(s->h_res + o_ext, s->sel_ext.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s->st));
@@ -1820,7 +1887,7 @@ static int collect_rows(fb2_sketcher *s, const uint32_t *h_idx, uint32_t m, fb2_
             if (h_posx[i] & (1ULL << 8)) ostride = std::max(ostride, s->arena[(size_t)h_kmer[i]].size());
     out->kmer_stride = (uint32_t)ostride;
     if (!has_arena) {
-        out->kmers = (uint8_t *)malloc(std::max<size_t>(1, (size_t)m * ostride));
+        out->kmers = (uint8_t *)result_alloc((size_t)m * ostride);
         if (!out->kmers) { fb2_result_free(out); return fb2_fail(FB2_ENOMEM, "malloc"); }
         if (m) parallel_memcpy(out->kmers, h_bytes, (size_t)m * stride);
     } else {
