@@ -3,6 +3,7 @@
 // Output per ordered pair: (common, i, j); containment / jaccard / mash distance are f64 and
 // are finished on the host (fb2_distance_finish) exactly as distance.rs:117-125 and :35-41 do.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "device_types.cuh"
 #include "../../include/finch_b200.h"
@@ -289,6 +290,147 @@ int launch_dist_tile_cut(const unsigned long long *hashes, const uint32_t *lens,
                          unsigned int *counter, uint32_t cap, int skip_self, double jlow, cudaStream_t s) {
     DistCut c; c.hits = hits; c.keys = keys; c.counter = counter; c.cap = cap; c.skip_self = skip_self; c.jlow = jlow;
     return dist_tile_launch(hashes, lens, stride, n_sk, q0, q1, scaled, max_hash, nullptr, &c, s);
+}
+// ---- the cut through an inverted index ------------------------------------------------------------------------
+// calc_sketch_distances keeps a pair iff mash_distance <= max_dist (cli/src/main.rs:326-330).  With a positive jaccard
+// bound a pair that shares NO hash cannot pass (jaccard 0; empty sketches aside), and in a large collection almost no
+// pair shares one: C5 holds 10^10 ordered pairs, 10^7 of them inside its 1000 clusters.  The tile kernel above still
+// probes every pair (1000 membership tests each).  Here the collection is turned into postings (hash, sketch), sorted
+// by hash; a block then owns ONE query sketch, walks the posting run of each of its hashes and counts, per reference
+// sketch, the hashes they share in 16-bit counters in shared memory (2 bytes x sketches of a column block).  Only
+// references with a non-zero count are candidates; their (common, i, j) are exact (i, j from the closed form of the
+// merge loop, like pair_warp) and go through the same jaccard test and hit list as the tile kernel's.
+// Work: sum over distinct hashes of (run length)^2 counter bumps instead of pairs x hashes probes.
+
+// one warp per sketch: keys[off[sk] + p] = its p-th hash, vals[...] = off[sk] + p (the posting's own index)
+__global__ void __launch_bounds__(256)
+postings_fill_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *__restrict__ lens, uint32_t stride,
+                     uint32_t n_sk, const uint32_t *__restrict__ off, unsigned long long *__restrict__ keys,
+                     uint32_t *__restrict__ vals) {
+    const uint32_t sk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (sk >= n_sk) return;
+    const uint32_t n = lens[sk], base = off[sk];
+    const unsigned long long *A = hashes + (uint64_t)sk * stride;
+    for (uint32_t p = lane; p < n; p += 32) { keys[base + p] = A[p]; vals[base + p] = base + p; }
+}
+// After the (stable) sort by hash: sorted_sk[e] = sketch of posting e (ascending inside a run); the first posting of
+// every run tells each member where the run lies: runinfo[posting index] = start | length << 32.
+__global__ void __launch_bounds__(256)
+postings_runs_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n,
+                     const uint32_t *__restrict__ off, uint32_t n_sk, uint32_t *__restrict__ sorted_sk,
+                     unsigned long long *__restrict__ runinfo, unsigned long long *__restrict__ sum_sq) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long sq = 0;
+    if (e < n) {
+        const uint32_t v = vals[e];
+        uint32_t lo = 0, hi = n_sk;                       // sk = last index with off[sk] <= v
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= v) lo = mid; else hi = mid; }
+        sorted_sk[e] = lo;
+        const unsigned long long k = keys[e];
+        if (e == 0u || keys[e - 1] != k) {
+            uint32_t t = e + 1u;
+            while (t < n && keys[t] == k) ++t;
+            const unsigned long long info = (unsigned long long)e | ((unsigned long long)(t - e) << 32);
+            for (uint32_t x = e; x < t; ++x) runinfo[vals[x]] = info;
+            sq = (unsigned long long)(t - e) * (unsigned long long)(t - e);
+        }
+    }
+    // block sum of the squared run lengths (the cost of the counting pass)
+    __shared__ unsigned long long part[8];
+    for (int d = 16; d > 0; d >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, d);
+    if ((threadIdx.x & 31u) == 0u) part[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += part[w];
+        if (s) atomicAdd(sum_sq, s);
+    }
+}
+constexpr int DI_THREADS = 1024;
+__global__ void __launch_bounds__(DI_THREADS, 1)
+dist_inverted_kernel(const unsigned long long *__restrict__ hashes, const uint32_t *__restrict__ lens, uint32_t stride,
+                     uint32_t n_sk, uint32_t q0, const uint32_t *__restrict__ off, const uint32_t *__restrict__ sorted_sk,
+                     const unsigned long long *__restrict__ runinfo, uint32_t cb, int scaled, unsigned long long max_hash,
+                     DistCut cut) {
+    extern __shared__ uint32_t di_cnt[];                  // cb / 2 words: two 16-bit counters each
+    const uint32_t q = q0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned long long *A = hashes + (uint64_t)q * stride;
+    const uint32_t na = lens[q], base = off[q], words = cb >> 1;
+    for (uint32_t c0 = 0; c0 < n_sk; c0 += cb) {
+        for (uint32_t x = tid; x < words; x += DI_THREADS) di_cnt[x] = 0u;
+        __syncthreads();
+        for (uint32_t p = warp; p < na; p += DI_THREADS / 32) {
+            const unsigned long long info = runinfo[base + p];
+            const uint32_t start = (uint32_t)info, len = (uint32_t)(info >> 32);
+            for (uint32_t x = lane; x < len; x += 32) {
+                const uint32_t r = sorted_sk[start + x] - c0;        // (unsigned: sketches below c0 wrap past cb)
+                if (r < cb) atomicAdd(&di_cnt[r >> 1], 1u << (16u * (r & 1u)));
+            }
+        }
+        __syncthreads();
+        for (uint32_t x = tid; x < words; x += DI_THREADS) {
+            const uint32_t w = di_cnt[x];
+            if (!w) continue;
+#pragma unroll
+            for (uint32_t half = 0; half < 2; ++half) {
+                const uint32_t c = (w >> (16u * half)) & 0xFFFFu, r = c0 + 2u * x + half;
+                if (!c || r >= n_sk) continue;
+                const unsigned long long *B = hashes + (uint64_t)r * stride;
+                const uint32_t nb = lens[r];
+                uint32_t i, j;                                       // na, nb > 0: the sketches share a hash
+                const unsigned long long ma = A[na - 1], mb = B[nb - 1];
+                if (ma <= mb) { i = na; j = (ma == mb) ? nb : lower_bound_u64(B, nb, ma + 1ULL); }
+                else { j = nb; i = lower_bound_u64(A, na, mb + 1ULL); }
+                if (scaled) { i = max(i, lower_bound_u64(A, na, max_hash)); j = max(j, lower_bound_u64(B, nb, max_hash)); }
+                const uint32_t total = i - c + j;
+                const double jac = total == 0u ? 1.0 : (double)c / (double)total;      // distance.rs:119-125
+                if ((cut.skip_self && q == r) || !(cut.jlow < 0.0 || jac >= cut.jlow)) continue;
+                const uint32_t idx = atomicAdd(cut.counter, 1u);
+                if (idx < cut.cap) {
+                    fb2_pair_hit h; h.q = q; h.r = r; h.common = c; h.i = i; h.j = j;
+                    cut.hits[idx] = h;
+                    cut.keys[idx] = ((unsigned long long)q << 32) | r;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+void launch_postings_fill(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk,
+                          const uint32_t *off, unsigned long long *keys, uint32_t *vals, cudaStream_t s) {
+    if (!n_sk) return;
+    postings_fill_kernel<<<(unsigned)(((uint64_t)n_sk * 32 + 255) / 256), 256, 0, s>>>(hashes, lens, stride, n_sk, off, keys, vals);
+}
+void launch_postings_runs(const unsigned long long *keys, const uint32_t *vals, uint32_t n, const uint32_t *off, uint32_t n_sk,
+                          uint32_t *sorted_sk, unsigned long long *runinfo, unsigned long long *sum_sq, cudaStream_t s) {
+    if (!n) return;
+    postings_runs_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(keys, vals, n, off, n_sk, sorted_sk, runinfo, sum_sq);
+}
+// Column block of the counting kernel: as many sketches as 16-bit counters fit into the shared memory of an SM.
+uint32_t dist_inverted_block(uint32_t n_sk) {
+    const uint32_t most = 112u * 1024u;                   // 224 KiB of counters
+    if (const char *e = getenv("FB2_DIST_CB")) { const long v = atol(e); if (v >= 2 && v <= (long)most) return (uint32_t)v & ~1u; }
+    return std::min(most, (n_sk + 1u) & ~1u);
+}
+// Rows [q0, q1): survivors appended to hits / keys like launch_dist_tile_cut.  No sketch may be empty or longer than
+// 65535 hashes, jlow must be positive (the caller checks).  Returns -1 when the shared memory cannot be reserved.
+int launch_dist_inverted_cut(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
+                             uint32_t q1, const uint32_t *off, const uint32_t *sorted_sk, const unsigned long long *runinfo,
+                             int scaled, unsigned long long max_hash, fb2_pair_hit *hits, unsigned long long *keys,
+                             unsigned int *counter, uint32_t cap, int skip_self, double jlow, cudaStream_t s) {
+    if (q1 <= q0 || !n_sk) return 0;
+    const uint32_t cb = dist_inverted_block(n_sk);
+    const size_t smem = (size_t)cb * 2u;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        if (cudaFuncSetAttribute(dist_inverted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
+        attr_set[dev] = true;
+    }
+    DistCut c; c.hits = hits; c.keys = keys; c.counter = counter; c.cap = cap; c.skip_self = skip_self; c.jlow = jlow;
+    dist_inverted_kernel<<<q1 - q0, DI_THREADS, smem, s>>>(hashes, lens, stride, n_sk, q0, off, sorted_sk, runinfo, cb, scaled, max_hash, c);
+    return 0;
 }
 // hits[order[i]] -> sorted[i]
 __global__ void gather_hits_kernel(const fb2_pair_hit *__restrict__ hits, const uint32_t *__restrict__ order, uint32_t n,

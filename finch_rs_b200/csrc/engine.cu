@@ -2193,6 +2193,7 @@ extern "C" int fb2_sketcher_enable_timing(fb2_sketcher *s, int on) {
 }
 
 // ---- dist --------------------------------------------------------------------------------------------
+static cudaError_t upload_large(void *dst, const void *src, size_t bytes);   // below
 static unsigned long long dist_max_hash(double scale) {
     // distance.rs:100: u64::MAX / scale.recip() as u64
     const double rec = 1.0 / scale;
@@ -2207,7 +2208,7 @@ static int dist_common(const uint64_t *hashes, const uint32_t *lens, size_t n_sk
     if (device >= 0) CU(cudaSetDevice(device));   // (the callers hold a DeviceScope)
     TRY(d_h.ensure(std::max<size_t>(8, n_sk * stride * 8)));
     TRY(d_l.ensure(std::max<size_t>(4, n_sk * 4)));
-    CU(cudaMemcpy(d_h.p, hashes, n_sk * stride * 8, cudaMemcpyHostToDevice));
+    CU(upload_large(d_h.p, hashes, n_sk * stride * 8));
     CU(cudaMemcpy(d_l.p, lens, n_sk * 4, cudaMemcpyHostToDevice));
     return FB2_OK;
 }
@@ -2277,6 +2278,43 @@ extern "C" int fb2_dist_batch(const uint64_t *hashes, const uint32_t *lens, size
     return rc;
 }
 static thread_local double g_dist_kernel_ms = 0.0;
+
+// Host (pageable) -> device for the large inputs of the dist calls.  A plain cudaMemcpy stages pageable memory through
+// the driver's own bounce buffer on ONE thread (~10 GB/s: 80 ms for the 800 MB matrix of C5); here four threads each
+// own a pinned 8 MiB buffer and a stream and copy their share of the pieces, so the link and the host copies overlap.
+static cudaError_t upload_large(void *dst, const void *src, size_t bytes) {
+    const size_t piece = (size_t)8 << 20;
+    if (bytes < 8 * piece || getenv("FB2_NO_STAGED_UPLOAD")) return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    const unsigned T = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<size_t> next{0};
+    std::atomic<int> err{(int)cudaSuccess};
+    const size_t n_pieces = (bytes + piece - 1) / piece;
+    auto work = [&](unsigned t) {
+        if (t) cudaSetDevice(dev);
+        uint8_t *pin = nullptr;
+        cudaStream_t st = nullptr;
+        cudaError_t e = cudaHostAlloc((void **)&pin, piece, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        while (e == cudaSuccess) {
+            const size_t q = next.fetch_add(1);
+            if (q >= n_pieces) break;
+            const size_t off = q * piece, n = std::min(piece, bytes - off);
+            memcpy(pin, (const char *)src + off, n);
+            e = cudaMemcpyAsync((char *)dst + off, pin, n, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the buffer is reused right away
+        }
+        if (e != cudaSuccess) err.store((int)e);
+        if (st) cudaStreamDestroy(st);
+        if (pin) cudaFreeHost(pin);
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    return (cudaError_t)err.load();
+}
 extern "C" double fb2_dist_last_kernel_ms(void) { return g_dist_kernel_ms; }
 
 extern "C" int fb2_dist_all_pairs(const uint64_t *hashes, const uint32_t *lens, size_t n_sk, size_t stride,
@@ -2398,10 +2436,25 @@ static bool host_passes_cut(const fb2_pair_out &o, double jlow) {
     const double jac = total == 0u ? 1.0 : (double)o.common / (double)total;
     return jlow < 0.0 || jac >= jlow;
 }
+// Where the surviving pairs of a row block go: straight into the caller's array when one GPU does all rows (they
+// arrive in final order), else into a vector of the block that is placed once the blocks before it are known.
+struct HitSink {
+    fb2_pair_hit *dst = nullptr;
+    size_t cap = 0;
+    uint64_t n = 0;                       // hits seen (may exceed cap: the caller then reports the count)
+    std::vector<fb2_pair_hit> vec;
+    void append(const fb2_pair_hit *p, size_t k) {
+        if (dst) {
+            if (n < cap) memcpy(dst + n, p, std::min<size_t>(k, cap - (size_t)n) * sizeof(fb2_pair_hit));
+        } else vec.insert(vec.end(), p, p + k);
+        n += k;
+    }
+    void push(const fb2_pair_hit &h) { append(&h, 1); }
+};
 // Rows [qa, qb) against all n_sk sketches on the current device; d_h / d_l hold the matrix.  Hits ascending by (q, r).
 static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, const uint32_t *lens, size_t n_sk, size_t stride,
                          int scaled, unsigned long long max_hash, size_t qa, size_t qb, int skip_self, double jlow,
-                         std::vector<fb2_pair_hit> &out, double *kernel_ms) {
+                         HitSink &out, double *kernel_ms) {
     if (qb <= qa || !n_sk) return FB2_OK;
     uint32_t max_qlen = 0;
     for (size_t q = qa; q < qb; ++q) max_qlen = std::max(max_qlen, lens[q]);
@@ -2426,16 +2479,93 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
     size_t pin_cap = 0;
     double kms = 0.0;
     std::vector<fb2_pair_out> h_dense;
+    // The cut through an inverted index (dist.cu): when a positive jaccard bound rules out every pair without a common
+    // hash, large jobs count shared hashes per query from sorted (hash, sketch) postings instead of probing every pair.
+    // Chosen when it is applicable (no empty sketch: an empty one has jaccard 1 with everything, distance.rs:119-123;
+    // lengths fit the 16-bit counters) and its work -- the sum of squared posting-run lengths -- is far below the
+    // pairs x hashes of the tile kernel.  FB2_DIST_INVERTED=0 / 1 forbids / forces it (where applicable).
+    bool inverted = false;
+    DevBuf p_keys, p_vals, p_tkeys, p_tvals, p_hist, p_off, p_sk, p_run, p_sum;
+    {
+        const char *inv_env = getenv("FB2_DIST_INVERTED");
+        const bool forbid = inv_env && atoi(inv_env) == 0, force = inv_env && atoi(inv_env) != 0;
+        uint64_t n_post = 0;
+        uint32_t min_len = ~0u, max_len = 0;
+        for (size_t i = 0; i < n_sk; ++i) { n_post += lens[i]; min_len = std::min(min_len, lens[i]); max_len = std::max(max_len, lens[i]); }
+        const double pairs = (double)(qb - qa) * (double)n_sk;
+        size_t mem_free = 0, mem_total = 0;
+        if (cudaMemGetInfo(&mem_free, &mem_total) != cudaSuccess) mem_free = 0;
+        const bool fits = (double)n_post * 44.0 < (double)mem_free * 0.7;     // postings, their sort buffers, run table
+        if (!forbid && jlow > 0.0 && min_len > 0 && max_len <= 65535u && n_post < 0xFFFFFF00ull && n_sk < 0x7FFFFFFFull && fits &&
+            (force || pairs >= 2e8)) {
+            std::vector<uint32_t> off(n_sk + 1);
+            uint64_t run = 0;
+            for (size_t i = 0; i < n_sk; ++i) { off[i] = (uint32_t)run; run += lens[i]; }
+            off[n_sk] = (uint32_t)run;
+            const uint32_t np = (uint32_t)n_post;
+            if ((rc = p_keys.ensure((size_t)np * 8 + 512)) == FB2_OK && (rc = p_tkeys.ensure((size_t)np * 8 + 512)) == FB2_OK &&
+                (rc = p_vals.ensure((size_t)np * 4 + 256)) == FB2_OK && (rc = p_tvals.ensure((size_t)np * 4 + 256)) == FB2_OK &&
+                (rc = p_hist.ensure((size_t)radix_hist_words(np) * 4)) == FB2_OK && (rc = p_off.ensure((n_sk + 1) * 4)) == FB2_OK &&
+                (rc = p_sk.ensure((size_t)np * 4)) == FB2_OK && (rc = p_run.ensure((size_t)np * 8)) == FB2_OK &&
+                (rc = p_sum.ensure(8)) == FB2_OK) {
+                unsigned long long sum_sq = 0;
+                cu(cudaMemcpyAsync(p_off.p, off.data(), (n_sk + 1) * 4, cudaMemcpyHostToDevice, st));
+                cu(cudaMemsetAsync(p_sum.p, 0, 8, st));
+                cu(cudaEventRecord(e0, st));
+                launch_postings_fill(d_h, d_l, (uint32_t)stride, (uint32_t)n_sk, p_off.as<uint32_t>(), p_keys.as<unsigned long long>(),
+                                     p_vals.as<uint32_t>(), st);
+                launch_radix_sort(p_keys.as<unsigned long long>(), p_vals.as<uint32_t>(), p_tkeys.as<unsigned long long>(),
+                                  p_tvals.as<uint32_t>(), np, p_hist.as<uint32_t>(), st);
+                launch_postings_runs(p_keys.as<unsigned long long>(), p_vals.as<uint32_t>(), np, p_off.as<uint32_t>(), (uint32_t)n_sk,
+                                     p_sk.as<uint32_t>(), p_run.as<unsigned long long>(), p_sum.as<unsigned long long>(), st);
+                cu(cudaEventRecord(e1, st));
+                cu(cudaMemcpyAsync(&sum_sq, p_sum.p, 8, cudaMemcpyDeviceToHost, st));
+                cu(cudaStreamSynchronize(st));
+                if (rc == FB2_OK) {
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) kms += ms;
+                    // bumps of the counting pass (all rows) against probes of the tile kernel (all rows), with a margin
+                    inverted = force || (double)sum_sq * 8.0 < (double)n_sk * (double)n_post;
+                    if (getenv("FB2_TRACE_DIST"))
+                        fprintf(stderr, "dist: %u postings, sum of squared runs %.3e vs %.3e probes: %s (index %.1f ms)\n", np,
+                                (double)sum_sq, (double)n_sk * (double)n_post, inverted ? "inverted index" : "tile kernel", ms);
+                }
+                // what the counting kernel does not read
+                p_keys.release(); p_vals.release(); p_tkeys.release(); p_tvals.release(); p_hist.release();
+                if (!inverted) { p_sk.release(); p_run.release(); }
+            }
+            if (rc != FB2_OK) {   // (e.g. out of device memory after all): the tile kernel does the job
+                inverted = false;
+                p_keys.release(); p_vals.release(); p_tkeys.release(); p_tvals.release(); p_hist.release(); p_off.release();
+                p_sk.release(); p_run.release(); p_sum.release();
+                cudaGetLastError();
+                rc = FB2_OK;
+            }
+        }
+        if (inverted) rows = env_size("FB2_DIST_ROWS", 16384);
+    }
+    const bool trace_rows = getenv("FB2_TRACE_DIST") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_wait = 0.0, t_sortcopy = 0.0, t_insert = 0.0, t_alloc = 0.0;
     for (size_t q = qa; q < qb && rc == FB2_OK;) {
         const size_t m = std::min(rows, qb - q);
-        if (tiled) {
+        if (tiled || inverted) {
+            double t0 = now_ms();
             if ((rc = hits.ensure((size_t)cap * sizeof(fb2_pair_hit))) != FB2_OK) break;
             if ((rc = sorted.ensure((size_t)cap * sizeof(fb2_pair_hit))) != FB2_OK) break;
             if ((rc = keys.ensure((size_t)cap * 8 + 512)) != FB2_OK || (rc = tkeys.ensure((size_t)cap * 8 + 512)) != FB2_OK) break;
             if ((rc = vals.ensure((size_t)cap * 4 + 256)) != FB2_OK || (rc = tvals.ensure((size_t)cap * 4 + 256)) != FB2_OK) break;
             if ((rc = hist.ensure((size_t)radix_hist_words(cap) * 4)) != FB2_OK) break;
+            t_alloc += now_ms() - t0; t0 = now_ms();
             cu(cudaMemsetAsync(counter.p, 0, sizeof(unsigned int), st));
             cu(cudaEventRecord(e0, st));
+            if (inverted) {
+                if (launch_dist_inverted_cut(d_h, d_l, (uint32_t)stride, (uint32_t)n_sk, (uint32_t)q, (uint32_t)(q + m), p_off.as<uint32_t>(),
+                                             p_sk.as<uint32_t>(), p_run.as<unsigned long long>(), scaled, max_hash, hits.as<fb2_pair_hit>(),
+                                             keys.as<unsigned long long>(), counter.as<unsigned int>(), cap, skip_self, jlow, st) != 0) {
+                    rc = fb2_fail(FB2_ECUDA, "dist_inverted_kernel: could not reserve shared memory"); break;
+                }
+            } else
             if (launch_dist_tile_cut(d_h, d_l, (uint32_t)stride, (uint32_t)n_sk, (uint32_t)q, (uint32_t)(q + m), scaled, max_hash,
                                      hits.as<fb2_pair_hit>(), keys.as<unsigned long long>(), counter.as<unsigned int>(), cap, skip_self,
                                      jlow, st) != 0) { rc = fb2_fail(FB2_ECUDA, "dist_tile_kernel: could not reserve shared memory"); break; }
@@ -2444,8 +2574,10 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
             cu(cudaStreamSynchronize(st));
             if (rc != FB2_OK) break;
             const unsigned int n = *h_cnt;
+            t_wait += now_ms() - t0; t0 = now_ms();
             if (n > cap) {                       // more survivors than the buffer holds: fewer rows, then a larger buffer
-                if (m > 9) { rows = std::max<size_t>(9, (m / 2 + 8) / 9 * 9); continue; }
+                if (m > 9) { rows = inverted ? std::max<size_t>(1, m / 2) : std::max<size_t>(9, (m / 2 + 8) / 9 * 9); continue; }
+                if (inverted && m > 1) { rows = std::max<size_t>(1, m / 2); continue; }
                 if (cap >= (1u << 30)) { rc = fb2_fail(FB2_ENOMEM, "dist: too many surviving pairs for one query tile"); break; }
                 cap <<= 1;
                 continue;
@@ -2467,7 +2599,9 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
                 cu(cudaMemcpyAsync(h_pin, sorted.p, (size_t)n * sizeof(fb2_pair_hit), cudaMemcpyDeviceToHost, st));
                 cu(cudaStreamSynchronize(st));
                 if (rc != FB2_OK) break;
-                out.insert(out.end(), h_pin, h_pin + n);
+                t_sortcopy += now_ms() - t0; t0 = now_ms();
+                out.append(h_pin, n);
+                t_insert += now_ms() - t0;
             }
         } else {                                 // sketches longer than the tile kernel takes: dense slab, cut on the host
             const uint64_t np = (uint64_t)m * n_sk;
@@ -2485,12 +2619,15 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
                 for (size_t r = 0; r < n_sk; ++r) {
                     const fb2_pair_out &o = h_dense[a * n_sk + r];
                     if ((skip_self && q + a == r) || !host_passes_cut(o, jlow)) continue;
-                    out.push_back(fb2_pair_hit{(uint32_t)(q + a), (uint32_t)r, o.common, o.i, o.j});
+                    out.push(fb2_pair_hit{(uint32_t)(q + a), (uint32_t)r, o.common, o.i, o.j});
                 }
         }
         q += m;
     }
     if (kernel_ms) *kernel_ms = kms;
+    if (trace_rows)
+        fprintf(stderr, "dist rows [%zu, %zu): buffers %.1f ms, kernel + wait %.1f ms, hit sort + D2H %.1f ms, append %.1f ms\n", qa, qb,
+                t_alloc, t_wait, t_sortcopy, t_insert);
     if (h_pin) cudaFreeHost(h_pin);
     if (h_cnt) cudaFreeHost(h_cnt);
     if (e0) cudaEventDestroy(e0);
@@ -2498,6 +2635,8 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
     if (st) cudaStreamDestroy(st);
     hits.release(); sorted.release(); keys.release(); tkeys.release(); vals.release(); tvals.release(); hist.release();
     counter.release(); dense.release();
+    p_keys.release(); p_vals.release(); p_tkeys.release(); p_tvals.release(); p_hist.release(); p_off.release(); p_sk.release();
+    p_run.release(); p_sum.release();
     return rc;
 }
 
@@ -2520,11 +2659,16 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
         devs.push_back(d);
     } else for (int d = 0; d < (ngpus <= 0 ? ndev : std::min(ngpus, ndev)); ++d) devs.push_back(d);
     const size_t G = std::min<size_t>(devs.size(), std::max<size_t>(1, (q1 - q0 + 8) / 9));
+    const bool trace = getenv("FB2_TRACE_DIST") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now_ms();
+    std::vector<double> t_up(G, 0.0), t_rows(G, 0.0);
     const int scaled = scale > 0.0;
     const unsigned long long max_hash = scaled ? dist_max_hash(scale) : 0;
     const double jlow = dist_cut_jlow(max_distance, kmer_length);
     const size_t mat_bytes = std::max<size_t>(8, n_sk * stride * 8), len_bytes = std::max<size_t>(4, n_sk * 4);
-    std::vector<std::vector<fb2_pair_hit>> found(G);
+    std::vector<HitSink> found(G);
+    if (G == 1) { found[0].dst = hits; found[0].cap = cap; }
     std::vector<int> rcs(G, FB2_OK);
     std::vector<std::string> msgs(G);
     std::vector<double> kms(G, 0.0);
@@ -2542,7 +2686,7 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
             if (cudaSetDevice(devs[g]) != cudaSuccess) { r = fb2_fail(FB2_ECUDA, "cudaSetDevice failed"); break; }
             if ((r = d_h[g].ensure(mat_bytes)) != FB2_OK || (r = d_l[g].ensure(len_bytes)) != FB2_OK) break;
             if (g == 0) {
-                cudaError_t e = cudaMemcpy(d_h[0].p, hashes, n_sk * stride * 8, cudaMemcpyHostToDevice);
+                cudaError_t e = upload_large(d_h[0].p, hashes, n_sk * stride * 8);
                 if (e == cudaSuccess) e = cudaMemcpy(d_l[0].p, lens, n_sk * 4, cudaMemcpyHostToDevice);
                 if (e != cudaSuccess) r = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
                 { std::lock_guard<std::mutex> lk(mu); src_ready = r == FB2_OK ? 1 : -1; }
@@ -2557,8 +2701,10 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
                 if (r != FB2_OK) break;
             }
             const size_t qa = std::min(q1, q0 + g * per), qb = std::min(q1, qa + per);
+            t_up[g] = now_ms();
             r = dist_cut_rows(d_h[g].as<unsigned long long>(), d_l[g].as<uint32_t>(), lens, n_sk, stride, scaled, max_hash, qa, qb,
                               skip_self, jlow, found[g], &kms[g]);
+            t_rows[g] = now_ms();
         } while (0);
         if (g == 0 && src_ready == 0) { { std::lock_guard<std::mutex> lk(mu); src_ready = -1; } cv.notify_all(); }
         rcs[g] = r;
@@ -2578,13 +2724,18 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
     uint64_t total = 0;
     double kmax = 0.0;
     for (size_t g = 0; g < G; ++g) {
-        const size_t room = total < cap ? cap - (size_t)total : 0, n = std::min(room, found[g].size());
-        if (n) memcpy(hits + total, found[g].data(), n * sizeof(fb2_pair_hit));
-        total += found[g].size();
+        if (!found[g].dst) {
+            const size_t room = total < cap ? cap - (size_t)total : 0, n = std::min(room, found[g].vec.size());
+            if (n) memcpy(hits + total, found[g].vec.data(), n * sizeof(fb2_pair_hit));
+        }
+        total += found[g].n;
         kmax = std::max(kmax, kms[g]);
     }
     g_dist_kernel_ms = kmax;     // the slowest GPU's summed kernel time
     *n_hits = total;
+    if (trace)
+        fprintf(stderr, "dist: matrix on GPU 0 after %.1f ms, its rows done after %.1f ms (kernels %.1f ms), everything after %.1f ms\n",
+                t_up[0] - t_begin, t_rows[0] - t_begin, kms[0], now_ms() - t_begin);
     if (total > cap) return fb2_fail(FB2_ENOMEM, "dist: " + std::to_string(total) + " surviving pairs, room for " + std::to_string(cap));
     return FB2_OK;
 }

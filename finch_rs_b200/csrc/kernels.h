@@ -92,6 +92,16 @@ void launch_minmer_matrix(const unsigned long long *ref, uint32_t n_ref, const u
                           const unsigned long long *sk_off, uint32_t n_sk, uint32_t max_len, int32_t *result, cudaStream_t s);
 void launch_iota(uint32_t *v, uint32_t n, cudaStream_t s);
 void launch_gather_hits(const fb2_pair_hit *hits, const uint32_t *order, uint32_t n, fb2_pair_hit *sorted, cudaStream_t s);
+// the cut through an inverted index over all (hash, sketch) postings (dist.cu)
+void launch_postings_fill(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk,
+                          const uint32_t *off, unsigned long long *keys, uint32_t *vals, cudaStream_t s);
+void launch_postings_runs(const unsigned long long *keys, const uint32_t *vals, uint32_t n, const uint32_t *off, uint32_t n_sk,
+                          uint32_t *sorted_sk, unsigned long long *runinfo, unsigned long long *sum_sq, cudaStream_t s);
+uint32_t dist_inverted_block(uint32_t n_sk);
+int launch_dist_inverted_cut(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk, uint32_t q0,
+                             uint32_t q1, const uint32_t *off, const uint32_t *sorted_sk, const unsigned long long *runinfo,
+                             int scaled, unsigned long long max_hash, fb2_pair_hit *hits, unsigned long long *keys,
+                             unsigned int *counter, uint32_t cap, int skip_self, double jlow, cudaStream_t s);
 void launch_dist_all(const unsigned long long *hashes, const uint32_t *lens, uint32_t stride, uint32_t n_sk,
                      uint32_t q0, uint64_t n_pairs, int scaled, unsigned long long max_hash, fb2_pair_out *out,
                      cudaStream_t s);

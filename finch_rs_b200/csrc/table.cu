@@ -9,6 +9,7 @@
 // The admission threshold only ever decreases, so a key that survives to the result was never
 // rejected or purged and its totals are complete.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "device_types.cuh"
 
@@ -374,6 +375,124 @@ radix_scatter_kernel(const unsigned long long *__restrict__ keys, const uint32_t
     }
 }
 
+// ---- the same sort for LARGE inputs: one block per tile of 4096 keys -------------------------------
+// The warp-per-segment scatter above writes every key to its own place (32 lanes, up to 32 digits: 8-byte writes all
+// over the output); fine for a table's worth of keys, 19 ms per pass for the 10^8 postings of `dist` (dist.cu).  Here a
+// block first orders its tile by digit in shared memory (stable: warps own consecutive sub-segments, lanes rank by
+// match_any as above) and then writes it out digit by digit, so that consecutive threads write consecutive addresses
+// (runs of ~16 keys per digit); the offsets come from a per-digit scan over the tiles (one block per digit).
+constexpr uint32_t RT_TILE = 4096, RT_THREADS = 256, RT_WARPS = RT_THREADS / 32, RT_SUB = RT_TILE / RT_WARPS, RT_IT = RT_SUB / 32;
+constexpr uint32_t RT_SMEM = RT_TILE * 8u + RT_TILE * 4u + RT_WARPS * 256u * 4u + 256u * 4u * 2u + 64u;
+
+__global__ void __launch_bounds__(RT_THREADS)
+radix_tile_hist_kernel(const unsigned long long *__restrict__ keys, uint32_t n, int shift, uint32_t n_tiles,
+                       uint32_t *__restrict__ hist /* [256][n_tiles] */) {
+    __shared__ uint32_t h[RT_WARPS][256];
+    const uint32_t tid = threadIdx.x, w = tid >> 5;
+    for (uint32_t i = tid; i < RT_WARPS * 256u; i += RT_THREADS) (&h[0][0])[i] = 0u;
+    __syncthreads();
+    const uint32_t tile = blockIdx.x, a = tile * RT_TILE, b = min(a + RT_TILE, n);
+    for (uint32_t i = a + tid; i < b; i += RT_THREADS) atomicAdd(&h[w][(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t x = 0; x < RT_WARPS; ++x) c += h[x][tid];
+    hist[tid * n_tiles + tile] = c;
+}
+// block d: exclusive scan of digit d's counts over the tiles (in place), its total to totals[d]
+__global__ void __launch_bounds__(1024) radix_tile_scan_kernel(uint32_t *hist, uint32_t n_tiles, uint32_t *__restrict__ totals) {
+    __shared__ uint32_t part[1024];
+    const uint32_t tid = threadIdx.x;
+    uint32_t *row = hist + (size_t)blockIdx.x * n_tiles;
+    const uint32_t G = (n_tiles + 1023u) / 1024u;
+    const uint32_t a = min(tid * G, n_tiles), b = min(a + G, n_tiles);
+    uint32_t s = 0;
+    for (uint32_t i = a; i < b; ++i) s += row[i];
+    part[tid] = s;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        const uint32_t v = tid >= d ? part[tid - d] : 0u;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[tid] - s;
+    for (uint32_t i = a; i < b; ++i) { const uint32_t v = row[i]; row[i] = run; run += v; }
+    if (tid == 1023u) totals[blockIdx.x] = part[1023];
+}
+// exclusive scan of one value per thread over the 256 threads of a block
+__device__ __forceinline__ uint32_t block_exscan_256(uint32_t v, uint32_t *tmp /* RT_WARPS + 1 words */) {
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+    __syncthreads();                       // tmp may still be read from a previous call
+    if (lane == 31u) tmp[w] = x;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < RT_WARPS; ++i) if (i < w) base += tmp[i];
+    return base + x - v;
+}
+__global__ void __launch_bounds__(RT_THREADS)
+radix_tile_scatter_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n, int shift,
+                          uint32_t n_tiles, const uint32_t *__restrict__ hist, const uint32_t *__restrict__ totals,
+                          unsigned long long *__restrict__ okeys, uint32_t *__restrict__ ovals) {
+    extern __shared__ __align__(16) uint8_t rt_smem[];
+    unsigned long long *sk = reinterpret_cast<unsigned long long *>(rt_smem);
+    uint32_t *sv = reinterpret_cast<uint32_t *>(rt_smem + RT_TILE * 8u);
+    uint32_t *cnt = sv + RT_TILE;                       // [RT_WARPS][256]: counts, then the running offset of (warp, digit)
+    uint32_t *dbase = cnt + RT_WARPS * 256u;            // [256] first tile-local position of a digit
+    uint32_t *gbase = dbase + 256u;                     // [256] global position of the tile's first key of a digit
+    uint32_t *tmp = gbase + 256u;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const uint32_t tile = blockIdx.x, a = tile * RT_TILE, nt = min(RT_TILE, n - a);
+    for (uint32_t i = tid; i < RT_WARPS * 256u; i += RT_THREADS) cnt[i] = 0u;
+    __syncthreads();
+    unsigned long long k[RT_IT];
+    uint32_t v[RT_IT];
+#pragma unroll
+    for (uint32_t it = 0; it < RT_IT; ++it) {
+        const uint32_t idx = w * RT_SUB + it * 32u + lane;
+        const bool in = idx < nt;
+        k[it] = in ? keys[a + idx] : 0ULL;
+        v[it] = in ? vals[a + idx] : 0u;
+        if (in) atomicAdd(&cnt[w * 256u + ((uint32_t)(k[it] >> shift) & 255u)], 1u);
+    }
+    __syncthreads();
+    {   // thread = digit
+        uint32_t run = 0;
+#pragma unroll
+        for (uint32_t x = 0; x < RT_WARPS; ++x) { const uint32_t c = cnt[x * 256u + tid]; cnt[x * 256u + tid] = run; run += c; }
+        const uint32_t local = block_exscan_256(run, tmp);
+        const uint32_t gstart = block_exscan_256(totals[tid], tmp);
+        dbase[tid] = local;
+        gbase[tid] = gstart + hist[tid * n_tiles + tile];
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t it = 0; it < RT_IT; ++it) {
+        const uint32_t idx = w * RT_SUB + it * 32u + lane;
+        const bool in = idx < nt;
+        const uint32_t d = (uint32_t)(k[it] >> shift) & 255u;
+        const uint32_t act = __ballot_sync(0xffffffffu, in);
+        const uint32_t peers = __match_any_sync(0xffffffffu, in ? d : (256u + lane)) & act;
+        uint32_t p = 0;
+        if (in) p = dbase[d] + cnt[w * 256u + d] + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (in && (int)lane == (31 - __clz(peers))) cnt[w * 256u + d] += __popc(peers);   // one writer per digit
+        __syncwarp();
+        if (in) { sk[p] = k[it]; sv[p] = v[it]; }
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < nt; p += RT_THREADS) {
+        const unsigned long long key = sk[p];
+        const uint32_t d = (uint32_t)(key >> shift) & 255u, dst = gbase[d] + (p - dbase[d]);
+        okeys[dst] = key;
+        ovals[dst] = sv[p];
+    }
+}
+
 // ---- bucket + rank sort for (nearly) uniform keys ------------------------------------------------
 // Sketch keys are murmur hashes below a known threshold, i.e. uniform: 4096 buckets on the top bits
 // hold ~n/4096 keys each, and a block ranks one bucket in shared memory by counting.  4 launches
@@ -632,10 +751,32 @@ void launch_gather(TableView t, SketchState *st, unsigned long long *keys, uint3
 void launch_radix_sort(unsigned long long *keys, uint32_t *vals, unsigned long long *tkeys, uint32_t *tvals,
                        uint32_t n, uint32_t *hist, cudaStream_t s) {
     if (n < 2) return;
-    const uint32_t n_segs = cdiv(n, SORT_SEG);
-    const uint32_t blocks = cdiv(n_segs, SORT_WARPS);
     unsigned long long *ka = keys, *kb = tkeys;
     uint32_t *va = vals, *vb = tvals;
+    if (n >= (1u << 18) && !getenv("FB2_RADIX_V1")) {   // large: tiles ordered in shared memory, coalesced output
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        bool ok = true;
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            ok = cudaFuncSetAttribute(radix_tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM) == cudaSuccess;
+            attr_set[dev] = ok;
+        }
+        if (ok) {
+            const uint32_t n_tiles = cdiv(n, RT_TILE);
+            uint32_t *totals = hist + (size_t)256u * n_tiles;          // (radix_hist_words leaves room)
+            for (int pass = 0; pass < 8; ++pass) {
+                radix_tile_hist_kernel<<<n_tiles, RT_THREADS, 0, s>>>(ka, n, pass * 8, n_tiles, hist);
+                radix_tile_scan_kernel<<<256, 1024, 0, s>>>(hist, n_tiles, totals);
+                radix_tile_scatter_kernel<<<n_tiles, RT_THREADS, RT_SMEM, s>>>(ka, va, n, pass * 8, n_tiles, hist, totals, kb, vb);
+                unsigned long long *tk = ka; ka = kb; kb = tk;
+                uint32_t *tv = va; va = vb; vb = tv;
+            }
+            return;
+        }
+    }
+    const uint32_t n_segs = cdiv(n, SORT_SEG);
+    const uint32_t blocks = cdiv(n_segs, SORT_WARPS);
     for (int pass = 0; pass < 8; ++pass) {
         radix_hist_kernel<<<blocks, SORT_WARPS * 32, 0, s>>>(ka, n, pass * 8, n_segs, hist);
         radix_scan_kernel<<<1, 1024, 0, s>>>(hist, 256u * n_segs);
@@ -668,7 +809,7 @@ void launch_bucket_sort(const unsigned long long *keys, const uint32_t *vals, un
     bucket_rank_kernel<<<PRUNE_BINS, 128, 0, s>>>(tkeys, tvals, offs, bins, okeys, ovals);
 }
 uint32_t bucket_cap() { return BUCKET_CAP; }
-uint32_t radix_hist_words(uint32_t n) { return 256u * cdiv(n ? n : 1, SORT_SEG); }
+uint32_t radix_hist_words(uint32_t n) { return 256u * cdiv(n ? n : 1, SORT_SEG) + 256u; }   // (+ the tile path's digit totals)
 
 void launch_select_rows(const uint32_t *idx, uint32_t m, int k, uint32_t stride, uint32_t kw, const unsigned long long *i_hash,
                         const uint32_t *i_cnt, const uint32_t *i_ext, const unsigned long long *i_kmer,

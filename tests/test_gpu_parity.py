@@ -976,6 +976,55 @@ def test_dist_all_pairs_cut(fb, synth, oracle, monkeypatch, scale):
     assert {(int(h["q"]), int(h["r"])) for h, m in zip(hits, md) if m <= 0.1} == want and len(want) >= 2
 
 
+@pytest.mark.parametrize("scale", [0.0, 0.5])
+@pytest.mark.parametrize("cb", ["", "64", "250"])
+def test_dist_cut_through_inverted_index(fb, synth, monkeypatch, scale, cb):
+    """The cut's second engine (sorted (hash, sketch) postings, 16-bit counters per query block) returns exactly what the
+    tile kernel returns: same hits, same (common, i, j), same order; column blocks smaller than the collection, ragged
+    lengths (incl. > 1023 hashes, which the tile kernel cannot take), row sub-ranges, tiny hit buffers, skip_self off."""
+    n = 500
+    mat = synth.synth_sketches(n, 1000, 6, 5)
+    lens = np.full(n, 1000, np.uint32)
+    lens[11] = 3; lens[12] = 1; lens[400] = 999
+    if scale:
+        mat = mat >> np.uint64(8)
+        assert np.all(np.diff(mat.astype(np.int64), axis=1) > 0)
+    if cb:
+        monkeypatch.setenv("FB2_DIST_CB", cb)
+    dense = fb.dist_all_pairs(mat, lens, scale)
+    k = 21
+    for max_d, rows, (q0, q1), skip in ((0.05, "27", (0, n), True), (0.3, "9", (100, 350), True), (0.6, "", (0, n), False)):
+        if rows:
+            monkeypatch.setenv("FB2_DIST_ROWS", rows)
+        else:
+            monkeypatch.delenv("FB2_DIST_ROWS", raising=False)
+        monkeypatch.setenv("FB2_DIST_INVERTED", "0")
+        want = fb.dist_all_pairs_cut(mat, lens, k, max_d, scale, q0, q1, skip_self=skip, cap=64)
+        monkeypatch.setenv("FB2_DIST_INVERTED", "1")
+        got = fb.dist_all_pairs_cut(mat, lens, k, max_d, scale, q0, q1, skip_self=skip, cap=64)
+        assert len(got) == len(want) and len(want) > 0
+        assert np.array_equal(got, want)
+        for t in range(0, len(got), 7):
+            assert tuple(dense[got["q"][t], got["r"][t]]) == (got["common"][t], got["i"][t], got["j"][t])
+        if not skip:
+            assert np.any(got["q"] == got["r"])
+    # an empty sketch has jaccard 1 with everything (distance.rs:119-123): the index is not applicable, the answer the same
+    lens2 = lens.copy(); lens2[7] = 0
+    monkeypatch.setenv("FB2_DIST_INVERTED", "0")
+    want = fb.dist_all_pairs_cut(mat, lens2, k, 0.05, scale)
+    monkeypatch.setenv("FB2_DIST_INVERTED", "1")
+    assert np.array_equal(fb.dist_all_pairs_cut(mat, lens2, k, 0.05, scale), want)
+    # sketches longer than the tile kernel takes: the index handles them (the other engine falls back to dense slabs)
+    big = np.sort(np.random.default_rng(1).integers(0, 2**62, size=(12, 1500), dtype=np.uint64), axis=1)
+    big[5, :700] = big[4, :700]; big[5] = np.sort(big[5])
+    bl = np.full(12, 1500, np.uint32)
+    monkeypatch.setenv("FB2_DIST_INVERTED", "0")
+    want = fb.dist_all_pairs_cut(big, bl, 21, 0.1, 0.0)
+    monkeypatch.setenv("FB2_DIST_INVERTED", "1")
+    got = fb.dist_all_pairs_cut(big, bl, 21, 0.1, 0.0)
+    assert np.array_equal(got, want) and len(want) >= 2
+
+
 def test_distance_scaled_end_to_end(fb):  # distance.rs:312-337
     def mk():
         q = fb.ScaledSketcher(3, 0.001, 2, 42)
