@@ -459,7 +459,8 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
         uint8_t *bufs[2] = {buf, nullptr};
         if (cudaHostAlloc((void **)&bufs[1], piece, cudaHostAllocDefault) != cudaSuccess) rc = fb2_fail(FB2_ECUDA, "cudaHostAlloc failed (second read buffer)");
         const int fd = fileno(fp);
-        const unsigned T = (unsigned)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency() / 2));
+        unsigned T = (unsigned)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency() / 2));
+        if (const char *e = getenv("FB2_READ_THREADS")) { const long v = atol(e); if (v >= 1 && v <= 64) T = (unsigned)v; }
         auto read_piece = [&](uint8_t *dst, uint64_t off) -> long {      // bytes read, or -1
             std::vector<long> got(T, 0);
             const size_t each = (piece / T + 4095) & ~(size_t)4095;
