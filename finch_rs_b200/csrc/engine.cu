@@ -179,6 +179,7 @@ struct fb2_sketcher {
     // FB2_HOST_STRIP=1: FASTQ record framing on the host, only the sequence lines cross PCIe (strip.cpp)
     bool strip_on = false;               // active for the open stream
     bool polite = false;                 // waits yield / sleep instead of spinning (fb2_sketcher_set_polite_sync)
+    bool force_strip = false;            // the next FASTQ stream is framed on the host whatever FB2_HOST_STRIP says (mapped files)
     unsigned polite_copy = 0;            // > 0: raw host-to-device copies go in pieces of that many MiB, one in flight (see feed_host_chunks)
     std::atomic<int> *link_flag = nullptr;   // two-ended streams: copies of the host-framed handle in flight (it raises the flag,
     bool link_owner = false;                 // the raw handle waits for zero before every piece: the framed lines go first)
@@ -1126,7 +1127,7 @@ static int begin_stream(fb2_sketcher *s, const uint8_t *first, size_t n) {
     s->strip_on = false;
     if (s->format == FB2_FORMAT_FASTQ) {
         const char *e = getenv("FB2_HOST_STRIP");
-        if (e && *e == '1') {
+        if ((e && *e == '1') || s->force_strip) {
             s->strip_on = true;
             s->strip_threads = (unsigned)std::min<size_t>(64, std::max<size_t>(1, env_size("FB2_STRIP_THREADS", std::min(16u, std::max(1u, std::thread::hardware_concurrency())))));
             s->strip_carry.clear(); s->strip_off = 0;
@@ -1557,6 +1558,7 @@ int fb2_sketcher_end_range(fb2_sketcher *s, uint32_t *end_state, uint32_t *last_
 }
 void fb2_sketcher_set_polite_copy(fb2_sketcher *s, unsigned piece_mb) { if (s) s->polite_copy = piece_mb; }
 void fb2_sketcher_set_polite_sync(fb2_sketcher *s, int on) { if (s) s->polite = on != 0; }
+void fb2_sketcher_set_force_strip(fb2_sketcher *s, int on) { if (s) s->force_strip = on != 0; }
 void fb2_sketcher_set_link_flag(fb2_sketcher *s, std::atomic<int> *flag, int owner) { if (s) { s->link_flag = flag; s->link_owner = owner != 0; } }
 uint32_t fb2_sketcher_halo(const fb2_sketcher *s) { return s->halo; }
 int fb2_sketcher_device(const fb2_sketcher *s) { return s->device; }
@@ -2454,8 +2456,9 @@ struct HitSink {
 // Rows [qa, qb) against all n_sk sketches on the current device; d_h / d_l hold the matrix.  Hits ascending by (q, r).
 static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, const uint32_t *lens, size_t n_sk, size_t stride,
                          int scaled, unsigned long long max_hash, size_t qa, size_t qb, int skip_self, double jlow,
-                         HitSink &out, double *kernel_ms) {
-    if (qb <= qa || !n_sk) return FB2_OK;
+                         HitSink &out, double *kernel_ms, int *index_only = nullptr) {
+    // index_only (in: non-null = do the rows only if the inverted index is chosen; out: 1 = done, 0 = nothing done)
+    if (qb <= qa || !n_sk) { if (index_only) *index_only = 0; return FB2_OK; }
     uint32_t max_qlen = 0;
     for (size_t q = qa; q < qb; ++q) max_qlen = std::max(max_qlen, lens[q]);
     const bool tiled = max_qlen <= dist_tile_max_len() && !getenv("FB2_DIST_NO_TILE");
@@ -2543,6 +2546,18 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
             }
         }
         if (inverted) rows = env_size("FB2_DIST_ROWS", 16384);
+    }
+    if (index_only) {
+        *index_only = inverted ? 1 : 0;
+        if (!inverted) {
+            if (kernel_ms) *kernel_ms = kms;
+            if (h_cnt) cudaFreeHost(h_cnt);
+            if (e0) cudaEventDestroy(e0);
+            if (e1) cudaEventDestroy(e1);
+            if (st) cudaStreamDestroy(st);
+            counter.release(); p_off.release(); p_sum.release();
+            return rc;
+        }
     }
     const bool trace_rows = getenv("FB2_TRACE_DIST") != nullptr;
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -2686,9 +2701,11 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
             if (cudaSetDevice(devs[g]) != cudaSuccess) { r = fb2_fail(FB2_ECUDA, "cudaSetDevice failed"); break; }
             if ((r = d_h[g].ensure(mat_bytes)) != FB2_OK || (r = d_l[g].ensure(len_bytes)) != FB2_OK) break;
             if (g == 0) {
-                cudaError_t e = upload_large(d_h[0].p, hashes, n_sk * stride * 8);
-                if (e == cudaSuccess) e = cudaMemcpy(d_l[0].p, lens, n_sk * 4, cudaMemcpyHostToDevice);
-                if (e != cudaSuccess) r = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+                if (src_ready != 1) {   // (already there when the index was tried first)
+                    cudaError_t e = upload_large(d_h[0].p, hashes, n_sk * stride * 8);
+                    if (e == cudaSuccess) e = cudaMemcpy(d_l[0].p, lens, n_sk * 4, cudaMemcpyHostToDevice);
+                    if (e != cudaSuccess) r = fb2_fail(FB2_ECUDA, cudaGetErrorString(e));
+                }
                 { std::lock_guard<std::mutex> lk(mu); src_ready = r == FB2_OK ? 1 : -1; }
                 cv.notify_all();
                 if (r != FB2_OK) break;
@@ -2710,7 +2727,37 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
         rcs[g] = r;
         if (r != FB2_OK) msgs[g] = fb2_last_error();
     };
-    if (G == 1) work(0);
+    // Several GPUs: the inverted index (when it applies) does ALL rows on the first GPU in less time than it takes to
+    // hand the matrix to the others (C5: 0.2 s on one GPU; every GPU would have to sort all postings anyway).  Only when
+    // the index declines (dense collections, no positive bound, empty sketches) are the rows cut over the GPUs.
+    bool done_on_first = false;
+    if (G > 1 && jlow > 0.0 && !(getenv("FB2_DIST_INVERTED") && atoi(getenv("FB2_DIST_INVERTED")) == 0)) {
+        int r = FB2_OK;
+        do {
+            if (cudaSetDevice(devs[0]) != cudaSuccess) { r = fb2_fail(FB2_ECUDA, "cudaSetDevice failed"); break; }
+            if ((r = d_h[0].ensure(mat_bytes)) != FB2_OK || (r = d_l[0].ensure(len_bytes)) != FB2_OK) break;
+            cudaError_t e = upload_large(d_h[0].p, hashes, n_sk * stride * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(d_l[0].p, lens, n_sk * 4, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { r = fb2_fail(FB2_ECUDA, cudaGetErrorString(e)); break; }
+            src_ready = 1;
+            int only = 1;
+            HitSink direct;
+            direct.dst = hits; direct.cap = cap;
+            t_up[0] = now_ms();
+            r = dist_cut_rows(d_h[0].as<unsigned long long>(), d_l[0].as<uint32_t>(), lens, n_sk, stride, scaled, max_hash, q0, q1,
+                              skip_self, jlow, direct, &kms[0], &only);
+            t_rows[0] = now_ms();
+            if (r == FB2_OK && only) { found[0] = std::move(direct); done_on_first = true; }
+        } while (0);
+        if (r != FB2_OK) {
+            const std::string msg = fb2_last_error();
+            DeviceScope restore(-1);
+            cudaSetDevice(devs[0]); d_h[0].release(); d_l[0].release();
+            return fb2_fail(r, msg);
+        }
+    }
+    if (done_on_first) { /* nothing left */ }
+    else if (G == 1) work(0);
     else {
         std::vector<std::thread> th;
         for (size_t g = 0; g < G; ++g) th.emplace_back(work, g);

@@ -351,6 +351,39 @@ def test_sketch_files_gzip(fb, oracle, tmp_path):
     assert "gzip" in str(ei.value)
 
 
+@pytest.mark.parametrize("crlf", [False, True])
+def test_large_fastq_file_framed_from_the_mapping(fb, oracle, tmp_path, monkeypatch, crlf):
+    """Large plain FASTQ files are mapped and framed by the host cores straight from the page cache (FB2_BIG_FILE_KB
+    lowers "large" for the test): same sketch as the oracle and as the copying path, same errors for malformed files;
+    FASTA files of that size keep the parallel-read path."""
+    rng = np.random.default_rng(23)
+    fq = gen.fastq(rng, n_records=6000, min_len=30, max_len=250, crlf=crlf, final_newline=not crlf)
+    fa = gen.fasta(rng, n_records=4, max_len=300000, width=70)
+    bad = bytearray(fq)
+    cut = fq.index(b"\n+", len(fq) // 2)                  # drop a '+' line's first byte deep inside the file
+    del bad[cut + 1]
+    pq, pa, pb = tmp_path / "reads.fq", tmp_path / "genome.fa", tmp_path / "bad.fq"
+    pq.write_bytes(fq); pa.write_bytes(fa); pb.write_bytes(bytes(bad))
+    sp = fb.SketchParams.mash(3000, 200, True, 21, 0)
+    fp = fb.FilterParams(False, (None, None), 0.21, 0.1)
+    monkeypatch.setenv("FB2_BIG_FILE_KB", "64")
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FB2_FILE_MMAP", mode)
+        res[mode] = fb.sketch_files([str(pq), str(pa)], sp, fp)
+        with pytest.raises(fb.FinchError) as ei:
+            fb.sketch_files([str(pb)], sp, fp)
+        assert ei.value.code == fb.ERECORD, str(ei.value)
+    for data, a, b in zip((fq, fa), res["1"], res["0"]):
+        rc, osk = oracle.sketch_stream(data, oracle.mash_params(3000, 200, True, 21, 0), oracle.make_filter(False, (None, None), 0.21, 0.1))
+        assert rc == oracle.OK
+        for sk in (a, b):
+            assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+            assert np.array_equal(sk.extra_counts, osk["extras"])
+            assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+            assert [sk.kmers[i, :21].tobytes() for i in range(len(sk))] == osk["kmers"]
+
+
 def test_sketch_files_bz2_xz(fb, oracle, tmp_path):
     """bzip2 ("BZ") and xz (fd 37) input, decompressed on the host through the system's libbz2 / liblzma (loaded at
     first use); one stream each, as needletail's BzDecoder / XzDecoder read them; truncated streams are errors."""
