@@ -2506,6 +2506,7 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
             for (size_t i = 0; i < n_sk; ++i) { off[i] = (uint32_t)run; run += lens[i]; }
             off[n_sk] = (uint32_t)run;
             const uint32_t np = (uint32_t)n_post;
+            const double t_ix0 = getenv("FB2_TRACE_DIST") ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0;
             if ((rc = p_keys.ensure((size_t)np * 8 + 512)) == FB2_OK && (rc = p_tkeys.ensure((size_t)np * 8 + 512)) == FB2_OK &&
                 (rc = p_vals.ensure((size_t)np * 4 + 256)) == FB2_OK && (rc = p_tvals.ensure((size_t)np * 4 + 256)) == FB2_OK &&
                 (rc = p_hist.ensure((size_t)radix_hist_words(np) * 4)) == FB2_OK && (rc = p_off.ensure((n_sk + 1) * 4)) == FB2_OK &&
@@ -2530,8 +2531,9 @@ static int dist_cut_rows(const unsigned long long *d_h, const uint32_t *d_l, con
                     // bumps of the counting pass (all rows) against probes of the tile kernel (all rows), with a margin
                     inverted = force || (double)sum_sq * 8.0 < (double)n_sk * (double)n_post;
                     if (getenv("FB2_TRACE_DIST"))
-                        fprintf(stderr, "dist: %u postings, sum of squared runs %.3e vs %.3e probes: %s (index %.1f ms)\n", np,
-                                (double)sum_sq, (double)n_sk * (double)n_post, inverted ? "inverted index" : "tile kernel", ms);
+                        fprintf(stderr, "dist: %u postings, sum of squared runs %.3e vs %.3e probes: %s (index kernels %.1f ms, with its buffers %.1f ms)\n", np,
+                                (double)sum_sq, (double)n_sk * (double)n_post, inverted ? "inverted index" : "tile kernel", ms,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_ix0);
                 }
                 // what the counting kernel does not read
                 p_keys.release(); p_vals.release(); p_tkeys.release(); p_tvals.release(); p_hist.release();
@@ -2765,7 +2767,8 @@ extern "C" int fb2_dist_all_pairs_cut(const uint64_t *hashes, const uint32_t *le
     }
     {
         DeviceScope restore(-1);
-        for (size_t g = 0; g < G; ++g) { cudaSetDevice(devs[g]); d_h[g].release(); d_l[g].release(); }
+        for (size_t g = 0; g < G; ++g)   // (only devices that hold something: selecting an untouched GPU creates its context, ~1 s)
+            if (d_h[g].p || d_l[g].p) { cudaSetDevice(devs[g]); d_h[g].release(); d_l[g].release(); }
     }
     for (size_t g = 0; g < G; ++g) if (rcs[g] != FB2_OK) return fb2_fail(rcs[g], msgs[g]);
     uint64_t total = 0;

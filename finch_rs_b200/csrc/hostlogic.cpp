@@ -412,6 +412,28 @@ static bool mapped_fastq_ok() {
     if (const char *e = getenv("FB2_HOST_STRIP")) if (*e == '0') return false;
     return std::thread::hardware_concurrency() >= 8;
 }
+// Is (nearly) all of the file in the page cache?  Only then is framing from the mapping a win: a cold file is read
+// from its device either way, and the parallel pread path asks for it in large sequential requests instead of page
+// faults.  (A sample of the pages, through a short-lived mapping.)
+static bool file_is_cached(int fd) {
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size <= 0) return false;
+    const size_t len = (size_t)sb.st_size;
+    void *map = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (map == MAP_FAILED) return false;
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE), n_pages = (len + page - 1) / page;
+    size_t seen = 0, resident = 0;
+    unsigned char vec[64];
+    const size_t stride = std::max<size_t>(64, n_pages / 256 / 64 * 64);      // ~256 windows of 64 pages
+    for (size_t p0 = 0; p0 < n_pages; p0 += stride) {
+        const size_t k = std::min<size_t>(64, n_pages - p0);
+        if (mincore((char *)map + p0 * page, k * page, vec) != 0) { seen = 1; resident = 0; break; }
+        for (size_t i = 0; i < k; ++i) resident += vec[i] & 1u;
+        seen += k;
+    }
+    munmap(map, len);
+    return seen > 0 && resident * 100 >= seen * 97;
+}
 static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_t *buf, size_t piece,
                            const fb2_params *p, const fb2_filter *f, fb2_result *out) {
     const bool is_stdin = strcmp(path, "-") == 0;  // lib.rs:38-40
@@ -462,7 +484,8 @@ static int sketch_one_file(fb2_sketcher *s, bool reuse, const char *path, uint8_
             if (fill == piece) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, fill, 0); fill = 0; }
         }
         if (rc == FB2_OK && fill) { any = true; rc = fb2_sketcher_feed_fastx(s, buf, fill, 0); }
-    } else if (rc == FB2_OK && !is_stdin && big_regular_file(fp) && nmagic == 2 && magic[0] == '@' && mapped_fastq_ok()) {
+    } else if (rc == FB2_OK && !is_stdin && big_regular_file(fp) && nmagic == 2 && magic[0] == '@' && mapped_fastq_ok() &&
+               file_is_cached(fileno(fp))) {
         // A large plain FASTQ file: the host cores frame its records straight out of the page cache (the file is
         // mapped, nothing is copied first) and only the sequence lines go to the pinned staging and over PCIe -- the
         // in-memory host-framed mode (strip.cpp, engine.cu feed_fastq_stripped), which reports malformed records itself.
