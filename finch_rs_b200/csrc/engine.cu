@@ -2315,7 +2315,11 @@ static cudaError_t upload_large(void *dst, const void *src, size_t bytes) {
     for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
     work(0);
     for (auto &x : th) x.join();
-    return (cudaError_t)err.load();
+    if (err.load() != (int)cudaSuccess) {   // (e.g. no pinned memory to be had): the plain copy decides
+        cudaGetLastError();
+        return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    }
+    return cudaSuccess;
 }
 extern "C" double fb2_dist_last_kernel_ms(void) { return g_dist_kernel_ms; }
 
