@@ -106,17 +106,20 @@ def main():
             [t.start() for t in ths]
             [t.join() for t in ths]
             total_bases = sum(W.c3_nbases(i) for i in range(nfiles))
-            for workers in ((8,) if args.quick else tuple(int(x) for x in args.c3_workers.split(","))):
-                os.environ["FB2_FILE_WORKERS"] = str(workers)
+            for workers in ((8,) if args.quick else tuple(int(x) for x in args.c3_workers.split(",")) + (0,)):
+                if workers:
+                    os.environ["FB2_FILE_WORKERS"] = str(workers)
+                else:                                    # the library's own choice (by host cores and GPUs)
+                    os.environ.pop("FB2_FILE_WORKERS", None)
                 # warm-up: every worker's handle exists (a worker creates its handle before it takes a file, so the call needs
                 # at least `workers` files per GPU), page cache.  Creating handles is the expensive part of a FIRST call:
                 # tools/c3_trace.py, tools/alloc_cost.cu
-                fb.sketch_files(paths[:min(nfiles, 4 * workers * G)], sp_cli, fp_auto, ngpus=G)
+                fb.sketch_files(paths[:min(nfiles, 4 * (workers or 16) * G)], sp_cli, fp_auto, ngpus=G)
                 t0 = time.perf_counter()
                 sks = fb.sketch_files(paths, sp_cli, fp_auto, ngpus=G)
                 dt = time.perf_counter() - t0
                 ok = all(matches(digest_of(sks[i], 21), digests.get(f"c3/file={i}")) for i in range(nfiles))
-                emit({"config": f"C3 fb2_sketch_files_multi({nfiles} x ~5 Mbp FASTA on tmpfs), {workers} worker handles per GPU",
+                emit({"config": f"C3 fb2_sketch_files_multi({nfiles} x ~5 Mbp FASTA on tmpfs), {workers or 'default'} worker handles per GPU",
                       "s": dt, "ms_per_file": dt * 1e3 / nfiles, "gbases_per_s_e2e": total_bases / dt / 1e9,
                       "bit_exact": bool(ok), "bit_exact_on": f"every one of the {nfiles} files vs its oracle digest"})
             os.environ.pop("FB2_FILE_WORKERS", None)

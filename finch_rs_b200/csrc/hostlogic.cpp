@@ -680,11 +680,13 @@ static int sketch_files_on(const char *const *paths, size_t n, const fb2_params 
     if (!n) return FB2_OK;
     const size_t G = devices.size();
     // Worker threads per GPU.  A worker's time per file is half file reading (page cache -> pinned buffer, ~5 GB/s per
-    // thread) and half waiting on its GPU in spinning synchronisations, so more threads than half the host's cores
-    // only fight each other (measured on a 16-core box: 8 threads 0.27 ms / file, 16 threads 0.39, 32 threads 1.5).
-    // (8 GPUs on 32 cores: 4 per GPU 0.14 ms / file, 8 per GPU 0.23.)  Half the cores, but up to 4 per GPU while cores last.
+    // thread) and half waiting on its GPU, so about one thread per core over all GPUs is where the throughput peaks once
+    // the handles exist (1024 files, handles warm: 16 cores / 1 GPU: 8 workers 0.28 ms per file, 16 workers 0.23-0.24;
+    // 24 cores / 2 GPUs: 8 per GPU 0.17, 16 per GPU 0.21; 32 cores / 8 GPUs: 4 per GPU 0.13, 8 per GPU 0.24).  Smaller
+    // hosts keep half their cores (creating a handle pins memory, which the driver serialises: tools/alloc_cost.cu).
     const size_t cores = std::max(1u, std::thread::hardware_concurrency());
     size_t workers = std::min<size_t>(8, std::max<size_t>(std::max<size_t>(1, cores / (2 * G)), std::min<size_t>(4, std::max<size_t>(1, cores / G))));
+    if (cores >= 16) workers = std::min<size_t>(16, std::max<size_t>(workers, cores / G));
     if (const char *e = getenv("FB2_FILE_WORKERS")) { const long v = atol(e); if (v >= 1 && v <= 64) workers = (size_t)v; }
     bool has_stdin = false;
     for (size_t i = 0; i < n; ++i) if (strcmp(paths[i], "-") == 0) has_stdin = true;   // stdin is consumed in order
