@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 os.environ.setdefault("FB2_CHUNK_MB", "1")        # several chunks, seams, the asynchronous path
 import numpy as np
 
@@ -113,4 +114,18 @@ if part(4):   # dist: pair list, tiled all pairs, the cut, minmer_matrix
     m = fb.minmer_matrix(sks[0], [(s, np.ones(len(s), np.uint32)) for s in sks[1:6]])
     assert np.array_equal(m, oracle.minmer_matrix(sks[0], [(s, np.ones(len(s), np.uint32)) for s in sks[1:6]]))
     print("ok: dist", len(hits), "hits", flush=True)
+if part(5):   # the cut through the inverted index (postings, tile radix sort, counting kernel) against the tile kernel
+    import synth
+    n = 300
+    mat = synth.synth_sketches(n, 1000, 6, 5)
+    lens = np.full(n, 1000, np.uint32); lens[11] = 3; lens[200] = 999
+    os.environ["FB2_DIST_INVERTED"] = "0"
+    want = fb.dist_all_pairs_cut(mat, lens, 21, 0.3)
+    os.environ["FB2_DIST_INVERTED"] = "1"
+    for cb in ("", "64"):
+        if cb: os.environ["FB2_DIST_CB"] = cb
+        got = fb.dist_all_pairs_cut(mat, lens, 21, 0.3)
+        assert np.array_equal(got, want) and len(want) > 0
+    os.environ.pop("FB2_DIST_CB"); os.environ.pop("FB2_DIST_INVERTED")
+    print("ok: dist through the inverted index", len(want), "hits", flush=True)
 print("all parts done", flush=True)
