@@ -362,3 +362,31 @@ def test_open_files_written_by_the_command_line(tmp_path):
             assert [c for _, _, c, _ in got.hashes] == [c for _, _, c, _ in want.hashes]
         assert got.compare(want) == (1.0, 1.0) and want.compare(got) == (1.0, 1.0)
         assert got.sketch_params["sketch_type"] == "mash" and got.sketch_params["kmer_length"] == 21
+
+
+def test_open_minimal_json_and_empty_collections(tmp_path):
+    """`.sk` files may hold hashes only (json.rs:91-139: counts default to 1, extra_count = count / 2, no k-mers); empty
+    collections and empty sketches survive a save / open round trip."""
+    import json
+    base = {"kmer": 21, "alphabet": "ACGT", "preserveCase": False, "canonical": True, "sketchSize": 3,
+            "hashType": "MurmurHash3_x64_128", "hashBits": 64, "hashSeed": 0,
+            "sketches": [{"name": "x", "seqLength": 5, "numValidKmers": 4, "comment": "c", "hashes": ["1", "5", "18446744073709551615"]}]}
+    p = tmp_path / "a.sk"
+    p.write_text(json.dumps(base))
+    s = finch.Multisketch.open(str(p))[0]
+    assert s.hashes == [(1, b"", 1, 0), (5, b"", 1, 0), (2**64 - 1, b"", 1, 0)]
+    assert (s.name, s.seq_length, s.num_valid_kmers, s.comment) == ("x", 5, 4, "c")
+    assert s.sketch_params == {"sketch_type": "mash", "kmers_to_sketch": 3, "final_size": 3, "no_strict": True, "kmer_length": 21, "hash_seed": 0}
+    base["sketches"][0]["kmers"] = ["AAA", "CCC", "GGG"]
+    base["sketches"][0]["counts"] = [3, 4, 5]
+    p.write_text(json.dumps(base))
+    assert finch.Multisketch.open(str(p))[0].hashes == [(1, b"AAA", 3, 1), (5, b"CCC", 4, 2), (2**64 - 1, b"GGG", 5, 2)]
+    base["sketches"] = []
+    p.write_text(json.dumps(base))
+    assert len(finch.Multisketch.open(str(p))) == 0
+    e = tmp_path / "e.bsk"
+    finch.Multisketch.from_sketches([]).save(str(e))
+    assert len(finch.Multisketch.open(str(e))) == 0
+    finch.Multisketch.from_sketches([finch.Sketch("empty")]).save(str(e))
+    back = finch.Multisketch.open(str(e))
+    assert len(back) == 1 and back["empty"].hashes == [] and back[0].sketch_params == finch.Sketch("q").sketch_params
