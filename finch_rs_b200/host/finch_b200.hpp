@@ -4,6 +4,7 @@
 //   SketchScheme::{process,total_bases_and_kmers,to_vec}  (mod.rs:24-51)
 //   MashSketcher::push / ScaledSketcher::push             (mash.rs:34, scaled.rs:37)
 //   sketch_stream                                          (lib/src/lib.rs:51-94)
+//   open_sketch_file / write_finch_file / write_mash_file  (lib/src/lib.rs:96-117, serialization/)
 // Compiled and run by tests/hpp_mirror_test.cpp (tests/test_abi_cpu.py builds it, tests/test_gpu_parity.py runs it).
 #pragma once
 #include <cstdint>
@@ -89,5 +90,58 @@ inline std::unique_ptr<SketchScheme> MashSketcher(size_t size, uint8_t k, uint64
 inline std::unique_ptr<SketchScheme> ScaledSketcher(size_t size, double scale, uint8_t k, uint64_t seed) {
     return SketchParams::create_sketcher(SketchParams::Scaled(size, k, scale, seed));
 }
+
+// ---- sketch files: Sketch (serialization/mod.rs:45-55), open_sketch_file (lib.rs:96-117), write_finch_file
+// (serialization/mod.rs:123-176), write_mash_file (mash.rs:12-71), the `.sk` JSON (json.rs:64-89).  Host only. ----
+struct Sketch {
+    std::string name, comment;
+    uint64_t seq_length = 0, num_valid_kmers = 0;
+    std::vector<KmerCount> hashes;
+    fb2_params sketch_params{};
+    fb2_filter filter_params{};
+};
+inline std::vector<Sketch> open_sketch_file(const std::string &path) {
+    fb2_sketch_set *set = nullptr;
+    check(fb2_sketch_set_open(path.c_str(), &set));
+    std::unique_ptr<fb2_sketch_set, void (*)(fb2_sketch_set *)> guard(set, fb2_sketch_set_close);
+    std::vector<Sketch> out(fb2_sketch_set_len(set));
+    for (size_t i = 0; i < out.size(); ++i) {
+        fb2_sketch_view v;
+        check(fb2_sketch_set_get(set, i, &v));
+        Sketch &s = out[i];
+        s.name = v.name; s.comment = v.comment; s.seq_length = v.seq_length; s.num_valid_kmers = v.num_valid_kmers;
+        s.sketch_params = v.params; s.filter_params = v.filter;
+        s.hashes.resize(v.n);
+        for (uint64_t q = 0; q < v.n; ++q) {
+            s.hashes[q].hash = v.hashes[q]; s.hashes[q].count = v.counts[q]; s.hashes[q].extra_count = v.extras[q];
+            s.hashes[q].kmer.assign(v.kmers + v.kmer_offs[q], v.kmers + v.kmer_offs[q + 1]);
+        }
+    }
+    return out;
+}
+inline void write_sketch_file(const std::string &path, const std::vector<Sketch> &sketches, int file_format) {
+    fb2_sketch_set *set = nullptr;
+    check(fb2_sketch_set_new(&set));
+    std::unique_ptr<fb2_sketch_set, void (*)(fb2_sketch_set *)> guard(set, fb2_sketch_set_close);
+    for (const Sketch &s : sketches) {
+        std::vector<uint64_t> h(s.hashes.size()), offs(s.hashes.size() + 1, 0);
+        std::vector<uint32_t> c(s.hashes.size()), x(s.hashes.size());
+        std::vector<uint8_t> bytes;
+        for (size_t q = 0; q < s.hashes.size(); ++q) {
+            h[q] = s.hashes[q].hash; c[q] = s.hashes[q].count; x[q] = s.hashes[q].extra_count;
+            offs[q] = bytes.size();
+            bytes.insert(bytes.end(), s.hashes[q].kmer.begin(), s.hashes[q].kmer.end());
+        }
+        offs[s.hashes.size()] = bytes.size();
+        fb2_sketch_view v{};
+        v.name = s.name.c_str(); v.comment = s.comment.c_str(); v.seq_length = s.seq_length; v.num_valid_kmers = s.num_valid_kmers;
+        v.params = s.sketch_params; v.filter = s.filter_params; v.n = h.size();
+        v.hashes = h.data(); v.counts = c.data(); v.extras = x.data(); v.kmers = bytes.data(); v.kmer_offs = offs.data();
+        check(fb2_sketch_set_add(set, &v));
+    }
+    check(fb2_sketch_set_save(set, path.c_str(), file_format));
+}
+inline void write_finch_file(const std::string &path, const std::vector<Sketch> &s) { write_sketch_file(path, s, FB2_FILE_BSK); }
+inline void write_mash_file(const std::string &path, const std::vector<Sketch> &s) { write_sketch_file(path, s, FB2_FILE_MSH); }
 
 }  // namespace finch

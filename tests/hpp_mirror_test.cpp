@@ -13,6 +13,45 @@ static std::string str(const std::vector<uint8_t> &v) { return std::string(v.beg
 
 int main(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "--link-only")) { printf("%s\n", fb2_version()); return 0; }
+    if (argc > 2 && !strcmp(argv[1], "--files")) {   // host only: sketch files through the mirror (no device needed)
+        try {
+            const std::string dir = argv[2];
+            std::vector<finch::Sketch> sk(2);
+            sk[0].name = "a.fa"; sk[0].comment = "first"; sk[0].seq_length = 100; sk[0].num_valid_kmers = 80;
+            sk[0].sketch_params = finch::SketchParams::Mash(3, 3, false, 4, 0);
+            sk[0].filter_params.filter_on = 0;
+            const char *kmers[3] = {"ACGT", "CCCC", "TTGA"};
+            for (int i = 0; i < 3; ++i) {
+                finch::KmerCount k;
+                k.hash = 10u + 7u * (uint64_t)i; k.count = 1 + i; k.extra_count = i; k.kmer.assign(kmers[i], kmers[i] + 4);
+                sk[0].hashes.push_back(k);
+            }
+            sk[1] = sk[0]; sk[1].name = "b.fa"; sk[1].comment = ""; sk[1].hashes.pop_back();
+            for (int fmt : {FB2_FILE_SK, FB2_FILE_BSK, FB2_FILE_MSH}) {
+                const std::string path = dir + (fmt == FB2_FILE_SK ? "/m.sk" : fmt == FB2_FILE_BSK ? "/m.bsk" : "/m.msh");
+                finch::write_sketch_file(path, sk, fmt);
+                const auto back = finch::open_sketch_file(path);
+                REQUIRE(back.size() == 2 && back[0].name == "a.fa" && back[1].name == "b.fa");
+                REQUIRE(back[0].hashes.size() == 3 && back[1].hashes.size() == 2);
+                REQUIRE(back[0].seq_length == 100 && back[0].sketch_params.kmer_length == 4);
+                for (int i = 0; i < 3; ++i) REQUIRE(back[0].hashes[i].hash == sk[0].hashes[i].hash);
+                if (fmt == FB2_FILE_BSK) {
+                    REQUIRE(back[0].comment == "first" && back[0].num_valid_kmers == 80);
+                    for (int i = 0; i < 3; ++i)
+                        REQUIRE(str(back[0].hashes[i].kmer) == kmers[i] && back[0].hashes[i].count == (uint32_t)(1 + i) &&
+                                back[0].hashes[i].extra_count == (uint32_t)i);
+                }
+            }
+            bool threw = false;
+            try { finch::open_sketch_file(dir + "/m.txt"); } catch (const finch::FinchError &e) { threw = std::string(e.what()).find("suffix") != std::string::npos || e.code == FB2_EIO; }
+            REQUIRE(threw);
+        } catch (const finch::FinchError &e) {
+            fprintf(stderr, "FinchError %d: %s\n", e.code, e.what());
+            return 1;
+        }
+        printf("files ok\n");
+        return 0;
+    }
     try {
         for (int which = 0; which < 2; ++which) {
             auto q = which == 0 ? finch::MashSketcher(3, 2, 42) : finch::ScaledSketcher(3, 1.0, 2, 42);

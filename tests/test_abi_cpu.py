@@ -3,6 +3,7 @@ include/finch_b200.h, the host-only logic (filters, distance epilogue, generator
 oracle, and compute entry points fail loudly without a GPU (no CPU fallback)."""
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -146,6 +147,19 @@ def test_cpp_mirror_header_compiles_and_links(fb):
     exe = build_hpp_mirror_test()
     out = subprocess.run([exe, "--link-only"], capture_output=True, text=True)
     assert out.returncode == 0 and "sm_100a" in out.stdout, out.stderr
+
+
+def test_cpp_mirror_sketch_files(fb, tmp_path):
+    """open_sketch_file / write_sketch_file of the C++ mirror: three formats written and read back (host only)."""
+    import subprocess
+    exe = build_hpp_mirror_test()
+    out = subprocess.run([exe, "--files", str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0 and "files ok" in out.stdout, out.stderr
+    # and the Python module reads what the C++ mirror wrote
+    sys.path.insert(0, os.path.join(ROOT, "python"))
+    import finch
+    ms = finch.Multisketch.open(str(tmp_path / "m.bsk"))
+    assert [s.name for s in ms] == ["a.fa", "b.fa"] and ms["a.fa"].hashes == [(10, b"ACGT", 1, 0), (17, b"CCCC", 2, 1), (24, b"TTGA", 3, 2)]
 
 
 def test_parameters_reports_what_the_reference_sketchers_report():
