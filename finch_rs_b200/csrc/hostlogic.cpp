@@ -232,10 +232,21 @@ static size_t env_size_h(const char *name, size_t dflt) {
     const long long v = atoll(e);
     return v > 0 ? (size_t)v : dflt;
 }
+// gzip / bzip2 / xz bytes in memory -> plain bytes (the decoders of the file path below)
+static int decompress_all(const uint8_t *bytes, size_t len, const char *name, std::vector<uint8_t> &plain);
 extern "C" int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
                                  const fb2_filter *f, fb2_result *out) {
     if (!p || !f || !out || (!bytes && len)) return fb2_fail(FB2_EINVAL, "null argument");
     memset(out, 0, sizeof(*out));
+    // sketch_stream takes any reader and needletail sniffs compressed input (lib.rs:58-60): so does this call
+    if (len >= 2 && ((bytes[0] == 0x1f && bytes[1] == 0x8b) || (bytes[0] == 'B' && bytes[1] == 'Z') || (bytes[0] == 0xFD && bytes[1] == '7'))) {
+        std::vector<uint8_t> plain;
+        const int rcd = decompress_all(bytes, len, name, plain);
+        if (rcd != FB2_OK) return rcd;
+        if (plain.size() >= 2 && ((plain[0] == 0x1f && plain[1] == 0x8b) || (plain[0] == 'B' && plain[1] == 'Z') || (plain[0] == 0xFD && plain[1] == '7')))
+            return fb2_fail(FB2_EFORMAT, std::string(name ? name : "") + ": compressed data inside compressed data");
+        return fb2_sketch_stream(plain.data(), plain.size(), name, p, f, out);
+    }
     {   // A large FASTQ stream from both ends, host-framed and raw at once (sketch_stream_two_ended): the default on a host
         // with >= 8 cores (FB2_HOST_STRIP unset), forced by FB2_HOST_STRIP=2; 0 / 1 pick the single-mode paths
         const char *e = getenv("FB2_HOST_STRIP");
@@ -398,6 +409,40 @@ static std::unique_ptr<StreamDecoder> make_xz_decoder(std::string &why) {
 static std::atomic<uint64_t> g_ns_reset{0}, g_ns_read{0}, g_ns_feed{0}, g_ns_finish{0}, g_n_files{0}, g_ns_create{0}, g_n_created{0};
 static inline uint64_t now_ns() {
     return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static int decompress_all(const uint8_t *bytes, size_t len, const char *name, std::vector<uint8_t> &plain) {
+    std::string why;
+    std::unique_ptr<StreamDecoder> dec;
+    if (bytes[0] == 0x1f) dec = make_gzip_decoder(why);
+    else if (bytes[0] == 'B') dec = make_bz2_decoder(why);
+    else dec = make_xz_decoder(why);
+    const std::string who = name ? name : "";
+    if (!dec) return fb2_fail(FB2_EUNSUPPORTED, who + ": " + why);
+    const uint8_t *in = bytes;
+    size_t avail_in = len;
+    bool member_done = false;
+    plain.clear();
+    plain.resize(std::max<size_t>(1u << 20, len * 4));
+    size_t fill = 0;
+    while (true) {
+        if (avail_in == 0) {
+            if (!member_done) return fb2_fail(FB2_EIO, who + ": truncated " + dec->name() + " stream");
+            break;
+        }
+        if (member_done) {                      // more bytes after the end of a stream
+            if (!dec->next_member()) break;     // bz2 / xz: one stream, the rest is ignored; gzip: another member follows
+            member_done = false;
+        }
+        if (fill == plain.size()) plain.resize(plain.size() * 2);
+        uint8_t *o = plain.data() + fill;
+        size_t avail_out = std::min<size_t>(plain.size() - fill, 1u << 30);
+        const int st = dec->step(in, avail_in, o, avail_out);
+        fill = (size_t)(o - plain.data());
+        if (st == 1) member_done = true;
+        else if (st < 0) return fb2_fail(FB2_EIO, who + ": corrupt " + dec->name() + " stream");
+    }
+    plain.resize(fill);
+    return FB2_OK;
 }
 static bool big_regular_file(FILE *fp) {
     struct stat sb;

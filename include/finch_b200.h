@@ -161,6 +161,8 @@ int fb2_process_post_filter(fb2_result *r, const fb2_params *p, const char *name
 uint32_t fb2_guess_filter_threshold(const uint32_t *counts, size_t n, double filter_level);
 
 /* ---- sketch_stream (lib.rs:51-94) over a host buffer -------------------------------------- */
+/* gzip / bzip2 / xz bytes are decompressed on the host first, as the reader sketch_stream goes through does
+ * (needletail sniffs the first bytes); the handle-level feed calls above take plain FASTA / FASTQ bytes only. */
 int fb2_sketch_stream(const uint8_t *bytes, size_t len, const char *name, const fb2_params *p,
                       const fb2_filter *f, fb2_result *out);
 /* ---- sketch_files (lib.rs:29-49): outs[i] <- paths[i], input order; "-" is stdin ---------- */

@@ -162,6 +162,21 @@ def test_cpp_mirror_sketch_files(fb, tmp_path):
     assert [s.name for s in ms] == ["a.fa", "b.fa"] and ms["a.fa"].hashes == [(10, b"ACGT", 1, 0), (17, b"CCCC", 2, 1), (24, b"TTGA", 3, 2)]
 
 
+def test_sketch_stream_rejects_broken_compressed_bytes_before_any_device_work(fb):
+    """fb2_sketch_stream inflates gzip / bzip2 / xz bytes on the host first: a truncated or corrupt stream is an I/O error
+    whether or not there is a device."""
+    import gzip
+    data = gzip.compress(b"@r\nACGT\n+\nIIII\n" * 500)
+    sp, fp = fb.SketchParams.mash(10, 10, True, 3, 0), fb.FilterParams(False, (None, None), 0.0, 0.0)
+    with pytest.raises(fb.FinchError) as ei:
+        fb.sketch_stream(data[:-20], "cut.fq.gz", sp, fp)
+    assert ei.value.code == fb.EIO and "truncated gzip stream" in str(ei.value)
+    bad = bytearray(data); bad[40] ^= 0xFF; bad[41] ^= 0xFF
+    with pytest.raises(fb.FinchError) as ei:
+        fb.sketch_stream(bytes(bad), "bad.fq.gz", sp, fp)
+    assert ei.value.code == fb.EIO
+
+
 def test_parameters_reports_what_the_reference_sketchers_report():
     """Quirks Q7 / Q8 (mash.rs:104-112, scaled.rs:102-109) in the mirror's parameters(), without a device."""
     import finch_rs_b200 as m

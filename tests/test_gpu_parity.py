@@ -384,6 +384,29 @@ def test_large_fastq_file_framed_from_the_mapping(fb, oracle, tmp_path, monkeypa
             assert [sk.kmers[i, :21].tobytes() for i in range(len(sk))] == osk["kmers"]
 
 
+def test_sketch_stream_takes_compressed_bytes(fb, oracle):
+    """sketch_stream reads through needletail, which sniffs gzip / bzip2 / xz (lib.rs:58-60): so does fb2_sketch_stream
+    for bytes in memory (two gzip members; one bzip2 / xz stream); the handle-level feed calls still refuse them."""
+    import bz2, gzip, lzma
+    rng = np.random.default_rng(92)
+    fq = gen.fastq(rng, n_records=700, max_len=250)
+    sp = fb.SketchParams.mash(3000, 200, True, 21, 0)
+    fp = fb.FilterParams(False, (None, None), 0.21, 0.1)
+    rc, osk = oracle.sketch_stream(fq, oracle.mash_params(3000, 200, True, 21, 0), oracle.make_filter(False, (None, None), 0.21, 0.1))
+    assert rc == oracle.OK
+    half = len(fq) // 2
+    for packed in (gzip.compress(fq[:half]) + gzip.compress(fq[half:]), bz2.compress(fq), lzma.compress(fq)):
+        sk = fb.sketch_stream(packed, "reads.fq.z", sp, fp)
+        assert np.array_equal(sk.hashes_u64, osk["hashes"]) and np.array_equal(sk.counts, osk["counts"])
+        assert (sk.seq_length, sk.num_valid_kmers) == (osk["seq_length"], osk["num_valid_kmers"])
+    with pytest.raises(fb.FinchError) as ei:
+        fb.sketch_stream(gzip.compress(fq)[:-300], "cut.fq.gz", sp, fp)
+    assert ei.value.code == fb.EIO and "truncated gzip" in str(ei.value)
+    with sp.create_sketcher() as s, pytest.raises(fb.FinchError) as ei:
+        s.feed_fastx(gzip.compress(fq), final=True)
+    assert ei.value.code == fb.EUNSUPPORTED
+
+
 def test_sketch_files_bz2_xz(fb, oracle, tmp_path):
     """bzip2 ("BZ") and xz (fd 37) input, decompressed on the host through the system's libbz2 / liblzma (loaded at
     first use); one stream each, as needletail's BzDecoder / XzDecoder read them; truncated streams are errors."""
